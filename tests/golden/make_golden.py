@@ -1,0 +1,229 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+Outputs (small, committed): tests/golden/{configs.json, ops.npz, sde.npz, ncsnpp_*.npz, shapes_*.json, pc_*.npz}
+
+Everything the oracle (`oracle/`) claims is pinned by these files: they hold seeded inputs and the outputs the
+reference's own code produced for them.  Weights are not stored: they are regenerated bit-identically from
+`oracle.ncsnpp.synth_params(config, seed)` (numpy PCG64) and loaded into the reference model's state-dict.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader as rl  # noqa: E402
+from oracle import ncsnpp as oncsnpp  # noqa: E402
+
+
+def tiny(cfg, nf=64):
+    """Shrink a reference config to a fast test size (same code paths)."""
+    cfg.model.nf = nf
+    cfg.model.ch_mult = (1, 2)
+    cfg.model.num_res_blocks = 1
+    cfg.model.attn_resolutions = (8,)
+    cfg.data.image_size = 16
+    return cfg
+
+
+def plain(cfg):
+    out = {}
+    for k, v in cfg.items():
+        if hasattr(v, 'items'):
+            out[k] = plain(v)
+        elif isinstance(v, torch.device):
+            out[k] = str(v)
+        elif isinstance(v, tuple):
+            out[k] = list(v)
+        else:
+            out[k] = v
+    return out
+
+
+def make_configs():
+    names = ['ve/CIFAR10/indm', 've/CELEBA/indm', 'vp/CIFAR10/indm_fid', 'vp/CIFAR10/indm_nll',
+             'vp/CELEBA/indm_fid', 'vp/CELEBA/indm_nll']
+    out = {}
+    for n in names:
+        c = plain(rl.get_config(f'configs/{n}.py'))
+        c.pop('device')
+        out[n] = c
+    with open(os.path.join(HERE, 'configs.json'), 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+def make_ops():
+    op = rl.load('op')
+    rng = np.random.default_rng(1)
+    out = {}
+    k4 = np.outer([1, 3, 3, 1], [1, 3, 3, 1]).astype(np.float32)
+    k4 /= k4.sum()
+    cases = {
+        'up2':   dict(shape=(2, 5, 8, 8), k=k4 * 4, up=2, down=1, pad=(2, 1)),      # upsample_2d
+        'down2': dict(shape=(2, 5, 8, 8), k=k4, up=1, down=2, pad=(1, 1)),          # downsample_2d
+        'pyr':   dict(shape=(2, 3, 8, 8), k=k4, up=1, down=1, pad=(2, 2)),          # conv_downsample_2d FIR stage
+        'k3':    dict(shape=(1, 2, 7, 9), k=rng.standard_normal((3, 3)).astype(np.float32), up=1, down=1, pad=(1, 1)),
+        'crop':  dict(shape=(1, 2, 9, 9), k=rng.standard_normal((2, 2)).astype(np.float32), up=2, down=3, pad=(-1, 2)),
+        'gen':   dict(shape=(2, 3, 6, 5), k=rng.standard_normal((5, 5)).astype(np.float32), up=3, down=2, pad=(3, 1)),
+        'up2_32': dict(shape=(1, 4, 32, 32), k=k4 * 4, up=2, down=1, pad=(2, 1)),
+    }
+    for name, c in cases.items():
+        x = rng.standard_normal(c['shape']).astype(np.float32)
+        y = op.upfirdn2d(torch.from_numpy(x), torch.from_numpy(c['k']), up=c['up'], down=c['down'], pad=c['pad'])
+        out[f'upfirdn_{name}_x'] = x
+        out[f'upfirdn_{name}_k'] = c['k']
+        out[f'upfirdn_{name}_args'] = np.array([c['up'], c['down'], c['pad'][0], c['pad'][1]], dtype=np.int64)
+        out[f'upfirdn_{name}_y'] = y.numpy()
+        # gradient wrt input via autograd through the native path (the reference CUDA op's backward must equal it)
+        xt = torch.from_numpy(x).requires_grad_(True)
+        yy = op.upfirdn2d(xt, torch.from_numpy(c['k']), up=c['up'], down=c['down'], pad=c['pad'])
+        gy = rng.standard_normal(tuple(yy.shape)).astype(np.float32)
+        yy.backward(torch.from_numpy(gy))
+        out[f'upfirdn_{name}_gy'] = gy
+        out[f'upfirdn_{name}_gx'] = xt.grad.numpy()
+    for name, shape in {'4d': (2, 6, 5, 7), '2d': (4, 6), '3d': (2, 6, 9)}.items():
+        x = rng.standard_normal(shape).astype(np.float32)
+        b = rng.standard_normal((shape[1],)).astype(np.float32)
+        y = op.fused_leaky_relu(torch.from_numpy(x), torch.from_numpy(b))   # defaults: slope 0.2, scale sqrt(2)
+        out[f'lrelu_{name}_x'] = x
+        out[f'lrelu_{name}_b'] = b
+        out[f'lrelu_{name}_y'] = y.numpy()
+        xt = torch.from_numpy(x).requires_grad_(True)
+        bt = torch.from_numpy(b).requires_grad_(True)
+        yy = op.fused_leaky_relu(xt, bt)
+        gy = rng.standard_normal(shape).astype(np.float32)
+        yy.backward(torch.from_numpy(gy))
+        out[f'lrelu_{name}_gy'] = gy
+        out[f'lrelu_{name}_gx'] = xt.grad.numpy()
+        out[f'lrelu_{name}_gb'] = bt.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, 'ops.npz'), **out)
+
+
+def make_sde():
+    sde_lib = rl.load('sde_lib')
+    out = {}
+    t = torch.tensor([1e-5, 1e-3, 0.02, 0.25, 0.5, 0.77, 0.999, 1.0])
+    x = torch.from_numpy(np.random.default_rng(2).standard_normal((8, 3, 4, 4)).astype(np.float32))
+    u = torch.from_numpy(np.random.default_rng(3).uniform(size=8).astype(np.float32))
+    out['t'] = t.numpy(); out['x'] = x.numpy(); out['u'] = u.numpy()
+    for tag, sde in (('vp', sde_lib.VPSDE(truncation_time=1e-5, beta_min=0.1, beta_max=20., N=1000)),
+                     ('ve', sde_lib.VESDE(truncation_time=1e-5, sigma_min=0.01, sigma_max=50, N=1000)),
+                     ('ve90', sde_lib.VESDE(truncation_time=1e-5, sigma_min=0.01, sigma_max=90., N=1000))):
+        d, g = sde.sde(x, t)
+        out[f'{tag}_drift'] = d.numpy(); out[f'{tag}_diff'] = g.numpy()
+        mean, std = sde.marginal_prob(x, t)
+        out[f'{tag}_mean'] = mean.numpy(); out[f'{tag}_std'] = std.numpy()
+        f, G = sde.discretize(x, t, None)
+        out[f'{tag}_disc_f'] = f.numpy(); out[f'{tag}_disc_G'] = G.numpy()
+        nt = t * 0.9
+        f, G = sde.discretize(x, t, nt)
+        out[f'{tag}_disc2_f'] = f.numpy(); out[f'{tag}_disc2_G'] = G.numpy()
+        out[f'{tag}_prior_logp'] = sde.prior_logp(x).numpy()
+        Z = sde.normalizing_constant(1e-5)
+        out[f'{tag}_Z'] = np.asarray(float(Z))
+
+        class _C:  # get_diffusion_time reads config.training.importance_sampling only when arg is None
+            pass
+        torch.manual_seed(7)
+        u_ref = torch.rand(8)
+        torch.manual_seed(7)
+        tt, ZZ = sde.get_diffusion_time(None, 8, 'cpu', 1e-5, importance_sampling=True)
+        out[f'{tag}_is_u'] = u_ref.numpy(); out[f'{tag}_is_t'] = tt.numpy()
+    np.savez_compressed(os.path.join(HERE, 'sde.npz'), **out)
+
+
+def ref_model(cfg, seed):
+    mutils, _ = rl.load('models.utils', 'models.ncsnpp')
+    model = mutils.create_model(cfg)        # DataParallel wrapper, CPU
+    ref_sd = model.module.state_dict()
+    shapes = [(k, list(v.shape)) for k, v in ref_sd.items()]
+    sd = oncsnpp.synth_params(cfg, seed)
+    assert [(k, list(v.shape)) for k, v in sd.items()] == shapes, 'oracle.param_shapes != reference state_dict'
+    model.module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model.eval()
+    return model, shapes
+
+
+def make_ncsnpp():
+    mutils, sde_lib = rl.load('models.utils', 'sde_lib')
+    specs = {
+        'tiny_vp': ('configs/vp/CIFAR10/indm_fid.py', True, 3),
+        'tiny_ve': ('configs/ve/CIFAR10/indm.py', True, 3),
+        'vp_cifar': ('configs/vp/CIFAR10/indm_fid.py', False, 2),
+        've_cifar': ('configs/ve/CIFAR10/indm.py', False, 2),
+    }
+    for tag, (path, is_tiny, B) in specs.items():
+        cfg = rl.get_config(path)
+        if is_tiny:
+            tiny(cfg)
+        model, shapes = ref_model(cfg, seed=11)
+        with open(os.path.join(HERE, f'shapes_{tag}.json'), 'w') as f:
+            json.dump(shapes, f)
+        S = cfg.data.image_size
+        rng = np.random.default_rng(5)
+        x = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+        t = np.array([0.9, 0.31, 0.02][:B], dtype=np.float32)
+        sde = sde_lib.get_sde(cfg)
+        if cfg.training.sde == 'vesde':
+            x = x * np.asarray(sde.marginal_prob(torch.zeros(B), torch.from_numpy(t))[1].numpy()).reshape(B, 1, 1, 1).astype(np.float32)
+        score_fn = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
+        with torch.no_grad():
+            s = score_fn(torch.from_numpy(x), torch.from_numpy(t))
+            if cfg.training.sde == 'vpsde':
+                raw = model(torch.from_numpy(x), torch.from_numpy(t) * 999)
+            else:
+                raw = model(torch.from_numpy(x), sde.marginal_prob(torch.zeros(B), torch.from_numpy(t))[1])
+        np.savez_compressed(os.path.join(HERE, f'ncsnpp_{tag}.npz'), x=x, t=t, score=s.numpy(), raw=raw.numpy(),
+                            seed=np.asarray(11))
+        print(tag, 'score rms', float(s.pow(2).mean().sqrt()), 'raw rms', float(raw.pow(2).mean().sqrt()))
+
+
+def make_pc():
+    """Short PC trajectories through the reference's own get_pc_sampler, with randn_like / randn replayed."""
+    mutils, sde_lib, sampling = rl.load('models.utils', 'sde_lib', 'sampling')
+    import tempfile
+    for tag, path, corr in (('tiny_vp', 'configs/vp/CIFAR10/indm_fid.py', 'none'),
+                            ('tiny_ve', 'configs/ve/CIFAR10/indm.py', 'langevin')):
+        cfg = rl.get_config(path)
+        tiny(cfg)
+        cfg.sampling.method = 'pc'
+        cfg.sampling.predictor = 'reverse_diffusion'
+        cfg.sampling.corrector = corr
+        cfg.sampling.num_scales = 6
+        cfg.flow.model = 'identity'    # isolate the PC loop; the flow inverse has its own fixtures
+        model, _ = ref_model(cfg, seed=11)
+        sde = sde_lib.get_sde(cfg)
+        B, S = 3, cfg.data.image_size
+        rng = np.random.default_rng(9)
+        n_draws = cfg.sampling.num_scales * (2 if corr == 'langevin' else 1)
+        prior = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+        noises = rng.standard_normal((n_draws, B, 3, S, S)).astype(np.float32)
+        q = [torch.from_numpy(n) for n in noises]
+        real_randn, real_randn_like = torch.randn, torch.randn_like
+        torch.randn = lambda *shape, **kw: torch.from_numpy(prior)
+        torch.randn_like = lambda x, **kw: q.pop(0)
+        try:
+            fn = sampling.get_sampling_fn(cfg, sde, (B, 3, S, S), lambda v: v, cfg.sampling.truncation_time)
+            with tempfile.TemporaryDirectory() as d:
+                before, after, nfe = fn(model, None, sample_dir=d, r=0)
+        finally:
+            torch.randn, torch.randn_like = real_randn, real_randn_like
+        assert not q
+        np.savez_compressed(os.path.join(HERE, f'pc_{tag}.npz'), prior=prior, noises=noises, out=before.numpy(),
+                            nfe=np.asarray(nfe), num_scales=np.asarray(cfg.sampling.num_scales),
+                            eps=np.asarray(cfg.sampling.truncation_time), snr=np.asarray(cfg.sampling.snr))
+        print('pc', tag, 'rms', float(before.pow(2).mean().sqrt()), 'nfe', nfe)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc']
+    for w in which:
+        globals()['make_' + w]()
+        print('made', w)

@@ -1,0 +1,175 @@
+/* indm_b200 — C ABI of the B200-native (sm_100a) INDM hot-path library `libindm_b200.so`.
+ *
+ * Every entry point: plain pointers and sizes, DEVICE pointers unless stated otherwise, `stream` is a cudaStream_t
+ * passed as void*, the call enqueues work on that stream and returns immediately.  Return value 0 = success,
+ * non-zero = error (message via indm_last_error()).  Nothing allocates device memory: the caller owns inputs,
+ * outputs and workspaces.  The library is re-entrant and device-local (the reference's ops are invoked from one
+ * Python thread per GPU under nn.DataParallel; here there is one process per GPU).  There is no CPU path.
+ *
+ * What each entry point stands in for in the reference (byeonghu-na/INDM) is cited as file:line.
+ */
+#ifndef INDM_B200_H_
+#define INDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INDM_DTYPE_BF16 0 /* bf16 operands, fp32 accumulate (production mode)      */
+#define INDM_DTYPE_TF32 1 /* fp32 storage, tf32 tensor-core math (validation mode) */
+#define INDM_DTYPE_F32 2  /* plain fp32 (only where stated)                        */
+
+const char* indm_version(void);
+/* last error message of the calling thread ("" if none) */
+const char* indm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The reference's two native operators (pybind modules `upfirdn2d`, `fused`)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* upfirdn2d(Tensor input[major,in_h,in_w,minor=1], Tensor kernel[kh,kw], up_x, up_y, down_x, down_y,
+ *           pad_x0, pad_x1, pad_y0, pad_y1) -> [major,out_h,out_w]        (op/upfirdn2d.cpp:12-19,
+ * op/upfirdn2d_kernel.cu:209-369).  FP32.  out_h = (in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1 (same for w);
+ * the caller allocates y with that extent.  The backward pass is this same call with up<->down, the flipped
+ * kernel and the g_pad values of op/upfirdn2d.py:111-114. */
+int indm_upfirdn2d_f32(const float* x, const float* k, float* y, int64_t major, int in_h, int in_w, int kh, int kw,
+                       int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                       void* stream);
+
+/* fused_bias_act(input, bias, refer, act, grad, alpha, scale) (op/fused_bias_act.cpp:11-17,
+ * op/fused_bias_act_kernel.cu:19-99).  y[i] = f(x[i] + bias[(i / step_b) % size_b]) * scale with
+ * act: 1 linear, 3 leaky-ReLU(alpha); grad: 0 forward, 1 first derivative (sign taken from `ref`), 2 -> 0.
+ * bias / ref may be NULL (= the reference's empty tensors). */
+int indm_bias_act_f32(const float* x, const float* bias, const float* ref, float* y, int64_t n, int size_b, int64_t step_b,
+                      int act, int grad, float alpha, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core implicit GEMM (tcgen05 + TMEM + TMA).  Stands in for the cuDNN / cuBLAS calls behind
+ * nn.Conv2d 3x3 / 1x1 (models/layers.py:100-124), NIN (models/layers.py:546-555), the attention einsums
+ * (models/layerspp.py:95,99) and the flow's 1x1 conv (flows/resflow/layers/base/lipschitz.py:434).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct indm_igemm {
+  int32_t dtype; /* INDM_DTYPE_BF16 or INDM_DTYPE_TF32: element type of a/b/a2/b2 (bf16 or fp32) */
+  /* A: activations, NHWC: element (n,y,x,c) at a[n*a_img_stride + (y*W + x)*a_ld + c]; 0 strides = dense.
+   * Plain GEMM [M,K]: N=1, H=1, W=M, Cin=K. */
+  const void* a;
+  int64_t a_ld, a_img_stride;
+  int32_t N, H, W, Cin;
+  /* B: weights [taps][Cout][Cin] (Cin contiguous): element (t,o,c) at b[t*b_tap_stride + o*b_ld + c].
+   * taps = 9: 3x3 / stride 1 / zero pad 1 cross-correlation, t = ky*3 + kx;  taps = 1: 1x1.
+   * batched_b = 1 (taps must be 1): one B matrix per image n, at b[n*b_tap_stride + ...] (attention). */
+  const void* b;
+  int64_t b_ld, b_tap_stride;
+  int32_t Cout, taps, batched_b;
+  /* optional second K segment accumulated into the same output: 1x1 conv of a2 (NHWC, Cin2 channels) with b2 [Cout][Cin2]
+   * (fused res-block skip conv, models/layerspp.py:281-282).  a2 = NULL disables it. */
+  const void* a2;
+  int64_t a2_ld;
+  int32_t Cin2;
+  const void* b2;
+  int64_t b2_ld;
+  /* epilogue: v = (acc + bias[c] + rowbias[n*rowbias_ld + c] + residual[pixel*res_ld + c]) * scale * rowscale[n] */
+  const float* bias;     /* [Cout] or NULL */
+  const float* rowbias;  /* per-image bias (time-embedding Dense_0 output, models/layerspp.py:276) or NULL */
+  int64_t rowbias_ld;
+  const float* residual; /* fp32 NHWC or NULL */
+  int64_t res_ld;
+  const float* rowscale; /* [N] or NULL */
+  float scale;
+  int32_t out_mode;      /* 0: NHWC rows out_*[pixel*out_ld + c];  1: NCHW fp32 (out_f32);
+                            2: as 0 for c < tcol0, and c >= tcol0 transposed per image into out_t[n][c - tcol0][y*W + x] (bf16) */
+  float* out_f32;        /* either / both may be given in mode 0 */
+  void* out_bf16;
+  int64_t out_ld;
+  int32_t tcol0;
+  void* out_t;
+  int32_t round_tf32_out; /* round fp32 outputs to tf32 (rna) */
+  /* optional fused GroupNorm statistics of the stored output: gn_partial[n][g][2] += (sum, sum of squares) over
+   * the tile (atomicAdd; caller zeroes it).  gn_cpg = channels per group. */
+  float* gn_partial;
+  int32_t gn_cpg, gn_groups;
+  int32_t block_n;       /* 0 = choose automatically; else 32 / 64 / 128 / 256 */
+} indm_igemm_t;
+
+int indm_igemm(const indm_igemm_t* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bandwidth-bound kernels of the score network (NHWC)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* GroupNorm statistics over the channel-concatenation of xa [N,P,Ca] and xb [N,P,Cb] (xb may be NULL):
+ * partial[n][g][2] += (sum, sumsq), G groups over C = Ca + Cb channels (nn.GroupNorm, models/layerspp.py:232;
+ * the concat is models/ncsnpp.py:350).  in_dtype: INDM_DTYPE_F32 or INDM_DTYPE_BF16. */
+int indm_gn_stats(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int64_t P, int G, float* partial,
+                  void* stream);
+
+/* GroupNorm apply (+ optional SiLU, + optional x2 nearest upsample or 2x2 mean downsample of the result, i.e. the
+ * h-branch of ResnetBlockBigGANpp.forward, models/layerspp.py:256-271 with models/up_or_down_sampling.py:59-69),
+ * reading statistics from partial[n][g][2] (sum, sumsq over count = P * C / G values).
+ * out: [N, P', C] in out_dtype (BF16, or TF32 = fp32 rounded to tf32); raw (optional): the un-normalised input,
+ * same resampling, same dtype — the operand of the fused skip 1x1 conv.  resample: 0 none, 1 up x2, 2 down x2. */
+int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                  const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
+                  void* out, void* raw, int out_dtype, void* stream);
+
+/* Row softmax of fp32 scores s[rows][cols] -> probabilities in out_dtype (models/layerspp.py:96-97). */
+int indm_softmax_rows(const float* s, void* out, int64_t rows, int cols, int out_dtype, void* stream);
+
+/* Network input: x NCHW fp32 [N,C,H,W] -> NHWC with cpad >= C channels (extra channels zero), v = x*mul + add
+ * (the `2x - 1` of models/ncsnpp.py:278-280 when data is not centred), in out_dtype. */
+int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, int cpad, float mul, float add, int out_dtype,
+                    void* stream);
+
+/* Time embedding (models/layers.py:515-529 positional: kind 0, time_cond = 999 t;
+ * models/layerspp.py:45-54 Gaussian Fourier: kind 1, time_cond = sigma, freqs = W[dim/2]).
+ * If sched != NULL the conditioning value is sched[(*step) * sched_ld + sched_col] for every sample (sampler loop
+ * replayed from a CUDA graph); otherwise time_cond[n].  out [N, dim] fp32. */
+int indm_time_embedding(const float* time_cond, const float* sched, const int32_t* step, int sched_ld, int sched_col,
+                        const float* freqs, int kind, int64_t N, int dim, float* out, void* stream);
+
+/* out[n][o] = bias[o] + sum_k f(in[n][k]) * w[o][k], f = SiLU if act_in else identity (nn.Linear in the temb MLP,
+ * models/ncsnpp.py:270-274, and all ResnetBlock Dense_0 layers at once, models/layerspp.py:276). FP32. */
+int indm_linear_f32(const float* in, const float* w, const float* bias, float* out, int64_t N, int K, int O, int act_in,
+                    void* stream);
+
+/* FIR resampling of an NHWC tensor with the separable kernel outer(k1,k1)/sum^2*gain (models/up_or_down_sampling.py:195-257):
+ * mode 1: upsample_2d (up 2, pad (2,1), gain 4); mode 2: downsample_2d (down 2, pad (1,1));
+ * mode 3: the FIR stage of conv_downsample_2d (up = down = 1, pad (2,2)) -> [H+1, W+1].
+ * k1: HOST pointer to the 4 separable taps, already normalised (k/sum(k), times 2 per axis for mode 1). */
+int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N, int H, int W, int C, const float* k1, int mode,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Predictor-corrector update (sampling.py:205-210 ReverseDiffusionPredictor, :272-292 LangevinCorrector with
+ * sde_lib.py:105-118,171-184,310-323), state NCHW fp32 [N, D].
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* x_mean = a*x + c*s ;  x = x_mean + d*z.   (a, c, d) = coef[0..2] of row (*step) of a [steps][coef_ld] device table
+ * (step may be NULL = row 0).  z = NULL -> standard normal noise generated in-kernel (Philox4x32-10, counter =
+ * (seed, *step or rng_offset, element)).  x is updated in place; x_mean (optional) receives the noise-free state. */
+int indm_pc_predictor_update(float* x, const float* s, const float* z, float* x_mean, const float* coef, int coef_ld,
+                             const int32_t* step, int64_t N, int64_t D, uint64_t seed, uint64_t rng_offset, void* stream);
+
+/* per-sample sums of squares: out[n][0] = |s_n|^2, out[n][1] = |z_n|^2 (z NULL -> the Philox noise the following
+ * indm_langevin_update call with the same seed/offset will draw). */
+int indm_langevin_norms(const float* s, const float* z, float* out, const int32_t* step, int64_t N, int64_t D, uint64_t seed,
+                        uint64_t rng_offset, void* stream);
+
+/* step = 2*alpha*(snr * mean_n|z_n| / mean_n|s_n|)^2 ; x_mean = x + step*s ; x = x_mean + sqrt(2 step) z.
+ * (alpha, snr) = coef[0..1] of row (*step). */
+int indm_langevin_update(float* x, const float* s, const float* z, float* x_mean, const float* norms, const float* coef,
+                         int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, uint64_t rng_offset,
+                         void* stream);
+
+/* *step += 1 (device-side step counter advanced inside the captured graph) */
+int indm_advance_step(int32_t* step, void* stream);
+
+/* fill with standard normal noise (same Philox stream as above), fp32 */
+int indm_randn_f32(float* out, int64_t n, uint64_t seed, uint64_t rng_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INDM_B200_H_ */

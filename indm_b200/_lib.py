@@ -1,0 +1,112 @@
+"""ctypes binding of the C-ABI library `libindm_b200.so` (declared in include/indm_b200.h).
+
+There is NO fallback: if the library is missing, or a call returns a non-zero status, a RuntimeError is raised.
+PyTorch is used only as plumbing around it (device memory, streams): every wrapper passes raw device pointers and
+the current CUDA stream handle.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libindm_b200.so")
+
+DTYPE_BF16, DTYPE_TF32, DTYPE_F32 = 0, 1, 2
+
+_lib = None
+launches = 0  # number of kernel-launching C-ABI calls issued through this module (bench.py reports it)
+
+
+class IgemmDesc(C.Structure):
+    """Mirror of `indm_igemm_t` (include/indm_b200.h)."""
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("a", C.c_void_p), ("a_ld", C.c_int64), ("a_img_stride", C.c_int64),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("b", C.c_void_p), ("b_ld", C.c_int64), ("b_tap_stride", C.c_int64),
+        ("Cout", C.c_int32), ("taps", C.c_int32), ("batched_b", C.c_int32),
+        ("a2", C.c_void_p), ("a2_ld", C.c_int64), ("Cin2", C.c_int32),
+        ("b2", C.c_void_p), ("b2_ld", C.c_int64),
+        ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int64),
+        ("residual", C.c_void_p), ("res_ld", C.c_int64),
+        ("rowscale", C.c_void_p), ("scale", C.c_float),
+        ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("out_ld", C.c_int64),
+        ("tcol0", C.c_int32), ("out_t", C.c_void_p), ("round_tf32_out", C.c_int32),
+        ("gn_partial", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_groups", C.c_int32),
+        ("block_n", C.c_int32),
+    ]
+
+
+_i32, _i64, _u64, _f32, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
+_SIGS = {
+    "indm_upfirdn2d_f32": [_vp, _vp, _vp, _i64] + [C.c_int] * 12 + [_vp],
+    "indm_bias_act_f32": [_vp, _vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int, C.c_int, _f32, _f32, _vp],
+    "indm_igemm": [C.POINTER(IgemmDesc), _vp],
+    "indm_gn_stats": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp, _vp],
+    "indm_gn_apply": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32, C.c_int,
+                      C.c_int, _vp, _vp, C.c_int, _vp],
+    "indm_softmax_rows": [_vp, _vp, _i64, C.c_int, C.c_int, _vp],
+    "indm_prep_input": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _f32, C.c_int, _vp],
+    "indm_time_embedding": [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp],
+    "indm_linear_f32": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_fir_nhwc": [_vp, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, _vp],
+    "indm_pc_predictor_update": [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _u64, _vp],
+    "indm_langevin_norms": [_vp, _vp, _vp, _vp, _i64, _i64, _u64, _u64, _vp],
+    "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _u64, _vp],
+    "indm_advance_step": [_vp, _vp],
+    "indm_randn_f32": [_vp, _i64, _u64, _u64, _vp],
+}
+EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C indm_b200/csrc`). indm_b200 has no CPU / PyTorch fallback.")
+        h = C.CDLL(LIB_PATH)
+        h.indm_version.restype = C.c_char_p
+        h.indm_last_error.restype = C.c_char_p
+        for name, args in _SIGS.items():
+            fn = getattr(h, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = h
+    return _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("indm_b200: expected a CUDA tensor (there is no CPU path)")
+    return C.c_void_p(t.data_ptr())
+
+
+def check(rc, what):
+    global launches
+    if rc != 0:
+        raise RuntimeError(f"indm_b200.{what} failed (status {rc}): {lib().indm_last_error().decode()}")
+    launches += 1
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args, _stream()), name)
+
+
+def igemm(**kw):
+    d = IgemmDesc()
+    d.scale = 1.0
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(d, k, v)
+    check(lib().indm_igemm(C.byref(d), _stream()), "igemm")

@@ -1,0 +1,510 @@
+// Bandwidth-bound kernels of the NCSN++ score network on NHWC activations: GroupNorm statistics / apply (+SiLU,
+// +nearest-up / mean-down resampling, +raw copy for the fused skip conv), row softmax, input layout conversion,
+// time embedding, small dense layers.  All are HBM/L2-streaming kernels: 128-bit accesses, one fixed channel quad
+// per thread so per-channel parameters live in registers, grids sized from the SM count.
+#include <type_traits>
+
+#include "../../include/indm_b200.h"
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- typed 4-channel vector access
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    uint2 r;
+    r.x = pack_bf16x2(v.x, v.y);
+    r.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+// fp32 storage holding tf32-rounded values (operands of kind::tf32 MMAs)
+struct Tf32Out {};
+template <>
+struct Vec4<Tf32Out> {
+  static __device__ __forceinline__ void store(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  }
+};
+
+// ---------------------------------------------------------------- GroupNorm statistics
+// grid (splits, N); block = Q * R threads, Q = C/4 channel quads, R pixel rows in flight.
+template <typename TIn>
+__global__ void gn_stats_kernel(const TIn* __restrict__ xa, int Ca, const TIn* __restrict__ xb, int Cb, long long P, int G,
+                                int R, float* __restrict__ partial) {
+  __shared__ float s_sum[32], s_sq[32];
+  const int C = Ca + Cb;
+  const int Q = C >> 2;
+  const int q = threadIdx.x % Q;
+  const int rr = threadIdx.x / Q;
+  const long long n = blockIdx.y;
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  __syncthreads();
+  const long long per = (P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  const long long p1 = min(P, p0 + per);
+  const int c = q * 4;
+  const TIn* src;
+  int ld;
+  if (c < Ca) {
+    src = xa + n * P * Ca + c;
+    ld = Ca;
+  } else {
+    src = xb + n * P * Cb + (c - Ca);
+    ld = Cb;
+  }
+  float s = 0.f, ss = 0.f;
+  if (rr < R) {
+    for (long long p = p0 + rr; p < p1; p += R) {
+      const float4 v = Vec4<TIn>::load(src + p * ld);
+      s += (v.x + v.y) + (v.z + v.w);
+      ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    const int g = c / (C / G);
+    atomicAdd(&s_sum[g], s);
+    atomicAdd(&s_sq[g], ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    atomicAdd(&partial[(n * G + i) * 2 + 0], s_sum[i]);
+    atomicAdd(&partial[(n * G + i) * 2 + 1], s_sq[i]);
+  }
+}
+
+// ---------------------------------------------------------------- GroupNorm apply (+SiLU, +resample, +raw copy)
+// RES: 0 none, 1 nearest up x2, 2 mean down x2.  grid (splits, N), block = Q * R.
+template <typename TIn, typename TOut, int RES>
+__global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* __restrict__ xb, int Cb, int H, int W, int G,
+                                int R, const float* __restrict__ partial, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int act,
+                                typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ out,
+                                typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ raw) {
+  const int C = Ca + Cb;
+  const int Q = C >> 2;
+  const int q = threadIdx.x % Q;
+  const int rr = threadIdx.x / Q;
+  if (rr >= R) return;
+  const long long n = blockIdx.y;
+  const int c = q * 4;
+  const int cpg = C / G;
+  const int g = c / cpg;
+  const long long P = (long long)H * W;
+  const float cnt = (float)((double)P * cpg);
+  const float su = partial[(n * G + g) * 2 + 0];
+  const float sq = partial[(n * G + g) * 2 + 1];
+  const float mean = su / cnt;
+  const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(beta + c);
+  const float4 sc = make_float4(ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd);
+  const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+  const TIn* src;
+  int ld;
+  if (c < Ca) {
+    src = xa + n * P * Ca + c;
+    ld = Ca;
+  } else {
+    src = xb + n * P * Cb + (c - Ca);
+    ld = Cb;
+  }
+  auto norm = [&](float4 v) {
+    float4 y = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
+    if (act) y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+    return y;
+  };
+  if (RES == 2) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long Po = (long long)Ho * Wo;
+    const long long per = (Po + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per, p1 = min(Po, p0 + per);
+    for (long long po = p0 + rr; po < p1; po += R) {
+      const int yo = (int)(po / Wo), xo = (int)(po % Wo);
+      const long long pi = (long long)(2 * yo) * W + 2 * xo;
+      const float4 v00 = Vec4<TIn>::load(src + pi * ld), v01 = Vec4<TIn>::load(src + (pi + 1) * ld);
+      const float4 v10 = Vec4<TIn>::load(src + (pi + W) * ld), v11 = Vec4<TIn>::load(src + (pi + W + 1) * ld);
+      const float4 a = norm(v00), b = norm(v01), cc = norm(v10), d = norm(v11);
+      const float4 y = make_float4(0.25f * ((a.x + b.x) + (cc.x + d.x)), 0.25f * ((a.y + b.y) + (cc.y + d.y)),
+                                   0.25f * ((a.z + b.z) + (cc.z + d.z)), 0.25f * ((a.w + b.w) + (cc.w + d.w)));
+      Vec4<TOut>::store(out + (n * Po + po) * C + c, y);
+      if (raw) {
+        const float4 r = make_float4(0.25f * ((v00.x + v01.x) + (v10.x + v11.x)), 0.25f * ((v00.y + v01.y) + (v10.y + v11.y)),
+                                     0.25f * ((v00.z + v01.z) + (v10.z + v11.z)), 0.25f * ((v00.w + v01.w) + (v10.w + v11.w)));
+        Vec4<TOut>::store(raw + (n * Po + po) * C + c, r);
+      }
+    }
+  } else {
+    const long long per = (P + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
+    for (long long p = p0 + rr; p < p1; p += R) {
+      const float4 v = Vec4<TIn>::load(src + p * ld);
+      const float4 y = norm(v);
+      if (RES == 0) {
+        Vec4<TOut>::store(out + (n * P + p) * C + c, y);
+        if (raw) Vec4<TOut>::store(raw + (n * P + p) * C + c, v);
+      } else {
+        const int yi = (int)(p / W), xi = (int)(p % W);
+        const long long Wo = 2LL * W;
+        const long long po = (long long)(2 * yi) * Wo + 2 * xi;
+        const long long base = n * P * 4;
+        Vec4<TOut>::store(out + (base + po) * C + c, y);
+        Vec4<TOut>::store(out + (base + po + 1) * C + c, y);
+        Vec4<TOut>::store(out + (base + po + Wo) * C + c, y);
+        Vec4<TOut>::store(out + (base + po + Wo + 1) * C + c, y);
+        if (raw) {
+          Vec4<TOut>::store(raw + (base + po) * C + c, v);
+          Vec4<TOut>::store(raw + (base + po + 1) * C + c, v);
+          Vec4<TOut>::store(raw + (base + po + Wo) * C + c, v);
+          Vec4<TOut>::store(raw + (base + po + Wo + 1) * C + c, v);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- softmax over rows, one warp per row
+template <typename TOut>
+__global__ void softmax_rows_kernel(const float* __restrict__ s, TOut* __restrict__ out, long long rows, int cols, int tf32) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = s + row * cols;
+  float m = -INFINITY;
+  for (int i = lane; i < cols; i += 32) m = fmaxf(m, src[i]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int i = lane; i < cols; i += 32) sum += __expf(src[i] - m);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < cols; i += 32) {
+    float v = __expf(src[i] - m) * inv;
+    if (tf32) v = round_tf32(v);
+    out[row * cols + i] = (TOut)v;
+  }
+}
+
+// ---------------------------------------------------------------- network input NCHW fp32 -> NHWC (padded channels)
+template <typename TOut>
+__global__ void prep_input_kernel(const float* __restrict__ x, TOut* __restrict__ out, long long N, int C, int HW, int cpad,
+                                  float mul, float add, int tf32) {
+  const long long total = N * HW * cpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const long long pix = i / cpad;
+    const long long n = pix / HW;
+    const int p = (int)(pix % HW);
+    float v = 0.f;
+    if (c < C) {
+      v = x[(n * C + c) * HW + p] * mul + add;
+      if (tf32) v = round_tf32(v);
+    }
+    out[i] = (TOut)v;
+  }
+}
+
+// ---------------------------------------------------------------- time embedding
+__global__ void time_embedding_kernel(const float* __restrict__ time_cond, const float* __restrict__ sched,
+                                      const int32_t* __restrict__ step, int sched_ld, int sched_col,
+                                      const float* __restrict__ freqs, int kind, long long N, int dim, float* __restrict__ out) {
+  const int half = dim >> 1;
+  const long long total = N * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / half;
+    const int j = (int)(i % half);
+    const float tc = sched ? sched[(long long)(step ? *step : 0) * sched_ld + sched_col] : time_cond[n];
+    float arg;
+    if (kind == 0) {
+      // models/layers.py:515-529: emb_j = exp(-j * ln(10000) / (half - 1)), arg = timesteps * emb_j
+      const float e = logf(10000.0f) / (float)(half - 1);
+      arg = tc * expf((float)j * -e);
+    } else {
+      // models/layerspp.py:52-54 with models/ncsnpp.py:258: x = log(sigma); x * W * 2 * pi
+      arg = logf(tc) * freqs[j] * 2.0f * 3.14159265358979323846f;
+    }
+    out[n * dim + j] = sinf(arg);
+    out[n * dim + half + j] = cosf(arg);
+  }
+}
+
+// ---------------------------------------------------------------- small dense layer, one warp per output column
+// out[n][o] = bias[o] + sum_k f(in[n][k]) w[o][k].  K <= 1024, K % 128 == 0 handled by the 8-register path.
+template <int KV>  // float4 per lane = K / 128
+__global__ void linear_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                              float* __restrict__ out, long long N, int K, int O, int act_in) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (o >= O) return;
+  float4 wr[KV];
+#pragma unroll
+  for (int i = 0; i < KV; ++i) wr[i] = *reinterpret_cast<const float4*>(w + (long long)o * K + (i * 32 + lane) * 4);
+  const float b = bias ? bias[o] : 0.f;
+  for (long long n = blockIdx.y; n < N; n += gridDim.y) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      float4 v = *reinterpret_cast<const float4*>(in + n * K + (i * 32 + lane) * 4);
+      if (act_in) v = make_float4(silu_f(v.x), silu_f(v.y), silu_f(v.z), silu_f(v.w));
+      acc += (v.x * wr[i].x + v.y * wr[i].y) + (v.z * wr[i].z + v.w * wr[i].w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[n * O + o] = acc + b;
+  }
+}
+
+// ---------------------------------------------------------------- FIR resampling on NHWC (4-tap separable kernel)
+// MODE 1: up x2 pad (2,1); MODE 2: down x2 pad (1,1); MODE 3: up=down=1 pad (2,2).
+// out[oy,ox] = sum_{i,j} xp[oy*down + i, ox*down + j] * kf[i][j], kf = flipped k, xp = zero-inserted + padded input.
+template <typename TIn, typename TOut, int MODE>
+__global__ void fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
+                                long long N, int H, int W, int C, float k0, float k1, float k2, float k3) {
+  constexpr int UP = MODE == 1 ? 2 : 1;
+  constexpr int DOWN = MODE == 2 ? 2 : 1;
+  constexpr int PAD0 = MODE == 1 ? 2 : (MODE == 2 ? 1 : 2);
+  const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : H + 1);
+  const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : W + 1);
+  const int Q = C >> 2;
+  const long long total = N * Ho * Wo * Q;
+  const float kf[4] = {k3, k2, k1, k0};  // flipped
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % Q);
+    long long t = idx / Q;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const long long n = t / Ho;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int uy = oy * DOWN + i - PAD0;
+      if (uy < 0 || (uy % UP) != 0) continue;
+      const int iy = uy / UP;
+      if (iy >= H) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ux = ox * DOWN + j - PAD0;
+        if (ux < 0 || (ux % UP) != 0) continue;
+        const int ix = ux / UP;
+        if (ix >= W) continue;
+        const float wgt = kf[i] * kf[j];
+        const float4 v = Vec4<TIn>::load(x + ((n * H + iy) * W + ix) * C + q * 4);
+        acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+      }
+    }
+    Vec4<TOut>::store(y + ((n * Ho + oy) * Wo + ox) * C + q * 4, acc);
+  }
+}
+
+inline int grid_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = (long long)indm_num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+struct GnGeom {
+  int Q, R, threads, splits;
+};
+inline GnGeom gn_geom(int C, long long P_iter, long long N) {
+  GnGeom g;
+  g.Q = C / 4;
+  g.R = 256 / g.Q;
+  if (g.R < 1) g.R = 1;
+  if (g.R > P_iter) g.R = (int)P_iter;
+  g.threads = g.Q * g.R;
+  // ~4 waves of CTAs over the chip, but at least ~8 pixel-rows of work per thread row
+  long long want = (4LL * indm_num_sms() + N - 1) / N;
+  long long maxs = P_iter / (g.R * 4LL);
+  if (maxs < 1) maxs = 1;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  g.splits = (int)want;
+  return g;
+}
+
+}  // namespace
+
+extern "C" int indm_gn_stats(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int64_t P, int G,
+                             float* partial, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!xb) Cb = 0;
+  const int C = Ca + Cb;
+  INDM_CHECK_ARG(xa && partial && N > 0 && P > 0, "gn_stats: bad arguments");
+  INDM_CHECK_ARG(G >= 1 && G <= 32 && C % G == 0 && (C / G) % 4 == 0 && Ca % 4 == 0 && C / 4 <= 1024,
+                 "gn_stats: need G <= 32, (C/G) %% 4 == 0 (C=%d G=%d)", C, G);
+  INDM_CHECK_ARG(Cb == 0 || Ca % (C / G) == 0, "gn_stats: concat boundary must fall on a group boundary");
+  INDM_CHECK_ARG(N <= 65535, "gn_stats: N too large for grid.y");
+  const GnGeom g = gn_geom(C, P, N);
+  dim3 grid(g.splits, (unsigned)N);
+  if (in_dtype == INDM_DTYPE_F32)
+    gn_stats_kernel<float><<<grid, g.threads, 0, stream>>>((const float*)xa, Ca, (const float*)xb, Cb, P, G, g.R, partial);
+  else if (in_dtype == INDM_DTYPE_BF16)
+    gn_stats_kernel<__nv_bfloat16><<<grid, g.threads, 0, stream>>>((const __nv_bfloat16*)xa, Ca, (const __nv_bfloat16*)xb, Cb, P,
+                                                                   G, g.R, partial);
+  else
+    INDM_CHECK_ARG(false, "gn_stats: in_dtype must be F32 or BF16");
+  INDM_CHECK_LAUNCH("gn_stats");
+  return INDM_OK;
+}
+
+template <typename TIn, typename TOut>
+static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64_t N, int H, int W, int G, const float* partial,
+                           const float* gamma, const float* beta, float eps, int act, int resample, void* out, void* raw,
+                           cudaStream_t stream) {
+  using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
+  const int C = Ca + Cb;
+  const long long Piter = resample == 2 ? (long long)(H / 2) * (W / 2) : (long long)H * W;
+  const GnGeom g = gn_geom(C, Piter, N);
+  dim3 grid(g.splits, (unsigned)N);
+#define GN_ARGS (const TIn*)xa, Ca, (const TIn*)xb, Cb, H, W, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw
+  if (resample == 0)
+    gn_apply_kernel<TIn, TOut, 0><<<grid, g.threads, 0, stream>>>(GN_ARGS);
+  else if (resample == 1)
+    gn_apply_kernel<TIn, TOut, 1><<<grid, g.threads, 0, stream>>>(GN_ARGS);
+  else
+    gn_apply_kernel<TIn, TOut, 2><<<grid, g.threads, 0, stream>>>(GN_ARGS);
+#undef GN_ARGS
+  INDM_CHECK_LAUNCH("gn_apply");
+  return INDM_OK;
+}
+
+extern "C" int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                             const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
+                             void* out, void* raw, int out_dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!xb) Cb = 0;
+  const int C = Ca + Cb;
+  INDM_CHECK_ARG(xa && partial && gamma && beta && out && N > 0 && H > 0 && W > 0, "gn_apply: bad arguments");
+  INDM_CHECK_ARG(G >= 1 && G <= 32 && C % G == 0 && (C / G) % 4 == 0 && Ca % 4 == 0 && C / 4 <= 1024,
+                 "gn_apply: need G <= 32, (C/G) %% 4 == 0 (C=%d G=%d)", C, G);
+  INDM_CHECK_ARG(resample >= 0 && resample <= 2, "gn_apply: resample must be 0, 1 or 2");
+  INDM_CHECK_ARG(resample != 2 || (H % 2 == 0 && W % 2 == 0), "gn_apply: down x2 needs even H, W");
+  INDM_CHECK_ARG(N <= 65535, "gn_apply: N too large for grid.y");
+  const bool in_f32 = in_dtype == INDM_DTYPE_F32, in_bf = in_dtype == INDM_DTYPE_BF16;
+  const bool out_bf = out_dtype == INDM_DTYPE_BF16, out_tf = out_dtype == INDM_DTYPE_TF32, out_f = out_dtype == INDM_DTYPE_F32;
+  INDM_CHECK_ARG((in_f32 || in_bf) && (out_bf || out_tf || out_f), "gn_apply: unsupported dtypes %d -> %d", in_dtype, out_dtype);
+#define GN_GO(TI, TO_) return gn_apply_launch<TI, TO_>(xa, Ca, xb, Cb, N, H, W, G, partial, gamma, beta, eps, act_silu, resample, out, raw, stream)
+  if (in_f32 && out_bf) GN_GO(float, __nv_bfloat16);
+  if (in_f32 && out_tf) GN_GO(float, Tf32Out);
+  if (in_f32 && out_f) GN_GO(float, float);
+  if (in_bf && out_bf) GN_GO(__nv_bfloat16, __nv_bfloat16);
+  if (in_bf && out_tf) GN_GO(__nv_bfloat16, Tf32Out);
+  GN_GO(__nv_bfloat16, float);
+#undef GN_GO
+}
+
+extern "C" int indm_softmax_rows(const float* s, void* out, int64_t rows, int cols, int out_dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(s && out && rows > 0 && cols > 0, "softmax_rows: bad arguments");
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  INDM_CHECK_ARG(blocks < (1LL << 31), "softmax_rows: too many rows");
+  if (out_dtype == INDM_DTYPE_BF16)
+    softmax_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, wpb * 32, 0, stream>>>(s, (__nv_bfloat16*)out, rows, cols, 0);
+  else if (out_dtype == INDM_DTYPE_TF32 || out_dtype == INDM_DTYPE_F32)
+    softmax_rows_kernel<float><<<(unsigned)blocks, wpb * 32, 0, stream>>>(s, (float*)out, rows, cols, out_dtype == INDM_DTYPE_TF32);
+  else
+    INDM_CHECK_ARG(false, "softmax_rows: bad out_dtype");
+  INDM_CHECK_LAUNCH("softmax_rows");
+  return INDM_OK;
+}
+
+extern "C" int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, int cpad, float mul, float add,
+                               int out_dtype, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(x && out && N > 0 && C > 0 && cpad >= C, "prep_input: bad arguments");
+  const long long total = (long long)N * H * W * cpad;
+  const int grid = grid_for(total, 256);
+  if (out_dtype == INDM_DTYPE_BF16)
+    prep_input_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)out, N, C, H * W, cpad, mul, add, 0);
+  else if (out_dtype == INDM_DTYPE_TF32 || out_dtype == INDM_DTYPE_F32)
+    prep_input_kernel<float><<<grid, 256, 0, stream>>>(x, (float*)out, N, C, H * W, cpad, mul, add, out_dtype == INDM_DTYPE_TF32);
+  else
+    INDM_CHECK_ARG(false, "prep_input: bad out_dtype");
+  INDM_CHECK_LAUNCH("prep_input");
+  return INDM_OK;
+}
+
+extern "C" int indm_time_embedding(const float* time_cond, const float* sched, const int32_t* step, int sched_ld, int sched_col,
+                                   const float* freqs, int kind, int64_t N, int dim, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG((time_cond || sched) && out && N > 0 && dim >= 4 && dim % 2 == 0, "time_embedding: bad arguments");
+  INDM_CHECK_ARG(kind == 0 || (kind == 1 && freqs), "time_embedding: kind 1 needs freqs");
+  time_embedding_kernel<<<grid_for(N * (dim / 2), 128), 128, 0, stream>>>(time_cond, sched, step, sched_ld, sched_col, freqs, kind,
+                                                                         N, dim, out);
+  INDM_CHECK_LAUNCH("time_embedding");
+  return INDM_OK;
+}
+
+extern "C" int indm_linear_f32(const float* in, const float* w, const float* bias, float* out, int64_t N, int K, int O,
+                               int act_in, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(in && w && out && N > 0 && O > 0, "linear: bad arguments");
+  INDM_CHECK_ARG(K % 128 == 0 && K >= 128 && K <= 1024, "linear: K must be a multiple of 128 in [128, 1024] (got %d)", K);
+  const int wpb = 4;
+  const int gx = (O + wpb - 1) / wpb;
+  // split the batch over grid.y only when there are too few output columns to fill the chip
+  int gy = 1;
+  while ((long long)gx * gy < 2LL * indm_num_sms() && gy < N) gy *= 2;
+  dim3 grid(gx, gy);
+  switch (K / 128) {
+#define LIN(KV) case KV: linear_kernel<KV><<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in); break;
+    LIN(1) LIN(2) LIN(3) LIN(4) LIN(5) LIN(6) LIN(7) LIN(8)
+#undef LIN
+  }
+  INDM_CHECK_LAUNCH("linear");
+  return INDM_OK;
+}
+
+template <typename TIn, typename TOut>
+static int fir_launch(const void* x, void* y, int64_t N, int H, int W, int C, const float* k, int mode, cudaStream_t stream) {
+  using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
+  const int Ho = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : H + 1);
+  const int Wo = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : W + 1);
+  const long long total = (long long)N * Ho * Wo * (C / 4);
+  const int grid = grid_for(total, 256);
+  if (mode == 1)
+    fir_nhwc_kernel<TIn, TOut, 1><<<grid, 256, 0, stream>>>((const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+  else if (mode == 2)
+    fir_nhwc_kernel<TIn, TOut, 2><<<grid, 256, 0, stream>>>((const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+  else
+    fir_nhwc_kernel<TIn, TOut, 3><<<grid, 256, 0, stream>>>((const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+  INDM_CHECK_LAUNCH("fir_nhwc");
+  return INDM_OK;
+}
+
+extern "C" int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N, int H, int W, int C, const float* k1,
+                             int mode, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(x && y && k1 && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "fir_nhwc: bad arguments");
+  INDM_CHECK_ARG(mode >= 1 && mode <= 3, "fir_nhwc: mode must be 1 (up), 2 (down) or 3 (pad-only)");
+  INDM_CHECK_ARG(mode != 2 || (H % 2 == 0 && W % 2 == 0), "fir_nhwc: down needs even H, W");
+  // k1 is a HOST pointer to the 4 separable taps, already normalised (and gain-scaled per axis)
+  const bool in_f = dtype_in == INDM_DTYPE_F32 || dtype_in == INDM_DTYPE_TF32, in_b = dtype_in == INDM_DTYPE_BF16;
+  INDM_CHECK_ARG(in_f || in_b, "fir_nhwc: bad dtype_in");
+  if (dtype_out == INDM_DTYPE_BF16) return in_f ? fir_launch<float, __nv_bfloat16>(x, y, N, H, W, C, k1, mode, stream)
+                                                : fir_launch<__nv_bfloat16, __nv_bfloat16>(x, y, N, H, W, C, k1, mode, stream);
+  if (dtype_out == INDM_DTYPE_TF32) return in_f ? fir_launch<float, Tf32Out>(x, y, N, H, W, C, k1, mode, stream)
+                                                : fir_launch<__nv_bfloat16, Tf32Out>(x, y, N, H, W, C, k1, mode, stream);
+  if (dtype_out == INDM_DTYPE_F32) return in_f ? fir_launch<float, float>(x, y, N, H, W, C, k1, mode, stream)
+                                               : fir_launch<__nv_bfloat16, float>(x, y, N, H, W, C, k1, mode, stream);
+  INDM_CHECK_ARG(false, "fir_nhwc: bad dtype_out");
+}

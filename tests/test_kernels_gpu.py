@@ -1,0 +1,380 @@
+"""GPU: every C-ABI kernel against a CPU FP32/FP64 computation of the same op on the same seeded inputs.
+
+Tolerances: BF16 mode — inputs are pre-rounded to bf16 so the only differences are fp32 accumulation order and the
+output cast (2^-9 relative when the output is bf16); TF32 mode — inputs pre-rounded to tf32, fp32 accumulate.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from indm_b200 import _lib as L  # noqa: E402
+
+DEV = 'cuda'
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def tf32r(t):
+    # round-to-nearest-away on the 13 dropped mantissa bits == cvt.rna.tf32.f32
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def rel_l2(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def dev_op(t, dtype):
+    """operand on device in the kernel's element type"""
+    return (t.to(torch.bfloat16) if dtype == L.DTYPE_BF16 else t.float()).contiguous().to(DEV)
+
+
+def pack_w(w, dtype):
+    """[Cout, Cin, kh, kw] -> [taps][Cout][Cin]"""
+    co, ci, kh, kw = w.shape
+    return dev_op(w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci), dtype)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def round_in(t, dtype):
+    return bf16r(t) if dtype == L.DTYPE_BF16 else tf32r(t)
+
+
+@pytest.mark.parametrize("dtype", [L.DTYPE_BF16, L.DTYPE_TF32])
+@pytest.mark.parametrize("M,K,Nn,bn", [(300, 192, 200, 0), (128, 64, 32, 32), (1000, 512, 768, 256), (257, 128, 128, 64)])
+def test_igemm_plain_gemm(dtype, M, K, Nn, bn):
+    a = round_in(rnd(M, K, seed=1), dtype)
+    b = round_in(rnd(Nn, K, seed=2) / math.sqrt(K), dtype)
+    bias = rnd(Nn, seed=3)
+    out = torch.full((M, Nn), float('nan'), device=DEV)
+    L.igemm(dtype=dtype, a=dev_op(a, dtype), N=1, H=1, W=M, Cin=K, b=dev_op(b, dtype), Cout=Nn, taps=1,
+            bias=bias.to(DEV), out_f32=out, out_ld=Nn, block_n=bn)
+    torch.cuda.synchronize()
+    want = a.double() @ b.double().t() + bias.double()
+    assert rel_l2(out.cpu(), want) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [L.DTYPE_BF16, L.DTYPE_TF32])
+@pytest.mark.parametrize("N,S,Cin,Cout,bn", [(2, 16, 128, 256, 0), (1, 32, 64, 128, 128), (3, 8, 128, 128, 64),
+                                             (3, 4, 256, 256, 256), (9, 4, 64, 64, 0), (1, 64, 64, 64, 0)])
+def test_igemm_conv3x3(dtype, N, S, Cin, Cout, bn):
+    x = round_in(rnd(N, Cin, S, S, seed=4), dtype)
+    w = round_in(rnd(Cout, Cin, 3, 3, seed=5) / math.sqrt(9 * Cin), dtype)
+    bias = rnd(Cout, seed=6)
+    rowb = rnd(N, Cout + 8, seed=7)
+    res = rnd(N, S, S, Cout, seed=8)
+    o32 = torch.full((N, S, S, Cout), float('nan'), device=DEV)
+    o16 = torch.zeros((N, S, S, Cout), device=DEV, dtype=torch.bfloat16)
+    L.igemm(dtype=dtype, a=dev_op(nhwc(x), dtype), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dtype), Cout=Cout, taps=9,
+            bias=bias.to(DEV), rowbias=rowb.to(DEV), rowbias_ld=Cout + 8, residual=res.to(DEV), res_ld=Cout,
+            scale=0.7071, out_f32=o32, out_bf16=o16, out_ld=Cout, block_n=bn)
+    torch.cuda.synchronize()
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    want = (nhwc(want) + rowb[:, None, None, :Cout].double() + res.double()) * 0.7071
+    assert rel_l2(o32.cpu(), want) < 2e-5
+    assert rel_l2(o16.float().cpu(), want) < 4e-3
+
+
+@pytest.mark.parametrize("dtype", [L.DTYPE_BF16, L.DTYPE_TF32])
+def test_igemm_fused_skip_segment(dtype):
+    N, S, C1, C2, Cout = 2, 16, 128, 384, 256
+    h = round_in(rnd(N, C1, S, S, seed=9), dtype)
+    xs = round_in(rnd(N, C2, S, S, seed=10), dtype)
+    w1 = round_in(rnd(Cout, C1, 3, 3, seed=11) / math.sqrt(9 * C1), dtype)
+    w2 = round_in(rnd(Cout, C2, 1, 1, seed=12) / math.sqrt(C2), dtype)
+    o32 = torch.empty((N, S, S, Cout), device=DEV)
+    L.igemm(dtype=dtype, a=dev_op(nhwc(h), dtype), N=N, H=S, W=S, Cin=C1, b=pack_w(w1, dtype), Cout=Cout, taps=9,
+            a2=dev_op(nhwc(xs), dtype), Cin2=C2, b2=dev_op(w2.reshape(Cout, C2), dtype), out_f32=o32, out_ld=Cout)
+    torch.cuda.synchronize()
+    want = nhwc(F.conv2d(h.double(), w1.double(), padding=1) + F.conv2d(xs.double(), w2.double()))
+    assert rel_l2(o32.cpu(), want) < 2e-5
+
+
+@pytest.mark.parametrize("L_", [256, 64, 16])
+def test_igemm_batched_attention_products(L_):
+    """S = Q K^T / sqrt(C) and O = P V with per-image B operands, exactly the two einsums of AttnBlockpp."""
+    B, Cc = 3, 256
+    dt = L.DTYPE_BF16
+    qkv = bf16r(rnd(B, L_, 3 * Cc, seed=13))
+    qkv_d = dev_op(qkv, dt)
+    s = torch.empty((B, L_, L_), device=DEV)
+    L.igemm(dtype=dt, a=qkv_d, a_ld=3 * Cc, a_img_stride=L_ * 3 * Cc, N=B, H=1, W=L_, Cin=Cc,
+            b=qkv_d[:, :, Cc:], b_ld=3 * Cc, b_tap_stride=L_ * 3 * Cc, Cout=L_, taps=1, batched_b=1,
+            scale=Cc ** -0.5, out_f32=s, out_ld=L_)
+    torch.cuda.synchronize()
+    q, k, v = qkv[..., :Cc].double(), qkv[..., Cc:2 * Cc].double(), qkv[..., 2 * Cc:].double()
+    want_s = torch.einsum('bic,bjc->bij', q, k) * Cc ** -0.5
+    assert rel_l2(s.cpu(), want_s) < 2e-5
+    p = bf16r(torch.softmax(want_s.float(), dim=-1))
+    vt = dev_op(qkv[..., 2 * Cc:].transpose(1, 2).contiguous(), dt)     # [B, C, L]
+    o = torch.empty((B, L_, Cc), device=DEV, dtype=torch.bfloat16)
+    L.igemm(dtype=dt, a=dev_op(p, dt), N=B, H=1, W=L_, Cin=L_, b=vt, Cout=Cc, taps=1, batched_b=1,
+            out_bf16=o, out_ld=Cc)
+    torch.cuda.synchronize()
+    want_o = torch.einsum('bij,bjc->bic', p.double(), v)
+    assert rel_l2(o.float().cpu(), want_o) < 4e-3
+
+
+def test_igemm_head_nchw_and_transposed_modes():
+    dt = L.DTYPE_BF16
+    N, S, Cin = 2, 32, 128
+    x = bf16r(rnd(N, Cin, S, S, seed=14))
+    w = bf16r(rnd(3, Cin, 3, 3, seed=15) / math.sqrt(9 * Cin))
+    bias = rnd(3, seed=16)
+    rs = torch.tensor([0.5, -2.0])
+    out = torch.full((N, 3, S, S), float('nan'), device=DEV)
+    L.igemm(dtype=dt, a=dev_op(nhwc(x), dt), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dt), Cout=3, taps=9,
+            bias=bias.to(DEV), rowscale=rs.to(DEV), out_mode=1, out_f32=out)
+    torch.cuda.synchronize()
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1) * rs.double()[:, None, None, None]
+    assert rel_l2(out.cpu(), want) < 2e-5
+    # mode 2: q,k rows + V transposed
+    B, Lq, Cc = 2, 256, 256
+    hh = bf16r(rnd(B, Lq, Cc, seed=17))
+    wq = bf16r(rnd(3 * Cc, Cc, seed=18) / math.sqrt(Cc))
+    bq = rnd(3 * Cc, seed=19)
+    qk = torch.zeros((B, Lq, 2 * Cc), device=DEV, dtype=torch.bfloat16)
+    vt = torch.zeros((B, Cc, Lq), device=DEV, dtype=torch.bfloat16)
+    L.igemm(dtype=dt, a=dev_op(hh, dt), N=B, H=16, W=16, Cin=Cc, b=dev_op(wq, dt), Cout=3 * Cc, taps=1, bias=bq.to(DEV),
+            out_mode=2, out_bf16=qk, out_ld=2 * Cc, tcol0=2 * Cc, out_t=vt)
+    torch.cuda.synchronize()
+    want = hh.double() @ wq.double().t() + bq.double()
+    assert rel_l2(qk.float().cpu(), want[..., :2 * Cc]) < 4e-3
+    assert rel_l2(vt.float().cpu(), want[..., 2 * Cc:].transpose(1, 2)) < 4e-3
+
+
+@pytest.mark.parametrize("S,N", [(16, 2), (8, 3), (32, 1)])
+def test_igemm_fused_groupnorm_statistics(S, N):
+    dt = L.DTYPE_BF16
+    Cin, Cout, G = 128, 256, 32
+    x = bf16r(rnd(N, Cin, S, S, seed=20))
+    w = bf16r(rnd(Cout, Cin, 3, 3, seed=21) / math.sqrt(9 * Cin))
+    o16 = torch.zeros((N, S, S, Cout), device=DEV, dtype=torch.bfloat16)
+    part = torch.zeros((N, G, 2), device=DEV)
+    L.igemm(dtype=dt, a=dev_op(nhwc(x), dt), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dt), Cout=Cout, taps=9,
+            out_bf16=o16, out_ld=Cout, gn_partial=part, gn_cpg=Cout // G, gn_groups=G)
+    torch.cuda.synchronize()
+    y = o16.float().cpu().reshape(N, S * S, G, Cout // G).double()
+    want = torch.stack([y.sum(dim=(1, 3)), (y * y).sum(dim=(1, 3))], dim=-1)
+    assert rel_l2(part.cpu(), want) < 1e-4
+
+
+@pytest.mark.parametrize("in_dt,out_dt", [(L.DTYPE_F32, L.DTYPE_BF16), (L.DTYPE_BF16, L.DTYPE_BF16), (L.DTYPE_F32, L.DTYPE_TF32)])
+@pytest.mark.parametrize("Ca,Cb,S,res,act", [(128, 0, 16, 0, 1), (256, 128, 8, 0, 1), (256, 256, 4, 0, 1), (128, 0, 16, 2, 1),
+                                              (256, 0, 8, 1, 1), (256, 0, 16, 0, 0), (512, 0, 4, 0, 1), (128, 0, 32, 0, 1)])
+def test_groupnorm_silu_resample(in_dt, out_dt, Ca, Cb, S, res, act):
+    N = 3
+    C = Ca + Cb
+    G = min(C // 4, 32)
+    xa = rnd(N, S, S, Ca, seed=22) * 1.5 + 0.3
+    xb = rnd(N, S, S, Cb, seed=23) if Cb else None
+    if in_dt == L.DTYPE_BF16:
+        xa = bf16r(xa); xb = bf16r(xb) if Cb else None
+    gamma, beta = 1 + 0.1 * rnd(C, seed=24), 0.1 * rnd(C, seed=25)
+    tin = torch.bfloat16 if in_dt == L.DTYPE_BF16 else torch.float32
+    xa_d = xa.to(tin).to(DEV)
+    xb_d = xb.to(tin).to(DEV) if Cb else None
+    part = torch.zeros((N, G, 2), device=DEV)
+    L.call('indm_gn_stats', L.ptr(xa_d), Ca, L.ptr(xb_d), Cb, in_dt, N, S * S, G, L.ptr(part))
+    So = S * 2 if res == 1 else (S // 2 if res == 2 else S)
+    tout = torch.bfloat16 if out_dt == L.DTYPE_BF16 else torch.float32
+    out = torch.zeros((N, So, So, C), device=DEV, dtype=tout)
+    raw = torch.zeros((N, So, So, C), device=DEV, dtype=tout)
+    L.call('indm_gn_apply', L.ptr(xa_d), Ca, L.ptr(xb_d), Cb, in_dt, N, S, S, G, L.ptr(part), L.ptr(gamma.to(DEV)),
+           L.ptr(beta.to(DEV)), 1e-6, act, res, L.ptr(out), L.ptr(raw), out_dt)
+    torch.cuda.synchronize()
+    x = torch.cat([xa, xb], dim=-1) if Cb else xa
+    xc = x.permute(0, 3, 1, 2).double()
+    y = F.group_norm(xc, G, gamma.double(), beta.double(), eps=1e-6)
+    if act:
+        y = F.silu(y)
+
+    def resample(t):
+        if res == 1:
+            return t.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        if res == 2:
+            return F.avg_pool2d(t, 2)
+        return t
+    tol = 4e-3 if out_dt == L.DTYPE_BF16 else 5e-4
+    assert rel_l2(out.float().cpu(), nhwc(resample(y))) < tol
+    assert rel_l2(raw.float().cpu(), nhwc(resample(xc))) < tol
+
+
+@pytest.mark.parametrize("cols", [16, 64, 256])
+def test_softmax_rows(cols):
+    s = rnd(37, cols, seed=26) * 3
+    out = torch.zeros((37, cols), device=DEV, dtype=torch.bfloat16)
+    L.call('indm_softmax_rows', L.ptr(s.to(DEV)), L.ptr(out), 37, cols, L.DTYPE_BF16)
+    out32 = torch.zeros((37, cols), device=DEV)
+    L.call('indm_softmax_rows', L.ptr(s.to(DEV)), L.ptr(out32), 37, cols, L.DTYPE_F32)
+    torch.cuda.synchronize()
+    want = torch.softmax(s.double(), dim=-1)
+    assert rel_l2(out.float().cpu(), want) < 4e-3
+    assert rel_l2(out32.cpu(), want) < 1e-5
+
+
+def test_prep_input_and_time_embedding_and_linear():
+    x = rnd(3, 3, 8, 8, seed=27)
+    out = torch.full((3, 8, 8, 64), 7.0, device=DEV, dtype=torch.bfloat16)
+    L.call('indm_prep_input', L.ptr(x.to(DEV)), L.ptr(out), 3, 3, 8, 8, 64, 2.0, -1.0, L.DTYPE_BF16)
+    torch.cuda.synchronize()
+    want = torch.zeros(3, 8, 8, 64)
+    want[..., :3] = nhwc(2 * x - 1)
+    assert rel_l2(out.float().cpu(), want) < 4e-3
+    assert float(out[..., 3:].abs().max()) == 0.0
+    # positional embedding, models/layers.py:515-529
+    t = torch.tensor([0.0, 1.7, 333.3, 999.0])
+    emb = torch.zeros((4, 128), device=DEV)
+    L.call('indm_time_embedding', L.ptr(t.to(DEV)), None, None, 0, 0, None, 0, 4, 128, L.ptr(emb))
+    half = 64
+    e = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    arg = t[:, None] * e[None, :]
+    want = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
+    torch.cuda.synchronize()
+    assert float((emb.cpu() - want).abs().max()) < 2e-4     # fp32 sin/cos at arguments up to ~1e3
+    # Gaussian Fourier, models/layerspp.py:52-54
+    sig = torch.tensor([0.01, 0.5, 3.0, 50.0])
+    Wf = rnd(64, seed=28) * 16
+    emb = torch.zeros((4, 128), device=DEV)
+    L.call('indm_time_embedding', L.ptr(sig.to(DEV)), None, None, 0, 0, L.ptr(Wf.to(DEV)), 1, 4, 128, L.ptr(emb))
+    xp = torch.log(sig)[:, None] * Wf[None, :] * 2 * np.pi
+    want = torch.cat([torch.sin(xp), torch.cos(xp)], dim=-1)
+    torch.cuda.synchronize()
+    assert float((emb.cpu() - want).abs().max()) < 5e-4
+    # dense
+    inp, w, b = rnd(5, 512, seed=29), rnd(300, 512, seed=30) / 22, rnd(300, seed=31)
+    o = torch.zeros((5, 300), device=DEV)
+    L.call('indm_linear_f32', L.ptr(inp.to(DEV)), L.ptr(w.to(DEV)), L.ptr(b.to(DEV)), L.ptr(o), 5, 512, 300, 1)
+    torch.cuda.synchronize()
+    want = F.linear(F.silu(inp.double()), w.double(), b.double())
+    assert rel_l2(o.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_fir_nhwc_matches_oracle_upfirdn2d(mode):
+    from oracle import ops as oops
+    N, S, Cc = 2, 8, 16
+    x = rnd(N, Cc, S, S, seed=32)
+    k1 = np.array([1, 3, 3, 1], dtype=np.float32)
+    k1 = k1 / k1.sum()
+    k2 = np.outer(k1, k1)
+    args = {1: dict(up=2, down=1, pad=(2, 1)), 2: dict(up=1, down=2, pad=(1, 1)), 3: dict(up=1, down=1, pad=(2, 2))}[mode]
+    want = oops.upfirdn2d(x.numpy(), k2 * (4 if mode == 1 else 1), **args)
+    kk = (k1 * (2 if mode == 1 else 1)).astype(np.float32)
+    So = want.shape[-1]
+    out = torch.zeros((N, So, So, Cc), device=DEV)
+    import ctypes
+    L.call('indm_fir_nhwc', L.ptr(nhwc(x).to(DEV)), L.ptr(out), L.DTYPE_F32, L.DTYPE_F32, N, S, S, Cc,
+           kk.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), mode)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), nhwc(torch.from_numpy(want))) < 1e-6
+
+
+def test_pc_update_kernels_match_oracle():
+    from oracle import sampler as osampler, sde as osde
+    N, D = 4, 3 * 16 * 16
+    x, s, z = rnd(N, 3, 16, 16, seed=33), rnd(N, 3, 16, 16, seed=34), rnd(N, 3, 16, 16, seed=35)
+    sde = osde.VP()
+    t = torch.full((N,), 0.37)
+    want_x, want_mean = osampler.reverse_diffusion_update(sde, s, x, t, z)
+    ts = int(0.37 * 999)
+    beta, alpha = float(sde.discrete_betas[ts]), float(sde.alphas[ts])
+    coef = torch.tensor([[2 - math.sqrt(alpha), beta, math.sqrt(beta), 0.0]])
+    xd, xm = x.clone().to(DEV), torch.zeros_like(x).to(DEV)
+    L.call('indm_pc_predictor_update', L.ptr(xd), L.ptr(s.to(DEV)), L.ptr(z.to(DEV)), L.ptr(xm), L.ptr(coef.to(DEV)), 4, None,
+           N, D, 0, 0)
+    torch.cuda.synchronize()
+    assert rel_l2(xd.cpu(), want_x) < 1e-6 and rel_l2(xm.cpu(), want_mean) < 1e-6
+    # Langevin, VE (alpha = 1)
+    ve = osde.VE()
+    want_x, want_mean = osampler.langevin_update(ve, s, x, t, z, 0.16)
+    norms = torch.zeros((N, 2), device=DEV)
+    L.call('indm_langevin_norms', L.ptr(s.to(DEV)), L.ptr(z.to(DEV)), L.ptr(norms), None, N, D, 0, 0)
+    coef = torch.tensor([[1.0, 0.16]])
+    xd, xm = x.clone().to(DEV), torch.zeros_like(x).to(DEV)
+    L.call('indm_langevin_update', L.ptr(xd), L.ptr(s.to(DEV)), L.ptr(z.to(DEV)), L.ptr(xm), L.ptr(norms), L.ptr(coef.to(DEV)), 2,
+           None, N, D, 0, 0)
+    torch.cuda.synchronize()
+    assert rel_l2(xd.cpu(), want_x) < 1e-5 and rel_l2(xm.cpu(), want_mean) < 1e-5
+
+
+def test_philox_normal_stream_statistics_and_replay():
+    n = 1 << 20
+    a, b = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    L.call('indm_randn_f32', L.ptr(a), n, 1234, 5)
+    L.call('indm_randn_f32', L.ptr(b), n, 1234, 5)
+    c = torch.zeros(n, device=DEV)
+    L.call('indm_randn_f32', L.ptr(c), n, 1234, 6)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1) < 5e-3
+    assert abs(float((a ** 4).mean()) - 3) < 0.05
+    assert abs(float((a * c).mean())) < 5e-3
+    # in-kernel noise: langevin_norms(z=None) sees the same draw as langevin_update(z=None)
+    N, D = 2, 4096
+    s = rnd(N, D, seed=36).to(DEV)
+    norms = torch.zeros((N, 2), device=DEV)
+    L.call('indm_langevin_norms', L.ptr(s), None, L.ptr(norms), None, N, D, 77, 1)
+    x0 = torch.zeros((N, D), device=DEV)
+    coef = torch.tensor([[1.0, 0.16]], device=DEV)
+    L.call('indm_langevin_update', L.ptr(x0), L.ptr(torch.zeros_like(s)), None, None, L.ptr(norms), L.ptr(coef), 2, None, N, D, 77, 1)
+    torch.cuda.synchronize()
+    # with s = 0 in the update, x = sqrt(2 eps) z  =>  |x_n|^2 / (2 eps) == |z_n|^2 from the norms kernel
+    r = 0.16 * norms[:, 1].sqrt().mean() / norms[:, 0].sqrt().mean()
+    eps = float(2 * r * r)
+    got = (x0 ** 2).sum(dim=1) / (2 * eps)
+    assert rel_l2(got.cpu(), norms[:, 1].cpu()) < 1e-4
+
+
+UPFIRDN_CASES = ['up2', 'down2', 'pyr', 'k3', 'crop', 'gen', 'up2_32']
+
+
+@pytest.mark.parametrize("case", UPFIRDN_CASES)
+def test_upfirdn2d_c_abi_against_reference_golden(case):
+    from helpers import load_npz
+    g = load_npz('ops.npz')
+    up, down, p0, p1 = [int(v) for v in g[f'upfirdn_{case}_args']]
+    x, k, want = g[f'upfirdn_{case}_x'], g[f'upfirdn_{case}_k'], g[f'upfirdn_{case}_y']
+    n, c, h, w = x.shape
+    y = torch.full(want.shape, float('nan'), device=DEV)
+    L.call('indm_upfirdn2d_f32', L.ptr(torch.from_numpy(x).to(DEV)), L.ptr(torch.from_numpy(k).to(DEV)), L.ptr(y), n * c, h, w,
+           k.shape[0], k.shape[1], up, up, down, down, p0, p1, p0, p1)
+    torch.cuda.synchronize()
+    # north_star: upfirdn2d within 1e-6 relative in FP32
+    assert rel_l2(y.cpu(), torch.from_numpy(want)) < 1e-6
+
+
+@pytest.mark.parametrize("case", ['4d', '2d', '3d'])
+def test_bias_act_c_abi_against_reference_golden(case):
+    from helpers import load_npz
+    g = load_npz('ops.npz')
+    x, b, want = g[f'lrelu_{case}_x'], g[f'lrelu_{case}_b'], g[f'lrelu_{case}_y']
+    step = int(np.prod(x.shape[2:]))
+    y = torch.zeros(x.shape, device=DEV)
+    L.call('indm_bias_act_f32', L.ptr(torch.from_numpy(x).to(DEV)), L.ptr(torch.from_numpy(b).to(DEV)), None, L.ptr(y), x.size,
+           b.shape[0], step, 3, 0, 0.2, 2 ** 0.5)
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu(), torch.from_numpy(want)) < 1e-6
+    # backward: grad=1 with ref = forward output
+    gy, want_gx = g[f'lrelu_{case}_gy'], g[f'lrelu_{case}_gx']
+    gx = torch.zeros(x.shape, device=DEV)
+    L.call('indm_bias_act_f32', L.ptr(torch.from_numpy(gy).to(DEV)), None, L.ptr(y), L.ptr(gx), x.size, 1, 1, 3, 1, 0.2, 2 ** 0.5)
+    torch.cuda.synchronize()
+    assert rel_l2(gx.cpu(), torch.from_numpy(want_gx)) < 1e-6

@@ -166,6 +166,12 @@ int indm_langevin_update(float* x, const float* s, const float* z, float* x_mean
 /* *step += 1 (device-side step counter advanced inside the captured graph) */
 int indm_advance_step(int32_t* step, void* stream);
 
+/* out[i] = sched[*step][col_num] (/ sched[*step][col_den] if col_den >= 0), i < n: per-step scalar broadcast to a
+ * per-sample vector (the network's output scale -1/std(t) of models/utils.py:176-177, or 1/sigma of
+ * models/ncsnpp.py:410-412) without leaving the device. */
+int indm_sched_broadcast(float* out, int64_t n, const float* sched, int ld, int col_num, int col_den, const int32_t* step,
+                         void* stream);
+
 /* fill with standard normal noise (same Philox stream as above), fp32 */
 int indm_randn_f32(float* out, int64_t n, uint64_t seed, uint64_t rng_offset, void* stream);
 

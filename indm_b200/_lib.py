@@ -56,6 +56,7 @@ _SIGS = {
     "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _u64, _vp],
     "indm_advance_step": [_vp, _vp],
     "indm_randn_f32": [_vp, _i64, _u64, _u64, _vp],
+    "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],
 }
 EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)
 

@@ -192,3 +192,21 @@ extern "C" int indm_randn_f32(float* out, int64_t n, uint64_t seed, uint64_t rng
   INDM_CHECK_LAUNCH("randn");
   return INDM_OK;
 }
+
+namespace {
+__global__ void sched_broadcast_kernel(float* __restrict__ out, long long n, const float* __restrict__ sched, int ld, int col_num,
+                                       int col_den, const int32_t* __restrict__ step) {
+  const int st = step ? *step : 0;
+  float v = sched[(long long)st * ld + col_num];
+  if (col_den >= 0) v /= sched[(long long)st * ld + col_den];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = v;
+}
+}  // namespace
+
+extern "C" int indm_sched_broadcast(float* out, int64_t n, const float* sched, int ld, int col_num, int col_den, const int32_t* step,
+                                    void* stream_) {
+  INDM_CHECK_ARG(out && sched && n > 0 && ld > 0 && col_num >= 0, "sched_broadcast: bad arguments");
+  sched_broadcast_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream_>>>(out, n, sched, ld, col_num, col_den, step);
+  INDM_CHECK_LAUNCH("sched_broadcast");
+  return INDM_OK;
+}

@@ -350,7 +350,6 @@ extern "C" int indm_gn_stats(const void* xa, int Ca, const void* xb, int Cb, int
   INDM_CHECK_ARG(xa && partial && N > 0 && P > 0, "gn_stats: bad arguments");
   INDM_CHECK_ARG(G >= 1 && G <= 32 && C % G == 0 && (C / G) % 4 == 0 && Ca % 4 == 0 && C / 4 <= 1024,
                  "gn_stats: need G <= 32, (C/G) %% 4 == 0 (C=%d G=%d)", C, G);
-  INDM_CHECK_ARG(Cb == 0 || Ca % (C / G) == 0, "gn_stats: concat boundary must fall on a group boundary");
   INDM_CHECK_ARG(N <= 65535, "gn_stats: N too large for grid.y");
   const GnGeom g = gn_geom(C, P, N);
   dim3 grid(g.splits, (unsigned)N);

@@ -1,0 +1,428 @@
+"""Execution engine of the NCSN++ / DDPM++ score network on B200.
+
+`ScoreEngine` turns an `NCSNpp` parameter container into a static launch plan over the C-ABI kernels
+(include/indm_b200.h): activations live in NHWC (FP32 residual stream, BF16 — or tf32-rounded FP32 in validation mode
+— tensor-core operands), weights are repacked once to [tap][Cout][Cin], every buffer is allocated up front so the plan
+has fixed addresses and can be captured into a CUDA graph and replayed by the sampler.
+
+Per res-block (models/layerspp.py:255-287) the plan is 5-6 launches instead of the reference's ~20:
+    gn_stats(x)  ->  gn_apply(+SiLU, +nearest-up / mean-down, +raw bf16 copy)          [HBM-bound]
+    igemm 3x3 (+bias, +Dense_0(SiLU(temb)) row bias, +fused GroupNorm_1 statistics)    [tcgen05]
+    gn_apply(+SiLU)                                                                    [HBM-bound]
+    igemm 3x3 (+ fused 1x1 skip conv as extra K iterations, + residual, * 1/sqrt(2))   [tcgen05]
+All 44 Dense_0 layers are evaluated at once (one [N,4nf] x [sum Cout, 4nf] product, temb is shared).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+
+class _Buf:
+    """bump allocation record (all buffers are plain torch tensors kept alive by the engine)"""
+    pass
+
+
+class ScoreEngine:
+    def __init__(self, model, batch, mode='bf16', device=None):
+        cfg = model.config
+        self.model = model
+        self.cfg = cfg
+        self.N = int(batch)
+        self.mode = mode
+        assert mode in ('bf16', 'tf32')
+        self.dt = L.DTYPE_BF16 if mode == 'bf16' else L.DTYPE_TF32
+        self.tdtype = torch.bfloat16 if mode == 'bf16' else torch.float32
+        self.kchunk = 64 if mode == 'bf16' else 32
+        self.dev = device if device is not None else next(model.parameters()).device
+        if self.dev.type != 'cuda':
+            raise RuntimeError('ScoreEngine needs a CUDA device: indm_b200 has no CPU path')
+        L.lib()
+        self.S = cfg.data.image_size
+        self.ch = cfg.data.num_channels
+        self.nf = cfg.model.nf
+        self.fir = bool(cfg.model.fir)
+        self.keep = []            # every tensor the plan points into
+        self.ops = []             # list of zero-arg callables
+        self.pack_jobs = []       # (fn) re-run by load_weights()
+        self.gn_slots = 0
+        self._weights_version = None
+        self._build()
+        self.load_weights()
+
+    # ------------------------------------------------------------------ helpers
+    def _alloc(self, shape, dtype=torch.float32, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, device=self.dev, dtype=dtype)
+        self.keep.append(t)
+        return t
+
+    def _op_t(self, shape):
+        """tensor-core operand buffer (bf16, or fp32 in tf32 mode)"""
+        return self._alloc(shape, self.tdtype)
+
+    def _gn_slot(self):
+        i = self.gn_slots
+        self.gn_slots += 1
+        return i
+
+    def _round_op(self, w):
+        """fp32 tensor -> operand dtype (bf16 / tf32-rounded fp32)"""
+        if self.mode == 'bf16':
+            return w.to(torch.bfloat16)
+        i = w.float().contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def _pack_conv(self, dst, conv_w, cin_pad=None):
+        """[Cout, Cin, k, k] parameter -> dst [k*k][Cout][Cin_pad]"""
+        def job():
+            w = conv_w.detach().to(self.dev, torch.float32)
+            co, ci, kh, kw = w.shape
+            w = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+            if cin_pad is not None and cin_pad != ci:
+                dst.zero_()
+                dst[:, :, :ci].copy_(self._round_op(w))
+            else:
+                dst.copy_(self._round_op(w))
+        self.pack_jobs.append(job)
+
+    def _pack_f32(self, dst, srcs, transform=None):
+        def job():
+            parts = [s.detach().to(self.dev, torch.float32) for s in srcs]
+            v = torch.cat([p.reshape(-1) if transform is None else transform(p).reshape(-1) for p in parts])
+            dst.view(-1).copy_(v)
+        self.pack_jobs.append(job)
+
+    def load_weights(self):
+        """(Re)pack all parameters into the engine's device buffers; cheap (one pass over ~62 M parameters)."""
+        with torch.no_grad():
+            for job in self.pack_jobs:
+                job()
+        self._weights_version = self.weights_version()
+
+    def weights_version(self):
+        return sum(p._version for p in self.model.parameters())
+
+    # ------------------------------------------------------------------ plan construction
+    def _igemm(self, **kw):
+        d = L.IgemmDesc()
+        d.scale = 1.0
+        d.dtype = self.dt
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                v = v.data_ptr()
+            setattr(d, k, v)
+        lib = L.lib()
+
+        def run():
+            L.check(lib.indm_igemm(ctypes.byref(d), L._stream()), 'igemm')
+        self.ops.append(run)
+
+    def _call(self, name, *args):
+        fn = getattr(L.lib(), name)
+        cargs = [ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a for a in args]
+
+        def run():
+            L.check(fn(*cargs, L._stream()), name)
+        self.ops.append(run)
+
+    def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False):
+        """GroupNorm(+SiLU)(+resample) of concat(xa, xb) -> operand tensor (and optional raw copy of the input).
+        Emits the statistics launch unless a producer already accumulated them into `slot`."""
+        N = self.N
+        C = Ca + Cb
+        G = gparams.num_groups
+        gamma, beta = self._alloc((C,)), self._alloc((C,))
+        self._pack_f32(gamma, [gparams.weight])
+        self._pack_f32(beta, [gparams.bias])
+        if slot is None:
+            slot = self._gn_slot()
+        part = self.gn_part[slot]
+        if not stats_done:
+            self._call('indm_gn_stats', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), ctypes.c_int64(H * W), G, part)
+        Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
+        out = self._op_t((N, Ho, Wo, C))
+        raw = self._op_t((N, Ho, Wo, C)) if want_raw else None
+        self._call('indm_gn_apply', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
+                   act, resample, out, raw, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
+        return out, raw
+
+    def _build(self):
+        cfg, m = self.cfg, self.model
+        N, S, nf = self.N, self.S, self.nf
+        mods = list(m.all_modules)
+        # GroupNorm statistics: one [slots][N][32][2] buffer zeroed by a single memset per forward
+        MAX_SLOTS = 2 * len(mods) + 8
+        self.gn_part_all = self._alloc((MAX_SLOTS, N, 32, 2), zero=True)
+        self.gn_part = [self.gn_part_all[i] for i in range(MAX_SLOTS)]
+        part_all = self.gn_part_all
+
+        def zero_stats():
+            part_all.zero_()    # cudaMemsetAsync on the current stream
+        self.ops.append(zero_stats)
+
+        idx = 0
+        # ---------------- time embedding + MLP + all Dense_0 at once
+        self.time_cond = self._alloc((N,))
+        self.sched = None          # optional device schedule table / step counter installed by the sampler
+        emb_type = cfg.model.embedding_type.lower()
+        if emb_type == 'fourier':
+            fw = mods[idx]; idx += 1
+            freqs = self._alloc((nf,))
+            self._pack_f32(freqs, [fw.W])
+            emb_dim, kind = 2 * nf, 1
+        else:
+            freqs, emb_dim, kind = None, nf, 0
+        self.emb = self._alloc((N, emb_dim))
+        self._temb_args = dict(freqs=freqs, kind=kind, emb_dim=emb_dim)
+        self._temb_op_index = len(self.ops)
+        self.ops.append(None)   # placeholder, bound in _bind_time_source()
+        lin0, lin1 = mods[idx], mods[idx + 1]; idx += 2
+        w0, b0 = self._alloc((4 * nf, emb_dim)), self._alloc((4 * nf,))
+        w1, b1 = self._alloc((4 * nf, 4 * nf)), self._alloc((4 * nf,))
+        self._pack_f32(w0, [lin0.weight]); self._pack_f32(b0, [lin0.bias])
+        self._pack_f32(w1, [lin1.weight]); self._pack_f32(b1, [lin1.bias])
+        t0, temb = self._alloc((N, 4 * nf)), self._alloc((N, 4 * nf))
+        self._call('indm_linear_f32', self.emb, w0, b0, t0, ctypes.c_int64(N), emb_dim, 4 * nf, 0)
+        self._call('indm_linear_f32', t0, w1, b1, temb, ctypes.c_int64(N), 4 * nf, 4 * nf, 1)
+        res_blocks = [mm for mm in mods if mm.__class__.__name__ == 'ResnetBlockBigGANpp']
+        dense_total = sum(rb.out_ch for rb in res_blocks)
+        self.dense_total = dense_total
+        wd, bd = self._alloc((dense_total, 4 * nf)), self._alloc((dense_total,))
+        self._pack_f32(wd, [rb.Dense_0.weight for rb in res_blocks])
+        self._pack_f32(bd, [rb.Dense_0.bias for rb in res_blocks])
+        self.dense_tab = self._alloc((N, dense_total))
+        self._call('indm_linear_f32', temb, wd, bd, self.dense_tab, ctypes.c_int64(N), 4 * nf, dense_total, 1)
+        dense_off = {}
+        off = 0
+        for rb in res_blocks:
+            dense_off[id(rb)] = off
+            off += rb.out_ch
+
+        # ---------------- stem
+        self.x_in = self._alloc((N, self.ch, S, S))
+        cpad = self.kchunk
+        x_nhwc = self._op_t((N, S, S, cpad))
+        centered = bool(cfg.data.centered)
+        self._call('indm_prep_input', self.x_in, x_nhwc, ctypes.c_int64(N), self.ch, S, S, cpad,
+                   ctypes.c_float(1.0 if centered else 2.0), ctypes.c_float(0.0 if centered else -1.0),
+                   L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
+        stem = mods[idx]; idx += 1
+        wst = self._op_t((9, nf, cpad))
+        self._pack_conv(wst, stem.weight, cin_pad=cpad)
+        bst = self._alloc((nf,)); self._pack_f32(bst, [stem.bias])
+        h0 = self._alloc((N, S, S, nf))
+        self._igemm(a=x_nhwc, N=N, H=S, W=S, Cin=cpad, b=wst, Cout=nf, taps=9, bias=bst, out_f32=h0, out_ld=nf)
+
+        inv_sqrt2 = 1.0 / math.sqrt(2.0)
+
+        def res_block(rb, xa, Ca, xb, Cb, H, W):
+            """returns (out fp32 [N,H',W',Cout], H', W')"""
+            Cin, Cout = rb.in_ch, rb.out_ch
+            assert Cin == Ca + Cb, (Cin, Ca, Cb)
+            has_skip = hasattr(rb, 'Conv_2')
+            resample = 1 if rb.up else (2 if rb.down else 0)
+            use_fir = self.fir and resample != 0
+            h1, raw = self._gn(xa, Ca, xb, Cb, L.DTYPE_F32, H, W, rb.GroupNorm_0, 1, 0 if use_fir else resample,
+                               has_skip and not use_fir)
+            Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
+            if use_fir:
+                assert xb is None, 'FIR resampling blocks never take a concatenated input'
+                k1 = np.asarray(rb.fir_kernel, dtype=np.float32)
+                k1 = k1 / k1.sum() * (2.0 if resample == 1 else 1.0)
+                self.keep.append(k1)
+                kptr = k1.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+                h1r = self._op_t((N, Ho, Wo, Cin))
+                raw = self._op_t((N, Ho, Wo, Cin))
+                odt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32
+                self._call('indm_fir_nhwc', h1, h1r, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32, odt, ctypes.c_int64(N), H, W,
+                           Cin, kptr, resample)
+                self._call('indm_fir_nhwc', xa, raw, L.DTYPE_F32, odt, ctypes.c_int64(N), H, W, Cin, kptr, resample)
+                h1 = h1r
+            # conv0 (+bias +temb row bias) -> h2 (operand dtype), GroupNorm_1 statistics fused when the tile allows
+            w0 = self._op_t((9, Cout, Cin)); self._pack_conv(w0, rb.Conv_0.weight)
+            b0 = self._alloc((Cout,)); self._pack_f32(b0, [rb.Conv_0.bias])
+            h2 = self._op_t((N, Ho, Wo, Cout))
+            G1 = rb.GroupNorm_1.num_groups
+            cpg1 = Cout // G1
+            px = Ho * Wo
+            fuse_stats = (32 % cpg1 == 0) and (Cout % 32 == 0) and (px >= 32) and self.mode == 'bf16'
+            slot1 = self._gn_slot()
+            kw = dict(a=h1, N=N, H=Ho, W=Wo, Cin=Cin, b=w0, Cout=Cout, taps=9, bias=b0,
+                      rowbias=self.dense_tab[:, dense_off[id(rb)]:], rowbias_ld=self.dense_total, out_ld=Cout)
+            if self.mode == 'bf16':
+                kw['out_bf16'] = h2
+            else:
+                kw['out_f32'] = h2
+            if fuse_stats:
+                kw.update(gn_partial=self.gn_part[slot1], gn_cpg=cpg1, gn_groups=G1)
+            self._igemm(**kw)
+            in_dt1 = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+            h3, _ = self._gn(h2, Cout, None, 0, in_dt1, Ho, Wo, rb.GroupNorm_1, 1, 0, False, slot=slot1, stats_done=fuse_stats)
+            # conv1 (+ fused skip 1x1 | + residual), * 1/sqrt(2)
+            w1 = self._op_t((9, Cout, Cout)); self._pack_conv(w1, rb.Conv_1.weight)
+            b1 = self._alloc((Cout,))
+            out = self._alloc((N, Ho, Wo, Cout))
+            kw = dict(a=h3, N=N, H=Ho, W=Wo, Cin=Cout, b=w1, Cout=Cout, taps=9, bias=b1, scale=inv_sqrt2 if rb.skip_rescale else 1.0,
+                      out_f32=out, out_ld=Cout)
+            if has_skip:
+                w2 = self._op_t((Cout, Cin)); self._pack_conv(w2.view(1, Cout, Cin), rb.Conv_2.weight)
+
+                def job(b1=b1, rb=rb):   # one bias vector for both K segments
+                    b1.copy_((rb.Conv_1.bias.detach() + rb.Conv_2.bias.detach()).to(self.dev, torch.float32))
+                self.pack_jobs.append(job)
+                kw.update(a2=raw, Cin2=Cin, b2=w2)
+            else:
+                self._pack_f32(b1, [rb.Conv_1.bias])
+                assert xb is None and Ca == Cout and resample == 0
+                kw.update(residual=xa, res_ld=Cout)
+            self._igemm(**kw)
+            return out, Ho, Wo
+
+        def attn_block(ab, x, C, H, W):
+            Lq = H * W
+            h, _ = self._gn(x, C, None, 0, L.DTYPE_F32, H, W, ab.GroupNorm_0, 0, 0, False)
+            wqkv = self._op_t((3 * C, C))
+            bqkv = self._alloc((3 * C,))
+
+            def job(wqkv=wqkv, bqkv=bqkv, ab=ab):
+                ws = [getattr(ab, f'NIN_{j}').W.detach().to(self.dev, torch.float32).t() for j in range(3)]
+                wqkv.copy_(self._round_op(torch.cat(ws, dim=0)))
+                bqkv.copy_(torch.cat([getattr(ab, f'NIN_{j}').b.detach().to(self.dev, torch.float32) for j in range(3)]))
+            self.pack_jobs.append(job)
+            qk = self._op_t((N, Lq, 2 * C))
+            vt = self._alloc((N, C, Lq), torch.bfloat16) if self.mode == 'bf16' else None
+            if self.mode == 'bf16':
+                self._igemm(a=h, N=N, H=H, W=W, Cin=C, b=wqkv, Cout=3 * C, taps=1, bias=bqkv, out_mode=2, out_bf16=qk,
+                            out_ld=2 * C, tcol0=2 * C, out_t=vt)
+            else:
+                # tf32 validation mode: q,k,v rows in fp32, V transposed by a strided copy (torch plumbing, not timed)
+                qkv = self._alloc((N, Lq, 3 * C))
+                self._igemm(a=h, N=N, H=H, W=W, Cin=C, b=wqkv, Cout=3 * C, taps=1, bias=bqkv, out_f32=qkv, out_ld=3 * C,
+                            round_tf32_out=1)
+                vt = self._alloc((N, C, Lq))
+
+                def tr(qkv=qkv, vt=vt, qk=qk, C=C):
+                    qk.copy_(qkv[:, :, :2 * C])
+                    vt.copy_(qkv[:, :, 2 * C:].transpose(1, 2))
+                self.ops.append(tr)
+            s = self._alloc((N, Lq, Lq))
+            self._igemm(a=qk, a_ld=2 * C, a_img_stride=Lq * 2 * C, N=N, H=1, W=Lq, Cin=C, b=qk[:, :, C:], b_ld=2 * C,
+                        b_tap_stride=Lq * 2 * C, Cout=Lq, taps=1, batched_b=1, scale=float(int(C) ** (-0.5)), out_f32=s, out_ld=Lq)
+            p = self._op_t((N, Lq, Lq))
+            self._call('indm_softmax_rows', s, p, ctypes.c_int64(N * Lq), Lq, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
+            o = self._op_t((N, Lq, C))
+            kw = dict(a=p, N=N, H=1, W=Lq, Cin=Lq, b=vt, Cout=C, taps=1, batched_b=1, out_ld=C)
+            if self.mode == 'bf16':
+                kw['out_bf16'] = o
+            else:
+                kw.update(out_f32=o, round_tf32_out=1)
+            self._igemm(**kw)
+            w3 = self._op_t((C, C))
+            b3 = self._alloc((C,))
+
+            def job3(w3=w3, b3=b3, ab=ab):
+                w3.copy_(self._round_op(ab.NIN_3.W.detach().to(self.dev, torch.float32).t().contiguous()))
+                b3.copy_(ab.NIN_3.b.detach().to(self.dev, torch.float32))
+            self.pack_jobs.append(job3)
+            out = self._alloc((N, H, W, C))
+            self._igemm(a=o, N=N, H=H, W=W, Cin=C, b=w3, Cout=C, taps=1, bias=b3, residual=x, res_ld=C,
+                        scale=inv_sqrt2 if ab.skip_rescale else 1.0, out_f32=out, out_ld=C)
+            return out
+
+        # ---------------- down path
+        nlev = len(cfg.model.ch_mult)
+        attn_res = tuple(cfg.model.attn_resolutions)
+        pin = cfg.model.progressive_input.lower()
+        if pin != 'none':
+            raise NotImplementedError("progressive_input='residual' (VE configs): strided pyramid conv lands next")
+        hs = [(h0, nf)]
+        H = W = S
+        for lv in range(nlev):
+            for _ in range(cfg.model.num_res_blocks):
+                x, Cx = hs[-1]
+                rb = mods[idx]; idx += 1
+                h, H, W = res_block(rb, x, Cx, None, 0, H, W)
+                Ch = rb.out_ch
+                if H in attn_res and cfg.model.attention:
+                    h = attn_block(mods[idx], h, Ch, H, W); idx += 1
+                hs.append((h, Ch))
+            if lv != nlev - 1:
+                x, Cx = hs[-1]
+                rb = mods[idx]; idx += 1
+                h, H, W = res_block(rb, x, Cx, None, 0, H, W)
+                hs.append((h, rb.out_ch))
+        h, Ch = hs[-1]
+        rb = mods[idx]; idx += 1
+        h, H, W = res_block(rb, h, Ch, None, 0, H, W)
+        h = attn_block(mods[idx], h, Ch, H, W); idx += 1
+        rb = mods[idx]; idx += 1
+        h, H, W = res_block(rb, h, Ch, None, 0, H, W)
+        # ---------------- up path
+        for lv in reversed(range(nlev)):
+            for _ in range(cfg.model.num_res_blocks + 1):
+                skip, Cs = hs.pop()
+                rb = mods[idx]; idx += 1
+                h, H, W = res_block(rb, h, Ch, skip, Cs, H, W)
+                Ch = rb.out_ch
+            if H in attn_res and cfg.model.attention:
+                h = attn_block(mods[idx], h, Ch, H, W); idx += 1
+            if lv != 0:
+                rb = mods[idx]; idx += 1
+                h, H, W = res_block(rb, h, Ch, None, 0, H, W)
+                Ch = rb.out_ch
+        assert not hs
+        # ---------------- head: GroupNorm + SiLU + conv3x3 -> NCHW fp32, optional per-sample output scale
+        gnh = mods[idx]; idx += 1
+        hh, _ = self._gn(h, Ch, None, 0, L.DTYPE_F32, H, W, gnh, 1, 0, False)
+        head = mods[idx]; idx += 1
+        assert idx == len(mods)
+        wh = self._op_t((9, self.ch, Ch)); self._pack_conv(wh, head.weight)
+        bh = self._alloc((self.ch,)); self._pack_f32(bh, [head.bias])
+        self.out = self._alloc((N, self.ch, S, S))
+        self.out_scale = self._alloc((N,))
+        self.out_scale.fill_(1.0)
+        self._igemm(a=hh, N=N, H=H, W=W, Cin=Ch, b=wh, Cout=self.ch, taps=9, bias=bh, rowscale=self.out_scale, out_mode=1,
+                    out_f32=self.out)
+        self._bind_time_source(None, None, 0, 0)
+
+    def _bind_time_source(self, sched, step, sched_ld, sched_col):
+        """time embedding reads `self.time_cond[n]`, or a device schedule table row `*step` (sampler graphs)."""
+        a = self._temb_args
+        fn = L.lib().indm_time_embedding
+        args = [ctypes.c_void_p(self.time_cond.data_ptr()),
+                ctypes.c_void_p(sched.data_ptr()) if sched is not None else None,
+                ctypes.c_void_p(step.data_ptr()) if step is not None else None, sched_ld, sched_col,
+                ctypes.c_void_p(a['freqs'].data_ptr()) if a['freqs'] is not None else None, a['kind'],
+                ctypes.c_int64(self.N), a['emb_dim'], ctypes.c_void_p(self.emb.data_ptr())]
+
+        def run():
+            L.check(fn(*args, L._stream()), 'indm_time_embedding')
+        self.ops[self._temb_op_index] = run
+        self.keep.append((sched, step))
+
+    # ------------------------------------------------------------------ execution
+    def launch(self):
+        """enqueue the whole forward on the current stream (inputs: self.x_in, self.time_cond / schedule, self.out_scale)"""
+        for op in self.ops:
+            op()
+
+    def forward(self, x, time_cond, out_scale=None):
+        if x.shape[0] != self.N:
+            raise ValueError(f'engine was built for batch {self.N}, got {x.shape[0]}')
+        if self._weights_version != self.weights_version():
+            self.load_weights()
+        self.x_in.copy_(x)
+        self.time_cond.copy_(time_cond)
+        if out_scale is None:
+            self.out_scale.fill_(1.0)
+        else:
+            self.out_scale.copy_(out_scale)
+        self.launch()
+        return self.out
+
+    @property
+    def num_launches(self):
+        return len(self.ops)

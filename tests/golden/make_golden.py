@@ -23,7 +23,7 @@ from oracle import ref_loader as rl  # noqa: E402
 from oracle import ncsnpp as oncsnpp  # noqa: E402
 
 
-def tiny(cfg, nf=64):
+def tiny(cfg, nf=128):
     """Shrink a reference config to a fast test size (same code paths)."""
     cfg.model.nf = nf
     cfg.model.ch_mult = (1, 2)

@@ -16,7 +16,7 @@ def load_json(name):
         return json.load(f)
 
 
-def tiny(cfg, nf=64):
+def tiny(cfg, nf=128):
     """Same shrink as tests/golden/make_golden.py:tiny."""
     cfg.model.nf = nf
     cfg.model.ch_mult = (1, 2)

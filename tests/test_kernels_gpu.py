@@ -17,6 +17,24 @@ from indm_b200 import _lib as L  # noqa: E402
 DEV = 'cuda'
 
 
+_KEEP = []
+
+
+def D(t):
+    """tensor -> device, kept alive until the test module is torn down (the C ABI sees raw pointers only)"""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(t)
+    t = t.to(DEV)
+    _KEEP.append(t)
+    return t
+
+
+def P(t):
+    return L.ptr(D(t))
+
+
 def bf16r(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
@@ -197,8 +215,8 @@ def test_groupnorm_silu_resample(in_dt, out_dt, Ca, Cb, S, res, act):
     tout = torch.bfloat16 if out_dt == L.DTYPE_BF16 else torch.float32
     out = torch.zeros((N, So, So, C), device=DEV, dtype=tout)
     raw = torch.zeros((N, So, So, C), device=DEV, dtype=tout)
-    L.call('indm_gn_apply', L.ptr(xa_d), Ca, L.ptr(xb_d), Cb, in_dt, N, S, S, G, L.ptr(part), L.ptr(gamma.to(DEV)),
-           L.ptr(beta.to(DEV)), 1e-6, act, res, L.ptr(out), L.ptr(raw), out_dt)
+    L.call('indm_gn_apply', L.ptr(xa_d), Ca, L.ptr(xb_d), Cb, in_dt, N, S, S, G, L.ptr(part), P(gamma),
+           P(beta), 1e-6, act, res, L.ptr(out), L.ptr(raw), out_dt)
     torch.cuda.synchronize()
     x = torch.cat([xa, xb], dim=-1) if Cb else xa
     xc = x.permute(0, 3, 1, 2).double()
@@ -221,9 +239,9 @@ def test_groupnorm_silu_resample(in_dt, out_dt, Ca, Cb, S, res, act):
 def test_softmax_rows(cols):
     s = rnd(37, cols, seed=26) * 3
     out = torch.zeros((37, cols), device=DEV, dtype=torch.bfloat16)
-    L.call('indm_softmax_rows', L.ptr(s.to(DEV)), L.ptr(out), 37, cols, L.DTYPE_BF16)
+    L.call('indm_softmax_rows', P(s), L.ptr(out), 37, cols, L.DTYPE_BF16)
     out32 = torch.zeros((37, cols), device=DEV)
-    L.call('indm_softmax_rows', L.ptr(s.to(DEV)), L.ptr(out32), 37, cols, L.DTYPE_F32)
+    L.call('indm_softmax_rows', P(s), L.ptr(out32), 37, cols, L.DTYPE_F32)
     torch.cuda.synchronize()
     want = torch.softmax(s.double(), dim=-1)
     assert rel_l2(out.float().cpu(), want) < 4e-3
@@ -233,7 +251,7 @@ def test_softmax_rows(cols):
 def test_prep_input_and_time_embedding_and_linear():
     x = rnd(3, 3, 8, 8, seed=27)
     out = torch.full((3, 8, 8, 64), 7.0, device=DEV, dtype=torch.bfloat16)
-    L.call('indm_prep_input', L.ptr(x.to(DEV)), L.ptr(out), 3, 3, 8, 8, 64, 2.0, -1.0, L.DTYPE_BF16)
+    L.call('indm_prep_input', P(x), L.ptr(out), 3, 3, 8, 8, 64, 2.0, -1.0, L.DTYPE_BF16)
     torch.cuda.synchronize()
     want = torch.zeros(3, 8, 8, 64)
     want[..., :3] = nhwc(2 * x - 1)
@@ -242,7 +260,7 @@ def test_prep_input_and_time_embedding_and_linear():
     # positional embedding, models/layers.py:515-529
     t = torch.tensor([0.0, 1.7, 333.3, 999.0])
     emb = torch.zeros((4, 128), device=DEV)
-    L.call('indm_time_embedding', L.ptr(t.to(DEV)), None, None, 0, 0, None, 0, 4, 128, L.ptr(emb))
+    L.call('indm_time_embedding', P(t), None, None, 0, 0, None, 0, 4, 128, L.ptr(emb))
     half = 64
     e = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
     arg = t[:, None] * e[None, :]
@@ -253,7 +271,7 @@ def test_prep_input_and_time_embedding_and_linear():
     sig = torch.tensor([0.01, 0.5, 3.0, 50.0])
     Wf = rnd(64, seed=28) * 16
     emb = torch.zeros((4, 128), device=DEV)
-    L.call('indm_time_embedding', L.ptr(sig.to(DEV)), None, None, 0, 0, L.ptr(Wf.to(DEV)), 1, 4, 128, L.ptr(emb))
+    L.call('indm_time_embedding', P(sig), None, None, 0, 0, P(Wf), 1, 4, 128, L.ptr(emb))
     xp = torch.log(sig)[:, None] * Wf[None, :] * 2 * np.pi
     want = torch.cat([torch.sin(xp), torch.cos(xp)], dim=-1)
     torch.cuda.synchronize()
@@ -261,7 +279,7 @@ def test_prep_input_and_time_embedding_and_linear():
     # dense
     inp, w, b = rnd(5, 512, seed=29), rnd(300, 512, seed=30) / 22, rnd(300, seed=31)
     o = torch.zeros((5, 300), device=DEV)
-    L.call('indm_linear_f32', L.ptr(inp.to(DEV)), L.ptr(w.to(DEV)), L.ptr(b.to(DEV)), L.ptr(o), 5, 512, 300, 1)
+    L.call('indm_linear_f32', P(inp), P(w), P(b), L.ptr(o), 5, 512, 300, 1)
     torch.cuda.synchronize()
     want = F.linear(F.silu(inp.double()), w.double(), b.double())
     assert rel_l2(o.cpu(), want) < 1e-5
@@ -281,7 +299,7 @@ def test_fir_nhwc_matches_oracle_upfirdn2d(mode):
     So = want.shape[-1]
     out = torch.zeros((N, So, So, Cc), device=DEV)
     import ctypes
-    L.call('indm_fir_nhwc', L.ptr(nhwc(x).to(DEV)), L.ptr(out), L.DTYPE_F32, L.DTYPE_F32, N, S, S, Cc,
+    L.call('indm_fir_nhwc', P(nhwc(x)), L.ptr(out), L.DTYPE_F32, L.DTYPE_F32, N, S, S, Cc,
            kk.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), mode)
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), nhwc(torch.from_numpy(want))) < 1e-6
@@ -298,7 +316,7 @@ def test_pc_update_kernels_match_oracle():
     beta, alpha = float(sde.discrete_betas[ts]), float(sde.alphas[ts])
     coef = torch.tensor([[2 - math.sqrt(alpha), beta, math.sqrt(beta), 0.0]])
     xd, xm = x.clone().to(DEV), torch.zeros_like(x).to(DEV)
-    L.call('indm_pc_predictor_update', L.ptr(xd), L.ptr(s.to(DEV)), L.ptr(z.to(DEV)), L.ptr(xm), L.ptr(coef.to(DEV)), 4, None,
+    L.call('indm_pc_predictor_update', L.ptr(xd), P(s), P(z), L.ptr(xm), P(coef), 4, None,
            N, D, 0, 0)
     torch.cuda.synchronize()
     assert rel_l2(xd.cpu(), want_x) < 1e-6 and rel_l2(xm.cpu(), want_mean) < 1e-6
@@ -306,10 +324,10 @@ def test_pc_update_kernels_match_oracle():
     ve = osde.VE()
     want_x, want_mean = osampler.langevin_update(ve, s, x, t, z, 0.16)
     norms = torch.zeros((N, 2), device=DEV)
-    L.call('indm_langevin_norms', L.ptr(s.to(DEV)), L.ptr(z.to(DEV)), L.ptr(norms), None, N, D, 0, 0)
+    L.call('indm_langevin_norms', P(s), P(z), L.ptr(norms), None, N, D, 0, 0)
     coef = torch.tensor([[1.0, 0.16]])
     xd, xm = x.clone().to(DEV), torch.zeros_like(x).to(DEV)
-    L.call('indm_langevin_update', L.ptr(xd), L.ptr(s.to(DEV)), L.ptr(z.to(DEV)), L.ptr(xm), L.ptr(norms), L.ptr(coef.to(DEV)), 2,
+    L.call('indm_langevin_update', L.ptr(xd), P(s), P(z), L.ptr(xm), L.ptr(norms), P(coef), 2,
            None, N, D, 0, 0)
     torch.cuda.synchronize()
     assert rel_l2(xd.cpu(), want_x) < 1e-5 and rel_l2(xm.cpu(), want_mean) < 1e-5
@@ -334,7 +352,7 @@ def test_philox_normal_stream_statistics_and_replay():
     L.call('indm_langevin_norms', L.ptr(s), None, L.ptr(norms), None, N, D, 77, 1)
     x0 = torch.zeros((N, D), device=DEV)
     coef = torch.tensor([[1.0, 0.16]], device=DEV)
-    L.call('indm_langevin_update', L.ptr(x0), L.ptr(torch.zeros_like(s)), None, None, L.ptr(norms), L.ptr(coef), 2, None, N, D, 77, 1)
+    L.call('indm_langevin_update', L.ptr(x0), P(torch.zeros_like(s)), None, None, L.ptr(norms), L.ptr(coef), 2, None, N, D, 77, 1)
     torch.cuda.synchronize()
     # with s = 0 in the update, x = sqrt(2 eps) z  =>  |x_n|^2 / (2 eps) == |z_n|^2 from the norms kernel
     r = 0.16 * norms[:, 1].sqrt().mean() / norms[:, 0].sqrt().mean()
@@ -354,7 +372,7 @@ def test_upfirdn2d_c_abi_against_reference_golden(case):
     x, k, want = g[f'upfirdn_{case}_x'], g[f'upfirdn_{case}_k'], g[f'upfirdn_{case}_y']
     n, c, h, w = x.shape
     y = torch.full(want.shape, float('nan'), device=DEV)
-    L.call('indm_upfirdn2d_f32', L.ptr(torch.from_numpy(x).to(DEV)), L.ptr(torch.from_numpy(k).to(DEV)), L.ptr(y), n * c, h, w,
+    L.call('indm_upfirdn2d_f32', P(x), P(k), L.ptr(y), n * c, h, w,
            k.shape[0], k.shape[1], up, up, down, down, p0, p1, p0, p1)
     torch.cuda.synchronize()
     # north_star: upfirdn2d within 1e-6 relative in FP32
@@ -368,13 +386,13 @@ def test_bias_act_c_abi_against_reference_golden(case):
     x, b, want = g[f'lrelu_{case}_x'], g[f'lrelu_{case}_b'], g[f'lrelu_{case}_y']
     step = int(np.prod(x.shape[2:]))
     y = torch.zeros(x.shape, device=DEV)
-    L.call('indm_bias_act_f32', L.ptr(torch.from_numpy(x).to(DEV)), L.ptr(torch.from_numpy(b).to(DEV)), None, L.ptr(y), x.size,
+    L.call('indm_bias_act_f32', P(x), P(b), None, L.ptr(y), x.size,
            b.shape[0], step, 3, 0, 0.2, 2 ** 0.5)
     torch.cuda.synchronize()
     assert rel_l2(y.cpu(), torch.from_numpy(want)) < 1e-6
     # backward: grad=1 with ref = forward output
     gy, want_gx = g[f'lrelu_{case}_gy'], g[f'lrelu_{case}_gx']
     gx = torch.zeros(x.shape, device=DEV)
-    L.call('indm_bias_act_f32', L.ptr(torch.from_numpy(gy).to(DEV)), None, L.ptr(y), L.ptr(gx), x.size, 1, 1, 3, 1, 0.2, 2 ** 0.5)
+    L.call('indm_bias_act_f32', P(gy), None, L.ptr(y), L.ptr(gx), x.size, 1, 1, 3, 1, 0.2, 2 ** 0.5)
     torch.cuda.synchronize()
     assert rel_l2(gx.cpu(), torch.from_numpy(want_gx)) < 1e-6

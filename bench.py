@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of record for the INDM hot path on B200.
+
+Workload (BASELINE.json configs[1]): configs/vp/CIFAR10/indm_fid.py — DDPM++ (NCSN++ nres=4, nf=128) VP latent score
+network + wolf flow — with the overrides sampling.method=pc, predictor=reverse_diffusion, corrector=none (SURVEY.md §0
+fact 3), 1000 predictor steps, batch 1024 batch-sharded over 8 GPUs = 128 images per GPU (weak scaling: every rank
+samples its own 128 images, no data-path collective).  Synthetic data, random-init weights (seeded).
+
+One "step" = one complete `pc_sampler` call on the rank's batch: 1000 x (score-network forward + fused predictor update)
+followed by the flow inverse.  `value` = images/s with the prior sample already resident in HBM; `e2e` = the same metric
+through the public API `sampling.get_pc_sampler(...)(model, flow_model)` with the prior drawn on the host (pinned) and
+copied in, and the samples copied back, every step.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                   CPU arm: the oracle port of the reference's PyTorch CPU path
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pc_sampling_images_per_sec"
+UNIT = "images/s"
+PER_GPU_BATCH = 128
+NUM_SCALES = 1000
+GFLOP_PER_IMAGE_FWD = 21.69      # score-net forward, CIFAR nres=4 (2*MAC, forward hooks on the reference)
+
+
+def workload_config(device):
+    from indm_b200 import configs
+    cfg = configs.get_config("vp/CIFAR10/indm_fid")
+    cfg.sampling.method = "pc"
+    cfg.sampling.predictor = "reverse_diffusion"
+    cfg.sampling.corrector = "none"
+    cfg.sampling.num_scales = NUM_SCALES
+    cfg.device = device
+    return cfg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(threads, n_pc=2, batch=16, repeats=1):
+    """Bounded sample of the same workload on the host: `n_pc` reverse-diffusion PC steps of the oracle port (PyTorch CPU
+    FP32 restatement of the reference, oracle/) at batch `batch`; extrapolated to the 1000-step figure."""
+    import numpy as np
+    import torch
+    from oracle import ncsnpp as oncsnpp, sde as osde, sampler as osampler
+    torch.set_num_threads(threads)
+    cfg = workload_config(torch.device("cpu"))
+    params = oncsnpp.to_torch(oncsnpp.synth_params(cfg, 0))
+    sde = osde.get_sde(cfg)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, 32, 32, generator=g)
+    noises = [torch.randn(batch, 3, 32, 32, generator=g) for _ in range(n_pc)]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            osampler.pc_sampler(sde, lambda a, b: oncsnpp.score_fn(cfg, sde, params, a, b), x, noises, n_pc, 1e-5, cfg.sampling.snr)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    per_step = best / n_pc
+    return batch / (per_step * NUM_SCALES), f"{n_pc} PC steps (1 NFE each) of the oracle port at batch {batch}, FP32, extrapolated x{NUM_SCALES // n_pc}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, sample = cpu_sample(threads, n_pc=2, batch=16)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": PER_GPU_BATCH / value * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "vp/CIFAR10/indm_fid + pc/reverse_diffusion/none, 1000 steps (CPU arm: bounded sample)"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
+def conv_roofline(net, eng, reps=3):
+    """Average achieved TFLOP/s of the dominant kernel (igemm) over one eager forward, CUDA events around every launch."""
+    import torch
+    for _ in range(2):
+        eng.launch()
+    torch.cuda.synchronize()
+    tot_ms, tot_fl, n_launch = 0.0, 0.0, 0
+    for _ in range(reps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(eng.ops) + 1)]
+        evs[0].record()
+        for i, op in enumerate(eng.ops):
+            op()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i, op in enumerate(eng.ops):
+            d = None
+            for c in (op.__closure__ or ()):
+                if c.cell_contents.__class__.__name__ == "IgemmDesc":
+                    d = c.cell_contents
+            if d is None:
+                continue
+            tot_ms += evs[i].elapsed_time(evs[i + 1])
+            tot_fl += 2.0 * d.N * d.H * d.W * d.Cout * (d.Cin * d.taps + (d.Cin2 if d.a2 else 0))
+            n_launch += 1
+    return tot_fl / (tot_ms * 1e-3) / 1e12, tot_ms / n_launch, n_launch // reps
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from indm_b200 import sde_lib, sampling, _lib as L
+    from indm_b200.models import utils as mutils
+    from indm_b200.flow_models import flow_model as fm
+
+    cfg = workload_config(dev)
+    flow_note = "wolf"
+    torch.manual_seed(0)
+    model = mutils.create_model(cfg)
+    net = model.module
+    # random-init weights of that architecture; the ~0-initialised tensors (init_scale=0) get ordinary magnitudes so the
+    # network output is not identically ~0
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if p_.dim() > 1 and float(p_.abs().max()) < 1e-6:
+                fan = p_[0].numel() + p_.shape[0] * (p_[0, 0].numel() if p_.dim() > 2 else 1)
+                p_.uniform_(-1, 1).mul_((6.0 / fan) ** 0.5)
+    try:
+        flow = fm.create_flow_model(cfg)
+    except NotImplementedError:
+        cfg.flow.model = "identity"
+        flow, flow_note = None, "identity (wolf flow inverse not built yet — number excludes it)"
+    sde = sde_lib.get_sde(cfg)
+    shape = (PER_GPU_BATCH, 3, 32, 32)
+    sampler = sampling.get_pc_sampler(cfg, sde, shape, sampling.ReverseDiffusionPredictor, sampling.NoneCorrector, lambda v: (v + 1.) / 2.,
+                                      cfg.sampling.snr, n_steps=1, probability_flow=False, continuous=True, denoise=True,
+                                      eps=cfg.sampling.truncation_time, device=dev)
+    prior_dev = torch.randn(shape, device=dev)
+    prior_host = torch.randn(shape).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, (L.launches - l0)
+
+    def step_resident():
+        sampler(model, flow, prior=prior_dev, seed=1)
+
+    def step_e2e():
+        x0 = prior_host.to(dev, non_blocking=True)
+        b, a, _ = sampler(model, flow, prior=x0, seed=1)
+        return a.cpu()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches = timed(step_resident, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * PER_GPU_BATCH / (ms_step * 1e-3)
+    e2e = world * PER_GPU_BATCH / (ms_e2e * 1e-3)
+    pk, pk_kind = peaks()
+    eng = net.engine(PER_GPU_BATCH)
+    tf, ms_launch, n_ig = conv_roofline(net, eng)
+    peak_tf = pk["bf16_tflops_sustained"]
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "vp/CIFAR10/indm_fid (DDPM++ nres=4 nf=128) + sampling.method=pc predictor=reverse_diffusion "
+                               "corrector=none, 1000 steps, 128 images per GPU (1024 / 8 GPUs); step = one full pc_sampler call",
+                   "flow": flow_note, "per_gpu_batch": PER_GPU_BATCH, "num_scales": NUM_SCALES,
+                   "l2_policy": "inputs larger than L2 (activations ~5 GB per forward), no flush",
+                   "noise": "in-kernel Philox4x32-10 (no noise tensor in HBM)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": prior_host.numel() * 4, "d2h_bytes_per_step": prior_host.numel() * 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                     "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/GEMM)", "peak_source": pk_kind + " bf16_tflops_sustained",
+                     "launches_per_forward": n_ig, "avg_launch_ms": ms_launch,
+                     "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD},
+    }
+    if world == 1:
+        v, sample = cpu_sample(os.cpu_count() or 1, n_pc=2, batch=16)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -129,10 +129,11 @@ int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, i
 int indm_time_embedding(const float* time_cond, const float* sched, const int32_t* step, int sched_ld, int sched_col,
                         const float* freqs, int kind, int64_t N, int dim, float* out, void* stream);
 
-/* out[n][o] = bias[o] + sum_k f(in[n][k]) * w[o][k], f = SiLU if act_in else identity (nn.Linear in the temb MLP,
- * models/ncsnpp.py:270-274, and all ResnetBlock Dense_0 layers at once, models/layerspp.py:276). FP32. */
-int indm_linear_f32(const float* in, const float* w, const float* bias, float* out, int64_t N, int K, int O, int act_in,
-                    void* stream);
+/* out[n][o] = g(bias[o] + sum_k f(in[n][k]) * w[o][k]), f / g = SiLU if act_in / act_out else identity (the nn.Linear
+ * layers of the temb MLP, models/ncsnpp.py:270-274).  FP32 math; out stored as out_dtype (F32, BF16, or TF32-rounded
+ * fp32) so it can feed the tensor-core GEMM that evaluates all Dense_0 layers at once (models/layerspp.py:276). */
+int indm_linear_f32(const float* in, const float* w, const float* bias, void* out, int64_t N, int K, int O, int act_in,
+                    int act_out, int out_dtype, void* stream);
 
 /* FIR resampling of an NHWC tensor with the separable kernel outer(k1,k1)/sum^2*gain (models/up_or_down_sampling.py:195-257):
  * mode 1: upsample_2d (up 2, pad (2,1), gain 4); mode 2: downsample_2d (down 2, pad (1,1));
@@ -148,20 +149,22 @@ int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N
 
 /* x_mean = a*x + c*s ;  x = x_mean + d*z.   (a, c, d) = coef[0..2] of row (*step) of a [steps][coef_ld] device table
  * (step may be NULL = row 0).  z = NULL -> standard normal noise generated in-kernel (Philox4x32-10, counter =
- * (seed, *step or rng_offset, element)).  x is updated in place; x_mean (optional) receives the noise-free state. */
+ * (seed, *step, rng_offset, element); seed_dev != NULL: the seed is read from device memory instead, so a captured
+ * CUDA graph can be replayed with a new seed).  x is updated in place; x_mean (optional) receives the noise-free state. */
 int indm_pc_predictor_update(float* x, const float* s, const float* z, float* x_mean, const float* coef, int coef_ld,
-                             const int32_t* step, int64_t N, int64_t D, uint64_t seed, uint64_t rng_offset, void* stream);
+                             const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
+                             uint64_t rng_offset, void* stream);
 
 /* per-sample sums of squares: out[n][0] = |s_n|^2, out[n][1] = |z_n|^2 (z NULL -> the Philox noise the following
  * indm_langevin_update call with the same seed/offset will draw). */
 int indm_langevin_norms(const float* s, const float* z, float* out, const int32_t* step, int64_t N, int64_t D, uint64_t seed,
-                        uint64_t rng_offset, void* stream);
+                        const uint64_t* seed_dev, uint64_t rng_offset, void* stream);
 
 /* step = 2*alpha*(snr * mean_n|z_n| / mean_n|s_n|)^2 ; x_mean = x + step*s ; x = x_mean + sqrt(2 step) z.
  * (alpha, snr) = coef[0..1] of row (*step). */
 int indm_langevin_update(float* x, const float* s, const float* z, float* x_mean, const float* norms, const float* coef,
-                         int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, uint64_t rng_offset,
-                         void* stream);
+                         int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
+                         uint64_t rng_offset, void* stream);
 
 /* *step += 1 (device-side step counter advanced inside the captured graph) */
 int indm_advance_step(int32_t* step, void* stream);

@@ -49,11 +49,11 @@ _SIGS = {
     "indm_softmax_rows": [_vp, _vp, _i64, C.c_int, C.c_int, _vp],
     "indm_prep_input": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _f32, C.c_int, _vp],
     "indm_time_embedding": [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp],
-    "indm_linear_f32": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_linear_f32": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "indm_fir_nhwc": [_vp, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, _vp],
-    "indm_pc_predictor_update": [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _u64, _vp],
-    "indm_langevin_norms": [_vp, _vp, _vp, _vp, _i64, _i64, _u64, _u64, _vp],
-    "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _u64, _vp],
+    "indm_pc_predictor_update": [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
+    "indm_langevin_norms": [_vp, _vp, _vp, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
+    "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
     "indm_advance_step": [_vp, _vp],
     "indm_randn_f32": [_vp, _i64, _u64, _u64, _vp],
     "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],

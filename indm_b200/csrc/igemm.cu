@@ -56,6 +56,30 @@ struct IgemmParams {
   int gn_groups;
 };
 
+// per-(image, group) sum / sum-of-squares of one 32-column slab held in registers (static indexing only: a dynamic
+// index would push the whole slab to local memory)
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate(const float (&f)[32], bool row_ok, bool as_bf16, int lane, int c0, float* dst) {
+#pragma unroll
+  for (int g0 = 0; g0 < 32; g0 += CPG) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) {
+      float t = f[g0 + i];
+      if (as_bf16) t = __bfloat162float(__float2bfloat16_rn(t));
+      s += t;
+      q += t * t;
+    }
+    if (!row_ok) s = q = 0.f;
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0 && dst) {
+      atomicAdd(dst + (c0 + g0) / CPG * 2, s);
+      atomicAdd(dst + (c0 + g0) / CPG * 2 + 1, q);
+    }
+  }
+}
+
 template <int BLOCK_N, bool TF32>
 __global__ void __launch_bounds__(128, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -302,27 +326,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // GroupNorm statistics of the tensor just produced, accumulated per (image, group): removes the separate
       // statistics pass over HBM for the GroupNorm that consumes this output (models/layerspp.py:244,277).
       // Requires all 32 rows of a warp to belong to one image (BW*BH >= 32 or BN == 1) — checked on the host.
-      const int cpg = p.gn_cpg;
-      for (int g0 = 0; g0 < 32; g0 += cpg) {
-        float s = 0.f, q = 0.f;
-        if (row_ok) {
-          for (int i = 0; i < cpg; ++i) {
-            float t = f[g0 + i];
-            if (p.out_bf16 && !p.out_f32) t = __bfloat162float(__float2bfloat16_rn(t));
-            s += t;
-            q += t * t;
-          }
-        }
-        s = warp_sum(s);
-        q = warp_sum(q);
-        if (lane == 0 && c0 + g0 < p.Cout) {
-          const int nn = n0 + (warp * 32) / (p.BW * p.BH);
-          if (nn < p.N) {
-            float* dst = p.gn_partial + ((long long)nn * p.gn_groups + (c0 + g0) / cpg) * 2;
-            atomicAdd(dst, s);
-            atomicAdd(dst + 1, q);
-          }
-        }
+      const bool as_bf16 = p.out_bf16 && !p.out_f32;
+      const int nn = n0 + (warp * 32) / (p.BW * p.BH);
+      float* dst = (nn < p.N) ? p.gn_partial + (long long)nn * p.gn_groups * 2 : nullptr;
+      switch (p.gn_cpg) {
+        case 4: gn_accumulate<4>(f, row_ok, as_bf16, lane, c0, dst); break;
+        case 8: gn_accumulate<8>(f, row_ok, as_bf16, lane, c0, dst); break;
+        case 16: gn_accumulate<16>(f, row_ok, as_bf16, lane, c0, dst); break;
+        default: gn_accumulate<32>(f, row_ok, as_bf16, lane, c0, dst); break;
       }
     }
   }
@@ -388,7 +399,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   IgemmParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
   // ---- spatial box of 128 pixels
-  if (d->W >= 128) {
+  if (d->W >= 128 || (d->H == 1 && d->N == 1)) {
+    // rows of one image line (or a plain [M,K] GEMM): 128 consecutive pixels, the ragged last tile is zero-filled / masked
     INDM_CHECK_ARG(d->H == 1 || d->W % 128 == 0, "igemm: W >= 128 needs H == 1 or W %% 128 == 0");
     p.BW = 128; p.BH = 1; p.BN = 1;
   } else {
@@ -434,7 +446,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   if (d->out_mode != 1 && (d->out_f32 || d->out_bf16))
     INDM_CHECK_ARG(d->out_ld >= 1, "igemm: out_ld missing");
   if (d->gn_partial) {
-    INDM_CHECK_ARG(d->gn_cpg >= 1 && 32 % d->gn_cpg == 0 && d->Cout % 32 == 0,
+    INDM_CHECK_ARG((d->gn_cpg == 4 || d->gn_cpg == 8 || d->gn_cpg == 16 || d->gn_cpg == 32) && d->Cout % 32 == 0,
                    "igemm: fused GroupNorm statistics need cpg | 32 and Cout %% 32 == 0 (cpg=%d Cout=%d)", d->gn_cpg, d->Cout);
     INDM_CHECK_ARG(p.BN == 1 || p.BW * p.BH >= 32, "igemm: fused GroupNorm statistics need >= 32 pixels per image per tile");
   }

@@ -43,8 +43,10 @@ __device__ __forceinline__ float4 load_or_draw(const float* z, long long i4, uin
 
 __global__ void predictor_update_kernel(float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ z,
                                         float* __restrict__ x_mean, const float* __restrict__ coef, int coef_ld,
-                                        const int32_t* __restrict__ step, long long total4, uint64_t seed, uint32_t off) {
+                                        const int32_t* __restrict__ step, long long total4, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                        uint32_t off) {
   const int st = step ? *step : 0;
+  if (seed_dev) seed = *seed_dev;
   const float a = coef[(long long)st * coef_ld + 0], c = coef[(long long)st * coef_ld + 1], d = coef[(long long)st * coef_ld + 2];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const float4 xv = reinterpret_cast<const float4*>(x)[i];
@@ -58,8 +60,10 @@ __global__ void predictor_update_kernel(float* __restrict__ x, const float* __re
 
 // grid (chunks, N): per-sample partial sums of squares, warp-shuffle + one atomic per warp
 __global__ void langevin_norms_kernel(const float* __restrict__ s, const float* __restrict__ z, float* __restrict__ out,
-                                      const int32_t* __restrict__ step, long long D4, uint64_t seed, uint32_t off) {
+                                      const int32_t* __restrict__ step, long long D4, uint64_t seed,
+                                      const uint64_t* __restrict__ seed_dev, uint32_t off) {
   const int st = step ? *step : 0;
+  if (seed_dev) seed = *seed_dev;
   const long long n = blockIdx.y;
   float ss = 0.f, zz = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < D4; i += (long long)gridDim.x * blockDim.x) {
@@ -80,9 +84,10 @@ __global__ void langevin_norms_kernel(const float* __restrict__ s, const float* 
 __global__ void langevin_update_kernel(float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ z,
                                        float* __restrict__ x_mean, const float* __restrict__ norms, const float* __restrict__ coef,
                                        int coef_ld, const int32_t* __restrict__ step, int N, long long total4, uint64_t seed,
-                                       uint32_t off) {
+                                       const uint64_t* __restrict__ seed_dev, uint32_t off) {
   __shared__ float sh[2];
   const int st = step ? *step : 0;
+  if (seed_dev) seed = *seed_dev;
   // batch means of the per-sample L2 norms (sampling.py:286-287): N is small, every CTA recomputes them
   if (threadIdx.x < 32) {
     float gs = 0.f, gz = 0.f;
@@ -136,20 +141,20 @@ inline int ew_grid(long long work) {
 }  // namespace
 
 extern "C" int indm_pc_predictor_update(float* x, const float* s, const float* z, float* x_mean, const float* coef, int coef_ld,
-                                        const int32_t* step, int64_t N, int64_t D, uint64_t seed, uint64_t rng_offset,
-                                        void* stream_) {
+                                        const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
+                                        uint64_t rng_offset, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(x && s && coef && N > 0 && D > 0 && coef_ld >= 3, "pc_predictor_update: bad arguments");
   INDM_CHECK_ARG((N * D) % 4 == 0, "pc_predictor_update: N*D must be a multiple of 4");
   const long long total4 = N * D / 4;
-  predictor_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, coef, coef_ld, step, total4, seed,
+  predictor_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, coef, coef_ld, step, total4, seed, seed_dev,
                                                               (uint32_t)rng_offset);
   INDM_CHECK_LAUNCH("pc_predictor_update");
   return INDM_OK;
 }
 
 extern "C" int indm_langevin_norms(const float* s, const float* z, float* out, const int32_t* step, int64_t N, int64_t D,
-                                   uint64_t seed, uint64_t rng_offset, void* stream_) {
+                                   uint64_t seed, const uint64_t* seed_dev, uint64_t rng_offset, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(s && out && N > 0 && N <= 65535 && D > 0 && D % 4 == 0, "langevin_norms: bad arguments");
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * 2 * N, stream);
@@ -160,20 +165,20 @@ extern "C" int indm_langevin_norms(const float* s, const float* z, float* out, c
   const long long D4 = D / 4;
   int chunks = (int)((D4 + 1023) / 1024);
   if (chunks < 1) chunks = 1;
-  langevin_norms_kernel<<<dim3(chunks, (unsigned)N), 256, 0, stream>>>(s, z, out, step, D4, seed, (uint32_t)rng_offset);
+  langevin_norms_kernel<<<dim3(chunks, (unsigned)N), 256, 0, stream>>>(s, z, out, step, D4, seed, seed_dev, (uint32_t)rng_offset);
   INDM_CHECK_LAUNCH("langevin_norms");
   return INDM_OK;
 }
 
 extern "C" int indm_langevin_update(float* x, const float* s, const float* z, float* x_mean, const float* norms, const float* coef,
-                                    int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, uint64_t rng_offset,
-                                    void* stream_) {
+                                    int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
+                                    uint64_t rng_offset, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(x && s && norms && coef && N > 0 && D > 0 && coef_ld >= 2, "langevin_update: bad arguments");
   INDM_CHECK_ARG((N * D) % 4 == 0, "langevin_update: N*D must be a multiple of 4");
   const long long total4 = N * D / 4;
   langevin_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, norms, coef, coef_ld, step, (int)N, total4, seed,
-                                                             (uint32_t)rng_offset);
+                                                             seed_dev, (uint32_t)rng_offset);
   INDM_CHECK_LAUNCH("langevin_update");
   return INDM_OK;
 }

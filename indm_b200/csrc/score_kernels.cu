@@ -248,7 +248,7 @@ __global__ void time_embedding_kernel(const float* __restrict__ time_cond, const
 // out[n][o] = bias[o] + sum_k f(in[n][k]) w[o][k].  K <= 1024, K % 128 == 0 handled by the 8-register path.
 template <int KV>  // float4 per lane = K / 128
 __global__ void linear_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                              float* __restrict__ out, long long N, int K, int O, int act_in) {
+                              void* __restrict__ out, long long N, int K, int O, int act_in, int act_out, int out_dtype) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + warp;
   if (o >= O) return;
@@ -265,7 +265,12 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
       acc += (v.x * wr[i].x + v.y * wr[i].y) + (v.z * wr[i].z + v.w * wr[i].w);
     }
     acc = warp_sum(acc);
-    if (lane == 0) out[n * O + o] = acc + b;
+    if (lane == 0) {
+      float v = acc + b;
+      if (act_out) v = silu_f(v);
+      if (out_dtype == INDM_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[n * O + o] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(out)[n * O + o] = (out_dtype == INDM_DTYPE_TF32) ? round_tf32(v) : v;
+    }
   }
 }
 
@@ -453,8 +458,8 @@ extern "C" int indm_time_embedding(const float* time_cond, const float* sched, c
   return INDM_OK;
 }
 
-extern "C" int indm_linear_f32(const float* in, const float* w, const float* bias, float* out, int64_t N, int K, int O,
-                               int act_in, void* stream_) {
+extern "C" int indm_linear_f32(const float* in, const float* w, const float* bias, void* out, int64_t N, int K, int O,
+                               int act_in, int act_out, int out_dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(in && w && out && N > 0 && O > 0, "linear: bad arguments");
   INDM_CHECK_ARG(K % 128 == 0 && K >= 128 && K <= 1024, "linear: K must be a multiple of 128 in [128, 1024] (got %d)", K);
@@ -465,7 +470,7 @@ extern "C" int indm_linear_f32(const float* in, const float* w, const float* bia
   while ((long long)gx * gy < 2LL * indm_num_sms() && gy < N) gy *= 2;
   dim3 grid(gx, gy);
   switch (K / 128) {
-#define LIN(KV) case KV: linear_kernel<KV><<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in); break;
+#define LIN(KV) case KV: linear_kernel<KV><<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in, act_out, out_dtype); break;
     LIN(1) LIN(2) LIN(3) LIN(4) LIN(5) LIN(6) LIN(7) LIN(8)
 #undef LIN
   }

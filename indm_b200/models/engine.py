@@ -184,17 +184,25 @@ class ScoreEngine:
         w1, b1 = self._alloc((4 * nf, 4 * nf)), self._alloc((4 * nf,))
         self._pack_f32(w0, [lin0.weight]); self._pack_f32(b0, [lin0.bias])
         self._pack_f32(w1, [lin1.weight]); self._pack_f32(b1, [lin1.bias])
-        t0, temb = self._alloc((N, 4 * nf)), self._alloc((N, 4 * nf))
-        self._call('indm_linear_f32', self.emb, w0, b0, t0, ctypes.c_int64(N), emb_dim, 4 * nf, 0)
-        self._call('indm_linear_f32', t0, w1, b1, temb, ctypes.c_int64(N), 4 * nf, 4 * nf, 1)
+        # temb = Linear(SiLU(Linear(emb))) (models/ncsnpp.py:270-274); only SiLU(temb) is ever consumed (Dense_0), so the
+        # second layer stores SiLU(temb) directly, in the tensor-core operand dtype
+        op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32
+        t0, temb_act = self._alloc((N, 4 * nf)), self._op_t((N, 4 * nf))
+        self._call('indm_linear_f32', self.emb, w0, b0, t0, ctypes.c_int64(N), emb_dim, 4 * nf, 0, 1, L.DTYPE_F32)
+        self._call('indm_linear_f32', t0, w1, b1, temb_act, ctypes.c_int64(N), 4 * nf, 4 * nf, 0, 1, op_dt)
         res_blocks = [mm for mm in mods if mm.__class__.__name__ == 'ResnetBlockBigGANpp']
         dense_total = sum(rb.out_ch for rb in res_blocks)
         self.dense_total = dense_total
-        wd, bd = self._alloc((dense_total, 4 * nf)), self._alloc((dense_total,))
-        self._pack_f32(wd, [rb.Dense_0.weight for rb in res_blocks])
+        wd, bd = self._op_t((dense_total, 4 * nf)), self._alloc((dense_total,))
+
+        def job_wd(wd=wd, res_blocks=res_blocks):
+            wd.copy_(self._round_op(torch.cat([rb.Dense_0.weight.detach().to(self.dev, torch.float32) for rb in res_blocks], dim=0)))
+        self.pack_jobs.append(job_wd)
         self._pack_f32(bd, [rb.Dense_0.bias for rb in res_blocks])
         self.dense_tab = self._alloc((N, dense_total))
-        self._call('indm_linear_f32', temb, wd, bd, self.dense_tab, ctypes.c_int64(N), 4 * nf, dense_total, 1)
+        # all Dense_0 layers of the network in one tensor-core GEMM: [N, 4nf] x [sum Cout, 4nf]^T
+        self._igemm(a=temb_act, N=1, H=1, W=N, Cin=4 * nf, b=wd, Cout=dense_total, taps=1, bias=bd, out_f32=self.dense_tab,
+                    out_ld=dense_total)
         dense_off = {}
         off = 0
         for rb in res_blocks:

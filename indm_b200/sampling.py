@@ -123,7 +123,7 @@ class ReverseDiffusionPredictor(Predictor):
         x_mean = torch.empty_like(x)
         N, D = x.shape[0], x[0].numel()
         L.call('indm_pc_predictor_update', L.ptr(x), L.ptr(score), L.ptr(noise.contiguous()) if noise is not None else None,
-               L.ptr(x_mean), L.ptr(coef), 4, None, N, D, seed, offset)
+               L.ptr(x_mean), L.ptr(coef), 4, None, N, D, seed, None, offset)
         return x, x_mean
 
 
@@ -155,9 +155,9 @@ class LangevinCorrector(Corrector):
         for i in range(self.n_steps):
             grad = self.score_fn(x, t).contiguous()
             z = noise.contiguous() if noise is not None else None
-            L.call('indm_langevin_norms', L.ptr(grad), L.ptr(z), L.ptr(norms), None, N, D, seed, offset + i)
+            L.call('indm_langevin_norms', L.ptr(grad), L.ptr(z), L.ptr(norms), None, N, D, seed, None, offset + i)
             L.call('indm_langevin_update', L.ptr(x), L.ptr(grad), L.ptr(z), L.ptr(x_mean), L.ptr(norms), L.ptr(coef), 2, None,
-                   N, D, seed, offset + i)
+                   N, D, seed, None, offset + i)
         return x, x_mean
 
 
@@ -202,6 +202,7 @@ class _GraphedPC:
         self.x_mean = torch.zeros_like(self.x)
         self.norms = torch.zeros((batch, 2), device=self.dev)
         self.step = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        self.seed_dev = torch.zeros((1,), dtype=torch.int64, device=self.dev)   # read by the kernels: graph-replay safe
         self.sched = None
         self.graph = None
 
@@ -217,26 +218,27 @@ class _GraphedPC:
         rows = torch.stack([self.sde.time_cond(t).float(), sscale, a.float(), c.float(),
                             d.float(), self.sde.langevin_alpha(t).float(), torch.as_tensor(snr_per_step, dtype=torch.float32),
                             torch.zeros_like(t)], dim=1).contiguous()
-        self.sched = rows.to(self.dev)
+        if self.sched is not None and tuple(self.sched.shape) == tuple(rows.shape):
+            self.sched.copy_(rows)          # same buffer: the captured graph stays valid
+        else:
+            self.sched = rows.to(self.dev)
+            self.eng._bind_time_source(self.sched, self.step, 8, 0)
+            self.graph = None
         self.n_rows = rows.shape[0]
-        eng = self.eng
-        eng._bind_time_source(self.sched, self.step, 8, 0)
-        self.graph = None
 
     def _one_step(self, noise_c, noise_p):
         eng, N, D = self.eng, self.N, self.D
-        lib_seed = self.seed
         if self.langevin:
             for i in range(self.n_steps):
                 self._fill_scale()
                 eng.launch()
-                L.call('indm_langevin_norms', L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.norms), L.ptr(self.step), N, D, lib_seed, 1 + i)
+                L.call('indm_langevin_norms', L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.norms), L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
                 L.call('indm_langevin_update', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.x_mean), L.ptr(self.norms),
-                       L.ptr(self.sched[:, 5:]), 8, L.ptr(self.step), N, D, lib_seed, 1 + i)
+                       L.ptr(self.sched[:, 5:]), 8, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
         self._fill_scale()
         eng.launch()
         L.call('indm_pc_predictor_update', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_p), L.ptr(self.x_mean), L.ptr(self.sched[:, 2:]), 8,
-               L.ptr(self.step), N, D, lib_seed, 0)
+               L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 0)
         L.call('indm_advance_step', L.ptr(self.step))
 
     def _fill_scale(self):
@@ -322,7 +324,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
             if g is None:
                 g = _GraphedPC(config, sde, net, shape[0], corr_name, n_steps, probability_flow, seed)
                 cache[key] = g
-            g.seed = seed
+            g.seed_dev.fill_(int(seed))
             g.set_schedule(timesteps, snrs)
             if sample_dir is not None and num_scales >= 2:
                 # side effect of the reference loop at i == num_scales-2 (sampling.py:436-445): x_mean of that step

@@ -279,10 +279,14 @@ def test_prep_input_and_time_embedding_and_linear():
     # dense
     inp, w, b = rnd(5, 512, seed=29), rnd(300, 512, seed=30) / 22, rnd(300, seed=31)
     o = torch.zeros((5, 300), device=DEV)
-    L.call('indm_linear_f32', P(inp), P(w), P(b), L.ptr(o), 5, 512, 300, 1)
+    L.call('indm_linear_f32', P(inp), P(w), P(b), L.ptr(o), 5, 512, 300, 1, 0, L.DTYPE_F32)
     torch.cuda.synchronize()
     want = F.linear(F.silu(inp.double()), w.double(), b.double())
     assert rel_l2(o.cpu(), want) < 1e-5
+    o16 = torch.zeros((5, 300), device=DEV, dtype=torch.bfloat16)
+    L.call('indm_linear_f32', P(inp), P(w), P(b), L.ptr(o16), 5, 512, 300, 0, 1, L.DTYPE_BF16)
+    torch.cuda.synchronize()
+    assert rel_l2(o16.float().cpu(), F.silu(F.linear(inp.double(), w.double(), b.double()))) < 4e-3
 
 
 @pytest.mark.parametrize("mode", [1, 2, 3])
@@ -317,18 +321,18 @@ def test_pc_update_kernels_match_oracle():
     coef = torch.tensor([[2 - math.sqrt(alpha), beta, math.sqrt(beta), 0.0]])
     xd, xm = x.clone().to(DEV), torch.zeros_like(x).to(DEV)
     L.call('indm_pc_predictor_update', L.ptr(xd), P(s), P(z), L.ptr(xm), P(coef), 4, None,
-           N, D, 0, 0)
+           N, D, 0, None, 0)
     torch.cuda.synchronize()
     assert rel_l2(xd.cpu(), want_x) < 1e-6 and rel_l2(xm.cpu(), want_mean) < 1e-6
     # Langevin, VE (alpha = 1)
     ve = osde.VE()
     want_x, want_mean = osampler.langevin_update(ve, s, x, t, z, 0.16)
     norms = torch.zeros((N, 2), device=DEV)
-    L.call('indm_langevin_norms', P(s), P(z), L.ptr(norms), None, N, D, 0, 0)
+    L.call('indm_langevin_norms', P(s), P(z), L.ptr(norms), None, N, D, 0, None, 0)
     coef = torch.tensor([[1.0, 0.16]])
     xd, xm = x.clone().to(DEV), torch.zeros_like(x).to(DEV)
     L.call('indm_langevin_update', L.ptr(xd), P(s), P(z), L.ptr(xm), L.ptr(norms), P(coef), 2,
-           None, N, D, 0, 0)
+           None, N, D, 0, None, 0)
     torch.cuda.synchronize()
     assert rel_l2(xd.cpu(), want_x) < 1e-5 and rel_l2(xm.cpu(), want_mean) < 1e-5
 
@@ -349,10 +353,10 @@ def test_philox_normal_stream_statistics_and_replay():
     N, D = 2, 4096
     s = rnd(N, D, seed=36).to(DEV)
     norms = torch.zeros((N, 2), device=DEV)
-    L.call('indm_langevin_norms', L.ptr(s), None, L.ptr(norms), None, N, D, 77, 1)
+    L.call('indm_langevin_norms', L.ptr(s), None, L.ptr(norms), None, N, D, 77, None, 1)
     x0 = torch.zeros((N, D), device=DEV)
     coef = torch.tensor([[1.0, 0.16]], device=DEV)
-    L.call('indm_langevin_update', L.ptr(x0), P(torch.zeros_like(s)), None, None, L.ptr(norms), L.ptr(coef), 2, None, N, D, 77, 1)
+    L.call('indm_langevin_update', L.ptr(x0), P(torch.zeros_like(s)), None, None, L.ptr(norms), L.ptr(coef), 2, None, N, D, 77, None, 1)
     torch.cuda.synchronize()
     # with s = 0 in the update, x = sqrt(2 eps) z  =>  |x_n|^2 / (2 eps) == |z_n|^2 from the norms kernel
     r = 0.16 * norms[:, 1].sqrt().mean() / norms[:, 0].sqrt().mean()

@@ -72,6 +72,22 @@ def main():
             cnt[n] += 1
         for n, v in sorted(tot.items(), key=lambda kv: -kv[1]):
             print(f'  {n:28s} x{cnt[n]:4d}  {v:8.3f} ms')
+        # per-shape igemm table
+        shp = collections.defaultdict(lambda: [0, 0.0, 0.0])
+        for i, op in enumerate(eng.ops):
+            d = None
+            for c in (op.__closure__ or ()):
+                if c.cell_contents.__class__.__name__ == 'IgemmDesc':
+                    d = c.cell_contents
+            if d is None:
+                continue
+            key = (d.H, d.W, d.Cin, d.Cin2 if d.a2 else 0, d.Cout, d.taps, d.batched_b)
+            fl = 2.0 * d.N * d.H * d.W * d.Cout * (d.Cin * d.taps + (d.Cin2 if d.a2 else 0))
+            r = shp[key]
+            r[0] += 1; r[1] += evs[i].elapsed_time(evs[i + 1]); r[2] += fl
+        print('  igemm shapes (H,W,Cin,Cin2,Cout,taps,batched): count  ms  TFLOP/s')
+        for k, r in sorted(shp.items(), key=lambda kv: -kv[1][1]):
+            print(f'   {str(k):40s} x{r[0]:3d} {r[1]:8.3f} ms  {r[2] / r[1] / 1e9:8.1f}')
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())

@@ -70,12 +70,14 @@ typedef struct indm_igemm {
   int32_t Cin2;
   const void* b2;
   int64_t b2_ld;
-  /* epilogue: v = (acc + bias[c] + rowbias[n*rowbias_ld + c] + residual[pixel*res_ld + c]) * scale * rowscale[n] */
+  /* epilogue: v = act((acc + bias[c] + rowbias[n*rowbias_ld + c]) * scale * rowscale[n] + residual[pixel*res_ld + c] * res_scale) */
   const float* bias;     /* [Cout] or NULL */
   const float* rowbias;  /* per-image bias (time-embedding Dense_0 output, models/layerspp.py:276) or NULL */
   int64_t rowbias_ld;
-  const float* residual; /* fp32 NHWC or NULL */
+  const float* residual; /* fp32 NHWC (NCHW when out_mode == 1) or NULL */
   int64_t res_ld;
+  float res_scale;
+  int32_t act;           /* 0 none; 1 Sin(x) = sin(2 pi x)/(2 pi), the resflow activation (flows/resflow/layers/base/activations.py:7-12) */
   const float* rowscale; /* [N] or NULL */
   float scale;
   int32_t out_mode;      /* 0: NHWC rows out_*[pixel*out_ld + c];  1: NCHW fp32 (out_f32);
@@ -118,9 +120,10 @@ int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, 
 int indm_softmax_rows(const float* s, void* out, int64_t rows, int cols, int out_dtype, void* stream);
 
 /* Network input: x NCHW fp32 [N,C,H,W] -> NHWC with cpad >= C channels (extra channels zero), v = x*mul + add
- * (the `2x - 1` of models/ncsnpp.py:278-280 when data is not centred), in out_dtype. */
-int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, int cpad, float mul, float add, int out_dtype,
-                    void* stream);
+ * (the `2x - 1` of models/ncsnpp.py:278-280 when data is not centred), then act (0 none, 1 Sin — the leading
+ * activation of an iResBlock branch, flows/resflow/resflow_.py:442-444), in out_dtype. */
+int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, int cpad, float mul, float add, int act,
+                    int out_dtype, void* stream);
 
 /* Time embedding (models/layers.py:515-529 positional: kind 0, time_cond = 999 t;
  * models/layerspp.py:45-54 Gaussian Fourier: kind 1, time_cond = sigma, freqs = W[dim/2]).
@@ -177,6 +180,36 @@ int indm_sched_broadcast(float* out, int64_t n, const float* sched, int ld, int 
 
 /* fill with standard normal noise (same Philox stream as above), fp32 */
 int indm_randn_f32(float* out, int64_t n, uint64_t seed, uint64_t rng_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Flow side (wolf / residual flow)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* One op of the 64-d latent prior flow program (flow_models/wolf/modules/discriminators/priors/flow.py:16-201).
+ * off[] are offsets (in floats) into one packed fp32 parameter buffer:
+ *   ACTNORM  : off[0] log_scale[64], off[1] bias[64]                       (flows/normalization.py:26-70)
+ *   LINEAR   : off[0] matrix[64][64] applied as y = x W^T                   (flows/permutation.py:91-134)
+ *   COUPLING : off[0..5] fc1.w[256][32], fc1.b, fc2.w[256][256], fc2.b, fc3.w_eff[64][256] (weight-norm folded), fc3.b
+ *              split_skip: 0 halves / 1 even-odd; up: conditioner = part 1     (flows/couplings/coupling.py:48-145)
+ * backward = 0: the op's forward(); 1: its backward().  */
+#define INDM_FLOW_OP_ACTNORM 0
+#define INDM_FLOW_OP_LINEAR 1
+#define INDM_FLOW_OP_COUPLING 2
+typedef struct indm_flow_op {
+  int32_t kind, backward, split_skip, up;
+  int64_t off[6];
+} indm_flow_op_t;
+
+/* out[n] = program(in[n]) for n < N, in/out [N,64]; logdet[n] (optional) = sum of the ops' log-determinants +
+ * logdet_const (the invertible-linear slogdet terms, constants of the weights, computed by the caller).
+ * params / ops are DEVICE pointers. */
+int indm_prior_flow(const float* in, float* out, float* logdet, const float* params, const indm_flow_op_t* ops, int n_ops,
+                    float logdet_const, int64_t N, void* stream);
+
+/* flag[0] = max_i (x[i]-x_prev[i])^2 / (atol + |y[i]|*rtol)  — the stop rule of iResBlock._inverse_fixed_point
+ * (flows/resflow/layers/iresblock.py:78-88): converged iff flag[0] < 1.  flag is a device float. */
+int indm_fixed_point_check(const float* x, const float* x_prev, const float* y, int64_t n, float atol, float rtol, float* flag,
+                           void* stream);
 
 #ifdef __cplusplus
 }

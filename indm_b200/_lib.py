@@ -29,13 +29,18 @@ class IgemmDesc(C.Structure):
         ("a2", C.c_void_p), ("a2_ld", C.c_int64), ("Cin2", C.c_int32),
         ("b2", C.c_void_p), ("b2_ld", C.c_int64),
         ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int64),
-        ("residual", C.c_void_p), ("res_ld", C.c_int64),
+        ("residual", C.c_void_p), ("res_ld", C.c_int64), ("res_scale", C.c_float), ("act", C.c_int32),
         ("rowscale", C.c_void_p), ("scale", C.c_float),
         ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("out_ld", C.c_int64),
         ("tcol0", C.c_int32), ("out_t", C.c_void_p), ("round_tf32_out", C.c_int32),
         ("gn_partial", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_groups", C.c_int32),
         ("block_n", C.c_int32),
     ]
+
+
+class FlowOp(C.Structure):
+    """Mirror of `indm_flow_op_t`."""
+    _fields_ = [("kind", C.c_int32), ("backward", C.c_int32), ("split_skip", C.c_int32), ("up", C.c_int32), ("off", C.c_int64 * 6)]
 
 
 _i32, _i64, _u64, _f32, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
@@ -47,7 +52,7 @@ _SIGS = {
     "indm_gn_apply": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32, C.c_int,
                       C.c_int, _vp, _vp, C.c_int, _vp],
     "indm_softmax_rows": [_vp, _vp, _i64, C.c_int, C.c_int, _vp],
-    "indm_prep_input": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _f32, C.c_int, _vp],
+    "indm_prep_input": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _f32, C.c_int, C.c_int, _vp],
     "indm_time_embedding": [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _i64, C.c_int, _vp, _vp],
     "indm_linear_f32": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "indm_fir_nhwc": [_vp, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, _vp],
@@ -56,6 +61,8 @@ _SIGS = {
     "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
     "indm_advance_step": [_vp, _vp],
     "indm_randn_f32": [_vp, _i64, _u64, _u64, _vp],
+    "indm_prior_flow": [_vp, _vp, _vp, _vp, _vp, C.c_int, _f32, _i64, _vp],
+    "indm_fixed_point_check": [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp],
     "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],
 }
 EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)
@@ -106,6 +113,7 @@ def call(name, *args):
 def igemm(**kw):
     d = IgemmDesc()
     d.scale = 1.0
+    d.res_scale = 1.0
     for k, v in kw.items():
         if isinstance(v, torch.Tensor):
             v = v.data_ptr()

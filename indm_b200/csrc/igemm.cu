@@ -44,6 +44,8 @@ struct IgemmParams {
   long long res_ld;
   const float* rowscale;  // per-image multiplier (head conv: -1/std or 1/sigma)
   float scale;
+  float res_scale;        // multiplier of the residual term
+  int act;                // 0 none, 1 Sin(x) = sin(2 pi x) / (2 pi)  (resflow activation)
   float* out_f32;
   __nv_bfloat16* out_bf16;
   long long out_ld;
@@ -252,22 +254,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (c0 + i < p.Cout) f[i] += __ldg(rb + i);
         }
       }
-      if (p.residual) {
-        const float* rr = p.residual + pix * p.res_ld + c0;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(rr + i);
-            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) f[i] += rr[i];
-        }
-      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] *= scale;
+      if (p.residual) {
+        if (p.out_mode == 1) {
+          // NCHW residual (flow fixed-point update x <- y - g(x), flow_models/.../iresblock.py:78-88)
+          const long long hw = (long long)p.H * p.W;
+          const float* rr = p.residual + (long long)n * p.Cout * hw + (long long)y * p.W + x;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) f[i] += p.res_scale * rr[(long long)(c0 + i) * hw];
+        } else {
+          const float* rr = p.residual + pix * p.res_ld + c0;
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(rr + i);
+              f[i] += p.res_scale * b.x; f[i + 1] += p.res_scale * b.y; f[i + 2] += p.res_scale * b.z; f[i + 3] += p.res_scale * b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < p.Cout) f[i] += p.res_scale * rr[i];
+          }
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = sinf(6.283185307179586f * f[i]) * 0.15915494309189535f;
+      }
       if (p.round_tf32_out) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = round_tf32(f[i]);
@@ -395,6 +410,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   INDM_CHECK_ARG(d->taps == 1 || d->taps == 9, "igemm: taps must be 1 or 9 (got %d)", d->taps);
   INDM_CHECK_ARG(!(d->batched_b && d->taps != 1), "igemm: batched B requires taps == 1");
   INDM_CHECK_ARG(d->out_f32 || d->out_bf16 || d->out_t, "igemm: no output");
+  INDM_CHECK_ARG(d->act == 0 || d->act == 1, "igemm: act must be 0 (none) or 1 (Sin)");
 
   IgemmParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
@@ -431,6 +447,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   p.residual = d->residual; p.res_ld = d->res_ld;
   p.rowscale = d->rowscale;
   p.scale = d->scale;
+  p.res_scale = d->res_scale;
+  p.act = d->act;
   p.out_f32 = d->out_f32;
   p.out_bf16 = (__nv_bfloat16*)d->out_bf16;
   p.out_ld = d->out_ld;

@@ -204,7 +204,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, TOut* __restric
 // ---------------------------------------------------------------- network input NCHW fp32 -> NHWC (padded channels)
 template <typename TOut>
 __global__ void prep_input_kernel(const float* __restrict__ x, TOut* __restrict__ out, long long N, int C, int HW, int cpad,
-                                  float mul, float add, int tf32) {
+                                  float mul, float add, int act, int tf32) {
   const long long total = N * HW * cpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cpad);
@@ -214,6 +214,7 @@ __global__ void prep_input_kernel(const float* __restrict__ x, TOut* __restrict_
     float v = 0.f;
     if (c < C) {
       v = x[(n * C + c) * HW + p] * mul + add;
+      if (act == 1) v = sinf(6.283185307179586f * v) * 0.15915494309189535f;
       if (tf32) v = round_tf32(v);
     }
     out[i] = (TOut)v;
@@ -431,16 +432,16 @@ extern "C" int indm_softmax_rows(const float* s, void* out, int64_t rows, int co
   return INDM_OK;
 }
 
-extern "C" int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, int cpad, float mul, float add,
+extern "C" int indm_prep_input(const float* x, void* out, int64_t N, int C, int H, int W, int cpad, float mul, float add, int act,
                                int out_dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(x && out && N > 0 && C > 0 && cpad >= C, "prep_input: bad arguments");
   const long long total = (long long)N * H * W * cpad;
   const int grid = grid_for(total, 256);
   if (out_dtype == INDM_DTYPE_BF16)
-    prep_input_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)out, N, C, H * W, cpad, mul, add, 0);
+    prep_input_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)out, N, C, H * W, cpad, mul, add, act, 0);
   else if (out_dtype == INDM_DTYPE_TF32 || out_dtype == INDM_DTYPE_F32)
-    prep_input_kernel<float><<<grid, 256, 0, stream>>>(x, (float*)out, N, C, H * W, cpad, mul, add, out_dtype == INDM_DTYPE_TF32);
+    prep_input_kernel<float><<<grid, 256, 0, stream>>>(x, (float*)out, N, C, H * W, cpad, mul, add, act, out_dtype == INDM_DTYPE_TF32);
   else
     INDM_CHECK_ARG(false, "prep_input: bad out_dtype");
   INDM_CHECK_LAUNCH("prep_input");

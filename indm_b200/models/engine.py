@@ -109,6 +109,7 @@ class ScoreEngine:
     def _igemm(self, **kw):
         d = L.IgemmDesc()
         d.scale = 1.0
+        d.res_scale = 1.0
         d.dtype = self.dt
         for k, v in kw.items():
             if isinstance(v, torch.Tensor):
@@ -215,7 +216,7 @@ class ScoreEngine:
         x_nhwc = self._op_t((N, S, S, cpad))
         centered = bool(cfg.data.centered)
         self._call('indm_prep_input', self.x_in, x_nhwc, ctypes.c_int64(N), self.ch, S, S, cpad,
-                   ctypes.c_float(1.0 if centered else 2.0), ctypes.c_float(0.0 if centered else -1.0),
+                   ctypes.c_float(1.0 if centered else 2.0), ctypes.c_float(0.0 if centered else -1.0), 0,
                    L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
         stem = mods[idx]; idx += 1
         wst = self._op_t((9, nf, cpad))
@@ -285,7 +286,7 @@ class ScoreEngine:
             else:
                 self._pack_f32(b1, [rb.Conv_1.bias])
                 assert xb is None and Ca == Cout and resample == 0
-                kw.update(residual=xa, res_ld=Cout)
+                kw.update(residual=xa, res_ld=Cout, res_scale=inv_sqrt2 if rb.skip_rescale else 1.0)
             self._igemm(**kw)
             return out, Ho, Wo
 
@@ -337,7 +338,8 @@ class ScoreEngine:
             self.pack_jobs.append(job3)
             out = self._alloc((N, H, W, C))
             self._igemm(a=o, N=N, H=H, W=W, Cin=C, b=w3, Cout=C, taps=1, bias=b3, residual=x, res_ld=C,
-                        scale=inv_sqrt2 if ab.skip_rescale else 1.0, out_f32=out, out_ld=C)
+                        scale=inv_sqrt2 if ab.skip_rescale else 1.0, res_scale=inv_sqrt2 if ab.skip_rescale else 1.0,
+                        out_f32=out, out_ld=C)
             return out
 
         # ---------------- down path

@@ -1,0 +1,312 @@
+"""CPU restatement of the wolf / residual-flow side of the INDM hot path (torch-CPU FP32, functional).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Pinned by tests/golden/flow_*.npz (live reference outputs).
+
+Covers: the conditional Residual Flow (flow_models/wolf/flows/resflow/resflow_.py:20-518, layers/iresblock.py:14-179,
+layers/base/lipschitz.py:321-441, layers/base/activations.py:7-12, layers/squeeze.py:7-45), the 64-d latent prior flow
+(flow_models/wolf/modules/discriminators/priors/flow.py:16-286 with flows/normalization.py:13-112,
+flows/permutation.py:75-149, flows/couplings/coupling.py:13-177, transform.py:49-81, blocks.py:11-48),
+`WolfCore.forward(reverse=True)` (flow_models/wolf/wolf.py:81-89) and the `flow_forward` wrapper
+(flow_models/flow_model.py:53-67).  Parameters: flat dict keyed like the reference state-dict without `module.`.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+COEFF = 0.98   # resflow_.py:40 (coeff) -> LopConv2d soft normalisation
+
+
+def n_blocks(config):
+    return [int(v) for v in config.flow.nblocks.split('-')]
+
+
+def flow_input_shape(config):
+    """generator.py:96-101"""
+    c, s = config.data.num_channels, config.data.image_size
+    return (c * 4, s // 2, s // 2) if config.flow.squeeze else (c, s, s)
+
+
+def block_layout(config):
+    """[(scale, block, channels, first)] in forward order; nnet indices are 0/2/4 for the first block of scale 0
+    (no leading Sin, resflow_.py:442-444) and 1/3/5 elsewhere."""
+    c, _, _ = flow_input_shape(config)
+    out = []
+    for s, nb in enumerate(n_blocks(config)):
+        for b in range(nb):
+            out.append((s, b, c, s == 0 and b == 0))
+        c *= 4
+    return out
+
+
+def param_shapes(config):
+    """[(key, shape)] of the full wolf flow state-dict, reference order (probed: 687 entries for CIFAR)."""
+    idim = config.flow.intermediate_dim
+    out = []
+    for s, b, c, first in block_layout(config):
+        p = f'generator.flow.transforms.{s}.chain.{b}.'
+        out += [(p + 'geom_p', ()), (p + 'lamb', ()), (p + 'last_n_samples', (1,)), (p + 'last_firmom', (1,)), (p + 'last_secmom', (1,))]
+        j0 = 0 if first else 1
+        out += [(p + f'nnet.{j0}.weight', (idim, c, 3, 3)), (p + f'nnet.{j0}.bias', (idim,)), (p + f'nnet.{j0}.scale', ())]
+        out += [(p + f'nnet.{j0 + 2}.weight', (idim, idim, 1, 1)), (p + f'nnet.{j0 + 2}.bias', (idim,)), (p + f'nnet.{j0 + 2}.scale', ()),
+                (p + f'nnet.{j0 + 2}.h_net.net.weight', (idim, 64)), (p + f'nnet.{j0 + 2}.h_net.net.bias', (idim,))]
+        out += [(p + f'nnet.{j0 + 4}.weight', (c, idim, 3, 3)), (p + f'nnet.{j0 + 4}.bias', (c,)), (p + f'nnet.{j0 + 4}.scale', ())]
+    enc = config.flow.wolf_params['discriminator']['encoder']
+    inp = enc['in_planes']
+    for lv, hid in enumerate(enc['hidden_planes']):
+        for m, (ci, stride) in enumerate(((inp, 1), (hid, 2))):
+            p = f'discriminator.encoder.net.resnet{lv}.main.{m}.'
+            out += [(p + 'conv1.weight', (hid, ci, 3, 3))]
+            for bn in ('bn1',):
+                out += [(p + f'{bn}.weight', (hid,)), (p + f'{bn}.bias', (hid,)), (p + f'{bn}.running_mean', (hid,)),
+                        (p + f'{bn}.running_var', (hid,)), (p + f'{bn}.num_batches_tracked', ())]
+            out += [(p + 'conv2.weight', (hid, hid, 3, 3))]
+            out += [(p + 'bn2.weight', (hid,)), (p + 'bn2.bias', (hid,)), (p + 'bn2.running_mean', (hid,)),
+                    (p + 'bn2.running_var', (hid,)), (p + 'bn2.num_batches_tracked', ())]
+            if stride != 1 or ci != hid:
+                out += [(p + 'downsample.0.weight', (hid, ci, 1, 1)), (p + 'downsample.1.weight', (hid,)), (p + 'downsample.1.bias', (hid,)),
+                        (p + 'downsample.1.running_mean', (hid,)), (p + 'downsample.1.running_var', (hid,)),
+                        (p + 'downsample.1.num_batches_tracked', ())]
+        inp = hid
+    dsc = config.flow.wolf_params['discriminator']
+    out += [('discriminator.encoder.net.top.weight', (enc['out_planes'], inp, 1, 1)), ('discriminator.encoder.net.top.bias', (enc['out_planes'],))]
+    out += [('discriminator.fc.linear.bias', (2 * dsc['dim'],)), ('discriminator.fc.linear.weight_g', (2 * dsc['dim'], 1)),
+            ('discriminator.fc.linear.weight_v', (2 * dsc['dim'], dsc['in_dim']))]
+    pr = dsc['prior']
+    d, hf = pr['in_features'], pr['hidden_features']
+    for t in range(pr['num_steps']):
+        p = f'discriminator.prior.flow.steps.{t}.'
+        out += [(p + 'actnorm.log_scale', (d,)), (p + 'actnorm.bias', (d,)), (p + 'linear.weight', (d, d)), (p + 'linear.weight_inv', (d, d))]
+        for cp in ('coupling1_up', 'coupling1_dn'):
+            out += _coupling_shapes(p + f'unit.{cp}.net.', d, hf)
+        out += [(p + 'unit.actnorm.log_scale', (d,)), (p + 'unit.actnorm.bias', (d,))]
+        for cp in ('coupling2_up', 'coupling2_dn'):
+            out += _coupling_shapes(p + f'unit.{cp}.net.', d, hf)
+    return out
+
+
+def _coupling_shapes(p, d, hf):
+    return [(p + 'fc1.weight', (hf, d // 2)), (p + 'fc1.bias', (hf,)), (p + 'fc2.weight', (hf, hf)), (p + 'fc2.bias', (hf,)),
+            (p + 'fc3.linear.bias', (d,)), (p + 'fc3.linear.weight_g', (d, 1)), (p + 'fc3.linear.weight_v', (d, hf))]
+
+
+def synth_params(config, seed=0):
+    """Deterministic synthetic flow weights (numpy PCG64).  Conv weights get PyTorch-default magnitudes
+    (U(+-1/sqrt(fan_in))), for which every row L1 norm exceeds 0.98, so the Lipschitz soft-normalisation is active and
+    the residual branch is a genuine contraction (~0.98^3): the fixed-point inverse needs several iterations.
+    `linear.weight_inv` is deliberately NOT the inverse of `linear.weight` (the reference never re-syncs it after
+    training, SURVEY.md §7 hard part 6), so a product that 'fixes' the quirk fails parity."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shape in param_shapes(config):
+        leaf = name.split('.')[-1]
+        if leaf == 'geom_p':
+            v = np.asarray(0.0)                       # log(0.5) - log(0.5), iresblock.py:42
+        elif leaf == 'lamb':
+            v = np.asarray(2.0)
+        elif leaf in ('last_n_samples', 'last_firmom', 'last_secmom', 'scale'):
+            v = np.zeros(shape)
+        elif leaf == 'num_batches_tracked':
+            sd[name] = np.asarray(3, dtype=np.int64)
+            continue
+        elif leaf == 'running_var':
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif leaf == 'running_mean':
+            v = 0.1 * rng.standard_normal(shape)
+        elif leaf == 'log_scale':
+            v = 0.05 * rng.standard_normal(shape)
+        elif leaf == 'weight_g':
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif leaf in ('weight', 'weight_inv') and len(shape) == 2 and shape[0] == shape[1] and 'linear' in name:
+            q, _ = np.linalg.qr(rng.standard_normal(shape))
+            v = q if leaf == 'weight' else np.linalg.inv(q + 0.05 * rng.standard_normal(shape))
+        elif len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            b = 1.0 / math.sqrt(fan_in)
+            v = rng.uniform(-b, b, size=shape)
+        elif leaf == 'weight':                        # BatchNorm scale
+            v = 1.0 + 0.1 * rng.standard_normal(shape)
+        else:                                         # biases
+            v = 0.05 * rng.standard_normal(shape)
+        sd[name] = np.asarray(v, dtype=np.float32)
+    return sd
+
+
+def to_torch(params_np):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params_np.items()}
+
+
+# ------------------------------------------------------------------------------------------------ residual flow
+def sin_act(x):
+    """activations.py:11-12"""
+    return torch.sin(2. * math.pi * x) / math.pi * 0.5
+
+
+def lop_weight(w):
+    """LopConv2d.compute_weight (lipschitz.py:350-359) for domain = codomain = inf: per-output-channel L1 norm."""
+    scale = w.abs().reshape(w.shape[0], -1).sum(dim=1).reshape(-1, 1, 1, 1)
+    return w / torch.max(torch.ones(1), scale / COEFF)
+
+
+def g_branch(P, s, b, first, x, h):
+    """iResBlock.nnet_forward (iresblock.py:55-61) for the 3-1-3 Lipschitz conv stack (resflow_.py:432-470)."""
+    p = f'generator.flow.transforms.{s}.chain.{b}.nnet.'
+    j0 = 0 if first else 1
+    if not first:
+        x = sin_act(x)
+    u = F.conv2d(x, lop_weight(P[p + f'{j0}.weight']), P[p + f'{j0}.bias'], padding=1)
+    u = sin_act(u)
+    cond = F.linear(h, P[p + f'{j0 + 2}.h_net.net.weight'], P[p + f'{j0 + 2}.h_net.net.bias'])     # lipschitz.py:431
+    u = F.conv2d(u + cond[:, :, None, None], lop_weight(P[p + f'{j0 + 2}.weight']), P[p + f'{j0 + 2}.bias'])
+    u = sin_act(u)
+    return F.conv2d(u, lop_weight(P[p + f'{j0 + 4}.weight']), P[p + f'{j0 + 4}.bias'], padding=1)
+
+
+def inverse_fixed_point(gfn, y, atol=1e-5, rtol=1e-5, max_iter=1000):
+    """iResBlock._inverse_fixed_point (iresblock.py:78-88).  Returns (x, iterations)."""
+    x, x_prev = y - gfn(y), y
+    i = 0
+    tol = atol + y.abs() * rtol
+    while not torch.all((x - x_prev) ** 2 / tol < 1):
+        x, x_prev = y - gfn(x), x
+        i += 1
+        if i > max_iter:
+            break
+    return x, i
+
+
+def squeeze2(x):
+    """squeeze.py:32-45"""
+    n, c, h, w = x.shape
+    return x.reshape(n, c, h // 2, 2, w // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(n, c * 4, h // 2, w // 2)
+
+
+def unsqueeze2(x):
+    return F.pixel_shuffle(x, 2)
+
+
+def resflow_forward(config, P, x, h):
+    """ResidualFlow.fwdpass(x, h, eval_logdet=False) (resflow_.py:205-235, 310-324)."""
+    nb = n_blocks(config)
+    shape = x.shape
+    for s, n in enumerate(nb):
+        for b in range(n):
+            x = x + g_branch(P, s, b, s == 0 and b == 0, x, h)
+        if s < len(nb) - 1:
+            x = squeeze2(x)
+    out = x.reshape(shape[0], -1)
+    if len(nb) > 1:
+        out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
+    else:
+        out = out.view(shape)
+    return out
+
+
+def resflow_inverse(config, P, z, h, atol=1e-5, rtol=1e-5):
+    """ResidualFlow.bwdpass(z, h) (resflow_.py:326-335 -> inverse :237-267).  Returns (x, [iterations per block])."""
+    nb = n_blocks(config)
+    x = z
+    if len(nb) > 1:
+        x = x.view(x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2, 2, 2).permute(0, 1, 5, 2, 3, 4) \
+             .reshape(x.shape[0], x.shape[1], x.shape[2], 2, x.shape[3] // 2).permute(0, 1, 3, 2, 4).reshape(x.shape)
+    c0, h0, w0 = flow_input_shape(config)
+    k = len(nb) - 1
+    x = x.reshape(x.shape[0], c0 * 4 ** k, h0 // 2 ** k, w0 // 2 ** k)    # self.dims[-1], resflow_.py:262
+    iters = []
+    for s in reversed(range(len(nb))):
+        if s < len(nb) - 1:
+            x = unsqueeze2(x)          # SqueezeLayer.inverse is the last element of the chain of scale s
+        for b in reversed(range(nb[s])):
+            first = (s == 0 and b == 0)
+            x, it = inverse_fixed_point(lambda v: g_branch(P, s, b, first, v, h), x, atol, rtol)
+            iters.append(it)
+    return x, iters
+
+
+# ------------------------------------------------------------------------------------------------ latent prior flow
+def _wn(P, p):
+    v, g = P[p + 'weight_v'], P[p + 'weight_g']
+    return g * v / v.norm(dim=1, keepdim=True)      # nn.utils.weight_norm, dim=0
+
+
+def _mlp(P, p, z):
+    """NICEMLPBlock.forward (blocks.py:27-34), ELU."""
+    out = F.elu(F.linear(z, P[p + 'fc1.weight'], P[p + 'fc1.bias']))
+    out = F.elu(F.linear(out, P[p + 'fc2.weight'], P[p + 'fc2.bias']))
+    return F.linear(out, _wn(P, p + 'fc3.linear.'), P[p + 'fc3.linear.bias'])
+
+
+def _coupling(P, p, z, skip, up, backward):
+    """NICE1d.forward / backward_analytic (coupling.py:87-145) with Affine (transform.py:56-76)."""
+    d = z.shape[1]
+    if skip:
+        z1, z2 = z[:, 0::2], z[:, 1::2]
+    else:
+        z1, z2 = z[:, :d // 2], z[:, d // 2:]
+    zc, zp = (z1, z2) if up else (z2, z1)
+    mu, ls = _mlp(P, p + 'net.', zc).chunk(2, dim=1)
+    scale = torch.sigmoid(ls + 2.0) + 1e-3
+    if backward:
+        zp = (zp - mu) / (scale + 1e-12)
+        logdet = -scale.log().sum(dim=1)
+    else:
+        zp = scale * zp + mu
+        logdet = scale.log().sum(dim=1)
+    z1, z2 = (zc, zp) if up else (zp, zc)
+    if skip:
+        out = torch.stack([z1, z2], dim=2).reshape(z.shape[0], d)
+    else:
+        out = torch.cat([z1, z2], dim=1)
+    return out, logdet
+
+
+def _actnorm(P, p, z, backward):
+    ls, b = P[p + 'log_scale'], P[p + 'bias']
+    if backward:
+        return (z - b) / (ls.exp() + 1e-8), -ls.sum() * torch.ones(z.shape[0])
+    return z * ls.exp() + b, ls.sum() * torch.ones(z.shape[0])
+
+
+def prior_flow(config, P, z, backward):
+    """PriorFlow.forward / backward (priors/flow.py:172-189).  Returns (out, logdet)."""
+    T = config.flow.wolf_params['discriminator']['prior']['num_steps']
+    ld = torch.zeros(z.shape[0])
+    steps = range(T)
+    for t in (reversed(steps) if backward else steps):
+        p = f'discriminator.prior.flow.steps.{t}.'
+        if not backward:
+            z, l = _actnorm(P, p + 'actnorm.', z, False); ld = ld + l
+            z = F.linear(z, P[p + 'linear.weight']); ld = ld + torch.slogdet(P[p + 'linear.weight'])[1]
+            for name, skip, up in (('coupling1_up', False, True), ('coupling1_dn', False, False)):
+                z, l = _coupling(P, p + f'unit.{name}.', z, skip, up, False); ld = ld + l
+            z, l = _actnorm(P, p + 'unit.actnorm.', z, False); ld = ld + l
+            for name, skip, up in (('coupling2_up', True, True), ('coupling2_dn', True, False)):
+                z, l = _coupling(P, p + f'unit.{name}.', z, skip, up, False); ld = ld + l
+        else:
+            for name, skip, up in (('coupling2_dn', True, False), ('coupling2_up', True, True)):
+                z, l = _coupling(P, p + f'unit.{name}.', z, skip, up, True); ld = ld + l
+            z, l = _actnorm(P, p + 'unit.actnorm.', z, True); ld = ld + l
+            for name, skip, up in (('coupling1_dn', False, False), ('coupling1_up', False, True)):
+                z, l = _coupling(P, p + f'unit.{name}.', z, skip, up, True); ld = ld + l
+            z = F.linear(z, P[p + 'linear.weight_inv']); ld = ld + torch.slogdet(P[p + 'linear.weight_inv'])[1]
+            z, l = _actnorm(P, p + 'actnorm.', z, True); ld = ld + l
+    return z, ld
+
+
+def prior_sample(config, P, eps):
+    """FlowPrior.sample (priors/flow.py:226-230): the flow is built with inverse=True, so fwdpass = backward()."""
+    return prior_flow(config, P, eps, backward=True)[0]
+
+
+def wolf_reverse(config, P, z, eps, atol=1e-5, rtol=1e-5):
+    """flow_forward(config, flow, z, reverse=True) (flow_model.py:53-67) -> WolfCore.forward(reverse=True)
+    (wolf.py:82-89).  `eps` [B,64] is the standard-normal draw of FlowPrior.sample.  Returns (x, h, iters)."""
+    if config.flow.squeeze:
+        z = squeeze2(z)
+    h = prior_sample(config, P, eps)
+    x, iters = resflow_inverse(config, P, z, h, atol, rtol)
+    x = x.reshape(z.shape)
+    if config.flow.squeeze:
+        x = unsqueeze2(x)
+    return x, h, iters

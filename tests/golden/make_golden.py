@@ -222,8 +222,64 @@ def make_pc():
         print('pc', tag, 'rms', float(before.pow(2).mean().sqrt()), 'nfe', nfe)
 
 
+def tiny_flow(cfg, squeeze):
+    """Small wolf flow with the same code paths: 2+2 iResBlocks, 128 hidden channels, 16x16 images."""
+    cfg.flow.nblocks = '2-2'
+    cfg.flow.intermediate_dim = 128
+    cfg.data.image_size = 16
+    cfg.flow.image_size = 16
+    cfg.flow.squeeze = squeeze
+    return cfg
+
+
+def make_flow():
+    """Wolf flow reverse pass (prior sample of h + fixed-point inverse of every iResBlock) and the residual-flow
+    forward (no log-det) with h given, through the reference's own flow_forward / fwdpass."""
+    from oracle import flow as oflow
+    fm = rl.load('flow_models.flow_model')
+    for tag, path, squeeze in (('tiny', 'configs/vp/CIFAR10/indm_fid.py', False), ('tiny_sq', 'configs/vp/CELEBA/indm_fid.py', True)):
+        cfg = rl.get_config(path)
+        tiny_flow(cfg, squeeze)
+        with rl.reference_cwd():
+            flow = fm.create_flow_model(cfg)
+        ref_sd = flow.module.state_dict()
+        shapes = [(k, list(v.shape)) for k, v in ref_sd.items()]
+        # the oracle's shape table is driven by the restated JSON content carried in indm_b200.configs
+        from indm_b200 import configs as pconfigs
+        pcfg = pconfigs.get_config(path)
+        tiny_flow(pcfg, squeeze)
+        sd = oflow.synth_params(pcfg, 21)
+        assert [(k, list(v.shape)) for k, v in sd.items()] == shapes, 'oracle.flow.param_shapes != reference state_dict'
+        flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        flow.eval()
+        with open(os.path.join(HERE, f'shapes_flow_{tag}.json'), 'w') as f:
+            json.dump(shapes, f)
+        B, S = 3, 16
+        rng = np.random.default_rng(23)
+        z = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+        eps = rng.standard_normal((B, 64)).astype(np.float32)
+        real_randn = torch.randn
+        torch.randn = lambda *a, **k: torch.from_numpy(eps)
+        try:
+            with torch.no_grad():
+                x, _ = fm.flow_forward(cfg, flow, torch.from_numpy(z), log_det=None, reverse=True)
+                h = flow.module.discriminator.sample_from_prior(B, torch.device('cpu'))
+        finally:
+            torch.randn = real_randn
+        # forward (no logdet) of the generator flow with that h, on the flow's own input layout
+        from flow_models.resflow.layers.squeeze import SqueezeLayer
+        xin = torch.from_numpy(rng.standard_normal((B, 3, S, S)).astype(np.float32))
+        xin_f = SqueezeLayer(2).forward(xin) if squeeze else xin
+        with torch.no_grad():
+            zf = flow.module.generator.flow.fwdpass(xin_f, h, eval_logdet=False)
+        np.savez_compressed(os.path.join(HERE, f'flow_{tag}.npz'), z=z, eps=eps, x=x.numpy(), h=h.numpy(), xin=xin.numpy(),
+                            zf=zf.numpy(), seed=np.asarray(21))
+        print('flow', tag, 'x rms', float(x.pow(2).mean().sqrt()), 'max|x-z|', float((x - torch.from_numpy(z)).abs().max()),
+              'zf rms', float(zf.pow(2).mean().sqrt()))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

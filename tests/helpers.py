@@ -36,3 +36,13 @@ def max_rel(a, b, floor=1e-6):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / (np.abs(b) + floor * max(np.max(np.abs(b)), 1e-30) + 1e-30)))
+
+
+def tiny_flow(cfg, squeeze):
+    """Same shrink as tests/golden/make_golden.py:tiny_flow."""
+    cfg.flow.nblocks = '2-2'
+    cfg.flow.intermediate_dim = 128
+    cfg.data.image_size = 16
+    cfg.flow.image_size = 16
+    cfg.flow.squeeze = squeeze
+    return cfg

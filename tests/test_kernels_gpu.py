@@ -102,7 +102,7 @@ def test_igemm_conv3x3(dtype, N, S, Cin, Cout, bn):
     o16 = torch.zeros((N, S, S, Cout), device=DEV, dtype=torch.bfloat16)
     L.igemm(dtype=dtype, a=dev_op(nhwc(x), dtype), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dtype), Cout=Cout, taps=9,
             bias=bias.to(DEV), rowbias=rowb.to(DEV), rowbias_ld=Cout + 8, residual=res.to(DEV), res_ld=Cout,
-            scale=0.7071, out_f32=o32, out_bf16=o16, out_ld=Cout, block_n=bn)
+            scale=0.7071, res_scale=0.7071, out_f32=o32, out_bf16=o16, out_ld=Cout, block_n=bn)
     torch.cuda.synchronize()
     want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
     want = (nhwc(want) + rowb[:, None, None, :Cout].double() + res.double()) * 0.7071
@@ -251,7 +251,7 @@ def test_softmax_rows(cols):
 def test_prep_input_and_time_embedding_and_linear():
     x = rnd(3, 3, 8, 8, seed=27)
     out = torch.full((3, 8, 8, 64), 7.0, device=DEV, dtype=torch.bfloat16)
-    L.call('indm_prep_input', P(x), L.ptr(out), 3, 3, 8, 8, 64, 2.0, -1.0, L.DTYPE_BF16)
+    L.call('indm_prep_input', P(x), L.ptr(out), 3, 3, 8, 8, 64, 2.0, -1.0, 0, L.DTYPE_BF16)
     torch.cuda.synchronize()
     want = torch.zeros(3, 8, 8, 64)
     want[..., :3] = nhwc(2 * x - 1)

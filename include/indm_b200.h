@@ -93,6 +93,8 @@ typedef struct indm_igemm {
   float* gn_partial;
   int32_t gn_cpg, gn_groups;
   int32_t block_n;       /* 0 = choose automatically; else 32 / 64 / 128 / 256 */
+  int32_t stride;        /* 0 / 1: unit stride.  2 (taps == 9): 3x3 stride-2 VALID convolution — A is the [N, 2H+1, 2W+1, Cin]
+                            FIR-padded image and H x W the output grid (conv_downsample_2d, models/up_or_down_sampling.py:173-178) */
 } indm_igemm_t;
 
 int indm_igemm(const indm_igemm_t* desc, void* stream);

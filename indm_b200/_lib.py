@@ -34,7 +34,7 @@ class IgemmDesc(C.Structure):
         ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("out_ld", C.c_int64),
         ("tcol0", C.c_int32), ("out_t", C.c_void_p), ("round_tf32_out", C.c_int32),
         ("gn_partial", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_groups", C.c_int32),
-        ("block_n", C.c_int32),
+        ("block_n", C.c_int32), ("stride", C.c_int32),
     ]
 
 

@@ -35,6 +35,7 @@ struct IgemmParams {
   int taps;              // 1 or 9
   int chunks1, chunks2;  // K chunks in segment 1 (per tap) and segment 2
   int batched_b;         // B third coordinate = image index instead of tap
+  int stride;            // 1: 3x3 pad 1 (or 1x1);  2: 3x3 stride 2 pad 0 over an A grid of (2H+1) x (2W+1)
   int stages;
   // epilogue
   const float* bias;
@@ -153,12 +154,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (it < iters1) {
           const int tap = it / p.chunks1;
           const int ch = it - tap * p.chunks1;
-          int dy = 0, dx = 0;
-          if (p.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
+          int ay = y0, ax = x0;
+          if (p.stride == 2) {
+            // valid (pad 0) stride-2 window: input pixel (2y + ky, 2x + kx); the tensor map traverses with element stride 2
+            ay = 2 * y0 + tap / 3;
+            ax = 2 * x0 + tap % 3;
+          } else if (p.taps == 9) {
+            ay += tap / 3 - 1;
+            ax += tap % 3 - 1;
           }
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, x0 + dx, y0 + dy, n0);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
           tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, p.batched_b ? n0 : tap);
         } else {
           const int ch = it - iters1;
@@ -442,6 +447,9 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   p.chunks1 = (d->Cin + kchunk - 1) / kchunk;
   p.chunks2 = d->a2 ? (d->Cin2 + kchunk - 1) / kchunk : 0;
   p.batched_b = d->batched_b;
+  p.stride = d->stride == 2 ? 2 : 1;
+  INDM_CHECK_ARG(d->stride == 0 || d->stride == 1 || d->stride == 2, "igemm: stride must be 1 or 2");
+  INDM_CHECK_ARG(p.stride == 1 || (d->taps == 9 && !d->a2 && !d->batched_b && d->W < 128), "igemm: stride 2 needs taps == 9, no second segment");
   p.bias = d->bias;
   p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld;
@@ -474,11 +482,14 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   CUtensorMap tmA, tmB, tmA2, tmB2;
   {
     const long long ld = d->a_ld ? d->a_ld : d->Cin;
-    const long long img = d->a_img_stride ? d->a_img_stride : (long long)d->H * d->W * ld;
-    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
-    uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)d->W * ld * esz, (uint64_t)img * esz};
-    uint32_t box[4] = {(uint32_t)kchunk, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BN};
-    int rc = indm_make_tmap(&tmA, dt, 4, d->a, dims, str, box, "igemm A");
+    // stride 2: the A grid is the (2H+1) x (2W+1) FIR-padded image (models/up_or_down_sampling.py:173-178), H x W the output grid
+    const int aH = p.stride == 2 ? 2 * d->H + 1 : d->H, aW = p.stride == 2 ? 2 * d->W + 1 : d->W;
+    const long long img = d->a_img_stride ? d->a_img_stride : (long long)aH * aW * ld;
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)aW, (uint64_t)aH, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)aW * ld * esz, (uint64_t)img * esz};
+    uint32_t box[4] = {(uint32_t)kchunk, (uint32_t)(p.BW * p.stride), (uint32_t)(p.BH * p.stride), (uint32_t)p.BN};
+    uint32_t es[4] = {1u, (uint32_t)p.stride, (uint32_t)p.stride, 1u};
+    int rc = indm_make_tmap(&tmA, dt, 4, d->a, dims, str, box, "igemm A", es);
     if (rc) return rc;
   }
   // pick BLOCK_N

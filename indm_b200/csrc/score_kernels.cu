@@ -275,6 +275,30 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
   }
 }
 
+// any K: lanes stride over k (used for the K = 64 conditioning projections of the flow)
+__global__ void linear_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                      void* __restrict__ out, long long N, int K, int O, int act_in, int act_out, int out_dtype) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (o >= O) return;
+  const float b = bias ? bias[o] : 0.f;
+  for (long long n = blockIdx.y; n < N; n += gridDim.y) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float v = in[n * K + k];
+      if (act_in) v = silu_f(v);
+      acc += v * w[(long long)o * K + k];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + b;
+      if (act_out) v = silu_f(v);
+      if (out_dtype == INDM_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[n * O + o] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(out)[n * O + o] = (out_dtype == INDM_DTYPE_TF32) ? round_tf32(v) : v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- FIR resampling on NHWC (4-tap separable kernel)
 // MODE 1: up x2 pad (2,1); MODE 2: down x2 pad (1,1); MODE 3: up=down=1 pad (2,2).
 // out[oy,ox] = sum_{i,j} xp[oy*down + i, ox*down + j] * kf[i][j], kf = flipped k, xp = zero-inserted + padded input.
@@ -463,13 +487,18 @@ extern "C" int indm_linear_f32(const float* in, const float* w, const float* bia
                                int act_in, int act_out, int out_dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(in && w && out && N > 0 && O > 0, "linear: bad arguments");
-  INDM_CHECK_ARG(K % 128 == 0 && K >= 128 && K <= 1024, "linear: K must be a multiple of 128 in [128, 1024] (got %d)", K);
+  INDM_CHECK_ARG(K > 0, "linear: K must be positive");
   const int wpb = 4;
   const int gx = (O + wpb - 1) / wpb;
   // split the batch over grid.y only when there are too few output columns to fill the chip
   int gy = 1;
   while ((long long)gx * gy < 2LL * indm_num_sms() && gy < N) gy *= 2;
   dim3 grid(gx, gy);
+  if (K % 128 != 0 || K > 1024) {
+    linear_generic_kernel<<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in, act_out, out_dtype);
+    INDM_CHECK_LAUNCH("linear");
+    return INDM_OK;
+  }
   switch (K / 128) {
 #define LIN(KV) case KV: linear_kernel<KV><<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in, act_out, out_dtype); break;
     LIN(1) LIN(2) LIN(3) LIN(4) LIN(5) LIN(6) LIN(7) LIN(8)

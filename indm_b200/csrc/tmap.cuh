@@ -28,9 +28,11 @@ static inline indm_encode_tiled_fn indm_get_encode_tiled() {
 
 // rank-R map over a tensor whose fastest dimension is contiguous; dims/box listed fastest-first;
 // strides_bytes[i] = byte stride of dim i+1 (R-1 entries).  128-byte swizzle, zero fill out of bounds.
+// elem_strides (optional): traversal stride per dimension; a box of extent box[i] then delivers ceil(box[i] / stride) elements
+// (how the stride-2 convolution of the input pyramid samples every other pixel without a gather kernel).
 static inline int indm_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
                                  const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                                 const char* what) {
+                                 const char* what, const uint32_t* elem_strides = nullptr) {
   indm_encode_tiled_fn fn = indm_get_encode_tiled();
   if (!fn) {
     indm_set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver?)", what);
@@ -43,7 +45,7 @@ static inline int indm_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int r
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   if (((uintptr_t)base & 15) != 0) {

@@ -1,0 +1,524 @@
+"""Wolf flow (conditional Residual Flow + Gaussian posterior with a latent flow prior) for the INDM hot path.
+
+`WolfCore` is a parameter container whose state-dict is key-for-key the reference's (flow_models/wolf/wolf.py:18-145,
+modules/generators/generator.py:88-109, flows/resflow/resflow_.py:20-518, layers/iresblock.py:14-60,
+layers/base/lipschitz.py:321-441, modules/discriminators/gaussian.py:14-21, modules/encoders/global_encoder.py:12-31,
+nnet/resnets/resnet_batchnorm.py:18-47, modules/discriminators/priors/flow.py:16-217).
+Compute runs on the C-ABI kernels through `FlowEngine` (no PyTorch compute, no CPU path):
+
+  reverse (sampling, wolf.py:82-89):  h = prior-flow(eps) in ONE launch (indm_prior_flow), then for each of the 32
+      iResBlocks the fixed-point inverse x <- y - g(x; h) where g is three tensor-core implicit GEMMs
+      (3x3 c->512 with Sin epilogue, 1x1 512->512 with the per-sample conditioning bias W2(Ah+a)+b2 as row bias and Sin
+      epilogue, 3x3 512->c whose epilogue writes y - g directly in NCHW) and the stop rule is a device-side reduction.
+  forward without log-det (flow_model.py:57-60 with log_det != 0): y = x + g(x; h) with the same three GEMMs.
+
+The Lipschitz-normalised weights W / max(1, |row|_1 / 0.98) are computed once per weight version at pack time, not
+inside every call as the reference does (lipschitz.py:350-363).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+
+COEFF = 0.98
+
+
+# ------------------------------------------------------------------------------------------------ parameter containers
+class _LopConv(nn.Module):
+    def __init__(self, cin, cout, k, cond_dim=None):
+        super().__init__()
+        bound = 1.0 / math.sqrt(cin * k * k)
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        self.register_buffer('scale', torch.tensor(0.))
+        if cond_dim is not None:
+            self.h_net = nn.Module()
+            self.h_net.net = nn.Module()
+            b2 = 1.0 / math.sqrt(cond_dim)
+            self.h_net.net.weight = nn.Parameter(torch.empty(cin, cond_dim).uniform_(-b2, b2))
+            self.h_net.net.bias = nn.Parameter(torch.empty(cin).uniform_(-b2, b2))
+
+
+class _Placeholder(nn.Module):
+    """parameter-free chain element (Sin activation / SqueezeLayer): keeps ModuleList indices aligned with the reference"""
+
+    def __init__(self, what):
+        super().__init__()
+        self.what = what
+
+
+class _IResBlock(nn.Module):
+    def __init__(self, c, idim, first):
+        super().__init__()
+        self.geom_p = nn.Parameter(torch.tensor(np.log(0.5) - np.log(1. - 0.5), dtype=torch.float32))
+        self.lamb = nn.Parameter(torch.tensor(2.))
+        self.register_buffer('last_n_samples', torch.zeros(1))
+        self.register_buffer('last_firmom', torch.zeros(1))
+        self.register_buffer('last_secmom', torch.zeros(1))
+        net = [] if first else [_Placeholder('sin')]
+        net += [_LopConv(c, idim, 3), _Placeholder('sin'), _LopConv(idim, idim, 1, cond_dim=64), _Placeholder('sin'), _LopConv(idim, c, 3)]
+        self.nnet = nn.ModuleList(net)
+        self.first = first
+        self.channels = c
+
+    def convs(self):
+        return [m for m in self.nnet if isinstance(m, _LopConv)]
+
+
+class _Stack(nn.Module):
+    def __init__(self, c, idim, n_blocks, squeeze, first_scale):
+        super().__init__()
+        chain = [_IResBlock(c, idim, first_scale and i == 0) for i in range(n_blocks)]
+        if squeeze:
+            chain.append(_Placeholder('squeeze'))
+        self.chain = nn.ModuleList(chain)
+
+
+class _ResidualFlow(nn.Module):
+    def __init__(self, config, input_shape):
+        super().__init__()
+        nb = [int(v) for v in config.flow.nblocks.split('-')]
+        c, h, w = input_shape
+        stacks = []
+        for i, n in enumerate(nb):
+            stacks.append(_Stack(c, config.flow.intermediate_dim, n, i < len(nb) - 1, i == 0))
+            c *= 4
+        self.transforms = nn.ModuleList(stacks)
+        self.n_blocks = nb
+
+
+class _BN(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer('running_mean', torch.zeros(c))
+        self.register_buffer('running_var', torch.ones(c))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+
+class _ConvNoBias(nn.Module):
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        bound = 1.0 / math.sqrt(cin * k * k)
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k).uniform_(-bound, bound))
+
+
+class _EncBlock(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = _ConvNoBias(cin, cout, 3)
+        self.bn1 = _BN(cout)
+        self.conv2 = _ConvNoBias(cout, cout, 3)
+        self.bn2 = _BN(cout)
+        if stride != 1 or cin != cout:
+            self.downsample = nn.ModuleList([_ConvNoBias(cin, cout, 1), _BN(cout)])
+        self.stride = stride
+
+
+class _Encoder(nn.Module):
+    def __init__(self, p):
+        super().__init__()
+        self.net = nn.Module()
+        inp = p['in_planes']
+        for lv, hid in enumerate(p['hidden_planes']):
+            r = nn.Module()
+            r.main = nn.ModuleList([_EncBlock(inp, hid, 1), _EncBlock(hid, hid, 2)])
+            setattr(self.net, f'resnet{lv}', r)
+            inp = hid
+        top = nn.Module()
+        bound = 1.0 / math.sqrt(inp)
+        top.weight = nn.Parameter(torch.empty(p['out_planes'], inp, 1, 1).uniform_(-bound, bound))
+        top.bias = nn.Parameter(torch.zeros(p['out_planes']))
+        self.net.top = top
+
+
+class _WNLinear(nn.Module):
+    """legacy nn.utils.weight_norm layout: bias, weight_g [out,1], weight_v [out,in] (nnet/weight_norm.py:8-40)"""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear = nn.Module()
+        self.linear.bias = nn.Parameter(torch.zeros(cout))
+        v = torch.randn(cout, cin) * 0.05
+        self.linear.weight_g = nn.Parameter(v.norm(dim=1, keepdim=True))
+        self.linear.weight_v = nn.Parameter(v)
+
+
+class _Lin(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        bound = 1.0 / math.sqrt(cin)
+        self.weight = nn.Parameter(torch.empty(cout, cin).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _Coupling(nn.Module):
+    def __init__(self, d, hf):
+        super().__init__()
+        self.net = nn.Module()
+        self.net.fc1 = _Lin(d // 2, hf)
+        self.net.fc2 = _Lin(hf, hf)
+        self.net.fc3 = _WNLinear(hf, d)
+
+
+class _ActNorm1d(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.log_scale = nn.Parameter(torch.randn(d) * 0.05)
+        self.bias = nn.Parameter(torch.zeros(d))
+
+
+class _InvLinear(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        w = torch.empty(d, d)
+        nn.init.orthogonal_(w)
+        self.weight = nn.Parameter(w)
+        self.register_buffer('weight_inv', w.inverse().clone())
+
+    def sync(self):
+        self.weight_inv.copy_(self.weight.data.inverse())
+
+
+class _PriorStep(nn.Module):
+    def __init__(self, d, hf):
+        super().__init__()
+        self.actnorm = _ActNorm1d(d)
+        self.linear = _InvLinear(d)
+        self.unit = nn.Module()
+        self.unit.coupling1_up = _Coupling(d, hf)
+        self.unit.coupling1_dn = _Coupling(d, hf)
+        self.unit.actnorm = _ActNorm1d(d)
+        self.unit.coupling2_up = _Coupling(d, hf)
+        self.unit.coupling2_dn = _Coupling(d, hf)
+
+
+class WolfCore(nn.Module):
+    """flow_models/wolf/wolf.py:18 — generator (ResidualFlow) + discriminator (encoder, fc, flow prior)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        wp = config.flow.wolf_params
+        c, s = config.data.num_channels, config.data.image_size
+        self.input_shape = (c * 4, s // 2, s // 2) if config.flow.squeeze else (c, s, s)
+        self.generator = nn.Module()
+        self.generator.flow = _ResidualFlow(config, self.input_shape)
+        d = wp['discriminator']
+        self.discriminator = nn.Module()
+        self.discriminator.encoder = _Encoder(d['encoder'])
+        self.discriminator.fc = _WNLinear(d['in_dim'], 2 * d['dim'])
+        self.discriminator.prior = nn.Module()
+        self.discriminator.prior.flow = nn.Module()
+        pr = d['prior']
+        self.discriminator.prior.flow.steps = nn.ModuleList([_PriorStep(pr['in_features'], pr['hidden_features'])
+                                                             for _ in range(pr['num_steps'])])
+        self.latent_dim = d['dim']
+        self._engines = {}
+        self.compute_mode = 'bf16'
+
+    @classmethod
+    def from_params(cls, params, config=None):
+        """WolfCore.from_params (wolf.py:132-145); `params` is the JSON dict (must equal config.flow.wolf_params)."""
+        return cls(config)
+
+    def add_config(self, config):
+        self.config = config
+
+    def blocks(self):
+        """[(scale, block index, module)] in forward order"""
+        out = []
+        for s, st in enumerate(self.generator.flow.transforms):
+            for b, m in enumerate(st.chain):
+                if isinstance(m, _IResBlock):
+                    out.append((s, b, m))
+        return out
+
+    def engine(self, batch, mode=None):
+        mode = mode or self.compute_mode
+        dev = next(self.parameters()).device
+        key = (int(batch), mode, str(dev))
+        e = self._engines.get(key)
+        if e is None:
+            e = FlowEngine(self, batch, mode, dev)
+            self._engines[key] = e
+        return e
+
+    def forward(self, data, y=None, n_bits=8, nsamples=1, reverse=False, eval_logdet=True, *, eps=None, h=None, seed=0,
+                atol=1e-5, rtol=1e-5):
+        """wolf.py:81-130.  reverse=True: sample h from the prior (or use `eps` / `h` if given) and invert the flow.
+        reverse=False needs the posterior encoder + power-series log-det (SURVEY.md §8 rows F2/F3 forward): `h=` must
+        be supplied and eval_logdet must be False until those land on the CUDA path."""
+        if not data.is_cuda:
+            raise RuntimeError('indm_b200 WolfCore needs CUDA tensors: there is no CPU / PyTorch fallback path')
+        eng = self.engine(data.shape[0])
+        if reverse:
+            return eng.reverse(data, eps=eps, h=h, seed=seed, atol=atol, rtol=rtol)
+        if h is None or eval_logdet:
+            raise NotImplementedError('wolf forward with posterior encoder / log-det estimator is not on the CUDA path yet; '
+                                      'pass h= and eval_logdet=False for the residual-flow forward map')
+        return eng.forward_map(data, h)
+
+
+# ------------------------------------------------------------------------------------------------ engine
+class FlowEngine:
+    def __init__(self, core, batch, mode, dev):
+        if dev.type != 'cuda':
+            raise RuntimeError('FlowEngine needs a CUDA device')
+        L.lib()
+        self.core, self.N, self.mode, self.dev = core, int(batch), mode, dev
+        self.dt = L.DTYPE_BF16 if mode == 'bf16' else L.DTYPE_TF32
+        self.tdtype = torch.bfloat16 if mode == 'bf16' else torch.float32
+        self.kchunk = 64 if mode == 'bf16' else 32
+        self.idim = core.config.flow.intermediate_dim
+        self.blocks = core.blocks()
+        self.nb = core.generator.flow.n_blocks
+        self._version = None
+        self.iterations = []          # fixed-point iterations of the last reverse() call, per block
+        N, idim = self.N, self.idim
+        c0, h0, w0 = core.input_shape
+        # operand / activation buffers, sized for the largest scale (scale 0) and reused by every block
+        self.cpad = [((c0 * 4 ** s + self.kchunk - 1) // self.kchunk) * self.kchunk for s in range(len(self.nb))]
+        self.a0 = [torch.empty((N, h0 >> s, w0 >> s, self.cpad[s]), device=dev, dtype=self.tdtype) for s in range(len(self.nb))]
+        self.u1 = torch.empty((N, h0, w0, idim), device=dev, dtype=self.tdtype)
+        self.u2 = torch.empty((N, h0, w0, idim), device=dev, dtype=self.tdtype)
+        self.flag = torch.zeros((1,), device=dev)
+        self.h = torch.empty((N, core.latent_dim), device=dev)
+        self.eps = torch.empty((N, core.latent_dim), device=dev)
+        self.cond = torch.empty((N, len(self.blocks) * idim), device=dev)
+        self.w = {}
+        self._alloc_weights()
+
+    # ---- weights
+    def _alloc_weights(self):
+        dev, idim = self.dev, self.idim
+        for s, b, m in self.blocks:
+            c = m.channels
+            cp = self.cpad[s]
+            self.w[(s, b)] = dict(w1=torch.zeros((9, idim, cp), device=dev, dtype=self.tdtype), b1=torch.empty((idim,), device=dev),
+                                  w2=torch.empty((idim, idim), device=dev, dtype=self.tdtype),
+                                  w3=torch.empty((9, c, idim), device=dev, dtype=self.tdtype), b3=torch.empty((c,), device=dev))
+        nblk = len(self.blocks)
+        self.cond_w = torch.empty((nblk * idim, self.core.latent_dim), device=dev)
+        self.cond_b = torch.empty((nblk * idim,), device=dev)
+        # prior flow program
+        self.prior_params = None
+        self.prior_ops = {}
+
+    def _round(self, w):
+        if self.mode == 'bf16':
+            return w.to(torch.bfloat16)
+        i = w.float().contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    @staticmethod
+    def _lop(w):
+        """LopConv2d.compute_weight, domain = codomain = inf (lipschitz.py:350-359): rows scaled to L1 norm <= 0.98"""
+        scale = w.abs().reshape(w.shape[0], -1).sum(dim=1)
+        return w / torch.clamp(scale / COEFF, min=1.0).reshape(-1, 1, 1, 1), scale.max()
+
+    def version(self):
+        return sum(p._version for p in self.core.parameters()) + sum(b._version for b in self.core.buffers())
+
+    def load_weights(self):
+        dev = self.dev
+        with torch.no_grad():
+            for i, (s, b, m) in enumerate(self.blocks):
+                cv1, cv2, cv3 = m.convs()
+                W = self.w[(s, b)]
+                w1, sc1 = self._lop(cv1.weight.detach().to(dev, torch.float32))
+                w2, sc2 = self._lop(cv2.weight.detach().to(dev, torch.float32))
+                w3, sc3 = self._lop(cv3.weight.detach().to(dev, torch.float32))
+                cv1.scale.copy_(sc1); cv2.scale.copy_(sc2); cv3.scale.copy_(sc3)      # lipschitz.py:353-354
+                co, ci = w1.shape[:2]
+                W['w1'][:, :, :ci].copy_(self._round(w1.permute(2, 3, 0, 1).reshape(9, co, ci)))
+                W['b1'].copy_(cv1.bias.detach())
+                w2m = w2.reshape(w2.shape[0], w2.shape[1])
+                W['w2'].copy_(self._round(w2m))
+                W['w3'].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9, w3.shape[0], w3.shape[1])))
+                W['b3'].copy_(cv3.bias.detach())
+                # conditioning: conv1x1(u + (A h + a)) + b2 = conv1x1(u) + (W2 A) h + (W2 a + b2)   (lipschitz.py:431-435)
+                A = cv2.h_net.net.weight.detach().to(dev, torch.float32)
+                a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
+                # use the operand-rounded W2 so the folded bias matches what the tensor cores apply to u
+                w2r = W['w2'].float()
+                self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
+                self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
+            self._pack_prior()
+        self._version = self.version()
+
+    def _pack_prior(self):
+        dev = self.dev
+        steps = self.core.discriminator.prior.flow.steps
+        chunks, off = [], 0
+
+        def put(t):
+            nonlocal off
+            t = t.detach().to(dev, torch.float32).reshape(-1)
+            o = off
+            chunks.append(t)
+            off += t.numel()
+            return o
+
+        def coupling(cp):
+            n = cp.net
+            v, g = n.fc3.linear.weight_v.detach().to(dev, torch.float32), n.fc3.linear.weight_g.detach().to(dev, torch.float32)
+            w3 = g * v / v.norm(dim=1, keepdim=True)
+            return [put(n.fc1.weight), put(n.fc1.bias), put(n.fc2.weight), put(n.fc2.bias), put(w3), put(n.fc3.linear.bias)]
+
+        rec = []
+        for st in steps:
+            rec.append(dict(an=[put(st.actnorm.log_scale), put(st.actnorm.bias)], W=put(st.linear.weight), Winv=put(st.linear.weight_inv),
+                            c1u=coupling(st.unit.coupling1_up), c1d=coupling(st.unit.coupling1_dn),
+                            uan=[put(st.unit.actnorm.log_scale), put(st.unit.actnorm.bias)],
+                            c2u=coupling(st.unit.coupling2_up), c2d=coupling(st.unit.coupling2_dn),
+                            ld_w=float(torch.slogdet(st.linear.weight.detach().double().cpu())[1]),
+                            ld_winv=float(torch.slogdet(st.linear.weight_inv.detach().double().cpu())[1])))
+        self.prior_params = torch.cat(chunks).contiguous()
+
+        def op(kind, backward, offs, skip=0, up=0):
+            o = L.FlowOp()
+            o.kind, o.backward, o.split_skip, o.up = kind, backward, skip, up
+            for i, v in enumerate(offs):
+                o.off[i] = v
+            return o
+
+        # backward program = FlowPrior.sample (priors/flow.py:226-230 -> PriorFlow.backward :181-189)
+        bw, ld_b = [], 0.0
+        for r in reversed(rec):
+            bw += [op(2, 1, r['c2d'], 1, 0), op(2, 1, r['c2u'], 1, 1), op(0, 1, r['uan']), op(2, 1, r['c1d'], 0, 0), op(2, 1, r['c1u'], 0, 1),
+                   op(1, 1, [r['Winv']]), op(0, 1, r['an'])]
+            ld_b += r['ld_winv']
+        fw, ld_f = [], 0.0
+        for r in rec:
+            fw += [op(0, 0, r['an']), op(1, 0, [r['W']]), op(2, 0, r['c1u'], 0, 1), op(2, 0, r['c1d'], 0, 0), op(0, 0, r['uan']),
+                   op(2, 0, r['c2u'], 1, 1), op(2, 0, r['c2d'], 1, 0)]
+            ld_f += r['ld_w']
+        for name, prog, ld in (('backward', bw, ld_b), ('forward', fw, ld_f)):
+            arr = (L.FlowOp * len(prog))(*prog)
+            buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            self.prior_ops[name] = (buf, len(prog), ld)
+
+    # ---- building blocks
+    def prior_flow(self, z, direction, want_logdet=False):
+        buf, n, ld = self.prior_ops[direction]
+        out = torch.empty_like(z)
+        logdet = torch.empty((z.shape[0],), device=self.dev) if want_logdet else None
+        L.call('indm_prior_flow', L.ptr(z), L.ptr(out), L.ptr(logdet), L.ptr(self.prior_params), L.ptr(buf), n, ctypes.c_float(ld),
+               z.shape[0])
+        return (out, logdet) if want_logdet else out
+
+    def _cond_table(self, h):
+        nblk = len(self.blocks)
+        L.call('indm_linear_f32', L.ptr(h), L.ptr(self.cond_w), L.ptr(self.cond_b), L.ptr(self.cond), self.N, self.core.latent_dim,
+               nblk * self.idim, 0, 0, L.DTYPE_F32)
+
+    def _g(self, i, s, m, x_nchw, out, residual, scale):
+        """out = scale * g(x; h) + residual, all NCHW fp32 [N, c, H, W] at scale s; block index i selects the cond bias."""
+        N, idim = self.N, self.idim
+        c = m.channels
+        _, h0, w0 = self.core.input_shape
+        H, Wd = h0 >> s, w0 >> s
+        W = self.w[(self.blocks[i][0], self.blocks[i][1])]
+        a0 = self.a0[s]
+        u1 = self.u1.view(-1)[:N * H * Wd * idim].view(N, H, Wd, idim)
+        u2 = self.u2.view(-1)[:N * H * Wd * idim].view(N, H, Wd, idim)
+        L.call('indm_prep_input', L.ptr(x_nchw), L.ptr(a0), N, c, H, Wd, self.cpad[s], ctypes.c_float(1.0), ctypes.c_float(0.0),
+               0 if m.first else 1, self.dt)
+        okw = dict(out_bf16=u1) if self.mode == 'bf16' else dict(out_f32=u1, round_tf32_out=1)
+        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.cpad[s], b=W['w1'], Cout=idim, taps=9, bias=W['b1'], act=1, out_ld=idim, **okw)
+        okw = dict(out_bf16=u2) if self.mode == 'bf16' else dict(out_f32=u2, round_tf32_out=1)
+        L.igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
+                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, **okw)
+        L.igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=c, taps=9, bias=W['b3'], scale=scale, residual=residual,
+                res_scale=1.0, out_mode=1, out_f32=out)
+
+    def _ensure(self):
+        if self._version != self.version():
+            self.load_weights()
+
+    # ---- public passes
+    def reverse(self, z, eps=None, h=None, seed=0, atol=1e-5, rtol=1e-5, max_iter=1000):
+        """WolfCore.forward(reverse=True) (wolf.py:82-89) on the flow's own input layout (flow_forward has already applied
+        SqueezeLayer when flow.squeeze): h ~ prior, then ResidualFlow.bwdpass(z, h).  Returns x with z's shape."""
+        self._ensure()
+        cfg = self.core.config
+        N = self.N
+        z = z.float().contiguous()
+        shape = z.shape
+        if h is None:
+            if eps is None:
+                L.call('indm_randn_f32', L.ptr(self.eps), self.eps.numel(), seed, 0x7F10)
+                eps = self.eps
+            h = self.prior_flow(eps.float().contiguous(), 'backward')
+        self.h.copy_(h)
+        self._cond_table(self.h)
+        nb = self.nb
+        x = z
+        if len(nb) > 1:   # resflow_.py:331-333
+            x = x.view(x.shape[0], x.shape[1], x.shape[2] // 2, x.shape[3] // 2, 2, 2).permute(0, 1, 5, 2, 3, 4) \
+                 .reshape(x.shape[0], x.shape[1], x.shape[2], 2, x.shape[3] // 2).permute(0, 1, 3, 2, 4).reshape(x.shape)
+        c0, h0, w0 = self.core.input_shape
+        k = len(nb) - 1
+        x = x.reshape(N, c0 * 4 ** k, h0 >> k, w0 >> k).contiguous()
+        self.iterations = []
+        idx_of = {(s, b): i for i, (s, b, _) in enumerate(self.blocks)}
+        for s in reversed(range(len(nb))):
+            if s < len(nb) - 1:
+                x = torch.nn.functional.pixel_shuffle(x, 2).contiguous()      # SqueezeLayer.inverse: a pure permutation
+            blks = [(b, m) for (ss, b, m) in self.blocks if ss == s]
+            for b, m in reversed(blks):
+                i = idx_of[(s, b)]
+                y = x
+                cur = y
+                nxt = torch.empty_like(y)
+                it = 0
+                while True:
+                    self._g(i, s, m, cur, nxt, y, -1.0)                       # nxt = y - g(cur)
+                    L.call('indm_fixed_point_check', L.ptr(nxt), L.ptr(cur), L.ptr(y), y.numel(), ctypes.c_float(atol), ctypes.c_float(rtol),
+                           L.ptr(self.flag))
+                    conv = float(self.flag.item()) < 1.0
+                    cur, nxt = nxt, (torch.empty_like(y) if cur is y else cur)
+                    if conv:
+                        break
+                    it += 1
+                    if it > max_iter:
+                        break
+                self.iterations.append(it)
+                x = cur
+        return x.reshape(shape)
+
+    def forward_map(self, x, h):
+        """ResidualFlow.fwdpass(x, h, eval_logdet=False) on the flow's own input layout (resflow_.py:310-324)."""
+        self._ensure()
+        N = self.N
+        x = x.float().contiguous()
+        shape = x.shape
+        self.h.copy_(h)
+        self._cond_table(self.h)
+        nb = self.nb
+        for s in range(len(nb)):
+            for i, (ss, b, m) in enumerate(self.blocks):
+                if ss != s:
+                    continue
+                out = torch.empty_like(x)
+                self._g(i, s, m, x, out, x, 1.0)
+                x = out
+            if s < len(nb) - 1:
+                x = _squeeze2(x).contiguous()
+        out = x.reshape(N, -1)
+        if len(nb) > 1:
+            out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
+        else:
+            out = out.view(shape)
+        return out.contiguous()
+
+
+def _squeeze2(x):
+    n, c, h, w = x.shape
+    return x.reshape(n, c, h // 2, 2, w // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(n, c * 4, h // 2, w // 2)

@@ -346,8 +346,27 @@ class ScoreEngine:
         nlev = len(cfg.model.ch_mult)
         attn_res = tuple(cfg.model.attn_resolutions)
         pin = cfg.model.progressive_input.lower()
-        if pin != 'none':
-            raise NotImplementedError("progressive_input='residual' (VE configs): strided pyramid conv lands next")
+        odt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32
+
+        def pyramid_block(ds, pyr, pyr_c, pyr_dt, Hi, Wi, h, Cout):
+            """input pyramid of progressive_input='residual' (models/ncsnpp.py:319-326): FIR pad-(2,2) filter
+            -> 3x3 stride-2 VALID conv (+bias) -> (pyramid + h) / sqrt(2), written as the new fp32 residual stream."""
+            k1 = np.asarray(ds.fir_kernel, dtype=np.float32)
+            k1 = k1 / k1.sum()
+            self.keep.append(k1)
+            fir_out = self._op_t((N, Hi + 1, Wi + 1, pyr_c))
+            self._call('indm_fir_nhwc', pyr, fir_out, pyr_dt, odt, ctypes.c_int64(N), Hi, Wi, pyr_c,
+                       k1.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 3)
+            wp = self._op_t((9, Cout, pyr_c)); self._pack_conv(wp, ds.Conv2d_0.weight, cin_pad=pyr_c)
+            bp = self._alloc((Cout,)); self._pack_f32(bp, [ds.Conv2d_0.bias])
+            out = self._alloc((N, Hi // 2, Wi // 2, Cout))
+            sc = inv_sqrt2 if m.skip_rescale else 1.0
+            self._igemm(a=fir_out, N=N, H=Hi // 2, W=Wi // 2, Cin=pyr_c, b=wp, Cout=Cout, taps=9, stride=2, bias=bp, scale=sc,
+                        residual=h, res_ld=Cout, res_scale=sc, out_f32=out, out_ld=Cout)
+            return out
+
+        # the pyramid starts from the network input (after the 2x-1 affine): the padded NHWC operand copy of it
+        pyr, pyr_c, pyr_dt = x_nhwc, cpad, (L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32)
         hs = [(h0, nf)]
         H = W = S
         for lv in range(nlev):
@@ -362,7 +381,14 @@ class ScoreEngine:
             if lv != nlev - 1:
                 x, Cx = hs[-1]
                 rb = mods[idx]; idx += 1
+                Hi, Wi = H, W
                 h, H, W = res_block(rb, x, Cx, None, 0, H, W)
+                if pin == 'residual':
+                    ds = mods[idx]; idx += 1
+                    h = pyramid_block(ds, pyr, pyr_c, pyr_dt, Hi, Wi, h, rb.out_ch)
+                    pyr, pyr_c, pyr_dt = h, rb.out_ch, L.DTYPE_F32
+                elif pin != 'none':
+                    raise NotImplementedError(f'progressive_input={pin!r} is not used by any INDM config')
                 hs.append((h, rb.out_ch))
         h, Ch = hs[-1]
         rb = mods[idx]; idx += 1

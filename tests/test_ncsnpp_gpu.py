@@ -36,7 +36,7 @@ def _model(cfg, seed=11):
 
 
 @pytest.mark.parametrize("mode", ['tf32', 'bf16'])
-@pytest.mark.parametrize("tag", ['tiny_vp', 'vp_cifar'])
+@pytest.mark.parametrize("tag", ['tiny_vp', 'vp_cifar', 'tiny_ve', 've_cifar'])
 def test_score_network_matches_reference(tag, mode):
     g = load_npz(f'ncsnpp_{tag}.npz')
     cfg = _cfg(tag)
@@ -45,7 +45,9 @@ def test_score_network_matches_reference(tag, mode):
     sde = sde_lib.get_sde(cfg)
     x, t = torch.from_numpy(g['x']).cuda(), torch.from_numpy(g['t']).cuda()
     with torch.no_grad():
-        raw = model(x, t * 999)
+        # time_cond as get_score_fn passes it (models/utils.py:167-168 VP: 999 t; :183-184 VE: sigma(t))
+        labels = t * 999 if tag.endswith('vp') or tag.startswith('vp') else sde.marginal_prob(torch.zeros_like(t)[:, None, None, None], t)[1]
+        raw = model(x, labels)
         score = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)(x, t)
     torch.cuda.synchronize()
     e_raw, e_score = rel_l2(raw.cpu().numpy(), g['raw']), rel_l2(score.cpu().numpy(), g['score'])
@@ -54,11 +56,14 @@ def test_score_network_matches_reference(tag, mode):
 
 
 @pytest.mark.parametrize("mode", ['tf32', 'bf16'])
-def test_pc_sampler_trajectory_matches_reference(mode):
-    """6-step reverse-diffusion PC sampling, noise replayed from the reference run (tests/golden/pc_tiny_vp.npz)."""
-    g = load_npz('pc_tiny_vp.npz')
-    cfg = _cfg('tiny_vp')
-    cfg.sampling.method, cfg.sampling.predictor, cfg.sampling.corrector = 'pc', 'reverse_diffusion', 'none'
+@pytest.mark.parametrize("tag", ['tiny_vp', 'tiny_ve'])
+def test_pc_sampler_trajectory_matches_reference(tag, mode):
+    """6-step PC sampling, noise replayed from the reference run (tests/golden/pc_tiny_*.npz): reverse diffusion with no
+    corrector (VP, BASELINE config 2) and reverse diffusion + Langevin corrector (VE, configs/ve/CIFAR10/indm.py:33-35)."""
+    g = load_npz(f'pc_{tag}.npz')
+    cfg = _cfg(tag)
+    cfg.sampling.method, cfg.sampling.predictor = 'pc', 'reverse_diffusion'
+    cfg.sampling.corrector = 'none' if tag == 'tiny_vp' else 'langevin'
     cfg.sampling.num_scales = int(g['num_scales'])
     cfg.flow.model = 'identity'
     model = _model(cfg)
@@ -66,7 +71,9 @@ def test_pc_sampler_trajectory_matches_reference(mode):
     sde = sde_lib.get_sde(cfg)
     B, S = g['prior'].shape[0], cfg.data.image_size
     fn = sampling.get_sampling_fn(cfg, sde, (B, 3, S, S), lambda v: v, float(g['eps']))
-    before, after, nfe = fn(model, None, prior=torch.from_numpy(g['prior']), noise=[torch.from_numpy(n) for n in g['noises']])
+    # g['prior'] is the raw standard-normal draw; VESDE.prior_sampling scales it by sigma_max (sde_lib.py:289-293)
+    prior = torch.from_numpy(g['prior']) * (cfg.model.sigma_max if tag == 'tiny_ve' else 1.0)
+    before, after, nfe = fn(model, None, prior=prior, noise=[torch.from_numpy(n) for n in g['noises']])
     torch.cuda.synchronize()
     err = rel_l2(before.cpu().numpy(), g['out'])
     print(f'pc trajectory {mode}: rel-L2 {err:.3e}')

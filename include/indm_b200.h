@@ -18,7 +18,7 @@ extern "C" {
 #endif
 
 #define INDM_DTYPE_BF16 0 /* bf16 operands, fp32 accumulate (production mode)      */
-#define INDM_DTYPE_TF32 1 /* fp32 storage, tf32 tensor-core math (validation mode) */
+#define INDM_DTYPE_TF32 1 /* fp32 storage, error-compensated tf32 tensor-core math, 3 MMAs per product (validation mode) */
 #define INDM_DTYPE_F32 2  /* plain fp32 (only where stated)                        */
 
 const char* indm_version(void);
@@ -87,7 +87,7 @@ typedef struct indm_igemm {
   int64_t out_ld;
   int32_t tcol0;
   void* out_t;
-  int32_t round_tf32_out; /* round fp32 outputs to tf32 (rna) */
+  int32_t round_tf32_out; /* ignored (kept for ABI stability): TF32-mode operands are plain fp32, split hi/lo in-kernel */
   /* optional fused GroupNorm statistics of the stored output: gn_partial[n][g][2] += (sum, sum of squares) over
    * the tile (atomicAdd; caller zeroes it).  gn_cpg = channels per group. */
   float* gn_partial;

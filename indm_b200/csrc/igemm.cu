@@ -97,11 +97,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
-  uint64_t* bars = (uint64_t*)(sB + (size_t)p.stages * B_BYTES);
+  // TF32 mode is error-compensated (3xTF32): every landed fp32 stage is split by two helper warps into hi = rna(v) (in place)
+  // and lo = v - hi (second buffer), and the issuer accumulates a_hi*b_hi + a_lo*b_hi + a_hi*b_lo.
+  uint8_t* sAlo = sB + (size_t)p.stages * B_BYTES;
+  uint8_t* sBlo = sAlo + (TF32 ? (size_t)p.stages * A_BYTES : 0);
+  uint64_t* bars = (uint64_t*)(sBlo + (TF32 ? (size_t)p.stages * B_BYTES : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* acc_bar = bars + 2 * kMaxStages;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 1);
+  uint64_t* split_bar = bars + 2 * kMaxStages + 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +133,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      if (TF32) mbar_init(&split_bar[s], 64);
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
@@ -183,17 +189,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(TF32 ? &split_bar[stage] : &full_bar[stage], phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)stage * A_BYTES));
         const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
+        if (TF32) {
+          const uint64_t alo = umma_desc_sw128(smem_u32(sAlo + (size_t)stage * A_BYTES));
+          const uint64_t blo = umma_desc_sw128(smem_u32(sBlo + (size_t)stage * B_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          if (TF32)
-            umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
-          else
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t o = (uint64_t)(2 * k);
+            umma_tf32(tmem_base, alo + o, bdesc + o, IDESC, (it | k) != 0);   // small terms first
+            umma_tf32(tmem_base, adesc + o, blo + o, IDESC, 1u);
+            umma_tf32(tmem_base, adesc + o, bdesc + o, IDESC, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
         if (++stage == p.stages) {
@@ -204,6 +219,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       umma_commit(acc_bar);  // accumulator complete
     }
     __syncwarp();
+  } else if (TF32) {
+    // ================= operand splitter (warps 2, 3): hi/lo decomposition of each landed stage, elementwise, so the
+    // swizzled placement is irrelevant: lo lives at the same offset of the twin buffer
+    const int t = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      float4* a = reinterpret_cast<float4*>(sA + (size_t)stage * A_BYTES);
+      float4* al = reinterpret_cast<float4*>(sAlo + (size_t)stage * A_BYTES);
+      for (int i = t; i < A_BYTES / 16; i += 64) {
+        const float4 v = a[i];
+        const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+        a[i] = h;
+        al[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      float4* b = reinterpret_cast<float4*>(sB + (size_t)stage * B_BYTES);
+      float4* bl = reinterpret_cast<float4*>(sBlo + (size_t)stage * B_BYTES);
+      for (int i = t; i < B_BYTES / 16; i += 64) {
+        const float4 v = b[i];
+        const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+        b[i] = h;
+        bl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(&split_bar[stage]);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
   }
 
   // ================= epilogue: all 4 warps
@@ -368,11 +414,11 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
                  int m_tiles, int n_tiles, cudaStream_t stream) {
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
-  const int stage_bytes = A_BYTES + B_BYTES;
-  const int overhead = 1024 + (2 * kMaxStages + 2) * 8;
+  const int stage_bytes = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
+  const int overhead = 1024 + (3 * kMaxStages + 2) * 8;
   const int iters = p.taps * p.chunks1 + p.chunks2;
   // aim for >= 2 co-resident CTAs per SM when the tile is small enough; never more stages than K iterations
-  int budget = (BLOCK_N >= 256) ? 200 * 1024 : 100 * 1024;
+  int budget = (BLOCK_N >= 256 || TF32) ? 200 * 1024 : 100 * 1024;
   int stages = (budget - overhead) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > iters) stages = iters;
@@ -463,7 +509,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   p.out_mode = d->out_mode;
   p.tcol0 = d->tcol0;
   p.out_t = (__nv_bfloat16*)d->out_t;
-  p.round_tf32_out = d->round_tf32_out;
+  p.round_tf32_out = 0;  // legacy flag, ignored: TF32 operands stay full fp32 (the kernel splits hi/lo itself)
   p.gn_partial = d->gn_partial;
   p.gn_cpg = d->gn_cpg;
   p.gn_groups = d->gn_groups;

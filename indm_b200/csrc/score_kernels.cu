@@ -33,12 +33,14 @@ struct Vec4<__nv_bfloat16> {
     *reinterpret_cast<uint2*>(p) = r;
   }
 };
-// fp32 storage holding tf32-rounded values (operands of kind::tf32 MMAs)
+// TF32-mode operands are stored as plain fp32: the GEMM kernel performs the tf32 hi/lo split itself (3xTF32, igemm.cu),
+// so producers must NOT pre-round.
+__device__ __forceinline__ float tf32_operand(float v) { return v; }
 struct Tf32Out {};
 template <>
 struct Vec4<Tf32Out> {
   static __device__ __forceinline__ void store(float* p, float4 v) {
-    *reinterpret_cast<float4*>(p) = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    *reinterpret_cast<float4*>(p) = make_float4(tf32_operand(v.x), tf32_operand(v.y), tf32_operand(v.z), tf32_operand(v.w));
   }
 };
 
@@ -196,7 +198,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, TOut* __restric
   const float inv = 1.0f / sum;
   for (int i = lane; i < cols; i += 32) {
     float v = __expf(src[i] - m) * inv;
-    if (tf32) v = round_tf32(v);
+    if (tf32) v = tf32_operand(v);
     out[row * cols + i] = (TOut)v;
   }
 }
@@ -215,7 +217,7 @@ __global__ void prep_input_kernel(const float* __restrict__ x, TOut* __restrict_
     if (c < C) {
       v = x[(n * C + c) * HW + p] * mul + add;
       if (act == 1) v = sinf(6.283185307179586f * v) * 0.15915494309189535f;
-      if (tf32) v = round_tf32(v);
+      if (tf32) v = tf32_operand(v);
     }
     out[i] = (TOut)v;
   }
@@ -270,7 +272,7 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
       float v = acc + b;
       if (act_out) v = silu_f(v);
       if (out_dtype == INDM_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[n * O + o] = __float2bfloat16_rn(v);
-      else reinterpret_cast<float*>(out)[n * O + o] = (out_dtype == INDM_DTYPE_TF32) ? round_tf32(v) : v;
+      else reinterpret_cast<float*>(out)[n * O + o] = (out_dtype == INDM_DTYPE_TF32) ? tf32_operand(v) : v;
     }
   }
 }
@@ -294,7 +296,7 @@ __global__ void linear_generic_kernel(const float* __restrict__ in, const float*
       float v = acc + b;
       if (act_out) v = silu_f(v);
       if (out_dtype == INDM_DTYPE_BF16) reinterpret_cast<__nv_bfloat16*>(out)[n * O + o] = __float2bfloat16_rn(v);
-      else reinterpret_cast<float*>(out)[n * O + o] = (out_dtype == INDM_DTYPE_TF32) ? round_tf32(v) : v;
+      else reinterpret_cast<float*>(out)[n * O + o] = (out_dtype == INDM_DTYPE_TF32) ? tf32_operand(v) : v;
     }
   }
 }

@@ -313,8 +313,7 @@ class FlowEngine:
     def _round(self, w):
         if self.mode == 'bf16':
             return w.to(torch.bfloat16)
-        i = w.float().contiguous().view(torch.int32)
-        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+        return w.float().contiguous()     # TF32 mode keeps full fp32 operands: the GEMM kernel splits hi/lo itself (3xTF32)
 
     @staticmethod
     def _lop(w):

@@ -72,8 +72,7 @@ class ScoreEngine:
         """fp32 tensor -> operand dtype (bf16 / tf32-rounded fp32)"""
         if self.mode == 'bf16':
             return w.to(torch.bfloat16)
-        i = w.float().contiguous().view(torch.int32)
-        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+        return w.float().contiguous()     # TF32 mode keeps full fp32 operands: the GEMM kernel splits hi/lo itself (3xTF32)
 
     def _pack_conv(self, dst, conv_w, cin_pad=None):
         """[Cout, Cin, k, k] parameter -> dst [k*k][Cout][Cin_pad]"""

@@ -54,13 +54,16 @@ def test_prior_flow_sample_matches_reference(tag):
     eps = torch.from_numpy(g['eps']).cuda()
     h, ld_b = eng.prior_flow(eps, 'backward', want_logdet=True)
     assert rel_l2(h.cpu().numpy(), g['h']) < 1e-5
-    # forward program inverts it and the log-determinants cancel (weight_inv = weight^-1 at init)
-    back, ld_f = eng.prior_flow(h, 'forward', want_logdet=True)
-    assert float((back - eps).abs().max()) < 1e-4
-    assert float((ld_b + ld_f).abs().max()) < 1e-3
+    # both directions and their log-determinants against the oracle restatement (the synthetic weight_inv buffer is an
+    # independent random matrix, like a stale buffer would be — SURVEY.md §7 hard part 6 — so the two programs are not
+    # inverses of each other here and are checked separately)
     P = oflow.to_torch(oflow.synth_params(cfg, int(g['seed'])))
-    _, ld_ref = oflow.prior_flow(cfg, P, torch.from_numpy(g['h']), backward=False)
-    assert float((ld_f.cpu() - ld_ref).abs().max()) < 1e-3 * max(1.0, float(ld_ref.abs().max()))
+    h_ref, ldb_ref = oflow.prior_flow(cfg, P, torch.from_numpy(g['eps']), backward=True)
+    assert float((ld_b.cpu() - ldb_ref).abs().max()) < 1e-3 * max(1.0, float(ldb_ref.abs().max()))
+    fwd, ld_f = eng.prior_flow(h, 'forward', want_logdet=True)
+    fwd_ref, ldf_ref = oflow.prior_flow(cfg, P, h_ref, backward=False)
+    assert rel_l2(fwd.cpu().numpy(), fwd_ref.numpy()) < 1e-4
+    assert float((ld_f.cpu() - ldf_ref).abs().max()) < 1e-3 * max(1.0, float(ldf_ref.abs().max()))
 
 
 @pytest.mark.parametrize("mode,tol", [('tf32', 2e-4), ('bf16', 5e-3)])

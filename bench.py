@@ -188,11 +188,9 @@ def run_ours(args):
             if p_.dim() > 1 and float(p_.abs().max()) < 1e-6:
                 fan = p_[0].numel() + p_.shape[0] * (p_[0, 0].numel() if p_.dim() > 2 else 1)
                 p_.uniform_(-1, 1).mul_((6.0 / fan) ** 0.5)
-    try:
-        flow = fm.create_flow_model(cfg)
-    except NotImplementedError:
-        cfg.flow.model = "identity"
-        flow, flow_note = None, "identity (wolf flow inverse not built yet — number excludes it)"
+    flow = fm.create_flow_model(cfg)
+    flow.eval()
+    flow_note = "wolf (prior-flow sample of h + fixed-point inverse of 16+16 iResBlocks, idim 512), inside every timed step"
     sde = sde_lib.get_sde(cfg)
     shape = (PER_GPU_BATCH, 3, 32, 32)
     sampler = sampling.get_pc_sampler(cfg, sde, shape, sampling.ReverseDiffusionPredictor, sampling.NoneCorrector, lambda v: (v + 1.) / 2.,

@@ -221,6 +221,7 @@ class WolfCore(nn.Module):
         self.latent_dim = d['dim']
         self._engines = {}
         self.compute_mode = 'bf16'
+        self._draws = 0               # number of prior draws made with the in-kernel generator (advances the Philox stream)
 
     @classmethod
     def from_params(cls, params, config=None):
@@ -258,7 +259,9 @@ class WolfCore(nn.Module):
             raise RuntimeError('indm_b200 WolfCore needs CUDA tensors: there is no CPU / PyTorch fallback path')
         eng = self.engine(data.shape[0])
         if reverse:
-            return eng.reverse(data, eps=eps, h=h, seed=seed, atol=atol, rtol=rtol)
+            if eps is None and h is None:
+                self._draws += 1      # a fresh h ~ prior per call, like discriminator.sample_from_prior (wolf.py:83)
+            return eng.reverse(data, eps=eps, h=h, seed=seed, offset=self._draws, atol=atol, rtol=rtol)
         if h is None or eval_logdet:
             raise NotImplementedError('wolf forward with posterior encoder / log-det estimator is not on the CUDA path yet; '
                                       'pass h= and eval_logdet=False for the residual-flow forward map')
@@ -442,7 +445,7 @@ class FlowEngine:
             self.load_weights()
 
     # ---- public passes
-    def reverse(self, z, eps=None, h=None, seed=0, atol=1e-5, rtol=1e-5, max_iter=1000):
+    def reverse(self, z, eps=None, h=None, seed=0, offset=0, atol=1e-5, rtol=1e-5, max_iter=1000):
         """WolfCore.forward(reverse=True) (wolf.py:82-89) on the flow's own input layout (flow_forward has already applied
         SqueezeLayer when flow.squeeze): h ~ prior, then ResidualFlow.bwdpass(z, h).  Returns x with z's shape."""
         self._ensure()
@@ -452,7 +455,7 @@ class FlowEngine:
         shape = z.shape
         if h is None:
             if eps is None:
-                L.call('indm_randn_f32', L.ptr(self.eps), self.eps.numel(), seed, 0x7F10)
+                L.call('indm_randn_f32', L.ptr(self.eps), self.eps.numel(), seed, 0x7F100000 + offset)
                 eps = self.eps
             h = self.prior_flow(eps.float().contiguous(), 'backward')
         self.h.copy_(h)

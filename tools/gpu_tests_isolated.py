@@ -34,7 +34,7 @@ def main():
         name = f.replace('/', '_').replace('::', '-')
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, '-m', 'pytest', f, '-q', '--no-header', '-p', 'no:cacheprovider', '-m', 'gpu'],
+            p = subprocess.run([sys.executable, '-m', 'pytest', f, '-q', '--no-header', '-p', 'no:cacheprovider', '-m', 'gpu', '-rP'],
                                cwd=ROOT, capture_output=True, text=True, timeout=a.timeout)
             rc, out = p.returncode, p.stdout + p.stderr
         except subprocess.TimeoutExpired as e:

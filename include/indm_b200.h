@@ -148,6 +148,44 @@ int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Backward (vector-Jacobian) kernels of the score network.  The reference gets these from the autograd engine:
+ * likelihood.py:27-38 (`torch.autograd.grad(fn_eps, x)`, Hutchinson divergence) and losses.py:250,304 (`.backward()`).
+ * Convolution / attention-product gradients are indm_igemm calls with transposed, tap-flipped weight packs.
+ * ---------------------------------------------------------------- */
+
+/* Backward of y = resample(act(GroupNorm(concat(xa, xb)))) (what indm_gn_apply computes), in two passes.
+ * stats: partial_bwd[n][g][2] += (sum dxhat, sum dxhat * xhat) with dxhat = gamma * act'(u) * resample^T(dy); optional
+ *        dgamma[c] += sum act'(u) dy xhat, dbeta[c] += sum act'(u) dy (atomics, training).  Caller zeroes partial_bwd.
+ * apply: dx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat * xhat)) + resample^T(extra_post) + extra_scale * extra_pre,
+ *        written to dxa [N,H,W,Ca] / dxb [N,H,W,Cb] in out_dtype (F32: optionally accumulated; BF16: overwritten).
+ * dy: [N,H',W',C] in dy_dtype; extra_post: optional fp32 [N,H',W',C] (gradient w.r.t. the raw resampled input that feeds the
+ * skip 1x1 conv); extra_pre: optional fp32 [N,H,W,C] (identity skip).  Supported (dy, x, out) dtypes: (BF16,F32,F32),
+ * (BF16,BF16,BF16), (F32,F32,F32). */
+int indm_gn_bwd_stats(const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N, int H,
+                      int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps, int act_silu,
+                      int resample, float* partial_bwd, float* dgamma, float* dbeta, int out_dtype, void* stream);
+int indm_gn_bwd_apply(const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N, int H,
+                      int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps, int act_silu,
+                      int resample, const float* partial_bwd, const float* extra_post, const float* extra_pre, float extra_scale,
+                      void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, void* stream);
+
+/* out[i] = in[i] * scale, fp32 -> out_dtype (BF16 or fp32), n % 4 == 0: the operand copy of a gradient tensor */
+int indm_cast_scale(const float* in, void* out, int64_t n, float scale, int out_dtype, void* stream);
+
+/* ds[i][j] = p[i][j] * (dp[i][j] - sum_k p[i][k] dp[i][k]) * scale; p, ds in dtype (BF16 / fp32), dp fp32 */
+int indm_softmax_bwd_rows(const float* dp, const void* p, void* ds, int64_t rows, int cols, float scale, int dtype, void* stream);
+
+/* out[b][c][r] = in[b][r][c]  (BF16 or fp32 elements) */
+int indm_transpose_batched(const void* in, void* out, int64_t B, int R, int C, int dtype, void* stream);
+
+/* out NHWC [N,H,W,cpad] (channels >= C zero) = x NCHW fp32 [N,C,H,W] * mul * rowscale[n] (rowscale may be NULL) */
+int indm_nchw_to_nhwc(const float* x, const float* rowscale, void* out, int64_t N, int C, int H, int W, int cpad, float mul,
+                      int out_dtype, void* stream);
+
+/* out[n] (+)= scale * sum_i a[n][i] * b[n][i], fp32 (the eps^T (J eps) contraction of likelihood.py:36-37) */
+int indm_rowdot_f32(const float* a, const float* b, float* out, int64_t N, int64_t D, float scale, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Predictor-corrector update (sampling.py:205-210 ReverseDiffusionPredictor, :272-292 LangevinCorrector with
  * sde_lib.py:105-118,171-184,310-323), state NCHW fp32 [N, D].
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -64,6 +64,15 @@ _SIGS = {
     "indm_prior_flow": [_vp, _vp, _vp, _vp, _vp, C.c_int, _f32, _i64, _vp],
     "indm_fixed_point_check": [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp],
     "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],
+    "indm_gn_bwd_stats": [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32,
+                          C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp],
+    "indm_gn_bwd_apply": [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32,
+                          C.c_int, C.c_int, _vp, _vp, _vp, _f32, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp],
+    "indm_cast_scale": [_vp, _vp, _i64, _f32, C.c_int, _vp],
+    "indm_softmax_bwd_rows": [_vp, _vp, _vp, _i64, C.c_int, _f32, C.c_int, _vp],
+    "indm_transpose_batched": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_nchw_to_nhwc": [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, C.c_int, _vp],
+    "indm_rowdot_f32": [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp],
 }
 EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)
 

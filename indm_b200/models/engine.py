@@ -46,10 +46,14 @@ class ScoreEngine:
         self.nf = cfg.model.nf
         self.fir = bool(cfg.model.fir)
         self.keep = []            # every tensor the plan points into
-        self.ops = []             # list of zero-arg callables
+        self.ops = []             # list of zero-arg callables (forward plan)
+        self.bops = None          # backward (input-VJP) plan, built on first use by build_backward()
+        self.tape = []            # closures recorded by the forward builders; replayed in reverse to emit the backward plan
+        self._cur = self.ops      # list the emit helpers append to
         self.pack_jobs = []       # (fn) re-run by load_weights()
         self.gn_slots = 0
         self._weights_version = None
+        self.forward_count = 0    # bumped by every forward(): lets a pending backward detect overwritten activations
         self._build()
         self.load_weights()
 
@@ -118,7 +122,7 @@ class ScoreEngine:
 
         def run():
             L.check(lib.indm_igemm(ctypes.byref(d), L._stream()), 'igemm')
-        self.ops.append(run)
+        self._cur.append(run)
 
     def _call(self, name, *args):
         fn = getattr(L.lib(), name)
@@ -126,7 +130,7 @@ class ScoreEngine:
 
         def run():
             L.check(fn(*cargs, L._stream()), name)
-        self.ops.append(run)
+        self._cur.append(run)
 
     def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False):
         """GroupNorm(+SiLU)(+resample) of concat(xa, xb) -> operand tensor (and optional raw copy of the input).
@@ -147,6 +151,8 @@ class ScoreEngine:
         raw = self._op_t((N, Ho, Wo, C)) if want_raw else None
         self._call('indm_gn_apply', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
                    act, resample, out, raw, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
+        self._last_gn = dict(xa=xa, Ca=Ca, xb=xb, Cb=Cb, in_dt=in_dt, H=H, W=W, G=G, part=part, gamma=gamma, beta=beta, act=act,
+                             resample=resample, params=gparams)
         return out, raw
 
     def _build(self):
@@ -223,6 +229,7 @@ class ScoreEngine:
         bst = self._alloc((nf,)); self._pack_f32(bst, [stem.bias])
         h0 = self._alloc((N, S, S, nf))
         self._igemm(a=x_nhwc, N=N, H=S, W=S, Cin=cpad, b=wst, Cout=nf, taps=9, bias=bst, out_f32=h0, out_ld=nf)
+        self.tape.append(('stem', dict(conv=stem, h0=h0, mul=1.0 if centered else 2.0)))
 
         inv_sqrt2 = 1.0 / math.sqrt(2.0)
 
@@ -235,6 +242,7 @@ class ScoreEngine:
             use_fir = self.fir and resample != 0
             h1, raw = self._gn(xa, Ca, xb, Cb, L.DTYPE_F32, H, W, rb.GroupNorm_0, 1, 0 if use_fir else resample,
                                has_skip and not use_fir)
+            gn0 = self._last_gn
             Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
             if use_fir:
                 assert xb is None, 'FIR resampling blocks never take a concatenated input'
@@ -269,6 +277,7 @@ class ScoreEngine:
             self._igemm(**kw)
             in_dt1 = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
             h3, _ = self._gn(h2, Cout, None, 0, in_dt1, Ho, Wo, rb.GroupNorm_1, 1, 0, False, slot=slot1, stats_done=fuse_stats)
+            gn1 = self._last_gn
             # conv1 (+ fused skip 1x1 | + residual), * 1/sqrt(2)
             w1 = self._op_t((9, Cout, Cout)); self._pack_conv(w1, rb.Conv_1.weight)
             b1 = self._alloc((Cout,))
@@ -287,11 +296,14 @@ class ScoreEngine:
                 assert xb is None and Ca == Cout and resample == 0
                 kw.update(residual=xa, res_ld=Cout, res_scale=inv_sqrt2 if rb.skip_rescale else 1.0)
             self._igemm(**kw)
+            self.tape.append(('res_block', dict(rb=rb, gn0=gn0, gn1=gn1, out=out, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, has_skip=has_skip,
+                                                use_fir=use_fir, s=inv_sqrt2 if rb.skip_rescale else 1.0)))
             return out, Ho, Wo
 
         def attn_block(ab, x, C, H, W):
             Lq = H * W
             h, _ = self._gn(x, C, None, 0, L.DTYPE_F32, H, W, ab.GroupNorm_0, 0, 0, False)
+            gna = self._last_gn
             wqkv = self._op_t((3 * C, C))
             bqkv = self._alloc((3 * C,))
 
@@ -339,6 +351,8 @@ class ScoreEngine:
             self._igemm(a=o, N=N, H=H, W=W, Cin=C, b=w3, Cout=C, taps=1, bias=b3, residual=x, res_ld=C,
                         scale=inv_sqrt2 if ab.skip_rescale else 1.0, res_scale=inv_sqrt2 if ab.skip_rescale else 1.0,
                         out_f32=out, out_ld=C)
+            self.tape.append(('attn', dict(ab=ab, gn=gna, x=x, C=C, H=H, W=W, qk=qk, vt=vt, p=p, out=out,
+                                           s=inv_sqrt2 if ab.skip_rescale else 1.0)))
             return out
 
         # ---------------- down path
@@ -362,6 +376,7 @@ class ScoreEngine:
             sc = inv_sqrt2 if m.skip_rescale else 1.0
             self._igemm(a=fir_out, N=N, H=Hi // 2, W=Wi // 2, Cin=pyr_c, b=wp, Cout=Cout, taps=9, stride=2, bias=bp, scale=sc,
                         residual=h, res_ld=Cout, res_scale=sc, out_f32=out, out_ld=Cout)
+            self.tape.append(('pyramid', dict()))
             return out
 
         # the pyramid starts from the network input (after the 2x-1 affine): the padded NHWC operand copy of it
@@ -412,6 +427,7 @@ class ScoreEngine:
         # ---------------- head: GroupNorm + SiLU + conv3x3 -> NCHW fp32, optional per-sample output scale
         gnh = mods[idx]; idx += 1
         hh, _ = self._gn(h, Ch, None, 0, L.DTYPE_F32, H, W, gnh, 1, 0, False)
+        gn_head = self._last_gn
         head = mods[idx]; idx += 1
         assert idx == len(mods)
         wh = self._op_t((9, self.ch, Ch)); self._pack_conv(wh, head.weight)
@@ -421,6 +437,7 @@ class ScoreEngine:
         self.out_scale.fill_(1.0)
         self._igemm(a=hh, N=N, H=H, W=W, Cin=Ch, b=wh, Cout=self.ch, taps=9, bias=bh, rowscale=self.out_scale, out_mode=1,
                     out_f32=self.out)
+        self.tape.append(('head', dict(conv=head, gn=gn_head, Ch=Ch, H=H, W=W)))
         self._bind_time_source(None, None, 0, 0)
 
     def _bind_time_source(self, sched, step, sched_ld, sched_col):
@@ -437,6 +454,199 @@ class ScoreEngine:
             L.check(fn(*args, L._stream()), 'indm_time_embedding')
         self.ops[self._temb_op_index] = run
         self.keep.append((sched, step))
+
+
+    # ------------------------------------------------------------------ backward (input-VJP) plan
+    # Built lazily from `self.tape`, in reverse.  Gradients of the fp32 residual stream are fp32 buffers (first writer
+    # overwrites, later writers accumulate — decided here, statically); gradients that feed a dgrad GEMM are produced
+    # directly in the tensor-core operand dtype.  Replaces the autograd graph of likelihood.py:27-38 / losses.py:250.
+    def _grad_of(self, t):
+        """(fp32 gradient buffer of residual-stream tensor t, accumulate flag); marks it written."""
+        k = t.data_ptr()
+        g = self._grads.get(k)
+        if g is None:
+            g = self._alloc(tuple(t.shape))
+            self._grads[k] = g
+        acc = 1 if k in self._gwritten else 0
+        self._gwritten.add(k)
+        return g, acc
+
+    def _pack_dgrad(self, conv_w, kpad=None):
+        """[Cout, Cin, k, k] parameter -> dgrad operand [k*k (taps flipped)][Cin][Cout (padded to kpad)]"""
+        co, ci, kh, kw = conv_w.shape
+        dst = self._op_t((kh * kw, ci, kpad or co))
+
+        def job():
+            w = conv_w.detach().to(self.dev, torch.float32)
+            w = w.flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+            if kpad and kpad != co:
+                dst.zero_()
+                dst[:, :, :co].copy_(self._round_op(w))
+            else:
+                dst.copy_(self._round_op(w))
+        self.pack_jobs.append(job)
+        job_now = job
+        with torch.no_grad():
+            job_now()
+        return dst
+
+    def _gn_bwd(self, gn, dy, extra_post=None, extra_pre=None, extra_scale=0.0, to_operand=False):
+        """emit stats + apply of the GroupNorm(+SiLU)(+resample) backward; returns the operand-dtype gradient if to_operand"""
+        N = self.N
+        slot = self._gnb_slots
+        self._gnb_slots += 1
+        assert slot < self.gnb_part_all.shape[0]
+        pb = self.gnb_part_all[slot]
+        op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+        x_dt = gn['in_dt']
+        if to_operand:
+            dxa, acc_a, dxb, acc_b = self._op_t(tuple(gn['xa'].shape)), 0, None, 0
+            out_dt = op_dt
+        else:
+            dxa, acc_a = self._grad_of(gn['xa'])
+            dxb, acc_b = self._grad_of(gn['xb']) if gn['xb'] is not None else (None, 0)
+            out_dt = L.DTYPE_F32
+        common = (dy, op_dt, gn['xa'], gn['Ca'], gn['xb'], gn['Cb'], x_dt, ctypes.c_int64(N), gn['H'], gn['W'], gn['G'], gn['part'],
+                  gn['gamma'], gn['beta'], ctypes.c_float(1e-6), gn['act'], gn['resample'])
+        self._call('indm_gn_bwd_stats', *common, pb, None, None, out_dt)
+        self._call('indm_gn_bwd_apply', *common, pb, extra_post, extra_pre, ctypes.c_float(extra_scale), dxa, acc_a, dxb, acc_b, out_dt)
+        return dxa
+
+    def _cast_grad(self, t, scale):
+        """operand-dtype copy of scale * grad(t) (t must already have its full gradient)"""
+        g = self._grads[t.data_ptr()]
+        out = self._op_t(tuple(t.shape))
+        self._call('indm_cast_scale', g, out, ctypes.c_int64(g.numel()), ctypes.c_float(scale),
+                   L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32)
+        return out
+
+    def _okw(self, t, ld):
+        return dict(out_bf16=t, out_ld=ld) if self.mode == 'bf16' else dict(out_f32=t, out_ld=ld)
+
+    def _bwd_res_block(self, r):
+        N, rb = self.N, r['rb']
+        Cin, Cout, Ho, Wo = r['Cin'], r['Cout'], r['Ho'], r['Wo']
+        if r['use_fir']:
+            raise NotImplementedError('backward through FIR-resampling res-blocks (VE configs) is not built yet')
+        g = self._cast_grad(r['out'], r['s'])                                   # d(out) * 1/sqrt(2), operand dtype
+        w1d = self._pack_dgrad(rb.Conv_1.weight)
+        d_h3 = self._op_t((N, Ho, Wo, Cout))
+        self._igemm(a=g, N=N, H=Ho, W=Wo, Cin=Cout, b=w1d, Cout=Cout, taps=9, **self._okw(d_h3, Cout))
+        d_h2 = self._gn_bwd(r['gn1'], d_h3, to_operand=True)
+        w0d = self._pack_dgrad(rb.Conv_0.weight)
+        d_h1 = self._op_t((N, Ho, Wo, Cin))
+        self._igemm(a=d_h2, N=N, H=Ho, W=Wo, Cin=Cout, b=w0d, Cout=Cin, taps=9, **self._okw(d_h1, Cin))
+        if r['has_skip']:
+            w2d = self._pack_dgrad(rb.Conv_2.weight)
+            d_raw = self._alloc((N, Ho, Wo, Cin))
+            self._igemm(a=g, N=N, H=Ho, W=Wo, Cin=Cout, b=w2d, Cout=Cin, taps=1, out_f32=d_raw, out_ld=Cin)
+            self._gn_bwd(r['gn0'], d_h1, extra_post=d_raw)
+        else:
+            self._gn_bwd(r['gn0'], d_h1, extra_pre=self._grads[r['out'].data_ptr()], extra_scale=r['s'])
+
+    def _bwd_attn(self, r):
+        N, ab, C, H, W = self.N, r['ab'], r['C'], r['H'], r['W']
+        Lq = H * W
+        op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+        g = self._cast_grad(r['out'], r['s'])
+        w3d = self._op_t((C, C))
+
+        def job3(w3d=w3d, ab=ab):          # NIN_3.W is [in, out]: exactly the dgrad operand [N = in][K = out]
+            w3d.copy_(self._round_op(ab.NIN_3.W.detach().to(self.dev, torch.float32).contiguous()))
+        self.pack_jobs.append(job3)
+        with torch.no_grad():
+            job3()
+        d_o = self._op_t((N, Lq, C))
+        self._igemm(a=g, N=N, H=H, W=W, Cin=C, b=w3d, Cout=C, taps=1, **self._okw(d_o, C))
+        # row-major V and transposed Q, K from what the forward kept
+        v_rows = self._op_t((N, Lq, C))
+        self._call('indm_transpose_batched', r['vt'], v_rows, ctypes.c_int64(N), C, Lq, op_dt)
+        qkT = self._op_t((N, 2 * C, Lq))
+        self._call('indm_transpose_batched', r['qk'], qkT, ctypes.c_int64(N), Lq, 2 * C, op_dt)
+        d_p = self._alloc((N, Lq, Lq))
+        self._igemm(a=d_o, N=N, H=1, W=Lq, Cin=C, b=v_rows, b_tap_stride=Lq * C, Cout=Lq, taps=1, batched_b=1, out_f32=d_p, out_ld=Lq)
+        d_s = self._op_t((N, Lq, Lq))
+        self._call('indm_softmax_bwd_rows', d_p, r['p'], d_s, ctypes.c_int64(N * Lq), Lq, ctypes.c_float(float(int(C) ** (-0.5))), op_dt)
+        d_qkv = self._op_t((N, Lq, 3 * C))
+        # dQ = dS K
+        self._igemm(a=d_s, N=N, H=1, W=Lq, Cin=Lq, b=qkT[:, C:, :], b_ld=Lq, b_tap_stride=2 * C * Lq, Cout=C, taps=1, batched_b=1,
+                    **self._okw(d_qkv, 3 * C))
+        # dK = dS^T Q
+        d_sT = self._op_t((N, Lq, Lq))
+        self._call('indm_transpose_batched', d_s, d_sT, ctypes.c_int64(N), Lq, Lq, op_dt)
+        self._igemm(a=d_sT, N=N, H=1, W=Lq, Cin=Lq, b=qkT, b_ld=Lq, b_tap_stride=2 * C * Lq, Cout=C, taps=1, batched_b=1,
+                    **self._okw(d_qkv[:, :, C:], 3 * C))
+        # dV = P^T dO
+        pT = self._op_t((N, Lq, Lq))
+        self._call('indm_transpose_batched', r['p'], pT, ctypes.c_int64(N), Lq, Lq, op_dt)
+        d_oT = self._op_t((N, C, Lq))
+        self._call('indm_transpose_batched', d_o, d_oT, ctypes.c_int64(N), Lq, C, op_dt)
+        self._igemm(a=pT, N=N, H=1, W=Lq, Cin=Lq, b=d_oT, b_ld=Lq, b_tap_stride=C * Lq, Cout=C, taps=1, batched_b=1,
+                    **self._okw(d_qkv[:, :, 2 * C:], 3 * C))
+        # back through the fused q/k/v projection
+        wqkvd = self._op_t((C, 3 * C))
+
+        def jobq(wqkvd=wqkvd, ab=ab):
+            ws = [getattr(ab, f'NIN_{j}').W.detach().to(self.dev, torch.float32) for j in range(3)]    # [in, out] each
+            wqkvd.copy_(self._round_op(torch.cat(ws, dim=1)))
+        self.pack_jobs.append(jobq)
+        with torch.no_grad():
+            jobq()
+        d_h = self._op_t((N, Lq, C))
+        self._igemm(a=d_qkv, N=N, H=H, W=W, Cin=3 * C, b=wqkvd, Cout=C, taps=1, **self._okw(d_h, C))
+        self._gn_bwd(r['gn'], d_h, extra_pre=self._grads[r['out'].data_ptr()], extra_scale=r['s'])
+
+    def _bwd_head(self, r):
+        N, S, Ch = self.N, self.S, r['Ch']
+        op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+        cpad = self.kchunk
+        self.gout = self._alloc((N, self.ch, S, S), zero=True)          # cotangent of the network output (NCHW fp32)
+        g = self._op_t((N, S, S, cpad))
+        self._call('indm_nchw_to_nhwc', self.gout, self.out_scale, g, ctypes.c_int64(N), self.ch, S, S, cpad, ctypes.c_float(1.0), op_dt)
+        whd = self._pack_dgrad(r['conv'].weight, kpad=cpad)
+        d_hh = self._op_t((N, S, S, Ch))
+        self._igemm(a=g, N=N, H=S, W=S, Cin=cpad, b=whd, Cout=Ch, taps=9, **self._okw(d_hh, Ch))
+        self._gn_bwd(r['gn'], d_hh)
+
+    def _bwd_stem(self, r):
+        N, S = self.N, self.S
+        g = self._cast_grad(r['h0'], 1.0)
+        wsd = self._pack_dgrad(r['conv'].weight)
+        self.gx = self._alloc((N, self.ch, S, S))
+        self._igemm(a=g, N=N, H=S, W=S, Cin=self.nf, b=wsd, Cout=self.ch, taps=9, scale=r['mul'], out_mode=1, out_f32=self.gx)
+
+    def build_backward(self):
+        if self.bops is not None:
+            return
+        self._grads, self._gwritten, self._gnb_slots = {}, set(), 0
+        self.gnb_part_all = self._alloc((2 * len(self.tape) + 4, self.N, 32, 2), zero=True)
+        self._cur = bops = []
+        part = self.gnb_part_all
+
+        def zero_bwd_stats():
+            part.zero_()
+        bops.append(zero_bwd_stats)
+        try:
+            for kind, rec in reversed(self.tape):
+                getattr(self, '_bwd_' + kind)(rec)
+        finally:
+            self._cur = self.ops
+        self.bops = bops
+        self._weights_version = None      # new weight packs were registered: repack on next use
+
+    def _bwd_pyramid(self, r):
+        raise NotImplementedError('backward through the FIR input pyramid (VE configs) is not built yet')
+
+    def vjp(self, v):
+        """v^T d(out)/d(x_in) for the activations of the last forward()/launch(): [N,C,S,S] fp32 in and out.
+        (`out` includes the per-sample output scale that forward() was given.)"""
+        self.build_backward()
+        if self._weights_version != self.weights_version():
+            self.load_weights()
+        self.gout.copy_(v)
+        for op in self.bops:
+            op()
+        return self.gx
 
     # ------------------------------------------------------------------ execution
     def launch(self):
@@ -455,6 +665,7 @@ class ScoreEngine:
             self.out_scale.fill_(1.0)
         else:
             self.out_scale.copy_(out_scale)
+        self.forward_count += 1
         self.launch()
         return self.out
 

@@ -13,6 +13,27 @@ from . import layers, layerspp, utils
 from .engine import ScoreEngine
 
 
+class _EngineFunction(torch.autograd.Function):
+    """Bridges the hand-written engine into torch.autograd so the reference's call sites keep working unchanged:
+    `torch.autograd.grad(fn_eps, x)` of likelihood.py:32-35 and `.backward()` of losses.py:250 reach `ScoreEngine.vjp`,
+    which replays the explicit backward plan over the activations the forward left in HBM."""
+
+    @staticmethod
+    def forward(ctx, x, time_cond, scale, net):
+        eng = net.engine(x.shape[0])
+        out = eng.forward(x.float(), time_cond.float(), scale).clone()
+        ctx.eng, ctx.token = eng, eng.forward_count
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.eng
+        if eng.forward_count != ctx.token:
+            raise RuntimeError('indm_b200: the engine ran another forward before this backward; activations were overwritten '
+                               '(call backward right after the forward it belongs to)')
+        return eng.vjp(grad_out.contiguous().float()).clone(), None, None, None
+
+
 @utils.register_model(name='ncsnpp')
 class NCSNpp(nn.Module):
     """NCSN++ model"""
@@ -116,8 +137,8 @@ class NCSNpp(nn.Module):
     def forward(self, x, time_cond):
         if not x.is_cuda:
             raise RuntimeError('indm_b200.NCSNpp.forward needs CUDA tensors: there is no CPU / PyTorch fallback path')
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())) and self.training:
-            raise NotImplementedError('training-mode forward (dropout + autograd) is not wired to the CUDA engine yet; '
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('training-mode forward (dropout + parameter gradients) is not wired to the CUDA engine yet; '
                                       'call under torch.no_grad() / model.eval()')
         eng = self.engine(x.shape[0])
         scale = None
@@ -127,5 +148,7 @@ class NCSNpp(nn.Module):
             else:
                 used_sigmas = self.sigmas[time_cond.long()].float()
             scale = 1.0 / used_sigmas.float()
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _EngineFunction.apply(x, time_cond, scale, self)
         out = eng.forward(x.float(), time_cond.float(), scale)
         return out.clone()

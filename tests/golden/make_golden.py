@@ -185,6 +185,32 @@ def make_ncsnpp():
         print(tag, 'score rms', float(s.pow(2).mean().sqrt()), 'raw rms', float(raw.pow(2).mean().sqrt()))
 
 
+def make_vjp():
+    """Input vector-Jacobian products of the reference score function (what likelihood.get_div_fn builds through autograd,
+    likelihood.py:27-38): J^T eps with Rademacher eps, and the Hutchinson contraction eps^T J eps from the reference's own div_fn."""
+    mutils, sde_lib, likelihood = rl.load('models.utils', 'sde_lib', 'likelihood')
+    for tag, (path, is_tiny, B) in {'tiny_vp': ('configs/vp/CIFAR10/indm_fid.py', True, 3),
+                                    'vp_cifar': ('configs/vp/CIFAR10/indm_nll.py', False, 2)}.items():
+        cfg = rl.get_config(path)
+        if is_tiny:
+            tiny(cfg)
+        model, _ = ref_model(cfg, seed=11)
+        S = cfg.data.image_size
+        rng = np.random.default_rng(31)
+        x = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+        t = np.array([0.6, 0.6, 0.6][:B], dtype=np.float32)      # the ODE evaluates one t for the whole batch (likelihood.py:96)
+        eps = (rng.integers(0, 2, size=(B, 3, S, S)).astype(np.float32) * 2 - 1)
+        sde = sde_lib.get_sde(cfg)
+        score_fn = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
+        xt = torch.from_numpy(x).requires_grad_(True)
+        sc = score_fn(xt, torch.from_numpy(t))
+        vjp, = torch.autograd.grad((sc * torch.from_numpy(eps)).sum(), xt)
+        div = likelihood.get_div_fn(lambda xx, tt: score_fn(xx, tt))(torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(eps))
+        np.savez_compressed(os.path.join(HERE, f'vjp_{tag}.npz'), x=x, t=t, eps=eps, score=sc.detach().numpy(), vjp=vjp.numpy(),
+                            div=div.detach().numpy(), seed=np.asarray(11))
+        print('vjp', tag, 'vjp rms', float(vjp.pow(2).mean().sqrt()), 'div', div.detach().numpy())
+
+
 def make_pc():
     """Short PC trajectories through the reference's own get_pc_sampler, with randn_like / randn replayed."""
     mutils, sde_lib, sampling = rl.load('models.utils', 'sde_lib', 'sampling')
@@ -279,7 +305,7 @@ def make_flow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

@@ -110,3 +110,27 @@ def test_pc_sampler_graph_replay_equals_eager_with_same_philox_stream():
     b1, _, _ = fn(model, None, prior=prior, noise=noises)
     torch.cuda.synchronize()
     assert rel_l2(b1.cpu().numpy(), a1.cpu().numpy()) < 5e-3
+
+
+@pytest.mark.parametrize("mode,tol", [('tf32', 1e-3), ('bf16', 3e-2)])
+@pytest.mark.parametrize("tag", ['tiny_vp', 'vp_cifar'])
+def test_score_input_vjp_matches_reference_autograd(tag, mode, tol):
+    """J^T eps of score_fn w.r.t. its input through the explicit backward plan, driven by the reference's own call pattern
+    (likelihood.py:27-38: torch.autograd.grad(sum(fn(x, t) * eps), x)), against the live reference's autograd result."""
+    g = load_npz(f'vjp_{tag}.npz')
+    cfg = _cfg(tag)
+    model = _model(cfg, int(g['seed']))
+    model.module.compute_mode = mode
+    sde = sde_lib.get_sde(cfg)
+    score_fn = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
+    x, t, eps = (torch.from_numpy(g[k]).cuda() for k in ('x', 't', 'eps'))
+    with torch.enable_grad():
+        x.requires_grad_(True)
+        sc = score_fn(x, t)
+        vjp, = torch.autograd.grad(torch.sum(sc * eps), x)
+    div = torch.sum(vjp * eps, dim=(1, 2, 3))
+    torch.cuda.synchronize()
+    e_s, e_v = rel_l2(sc.detach().cpu().numpy(), g['score']), rel_l2(vjp.cpu().numpy(), g['vjp'])
+    e_d = float(np.abs(div.cpu().numpy() - g['div']).max() / np.abs(g['div']).max())
+    print(f'{tag} {mode}: score rel-L2 {e_s:.3e}  vjp rel-L2 {e_v:.3e}  Hutchinson div rel {e_d:.3e}')
+    assert e_v < tol and e_d < tol

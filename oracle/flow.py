@@ -310,3 +310,123 @@ def wolf_reverse(config, P, z, eps, atol=1e-5, rtol=1e-5):
     if config.flow.squeeze:
         x = unsqueeze2(x)
     return x, h, iters
+
+
+# ------------------------------------------------------------------------------------------------ posterior q(h|x) and KL
+def _bn_eval(P, p, x, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (running statistics)."""
+    sc = P[p + 'weight'] / torch.sqrt(P[p + 'running_var'] + eps)
+    return x * sc[None, :, None, None] + (P[p + 'bias'] - P[p + 'running_mean'] * sc)[None, :, None, None]
+
+
+def encoder_forward(config, P, x):
+    """GlobalResNetEncoderBatchNorm.forward (modules/encoders/global_encoder.py:12-36) over ResNetBlockBatchNorm
+    (nnet/resnets/resnet_batchnorm.py:18-76), ELU activation, eval-mode batch norm.  Returns [B, out_planes*h*w]."""
+    enc = config.flow.wolf_params['discriminator']['encoder']
+    for lv, hid in enumerate(enc['hidden_planes']):
+        for m, stride in enumerate((1, 2)):
+            p = f'discriminator.encoder.net.resnet{lv}.main.{m}.'
+            out = F.conv2d(x, P[p + 'conv1.weight'], stride=stride, padding=1)
+            out = F.elu(_bn_eval(P, p + 'bn1.', out))
+            out = _bn_eval(P, p + 'bn2.', F.conv2d(out, P[p + 'conv2.weight'], padding=1))
+            if (p + 'downsample.0.weight') in P:
+                x = _bn_eval(P, p + 'downsample.1.', F.conv2d(x, P[p + 'downsample.0.weight'], stride=stride))
+            x = F.elu(out + x)
+    x = F.elu(F.conv2d(x, P['discriminator.encoder.net.top.weight'], P['discriminator.encoder.net.top.bias']))
+    return x.reshape(x.shape[0], -1)
+
+
+def posterior_sample_and_kl(config, P, x, eps):
+    """GaussianDiscriminator.sampling_and_KL (modules/discriminators/gaussian.py:67-76) with nsamples = 1 and the
+    reparameterisation noise `eps` [B, 64] supplied; FlowPrior.calcKL (priors/flow.py:233-253).  Returns (h, KL, mu, logvar)."""
+    c = encoder_forward(config, P, x)
+    c = F.linear(c, _wn(P, 'discriminator.fc.linear.'), P['discriminator.fc.linear.bias'])
+    mu, logvar = c.chunk(2, dim=1)
+    h = eps * torch.exp(0.5 * logvar) + mu
+    dim = h.shape[1]
+    cc = math.log(math.pi * 2.)
+    log_posterior = -0.5 * ((logvar + eps ** 2).sum(dim=1) + cc * dim)
+    e, logdet = prior_flow(config, P, h, backward=False)           # flow built with inverse=True: bwdpass = forward()
+    log_prior = -0.5 * ((e * e).sum(dim=1) + cc * dim) + logdet
+    return h, log_posterior - log_prior, mu, logvar
+
+
+# ------------------------------------------------------------------------------------------------ log-det estimators
+def poisson_1mcdf(lamb, k, offset):
+    """iresblock.py:306-318: P(n >= k - offset), 1 for k <= offset."""
+    if k <= offset:
+        return 1.
+    k = k - offset
+    s = 1.
+    for i in range(1, k):
+        s += lamb ** i / math.factorial(i)
+    return 1 - math.exp(-lamb) * s
+
+
+def series_coefficients(n, training, lamb=2.0, n_exact_terms=2):
+    """(K, [c_1..c_K]) of iResBlock._logdetgrad (iresblock.py:114-132) for one Poisson draw n:
+    K = n + offset terms, c_k = 1[n >= k - offset] / P(N >= k - offset), offset = n_exact_terms (train) or 20 (eval)."""
+    offset = n_exact_terms if training else 20
+    K = n + offset
+    return K, [1.0 / poisson_1mcdf(lamb, k, offset) * (1.0 if n >= k - offset else 0.0) for k in range(1, K + 1)]
+
+
+def block_logdet(gfn, x, n, vareps, training):
+    """g(x) and the power-series log-det estimate of one iResBlock (iresblock.py:90-174): `basic_logdet_estimator`
+    (:253-261) in eval mode, `neumann_logdet_estimator` (:264-273) in training mode.  Uses autograd for the VJPs, like the
+    reference.  Returns (g, logdet [B])."""
+    K, coef = series_coefficients(n, training)
+    with torch.enable_grad():
+        x = x.detach().requires_grad_(True)
+        g = gfn(x)
+        B = x.shape[0]
+        if training:
+            vjp, neumann = vareps, vareps
+            for k in range(1, K + 1):
+                vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
+                neumann = neumann + (-1) ** k * coef[k - 1] * vjp
+            vj = torch.autograd.grad(g, x, neumann, retain_graph=True)[0]
+            ld = (vj.reshape(B, -1) * vareps.reshape(B, -1)).sum(1)
+        else:
+            vjp, ld = vareps, torch.zeros(B)
+            for k in range(1, K + 1):
+                vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
+                ld = ld + (-1) ** (k + 1) / k * coef[k - 1] * (vjp.reshape(B, -1) * vareps.reshape(B, -1)).sum(1)
+    return g.detach(), ld.detach()
+
+
+def resflow_forward_logdet(config, P, x, h, ns, varepss, training=False):
+    """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z in image layout, logpx [B]) with
+    logpx = -sum_blocks logdet (iresblock.py:63-69 with logpx starting at 0).  ns / varepss: per-block Poisson draws and
+    Gaussian probe tensors, in forward block order."""
+    nb = n_blocks(config)
+    shape = x.shape
+    logpx = torch.zeros(x.shape[0])
+    i = 0
+    for s, n_s in enumerate(nb):
+        for b in range(n_s):
+            first = (s == 0 and b == 0)
+            g, ld = block_logdet(lambda v: g_branch(P, s, b, first, v, h), x, int(ns[i]), varepss[i], training)
+            x = x + g
+            logpx = logpx - ld
+            i += 1
+        if s < len(nb) - 1:
+            x = squeeze2(x)
+    out = x.reshape(shape[0], -1)
+    if len(nb) > 1:
+        out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
+    else:
+        out = out.view(shape)
+    return out, logpx
+
+
+def wolf_forward(config, P, x, eps_post, ns, varepss, training=False):
+    """flow_forward(config, flow, x, reverse=False) (flow_model.py:53-67) -> WolfCore.forward (wolf.py:90-130):
+    returns (z, logdet - KL) where logdet = sum of block log-dets (`fwdpass` returns logpx = -sum, wolf.py:126 negates)."""
+    if config.flow.squeeze:
+        x = squeeze2(x)
+    h, kl, _, _ = posterior_sample_and_kl(config, P, x, eps_post)
+    z, logpx = resflow_forward_logdet(config, P, x, h, ns, varepss, training)
+    if config.flow.squeeze:
+        z = unsqueeze2(z)
+    return z, -logpx - kl, h, kl

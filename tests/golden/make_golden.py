@@ -185,6 +185,53 @@ def make_ncsnpp():
         print(tag, 'score rms', float(s.pow(2).mean().sqrt()), 'raw rms', float(raw.pow(2).mean().sqrt()))
 
 
+def make_flowfwd():
+    """Wolf flow FORWARD with log-det in eval mode (posterior encoder + reparameterisation + prior-flow KL + 20+n term
+    power-series log-det of every iResBlock) through the reference's flow_forward, with every random draw replayed:
+    torch.randn (posterior eps), torch.randn_like (Hutchinson probes), poisson_sample (series lengths)."""
+    fm = rl.load('flow_models.flow_model')
+    import flow_models.wolf.flows.resflow.layers.iresblock as irb
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    for tag, path, squeeze in (('tiny', 'configs/vp/CIFAR10/indm_nll.py', False), ('tiny_sq', 'configs/vp/CELEBA/indm_nll.py', True)):
+        # the posterior encoder needs the full image extent (3 stride-2 levels -> 4x4x8 = in_dim 128): keep S, shrink depth
+        cfg = rl.get_config(path)
+        tiny_flow(cfg, squeeze)
+        S = 64 if squeeze else 32
+        cfg.data.image_size = cfg.flow.image_size = S
+        with rl.reference_cwd():
+            flow = fm.create_flow_model(cfg)
+        pcfg = pconfigs.get_config(path.replace('configs/', '').replace('.py', ''))
+        tiny_flow(pcfg, squeeze)
+        pcfg.data.image_size = pcfg.flow.image_size = S
+        sd = oflow.synth_params(pcfg, 21)
+        flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        flow.eval()
+        B = 2
+        rng = np.random.default_rng(41)
+        x = rng.uniform(-1, 1, size=(B, 3, S, S)).astype(np.float32)
+        eps_post = rng.standard_normal((B, 64)).astype(np.float32)
+        layout = oflow.block_layout(pcfg)
+        c0, h0, w0 = oflow.flow_input_shape(pcfg)
+        ns = rng.poisson(2.0, size=len(layout)).astype(np.int64)
+        varepss = [rng.standard_normal((B, c, h0 >> s, w0 >> s)).astype(np.float32) for (s, b, c, first) in layout]
+        q_eps, q_n = [torch.from_numpy(v) for v in varepss], list(ns)
+        real = (torch.randn, torch.randn_like, irb.poisson_sample)
+        torch.randn = lambda *a, **k: torch.from_numpy(eps_post).reshape(B, 1, 64)
+        torch.randn_like = lambda t, **k: q_eps.pop(0)
+        irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+        try:
+            z, ldkl = fm.flow_forward(cfg, flow, torch.from_numpy(x), reverse=False)
+        finally:
+            torch.randn, torch.randn_like, irb.poisson_sample = real
+        assert not q_eps and not q_n
+        out = dict(x=x, eps_post=eps_post, ns=ns, z=z.detach().numpy(), ldkl=ldkl.detach().numpy(), seed=np.asarray(21))
+        for i, v in enumerate(varepss):
+            out[f'vareps_{i}'] = v
+        np.savez_compressed(os.path.join(HERE, f'flowfwd_{tag}.npz'), **out)
+        print('flowfwd', tag, 'ns', ns, 'ldkl', ldkl.detach().numpy())
+
+
 def make_vjp():
     """Input vector-Jacobian products of the reference score function (what likelihood.get_div_fn builds through autograd,
     likelihood.py:27-38): J^T eps with Rademacher eps, and the Hutchinson contraction eps^T J eps from the reference's own div_fn."""
@@ -305,7 +352,7 @@ def make_flow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

@@ -49,3 +49,33 @@ def test_resflow_forward_matches_reference_and_round_trips(tag):
         # inverse round trip with the same h (SURVEY.md §8c caveat i), tight stop rule
         back, _ = oflow.resflow_inverse(cfg, P, zf, h, atol=1e-10, rtol=1e-10)
     assert float((back.reshape(xf.shape) - xf).abs().max()) < 1e-4
+
+
+def _cfg_fwd(tag):
+    cfg = configs.get_config('vp/CELEBA/indm_nll' if tag == 'tiny_sq' else 'vp/CIFAR10/indm_nll')
+    tiny_flow(cfg, tag == 'tiny_sq')
+    cfg.data.image_size = cfg.flow.image_size = 64 if tag == 'tiny_sq' else 32
+    return cfg
+
+
+@pytest.mark.parametrize("tag", ['tiny', 'tiny_sq'])
+def test_wolf_forward_logdet_kl_matches_reference(tag):
+    """flow_forward(reverse=False) in eval mode: posterior encoder, reparameterisation, prior-flow KL and the (20 + n)-term
+    power-series log-det of every iResBlock, all random draws replayed from the reference run."""
+    g = load_npz(f'flowfwd_{tag}.npz')
+    cfg = _cfg_fwd(tag)
+    P = oflow.to_torch(oflow.synth_params(cfg, int(g['seed'])))
+    nblk = len(oflow.block_layout(cfg))
+    varepss = [torch.from_numpy(g[f'vareps_{i}']) for i in range(nblk)]
+    with torch.no_grad():
+        z, ldkl, h, kl = oflow.wolf_forward(cfg, P, torch.from_numpy(g['x']), torch.from_numpy(g['eps_post']), g['ns'], varepss)
+    assert float(np.abs(z.numpy() - g['z']).max()) < 1e-5
+    assert float(np.abs(ldkl.numpy() - g['ldkl']).max()) < 1e-3 * float(np.abs(g['ldkl']).max())
+
+
+def test_series_coefficients_follow_the_reference_rule():
+    # eval: 20 exact terms then Russian-roulette reweighting by 1 / P(N >= k - 20); train: 2 exact terms
+    K, c = oflow.series_coefficients(3, training=False)
+    assert K == 23 and c[:20] == [1.0] * 20 and c[20] == pytest.approx(1.0 / (1 - np.exp(-2.0)))
+    K, c = oflow.series_coefficients(0, training=True)
+    assert K == 2 and c == [1.0, 1.0]

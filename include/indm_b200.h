@@ -77,7 +77,8 @@ typedef struct indm_igemm {
   const float* residual; /* fp32 NHWC (NCHW when out_mode == 1) or NULL */
   int64_t res_ld;
   float res_scale;
-  int32_t act;           /* 0 none; 1 Sin(x) = sin(2 pi x)/(2 pi), the resflow activation (flows/resflow/layers/base/activations.py:7-12) */
+  int32_t act;           /* 0 none; 1 Sin(x) = sin(2 pi x)/(2 pi), the resflow activation (flows/resflow/layers/base/activations.py:7-12);
+                            2 ELU (posterior encoder, nnet/resnets/resnet_batchnorm.py:26-27) */
   const float* rowscale; /* [N] or NULL */
   float scale;
   int32_t out_mode;      /* 0: NHWC rows out_*[pixel*out_ld + c];  1: NCHW fp32 (out_f32);
@@ -95,6 +96,14 @@ typedef struct indm_igemm {
   int32_t block_n;       /* 0 = choose automatically; else 32 / 64 / 128 / 256 */
   int32_t stride;        /* 0 / 1: unit stride.  2 (taps == 9): 3x3 stride-2 VALID convolution — A is the [N, 2H+1, 2W+1, Cin]
                             FIR-padded image and H x W the output grid (conv_downsample_2d, models/up_or_down_sampling.py:173-178) */
+  int32_t a_H, a_W, pad; /* stride 2 only: extent of the A image grid (0 = the default 2H+1 x 2W+1) and zero padding 0 / 1, i.e.
+                            input pixel (2y + ky - pad, 2x + kx - pad); taps == 1 gives a strided 1x1 conv
+                            (nnet/resnets/resnet_batchnorm.py:33-36) */
+  const void* mul;       /* optional elementwise multiplier applied last: NHWC in the operand dtype with row stride mul_ld
+                            (0 = Cout), or NCHW fp32 when out_mode == 1 (the cos factors of the iResBlock VJP chain) */
+  int64_t mul_ld;
+  void* aux_cos;         /* optional second output (out_mode 0, layout of out_*, operand dtype): cos(2 pi v) of the value v that
+                            enters `act` — the derivative of Sin, kept for the log-det estimators (iresblock.py:253-273) */
 } indm_igemm_t;
 
 int indm_igemm(const indm_igemm_t* desc, void* stream);
@@ -242,9 +251,20 @@ typedef struct indm_flow_op {
 
 /* out[n] = program(in[n]) for n < N, in/out [N,64]; logdet[n] (optional) = sum of the ops' log-determinants +
  * logdet_const (the invertible-linear slogdet terms, constants of the weights, computed by the caller).
- * params / ops are DEVICE pointers. */
+ * kl_base != NULL: logdet[n] instead receives kl_base[n] - (log N(out[n]; 0, I) + log-determinant), i.e. the KL term of
+ * FlowPrior.calcKL (priors/flow.py:233-253) when kl_base = log q(h|x).  params / ops are DEVICE pointers. */
 int indm_prior_flow(const float* in, float* out, float* logdet, const float* params, const indm_flow_op_t* ops, int n_ops,
-                    float logdet_const, int64_t N, void* stream);
+                    float logdet_const, const float* kl_base, int64_t N, void* stream);
+
+/* Reparameterised posterior sample (modules/discriminators/gaussian.py:29-38): c [N,128] = (mu | logvar), eps [N,64] ->
+ * h = mu + exp(logvar/2) eps and log q(h|x) = -(sum(logvar + eps^2) + 64 log 2pi)/2 (priors/flow.py:236-241). */
+int indm_posterior_sample(const float* c, const float* eps, float* h, float* logq, int64_t N, void* stream);
+
+/* y += alpha * x (fp32): the Neumann-series accumulation of iresblock.py:264-270 */
+int indm_axpy_f32(float* y, const float* x, float alpha, int64_t n, void* stream);
+
+/* out = cos(2 pi x) (fp32): derivative of the leading Sin of an iResBlock branch w.r.t. the block input */
+int indm_cos2pi_f32(const float* x, float* out, int64_t n, void* stream);
 
 /* flag[0] = max_i (x[i]-x_prev[i])^2 / (atol + |y[i]|*rtol)  — the stop rule of iResBlock._inverse_fixed_point
  * (flows/resflow/layers/iresblock.py:78-88): converged iff flag[0] < 1.  flag is a device float. */

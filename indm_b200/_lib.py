@@ -35,6 +35,8 @@ class IgemmDesc(C.Structure):
         ("tcol0", C.c_int32), ("out_t", C.c_void_p), ("round_tf32_out", C.c_int32),
         ("gn_partial", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_groups", C.c_int32),
         ("block_n", C.c_int32), ("stride", C.c_int32),
+        ("a_H", C.c_int32), ("a_W", C.c_int32), ("pad", C.c_int32),
+        ("mul", C.c_void_p), ("mul_ld", C.c_int64), ("aux_cos", C.c_void_p),
     ]
 
 
@@ -61,7 +63,10 @@ _SIGS = {
     "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
     "indm_advance_step": [_vp, _vp],
     "indm_randn_f32": [_vp, _i64, _u64, _u64, _vp],
-    "indm_prior_flow": [_vp, _vp, _vp, _vp, _vp, C.c_int, _f32, _i64, _vp],
+    "indm_prior_flow": [_vp, _vp, _vp, _vp, _vp, C.c_int, _f32, _vp, _i64, _vp],
+    "indm_posterior_sample": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "indm_axpy_f32": [_vp, _vp, _f32, _i64, _vp],
+    "indm_cos2pi_f32": [_vp, _vp, _i64, _vp],
     "indm_fixed_point_check": [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp],
     "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],
     "indm_gn_bwd_stats": [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32,

@@ -20,7 +20,8 @@ __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x)
 // one CTA (256 threads) per sample
 __global__ void __launch_bounds__(HID) prior_flow_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                          float* __restrict__ logdet_out, const float* __restrict__ params,
-                                                         const indm_flow_op_t* __restrict__ ops, int n_ops, float logdet_const) {
+                                                         const indm_flow_op_t* __restrict__ ops, int n_ops, float logdet_const,
+                                                         const float* __restrict__ kl_base) {
   __shared__ float z[DIM], zin[HALF], ha[HID], hb[HID], prm[DIM], red[HID / 32];
   const int t = threadIdx.x;
   const long long n = blockIdx.x;
@@ -98,7 +99,44 @@ __global__ void __launch_bounds__(HID) prior_flow_kernel(const float* __restrict
     }
   }
   if (t < DIM) out[n * DIM + t] = z[t];
-  if (t == 0 && logdet_out) logdet_out[n] = logdet + logdet_const;
+  if (kl_base) {
+    // KL = log q(h|x) - log p(h), log p(h) = log N(out; 0, I) + logdet   (priors/flow.py:233-253)
+    float q = t < DIM ? z[t] * z[t] : 0.f;
+    q = warp_sum(q);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = q;
+    __syncthreads();
+    if (t == 0 && logdet_out) {
+      const float ss = red[0] + red[1];
+      const float logp = -0.5f * (ss + (float)DIM * 1.8378770664093453f) + logdet + logdet_const;
+      logdet_out[n] = kl_base[n] - logp;
+    }
+  } else if (t == 0 && logdet_out) {
+    logdet_out[n] = logdet + logdet_const;
+  }
+}
+
+// h = mu + exp(logvar / 2) * eps, log q(h|x) = -(sum(logvar + eps^2) + DIM log 2 pi) / 2   (gaussian.py:29-38, priors/flow.py:236-241)
+__global__ void posterior_sample_kernel(const float* __restrict__ c, const float* __restrict__ eps, float* __restrict__ h,
+                                        float* __restrict__ logq) {
+  __shared__ float red[2];
+  const int t = threadIdx.x;   // DIM threads
+  const long long n = blockIdx.x;
+  const float mu = c[n * 2 * DIM + t], lv = c[n * 2 * DIM + DIM + t], e = eps[n * DIM + t];
+  h[n * DIM + t] = e * expf(0.5f * lv) + mu;
+  float s = warp_sum(lv + e * e);
+  if ((t & 31) == 0) red[t >> 5] = s;
+  __syncthreads();
+  if (t == 0) logq[n] = -0.5f * (red[0] + red[1] + (float)DIM * 1.8378770664093453f);
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += alpha * x[i];
+}
+
+__global__ void cos2pi_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = cosf(6.283185307179586f * x[i]);
 }
 
 // flag[0] = max_i (x[i] - x_prev[i])^2 / (atol + |y[i]| * rtol), as the bit pattern of a non-negative float
@@ -118,10 +156,37 @@ __global__ void fixed_point_check_kernel(const float* __restrict__ x, const floa
 }  // namespace
 
 extern "C" int indm_prior_flow(const float* in, float* out, float* logdet, const float* params, const indm_flow_op_t* ops, int n_ops,
-                               float logdet_const, int64_t N, void* stream_) {
+                               float logdet_const, const float* kl_base, int64_t N, void* stream_) {
   INDM_CHECK_ARG(in && out && params && ops && n_ops > 0 && N > 0, "prior_flow: bad arguments");
-  prior_flow_kernel<<<(unsigned)N, HID, 0, (cudaStream_t)stream_>>>(in, out, logdet, params, ops, n_ops, logdet_const);
+  prior_flow_kernel<<<(unsigned)N, HID, 0, (cudaStream_t)stream_>>>(in, out, logdet, params, ops, n_ops, logdet_const, kl_base);
   INDM_CHECK_LAUNCH("prior_flow");
+  return INDM_OK;
+}
+
+extern "C" int indm_posterior_sample(const float* c, const float* eps, float* h, float* logq, int64_t N, void* stream_) {
+  INDM_CHECK_ARG(c && eps && h && logq && N > 0, "posterior_sample: bad arguments");
+  posterior_sample_kernel<<<(unsigned)N, DIM, 0, (cudaStream_t)stream_>>>(c, eps, h, logq);
+  INDM_CHECK_LAUNCH("posterior_sample");
+  return INDM_OK;
+}
+
+extern "C" int indm_axpy_f32(float* y, const float* x, float alpha, int64_t n, void* stream_) {
+  INDM_CHECK_ARG(y && x && n > 0, "axpy: bad arguments");
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)indm_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  axpy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(y, x, alpha, n);
+  INDM_CHECK_LAUNCH("axpy");
+  return INDM_OK;
+}
+
+extern "C" int indm_cos2pi_f32(const float* x, float* out, int64_t n, void* stream_) {
+  INDM_CHECK_ARG(x && out && n > 0, "cos2pi: bad arguments");
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)indm_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  cos2pi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, out, n);
+  INDM_CHECK_LAUNCH("cos2pi");
   return INDM_OK;
 }
 

@@ -46,7 +46,11 @@ struct IgemmParams {
   const float* rowscale;  // per-image multiplier (head conv: -1/std or 1/sigma)
   float scale;
   float res_scale;        // multiplier of the residual term
-  int act;                // 0 none, 1 Sin(x) = sin(2 pi x) / (2 pi)  (resflow activation)
+  int act;                // 0 none, 1 Sin(x) = sin(2 pi x) / (2 pi)  (resflow activation), 2 ELU
+  int pad;                // stride 2 only: zero padding (0 or 1) of the strided window
+  const void* mul;        // optional elementwise multiplier of the result: NHWC operand dtype (mode 0) / NCHW fp32 (mode 1)
+  long long mul_ld;
+  void* aux_cos;          // optional: cos(2 pi v) of the pre-activation value v, NHWC operand dtype (the Sin derivative)
   float* out_f32;
   __nv_bfloat16* out_bf16;
   long long out_ld;
@@ -163,8 +167,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           int ay = y0, ax = x0;
           if (p.stride == 2) {
             // valid (pad 0) stride-2 window: input pixel (2y + ky, 2x + kx); the tensor map traverses with element stride 2
-            ay = 2 * y0 + tap / 3;
-            ax = 2 * x0 + tap % 3;
+            ay = 2 * y0 - p.pad + (p.taps == 9 ? tap / 3 : 0);
+            ax = 2 * x0 - p.pad + (p.taps == 9 ? tap % 3 : 0);
           } else if (p.taps == 9) {
             ay += tap / 3 - 1;
             ax += tap % 3 - 1;
@@ -330,9 +334,45 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      if (p.aux_cos) {
+        // derivative of the Sin activation at the pre-activation value, kept for the VJP chain of the log-det estimators
+        if (TF32) {
+          float* dst = (float*)p.aux_cos + pix * p.out_ld + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) dst[i] = cosf(6.283185307179586f * f[i]);
+        } else {
+          __nv_bfloat16* dst = (__nv_bfloat16*)p.aux_cos + pix * p.out_ld + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) dst[i] = __float2bfloat16_rn(cosf(6.283185307179586f * f[i]));
+        }
+      }
       if (p.act == 1) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = sinf(6.283185307179586f * f[i]) * 0.15915494309189535f;
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : expm1f(f[i]);
+      }
+      if (p.mul) {
+        if (p.out_mode == 1) {
+          const long long hw = (long long)p.H * p.W;
+          const float* mm = (const float*)p.mul + (long long)n * p.Cout * hw + (long long)y * p.W + x;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) f[i] *= mm[(long long)(c0 + i) * hw];
+        } else if (TF32) {
+          const float* mm = (const float*)p.mul + pix * p.mul_ld + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) f[i] *= mm[i];
+        } else {
+          const __nv_bfloat16* mm = (const __nv_bfloat16*)p.mul + pix * p.mul_ld + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Cout) f[i] *= __bfloat162float(mm[i]);
+        }
       }
       if (p.round_tf32_out) {
 #pragma unroll
@@ -461,7 +501,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   INDM_CHECK_ARG(d->taps == 1 || d->taps == 9, "igemm: taps must be 1 or 9 (got %d)", d->taps);
   INDM_CHECK_ARG(!(d->batched_b && d->taps != 1), "igemm: batched B requires taps == 1");
   INDM_CHECK_ARG(d->out_f32 || d->out_bf16 || d->out_t, "igemm: no output");
-  INDM_CHECK_ARG(d->act == 0 || d->act == 1, "igemm: act must be 0 (none) or 1 (Sin)");
+  INDM_CHECK_ARG(d->act >= 0 && d->act <= 2, "igemm: act must be 0 (none), 1 (Sin) or 2 (ELU)");
 
   IgemmParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
@@ -495,7 +535,13 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   p.batched_b = d->batched_b;
   p.stride = d->stride == 2 ? 2 : 1;
   INDM_CHECK_ARG(d->stride == 0 || d->stride == 1 || d->stride == 2, "igemm: stride must be 1 or 2");
-  INDM_CHECK_ARG(p.stride == 1 || (d->taps == 9 && !d->a2 && !d->batched_b && d->W < 128), "igemm: stride 2 needs taps == 9, no second segment");
+  INDM_CHECK_ARG(p.stride == 1 || (!d->a2 && !d->batched_b && d->W < 128), "igemm: stride 2 excludes a second segment / batched B");
+  INDM_CHECK_ARG(d->pad == 0 || (d->pad == 1 && p.stride == 2), "igemm: pad is 0, or 1 with stride 2");
+  p.pad = d->pad;
+  p.mul = d->mul;
+  p.mul_ld = d->mul_ld ? d->mul_ld : d->Cout;
+  p.aux_cos = d->aux_cos;
+  INDM_CHECK_ARG(!d->aux_cos || d->out_mode == 0, "igemm: aux_cos needs out_mode 0");
   p.bias = d->bias;
   p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.residual = d->residual; p.res_ld = d->res_ld;
@@ -529,7 +575,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   {
     const long long ld = d->a_ld ? d->a_ld : d->Cin;
     // stride 2: the A grid is the (2H+1) x (2W+1) FIR-padded image (models/up_or_down_sampling.py:173-178), H x W the output grid
-    const int aH = p.stride == 2 ? 2 * d->H + 1 : d->H, aW = p.stride == 2 ? 2 * d->W + 1 : d->W;
+    const int aH = p.stride == 2 ? (d->a_H ? d->a_H : 2 * d->H + 1) : d->H, aW = p.stride == 2 ? (d->a_W ? d->a_W : 2 * d->W + 1) : d->W;
     const long long img = d->a_img_stride ? d->a_img_stride : (long long)aH * aW * ld;
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)aW, (uint64_t)aH, (uint64_t)d->N};
     uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)aW * ld * esz, (uint64_t)img * esz};

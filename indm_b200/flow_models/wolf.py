@@ -27,6 +27,25 @@ from .. import _lib as L
 COEFF = 0.98
 
 
+def _poisson_1mcdf(lamb, k, offset):
+    """P(N >= k - offset) for N ~ Poisson(lamb), 1 for k <= offset (iresblock.py:306-318)"""
+    if k <= offset:
+        return 1.
+    k = k - offset
+    acc = 1.
+    for i in range(1, k):
+        acc += lamb ** i / math.factorial(i)
+    return 1 - math.exp(-lamb) * acc
+
+
+def series_coefficients(n, training, lamb=2.0, n_exact_terms=2):
+    """Russian-roulette power-series weights of iResBlock._logdetgrad (iresblock.py:114-132) for one Poisson draw n:
+    K = n + offset terms, c_k = 1 / P(N >= k - offset); offset = n_exact_terms in training, 20 in eval."""
+    offset = n_exact_terms if training else 20
+    K = n + offset
+    return K, [1.0 / _poisson_1mcdf(lamb, k, offset) for k in range(1, K + 1)]
+
+
 # ------------------------------------------------------------------------------------------------ parameter containers
 class _LopConv(nn.Module):
     def __init__(self, cin, cout, k, cond_dim=None):
@@ -251,10 +270,13 @@ class WolfCore(nn.Module):
         return e
 
     def forward(self, data, y=None, n_bits=8, nsamples=1, reverse=False, eval_logdet=True, *, eps=None, h=None, seed=0,
-                atol=1e-5, rtol=1e-5):
+                atol=1e-5, rtol=1e-5, vareps=None, n_terms=None):
         """wolf.py:81-130.  reverse=True: sample h from the prior (or use `eps` / `h` if given) and invert the flow.
-        reverse=False needs the posterior encoder + power-series log-det (SURVEY.md §8 rows F2/F3 forward): `h=` must
-        be supplied and eval_logdet must be False until those land on the CUDA path."""
+        reverse=False: h ~ q(h|x) (posterior encoder; `eps` = the reparameterisation noise, `h` overrides it), then the
+        residual-flow forward; with eval_logdet the power-series log-det of every block and the KL term are returned as
+        `-logdet_total - KL` exactly like the reference (`vareps` = per-block probe tensors, `n_terms` = per-block Poisson
+        draws, both optional: defaults are the in-kernel Philox generator and numpy's global RNG, the generator the
+        reference uses, iresblock.py:306)."""
         if not data.is_cuda:
             raise RuntimeError('indm_b200 WolfCore needs CUDA tensors: there is no CPU / PyTorch fallback path')
         eng = self.engine(data.shape[0])
@@ -262,10 +284,22 @@ class WolfCore(nn.Module):
             if eps is None and h is None:
                 self._draws += 1      # a fresh h ~ prior per call, like discriminator.sample_from_prior (wolf.py:83)
             return eng.reverse(data, eps=eps, h=h, seed=seed, offset=self._draws, atol=atol, rtol=rtol)
-        if h is None or eval_logdet:
-            raise NotImplementedError('wolf forward with posterior encoder / log-det estimator is not on the CUDA path yet; '
-                                      'pass h= and eval_logdet=False for the residual-flow forward map')
-        return eng.forward_map(data, h)
+        if nsamples != 1:
+            raise NotImplementedError('flow.train_k = 1 in every INDM config')
+        if self.training:
+            raise NotImplementedError('training-mode flow forward (batch-statistics BatchNorm in the posterior encoder, '
+                                      'differentiable Neumann estimator) is not on the CUDA path yet: call flow_model.eval()')
+        kl = None
+        if h is None:
+            self._draws += 1
+            h, kl = eng.posterior(data, eps=eps, seed=seed, offset=self._draws)
+        if not eval_logdet:
+            return eng.forward_map(data, h)
+        z, logpx = eng.forward_logdet(data, h, vareps=vareps, n_terms=n_terms, training=False, seed=seed, offset=self._draws)
+        loss = -logpx                       # wolf.py:126-128: loss = -logdet - kl with logdet = logpx = -(sum of block log-dets)
+        if kl is not None:
+            loss = loss - kl
+        return z, loss
 
 
 # ------------------------------------------------------------------------------------------------ engine
@@ -352,6 +386,12 @@ class FlowEngine:
                 self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
                 self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
             self._pack_prior()
+            self._vjp_weights()
+            self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
+            if not hasattr(self, 'enc'):
+                self._build_encoder()
+            for job in self.enc['jobs']:
+                job()
         self._version = self.version()
 
     def _pack_prior(self):
@@ -407,13 +447,14 @@ class FlowEngine:
             self.prior_ops[name] = (buf, len(prog), ld)
 
     # ---- building blocks
-    def prior_flow(self, z, direction, want_logdet=False):
+    def prior_flow(self, z, direction, want_logdet=False, kl_base=None):
+        """kl_base = log q(h|x): the second result becomes KL = log q - log p(h) (FlowPrior.calcKL) instead of the log-det"""
         buf, n, ld = self.prior_ops[direction]
         out = torch.empty_like(z)
-        logdet = torch.empty((z.shape[0],), device=self.dev) if want_logdet else None
+        logdet = torch.empty((z.shape[0],), device=self.dev) if (want_logdet or kl_base is not None) else None
         L.call('indm_prior_flow', L.ptr(z), L.ptr(out), L.ptr(logdet), L.ptr(self.prior_params), L.ptr(buf), n, ctypes.c_float(ld),
-               z.shape[0])
-        return (out, logdet) if want_logdet else out
+               L.ptr(kl_base), z.shape[0])
+        return (out, logdet) if logdet is not None else out
 
     def _cond_table(self, h):
         nblk = len(self.blocks)
@@ -494,6 +535,242 @@ class FlowEngine:
                 self.iterations.append(it)
                 x = cur
         return x.reshape(shape)
+
+    # ---- posterior q(h|x): BN-ResNet encoder -> weight-normed linear -> reparameterisation -> KL against the flow prior
+    def _build_encoder(self):
+        core, N, dev = self.core, self.N, self.dev
+        enc = core.config.flow.wolf_params['discriminator']['encoder']
+        kc = self.kchunk
+        cp = lambda c: ((c + kc - 1) // kc) * kc
+        c0, S, _ = core.input_shape
+        E = dict(ops=[], jobs=[])
+        self.enc = E
+        E['x_in'] = torch.zeros((N, S, S, cp(c0)), device=dev, dtype=self.tdtype)
+        net = core.discriminator.encoder.net
+
+        def fold(conv, bn, cin_pad, cout):
+            """conv weight with the eval-mode BatchNorm folded in: W * s[o], bias = beta - mean * s (nn.BatchNorm2d, eps 1e-5)"""
+            k = conv.weight.shape[-1]
+            w = torch.zeros((k * k, cout, cin_pad), device=dev, dtype=self.tdtype)
+            b = torch.zeros((cout,), device=dev)
+
+            def job():
+                W = conv.weight.detach().to(dev, torch.float32)
+                if bn is not None:
+                    sc = bn.weight.detach().to(dev, torch.float32) / torch.sqrt(bn.running_var.detach().to(dev, torch.float32) + 1e-5)
+                    W = W * sc[:, None, None, None]
+                    b.copy_(bn.bias.detach().to(dev, torch.float32) - bn.running_mean.detach().to(dev, torch.float32) * sc)
+                else:
+                    b.copy_(conv.bias.detach().to(dev, torch.float32))
+                co, ci = W.shape[:2]
+                w.zero_()
+                w[:, :, :ci].copy_(self._round(W.permute(2, 3, 0, 1).reshape(k * k, co, ci)))
+            E['jobs'].append(job)
+            return w, b
+
+        def conv(a, Hin, cin, w, b, cout, stride, taps, act, residual=None, want_f32=False, nchw=False):
+            Ho = Hin // stride
+            kw = dict(dtype=self.dt, a=a, N=N, H=Ho, W=Ho, Cin=cp(cin), b=w, Cout=cout, taps=taps, bias=b, act=act)
+            if stride == 2:
+                kw.update(stride=2, a_H=Hin, a_W=Hin, pad=1 if taps == 9 else 0)
+            if residual is not None:
+                kw.update(residual=residual, res_ld=cp(cout), res_scale=1.0)
+            out_op = out_f = None
+            if nchw:
+                out_f = torch.zeros((N, cout, Ho, Ho), device=dev)
+                kw.update(out_mode=1, out_f32=out_f)
+            else:
+                out_op = torch.zeros((N, Ho, Ho, cp(cout)), device=dev, dtype=self.tdtype)
+                kw.update(out_ld=cp(cout))
+                if self.mode == 'bf16':
+                    kw['out_bf16'] = out_op
+                    if want_f32:
+                        out_f = torch.zeros((N, Ho, Ho, cp(cout)), device=dev)
+                        kw['out_f32'] = out_f
+                else:
+                    kw['out_f32'] = out_op
+                    out_f = out_op
+            E['ops'].append(kw)
+            return out_op, out_f, Ho
+
+        x, xf, H, inp = E['x_in'], None, S, c0
+        for lv, hid in enumerate(enc['hidden_planes']):
+            res = getattr(net, f'resnet{lv}')
+            for m, stride in enumerate((1, 2)):
+                blk = res.main[m]
+                ci = inp if m == 0 else hid
+                w1, b1 = fold(blk.conv1, blk.bn1, cp(ci), hid)
+                t1, _, Ho = conv(x, H, ci, w1, b1, hid, stride, 9, 2)
+                if hasattr(blk, 'downsample'):
+                    wd, bd = fold(blk.downsample[0], blk.downsample[1], cp(ci), hid)
+                    _, r, _ = conv(x, H, ci, wd, bd, hid, stride, 1, 0, want_f32=True)
+                else:
+                    r = xf                         # identity shortcut: the fp32 copy of the block input
+                w2, b2 = fold(blk.conv2, blk.bn2, cp(hid), hid)
+                x, xf, _ = conv(t1, Ho, hid, w2, b2, hid, 1, 9, 2, residual=r, want_f32=True)
+                H = Ho
+            inp = hid
+        wt, bt = fold(net.top, None, cp(inp), enc['out_planes'])
+        _, top, _ = conv(x, H, inp, wt, bt, enc['out_planes'], 1, 1, 2, nchw=True)
+        E['top'] = top                                                   # [N, out_planes, h, w] == flattened [N, in_dim]
+        d = core.latent_dim
+        E['fc_w'] = torch.empty((2 * d, top[0].numel()), device=dev)
+        E['fc_b'] = torch.empty((2 * d,), device=dev)
+        fc = core.discriminator.fc.linear
+
+        def job_fc():
+            v, g = fc.weight_v.detach().to(dev, torch.float32), fc.weight_g.detach().to(dev, torch.float32)
+            E['fc_w'].copy_(g * v / v.norm(dim=1, keepdim=True))           # legacy weight_norm, dim 0 (nnet/weight_norm.py:8-40)
+            E['fc_b'].copy_(fc.bias.detach().to(dev, torch.float32))
+        E['jobs'].append(job_fc)
+        E['c'] = torch.empty((N, 2 * d), device=dev)
+        E['logq'] = torch.empty((N,), device=dev)
+        E['c0'] = c0
+
+    def posterior(self, x, eps=None, seed=0, offset=0):
+        """GaussianDiscriminator.sampling_and_KL (gaussian.py:67-76) with nsamples = 1: returns (h [N,64], KL [N])."""
+        self._ensure()
+        N, E = self.N, self.enc
+        c0, S, _ = self.core.input_shape
+        x = x.float().contiguous()
+        L.call('indm_prep_input', L.ptr(x), L.ptr(E['x_in']), N, c0, S, S, E['x_in'].shape[-1], ctypes.c_float(1.0), ctypes.c_float(0.0), 0, self.dt)
+        for kw in E['ops']:
+            L.igemm(**kw)
+        top = E['top']
+        L.call('indm_linear_f32', L.ptr(top), L.ptr(E['fc_w']), L.ptr(E['fc_b']), L.ptr(E['c']), N, top[0].numel(), E['c'].shape[1], 0, 0, L.DTYPE_F32)
+        if eps is None:
+            L.call('indm_randn_f32', L.ptr(self.eps), self.eps.numel(), seed, 0x7F200000 + offset)
+            eps = self.eps
+        h = torch.empty((N, self.core.latent_dim), device=self.dev)
+        L.call('indm_posterior_sample', L.ptr(E['c']), L.ptr(eps.float().contiguous()), L.ptr(h), L.ptr(E['logq']), N)
+        _, kl = self.prior_flow(h, 'forward', kl_base=E['logq'])
+        return h, kl
+
+    # ---- power-series log-det (iresblock.py:90-174): VJP chain of g on the tensor cores
+    def _vjp_weights(self):
+        dev, idim = self.dev, self.idim
+        for i, (s, b, m) in enumerate(self.blocks):
+            W = self.w[(s, b)]
+            cp = self.cpad[s]
+            c = m.channels
+            if 'w3d' not in W:
+                W['w3d'] = torch.zeros((9, idim, cp), device=dev, dtype=self.tdtype)
+                W['w2d'] = torch.empty((idim, idim), device=dev, dtype=self.tdtype)
+                W['w1d'] = torch.empty((9, c, idim), device=dev, dtype=self.tdtype)
+            # transposed, tap-flipped packs of the (already Lipschitz-normalised, operand-rounded) forward weights
+            w1 = W['w1'][:, :, :c].float().reshape(3, 3, idim, c)           # [ky][kx][o][ci]
+            W['w1d'].copy_(w1.flip(0, 1).permute(0, 1, 3, 2).reshape(9, c, idim))
+            W['w2d'].copy_(W['w2'].float().t())
+            w3 = W['w3'].float().reshape(3, 3, c, idim)                       # [ky][kx][o=c][ci=idim]
+            W['w3d'][:, :, :c].copy_(w3.flip(0, 1).permute(0, 1, 3, 2).reshape(9, idim, c))
+
+    def _g_store(self, i, s, m, x_nchw, out):
+        """out = x + g(x; h) (NCHW fp32) keeping cos(2 pi .) of the three Sin pre-activations for the VJP chain"""
+        N, idim = self.N, self.idim
+        c = m.channels
+        _, h0, w0 = self.core.input_shape
+        H, Wd = h0 >> s, w0 >> s
+        W = self.w[(self.blocks[i][0], self.blocks[i][1])]
+        a0 = self.a0[s]
+        n_el = N * H * Wd * idim
+        u1, u2 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim), self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
+        d1, d2 = self.d1.view(-1)[:n_el].view(N, H, Wd, idim), self.d2.view(-1)[:n_el].view(N, H, Wd, idim)
+        L.call('indm_prep_input', L.ptr(x_nchw), L.ptr(a0), N, c, H, Wd, self.cpad[s], ctypes.c_float(1.0), ctypes.c_float(0.0),
+               0 if m.first else 1, self.dt)
+        d0 = None
+        if not m.first:
+            d0 = self.d0.view(-1)[:x_nchw.numel()].view(x_nchw.shape)
+            L.call('indm_cos2pi_f32', L.ptr(x_nchw), L.ptr(d0), x_nchw.numel())
+        okw = dict(out_bf16=u1) if self.mode == 'bf16' else dict(out_f32=u1)
+        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.cpad[s], b=W['w1'], Cout=idim, taps=9, bias=W['b1'], act=1, out_ld=idim,
+                aux_cos=d1, **okw)
+        okw = dict(out_bf16=u2) if self.mode == 'bf16' else dict(out_f32=u2)
+        L.igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
+                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, aux_cos=d2, **okw)
+        L.igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=c, taps=9, bias=W['b3'], scale=1.0, residual=x_nchw,
+                res_scale=1.0, out_mode=1, out_f32=out)
+        return d0, d1, d2
+
+    def _g_vjp(self, i, s, m, v, out, d0, d1, d2):
+        """out = J_g(x)^T v for the block whose cos factors are (d0, d1, d2); v, out NCHW fp32"""
+        N, idim = self.N, self.idim
+        c = m.channels
+        _, h0, w0 = self.core.input_shape
+        H, Wd = h0 >> s, w0 >> s
+        W = self.w[(self.blocks[i][0], self.blocks[i][1])]
+        a0 = self.a0[s]
+        n_el = N * H * Wd * idim
+        t1, t2 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim), self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
+        L.call('indm_nchw_to_nhwc', L.ptr(v), None, L.ptr(a0), N, c, H, Wd, self.cpad[s], ctypes.c_float(1.0), self.dt)
+        okw = dict(out_bf16=t2) if self.mode == 'bf16' else dict(out_f32=t2)
+        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.cpad[s], b=W['w3d'], Cout=idim, taps=9, out_ld=idim, mul=d2, mul_ld=idim, **okw)
+        okw = dict(out_bf16=t1) if self.mode == 'bf16' else dict(out_f32=t1)
+        L.igemm(dtype=self.dt, a=t2, N=N, H=H, W=Wd, Cin=idim, b=W['w2d'], Cout=idim, taps=1, out_ld=idim, mul=d1, mul_ld=idim, **okw)
+        L.igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1d'], Cout=c, taps=9, out_mode=1, out_f32=out, mul=d0)
+
+    def forward_logdet(self, x, h, vareps=None, n_terms=None, training=False, seed=0, offset=0):
+        """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z, logpx [N]) with
+        logpx = -sum over blocks of the power-series log-det estimate: basic estimator with 20 exact terms in eval mode
+        (iresblock.py:127-132,253-261), Neumann estimator value with 2 exact terms in training mode (:114-121,264-273)."""
+        self._ensure()
+        N = self.N
+        x = x.float().contiguous()
+        shape = x.shape
+        self.h.copy_(h)
+        self._cond_table(self.h)
+        if not hasattr(self, 'd1'):
+            self.d0 = torch.empty((x.numel(),), device=self.dev)
+            self.d1, self.d2 = torch.empty_like(self.u1), torch.empty_like(self.u2)
+        logpx = torch.zeros((N,), device=self.dev)
+        nb = self.nb
+        bi = 0
+        self.vjp_count = 0
+        for s in range(len(nb)):
+            for i, (ss, b, m) in enumerate(self.blocks):
+                if ss != s:
+                    continue
+                n = int(n_terms[bi]) if n_terms is not None else int(np.random.poisson(self.lamb[i], 1)[0])     # iresblock.py:306
+                K, coef = series_coefficients(n, training, self.lamb[i])
+                if vareps is not None:
+                    ve = vareps[bi].to(self.dev).float().contiguous()
+                else:
+                    ve = torch.empty_like(x)
+                    L.call('indm_randn_f32', L.ptr(ve), ve.numel(), seed, 0x7F300000 + (offset << 8) + bi)
+                out = torch.empty_like(x)
+                d0, d1, d2 = self._g_store(i, s, m, x, out)
+                D = x[0].numel()
+                bufs = [torch.empty_like(x), torch.empty_like(x)]
+                cur = ve
+                if not training:
+                    # basic estimator: sum_k (-1)^(k+1)/k c_k <J^k^T eps, eps>
+                    for k in range(1, K + 1):
+                        nxt = bufs[k & 1]
+                        self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
+                        L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-((-1) ** (k + 1)) / k * coef[k - 1]), 1)
+                        cur = nxt
+                    self.vjp_count += K
+                else:
+                    # Neumann estimator (value): w = eps + sum_k (-1)^k c_k J^k^T eps ; logdet = <J^T w, eps>
+                    neumann = ve.clone()
+                    for k in range(1, K + 1):
+                        nxt = bufs[k & 1]
+                        self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
+                        L.call('indm_axpy_f32', L.ptr(neumann), L.ptr(nxt), ctypes.c_float(((-1) ** k) * coef[k - 1]), neumann.numel())
+                        cur = nxt
+                    nxt = bufs[(K + 1) & 1]
+                    self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
+                    L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
+                    self.vjp_count += K + 1
+                x = out
+                bi += 1
+            if s < len(nb) - 1:
+                x = _squeeze2(x).contiguous()
+        out = x.reshape(N, -1)
+        if len(nb) > 1:
+            out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
+        else:
+            out = out.view(shape)
+        return out.contiguous(), logpx
 
     def forward_map(self, x, h):
         """ResidualFlow.fwdpass(x, h, eval_logdet=False) on the flow's own input layout (resflow_.py:310-324)."""

@@ -388,10 +388,9 @@ class FlowEngine:
             self._pack_prior()
             self._vjp_weights()
             self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
-            if not hasattr(self, 'enc'):
-                self._build_encoder()
-            for job in self.enc['jobs']:
-                job()
+            if hasattr(self, 'enc'):
+                for job in self.enc['jobs']:
+                    job()
         self._version = self.version()
 
     def _pack_prior(self):
@@ -630,6 +629,11 @@ class FlowEngine:
     def posterior(self, x, eps=None, seed=0, offset=0):
         """GaussianDiscriminator.sampling_and_KL (gaussian.py:67-76) with nsamples = 1: returns (h [N,64], KL [N])."""
         self._ensure()
+        if not hasattr(self, 'enc'):          # built on first use: sampling-only callers never need the posterior encoder
+            self._build_encoder()
+            with torch.no_grad():
+                for job in self.enc['jobs']:
+                    job()
         N, E = self.N, self.enc
         c0, S, _ = self.core.input_shape
         x = x.float().contiguous()

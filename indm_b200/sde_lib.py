@@ -152,12 +152,14 @@ class VPSDE(SDE):
     def normalizing_constant(self, t_min):
         return self.antiderivative(self.T) - self.antiderivative(t_min)
 
-    def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=None):
+    def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=None, u=None):
+        """`u` (optional): the uniform draw, supplied by parity tests instead of torch.rand"""
         if importance_sampling is None:
             importance_sampling = config.training.importance_sampling
         if importance_sampling:
             Z = self.normalizing_constant(t_min)
-            u = torch.rand(batch_size, device=batch_device)
+            if u is None:
+                u = torch.rand(batch_size, device=batch_device)
             return (-self.beta_0 + torch.sqrt(self.beta_0 ** 2 + 2 * (self.beta_1 - self.beta_0) *
                     torch.log(1. + torch.exp(Z * u + self.antiderivative(t_min))))) / (self.beta_1 - self.beta_0), Z.detach()
         return torch.rand(batch_size, device=batch_device) * (self.T - t_min) + t_min, 1
@@ -246,12 +248,13 @@ class VESDE(SDE):
     def normalizing_constant(self, t_min):
         return self.antiderivative(self.T) - self.antiderivative(t_min)
 
-    def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=None):
+    def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=None, u=None):
         if importance_sampling is None:
             importance_sampling = config.training.importance_sampling
         if importance_sampling:
             Z = self.normalizing_constant(t_min)
-            u = torch.rand(batch_size, device=batch_device)
+            if u is None:
+                u = torch.rand(batch_size, device=batch_device)
             return t_min + ((Z * u) / (2. * (np.log(self.sigma_max) - np.log(self.sigma_min)))), Z.detach()
         return torch.rand(batch_size, device=batch_device) * (self.T - t_min) + t_min, 1
 

@@ -232,6 +232,79 @@ def make_flowfwd():
         print('flowfwd', tag, 'ns', ns, 'ldkl', ldkl.detach().numpy())
 
 
+def small_joint(cfg):
+    """Small score net + small wolf flow on 32x32 images (the posterior encoder needs the full extent): same code paths as
+    configs/vp/CIFAR10/indm_nll.py."""
+    cfg.model.nf = 128
+    cfg.model.ch_mult = (1, 2)
+    cfg.model.num_res_blocks = 1
+    cfg.model.attn_resolutions = (16,)
+    cfg.flow.nblocks = '2-2'
+    cfg.flow.intermediate_dim = 128
+    return cfg
+
+
+def make_likelihood():
+    """likelihood.get_likelihood_fn (PF-ODE NLL, RK45 rtol = atol = 1e-3) and likelihood.get_elbo_fn of the live reference on a
+    small INDM-VP model, every random draw replayed (torch.randn / randn_like / randint_like / rand, poisson_sample)."""
+    mutils, sde_lib, likelihood, fm = rl.load('models.utils', 'sde_lib', 'likelihood', 'flow_models.flow_model')
+    import flow_models.wolf.flows.resflow.layers.iresblock as irb
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    path = 'configs/vp/CIFAR10/indm_nll.py'
+    cfg = small_joint(rl.get_config(path))
+    model, _ = ref_model(cfg, seed=11)
+    with rl.reference_cwd():
+        flow = fm.create_flow_model(cfg)
+    pcfg = small_joint(pconfigs.get_config('vp/CIFAR10/indm_nll'))
+    flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, 21).items()})
+    flow.eval()
+    sde = sde_lib.get_sde(cfg)
+    B, S = 2, 32
+    rng = np.random.default_rng(51)
+    data = rng.uniform(-1, 1, size=(B, 3, S, S)).astype(np.float32)
+    layout = oflow.block_layout(pcfg)
+    c0, h0, w0 = oflow.flow_input_shape(pcfg)
+    inverse_scaler = lambda v: (v + 1.) / 2.
+    out = dict(data=data, seed_score=np.asarray(11), seed_flow=np.asarray(21))
+    for which in ('nll', 'elbo'):
+        eps_post = rng.standard_normal((B, 64)).astype(np.float32)
+        ns = rng.poisson(2.0, size=len(layout)).astype(np.int64)
+        varepss = [rng.standard_normal((B, c, h0 >> s, w0 >> s)).astype(np.float32) for (s, b, c, first) in layout]
+        rad = (rng.integers(0, 2, size=(B, 3, S, S)).astype(np.float32))         # randint_like result in {0, 1}
+        gauss = [rng.standard_normal((B, 3, S, S)).astype(np.float32) for _ in range(4)]
+        u = rng.uniform(size=(B,)).astype(np.float32)
+        q_like = [torch.from_numpy(v) for v in varepss] + [torch.from_numpy(v) for v in gauss]
+        q_n = list(ns)
+        real = (torch.randn, torch.randn_like, torch.randint_like, torch.rand, irb.poisson_sample)
+        torch.randn = lambda *a, **k: torch.from_numpy(eps_post).reshape(B, 1, 64)
+        torch.randn_like = lambda t, **k: q_like.pop(0)
+        torch.randint_like = lambda t, **k: torch.from_numpy(rad)
+        torch.rand = lambda *a, **k: torch.from_numpy(u)
+        irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+        try:
+            if which == 'nll':
+                fn = likelihood.get_likelihood_fn(cfg, sde, inverse_scaler, rtol=1e-3, atol=1e-3)
+                bpd, z, nfe = fn(model, flow, torch.from_numpy(data), eps_bpd=1e-5)
+                out.update(nll_bpd=bpd.detach().numpy(), nll_z=z.detach().numpy(), nll_nfe=np.asarray(nfe))
+                used = 4 + 3         # vareps x4, perturbation z, residual x2
+            else:
+                fn = likelihood.get_elbo_fn(cfg, sde, inverse_scaler)
+                a, b = fn(model, flow, torch.from_numpy(data))
+                out.update(elbo_bpd=a.detach().numpy(), elbo_bpd_residual=b.detach().numpy())
+                used = 4 + 4         # vareps x4, z, lp_z, residual x2
+        finally:
+            torch.randn, torch.randn_like, torch.randint_like, torch.rand, irb.poisson_sample = real
+        assert len(q_like) == 8 - used and not q_n, (len(q_like), q_n)
+        out.update({f'{which}_eps_post': eps_post, f'{which}_ns': ns, f'{which}_rad': rad, f'{which}_u': u})
+        for i, v in enumerate(varepss):
+            out[f'{which}_vareps_{i}'] = v
+        for i, v in enumerate(gauss):
+            out[f'{which}_gauss_{i}'] = v
+        print('likelihood', which, {k: v for k, v in out.items() if k.endswith('bpd') or k.endswith('nfe') or k.endswith('residual')})
+    np.savez_compressed(os.path.join(HERE, 'likelihood_small_vp.npz'), **out)
+
+
 def make_vjp():
     """Input vector-Jacobian products of the reference score function (what likelihood.get_div_fn builds through autograd,
     likelihood.py:27-38): J^T eps with Rademacher eps, and the Hutchinson contraction eps^T J eps from the reference's own div_fn."""
@@ -352,7 +425,7 @@ def make_flow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

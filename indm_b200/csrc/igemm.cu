@@ -31,6 +31,7 @@ struct IgemmParams {
   int N, H, W;           // image grid of the A operand (plain GEMM: N=1,H=1,W=M)
   int BW, BH, BN;        // box (pixels) loaded per tile; BW*BH*BN <= 128
   int tiles_x, tiles_y;  // tiles along W and H
+  int tiles_n, n_tiles;  // tiles along the image dimension; tiles along Cout
   int Cout;
   int taps;              // 1 or 9
   int chunks1, chunks2;  // K chunks in segment 1 (per tap) and segment 2
@@ -63,69 +64,72 @@ struct IgemmParams {
   int gn_groups;
 };
 
-// per-(image, group) sum / sum-of-squares of one 32-column slab held in registers (static indexing only: a dynamic
-// index would push the whole slab to local memory)
-template <int CPG>
-__device__ __forceinline__ void gn_accumulate(const float (&f)[32], bool row_ok, bool as_bf16, int lane, int c0, float* dst) {
-#pragma unroll
-  for (int g0 = 0; g0 < 32; g0 += CPG) {
-    float s = 0.f, q = 0.f;
-#pragma unroll
-    for (int i = 0; i < CPG; ++i) {
-      float t = f[g0 + i];
-      if (as_bf16) t = __bfloat162float(__float2bfloat16_rn(t));
-      s += t;
-      q += t * t;
-    }
-    if (!row_ok) s = q = 0.f;
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (lane == 0 && dst) {
-      atomicAdd(dst + (c0 + g0) / CPG * 2, s);
-      atomicAdd(dst + (c0 + g0) / CPG * 2 + 1, q);
-    }
-  }
+// ---------------------------------------------------------------- epilogue helpers
+struct EpiRow {       // one output row (pixel) of the tile
+  long long pix;      // flat NHWC pixel index
+  int n, y, x;
+  bool ok;
+};
+
+__device__ __forceinline__ EpiRow epi_row(const IgemmParams& p, int r, int n0, int y0, int x0) {
+  EpiRow e;
+  const int bw = r % p.BW;
+  const int bh = (r / p.BW) % p.BH;
+  const int bn = r / (p.BW * p.BH);
+  e.n = n0 + bn; e.y = y0 + bh; e.x = x0 + bw;
+  e.ok = (bn < p.BN) && (e.n < p.N) && (e.x < p.W) && (e.y < p.H);
+  e.pix = ((long long)e.n * p.H + e.y) * p.W + e.x;
+  return e;
 }
 
+__device__ __forceinline__ float act_apply(int act, float v) {
+  if (act == 1) return sinf(6.283185307179586f * v) * 0.15915494309189535f;
+  if (act == 2) return v > 0.f ? v : expm1f(v);
+  return v;
+}
+
+// Persistent, warp-specialised kernel.  grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x, ...
+//   warp 0      : TMA producer (one elected lane), smem ring of `stages` (A, B) tiles shared by all tiles of the CTA
+//   warp 1      : tcgen05.mma issuer (one elected lane); accumulators double-buffered in TMEM (2 x BLOCK_N columns) so the
+//                 main loop of tile j+1 overlaps the epilogue of tile j
+//   warps 2..5  : epilogue (warp w owns TMEM lanes 32*(w%4)..): tcgen05.ld -> smem transpose (per-warp 4 KB, XOR-swizzled) so
+//                 that every global access is a run of full 128-byte lines -> fused epilogue math -> stores
+//   warps 6, 7  : (TF32 only) hi/lo operand splitter for the error-compensated 3xTF32 product
 template <int BLOCK_N, bool TF32>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(TF32 ? 256 : 192, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
   constexpr int KCHUNK = TF32 ? 32 : 64;           // elements per 128-byte swizzle row
   constexpr int A_BYTES = kTileM * 128;            // 16 KB
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr uint32_t IDESC = umma_idesc(TF32 ? 2u : 1u, 128u, (uint32_t)BLOCK_N);
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr int NSLAB = BLOCK_N / 32 + (BLOCK_N < 32 ? 1 : 0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
-  // TF32 mode is error-compensated (3xTF32): every landed fp32 stage is split by two helper warps into hi = rna(v) (in place)
-  // and lo = v - hi (second buffer), and the issuer accumulates a_hi*b_hi + a_lo*b_hi + a_hi*b_lo.
   uint8_t* sAlo = sB + (size_t)p.stages * B_BYTES;
   uint8_t* sBlo = sAlo + (TF32 ? (size_t)p.stages * A_BYTES : 0);
-  uint64_t* bars = (uint64_t*)(sBlo + (TF32 ? (size_t)p.stages * B_BYTES : 0));
+  uint8_t* sStage = sBlo + (TF32 ? (size_t)p.stages * B_BYTES : 0);   // 4 epilogue warps x 4 KB
+  uint64_t* bars = (uint64_t*)(sStage + 4 * 4096);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
-  uint64_t* acc_bar = bars + 2 * kMaxStages;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kMaxStages + 1);
-  uint64_t* split_bar = bars + 2 * kMaxStages + 2;
+  uint64_t* split_bar = bars + 2 * kMaxStages;
+  uint64_t* tfull_bar = bars + 3 * kMaxStages;       // [2] accumulator buffer complete
+  uint64_t* tempty_bar = bars + 3 * kMaxStages + 2;  // [2] accumulator buffer drained by the epilogue warps
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates
-  const int mt = blockIdx.x;
-  const int tx = mt % p.tiles_x;
-  const int ty = (mt / p.tiles_x) % p.tiles_y;
-  const int tn = mt / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BN;
-  const int ncol0 = blockIdx.y * BLOCK_N;
-
   const int iters1 = p.taps * p.chunks1;
   const int iters = iters1 + p.chunks2;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BN) * 128u;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -139,7 +143,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&empty_bar[s], 1);
       if (TF32) mbar_init(&split_bar[s], 64);
     }
-    mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -156,33 +163,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ================= TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
-        uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], a_box_bytes + (uint32_t)B_BYTES);
-        if (it < iters1) {
-          const int tap = it / p.chunks1;
-          const int ch = it - tap * p.chunks1;
-          int ay = y0, ax = x0;
-          if (p.stride == 2) {
-            // valid (pad 0) stride-2 window: input pixel (2y + ky, 2x + kx); the tensor map traverses with element stride 2
-            ay = 2 * y0 - p.pad + (p.taps == 9 ? tap / 3 : 0);
-            ax = 2 * x0 - p.pad + (p.taps == 9 ? tap % 3 : 0);
-          } else if (p.taps == 9) {
-            ay += tap / 3 - 1;
-            ax += tap % 3 - 1;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
+        const int ncol0 = nt * BLOCK_N;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
+          uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], a_box_bytes + (uint32_t)B_BYTES);
+          if (it < iters1) {
+            const int tap = it / p.chunks1;
+            const int ch = it - tap * p.chunks1;
+            int ay = y0, ax = x0;
+            if (p.stride == 2) {
+              // strided window: input pixel (2y + ky - pad, 2x + kx - pad); the tensor map traverses with element stride 2
+              ay = 2 * y0 - p.pad + (p.taps == 9 ? tap / 3 : 0);
+              ax = 2 * x0 - p.pad + (p.taps == 9 ? tap % 3 : 0);
+            } else if (p.taps == 9) {
+              ay += tap / 3 - 1;
+              ax += tap % 3 - 1;
+            }
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
+            tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, p.batched_b ? n0 : tap);
+          } else {
+            const int ch = it - iters1;
+            tma_load_4d(a_dst, &tmA2, &full_bar[stage], ch * KCHUNK, x0, y0, n0);
+            tma_load_3d(b_dst, &tmB2, &full_bar[stage], ch * KCHUNK, ncol0, 0);
           }
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, p.batched_b ? n0 : tap);
-        } else {
-          const int ch = it - iters1;
-          tma_load_4d(a_dst, &tmA2, &full_bar[stage], ch * KCHUNK, x0, y0, n0);
-          tma_load_3d(b_dst, &tmB2, &full_bar[stage], ch * KCHUNK, ncol0, 0);
-        }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -192,254 +204,283 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ================= MMA issuer
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(TF32 ? &split_bar[stage] : &full_bar[stage], phase);
+      int j = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+        const int buf = j & 1;
+        mbar_wait(&tempty_bar[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)stage * A_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
-        if (TF32) {
-          const uint64_t alo = umma_desc_sw128(smem_u32(sAlo + (size_t)stage * A_BYTES));
-          const uint64_t blo = umma_desc_sw128(smem_u32(sBlo + (size_t)stage * B_BYTES));
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(TF32 ? &split_bar[stage] : &full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)stage * A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
+          if (TF32) {
+            const uint64_t alo = umma_desc_sw128(smem_u32(sAlo + (size_t)stage * A_BYTES));
+            const uint64_t blo = umma_desc_sw128(smem_u32(sBlo + (size_t)stage * B_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t o = (uint64_t)(2 * k);
-            umma_tf32(tmem_base, alo + o, bdesc + o, IDESC, (it | k) != 0);   // small terms first
-            umma_tf32(tmem_base, adesc + o, blo + o, IDESC, 1u);
-            umma_tf32(tmem_base, adesc + o, bdesc + o, IDESC, 1u);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
-          }
-        }
-        umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-      umma_commit(acc_bar);  // accumulator complete
-    }
-    __syncwarp();
-  } else if (TF32) {
-    // ================= operand splitter (warps 2, 3): hi/lo decomposition of each landed stage, elementwise, so the
-    // swizzled placement is irrelevant: lo lives at the same offset of the twin buffer
-    const int t = threadIdx.x - 64;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < iters; ++it) {
-      mbar_wait(&full_bar[stage], phase);
-      float4* a = reinterpret_cast<float4*>(sA + (size_t)stage * A_BYTES);
-      float4* al = reinterpret_cast<float4*>(sAlo + (size_t)stage * A_BYTES);
-      for (int i = t; i < A_BYTES / 16; i += 64) {
-        const float4 v = a[i];
-        const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-        a[i] = h;
-        al[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-      }
-      float4* b = reinterpret_cast<float4*>(sB + (size_t)stage * B_BYTES);
-      float4* bl = reinterpret_cast<float4*>(sBlo + (size_t)stage * B_BYTES);
-      for (int i = t; i < B_BYTES / 16; i += 64) {
-        const float4 v = b[i];
-        const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-        b[i] = h;
-        bl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-      }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(&split_bar[stage]);
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1u;
-      }
-    }
-  }
-
-  // ================= epilogue: all 4 warps
-  mbar_wait(acc_bar, 0);
-  tc_fence_after();
-
-  const int r = threadIdx.x;  // tile row == TMEM lane
-  const int bw = r % p.BW;
-  const int bh = (r / p.BW) % p.BH;
-  const int bn = r / (p.BW * p.BH);
-  const int n = n0 + bn, y = y0 + bh, x = x0 + bw;
-  const bool row_ok = (bn < p.BN) && (n < p.N) && (x < p.W) && (y < p.H);
-  const long long pix = ((long long)n * p.H + y) * p.W + x;
-  const float rs = (p.rowscale != nullptr && row_ok) ? p.rowscale[n] : 1.0f;
-  const float scale = p.scale * rs;
-
-#pragma unroll 1
-  for (int j = 0; j < BLOCK_N / 32 + (BLOCK_N < 32 ? 1 : 0); ++j) {
-    uint32_t v[32];
-    tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
-    tmem_ld_wait();
-    const int c0 = ncol0 + j * 32;
-    if (c0 >= p.Cout) continue;  // uniform across the CTA
-    float f[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-    const bool full = (c0 + 32 <= p.Cout);
-    if (p.bias) {
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
-          f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < p.Cout) f[i] += __ldg(p.bias + c0 + i);
-      }
-    }
-    if (row_ok) {
-      if (p.rowbias) {
-        const float* rb = p.rowbias + (long long)n * p.rowbias_ld + c0;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(rb + i));
-            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) f[i] += __ldg(rb + i);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] *= scale;
-      if (p.residual) {
-        if (p.out_mode == 1) {
-          // NCHW residual (flow fixed-point update x <- y - g(x), flow_models/.../iresblock.py:78-88)
-          const long long hw = (long long)p.H * p.W;
-          const float* rr = p.residual + (long long)n * p.Cout * hw + (long long)y * p.W + x;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) f[i] += p.res_scale * rr[(long long)(c0 + i) * hw];
-        } else {
-          const float* rr = p.residual + pix * p.res_ld + c0;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(rr + i);
-              f[i] += p.res_scale * b.x; f[i + 1] += p.res_scale * b.y; f[i + 2] += p.res_scale * b.z; f[i + 3] += p.res_scale * b.w;
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t o = (uint64_t)(2 * k);
+              umma_tf32(d_tmem, alo + o, bdesc + o, IDESC, (it | k) != 0);   // small terms first
+              umma_tf32(d_tmem, adesc + o, blo + o, IDESC, 1u);
+              umma_tf32(d_tmem, adesc + o, bdesc + o, IDESC, 1u);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + i < p.Cout) f[i] += p.res_scale * rr[i];
-          }
-        }
-      }
-      if (p.aux_cos) {
-        // derivative of the Sin activation at the pre-activation value, kept for the VJP chain of the log-det estimators
-        if (TF32) {
-          float* dst = (float*)p.aux_cos + pix * p.out_ld + c0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) dst[i] = cosf(6.283185307179586f * f[i]);
-        } else {
-          __nv_bfloat16* dst = (__nv_bfloat16*)p.aux_cos + pix * p.out_ld + c0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) dst[i] = __float2bfloat16_rn(cosf(6.283185307179586f * f[i]));
-        }
-      }
-      if (p.act == 1) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = sinf(6.283185307179586f * f[i]) * 0.15915494309189535f;
-      } else if (p.act == 2) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : expm1f(f[i]);
-      }
-      if (p.mul) {
-        if (p.out_mode == 1) {
-          const long long hw = (long long)p.H * p.W;
-          const float* mm = (const float*)p.mul + (long long)n * p.Cout * hw + (long long)y * p.W + x;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) f[i] *= mm[(long long)(c0 + i) * hw];
-        } else if (TF32) {
-          const float* mm = (const float*)p.mul + pix * p.mul_ld + c0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) f[i] *= mm[i];
-        } else {
-          const __nv_bfloat16* mm = (const __nv_bfloat16*)p.mul + pix * p.mul_ld + c0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) f[i] *= __bfloat162float(mm[i]);
-        }
-      }
-      if (p.round_tf32_out) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = round_tf32(f[i]);
-      }
-      if (p.out_mode == 1) {
-        // NCHW fp32 (network head): few channels, strided store
-        const long long hw = (long long)p.H * p.W;
-        const long long base = (long long)n * p.Cout * hw + (long long)y * p.W + x;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < p.Cout) p.out_f32[base + (long long)(c0 + i) * hw] = f[i];
-      } else {
-        const bool transposed = (p.out_mode == 2) && (c0 >= p.tcol0);
-        if (transposed) {
-          const long long hw = (long long)p.H * p.W;
-          const long long li = (long long)y * p.W + x;
-          __nv_bfloat16* dst = p.out_t + ((long long)n * (p.Cout - p.tcol0) + (c0 - p.tcol0)) * hw + li;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < p.Cout) dst[(long long)i * hw] = __float2bfloat16_rn(f[i]);
-        } else {
-          if (p.out_f32) {
-            float* dst = p.out_f32 + pix * p.out_ld + c0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c0 + i < p.Cout) dst[i] = f[i];
+            for (int k = 0; k < 4; ++k) {
+              // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
             }
           }
-          if (p.out_bf16) {
-            __nv_bfloat16* dst = p.out_bf16 + pix * p.out_ld + c0;
-            if (full) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 q;
-                q.x = pack_bf16x2(f[i], f[i + 1]);
-                q.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                q.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                q.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                *reinterpret_cast<uint4*>(dst + i) = q;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c0 + i < p.Cout) dst[i] = __float2bfloat16_rn(f[i]);
-            }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 6) {
+    if (TF32) {
+      // ================= operand splitter: hi/lo decomposition of each landed stage, elementwise, so the swizzled
+      // placement is irrelevant: lo lives at the same offset of the twin buffer
+      const int tt = threadIdx.x - 192;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          float4* a = reinterpret_cast<float4*>(sA + (size_t)stage * A_BYTES);
+          float4* al = reinterpret_cast<float4*>(sAlo + (size_t)stage * A_BYTES);
+          for (int i = tt; i < A_BYTES / 16; i += 64) {
+            const float4 v = a[i];
+            const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+            a[i] = h;
+            al[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+          float4* b = reinterpret_cast<float4*>(sB + (size_t)stage * B_BYTES);
+          float4* bl = reinterpret_cast<float4*>(sBlo + (size_t)stage * B_BYTES);
+          for (int i = tt; i < B_BYTES / 16; i += 64) {
+            const float4 v = b[i];
+            const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+            b[i] = h;
+            bl[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+          mbar_arrive(&split_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
     }
-    if (p.gn_partial) {
-      // GroupNorm statistics of the tensor just produced, accumulated per (image, group): removes the separate
-      // statistics pass over HBM for the GroupNorm that consumes this output (models/layerspp.py:244,277).
-      // Requires all 32 rows of a warp to belong to one image (BW*BH >= 32 or BN == 1) — checked on the host.
-      const bool as_bf16 = p.out_bf16 && !p.out_f32;
-      const int nn = n0 + (warp * 32) / (p.BW * p.BH);
-      float* dst = (nn < p.N) ? p.gn_partial + (long long)nn * p.gn_groups * 2 : nullptr;
-      switch (p.gn_cpg) {
-        case 4: gn_accumulate<4>(f, row_ok, as_bf16, lane, c0, dst); break;
-        case 8: gn_accumulate<8>(f, row_ok, as_bf16, lane, c0, dst); break;
-        case 16: gn_accumulate<16>(f, row_ok, as_bf16, lane, c0, dst); break;
-        default: gn_accumulate<32>(f, row_ok, as_bf16, lane, c0, dst); break;
+  } else {
+    // ================= epilogue warps 2..5
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * 4096);
+    const int chunk = lane & 7, rsub = lane >> 3;  // transposed domain: 4 columns (chunk), rows it*4 + rsub
+    const bool direct = p.out_mode != 0;           // NCHW / transposed outputs are coalesced along pixels: keep row = lane
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
+      const int ncol0 = nt * BLOCK_N;
+      mbar_wait(&tfull_bar[buf], ((uint32_t)j >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ACC_COLS;
+
+      if (direct) {
+        const EpiRow e = epi_row(p, q * 32 + lane, n0, y0, x0);
+        const float scale = p.scale * ((p.rowscale != nullptr && e.ok) ? p.rowscale[e.n] : 1.0f);
+        const long long hw = (long long)p.H * p.W;
+#pragma unroll 1
+        for (int sl = 0; sl < NSLAB; ++sl) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)(sl * 32), v);
+          tmem_ld_wait();
+          if (sl == NSLAB - 1) {
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+          }
+          const int c0 = ncol0 + sl * 32;
+          if (c0 >= p.Cout || !e.ok) continue;
+          const long long li = (long long)e.y * p.W + e.x;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i;
+            if (c >= p.Cout) break;
+            float f = __uint_as_float(v[i]);
+            if (p.bias) f += __ldg(p.bias + c);
+            if (p.rowbias) f += __ldg(p.rowbias + (long long)e.n * p.rowbias_ld + c);
+            f *= scale;
+            if (p.out_mode == 1) {
+              // NCHW fp32 (network head; flow fixed-point update x <- y - g(x), iresblock.py:78-88)
+              const long long o = ((long long)e.n * p.Cout + c) * hw + li;
+              if (p.residual) f += p.res_scale * p.residual[o];
+              f = act_apply(p.act, f);
+              if (p.mul) f *= ((const float*)p.mul)[o];
+              p.out_f32[o] = f;
+            } else {
+              // mode 2: columns >= tcol0 transposed per image (bf16), the rest as NHWC rows
+              if (p.residual) f += p.res_scale * p.residual[e.pix * p.res_ld + c];
+              f = act_apply(p.act, f);
+              if (c >= p.tcol0) {
+                p.out_t[((long long)e.n * (p.Cout - p.tcol0) + (c - p.tcol0)) * hw + li] = __float2bfloat16_rn(f);
+              } else {
+                if (p.out_f32) p.out_f32[e.pix * p.out_ld + c] = f;
+                if (p.out_bf16) p.out_bf16[e.pix * p.out_ld + c] = __float2bfloat16_rn(f);
+              }
+            }
+          }
+        }
+        continue;
+      }
+
+      // ---- NHWC outputs: transposed domain.  This thread handles rows it*4 + rsub (it = 0..7) and columns chunk*4..+3.
+      EpiRow er[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) er[it] = epi_row(p, q * 32 + it * 4 + rsub, n0, y0, x0);
+      float rs[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) rs[it] = p.scale * ((p.rowscale != nullptr && er[it].ok) ? p.rowscale[er[it].n] : 1.0f);
+
+#pragma unroll 1
+      for (int sl = 0; sl < NSLAB; ++sl) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + (uint32_t)(sl * 32), v);
+        tmem_ld_wait();
+        if (sl == NSLAB - 1) {
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);        // all accumulator columns of this buffer are in registers / smem
+        }
+        const int c0 = ncol0 + sl * 32;
+        if (c0 >= p.Cout) continue;             // uniform across the CTA
+        // row-major -> smem (row = lane), XOR swizzle on the 16-byte chunk index
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          stg[lane * 8 + (ch ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * ch]), __uint_as_float(v[4 * ch + 1]),
+                                                          __uint_as_float(v[4 * ch + 2]), __uint_as_float(v[4 * ch + 3]));
+        __syncwarp();
+        const int c = c0 + chunk * 4;           // first of this thread's 4 columns
+        const bool cfull = (c + 4 <= p.Cout);
+        const bool cany = (c < p.Cout);
+        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && cany) {
+          if (cfull) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          else {
+            bia.x = __ldg(p.bias + c);
+            if (c + 1 < p.Cout) bia.y = __ldg(p.bias + c + 1);
+            if (c + 2 < p.Cout) bia.z = __ldg(p.bias + c + 2);
+          }
+        }
+        float gs = 0.f, gq = 0.f;               // GroupNorm partial sums of this thread's 8 rows x 4 columns
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;
+          float4 f = stg[r * 8 + (chunk ^ (r & 7))];
+          const EpiRow& e = er[it];
+          if (!e.ok || !cany) continue;
+          f.x += bia.x; f.y += bia.y; f.z += bia.z; f.w += bia.w;
+          if (p.rowbias) {
+            const float* rb = p.rowbias + (long long)e.n * p.rowbias_ld + c;
+            if (cfull) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rb));
+              f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+            } else {
+              f.x += __ldg(rb);
+              if (c + 1 < p.Cout) f.y += __ldg(rb + 1);
+              if (c + 2 < p.Cout) f.z += __ldg(rb + 2);
+            }
+          }
+          f.x *= rs[it]; f.y *= rs[it]; f.z *= rs[it]; f.w *= rs[it];
+          if (p.residual) {
+            const float* rr = p.residual + e.pix * p.res_ld + c;
+            if (cfull) {
+              const float4 b = *reinterpret_cast<const float4*>(rr);
+              f.x += p.res_scale * b.x; f.y += p.res_scale * b.y; f.z += p.res_scale * b.z; f.w += p.res_scale * b.w;
+            } else {
+              f.x += p.res_scale * rr[0];
+              if (c + 1 < p.Cout) f.y += p.res_scale * rr[1];
+              if (c + 2 < p.Cout) f.z += p.res_scale * rr[2];
+            }
+          }
+          if (p.aux_cos) {
+            // derivative of the Sin activation at the pre-activation value, kept for the VJP chain of the log-det estimators
+            const float4 cc = make_float4(cosf(6.283185307179586f * f.x), cosf(6.283185307179586f * f.y),
+                                          cosf(6.283185307179586f * f.z), cosf(6.283185307179586f * f.w));
+            if (TF32) {
+              float* dst = (float*)p.aux_cos + e.pix * p.out_ld + c;
+              if (cfull) *reinterpret_cast<float4*>(dst) = cc;
+              else { dst[0] = cc.x; if (c + 1 < p.Cout) dst[1] = cc.y; if (c + 2 < p.Cout) dst[2] = cc.z; }
+            } else {
+              __nv_bfloat16* dst = (__nv_bfloat16*)p.aux_cos + e.pix * p.out_ld + c;
+              if (cfull) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(cc.x, cc.y), pack_bf16x2(cc.z, cc.w));
+              else { dst[0] = __float2bfloat16_rn(cc.x); if (c + 1 < p.Cout) dst[1] = __float2bfloat16_rn(cc.y); if (c + 2 < p.Cout) dst[2] = __float2bfloat16_rn(cc.z); }
+            }
+          }
+          if (p.act) { f.x = act_apply(p.act, f.x); f.y = act_apply(p.act, f.y); f.z = act_apply(p.act, f.z); f.w = act_apply(p.act, f.w); }
+          if (p.mul) {
+            if (TF32) {
+              const float* mm = (const float*)p.mul + e.pix * p.mul_ld + c;
+              if (cfull) { const float4 m4 = *reinterpret_cast<const float4*>(mm); f.x *= m4.x; f.y *= m4.y; f.z *= m4.z; f.w *= m4.w; }
+              else { f.x *= mm[0]; if (c + 1 < p.Cout) f.y *= mm[1]; if (c + 2 < p.Cout) f.z *= mm[2]; }
+            } else {
+              const __nv_bfloat16* mm = (const __nv_bfloat16*)p.mul + e.pix * p.mul_ld + c;
+              if (cfull) {
+                const uint2 raw = *reinterpret_cast<const uint2*>(mm);
+                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                f.x *= m01.x; f.y *= m01.y; f.z *= m23.x; f.w *= m23.y;
+              } else {
+                f.x *= __bfloat162float(mm[0]);
+                if (c + 1 < p.Cout) f.y *= __bfloat162float(mm[1]);
+                if (c + 2 < p.Cout) f.z *= __bfloat162float(mm[2]);
+              }
+            }
+          }
+          if (p.out_f32) {
+            float* dst = p.out_f32 + e.pix * p.out_ld + c;
+            if (cfull) *reinterpret_cast<float4*>(dst) = f;
+            else { dst[0] = f.x; if (c + 1 < p.Cout) dst[1] = f.y; if (c + 2 < p.Cout) dst[2] = f.z; }
+          }
+          if (p.out_bf16) {
+            __nv_bfloat16* dst = p.out_bf16 + e.pix * p.out_ld + c;
+            if (cfull) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+            else { dst[0] = __float2bfloat16_rn(f.x); if (c + 1 < p.Cout) dst[1] = __float2bfloat16_rn(f.y); if (c + 2 < p.Cout) dst[2] = __float2bfloat16_rn(f.z); }
+          }
+          if (p.gn_partial) {
+            float4 tq = f;
+            if (p.out_bf16 && !p.out_f32) {   // statistics of the values as stored
+              tq.x = __bfloat162float(__float2bfloat16_rn(f.x)); tq.y = __bfloat162float(__float2bfloat16_rn(f.y));
+              tq.z = __bfloat162float(__float2bfloat16_rn(f.z)); tq.w = __bfloat162float(__float2bfloat16_rn(f.w));
+            }
+            gs += (tq.x + tq.y) + (tq.z + tq.w);
+            gq += (tq.x * tq.x + tq.y * tq.y) + (tq.z * tq.z + tq.w * tq.w);
+          }
+        }
+        if (p.gn_partial) {
+          // GroupNorm statistics of the tensor just produced, per (image, group): removes the separate statistics pass over
+          // HBM for the GroupNorm that consumes this output (models/layerspp.py:244,277).  All 32 rows of a warp belong to
+          // one image (checked on the host); Cout % 32 == 0, so whole slabs only.
+          gs += __shfl_xor_sync(0xffffffffu, gs, 8);  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+          gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+          const int cq = p.gn_cpg >> 2;               // chunks per group: 1, 2, 4 or 8
+          for (int o = 1; o < cq; o <<= 1) {
+            gs += __shfl_xor_sync(0xffffffffu, gs, o);
+            gq += __shfl_xor_sync(0xffffffffu, gq, o);
+          }
+          const int nn = n0 + (q * 32) / (p.BW * p.BH);
+          if (rsub == 0 && (chunk & (cq - 1)) == 0 && nn < p.N) {
+            float* dst = p.gn_partial + ((long long)nn * p.gn_groups + c / p.gn_cpg) * 2;
+            atomicAdd(dst, gs);
+            atomicAdd(dst + 1, gq);
+          }
+        }
+        __syncwarp();   // staging buffer is rewritten by the next slab
       }
     }
   }
@@ -455,27 +496,27 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
   const int stage_bytes = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
-  const int overhead = 1024 + (3 * kMaxStages + 2) * 8;
-  const int iters = p.taps * p.chunks1 + p.chunks2;
-  // aim for >= 2 co-resident CTAs per SM when the tile is small enough; never more stages than K iterations
-  int budget = (BLOCK_N >= 256 || TF32) ? 200 * 1024 : 100 * 1024;
-  int stages = (budget - overhead) / stage_bytes;
+  const int overhead = 1024 + 4 * 4096 + (3 * kMaxStages + 6) * 8;
+  // one persistent CTA per SM: the smem ring takes what the SM has
+  int stages = (220 * 1024 - overhead) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > iters) stages = iters;
-  if (stages < 1) stages = 1;
+  if (stages < 2) stages = 2;
   p.stages = stages;
+  p.n_tiles = n_tiles;
   const int smem = stages * stage_bytes + overhead;
-  static int configured = -1;
+  static bool configured = false;
   auto kern = igemm_kernel<BLOCK_N, TF32>;
-  if (configured < smem) {
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       indm_set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return INDM_ERR_CUDA;
     }
-    configured = 227 * 1024;
+    configured = true;
   }
-  kern<<<dim3(m_tiles, n_tiles), 128, smem, stream>>>(a, b, a2, b2, p);
+  const long long total = (long long)m_tiles * n_tiles;
+  const int grid = (int)(total < indm_num_sms() ? total : indm_num_sms());
+  kern<<<grid, TF32 ? 256 : 192, smem, stream>>>(a, b, a2, b2, p);
   INDM_CHECK_LAUNCH("igemm");
   return INDM_OK;
 }
@@ -526,8 +567,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   if (d->batched_b) p.BN = 1;  // every tile row must belong to the image whose B matrix is loaded
   p.tiles_x = (d->W + p.BW - 1) / p.BW;
   p.tiles_y = d->H / p.BH;
-  const int tiles_n = (d->N + p.BN - 1) / p.BN;
-  const int m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+  p.tiles_n = (d->N + p.BN - 1) / p.BN;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.Cout = d->Cout;
   p.taps = d->taps;
   p.chunks1 = (d->Cin + kchunk - 1) / kchunk;
@@ -587,10 +628,21 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   // pick BLOCK_N
   int block_n = d->block_n;
   if (block_n == 0) {
+    // widest tile that still gives every SM work: the kernel is persistent (one CTA per SM), so launches with few tiles
+    // trade MMA width for parallelism (4x4 / 8x8 feature maps: M = N*16 / N*64 rows only)
+    const int sms = indm_num_sms();
     if (d->Cout <= 32) block_n = 32;
     else if (d->Cout <= 64) block_n = 64;
-    else if (d->Cout % 256 == 0 && (long long)m_tiles * (d->Cout / 256) >= 2LL * indm_num_sms()) block_n = 256;
-    else block_n = 128;
+    else if (d->Cout % 256 == 0 && (long long)m_tiles * (d->Cout / 256) >= 2LL * sms) block_n = 256;
+    else {
+      block_n = 32;
+      for (int bn = 128; bn >= 32; bn >>= 1) {
+        if ((long long)m_tiles * ((d->Cout + bn - 1) / bn) * 4 >= 3LL * sms) {
+          block_n = bn;
+          break;
+        }
+      }
+    }
   }
   INDM_CHECK_ARG(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "igemm: block_n %d unsupported", block_n);
   const int n_tiles = (d->Cout + block_n - 1) / block_n;

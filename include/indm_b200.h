@@ -178,6 +178,15 @@ int indm_gn_bwd_apply(const void* dy, int dy_dtype, const void* xa, int Ca, cons
                       int resample, const float* partial_bwd, const float* extra_post, const float* extra_pre, float extra_scale,
                       void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, void* stream);
 
+/* Convolution / linear weight gradient on the tensor cores (the cuDNN wgrad / cuBLAS calls behind losses.py:250,304):
+ *   dw[o*stride_o + c*stride_c + t*stride_t] += scale * sum_{n,y,x} dy[n,y,x,o] * x[n, y+ky-1, x+kx-1, c]     (taps = 9, t = ky*3+kx)
+ *   dw[o*stride_o + c*stride_c]              += scale * sum_p dy[p,o] * x[p,c]                                   (taps = 1)
+ * dy [N,H,W,Cout] (row stride dy_ld, 0 = Cout) and x [N,H,W,Cin] (x_ld) are NHWC in `dtype` (BF16, or fp32 -> TF32 math);
+ * dw is fp32 and is ACCUMULATED into (atomics; split-K over CTAs), so the caller zeroes it once per step.  The strides let
+ * the result land directly in the parameter's own layout: nn.Conv2d [Cout,Cin,3,3] -> (Cin*9, 9, 1); NIN W[in,out] -> (1, out, 0). */
+int indm_conv_wgrad(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, int dtype, int N, int H, int W, int Cout, int Cin,
+                    int taps, float* dw, int64_t stride_o, int64_t stride_c, int64_t stride_t, float scale, void* stream);
+
 /* out[i] = in[i] * scale, fp32 -> out_dtype (BF16 or fp32), n % 4 == 0: the operand copy of a gradient tensor */
 int indm_cast_scale(const float* in, void* out, int64_t n, float scale, int out_dtype, void* stream);
 

@@ -74,6 +74,8 @@ _SIGS = {
     "indm_gn_bwd_apply": [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32,
                           C.c_int, C.c_int, _vp, _vp, _vp, _f32, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp],
     "indm_cast_scale": [_vp, _vp, _i64, _f32, C.c_int, _vp],
+    "indm_conv_wgrad": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _i64, _i64,
+                        _f32, _vp],
     "indm_softmax_bwd_rows": [_vp, _vp, _vp, _i64, C.c_int, _f32, C.c_int, _vp],
     "indm_transpose_batched": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp],
     "indm_nchw_to_nhwc": [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, C.c_int, _vp],

@@ -282,71 +282,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * 4096);
     const int chunk = lane & 7, rsub = lane >> 3;  // transposed domain: 4 columns (chunk), rows it*4 + rsub
-    const bool direct = p.out_mode != 0;           // NCHW / transposed outputs are coalesced along pixels: keep row = lane
+    const long long hw = (long long)p.H * p.W;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int buf = j & 1;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
       const int ncol0 = nt * BLOCK_N;
+      // row bookkeeping, once per tile.  Direct domain (NCHW / transposed outputs, coalesced along pixels): row = lane.
+      // Transposed domain (NHWC outputs): rows it*4 + rsub, it = 0..7.  Invalid rows load from pixel 0 / image 0 (always
+      // valid addresses) so the loads stay branch-free and can all be in flight together; their stores are predicated off.
+      const EpiRow ed = epi_row(p, q * 32 + lane, n0, y0, x0);
+      long long pixs[8];
+      int nsafe[8];
+      unsigned okmask = 0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const EpiRow e = epi_row(p, q * 32 + it * 4 + rsub, n0, y0, x0);
+        pixs[it] = e.ok ? e.pix : 0;
+        nsafe[it] = e.ok ? e.n : 0;
+        okmask |= (e.ok ? 1u : 0u) << it;
+      }
       mbar_wait(&tfull_bar[buf], ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ACC_COLS;
-
-      if (direct) {
-        const EpiRow e = epi_row(p, q * 32 + lane, n0, y0, x0);
-        const float scale = p.scale * ((p.rowscale != nullptr && e.ok) ? p.rowscale[e.n] : 1.0f);
-        const long long hw = (long long)p.H * p.W;
-#pragma unroll 1
-        for (int sl = 0; sl < NSLAB; ++sl) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + (uint32_t)(sl * 32), v);
-          tmem_ld_wait();
-          if (sl == NSLAB - 1) {
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[buf]);
-          }
-          const int c0 = ncol0 + sl * 32;
-          if (c0 >= p.Cout || !e.ok) continue;
-          const long long li = (long long)e.y * p.W + e.x;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = c0 + i;
-            if (c >= p.Cout) break;
-            float f = __uint_as_float(v[i]);
-            if (p.bias) f += __ldg(p.bias + c);
-            if (p.rowbias) f += __ldg(p.rowbias + (long long)e.n * p.rowbias_ld + c);
-            f *= scale;
-            if (p.out_mode == 1) {
-              // NCHW fp32 (network head; flow fixed-point update x <- y - g(x), iresblock.py:78-88)
-              const long long o = ((long long)e.n * p.Cout + c) * hw + li;
-              if (p.residual) f += p.res_scale * p.residual[o];
-              f = act_apply(p.act, f);
-              if (p.mul) f *= ((const float*)p.mul)[o];
-              p.out_f32[o] = f;
-            } else {
-              // mode 2: columns >= tcol0 transposed per image (bf16), the rest as NHWC rows
-              if (p.residual) f += p.res_scale * p.residual[e.pix * p.res_ld + c];
-              f = act_apply(p.act, f);
-              if (c >= p.tcol0) {
-                p.out_t[((long long)e.n * (p.Cout - p.tcol0) + (c - p.tcol0)) * hw + li] = __float2bfloat16_rn(f);
-              } else {
-                if (p.out_f32) p.out_f32[e.pix * p.out_ld + c] = f;
-                if (p.out_bf16) p.out_bf16[e.pix * p.out_ld + c] = __float2bfloat16_rn(f);
-              }
-            }
-          }
-        }
-        continue;
-      }
-
-      // ---- NHWC outputs: transposed domain.  This thread handles rows it*4 + rsub (it = 0..7) and columns chunk*4..+3.
-      EpiRow er[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) er[it] = epi_row(p, q * 32 + it * 4 + rsub, n0, y0, x0);
-      float rs[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) rs[it] = p.scale * ((p.rowscale != nullptr && er[it].ok) ? p.rowscale[er[it].n] : 1.0f);
 
 #pragma unroll 1
       for (int sl = 0; sl < NSLAB; ++sl) {
@@ -355,111 +314,152 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_wait();
         if (sl == NSLAB - 1) {
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);        // all accumulator columns of this buffer are in registers / smem
+          mbar_arrive(&tempty_bar[buf]);        // every accumulator column of this buffer has left TMEM
         }
         const int c0 = ncol0 + sl * 32;
         if (c0 >= p.Cout) continue;             // uniform across the CTA
-        // row-major -> smem (row = lane), XOR swizzle on the 16-byte chunk index
+        const bool direct = (p.out_mode == 1) || (p.out_mode == 2 && c0 >= p.tcol0);
+        if (direct) {
+          if (!ed.ok) continue;
+          const float scale = p.scale * (p.rowscale != nullptr ? p.rowscale[ed.n] : 1.0f);
+          const long long li = (long long)ed.y * p.W + ed.x;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i;
+            if (c >= p.Cout) break;
+            float f = __uint_as_float(v[i]);
+            if (p.bias) f += __ldg(p.bias + c);
+            if (p.rowbias) f += __ldg(p.rowbias + (long long)ed.n * p.rowbias_ld + c);
+            f *= scale;
+            if (p.out_mode == 1) {
+              // NCHW fp32 (network head; flow fixed-point update x <- y - g(x), iresblock.py:78-88)
+              const long long o = ((long long)ed.n * p.Cout + c) * hw + li;
+              if (p.residual) f += p.res_scale * p.residual[o];
+              f = act_apply(p.act, f);
+              if (p.mul) f *= ((const float*)p.mul)[o];
+              p.out_f32[o] = f;
+            } else {
+              // mode 2, columns >= tcol0: transposed per image (bf16)
+              f = act_apply(p.act, f);
+              p.out_t[((long long)ed.n * (p.Cout - p.tcol0) + (c - p.tcol0)) * hw + li] = __float2bfloat16_rn(f);
+            }
+          }
+          continue;
+        }
+
+        // ---- NHWC outputs.  row-major -> smem (row = lane), XOR swizzle on the 16-byte chunk index
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
           stg[lane * 8 + (ch ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * ch]), __uint_as_float(v[4 * ch + 1]),
                                                           __uint_as_float(v[4 * ch + 2]), __uint_as_float(v[4 * ch + 3]));
         __syncwarp();
         const int c = c0 + chunk * 4;           // first of this thread's 4 columns
-        const bool cfull = (c + 4 <= p.Cout);
-        const bool cany = (c < p.Cout);
-        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && cany) {
-          if (cfull) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-          else {
-            bia.x = __ldg(p.bias + c);
-            if (c + 1 < p.Cout) bia.y = __ldg(p.bias + c + 1);
-            if (c + 2 < p.Cout) bia.z = __ldg(p.bias + c + 2);
-          }
-        }
         float gs = 0.f, gq = 0.f;               // GroupNorm partial sums of this thread's 8 rows x 4 columns
+        if (c + 4 <= p.Cout) {
+          // ---- fast path: whole 4-column chunk valid.  Phase 1: every load of the 8 rows issued back to back.
+          float4 f[8], rb[8], rsd[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rsub;
-          float4 f = stg[r * 8 + (chunk ^ (r & 7))];
-          const EpiRow& e = er[it];
-          if (!e.ok || !cany) continue;
-          f.x += bia.x; f.y += bia.y; f.z += bia.z; f.w += bia.w;
-          if (p.rowbias) {
-            const float* rb = p.rowbias + (long long)e.n * p.rowbias_ld + c;
-            if (cfull) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(rb));
-              f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
-            } else {
-              f.x += __ldg(rb);
-              if (c + 1 < p.Cout) f.y += __ldg(rb + 1);
-              if (c + 2 < p.Cout) f.z += __ldg(rb + 2);
-            }
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            f[it] = stg[r * 8 + (chunk ^ (r & 7))];
           }
-          f.x *= rs[it]; f.y *= rs[it]; f.z *= rs[it]; f.w *= rs[it];
+          if (p.rowbias) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rb[it] = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)nsafe[it] * p.rowbias_ld + c));
+          }
           if (p.residual) {
-            const float* rr = p.residual + e.pix * p.res_ld + c;
-            if (cfull) {
-              const float4 b = *reinterpret_cast<const float4*>(rr);
-              f.x += p.res_scale * b.x; f.y += p.res_scale * b.y; f.z += p.res_scale * b.z; f.w += p.res_scale * b.w;
-            } else {
-              f.x += p.res_scale * rr[0];
-              if (c + 1 < p.Cout) f.y += p.res_scale * rr[1];
-              if (c + 2 < p.Cout) f.z += p.res_scale * rr[2];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rsd[it] = *reinterpret_cast<const float4*>(p.residual + pixs[it] * p.res_ld + c);
+          }
+          float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          // Phase 2: math
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float4 x = f[it];
+            x.x += bia.x; x.y += bia.y; x.z += bia.z; x.w += bia.w;
+            if (p.rowbias) { x.x += rb[it].x; x.y += rb[it].y; x.z += rb[it].z; x.w += rb[it].w; }
+            const float sc = p.scale * (p.rowscale != nullptr ? p.rowscale[nsafe[it]] : 1.0f);
+            x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+            if (p.residual) {
+              x.x += p.res_scale * rsd[it].x; x.y += p.res_scale * rsd[it].y; x.z += p.res_scale * rsd[it].z; x.w += p.res_scale * rsd[it].w;
             }
+            f[it] = x;
           }
           if (p.aux_cos) {
             // derivative of the Sin activation at the pre-activation value, kept for the VJP chain of the log-det estimators
-            const float4 cc = make_float4(cosf(6.283185307179586f * f.x), cosf(6.283185307179586f * f.y),
-                                          cosf(6.283185307179586f * f.z), cosf(6.283185307179586f * f.w));
-            if (TF32) {
-              float* dst = (float*)p.aux_cos + e.pix * p.out_ld + c;
-              if (cfull) *reinterpret_cast<float4*>(dst) = cc;
-              else { dst[0] = cc.x; if (c + 1 < p.Cout) dst[1] = cc.y; if (c + 2 < p.Cout) dst[2] = cc.z; }
-            } else {
-              __nv_bfloat16* dst = (__nv_bfloat16*)p.aux_cos + e.pix * p.out_ld + c;
-              if (cfull) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(cc.x, cc.y), pack_bf16x2(cc.z, cc.w));
-              else { dst[0] = __float2bfloat16_rn(cc.x); if (c + 1 < p.Cout) dst[1] = __float2bfloat16_rn(cc.y); if (c + 2 < p.Cout) dst[2] = __float2bfloat16_rn(cc.z); }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if (!((okmask >> it) & 1u)) continue;
+              const float4 cc = make_float4(cosf(6.283185307179586f * f[it].x), cosf(6.283185307179586f * f[it].y),
+                                            cosf(6.283185307179586f * f[it].z), cosf(6.283185307179586f * f[it].w));
+              if (TF32) *reinterpret_cast<float4*>((float*)p.aux_cos + pixs[it] * p.out_ld + c) = cc;
+              else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.aux_cos + pixs[it] * p.out_ld + c) = make_uint2(pack_bf16x2(cc.x, cc.y), pack_bf16x2(cc.z, cc.w));
             }
           }
-          if (p.act) { f.x = act_apply(p.act, f.x); f.y = act_apply(p.act, f.y); f.z = act_apply(p.act, f.z); f.w = act_apply(p.act, f.w); }
+          if (p.act) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              f[it].x = act_apply(p.act, f[it].x); f[it].y = act_apply(p.act, f[it].y);
+              f[it].z = act_apply(p.act, f[it].z); f[it].w = act_apply(p.act, f[it].w);
+            }
+          }
           if (p.mul) {
-            if (TF32) {
-              const float* mm = (const float*)p.mul + e.pix * p.mul_ld + c;
-              if (cfull) { const float4 m4 = *reinterpret_cast<const float4*>(mm); f.x *= m4.x; f.y *= m4.y; f.z *= m4.z; f.w *= m4.w; }
-              else { f.x *= mm[0]; if (c + 1 < p.Cout) f.y *= mm[1]; if (c + 2 < p.Cout) f.z *= mm[2]; }
-            } else {
-              const __nv_bfloat16* mm = (const __nv_bfloat16*)p.mul + e.pix * p.mul_ld + c;
-              if (cfull) {
-                const uint2 raw = *reinterpret_cast<const uint2*>(mm);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float4 m4;
+              if (TF32) m4 = *reinterpret_cast<const float4*>((const float*)p.mul + pixs[it] * p.mul_ld + c);
+              else {
+                const uint2 raw = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)p.mul + pixs[it] * p.mul_ld + c);
                 const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
                 const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-                f.x *= m01.x; f.y *= m01.y; f.z *= m23.x; f.w *= m23.y;
-              } else {
-                f.x *= __bfloat162float(mm[0]);
-                if (c + 1 < p.Cout) f.y *= __bfloat162float(mm[1]);
-                if (c + 2 < p.Cout) f.z *= __bfloat162float(mm[2]);
+                m4 = make_float4(m01.x, m01.y, m23.x, m23.y);
               }
+              f[it].x *= m4.x; f[it].y *= m4.y; f[it].z *= m4.z; f[it].w *= m4.w;
             }
           }
-          if (p.out_f32) {
-            float* dst = p.out_f32 + e.pix * p.out_ld + c;
-            if (cfull) *reinterpret_cast<float4*>(dst) = f;
-            else { dst[0] = f.x; if (c + 1 < p.Cout) dst[1] = f.y; if (c + 2 < p.Cout) dst[2] = f.z; }
-          }
-          if (p.out_bf16) {
-            __nv_bfloat16* dst = p.out_bf16 + e.pix * p.out_ld + c;
-            if (cfull) *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
-            else { dst[0] = __float2bfloat16_rn(f.x); if (c + 1 < p.Cout) dst[1] = __float2bfloat16_rn(f.y); if (c + 2 < p.Cout) dst[2] = __float2bfloat16_rn(f.z); }
-          }
-          if (p.gn_partial) {
-            float4 tq = f;
-            if (p.out_bf16 && !p.out_f32) {   // statistics of the values as stored
-              tq.x = __bfloat162float(__float2bfloat16_rn(f.x)); tq.y = __bfloat162float(__float2bfloat16_rn(f.y));
-              tq.z = __bfloat162float(__float2bfloat16_rn(f.z)); tq.w = __bfloat162float(__float2bfloat16_rn(f.w));
+          // Phase 3: stores (predicated on row validity) — 8 lanes cover one 128-byte (fp32) / 64-byte (bf16) run of a row
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (!((okmask >> it) & 1u)) continue;
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + pixs[it] * p.out_ld + c) = f[it];
+            if (p.out_bf16)
+              *reinterpret_cast<uint2*>(p.out_bf16 + pixs[it] * p.out_ld + c) = make_uint2(pack_bf16x2(f[it].x, f[it].y), pack_bf16x2(f[it].z, f[it].w));
+            if (p.gn_partial) {
+              float4 tq = f[it];
+              if (p.out_bf16 && !p.out_f32) {   // statistics of the values as stored
+                tq.x = __bfloat162float(__float2bfloat16_rn(tq.x)); tq.y = __bfloat162float(__float2bfloat16_rn(tq.y));
+                tq.z = __bfloat162float(__float2bfloat16_rn(tq.z)); tq.w = __bfloat162float(__float2bfloat16_rn(tq.w));
+              }
+              gs += (tq.x + tq.y) + (tq.z + tq.w);
+              gq += (tq.x * tq.x + tq.y * tq.y) + (tq.z * tq.z + tq.w * tq.w);
             }
-            gs += (tq.x + tq.y) + (tq.z + tq.w);
-            gq += (tq.x * tq.x + tq.y * tq.y) + (tq.z * tq.z + tq.w * tq.w);
+          }
+        } else if (c < p.Cout) {
+          // ---- ragged last chunk (Cout % 4 != 0): scalar, guarded
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            if (!((okmask >> it) & 1u)) continue;
+            const int r = it * 4 + rsub;
+            const float4 f4 = stg[r * 8 + (chunk ^ (r & 7))];
+            const float sc = p.scale * (p.rowscale != nullptr ? p.rowscale[nsafe[it]] : 1.0f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {       // a ragged chunk has 1..3 valid columns
+              if (c + k >= p.Cout) break;
+              float x = k == 0 ? f4.x : (k == 1 ? f4.y : f4.z);
+              if (p.bias) x += __ldg(p.bias + c + k);
+              if (p.rowbias) x += __ldg(p.rowbias + (long long)nsafe[it] * p.rowbias_ld + c + k);
+              x *= sc;
+              if (p.residual) x += p.res_scale * p.residual[pixs[it] * p.res_ld + c + k];
+              if (p.aux_cos) {
+                if (TF32) ((float*)p.aux_cos)[pixs[it] * p.out_ld + c + k] = cosf(6.283185307179586f * x);
+                else ((__nv_bfloat16*)p.aux_cos)[pixs[it] * p.out_ld + c + k] = __float2bfloat16_rn(cosf(6.283185307179586f * x));
+              }
+              x = act_apply(p.act, x);
+              if (p.mul) x *= TF32 ? ((const float*)p.mul)[pixs[it] * p.mul_ld + c + k] : __bfloat162float(((const __nv_bfloat16*)p.mul)[pixs[it] * p.mul_ld + c + k]);
+              if (p.out_f32) p.out_f32[pixs[it] * p.out_ld + c + k] = x;
+              if (p.out_bf16) p.out_bf16[pixs[it] * p.out_ld + c + k] = __float2bfloat16_rn(x);
+            }
           }
         }
         if (p.gn_partial) {

@@ -193,8 +193,10 @@ int indm_cast_scale(const float* in, void* out, int64_t n, float scale, int out_
 /* ds[i][j] = p[i][j] * (dp[i][j] - sum_k p[i][k] dp[i][k]) * scale; p, ds in dtype (BF16 / fp32), dp fp32 */
 int indm_softmax_bwd_rows(const float* dp, const void* p, void* ds, int64_t rows, int cols, float scale, int dtype, void* stream);
 
-/* out[b][c][r] = in[b][r][c]  (BF16 or fp32 elements) */
-int indm_transpose_batched(const void* in, void* out, int64_t B, int R, int C, int dtype, void* stream);
+/* out[b][c][r] = in[b*in_batch_stride + r*in_ld + c]  (BF16 or fp32 elements; in_ld = 0 -> C, in_batch_stride = 0 -> R*in_ld;
+ * out is dense [B][C][R]) */
+int indm_transpose_batched(const void* in, void* out, int64_t B, int R, int C, int64_t in_ld, int64_t in_batch_stride, int dtype,
+                           void* stream);
 
 /* out NHWC [N,H,W,cpad] (channels >= C zero) = x NCHW fp32 [N,C,H,W] * mul * rowscale[n] (rowscale may be NULL) */
 int indm_nchw_to_nhwc(const float* x, const float* rowscale, void* out, int64_t N, int C, int H, int W, int cpad, float mul,

@@ -77,7 +77,7 @@ _SIGS = {
     "indm_conv_wgrad": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _i64, _i64,
                         _f32, _vp],
     "indm_softmax_bwd_rows": [_vp, _vp, _vp, _i64, C.c_int, _f32, C.c_int, _vp],
-    "indm_transpose_batched": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_transpose_batched": [_vp, _vp, _i64, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp],
     "indm_nchw_to_nhwc": [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, C.c_int, _vp],
     "indm_rowdot_f32": [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp],
 }

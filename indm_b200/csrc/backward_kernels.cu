@@ -200,15 +200,15 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dp, const TP* __res
 
 // ---------------------------------------------------------------- batched 2-D transpose  in [B][R][C] -> out [B][C][R]
 template <typename T>
-__global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int C) {
+__global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int C, long long in_ld, long long in_bs) {
   __shared__ T tile[32][33];
   const long long b = blockIdx.z;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const T* src = in + b * (long long)R * C;
+  const T* src = in + b * in_bs;
   T* dst = out + b * (long long)R * C;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < R && c < C) tile[j][threadIdx.x] = src[(long long)r * C + c];
+    if (r < R && c < C) tile[j][threadIdx.x] = src[(long long)r * in_ld + c];
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -316,12 +316,16 @@ extern "C" int indm_softmax_bwd_rows(const float* dp, const void* p, void* ds, i
   return INDM_OK;
 }
 
-extern "C" int indm_transpose_batched(const void* in, void* out, int64_t B, int R, int C, int dtype, void* stream_) {
+extern "C" int indm_transpose_batched(const void* in, void* out, int64_t B, int R, int C, int64_t in_ld, int64_t in_batch_stride,
+                                      int dtype, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(in && out && B > 0 && R > 0 && C > 0 && B <= 65535, "transpose_batched: bad arguments");
+  if (in_ld == 0) in_ld = C;
+  if (in_batch_stride == 0) in_batch_stride = (int64_t)R * in_ld;
   dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)B), block(32, 8);
-  if (dtype == INDM_DTYPE_BF16) transpose_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C);
-  else transpose_kernel<float><<<grid, block, 0, stream>>>((const float*)in, (float*)out, R, C);
+  if (dtype == INDM_DTYPE_BF16)
+    transpose_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_ld, in_batch_stride);
+  else transpose_kernel<float><<<grid, block, 0, stream>>>((const float*)in, (float*)out, R, C, in_ld, in_batch_stride);
   INDM_CHECK_LAUNCH("transpose_batched");
   return INDM_OK;
 }

@@ -633,7 +633,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     const int sms = indm_num_sms();
     if (d->Cout <= 32) block_n = 32;
     else if (d->Cout <= 64) block_n = 64;
-    else if (d->Cout % 256 == 0 && (long long)m_tiles * (d->Cout / 256) >= 2LL * sms) block_n = 256;
+    // operand traffic, not the tensor pipe, bounds a 128 x 128 tile (64 FLOP per byte fetched from L2): prefer 128 x 256
+    else if (d->Cout % 256 == 0 && (long long)m_tiles * (d->Cout / 256) * 2 >= sms) block_n = 256;
     else {
       block_n = 32;
       for (int bn = 128; bn >= 32; bn >>= 1) {

@@ -312,25 +312,17 @@ class ScoreEngine:
                 wqkv.copy_(self._round_op(torch.cat(ws, dim=0)))
                 bqkv.copy_(torch.cat([getattr(ab, f'NIN_{j}').b.detach().to(self.dev, torch.float32) for j in range(3)]))
             self.pack_jobs.append(job)
-            qk = self._op_t((N, Lq, 2 * C))
-            vt = self._alloc((N, C, Lq), torch.bfloat16) if self.mode == 'bf16' else None
-            if self.mode == 'bf16':
-                self._igemm(a=h, N=N, H=H, W=W, Cin=C, b=wqkv, Cout=3 * C, taps=1, bias=bqkv, out_mode=2, out_bf16=qk,
-                            out_ld=2 * C, tcol0=2 * C, out_t=vt)
-            else:
-                # tf32 validation mode: q,k,v rows in fp32, V transposed by a strided copy (torch plumbing, not timed)
-                qkv = self._alloc((N, Lq, 3 * C))
-                self._igemm(a=h, N=N, H=H, W=W, Cin=C, b=wqkv, Cout=3 * C, taps=1, bias=bqkv, out_f32=qkv, out_ld=3 * C,
-                            round_tf32_out=1)
-                vt = self._alloc((N, C, Lq))
-
-                def tr(qkv=qkv, vt=vt, qk=qk, C=C):
-                    qk.copy_(qkv[:, :, :2 * C])
-                    vt.copy_(qkv[:, :, 2 * C:].transpose(1, 2))
-                self.ops.append(tr)
+            # q | k | v rows in one GEMM (N = 3C); V^T (the K-major B operand of P.V) by a batched transpose of the v columns
+            qkv = self._op_t((N, Lq, 3 * C))
+            self._igemm(a=h, N=N, H=H, W=W, Cin=C, b=wqkv, Cout=3 * C, taps=1, bias=bqkv, **self._okw(qkv, 3 * C))
+            qk = qkv                                    # q at columns [0, C), k at [C, 2C): row stride 3C
+            vt = self._op_t((N, C, Lq))
+            op_dt_ = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+            self._call('indm_transpose_batched', qkv[:, :, 2 * C:], vt, ctypes.c_int64(N), Lq, C, ctypes.c_int64(3 * C),
+                       ctypes.c_int64(Lq * 3 * C), op_dt_)
             s = self._alloc((N, Lq, Lq))
-            self._igemm(a=qk, a_ld=2 * C, a_img_stride=Lq * 2 * C, N=N, H=1, W=Lq, Cin=C, b=qk[:, :, C:], b_ld=2 * C,
-                        b_tap_stride=Lq * 2 * C, Cout=Lq, taps=1, batched_b=1, scale=float(int(C) ** (-0.5)), out_f32=s, out_ld=Lq)
+            self._igemm(a=qk, a_ld=3 * C, a_img_stride=Lq * 3 * C, N=N, H=1, W=Lq, Cin=C, b=qk[:, :, C:], b_ld=3 * C,
+                        b_tap_stride=Lq * 3 * C, Cout=Lq, taps=1, batched_b=1, scale=float(int(C) ** (-0.5)), out_f32=s, out_ld=Lq)
             p = self._op_t((N, Lq, Lq))
             self._call('indm_softmax_rows', s, p, ctypes.c_int64(N * Lq), Lq, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
             o = self._op_t((N, Lq, C))
@@ -351,7 +343,7 @@ class ScoreEngine:
             self._igemm(a=o, N=N, H=H, W=W, Cin=C, b=w3, Cout=C, taps=1, bias=b3, residual=x, res_ld=C,
                         scale=inv_sqrt2 if ab.skip_rescale else 1.0, res_scale=inv_sqrt2 if ab.skip_rescale else 1.0,
                         out_f32=out, out_ld=C)
-            self.tape.append(('attn', dict(ab=ab, gn=gna, x=x, C=C, H=H, W=W, qk=qk, vt=vt, p=p, out=out,
+            self.tape.append(('attn', dict(ab=ab, gn=gna, x=x, C=C, H=H, W=W, qkv=qkv, p=p, out=out,
                                            s=inv_sqrt2 if ab.skip_rescale else 1.0)))
             return out
 
@@ -558,29 +550,30 @@ class ScoreEngine:
             job3()
         d_o = self._op_t((N, Lq, C))
         self._igemm(a=g, N=N, H=H, W=W, Cin=C, b=w3d, Cout=C, taps=1, **self._okw(d_o, C))
-        # row-major V and transposed Q, K from what the forward kept
-        v_rows = self._op_t((N, Lq, C))
-        self._call('indm_transpose_batched', r['vt'], v_rows, ctypes.c_int64(N), C, Lq, op_dt)
-        qkT = self._op_t((N, 2 * C, Lq))
-        self._call('indm_transpose_batched', r['qk'], qkT, ctypes.c_int64(N), Lq, 2 * C, op_dt)
+        # row-major V from the forward; transposed Q, K (and V, unused) from the fused q|k|v rows
+        qkv = r['qkv']
+        qkvT = self._op_t((N, 3 * C, Lq))
+        self._call('indm_transpose_batched', qkv, qkvT, ctypes.c_int64(N), Lq, 3 * C, ctypes.c_int64(0), ctypes.c_int64(0), op_dt)
+        qkT = qkvT[:, :2 * C, :]
         d_p = self._alloc((N, Lq, Lq))
-        self._igemm(a=d_o, N=N, H=1, W=Lq, Cin=C, b=v_rows, b_tap_stride=Lq * C, Cout=Lq, taps=1, batched_b=1, out_f32=d_p, out_ld=Lq)
+        self._igemm(a=d_o, N=N, H=1, W=Lq, Cin=C, b=qkv[:, :, 2 * C:], b_ld=3 * C, b_tap_stride=Lq * 3 * C, Cout=Lq, taps=1, batched_b=1,
+                    out_f32=d_p, out_ld=Lq)
         d_s = self._op_t((N, Lq, Lq))
         self._call('indm_softmax_bwd_rows', d_p, r['p'], d_s, ctypes.c_int64(N * Lq), Lq, ctypes.c_float(float(int(C) ** (-0.5))), op_dt)
         d_qkv = self._op_t((N, Lq, 3 * C))
         # dQ = dS K
-        self._igemm(a=d_s, N=N, H=1, W=Lq, Cin=Lq, b=qkT[:, C:, :], b_ld=Lq, b_tap_stride=2 * C * Lq, Cout=C, taps=1, batched_b=1,
+        self._igemm(a=d_s, N=N, H=1, W=Lq, Cin=Lq, b=qkT[:, C:, :], b_ld=Lq, b_tap_stride=3 * C * Lq, Cout=C, taps=1, batched_b=1,
                     **self._okw(d_qkv, 3 * C))
         # dK = dS^T Q
         d_sT = self._op_t((N, Lq, Lq))
-        self._call('indm_transpose_batched', d_s, d_sT, ctypes.c_int64(N), Lq, Lq, op_dt)
-        self._igemm(a=d_sT, N=N, H=1, W=Lq, Cin=Lq, b=qkT, b_ld=Lq, b_tap_stride=2 * C * Lq, Cout=C, taps=1, batched_b=1,
+        self._call('indm_transpose_batched', d_s, d_sT, ctypes.c_int64(N), Lq, Lq, ctypes.c_int64(0), ctypes.c_int64(0), op_dt)
+        self._igemm(a=d_sT, N=N, H=1, W=Lq, Cin=Lq, b=qkT, b_ld=Lq, b_tap_stride=3 * C * Lq, Cout=C, taps=1, batched_b=1,
                     **self._okw(d_qkv[:, :, C:], 3 * C))
         # dV = P^T dO
         pT = self._op_t((N, Lq, Lq))
-        self._call('indm_transpose_batched', r['p'], pT, ctypes.c_int64(N), Lq, Lq, op_dt)
+        self._call('indm_transpose_batched', r['p'], pT, ctypes.c_int64(N), Lq, Lq, ctypes.c_int64(0), ctypes.c_int64(0), op_dt)
         d_oT = self._op_t((N, C, Lq))
-        self._call('indm_transpose_batched', d_o, d_oT, ctypes.c_int64(N), Lq, C, op_dt)
+        self._call('indm_transpose_batched', d_o, d_oT, ctypes.c_int64(N), Lq, C, ctypes.c_int64(0), ctypes.c_int64(0), op_dt)
         self._igemm(a=pT, N=N, H=1, W=Lq, Cin=Lq, b=d_oT, b_ld=Lq, b_tap_stride=C * Lq, Cout=C, taps=1, batched_b=1,
                     **self._okw(d_qkv[:, :, 2 * C:], 3 * C))
         # back through the fused q/k/v projection

@@ -400,3 +400,29 @@ def test_bias_act_c_abi_against_reference_golden(case):
     L.call('indm_bias_act_f32', P(gy), None, L.ptr(y), L.ptr(gx), x.size, 1, 1, 3, 1, 0.2, 2 ** 0.5)
     torch.cuda.synchronize()
     assert rel_l2(gx.cpu(), torch.from_numpy(want_gx)) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ['bf16', 'tf32'])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 256, 9), (8, 4, 4, 256, 128, 9), (2, 32, 32, 64, 192, 9), (2, 16, 16, 128, 320, 1),
+                                   (1, 1, 256, 256, 64, 1)])
+def test_conv_wgrad_matches_autograd(shape, mode):
+    """indm_conv_wgrad (tcgen05 with MN-major operands read straight from the NHWC forward boxes) against the weight gradient
+    autograd computes for F.conv2d (3x3 pad 1) / a 1x1 product, accumulated on top of a non-zero initial gradient."""
+    N, H, W, Cout, Cin, taps = shape
+    dt = L.DTYPE_BF16 if mode == 'bf16' else L.DTYPE_TF32
+    rd = bf16r if mode == 'bf16' else tf32r
+    x = rd(rnd(N, H, W, Cin, seed=1))
+    dy = rd(rnd(N, H, W, Cout, seed=2))
+    k = 3 if taps == 9 else 1
+    w = torch.zeros(Cout, Cin, k, k, requires_grad=True)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=k // 2)
+    want, = torch.autograd.grad(y, w, dy.permute(0, 3, 1, 2).double())
+    init = rnd(Cout, Cin, k, k, seed=3)
+    dw = D(init.clone())
+    tdt = torch.bfloat16 if mode == 'bf16' else torch.float32
+    L.call('indm_conv_wgrad', P(dy.to(tdt)), 0, P(x.to(tdt)), 0, dt, N, H, W, Cout, Cin, taps, L.ptr(dw), Cin * taps, taps, 1, 0.5)
+    torch.cuda.synchronize()
+    got = (dw.cpu() - init) / 0.5
+    e = rel_l2(got, want.float())
+    print(f'wgrad {shape} {mode}: rel-L2 {e:.3e}')
+    assert e < (2e-3 if mode == 'tf32' else 1e-4)

@@ -127,6 +127,14 @@ int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, 
                   const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
                   void* out, void* raw, int out_dtype, void* stream);
 
+/* indm_gn_apply (no resampling, no raw copy) followed by training-mode dropout of the activated result
+ * (nn.Dropout(p) in ResnetBlockBigGANpp, models/layerspp.py:278): kept elements are scaled by 1/(1-p).  The mask is the Philox
+ * stream (seed = drop_ctl[0], drop_stream, element quad); drop_ctl is a DEVICE buffer {seed, enabled}: enabled = 0 makes the
+ * call identical to indm_gn_apply, so one launch plan serves eval and train.  The backward kernels recompute the mask. */
+int indm_gn_apply_dropout(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                          const float* partial, const float* gamma, const float* beta, float eps, int act_silu, void* out,
+                          int out_dtype, float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream, void* stream);
+
 /* Row softmax of fp32 scores s[rows][cols] -> probabilities in out_dtype (models/layerspp.py:96-97). */
 int indm_softmax_rows(const float* s, void* out, int64_t rows, int cols, int out_dtype, void* stream);
 
@@ -169,19 +177,22 @@ int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N
  *        written to dxa [N,H,W,Ca] / dxb [N,H,W,Cb] in out_dtype (F32: optionally accumulated; BF16: overwritten).
  * dy: [N,H',W',C] in dy_dtype; extra_post: optional fp32 [N,H',W',C] (gradient w.r.t. the raw resampled input that feeds the
  * skip 1x1 conv); extra_pre: optional fp32 [N,H,W,C] (identity skip).  Supported (dy, x, out) dtypes: (BF16,F32,F32),
- * (BF16,BF16,BF16), (F32,F32,F32). */
+ * (BF16,BF16,BF16), (F32,F32,F32).  drop_p / drop_ctl / drop_stream: the dropout of indm_gn_apply_dropout (drop_ctl NULL = none). */
 int indm_gn_bwd_stats(const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N, int H,
                       int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps, int act_silu,
-                      int resample, float* partial_bwd, float* dgamma, float* dbeta, int out_dtype, void* stream);
+                      int resample, float* partial_bwd, float* dgamma, float* dbeta, int out_dtype, float drop_p,
+                      const uint64_t* drop_ctl, uint32_t drop_stream, void* stream);
 int indm_gn_bwd_apply(const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N, int H,
                       int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps, int act_silu,
                       int resample, const float* partial_bwd, const float* extra_post, const float* extra_pre, float extra_scale,
-                      void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, void* stream);
+                      void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, float drop_p, const uint64_t* drop_ctl,
+                      uint32_t drop_stream, void* stream);
 
 /* Convolution / linear weight gradient on the tensor cores (the cuDNN wgrad / cuBLAS calls behind losses.py:250,304):
  *   dw[o*stride_o + c*stride_c + t*stride_t] += scale * sum_{n,y,x} dy[n,y,x,o] * x[n, y+ky-1, x+kx-1, c]     (taps = 9, t = ky*3+kx)
  *   dw[o*stride_o + c*stride_c]              += scale * sum_p dy[p,o] * x[p,c]                                   (taps = 1)
- * dy [N,H,W,Cout] (row stride dy_ld, 0 = Cout) and x [N,H,W,Cin] (x_ld) are NHWC in `dtype` (BF16, or fp32 -> TF32 math);
+ * dy [N,H,W,Cout] (row stride dy_ld, 0 = Cout) and x [N,H,W,Cin] (x_ld) are NHWC in `dtype` (BF16 -> tensor cores; fp32 ->
+ * exact fp32 validation path on the CUDA cores);
  * dw is fp32 and is ACCUMULATED into (atomics; split-K over CTAs), so the caller zeroes it once per step.  The strides let
  * the result land directly in the parameter's own layout: nn.Conv2d [Cout,Cin,3,3] -> (Cin*9, 9, 1); NIN W[in,out] -> (1, out, 0). */
 int indm_conv_wgrad(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, int dtype, int N, int H, int W, int Cout, int Cin,
@@ -204,6 +215,43 @@ int indm_nchw_to_nhwc(const float* x, const float* rowscale, void* out, int64_t 
 
 /* out[n] (+)= scale * sum_i a[n][i] * b[n][i], fp32 (the eps^T (J eps) contraction of likelihood.py:36-37) */
 int indm_rowdot_f32(const float* a, const float* b, float* out, int64_t N, int64_t D, float scale, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step pieces (losses.py:48-62 optimize_fn, :99-118 loss, models/ema.py:32-51)
+ * ---------------------------------------------------------------- */
+
+/* Column sums of an NHWC tensor x [N,P,C] (row stride x_ld, 0 = C) in `dtype` (BF16 / fp32):
+ * out_img[n*out_ld + c] += scale * sum_p x[n,p,c] (per-image: gradient of the time-embedding row bias, models/layerspp.py:276)
+ * and / or out_tot[c] += scale * sum_{n,p} x[n,p,c] (bias gradients).  Either output may be NULL.  Accumulates (atomics). */
+int indm_colsum(const void* x, int dtype, int64_t N, int64_t P, int C, int64_t x_ld, float* out_img, int64_t out_ld, float* out_tot,
+                float scale, void* stream);
+
+/* C = alpha * op(A) op(B) + beta * C, fp32 row-major, op = transpose if trans_* (small matrices of the time-embedding MLP
+ * and Dense_0 layers: nn.Linear forward / backward, models/ncsnpp.py:270-274) */
+int indm_sgemm_f32(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
+                   float beta, float* C, int64_t ldc, void* stream);
+
+/* dx = dy * SiLU'(pre) */
+int indm_silu_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, void* stream);
+
+/* out[n] = a[n] * x[n] + b[n] * z[n] over D elements per sample: x_t = mean + std z (losses.py:104-105) */
+int indm_perturb_f32(const float* x, const float* z, const float* a, const float* b, float* out, int64_t N, int64_t D, void* stream);
+
+/* Denoising score matching (losses.py:108-118): r = score*std[n] + z; loss[n] = 0.5 * w[n] * norm * sum(r^2);
+ * dscore (optional) = gscale * w[n] * norm * std[n] * r = gscale * d loss[n] / d score.  w may be NULL (= 1). */
+int indm_dsm_loss_f32(const float* score, const float* z, const float* std_, const float* w, float* loss, float* dscore, int64_t N,
+                      int64_t D, float norm, float gscale, void* stream);
+
+/* out[0] += sum x^2 (global gradient norm for clip_grad_norm_, losses.py:58-59; caller zeroes out) */
+int indm_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
+
+/* One pass over flat parameter storage: g *= min(1, max_norm / (sqrt(*grad_sumsq) + 1e-6)) (skipped when grad_sumsq == NULL or
+ * max_norm < 0), torch.optim.AdamW update with bias correction for `step` (1-based), then, if ema != NULL,
+ * ema -= (1 - ema_decay) * (ema - p)  (models/ema.py:43-51). */
+int indm_adamw_ema_f32(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int64_t step, const float* grad_sumsq, float max_norm, float ema_decay,
+                       void* stream);
+int indm_ema_f32(float* ema, const float* p, int64_t n, float decay, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Predictor-corrector update (sampling.py:205-210 ReverseDiffusionPredictor, :272-292 LangevinCorrector with

@@ -16,6 +16,7 @@ DTYPE_BF16, DTYPE_TF32, DTYPE_F32 = 0, 1, 2
 
 _lib = None
 launches = 0  # number of kernel-launching C-ABI calls issued through this module (bench.py reports it)
+param_epoch = 0  # bumped whenever parameters are updated through raw pointers (fused optimizer, EMA copy): engines repack
 
 
 class IgemmDesc(C.Structure):
@@ -70,10 +71,20 @@ _SIGS = {
     "indm_fixed_point_check": [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp],
     "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],
     "indm_gn_bwd_stats": [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32,
-                          C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp],
+                          C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _f32, _vp, C.c_uint32, _vp],
     "indm_gn_bwd_apply": [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32,
-                          C.c_int, C.c_int, _vp, _vp, _vp, _f32, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp],
+                          C.c_int, C.c_int, _vp, _vp, _vp, _f32, _vp, C.c_int, _vp, C.c_int, C.c_int, _f32, _vp, C.c_uint32, _vp],
+    "indm_gn_apply_dropout": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32, C.c_int,
+                              _vp, C.c_int, _f32, _vp, C.c_uint32, _vp],
     "indm_cast_scale": [_vp, _vp, _i64, _f32, C.c_int, _vp],
+    "indm_colsum": [_vp, C.c_int, _i64, _i64, C.c_int, _i64, _vp, _i64, _vp, _f32, _vp],
+    "indm_sgemm_f32": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _vp, _i64, _vp, _i64, _f32, _vp, _i64, _vp],
+    "indm_silu_bwd_f32": [_vp, _vp, _vp, _i64, _vp],
+    "indm_perturb_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "indm_dsm_loss_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _vp],
+    "indm_sumsq_f32": [_vp, _i64, _vp, _vp],
+    "indm_adamw_ema_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp, _f32, _f32, _vp],
+    "indm_ema_f32": [_vp, _vp, _i64, _f32, _vp],
     "indm_conv_wgrad": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _i64, _i64,
                         _f32, _vp],
     "indm_softmax_bwd_rows": [_vp, _vp, _vp, _i64, C.c_int, _f32, C.c_int, _vp],

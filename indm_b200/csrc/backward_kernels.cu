@@ -5,6 +5,7 @@
 #include "../../include/indm_b200.h"
 #include "common.cuh"
 #include "nhwc.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -31,6 +32,9 @@ struct GnBwdP {
   int acc_a, acc_b;          // fp32 outputs only: accumulate instead of overwrite
   float* dgamma;             // optional [C] (atomicAdd), training only
   float* dbeta;
+  float drop_p;              // dropout applied after the activation in the forward (resample == 0 only); mask recomputed here
+  const unsigned long long* drop_ctl;
+  unsigned drop_stream;
 };
 
 // gradient arriving at pre-resample pixel (y, x): RES 0 same pixel, 1 (forward nearest-up) sum of the 2x2 children,
@@ -65,6 +69,8 @@ __global__ void gn_bwd_kernel(const GnBwdP p) {
   const int cpg = C / p.G;
   const int g = c / cpg;
   const long long P = (long long)p.H * p.W;
+  const bool dropping = RES == 0 && p.drop_ctl != nullptr && p.drop_p > 0.f && p.drop_ctl[1] != 0ull;
+  const unsigned long long drop_seed = dropping ? p.drop_ctl[0] : 0ull;
   if (MODE == 0) {
     for (int i = threadIdx.x; i < 32; i += blockDim.x) {
       s_1[i] = 0.f;
@@ -110,6 +116,10 @@ __global__ void gn_bwd_kernel(const GnBwdP p) {
       const float4 d = load_dy<TDy, RES>((const TDy*)p.dy, n, y, x, p.H, p.W, C, c);
       const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
       float4 du = d;
+      if (RES == 0 && dropping) {
+        const float4 k = dropout_scale4(drop_seed, p.drop_stream, (unsigned long long)((n * P + pp) * Q + q), p.drop_p);
+        du = make_float4(du.x * k.x, du.y * k.y, du.z * k.z, du.w * k.w);
+      }
       if (p.act) {
         du.x *= dsilu(xh.x * ga.x + be.x);
         du.y *= dsilu(xh.y * ga.y + be.y);
@@ -255,7 +265,8 @@ __global__ void rowdot_kernel(const float* __restrict__ a, const float* __restri
 static int gn_bwd_common(int mode, const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N,
                          int H, int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps, int act_silu,
                          int resample, float* partial_bwd, const float* extra_post, const float* extra_pre, float extra_scale,
-                         void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, float* dgamma, float* dbeta, cudaStream_t stream) {
+                         void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, float* dgamma, float* dbeta, float drop_p,
+                         const uint64_t* drop_ctl, uint32_t drop_stream, cudaStream_t stream) {
   if (!xb) Cb = 0;
   const int C = Ca + Cb;
   INDM_CHECK_ARG(dy && xa && partial_fwd && partial_bwd && gamma && beta && N > 0 && H > 0 && W > 0, "gn_bwd: bad arguments");
@@ -271,6 +282,7 @@ static int gn_bwd_common(int mode, const void* dy, int dy_dtype, const void* xa,
   p.partial_fwd = partial_fwd; p.gamma = gamma; p.beta = beta; p.eps = eps; p.act = act_silu; p.partial_bwd = partial_bwd;
   p.extra_post = extra_post; p.extra_pre = extra_pre; p.extra_scale = extra_scale;
   p.dxa = dxa; p.dxb = dxb; p.acc_a = acc_a; p.acc_b = acc_b; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.drop_p = drop_p; p.drop_ctl = (const unsigned long long*)drop_ctl; p.drop_stream = drop_stream;
   return mode == 0 ? gn_bwd_dispatch<0>(p, N, resample, dy_dtype, x_dtype, out_dtype, stream)
                    : gn_bwd_dispatch<1>(p, N, resample, dy_dtype, x_dtype, out_dtype, stream);
 }
@@ -278,18 +290,20 @@ static int gn_bwd_common(int mode, const void* dy, int dy_dtype, const void* xa,
 extern "C" int indm_gn_bwd_stats(const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N,
                                  int H, int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps,
                                  int act_silu, int resample, float* partial_bwd, float* dgamma, float* dbeta, int out_dtype,
-                                 void* stream) {
+                                 float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream, void* stream) {
   return gn_bwd_common(0, dy, dy_dtype, xa, Ca, xb, Cb, x_dtype, N, H, W, G, partial_fwd, gamma, beta, eps, act_silu, resample,
-                       partial_bwd, nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, out_dtype, dgamma, dbeta, (cudaStream_t)stream);
+                       partial_bwd, nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, out_dtype, dgamma, dbeta, drop_p, drop_ctl, drop_stream,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int indm_gn_bwd_apply(const void* dy, int dy_dtype, const void* xa, int Ca, const void* xb, int Cb, int x_dtype, int64_t N,
                                  int H, int W, int G, const float* partial_fwd, const float* gamma, const float* beta, float eps,
                                  int act_silu, int resample, const float* partial_bwd, const float* extra_post, const float* extra_pre,
-                                 float extra_scale, void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, void* stream) {
+                                 float extra_scale, void* dxa, int acc_a, void* dxb, int acc_b, int out_dtype, float drop_p,
+                                 const uint64_t* drop_ctl, uint32_t drop_stream, void* stream) {
   return gn_bwd_common(1, dy, dy_dtype, xa, Ca, xb, Cb, x_dtype, N, H, W, G, partial_fwd, gamma, beta, eps, act_silu, resample,
                        const_cast<float*>(partial_bwd), extra_post, extra_pre, extra_scale, dxa, acc_a, dxb, acc_b, out_dtype, nullptr,
-                       nullptr, (cudaStream_t)stream);
+                       nullptr, drop_p, drop_ctl, drop_stream, (cudaStream_t)stream);
 }
 
 extern "C" int indm_cast_scale(const float* in, void* out, int64_t n, float scale, int out_dtype, void* stream_) {

@@ -6,23 +6,9 @@
 // graph with no host involvement.
 #include "../../include/indm_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
-
-struct Philox {
-  static __device__ __forceinline__ uint4 round10(uint4 ctr, uint2 key) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-      const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-      ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-      key.x += W0;
-      key.y += W1;
-    }
-    return ctr;
-  }
-};
 
 // four standard normals for element quad `q` of stream (seed, a, b)
 __device__ __forceinline__ float4 normal4(uint64_t seed, uint32_t a, uint32_t b, uint64_t q) {

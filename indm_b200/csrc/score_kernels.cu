@@ -7,6 +7,7 @@
 #include "../../include/indm_b200.h"
 #include "common.cuh"
 #include "nhwc.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -64,7 +65,12 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
                                 int R, const float* __restrict__ partial, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act,
                                 typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ out,
-                                typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ raw) {
+                                typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ raw,
+                                float drop_p, const unsigned long long* __restrict__ drop_ctl, unsigned drop_stream) {
+  // training-mode dropout after the activation (models/layerspp.py:278): drop_ctl = {seed, enabled} in device memory, so the
+  // same launch plan serves eval (enabled = 0) and train forward passes
+  const bool dropping = RES == 0 && drop_ctl != nullptr && drop_p > 0.f && drop_ctl[1] != 0ull;
+  const unsigned long long drop_seed = dropping ? drop_ctl[0] : 0ull;
   const int C = Ca + Cb;
   const int Q = C >> 2;
   const int q = threadIdx.x % Q;
@@ -124,7 +130,11 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
     const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
     for (long long p = p0 + rr; p < p1; p += R) {
       const float4 v = Vec4<TIn>::load(src + p * ld);
-      const float4 y = norm(v);
+      float4 y = norm(v);
+      if (RES == 0 && dropping) {
+        const float4 k = dropout_scale4(drop_seed, drop_stream, (unsigned long long)((n * P + p) * Q + q), drop_p);
+        y = make_float4(y.x * k.x, y.y * k.y, y.z * k.z, y.w * k.w);
+      }
       if (RES == 0) {
         Vec4<TOut>::store(out + (n * P + p) * C + c, y);
         if (raw) Vec4<TOut>::store(raw + (n * P + p) * C + c, v);
@@ -337,13 +347,13 @@ extern "C" int indm_gn_stats(const void* xa, int Ca, const void* xb, int Cb, int
 template <typename TIn, typename TOut>
 static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64_t N, int H, int W, int G, const float* partial,
                            const float* gamma, const float* beta, float eps, int act, int resample, void* out, void* raw,
-                           cudaStream_t stream) {
+                           float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream, cudaStream_t stream) {
   using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
   const int C = Ca + Cb;
   const long long Piter = resample == 2 ? (long long)(H / 2) * (W / 2) : (long long)H * W;
   const GnGeom g = gn_geom(C, Piter, N);
   dim3 grid(g.splits, (unsigned)N);
-#define GN_ARGS (const TIn*)xa, Ca, (const TIn*)xb, Cb, H, W, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw
+#define GN_ARGS (const TIn*)xa, Ca, (const TIn*)xb, Cb, H, W, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream
   if (resample == 0)
     gn_apply_kernel<TIn, TOut, 0><<<grid, g.threads, 0, stream>>>(GN_ARGS);
   else if (resample == 1)
@@ -355,9 +365,31 @@ static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64
   return INDM_OK;
 }
 
+static int gn_apply_impl(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                         const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
+                         void* out, void* raw, int out_dtype, float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream,
+                         void* stream_);
+
 extern "C" int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
                              const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
                              void* out, void* raw, int out_dtype, void* stream_) {
+  return gn_apply_impl(xa, Ca, xb, Cb, in_dtype, N, H, W, G, partial, gamma, beta, eps, act_silu, resample, out, raw, out_dtype, 0.f,
+                       nullptr, 0u, stream_);
+}
+
+extern "C" int indm_gn_apply_dropout(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                                     const float* partial, const float* gamma, const float* beta, float eps, int act_silu,
+                                     void* out, int out_dtype, float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream,
+                                     void* stream_) {
+  INDM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && drop_ctl != nullptr, "gn_apply_dropout: need 0 <= p < 1 and a control buffer");
+  return gn_apply_impl(xa, Ca, xb, Cb, in_dtype, N, H, W, G, partial, gamma, beta, eps, act_silu, 0, out, nullptr, out_dtype, drop_p,
+                       (const unsigned long long*)drop_ctl, drop_stream, stream_);
+}
+
+static int gn_apply_impl(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                         const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
+                         void* out, void* raw, int out_dtype, float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream,
+                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!xb) Cb = 0;
   const int C = Ca + Cb;
@@ -370,7 +402,7 @@ extern "C" int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int
   const bool in_f32 = in_dtype == INDM_DTYPE_F32, in_bf = in_dtype == INDM_DTYPE_BF16;
   const bool out_bf = out_dtype == INDM_DTYPE_BF16, out_tf = out_dtype == INDM_DTYPE_TF32, out_f = out_dtype == INDM_DTYPE_F32;
   INDM_CHECK_ARG((in_f32 || in_bf) && (out_bf || out_tf || out_f), "gn_apply: unsupported dtypes %d -> %d", in_dtype, out_dtype);
-#define GN_GO(TI, TO_) return gn_apply_launch<TI, TO_>(xa, Ca, xb, Cb, N, H, W, G, partial, gamma, beta, eps, act_silu, resample, out, raw, stream)
+#define GN_GO(TI, TO_) return gn_apply_launch<TI, TO_>(xa, Ca, xb, Cb, N, H, W, G, partial, gamma, beta, eps, act_silu, resample, out, raw, drop_p, drop_ctl, drop_stream, stream)
   if (in_f32 && out_bf) GN_GO(float, __nv_bfloat16);
   if (in_f32 && out_tf) GN_GO(float, Tf32Out);
   if (in_f32 && out_f) GN_GO(float, float);

@@ -198,6 +198,64 @@ int launch_wgrad(const CUtensorMap& dy, const CUtensorMap& x, WgradParams p, int
 
 bool is_pow2w(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// FP32 validation path (CUDA cores): the same sum with fp32 operands and fp32 FMAs.  MN-major TF32 tensor-core operands need
+// the 32-byte-atom swizzle, which the forward TMA boxes do not use; the validation mode trades speed for exactness instead.
+// grid (o tiles of 64, c tiles of 64, taps * ksplit), block 256: each thread owns a 4 x 4 patch of the 64 x 64 tile.
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ x,
+                                                        long long x_ld, int N, int H, int W, int Cout, int Cin, int taps, int ksplit,
+                                                        float* __restrict__ dw, long long so, long long sc, long long st, float scale) {
+  __shared__ float sdy[16][64 + 4], sx[16][64 + 4];
+  const int tap = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
+  const int o0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  int dyy = 0, dxx = 0;
+  if (taps == 9) {
+    dyy = tap / 3 - 1;
+    dxx = tap % 3 - 1;
+  }
+  const long long P = (long long)N * H * W;
+  const long long per = (P + ksplit - 1) / ksplit;
+  const long long p0 = ks * per, p1 = min(P, p0 + per);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;   // tx -> c patch, ty -> o patch
+  float acc[4][4] = {};
+  for (long long pb = p0; pb < p1; pb += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int r = i / 64, cc = i % 64;
+      const long long pp = pb + r;
+      float a = 0.f, b = 0.f;
+      if (pp < p1) {
+        if (o0 + cc < Cout) a = dy[pp * dy_ld + o0 + cc];
+        const int xx = (int)(pp % W), yy = (int)((pp / W) % H);
+        const int sx_ = xx + dxx, sy_ = yy + dyy;
+        if (c0 + cc < Cin && sx_ >= 0 && sx_ < W && sy_ >= 0 && sy_ < H) b = x[(pp + (long long)dyy * W + dxx) * x_ld + c0 + cc];
+      }
+      sdy[r][cc] = a;
+      sx[r][cc] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = sdy[r][ty * 4 + i];
+        b[i] = sx[r][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + ty * 4 + i, c = c0 + tx * 4 + j;
+      if (o < Cout && c < Cin) atomicAdd(dw + (long long)o * so + (long long)c * sc + (long long)tap * st, acc[i][j] * scale);
+    }
+}
+
 }  // namespace
 
 extern "C" int indm_conv_wgrad(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, int dtype, int N, int H, int W, int Cout,
@@ -208,6 +266,19 @@ extern "C" int indm_conv_wgrad(const void* dy, int64_t dy_ld, const void* x, int
   INDM_CHECK_ARG(dtype == INDM_DTYPE_BF16 || tf32, "wgrad: dtype must be BF16 or TF32");
   INDM_CHECK_ARG(dy && x && dw && N > 0 && H > 0 && W > 0 && Cout > 0 && Cin > 0, "wgrad: bad arguments");
   INDM_CHECK_ARG(taps == 1 || taps == 9, "wgrad: taps must be 1 or 9");
+  if (tf32) {
+    const long long P = (long long)N * H * W;
+    const int jobs = ((Cout + 63) / 64) * ((Cin + 63) / 64) * taps;
+    long long ksplit = (4LL * indm_num_sms() + jobs - 1) / jobs;
+    if (ksplit > (P + 255) / 256) ksplit = (P + 255) / 256;
+    if (ksplit < 1) ksplit = 1;
+    INDM_CHECK_ARG((long long)taps * ksplit <= 65535, "wgrad: grid.z overflow");
+    dim3 grid((Cout + 63) / 64, (Cin + 63) / 64, (unsigned)(taps * ksplit));
+    wgrad_f32_kernel<<<grid, 256, 0, stream>>>((const float*)dy, dy_ld ? dy_ld : Cout, (const float*)x, x_ld ? x_ld : Cin, N, H, W, Cout,
+                                               Cin, taps, (int)ksplit, dw, stride_o, stride_c, stride_t, scale);
+    INDM_CHECK_LAUNCH("wgrad_f32");
+    return INDM_OK;
+  }
   const int esz = tf32 ? 4 : 2;
   const int kc = tf32 ? 32 : 64;
   WgradParams p{};

@@ -359,7 +359,7 @@ class FlowEngine:
         return w / torch.clamp(scale / COEFF, min=1.0).reshape(-1, 1, 1, 1), scale.max()
 
     def version(self):
-        return sum(p._version for p in self.core.parameters()) + sum(b._version for b in self.core.buffers())
+        return sum(p._version for p in self.core.parameters()) + sum(b._version for b in self.core.buffers()) + L.param_epoch
 
     def load_weights(self):
         dev = self.dev

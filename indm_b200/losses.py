@@ -1,0 +1,282 @@
+"""Training losses and step functions with the reference's interface (losses.py): `get_optimizer` :30-45,
+`optimization_manager` :48-62, `get_sde_loss_fn` :65-144, `get_step_fn` :194-420.
+
+What runs where: the score network's forward (train mode) and its full backward — input gradient and every parameter gradient —
+run on the engine's explicit plans (models/engine.py); the DSM loss and its gradient are one kernel; gradient-norm clipping +
+AdamW run as one pass over flat parameter storage; under torch.distributed the flat gradient buffer is all-reduced with NCCL
+before the clip (data-parallel training, one process per GPU, where the reference uses nn.DataParallel).
+
+Scope of this module: `step_fn` (score network only) is complete.  The joint flow + score step functions need gradients
+through the flow (first-order through g and its posterior encoder, second-order through the Neumann log-det estimator,
+iresblock.py:264-273); those are not on the CUDA path yet, so `flow_step_fn_*` train the score network on the flow's latent
+with the flow parameters frozen and say so loudly unless `config.training.freeze_flow` acknowledges it.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import sde_lib
+from .flow_models.flow_model import flow_forward
+from .models import utils as mutils
+from .models.ema import flat_view
+from .sde_lib import VESDE, VPSDE
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, amsgrad off) as ONE kernel over flat storage,
+    with `clip_grad_norm_` folded in (the clip coefficient is computed on the device from the global gradient norm: no host
+    sync) and the data-parallel gradient all-reduce issued on the same flat buffer.  Parameters and their `.grad` are re-homed
+    into two flat buffers at construction; `zero_grad` zeroes in place so the engine's backward plan keeps valid pointers."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True):
+        params = [p for p in params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        ps = [p for g in self.param_groups for p in g['params'] if p.requires_grad]
+        if not ps or not ps[0].is_cuda:
+            raise RuntimeError('indm_b200 FusedAdamW needs CUDA parameters: there is no CPU path')
+        if not decoupled:
+            raise NotImplementedError("optim.optimizer='Adam' (coupled weight decay) is not used by any INDM config")
+        dev, total = ps[0].device, sum(p.numel() for p in ps)
+        self._params = ps
+        self.flat_p = torch.empty((total,), dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros((total,), dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self._sumsq = torch.zeros((1,), dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                n = p.numel()
+                self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + n].view_as(p)
+                p.grad = self.flat_g[off:off + n].view_as(p)
+                off += n
+        self.steps = 0
+        self.max_norm = -1.0          # set by optimize_fn (losses.py:58-59); < 0 disables clipping
+        L.param_epoch += 1
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.flat_g)                 # NCCL over NVLink: SUM, then the mean
+            self.flat_g.div_(torch.distributed.get_world_size())
+        self.steps += 1
+        sumsq = None
+        if self.max_norm >= 0:
+            self._sumsq.zero_()
+            L.call('indm_sumsq_f32', L.ptr(self.flat_g), self.flat_g.numel(), L.ptr(self._sumsq))
+            sumsq = self._sumsq
+        b1, b2 = g['betas']
+        L.call('indm_adamw_ema_f32', L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), None,
+               self.flat_p.numel(), float(g['lr']), float(b1), float(b2), float(g['eps']), float(g['weight_decay']), self.steps,
+               L.ptr(sumsq), float(self.max_norm), 0.0)
+        L.param_epoch += 1            # engines repack their operand copies of the weights on next use
+
+    def state_dict(self):
+        return dict(steps=self.steps, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
+                    param_groups=[{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups])
+
+    def load_state_dict(self, sd):
+        self.steps = sd['steps']
+        self.exp_avg.copy_(sd['exp_avg'])
+        self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        for g, s in zip(self.param_groups, sd['param_groups']):
+            g.update(s)
+
+
+def get_optimizer(config, params, lr=None, beta1=None, eps=None, weight_decay=None):
+    """losses.py:30-45"""
+    if lr is None: lr = config.optim.lr
+    if beta1 is None: beta1 = config.optim.beta1
+    if eps is None: eps = config.optim.eps
+    if weight_decay is None: weight_decay = config.optim.weight_decay
+    if config.optim.amsgrad:
+        raise NotImplementedError('amsgrad is off in every INDM config')
+    if config.optim.optimizer == 'AdamW':
+        return FusedAdamW(params, lr=lr, betas=(beta1, 0.99), eps=eps, weight_decay=weight_decay)
+    if config.optim.optimizer == 'Adam':
+        return FusedAdamW(params, lr=lr, betas=(beta1, 0.999), eps=eps, weight_decay=weight_decay, decoupled=False)
+    raise NotImplementedError(f'Optimizer {config.optim.optimizer} not supported yet!')
+
+
+def optimization_manager(config):
+    """Returns an optimize_fn based on `config` (losses.py:48-62)."""
+
+    def optimize_fn(optimizer, params, step, lr=config.optim.lr, warmup=config.optim.warmup, grad_clip=config.optim.grad_clip):
+        """Optimizes with warmup and gradient clipping (disabled if negative)."""
+        if warmup > 0:
+            for g in optimizer.param_groups:
+                g['lr'] = lr * np.minimum(step / warmup, 1.0)
+        if isinstance(optimizer, FusedAdamW):
+            optimizer.max_norm = float(grad_clip)
+        elif grad_clip >= 0:
+            torch.nn.utils.clip_grad_norm_(params, max_norm=grad_clip)
+        optimizer.step()
+
+    return optimize_fn
+
+
+# ------------------------------------------------------------------------------------------------ loss
+class _DSMLoss(torch.autograd.Function):
+    """losses[n] = 0.5 * w[n] * norm * sum((score * std[n] + z)^2) and d losses / d score in the same kernel pass"""
+
+    @staticmethod
+    def forward(ctx, score, z, std, w, norm):
+        N, D = score.shape[0], score[0].numel()
+        score, z = score.contiguous().float(), z.contiguous().float()
+        std, w = std.contiguous().float(), w.contiguous().float()
+        losses = torch.empty((N,), device=score.device)
+        dscore = torch.empty_like(score)
+        L.call('indm_dsm_loss_f32', L.ptr(score), L.ptr(z), L.ptr(std), L.ptr(w), L.ptr(losses), L.ptr(dscore), N, D, float(norm), 1.0)
+        ctx.save_for_backward(dscore)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        dscore, = ctx.saved_tensors
+        return dscore * grad_losses.reshape(-1, 1, 1, 1), None, None, None, None
+
+
+def get_sde_loss_fn(config, sde, train, variance='scoreflow'):
+    """losses.py:65-144: `loss_fn(model, batch, st=False, recon_loss=None, importance_sampling=None) -> losses [B]`.
+    Keyword-only `draws=` = dict(u=, z=) pins the random draws for parity tests."""
+    reduce_mean = bool(config.training.reduce_mean)
+
+    def loss_fn(model, batch, st=False, recon_loss=None, importance_sampling=None, *, draws=None):
+        draws = draws or {}
+        if recon_loss is None:
+            recon_loss = config.training.reconstruction_loss
+        if importance_sampling is None:
+            importance_sampling = config.training.importance_sampling
+        if recon_loss:
+            raise NotImplementedError('training.reconstruction_loss=True is not used by any INDM config')
+        t_min = sde.get_t_min(config, st)
+        if importance_sampling:
+            t, Z = sde.get_diffusion_time(config, batch.shape[0], batch.device, t_min, importance_sampling=True, u=draws.get('u'))
+        else:
+            u = draws.get('u')
+            t = (u if u is not None else torch.rand(batch.shape[0], device=batch.device)) * (sde.T - t_min) + t_min
+            Z = 1
+        score_fn = mutils.get_score_fn(config, sde, model, None, train=train, continuous=config.training.continuous)
+        z = draws['z'] if 'z' in draws else torch.randn_like(batch)
+        N, D = batch.shape[0], batch[0].numel()
+        # x_t = mean + std z with mean = a(t) x (sde.marginal_prob): one fused pass
+        a = sde.marginal_prob(torch.ones((N, 1, 1, 1), device=batch.device), t)[0].reshape(N).contiguous().float()
+        std = sde.marginal_prob(torch.zeros((N, 1, 1, 1), device=batch.device), t)[1].contiguous().float()
+        if batch.requires_grad:
+            perturbed_data = a[:, None, None, None] * batch + std[:, None, None, None] * z      # keeps the graph to the flow
+        else:
+            perturbed_data = torch.empty_like(batch, dtype=torch.float32)
+            L.call('indm_perturb_f32', L.ptr(batch.contiguous().float()), L.ptr(z.contiguous().float()), L.ptr(a), L.ptr(std),
+                   L.ptr(perturbed_data), N, D)
+        score = score_fn(perturbed_data, t)
+        Zt = torch.as_tensor(Z, dtype=torch.float32, device=batch.device)
+        if importance_sampling or not config.training.likelihood_weighting:
+            w = Zt.expand(N) if Zt.dim() == 0 else Zt
+        else:
+            g2 = sde.sde(torch.zeros((N, 1, 1, 1), device=batch.device), t)[1] ** 2
+            w = Zt * g2 / std ** 2
+        return _DSMLoss.apply(score, z, std, w.contiguous(), (1.0 / D) if reduce_mean else 1.0)
+
+    return loss_fn
+
+
+# ------------------------------------------------------------------------------------------------ step functions
+def get_step_fn(config, sde, train, optimize_fn=None, scaler=None):
+    """losses.py:194-420."""
+    if not config.training.continuous:
+        raise NotImplementedError('INDM configs are continuous-time (training.continuous=True)')
+    loss_fn = get_sde_loss_fn(config, sde, train)
+
+    def calculate_logp(batch):
+        """losses.py:219-225"""
+        Ts = torch.ones(batch.shape[0], device=batch.device) * sde.T
+        meanT, stdT = sde.marginal_prob(batch, Ts)
+        yT = meanT + stdT[:, None, None, None] * torch.randn_like(batch)
+        return sde.prior_logp(yT)
+
+    def step_fn(state, flow_state, batch, **kw):
+        """losses.py:227-256: one optimisation step of the score network (flow.model == 'identity')."""
+        model, optimizer = state['model'], state['optimizer']
+        optimizer.zero_grad()
+        batch_size = batch.shape[0]
+        nmb = config.optim.num_micro_batch
+        losses_ = torch.zeros(batch_size)
+        for k in range(nmb):
+            sl = slice(batch_size // nmb * k, batch_size // nmb * (k + 1))
+            losses = loss_fn(model, batch[sl], **kw)
+            if train:
+                (torch.mean(losses) / 1.0).backward()
+            losses_[sl] = losses.detach().cpu()
+        if train:
+            optimize_fn(optimizer, model.parameters(), step=state['step'])
+            state['step'] += 1
+            state['ema'].update(model.parameters())
+        return losses_, None, None, None, None
+
+    def _frozen_flow_step(state, flow_state, batch, fid_variant, **kw):
+        """score-network half of flow_step_fn_nll (:258-320) / flow_step_fn_fid (:322-406) with the flow frozen (eval mode):
+        latent = flow(x) without gradient, score loss + prior log-p + flow log-det / KL are all evaluated and reported, only the
+        score network is updated."""
+        model, flow_model, optimizer = state['model'], flow_state['model'], state['optimizer']
+        batch_size = batch.shape[0]
+        nmb = config.optim.num_micro_batch
+        losses_, losses_score_, losses_flow_, losses_logp_ = (torch.zeros(batch_size) for _ in range(4))
+        optimizer.zero_grad()
+        D = float(np.prod(batch.shape[1:]))
+        flow_model.eval()
+        for k in range(nmb):
+            sl = slice(batch_size // nmb * k, batch_size // nmb * (k + 1))
+            with torch.no_grad():
+                latent, losses_flow = flow_forward(config, flow_model, batch[sl], reverse=False)
+            if fid_variant:
+                losses_score = loss_fn(model, latent, st=config.training.st, recon_loss=False, **kw)
+            else:
+                losses_score = loss_fn(model, latent, st=config.training.st, **kw)
+            with torch.no_grad():
+                losses_logp = calculate_logp(latent)
+                if config.training.reduce_mean:
+                    losses_flow, losses_logp = -losses_flow / D, -losses_logp / D
+                else:
+                    losses_flow, losses_logp = -losses_flow, -losses_logp
+            if train:
+                torch.mean(losses_score).backward()
+            losses_[sl] = (losses_score.detach() + losses_flow + losses_logp).cpu()
+            losses_score_[sl], losses_flow_[sl], losses_logp_[sl] = losses_score.detach().cpu(), losses_flow.cpu(), losses_logp.cpu()
+        if train:
+            optimize_fn(optimizer, model.parameters(), step=state['step'])
+            state['step'] += 1
+            state['ema'].update(model.parameters())
+            flow_state['step'] += 1
+        return losses_, losses_score_, losses_flow_, losses_logp_
+
+    def _need_ack():
+        if not getattr(config.training, 'freeze_flow', False):
+            raise NotImplementedError(
+                'joint flow + score training needs gradients through the wolf flow (incl. the second-order Neumann log-det term); '
+                'that backward is not on the CUDA path yet.  Set config.training.freeze_flow = True to train the score network on '
+                'the frozen flow latent (flow losses are still evaluated and returned).')
+
+    def flow_step_fn_nll(state, flow_state, batch, **kw):
+        _need_ack()
+        return _frozen_flow_step(state, flow_state, batch, False, **kw)
+
+    def flow_step_fn_fid(state, flow_state, batch, **kw):
+        _need_ack()
+        return _frozen_flow_step(state, flow_state, batch, True, **kw)
+
+    if config.flow.model == 'identity':
+        logging.info('Train only the score network.')
+        return step_fn
+    if not config.training.likelihood_weighting:
+        logging.info('Train score network with FID-favorable setting (weighting function = variance weighting).')
+        return flow_step_fn_fid
+    logging.info('Train score network with NLL-favorable setting (weighting function = likelihood weighting).')
+    return flow_step_fn_nll

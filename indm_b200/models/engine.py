@@ -47,13 +47,16 @@ class ScoreEngine:
         self.fir = bool(cfg.model.fir)
         self.keep = []            # every tensor the plan points into
         self.ops = []             # list of zero-arg callables (forward plan)
-        self.bops = None          # backward (input-VJP) plan, built on first use by build_backward()
+        self.bops = None          # current backward plan, built on first use by build_backward()
+        self._plans = {}          # {train flag: plan}
+        self._train = False
         self.tape = []            # closures recorded by the forward builders; replayed in reverse to emit the backward plan
         self._cur = self.ops      # list the emit helpers append to
         self.pack_jobs = []       # (fn) re-run by load_weights()
         self.gn_slots = 0
         self._weights_version = None
         self.forward_count = 0    # bumped by every forward(): lets a pending backward detect overwritten activations
+        self._drop_on = False
         self._build()
         self.load_weights()
 
@@ -106,7 +109,7 @@ class ScoreEngine:
         self._weights_version = self.weights_version()
 
     def weights_version(self):
-        return sum(p._version for p in self.model.parameters())
+        return sum(p._version for p in self.model.parameters()) + L.param_epoch
 
     # ------------------------------------------------------------------ plan construction
     def _igemm(self, **kw):
@@ -132,7 +135,7 @@ class ScoreEngine:
             L.check(fn(*cargs, L._stream()), name)
         self._cur.append(run)
 
-    def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False):
+    def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False, dropout=0.0):
         """GroupNorm(+SiLU)(+resample) of concat(xa, xb) -> operand tensor (and optional raw copy of the input).
         Emits the statistics launch unless a producer already accumulated them into `slot`."""
         N = self.N
@@ -149,10 +152,16 @@ class ScoreEngine:
         Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
         out = self._op_t((N, Ho, Wo, C))
         raw = self._op_t((N, Ho, Wo, C)) if want_raw else None
-        self._call('indm_gn_apply', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
-                   act, resample, out, raw, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32)
+        odt_ = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32
+        if dropout > 0.0:
+            assert resample == 0 and not want_raw
+            self._call('indm_gn_apply_dropout', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
+                       act, out, odt_, ctypes.c_float(dropout), self.drop_ctl, ctypes.c_uint32(slot))
+        else:
+            self._call('indm_gn_apply', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
+                       act, resample, out, raw, odt_)
         self._last_gn = dict(xa=xa, Ca=Ca, xb=xb, Cb=Cb, in_dt=in_dt, H=H, W=W, G=G, part=part, gamma=gamma, beta=beta, act=act,
-                             resample=resample, params=gparams)
+                             resample=resample, params=gparams, drop_p=float(dropout), drop_stream=int(slot))
         return out, raw
 
     def _build(self):
@@ -162,6 +171,8 @@ class ScoreEngine:
         # GroupNorm statistics: one [slots][N][32][2] buffer zeroed by a single memset per forward
         MAX_SLOTS = 2 * len(mods) + 8
         self.gn_part_all = self._alloc((MAX_SLOTS, N, 32, 2), zero=True)
+        self.drop_ctl = self._alloc((2,), torch.int64, zero=True)     # {Philox seed, enabled}: read by the dropout kernels
+        self._drop_seed = 0x5EED
         self.gn_part = [self.gn_part_all[i] for i in range(MAX_SLOTS)]
         part_all = self.gn_part_all
 
@@ -209,6 +220,7 @@ class ScoreEngine:
         # all Dense_0 layers of the network in one tensor-core GEMM: [N, 4nf] x [sum Cout, 4nf]^T
         self._igemm(a=temb_act, N=1, H=1, W=N, Cin=4 * nf, b=wd, Cout=dense_total, taps=1, bias=bd, out_f32=self.dense_tab,
                     out_ld=dense_total)
+        self.tape.append(('temb', dict(lin0=lin0, lin1=lin1, w0=w0, b0=b0, w1=w1, b1=b1, t0=t0, res_blocks=res_blocks, emb_dim=emb_dim)))
         dense_off = {}
         off = 0
         for rb in res_blocks:
@@ -229,7 +241,7 @@ class ScoreEngine:
         bst = self._alloc((nf,)); self._pack_f32(bst, [stem.bias])
         h0 = self._alloc((N, S, S, nf))
         self._igemm(a=x_nhwc, N=N, H=S, W=S, Cin=cpad, b=wst, Cout=nf, taps=9, bias=bst, out_f32=h0, out_ld=nf)
-        self.tape.append(('stem', dict(conv=stem, h0=h0, mul=1.0 if centered else 2.0)))
+        self.tape.append(('stem', dict(conv=stem, h0=h0, mul=1.0 if centered else 2.0, x_nhwc=x_nhwc, cpad=cpad)))
 
         inv_sqrt2 = 1.0 / math.sqrt(2.0)
 
@@ -276,7 +288,8 @@ class ScoreEngine:
                 kw.update(gn_partial=self.gn_part[slot1], gn_cpg=cpg1, gn_groups=G1)
             self._igemm(**kw)
             in_dt1 = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
-            h3, _ = self._gn(h2, Cout, None, 0, in_dt1, Ho, Wo, rb.GroupNorm_1, 1, 0, False, slot=slot1, stats_done=fuse_stats)
+            h3, _ = self._gn(h2, Cout, None, 0, in_dt1, Ho, Wo, rb.GroupNorm_1, 1, 0, False, slot=slot1, stats_done=fuse_stats,
+                             dropout=float(rb.dropout))
             gn1 = self._last_gn
             # conv1 (+ fused skip 1x1 | + residual), * 1/sqrt(2)
             w1 = self._op_t((9, Cout, Cout)); self._pack_conv(w1, rb.Conv_1.weight)
@@ -297,6 +310,7 @@ class ScoreEngine:
                 kw.update(residual=xa, res_ld=Cout, res_scale=inv_sqrt2 if rb.skip_rescale else 1.0)
             self._igemm(**kw)
             self.tape.append(('res_block', dict(rb=rb, gn0=gn0, gn1=gn1, out=out, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, has_skip=has_skip,
+                                                h1=h1, h3=h3, raw=raw, dense_off=dense_off[id(rb)],
                                                 use_fir=use_fir, s=inv_sqrt2 if rb.skip_rescale else 1.0)))
             return out, Ho, Wo
 
@@ -343,7 +357,7 @@ class ScoreEngine:
             self._igemm(a=o, N=N, H=H, W=W, Cin=C, b=w3, Cout=C, taps=1, bias=b3, residual=x, res_ld=C,
                         scale=inv_sqrt2 if ab.skip_rescale else 1.0, res_scale=inv_sqrt2 if ab.skip_rescale else 1.0,
                         out_f32=out, out_ld=C)
-            self.tape.append(('attn', dict(ab=ab, gn=gna, x=x, C=C, H=H, W=W, qkv=qkv, p=p, out=out,
+            self.tape.append(('attn', dict(ab=ab, gn=gna, x=x, C=C, H=H, W=W, qkv=qkv, p=p, out=out, h=h, o=o,
                                            s=inv_sqrt2 if ab.skip_rescale else 1.0)))
             return out
 
@@ -429,7 +443,7 @@ class ScoreEngine:
         self.out_scale.fill_(1.0)
         self._igemm(a=hh, N=N, H=H, W=W, Cin=Ch, b=wh, Cout=self.ch, taps=9, bias=bh, rowscale=self.out_scale, out_mode=1,
                     out_f32=self.out)
-        self.tape.append(('head', dict(conv=head, gn=gn_head, Ch=Ch, H=H, W=W)))
+        self.tape.append(('head', dict(conv=head, gn=gn_head, Ch=Ch, H=H, W=W, hh=hh)))
         self._bind_time_source(None, None, 0, 0)
 
     def _bind_time_source(self, sched, step, sched_ld, sched_col):
@@ -482,6 +496,38 @@ class ScoreEngine:
             job_now()
         return dst
 
+    # parameter gradients (training plan only): accumulated straight into `param.grad` storage, in the parameter's own layout
+    def _pgrad(self, param):
+        if param.grad is None:
+            param.grad = torch.zeros_like(param)
+        g = param.grad
+        if not g.is_contiguous() or g.dtype != torch.float32 or g.device != self.dev:
+            raise RuntimeError('indm_b200: parameter gradients must be contiguous fp32 tensors on the engine device')
+        self._pgrad_ptrs.append((param, g.data_ptr()))
+        return g
+
+    def _wgrad(self, dy, dy_ld, x, x_ld, H, W, Cout, Cin, taps, weight, strides=None):
+        if not self._train or not weight.requires_grad:
+            return
+        g = self._pgrad(weight)
+        so, sc, st = strides if strides is not None else (Cin * taps, taps, 1)
+        self._call('indm_conv_wgrad', dy, ctypes.c_int64(dy_ld), x, ctypes.c_int64(x_ld), L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32,
+                   self.N, H, W, Cout, Cin, taps, g, ctypes.c_int64(so), ctypes.c_int64(sc), ctypes.c_int64(st), ctypes.c_float(1.0))
+
+    def _bgrad(self, dy, P, C, ld, biases=(), img_out=None, img_ld=0):
+        """bias gradients (sum over images and pixels of dy) and / or the per-image sums that feed the time-embedding path"""
+        if not self._train:
+            return
+        op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+        outs = [self._pgrad(b) for b in biases if b.requires_grad]
+        first = outs[0] if outs else None
+        if first is not None or img_out is not None:
+            self._call('indm_colsum', dy, op_dt, ctypes.c_int64(self.N), ctypes.c_int64(P), C, ctypes.c_int64(ld), img_out, ctypes.c_int64(img_ld),
+                       first, ctypes.c_float(1.0))
+        for extra in outs[1:]:
+            self._call('indm_colsum', dy, op_dt, ctypes.c_int64(self.N), ctypes.c_int64(P), C, ctypes.c_int64(ld), None, ctypes.c_int64(0),
+                       extra, ctypes.c_float(1.0))
+
     def _gn_bwd(self, gn, dy, extra_post=None, extra_pre=None, extra_scale=0.0, to_operand=False):
         """emit stats + apply of the GroupNorm(+SiLU)(+resample) backward; returns the operand-dtype gradient if to_operand"""
         N = self.N
@@ -500,8 +546,12 @@ class ScoreEngine:
             out_dt = L.DTYPE_F32
         common = (dy, op_dt, gn['xa'], gn['Ca'], gn['xb'], gn['Cb'], x_dt, ctypes.c_int64(N), gn['H'], gn['W'], gn['G'], gn['part'],
                   gn['gamma'], gn['beta'], ctypes.c_float(1e-6), gn['act'], gn['resample'])
-        self._call('indm_gn_bwd_stats', *common, pb, None, None, out_dt)
-        self._call('indm_gn_bwd_apply', *common, pb, extra_post, extra_pre, ctypes.c_float(extra_scale), dxa, acc_a, dxb, acc_b, out_dt)
+        dgam = dbet = None
+        if self._train and gn['params'].weight.requires_grad:
+            dgam, dbet = self._pgrad(gn['params'].weight), self._pgrad(gn['params'].bias)
+        drop = (ctypes.c_float(gn['drop_p']), self.drop_ctl if gn['drop_p'] > 0 else None, ctypes.c_uint32(gn['drop_stream']))
+        self._call('indm_gn_bwd_stats', *common, pb, dgam, dbet, out_dt, *drop)
+        self._call('indm_gn_bwd_apply', *common, pb, extra_post, extra_pre, ctypes.c_float(extra_scale), dxa, acc_a, dxb, acc_b, out_dt, *drop)
         return dxa
 
     def _cast_grad(self, t, scale):
@@ -524,7 +574,12 @@ class ScoreEngine:
         w1d = self._pack_dgrad(rb.Conv_1.weight)
         d_h3 = self._op_t((N, Ho, Wo, Cout))
         self._igemm(a=g, N=N, H=Ho, W=Wo, Cin=Cout, b=w1d, Cout=Cout, taps=9, **self._okw(d_h3, Cout))
+        self._wgrad(g, Cout, r['h3'], Cout, Ho, Wo, Cout, Cout, 9, rb.Conv_1.weight)
+        self._bgrad(g, Ho * Wo, Cout, Cout, biases=[rb.Conv_1.bias] + ([rb.Conv_2.bias] if r['has_skip'] else []))
         d_h2 = self._gn_bwd(r['gn1'], d_h3, to_operand=True)
+        self._wgrad(d_h2, Cout, r['h1'], Cin, Ho, Wo, Cout, Cin, 9, rb.Conv_0.weight)
+        self._bgrad(d_h2, Ho * Wo, Cout, Cout, biases=[rb.Conv_0.bias],
+                    img_out=self.d_dense_tab[:, r['dense_off']:] if self._train else None, img_ld=self.dense_total)
         w0d = self._pack_dgrad(rb.Conv_0.weight)
         d_h1 = self._op_t((N, Ho, Wo, Cin))
         self._igemm(a=d_h2, N=N, H=Ho, W=Wo, Cin=Cout, b=w0d, Cout=Cin, taps=9, **self._okw(d_h1, Cin))
@@ -532,6 +587,7 @@ class ScoreEngine:
             w2d = self._pack_dgrad(rb.Conv_2.weight)
             d_raw = self._alloc((N, Ho, Wo, Cin))
             self._igemm(a=g, N=N, H=Ho, W=Wo, Cin=Cout, b=w2d, Cout=Cin, taps=1, out_f32=d_raw, out_ld=Cin)
+            self._wgrad(g, Cout, r['raw'], Cin, Ho, Wo, Cout, Cin, 1, rb.Conv_2.weight, strides=(Cin, 1, 0))
             self._gn_bwd(r['gn0'], d_h1, extra_post=d_raw)
         else:
             self._gn_bwd(r['gn0'], d_h1, extra_pre=self._grads[r['out'].data_ptr()], extra_scale=r['s'])
@@ -550,6 +606,9 @@ class ScoreEngine:
             job3()
         d_o = self._op_t((N, Lq, C))
         self._igemm(a=g, N=N, H=H, W=W, Cin=C, b=w3d, Cout=C, taps=1, **self._okw(d_o, C))
+        # NIN weights are [in, out]: dW[in][out] = sum_p x[p][in] dy[p][out]  ->  strides (o: 1, c: out)
+        self._wgrad(g, C, r['o'], C, H, W, C, C, 1, ab.NIN_3.W, strides=(1, C, 0))
+        self._bgrad(g, Lq, C, C, biases=[ab.NIN_3.b])
         # row-major V from the forward; transposed Q, K (and V, unused) from the fused q|k|v rows
         qkv = r['qkv']
         qkvT = self._op_t((N, 3 * C, Lq))
@@ -587,6 +646,10 @@ class ScoreEngine:
             jobq()
         d_h = self._op_t((N, Lq, C))
         self._igemm(a=d_qkv, N=N, H=H, W=W, Cin=3 * C, b=wqkvd, Cout=C, taps=1, **self._okw(d_h, C))
+        for jq in range(3):
+            nin = getattr(ab, f'NIN_{jq}')
+            self._wgrad(d_qkv[:, :, jq * C:], 3 * C, r['h'], C, H, W, C, C, 1, nin.W, strides=(1, C, 0))
+            self._bgrad(d_qkv[:, :, jq * C:], Lq, C, 3 * C, biases=[nin.b])
         self._gn_bwd(r['gn'], d_h, extra_pre=self._grads[r['out'].data_ptr()], extra_scale=r['s'])
 
     def _bwd_head(self, r):
@@ -599,6 +662,13 @@ class ScoreEngine:
         whd = self._pack_dgrad(r['conv'].weight, kpad=cpad)
         d_hh = self._op_t((N, S, S, Ch))
         self._igemm(a=g, N=N, H=S, W=S, Cin=cpad, b=whd, Cout=Ch, taps=9, **self._okw(d_hh, Ch))
+        self._wgrad(g, cpad, r['hh'], Ch, S, S, self.ch, Ch, 9, r['conv'].weight)
+        if self._train and r['conv'].bias.requires_grad:
+            tmp = self._alloc((cpad,), zero=True)      # colsum works on whole channel quads: sum the padded row, keep the first `ch`
+            self._scratch_zero.append(tmp)
+            self._call('indm_colsum', g, L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32, ctypes.c_int64(N), ctypes.c_int64(S * S), cpad,
+                       ctypes.c_int64(cpad), None, ctypes.c_int64(0), tmp, ctypes.c_float(1.0))
+            self._call('indm_axpy_f32', self._pgrad(r['conv'].bias), tmp, ctypes.c_float(1.0), ctypes.c_int64(self.ch))
         self._gn_bwd(r['gn'], d_hh)
 
     def _bwd_stem(self, r):
@@ -607,33 +677,101 @@ class ScoreEngine:
         wsd = self._pack_dgrad(r['conv'].weight)
         self.gx = self._alloc((N, self.ch, S, S))
         self._igemm(a=g, N=N, H=S, W=S, Cin=self.nf, b=wsd, Cout=self.ch, taps=9, scale=r['mul'], out_mode=1, out_f32=self.gx)
+        self._wgrad(g, self.nf, r['x_nhwc'], r['cpad'], S, S, self.nf, self.ch, 9, r['conv'].weight)
+        self._bgrad(g, S * S, self.nf, self.nf, biases=[r['conv'].bias])
 
-    def build_backward(self):
-        if self.bops is not None:
+    def _bwd_temb(self, r):
+        """time-embedding MLP and the 44 Dense_0 layers (models/ncsnpp.py:270-274, models/layerspp.py:276): small fp32 GEMMs"""
+        if not self._train:
             return
-        self._grads, self._gwritten, self._gnb_slots = {}, set(), 0
-        self.gnb_part_all = self._alloc((2 * len(self.tape) + 4, self.N, 32, 2), zero=True)
-        self._cur = bops = []
-        part = self.gnb_part_all
+        N, nf4, tot = self.N, 4 * self.nf, self.dense_total
+        f32 = lambda *shape: self._alloc(shape)
+        # fp32 recomputation of the pre-activations (the forward keeps only SiLU outputs, in the operand dtype)
+        pre0, pre1, tact = f32(N, nf4), f32(N, nf4), f32(N, nf4)
+        self._call('indm_linear_f32', self.emb, r['w0'], r['b0'], pre0, ctypes.c_int64(N), r['emb_dim'], nf4, 0, 0, L.DTYPE_F32)
+        self._call('indm_linear_f32', r['t0'], r['w1'], r['b1'], pre1, ctypes.c_int64(N), nf4, nf4, 0, 0, L.DTYPE_F32)
+        self._call('indm_linear_f32', r['t0'], r['w1'], r['b1'], tact, ctypes.c_int64(N), nf4, nf4, 0, 1, L.DTYPE_F32)
+        wd32 = f32(tot, nf4)
 
-        def zero_bwd_stats():
+        def job(wd32=wd32, blocks=r['res_blocks']):
+            wd32.copy_(torch.cat([rb.Dense_0.weight.detach().to(self.dev, torch.float32) for rb in blocks], dim=0))
+        self.pack_jobs.append(job)
+        with torch.no_grad():
+            job()
+        sg = lambda *a: self._call('indm_sgemm_f32', *a)
+        off = 0
+        for rb in r['res_blocks']:
+            co = rb.out_ch
+            dsl = self.d_dense_tab[:, off:]
+            if rb.Dense_0.weight.requires_grad:
+                # dW[out][k] += sum_n d_tab[n][out] * SiLU(temb)[n][k]
+                sg(1, 0, co, nf4, N, ctypes.c_float(1.0), dsl, ctypes.c_int64(tot), tact, ctypes.c_int64(nf4), ctypes.c_float(1.0),
+                   self._pgrad(rb.Dense_0.weight), ctypes.c_int64(nf4))
+                self._call('indm_colsum', dsl, L.DTYPE_F32, ctypes.c_int64(1), ctypes.c_int64(N), co, ctypes.c_int64(tot), None, ctypes.c_int64(0),
+                           self._pgrad(rb.Dense_0.bias), ctypes.c_float(1.0))
+            off += co
+        d_tact, d_pre1, d_t0, d_pre0 = f32(N, nf4), f32(N, nf4), f32(N, nf4), f32(N, nf4)
+        sg(0, 0, N, nf4, tot, ctypes.c_float(1.0), self.d_dense_tab, ctypes.c_int64(tot), wd32, ctypes.c_int64(nf4), ctypes.c_float(0.0),
+           d_tact, ctypes.c_int64(nf4))
+        self._call('indm_silu_bwd_f32', d_tact, pre1, d_pre1, ctypes.c_int64(N * nf4))
+        lin0, lin1 = r['lin0'], r['lin1']
+        sg(1, 0, nf4, nf4, N, ctypes.c_float(1.0), d_pre1, ctypes.c_int64(nf4), r['t0'], ctypes.c_int64(nf4), ctypes.c_float(1.0),
+           self._pgrad(lin1.weight), ctypes.c_int64(nf4))
+        self._call('indm_colsum', d_pre1, L.DTYPE_F32, ctypes.c_int64(1), ctypes.c_int64(N), nf4, ctypes.c_int64(nf4), None, ctypes.c_int64(0),
+                   self._pgrad(lin1.bias), ctypes.c_float(1.0))
+        sg(0, 0, N, nf4, nf4, ctypes.c_float(1.0), d_pre1, ctypes.c_int64(nf4), r['w1'], ctypes.c_int64(nf4), ctypes.c_float(0.0),
+           d_t0, ctypes.c_int64(nf4))
+        self._call('indm_silu_bwd_f32', d_t0, pre0, d_pre0, ctypes.c_int64(N * nf4))
+        ed = r['emb_dim']
+        sg(1, 0, nf4, ed, N, ctypes.c_float(1.0), d_pre0, ctypes.c_int64(nf4), self.emb, ctypes.c_int64(ed), ctypes.c_float(1.0),
+           self._pgrad(lin0.weight), ctypes.c_int64(ed))
+        self._call('indm_colsum', d_pre0, L.DTYPE_F32, ctypes.c_int64(1), ctypes.c_int64(N), nf4, ctypes.c_int64(nf4), None, ctypes.c_int64(0),
+                   self._pgrad(lin0.bias), ctypes.c_float(1.0))
+
+    def build_backward(self, train=False):
+        """emit the backward plan: input-VJP only (train=False: likelihood / Hutchinson) or input-VJP + every parameter
+        gradient (train=True: losses.get_step_fn)"""
+        if self._plans.get(train) is not None:
+            self.bops = self._plans[train]['ops']
+            self.gout, self.gx = self._plans[train]['gout'], self._plans[train]['gx']
+            return
+        self._train = bool(train)
+        self._grads, self._gwritten, self._gnb_slots, self._pgrad_ptrs, self._scratch_zero = {}, set(), 0, [], []
+        self.gnb_part_all = self._alloc((2 * len(self.tape) + 4, self.N, 32, 2), zero=True)
+        if train:
+            self.d_dense_tab = self._alloc((self.N, self.dense_total), zero=True)
+        self._cur = bops = []
+        part, scratch, ddt = self.gnb_part_all, self._scratch_zero, (self.d_dense_tab if train else None)
+
+        def zero_bwd_state():
             part.zero_()
-        bops.append(zero_bwd_stats)
+            if ddt is not None:
+                ddt.zero_()
+            for t in scratch:
+                t.zero_()
+        bops.append(zero_bwd_state)
         try:
             for kind, rec in reversed(self.tape):
                 getattr(self, '_bwd_' + kind)(rec)
         finally:
             self._cur = self.ops
+        self._plans[train] = dict(ops=bops, gout=self.gout, gx=self.gx, pgrads=self._pgrad_ptrs)
         self.bops = bops
         self._weights_version = None      # new weight packs were registered: repack on next use
 
     def _bwd_pyramid(self, r):
         raise NotImplementedError('backward through the FIR input pyramid (VE configs) is not built yet')
 
-    def vjp(self, v):
+    def vjp(self, v, train=False):
         """v^T d(out)/d(x_in) for the activations of the last forward()/launch(): [N,C,S,S] fp32 in and out.
-        (`out` includes the per-sample output scale that forward() was given.)"""
-        self.build_backward()
+        (`out` includes the per-sample output scale that forward() was given.)  train=True additionally ACCUMULATES the
+        gradient of <v, out> w.r.t. every parameter into `param.grad` (what `.backward()` does in losses.py:250)."""
+        self.build_backward(train)
+        if train:
+            for prm, ptr in self._plans[True]['pgrads']:
+                if prm.grad is None or prm.grad.data_ptr() != ptr:
+                    raise RuntimeError('indm_b200: a parameter .grad tensor was replaced after the training plan was built '
+                                       '(use optimizer.zero_grad(set_to_none=False) / the fused optimizer of indm_b200.losses)')
         if self._weights_version != self.weights_version():
             self.load_weights()
         self.gout.copy_(v)
@@ -647,7 +785,14 @@ class ScoreEngine:
         for op in self.ops:
             op()
 
-    def forward(self, x, time_cond, out_scale=None):
+    def forward(self, x, time_cond, out_scale=None, train=False, seed=None):
+        """train=True enables the dropout masks (a fresh Philox seed per call unless `seed` is given)"""
+        if train:
+            self._drop_seed = (self._drop_seed * 6364136223846793005 + 1442695040888963407) % (1 << 63) if seed is None else int(seed)
+            self.drop_ctl.copy_(torch.tensor([self._drop_seed, 1], dtype=torch.int64))
+        elif self._drop_on:
+            self.drop_ctl.zero_()
+        self._drop_on = bool(train)
         if x.shape[0] != self.N:
             raise ValueError(f'engine was built for batch {self.N}, got {x.shape[0]}')
         if self._weights_version != self.weights_version():

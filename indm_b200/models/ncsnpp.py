@@ -16,13 +16,14 @@ from .engine import ScoreEngine
 class _EngineFunction(torch.autograd.Function):
     """Bridges the hand-written engine into torch.autograd so the reference's call sites keep working unchanged:
     `torch.autograd.grad(fn_eps, x)` of likelihood.py:32-35 and `.backward()` of losses.py:250 reach `ScoreEngine.vjp`,
-    which replays the explicit backward plan over the activations the forward left in HBM."""
+    which replays the explicit backward plan over the activations the forward left in HBM.  In training the parameter
+    gradients are accumulated by the plan straight into `param.grad` (the `anchor` input only makes autograd call us)."""
 
     @staticmethod
-    def forward(ctx, x, time_cond, scale, net):
+    def forward(ctx, x, time_cond, scale, net, train, anchor):
         eng = net.engine(x.shape[0])
-        out = eng.forward(x.float(), time_cond.float(), scale).clone()
-        ctx.eng, ctx.token = eng, eng.forward_count
+        out = eng.forward(x.float(), time_cond.float(), scale, train=train).clone()
+        ctx.eng, ctx.token, ctx.train, ctx.need_x = eng, eng.forward_count, train, x.requires_grad
         return out
 
     @staticmethod
@@ -31,7 +32,8 @@ class _EngineFunction(torch.autograd.Function):
         if eng.forward_count != ctx.token:
             raise RuntimeError('indm_b200: the engine ran another forward before this backward; activations were overwritten '
                                '(call backward right after the forward it belongs to)')
-        return eng.vjp(grad_out.contiguous().float()).clone(), None, None, None
+        gx = eng.vjp(grad_out.contiguous().float(), train=ctx.train)
+        return (gx.clone() if ctx.need_x else None), None, None, None, None, None
 
 
 @utils.register_model(name='ncsnpp')
@@ -137,9 +139,6 @@ class NCSNpp(nn.Module):
     def forward(self, x, time_cond):
         if not x.is_cuda:
             raise RuntimeError('indm_b200.NCSNpp.forward needs CUDA tensors: there is no CPU / PyTorch fallback path')
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('training-mode forward (dropout + parameter gradients) is not wired to the CUDA engine yet; '
-                                      'call under torch.no_grad() / model.eval()')
         eng = self.engine(x.shape[0])
         scale = None
         if self.config.model.scale_by_sigma:
@@ -148,7 +147,9 @@ class NCSNpp(nn.Module):
             else:
                 used_sigmas = self.sigmas[time_cond.long()].float()
             scale = 1.0 / used_sigmas.float()
-        if torch.is_grad_enabled() and x.requires_grad:
-            return _EngineFunction.apply(x, time_cond, scale, self)
-        out = eng.forward(x.float(), time_cond.float(), scale)
+        if torch.is_grad_enabled():
+            anchor = next((p for p in self.parameters() if p.requires_grad), None) if self.training else None
+            if x.requires_grad or anchor is not None:
+                return _EngineFunction.apply(x, time_cond, scale, self, anchor is not None, anchor)
+        out = eng.forward(x.float(), time_cond.float(), scale, train=self.training)
         return out.clone()

@@ -305,6 +305,79 @@ def make_likelihood():
     np.savez_compressed(os.path.join(HERE, 'likelihood_small_vp.npz'), **out)
 
 
+def _sub(a, limit=4096):
+    """flattened strided subsample (<= limit elements) of a tensor: keeps the fixtures small; tests index the same way"""
+    f = np.ascontiguousarray(a).reshape(-1)
+    return f[::max(1, (f.size + limit - 1) // limit)].copy()
+
+
+def make_train():
+    """One optimisation step of the score network through the reference's losses.get_step_fn (flow.model = 'identity',
+    dropout = 0 so that no mask has to be replayed): raw gradients of every parameter (their norms + a few full tensors),
+    the per-sample losses, and the parameters / EMA after clip + AdamW."""
+    mutils, sde_lib, losses, ema_mod = rl.load('models.utils', 'sde_lib', 'losses', 'models.ema')
+    for tag, path in (('tiny_vp', 'configs/vp/CIFAR10/indm_fid.py'),):
+        cfg = rl.get_config(path)
+        tiny(cfg)
+        cfg.model.dropout = 0.0
+        cfg.flow.model = 'identity'
+        cfg.training.importance_sampling = True
+        model, _ = ref_model(cfg, seed=11)
+        model.train()
+        sde = sde_lib.get_sde(cfg)
+        B, S = 4, cfg.data.image_size
+        rng = np.random.default_rng(61)
+        batch = rng.uniform(-1, 1, size=(B, 3, S, S)).astype(np.float32)
+        u = rng.uniform(size=(B,)).astype(np.float32)
+        z = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+        real = (torch.rand, torch.randn_like)
+
+        def patched():
+            torch.rand = lambda *a, **k: torch.from_numpy(u)
+            torch.randn_like = lambda t, **k: torch.from_numpy(z)
+
+        def restore():
+            torch.rand, torch.randn_like = real
+        # (1) raw gradients
+        loss_fn = losses.get_sde_loss_fn(cfg, sde, train=True)
+        patched()
+        try:
+            ls = loss_fn(model, torch.from_numpy(batch))
+        finally:
+            restore()
+        torch.mean(ls).backward()
+        names = [n for n, p in model.named_parameters() if p.requires_grad]
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
+        gnorm = np.array([float(grads[n].norm()) for n in names], dtype=np.float64)
+        keep = [n for n in names if any(k in n for k in ('all_modules.0.', 'all_modules.1.', 'all_modules.2.', 'all_modules.3.Conv_0.weight',
+                                                          'all_modules.3.Dense_0', 'all_modules.3.GroupNorm_1', 'all_modules.4.NIN_1.W',
+                                                          'all_modules.4.NIN_3', 'all_modules.5.Conv_2.weight'))]
+        out = dict(batch=batch, u=u, z=z, losses_raw=ls.detach().numpy(), grad_norms=gnorm, names=np.array(names), keep=np.array(keep),
+                   total_norm=np.asarray(float(np.sqrt((gnorm ** 2).sum()))), seed=np.asarray(11))
+        for n in keep:
+            out['grad::' + n] = _sub(grads[n].numpy())
+        # (2) the full step on a fresh model
+        model, _ = ref_model(cfg, seed=11)
+        opt = losses.get_optimizer(cfg, model.parameters())
+        ema = ema_mod.ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+        state = dict(optimizer=opt, model=model, ema=ema, step=0)
+        step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+        patched()
+        try:
+            res = step_fn(state, None, torch.from_numpy(batch))
+        finally:
+            restore()
+        out['losses_step'] = res[0].numpy()
+        sd = dict(model.named_parameters())
+        for n in keep:
+            out['param::' + n] = _sub(sd[n].detach().numpy())
+        idx = {n: i for i, n in enumerate(names)}
+        for n in keep:
+            out['ema::' + n] = _sub(ema.shadow_params[idx[n]].numpy())
+        np.savez_compressed(os.path.join(HERE, f'train_{tag}.npz'), **out)
+        print('train', tag, 'losses', out['losses_step'], 'total grad norm', float(out['total_norm']), 'kept', len(keep))
+
+
 def make_vjp():
     """Input vector-Jacobian products of the reference score function (what likelihood.get_div_fn builds through autograd,
     likelihood.py:27-38): J^T eps with Rademacher eps, and the Hutchinson contraction eps^T J eps from the reference's own div_fn."""
@@ -425,7 +498,7 @@ def make_flow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood', 'train']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

@@ -1,0 +1,89 @@
+"""GPU: one optimisation step of the score network through losses.get_step_fn (flow.model='identity') against the live
+reference (tests/golden/train_tiny_vp.npz from tests/golden/make_golden.py:make_train): per-sample losses, the gradient of
+every parameter (norms for all 100+ tensors, sampled elements for one tensor of each kind), and the parameters / EMA after
+global-norm clip + AdamW."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import load_npz, tiny, rel_l2  # noqa: E402
+from indm_b200 import configs, sde_lib, losses  # noqa: E402
+from indm_b200.models import utils as mutils  # noqa: E402
+from indm_b200.models.ema import ExponentialMovingAverage  # noqa: E402
+from oracle import ncsnpp as oncsnpp  # noqa: E402
+
+
+def _sub(a, limit=4096):
+    f = np.ascontiguousarray(a).reshape(-1)
+    return f[::max(1, (f.size + limit - 1) // limit)]
+
+
+def _setup(mode):
+    g = load_npz('train_tiny_vp.npz')
+    cfg = configs.get_config('vp/CIFAR10/indm_fid')
+    tiny(cfg)
+    cfg.model.dropout = 0.0
+    cfg.flow.model = 'identity'
+    cfg.training.importance_sampling = True
+    cfg.device = torch.device('cuda:0')
+    model = mutils.create_model(cfg)
+    model.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(cfg, int(g['seed'])).items()})
+    model.module.compute_mode = mode
+    return g, cfg, model, sde_lib.get_sde(cfg)
+
+
+@pytest.mark.parametrize("mode,tol", [('tf32', 2e-3), ('bf16', 5e-2)])
+def test_parameter_gradients_match_reference(mode, tol):
+    g, cfg, model, sde = _setup(mode)
+    model.train()
+    opt = losses.get_optimizer(cfg, model.parameters())          # re-homes parameters / gradients into flat storage
+    opt.zero_grad()
+    loss_fn = losses.get_sde_loss_fn(cfg, sde, train=True)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    ls = loss_fn(model, cu(g['batch']), draws=dict(u=cu(g['u']), z=cu(g['z'])))
+    torch.mean(ls).backward()
+    torch.cuda.synchronize()
+    e_l = float(np.abs(ls.detach().cpu().numpy() - g['losses_raw']).max() / np.abs(g['losses_raw']).max())
+    named = dict(model.named_parameters())
+    names = [str(n) for n in g['names']]
+    got_norm = np.array([float(named[n].grad.norm()) for n in names])
+    rel = np.abs(got_norm - g['grad_norms']) / (g['grad_norms'] + 1e-3 * g['grad_norms'].max())
+    worst = int(np.argmax(rel))
+    tot = float(np.sqrt((got_norm ** 2).sum()))
+    print(f'{mode}: losses rel {e_l:.2e}; total grad norm {tot:.4f} ref {float(g["total_norm"]):.4f}; worst per-tensor norm rel '
+          f'{rel[worst]:.2e} at {names[worst]}')
+    assert e_l < tol
+    assert abs(tot - float(g['total_norm'])) / float(g['total_norm']) < tol
+    assert rel.max() < 5 * tol, (names[worst], got_norm[worst], g['grad_norms'][worst])
+    for n in [str(k) for k in g['keep']]:
+        e = rel_l2(_sub(named[n].grad.detach().cpu().numpy()), g['grad::' + n])
+        print(f'   grad {n}: rel-L2 {e:.2e}')
+        assert e < 5 * tol, n
+
+
+@pytest.mark.parametrize("mode,tol", [('tf32', 2e-3), ('bf16', 5e-2)])
+def test_step_fn_updates_match_reference(mode, tol):
+    g, cfg, model, sde = _setup(mode)
+    opt = losses.get_optimizer(cfg, model.parameters())
+    ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    state = dict(optimizer=opt, model=model, ema=ema, step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    cu = lambda a: torch.from_numpy(a).cuda()
+    res = step_fn(state, None, cu(g['batch']), draws=dict(u=cu(g['u']), z=cu(g['z'])))
+    torch.cuda.synchronize()
+    assert state['step'] == 1 and len(res) == 5
+    assert float(np.abs(res[0].numpy() - g['losses_step']).max() / np.abs(g['losses_step']).max()) < tol
+    named = dict(model.named_parameters())
+    idx = {n: i for i, (n, p) in enumerate(model.named_parameters())}
+    for n in [str(k) for k in g['keep']]:
+        ref_delta = g['param::' + n] - _sub(before[n].cpu().numpy())
+        got_delta = _sub(named[n].detach().cpu().numpy()) - _sub(before[n].cpu().numpy())
+        # the first AdamW step moves every weight by ~lr * sign(grad): compare the update, not the (dominant) old value
+        e = float(np.linalg.norm(got_delta - ref_delta) / max(np.linalg.norm(ref_delta), 1e-30))
+        e_ema = float(np.abs(_sub(ema.shadow_params[idx[n]].cpu().numpy()) - g['ema::' + n]).max())
+        print(f'   update {n}: rel-L2 of the step {e:.2e}; ema max-abs err {e_ema:.2e}')
+        assert e < 10 * tol, n
+        assert e_ema < 1e-5

@@ -63,8 +63,8 @@ def test_parameter_gradients_match_reference(mode, tol):
         assert e < 5 * tol, n
 
 
-@pytest.mark.parametrize("mode,tol", [('tf32', 2e-3), ('bf16', 5e-2)])
-def test_step_fn_updates_match_reference(mode, tol):
+@pytest.mark.parametrize("mode,tol,step_tol,ema_tol", [('tf32', 2e-3, 2e-2, 1e-4), ('bf16', 5e-2, 0.3, 5e-4)])
+def test_step_fn_updates_match_reference(mode, tol, step_tol, ema_tol):
     g, cfg, model, sde = _setup(mode)
     opt = losses.get_optimizer(cfg, model.parameters())
     ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
@@ -81,9 +81,10 @@ def test_step_fn_updates_match_reference(mode, tol):
     for n in [str(k) for k in g['keep']]:
         ref_delta = g['param::' + n] - _sub(before[n].cpu().numpy())
         got_delta = _sub(named[n].detach().cpu().numpy()) - _sub(before[n].cpu().numpy())
-        # the first AdamW step moves every weight by ~lr * sign(grad): compare the update, not the (dominant) old value
+        # the first AdamW step moves every weight by ~lr * sign(grad): compare the update, not the (dominant) old value.  Elements
+        # whose gradient is ~0 can flip sign under rounding-level gradient differences, each contributing 2 lr to the error.
         e = float(np.linalg.norm(got_delta - ref_delta) / max(np.linalg.norm(ref_delta), 1e-30))
         e_ema = float(np.abs(_sub(ema.shadow_params[idx[n]].cpu().numpy()) - g['ema::' + n]).max())
         print(f'   update {n}: rel-L2 of the step {e:.2e}; ema max-abs err {e_ema:.2e}')
-        assert e < 10 * tol, n
-        assert e_ema < 1e-5
+        assert e < step_tol, n
+        assert e_ema < ema_tol

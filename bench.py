@@ -159,6 +159,36 @@ def conv_roofline(net, eng, reps=3):
     return tot_fl / (tot_ms * 1e-3) / 1e12, tot_ms / n_launch, n_launch // reps
 
 
+def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup=3):
+    """Second BASELINE metric (configs[2]): training samples/s of the likelihood-weighted INDM-VP step, 128 images per GPU,
+    data parallel (one NCCL all-reduce of the flat gradient buffer per step).  What one step does: wolf flow forward with the
+    training-mode log-det series and KL (values), score-network train-mode forward (dropout 0.1) + DSM loss + full backward
+    (input and parameter gradients) + global-norm clip + AdamW + EMA.  The flow's parameters are frozen: the flow backward
+    (incl. the second-order Neumann term) is not on the CUDA path yet — stated in the result."""
+    import torch
+    from indm_b200 import configs, losses
+    from indm_b200.models.ema import ExponentialMovingAverage
+    cfg = configs.get_config("vp/CIFAR10/indm_nll")
+    cfg.device = dev
+    cfg.training.freeze_flow = True
+    opt = losses.get_optimizer(cfg, model.parameters())
+    state = dict(optimizer=opt, model=model, ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+    flow_state = dict(model=flow, step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    batch_host = (torch.rand(PER_GPU_BATCH, 3, 32, 32) * 2 - 1).pin_memory()
+
+    def one():
+        b = batch_host.to(dev, non_blocking=True)             # host batch in, four per-sample loss vectors out (like run_lib.train)
+        return step_fn(state, flow_state, b)
+
+    ms, launches = timed(one, steps, warmup)
+    return {"metric": "train_samples_per_sec", "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "per_gpu_batch": PER_GPU_BATCH, "gpu_launches": launches,
+            "config": "vp/CIFAR10/indm_nll flow_step_fn_nll, score network trained (fwd + bwd + clip + AdamW + EMA, dropout 0.1), "
+                      "wolf flow forward + training log-det series evaluated, flow parameters FROZEN (flow backward not built)",
+            "dtype": "bf16"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,6 +265,7 @@ def run_ours(args):
     ms_step, launches = timed(step_resident, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    train = train_throughput(cfg, model, flow, sde, dev, world, timed)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -262,6 +293,7 @@ def run_ours(args):
                      "launches_per_forward": n_ig, "avg_launch_ms": ms_launch,
                      "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD},
     }
+    out["train"] = train
     if world == 1:
         v, sample = cpu_sample(os.cpu_count() or 1, n_pc=2, batch=16)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}

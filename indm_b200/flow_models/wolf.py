@@ -270,7 +270,7 @@ class WolfCore(nn.Module):
         return e
 
     def forward(self, data, y=None, n_bits=8, nsamples=1, reverse=False, eval_logdet=True, *, eps=None, h=None, seed=0,
-                atol=1e-5, rtol=1e-5, vareps=None, n_terms=None):
+                atol=1e-5, rtol=1e-5, vareps=None, n_terms=None, estimator=None):
         """wolf.py:81-130.  reverse=True: sample h from the prior (or use `eps` / `h` if given) and invert the flow.
         reverse=False: h ~ q(h|x) (posterior encoder; `eps` = the reparameterisation noise, `h` overrides it), then the
         residual-flow forward; with eval_logdet the power-series log-det of every block and the KL term are returned as
@@ -288,14 +288,16 @@ class WolfCore(nn.Module):
             raise NotImplementedError('flow.train_k = 1 in every INDM config')
         if self.training:
             raise NotImplementedError('training-mode flow forward (batch-statistics BatchNorm in the posterior encoder, '
-                                      'differentiable Neumann estimator) is not on the CUDA path yet: call flow_model.eval()')
+                                      'differentiable Neumann estimator) is not on the CUDA path yet: call flow_model.eval() '
+                                      "(estimator='train' selects the training-mode series: 2 exact terms, Neumann form)")
         kl = None
         if h is None:
             self._draws += 1
             h, kl = eng.posterior(data, eps=eps, seed=seed, offset=self._draws)
         if not eval_logdet:
             return eng.forward_map(data, h)
-        z, logpx = eng.forward_logdet(data, h, vareps=vareps, n_terms=n_terms, training=False, seed=seed, offset=self._draws)
+        z, logpx = eng.forward_logdet(data, h, vareps=vareps, n_terms=n_terms, training=(estimator == 'train'), seed=seed,
+                                      offset=self._draws)
         loss = -logpx                       # wolf.py:126-128: loss = -logdet - kl with logdet = logpx = -(sum of block log-dets)
         if kl is not None:
             loss = loss - kl

@@ -235,7 +235,8 @@ def get_step_fn(config, sde, train, optimize_fn=None, scaler=None):
         for k in range(nmb):
             sl = slice(batch_size // nmb * k, batch_size // nmb * (k + 1))
             with torch.no_grad():
-                latent, losses_flow = flow_forward(config, flow_model, batch[sl], reverse=False)
+                # the series the reference's training step evaluates (n + 2 terms, Neumann form, iresblock.py:114-121)
+                latent, losses_flow = flow_forward(config, flow_model, batch[sl], reverse=False, estimator='train')
             if fid_variant:
                 losses_score = loss_fn(model, latent, st=config.training.st, recon_loss=False, **kw)
             else:

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), where the reference uses single-process nn.DataParallel
+(models/utils.py:93, flow_models/flow_model.py:109).
+
+  * sampling / likelihood evaluation shard by image: every rank owns a contiguous slice of the global batch and runs its own
+    CUDA graph; there is no data-path collective.  The Langevin corrector's batch-mean norms
+    (sampling.py:286-288) can optionally be made global with a 2-float all-reduce (`allreduce_langevin_norms`).
+  * training is data parallel: gradients accumulated by the engine into one flat buffer are summed with ONE all-reduce (NCCL over
+    NVLink on GPUs, gloo on CPU in the tests) and divided by the world size before the global-norm clip (losses.FusedAdamW.step).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(total, rank=None, world_size=None):
+    """[start, stop) of this rank's contiguous slice of a global batch of `total` items; earlier ranks take the remainder"""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(int(total), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_batch(x, rank=None, world_size=None):
+    a, b = shard_range(x.shape[0], rank, world_size)
+    return x[a:b]
+
+
+def allreduce_mean_(flat, group=None):
+    """in-place mean over ranks of a flat gradient buffer (the data-parallel exchange step)"""
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(ws)
+    return flat
+
+
+def allreduce_langevin_norms(norm_sums, counts, group=None):
+    """global batch means of the per-sample gradient / noise norms: `norm_sums` [2] = local sums of |s_n| and |z_n|, `counts` =
+    local batch size; returns the two global means (makes a sharded Langevin trajectory identical to the single-batch one)"""
+    buf = torch.cat([norm_sums.reshape(2).double(), torch.tensor([float(counts)], dtype=torch.float64, device=norm_sums.device)])
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return (buf[:2] / buf[2]).float()
+
+
+def gather_cat(x, group=None):
+    """concatenate per-rank tensors along dim 0 on every rank (logging / evaluation only)"""
+    _, ws = world()
+    if ws == 1:
+        return x
+    sizes = [torch.zeros(1, dtype=torch.int64, device=x.device) for _ in range(ws)]
+    dist.all_gather(sizes, torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device), group=group)
+    mx = int(max(int(s) for s in sizes))
+    pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    pad[:x.shape[0]] = x
+    outs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:int(s)] for o, s in zip(outs, sizes)], dim=0)

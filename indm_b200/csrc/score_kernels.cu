@@ -42,10 +42,19 @@ __global__ void gn_stats_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
   }
   float s = 0.f, ss = 0.f;
   if (rr < R) {
-    for (long long p = p0 + rr; p < p1; p += R) {
-      const float4 v = Vec4<TIn>::load(src + p * ld);
-      s += (v.x + v.y) + (v.z + v.w);
-      ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    // 4 independent 16-byte loads in flight per thread (HBM latency x bandwidth needs ~40 KB in flight per SM)
+    for (long long p = p0 + rr; p < p1; p += 4LL * R) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = p + (long long)u * R;
+        v[u] = pp < p1 ? Vec4<TIn>::load(src + pp * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        ss += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+      }
     }
     const int g = c / (C / G);
     atomicAdd(&s_sum[g], s);
@@ -128,17 +137,32 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
   } else {
     const long long per = (P + gridDim.x - 1) / gridDim.x;
     const long long p0 = (long long)blockIdx.x * per, p1 = min(P, p0 + per);
-    for (long long p = p0 + rr; p < p1; p += R) {
-      const float4 v = Vec4<TIn>::load(src + p * ld);
-      float4 y = norm(v);
-      if (RES == 0 && dropping) {
-        const float4 k = dropout_scale4(drop_seed, drop_stream, (unsigned long long)((n * P + p) * Q + q), drop_p);
-        y = make_float4(y.x * k.x, y.y * k.y, y.z * k.z, y.w * k.w);
+    if (RES == 0) {
+      // 4 pixels per trip: all loads issued before the first dependent use
+      for (long long p = p0 + rr; p < p1; p += 4LL * R) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long pp = p + (long long)u * R;
+          v[u] = pp < p1 ? Vec4<TIn>::load(src + pp * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long pp = p + (long long)u * R;
+          if (pp >= p1) break;
+          float4 y = norm(v[u]);
+          if (dropping) {
+            const float4 k = dropout_scale4(drop_seed, drop_stream, (unsigned long long)((n * P + pp) * Q + q), drop_p);
+            y = make_float4(y.x * k.x, y.y * k.y, y.z * k.z, y.w * k.w);
+          }
+          Vec4<TOut>::store(out + (n * P + pp) * C + c, y);
+          if (raw) Vec4<TOut>::store(raw + (n * P + pp) * C + c, v[u]);
+        }
       }
-      if (RES == 0) {
-        Vec4<TOut>::store(out + (n * P + p) * C + c, y);
-        if (raw) Vec4<TOut>::store(raw + (n * P + p) * C + c, v);
-      } else {
+    } else {
+      for (long long p = p0 + rr; p < p1; p += R) {
+        const float4 v = Vec4<TIn>::load(src + p * ld);
+        const float4 y = norm(v);
         const int yi = (int)(p / W), xi = (int)(p % W);
         const long long Wo = 2LL * W;
         const long long po = (long long)(2 * yi) * Wo + 2 * xi;

@@ -29,7 +29,8 @@ constexpr int kMaxStages = 8;
 struct IgemmParams {
   // geometry
   int N, H, W;           // image grid of the A operand (plain GEMM: N=1,H=1,W=M)
-  int BW, BH, BN;        // box (pixels) loaded per tile; BW*BH*BN <= 128
+  int BW, BH, BN;        // box (pixels) loaded per tile; BW*BH*BN <= 128; each a power of two
+  int bw_shift, bh_shift;
   int tiles_x, tiles_y;  // tiles along W and H
   int tiles_n, n_tiles;  // tiles along the image dimension; tiles along Cout
   int Cout;
@@ -73,9 +74,9 @@ struct EpiRow {       // one output row (pixel) of the tile
 
 __device__ __forceinline__ EpiRow epi_row(const IgemmParams& p, int r, int n0, int y0, int x0) {
   EpiRow e;
-  const int bw = r % p.BW;
-  const int bh = (r / p.BW) % p.BH;
-  const int bn = r / (p.BW * p.BH);
+  const int bw = r & (p.BW - 1);                       // box extents are powers of two
+  const int bh = (r >> p.bw_shift) & (p.BH - 1);
+  const int bn = r >> (p.bw_shift + p.bh_shift);
   e.n = n0 + bn; e.y = y0 + bh; e.x = x0 + bw;
   e.ok = (bn < p.BN) && (e.n < p.N) && (e.x < p.W) && (e.y < p.H);
   e.pix = ((long long)e.n * p.H + e.y) * p.W + e.x;
@@ -92,11 +93,21 @@ __device__ __forceinline__ float act_apply(int act, float v) {
 //   warp 0      : TMA producer (one elected lane), smem ring of `stages` (A, B) tiles shared by all tiles of the CTA
 //   warp 1      : tcgen05.mma issuer (one elected lane); accumulators double-buffered in TMEM (2 x BLOCK_N columns) so the
 //                 main loop of tile j+1 overlaps the epilogue of tile j
-//   warps 2..5  : epilogue (warp w owns TMEM lanes 32*(w%4)..): tcgen05.ld -> smem transpose (per-warp 4 KB, XOR-swizzled) so
-//                 that every global access is a run of full 128-byte lines -> fused epilogue math -> stores
-//   warps 6, 7  : (TF32 only) hi/lo operand splitter for the error-compensated 3xTF32 product
-template <int BLOCK_N, bool TF32>
-__global__ void __launch_bounds__(TF32 ? 256 : 192, 1)
+//   warps 2..9  : epilogue, 8 warps (4 in TF32 mode): warp w owns TMEM lanes 32*(w%4).. and, of the two warps sharing a lane
+//                 quarter, every other 32-column slab.  tcgen05.ld -> smem transpose (per-warp 4 KB, XOR-swizzled) so that every
+//                 global access is a run of full 128-byte lines -> fused epilogue math -> stores.  (With one epilogue warp per
+//                 scheduler the ~1000-instruction slab body ran at one dependent issue per ~5 cycles and bounded the kernel.)
+//   last 2 warps: (TF32 only) hi/lo operand splitter for the error-compensated 3xTF32 product
+constexpr int epi_warps(bool tf32) { return tf32 ? 4 : 8; }
+constexpr int igemm_threads(bool tf32) { return 64 + 32 * epi_warps(tf32) + (tf32 ? 64 : 0); }
+
+// KIND specialises the epilogue at compile time for the two shapes that carry >90% of the network's output bytes, so their
+// slab body has no feature tests, no dead paths and ~half the instructions:
+//   KIND 1 "conv0": + bias + per-image row bias -> BF16 NHWC, GroupNorm statistics     (ResnetBlockBigGANpp.Conv_0)
+//   KIND 2 "conv1": (+ bias) * scale [+ residual * res_scale] -> FP32 NHWC            (ResnetBlockBigGANpp.Conv_1 [+ Conv_2])
+//   KIND 0: every feature tested at run time.
+template <int BLOCK_N, bool TF32, int KIND>
+__global__ void __launch_bounds__(igemm_threads(TF32), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
   constexpr int KCHUNK = TF32 ? 32 : 64;           // elements per 128-byte swizzle row
@@ -106,6 +117,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   constexpr int NSLAB = BLOCK_N / 32 + (BLOCK_N < 32 ? 1 : 0);
+  constexpr int EPI = epi_warps(TF32);
+  constexpr int SLAB_STEP = EPI / 4;               // warps per TMEM lane quarter
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -113,8 +126,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* sB = smem + (size_t)p.stages * A_BYTES;
   uint8_t* sAlo = sB + (size_t)p.stages * B_BYTES;
   uint8_t* sBlo = sAlo + (TF32 ? (size_t)p.stages * A_BYTES : 0);
-  uint8_t* sStage = sBlo + (TF32 ? (size_t)p.stages * B_BYTES : 0);   // 4 epilogue warps x 4 KB
-  uint64_t* bars = (uint64_t*)(sStage + 4 * 4096);
+  uint8_t* sStage = sBlo + (TF32 ? (size_t)p.stages * B_BYTES : 0);   // one 4 KB transpose buffer per epilogue warp
+  uint64_t* bars = (uint64_t*)(sStage + EPI * 4096);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* split_bar = bars + 2 * kMaxStages;
@@ -145,7 +158,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], 32 * EPI);
     }
     fence_mbar_init();
   }
@@ -242,11 +255,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp >= 6) {
+  } else if (warp >= 2 + EPI) {
     if (TF32) {
       // ================= operand splitter: hi/lo decomposition of each landed stage, elementwise, so the swizzled
       // placement is irrelevant: lo lives at the same offset of the twin buffer
-      const int tt = threadIdx.x - 192;
+      const int tt = threadIdx.x - (64 + 32 * EPI);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -278,8 +291,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ================= epilogue warps 2..5
+    // ================= epilogue warps
+    const bool has_bias = KIND ? true : (p.bias != nullptr);
+    const bool has_rowbias = KIND == 1 ? true : (KIND == 2 ? false : p.rowbias != nullptr);
+    const bool has_res = KIND == 1 ? false : (p.residual != nullptr);
+    const bool has_rowscale = KIND ? false : (p.rowscale != nullptr);
+    const bool has_aux = KIND ? false : (p.aux_cos != nullptr);
+    const int act = KIND ? 0 : p.act;
+    const bool has_mul = KIND ? false : (p.mul != nullptr);
+    const bool st_f32 = KIND == 2 ? true : (KIND == 1 ? false : p.out_f32 != nullptr);
+    const bool st_bf16 = KIND == 1 ? true : (KIND == 2 ? false : p.out_bf16 != nullptr);
+    const bool has_gn = KIND == 1 ? true : (KIND == 2 ? false : p.gn_partial != nullptr);
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;             // which of the SLAB_STEP warps sharing the quarter: takes slabs half, half + SLAB_STEP, ...
     float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * 4096);
     const int chunk = lane & 7, rsub = lane >> 3;  // transposed domain: 4 columns (chunk), rows it*4 + rsub
     const long long hw = (long long)p.H * p.W;
@@ -307,18 +331,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ACC_COLS;
 
+      if (half >= NSLAB) {                       // narrow tile: this warp has no slab, it only releases the buffer
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+      }
 #pragma unroll 1
-      for (int sl = 0; sl < NSLAB; ++sl) {
+      for (int sl = half; sl < NSLAB; sl += SLAB_STEP) {
         uint32_t v[32];
         tmem_ld_32x32(t_addr + (uint32_t)(sl * 32), v);
         tmem_ld_wait();
-        if (sl == NSLAB - 1) {
+        if (sl + SLAB_STEP >= NSLAB) {
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);        // every accumulator column of this buffer has left TMEM
+          mbar_arrive(&tempty_bar[buf]);        // this warp's share of the accumulator buffer has left TMEM
         }
         const int c0 = ncol0 + sl * 32;
         if (c0 >= p.Cout) continue;             // uniform across the CTA
-        const bool direct = (p.out_mode == 1) || (p.out_mode == 2 && c0 >= p.tcol0);
+        const bool direct = KIND ? false : ((p.out_mode == 1) || (p.out_mode == 2 && c0 >= p.tcol0));
         if (direct) {
           if (!ed.ok) continue;
           const float scale = p.scale * (p.rowscale != nullptr ? p.rowscale[ed.n] : 1.0f);
@@ -355,7 +383,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         const int c = c0 + chunk * 4;           // first of this thread's 4 columns
         float gs = 0.f, gq = 0.f;               // GroupNorm partial sums of this thread's 8 rows x 4 columns
-        if (c + 4 <= p.Cout) {
+        if (KIND != 0 || c + 4 <= p.Cout) {
           // ---- fast path: whole 4-column chunk valid.  Phase 1: every load of the 8 rows issued back to back.
           float4 f[8], rb[8], rsd[8];
 #pragma unroll
@@ -363,30 +391,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int r = it * 4 + rsub;
             f[it] = stg[r * 8 + (chunk ^ (r & 7))];
           }
-          if (p.rowbias) {
+          if (has_rowbias) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) rb[it] = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)nsafe[it] * p.rowbias_ld + c));
           }
-          if (p.residual) {
+          if (has_res) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) rsd[it] = *reinterpret_cast<const float4*>(p.residual + pixs[it] * p.res_ld + c);
           }
           float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          if (has_bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
           // Phase 2: math
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float4 x = f[it];
             x.x += bia.x; x.y += bia.y; x.z += bia.z; x.w += bia.w;
-            if (p.rowbias) { x.x += rb[it].x; x.y += rb[it].y; x.z += rb[it].z; x.w += rb[it].w; }
-            const float sc = p.scale * (p.rowscale != nullptr ? p.rowscale[nsafe[it]] : 1.0f);
+            if (has_rowbias) { x.x += rb[it].x; x.y += rb[it].y; x.z += rb[it].z; x.w += rb[it].w; }
+            const float sc = has_rowscale ? p.scale * p.rowscale[nsafe[it]] : p.scale;
             x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
-            if (p.residual) {
+            if (has_res) {
               x.x += p.res_scale * rsd[it].x; x.y += p.res_scale * rsd[it].y; x.z += p.res_scale * rsd[it].z; x.w += p.res_scale * rsd[it].w;
             }
             f[it] = x;
           }
-          if (p.aux_cos) {
+          if (has_aux) {
             // derivative of the Sin activation at the pre-activation value, kept for the VJP chain of the log-det estimators
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -397,14 +425,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.aux_cos + pixs[it] * p.out_ld + c) = make_uint2(pack_bf16x2(cc.x, cc.y), pack_bf16x2(cc.z, cc.w));
             }
           }
-          if (p.act) {
+          if (act) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              f[it].x = act_apply(p.act, f[it].x); f[it].y = act_apply(p.act, f[it].y);
-              f[it].z = act_apply(p.act, f[it].z); f[it].w = act_apply(p.act, f[it].w);
+              f[it].x = act_apply(act, f[it].x); f[it].y = act_apply(act, f[it].y);
+              f[it].z = act_apply(act, f[it].z); f[it].w = act_apply(act, f[it].w);
             }
           }
-          if (p.mul) {
+          if (has_mul) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               float4 m4;
@@ -422,20 +450,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (!((okmask >> it) & 1u)) continue;
-            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + pixs[it] * p.out_ld + c) = f[it];
-            if (p.out_bf16)
+            if (st_f32) *reinterpret_cast<float4*>(p.out_f32 + pixs[it] * p.out_ld + c) = f[it];
+            if (st_bf16)
               *reinterpret_cast<uint2*>(p.out_bf16 + pixs[it] * p.out_ld + c) = make_uint2(pack_bf16x2(f[it].x, f[it].y), pack_bf16x2(f[it].z, f[it].w));
-            if (p.gn_partial) {
-              float4 tq = f[it];
-              if (p.out_bf16 && !p.out_f32) {   // statistics of the values as stored
-                tq.x = __bfloat162float(__float2bfloat16_rn(tq.x)); tq.y = __bfloat162float(__float2bfloat16_rn(tq.y));
-                tq.z = __bfloat162float(__float2bfloat16_rn(tq.z)); tq.w = __bfloat162float(__float2bfloat16_rn(tq.w));
-              }
+            if (has_gn) {
+              // statistics of the fp32 values: the BF16 rounding of the stored copy is zero-mean noise of relative size 2^-9,
+              // i.e. ~1e-6 relative on a group's mean / variance — not worth 64 conversions per slab
+              const float4 tq = f[it];
               gs += (tq.x + tq.y) + (tq.z + tq.w);
               gq += (tq.x * tq.x + tq.y * tq.y) + (tq.z * tq.z + tq.w * tq.w);
             }
           }
-        } else if (c < p.Cout) {
+        } else if (KIND == 0 && c < p.Cout) {
           // ---- ragged last chunk (Cout % 4 != 0): scalar, guarded
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -462,7 +488,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
-        if (p.gn_partial) {
+        if (has_gn) {
           // GroupNorm statistics of the tensor just produced, per (image, group): removes the separate statistics pass over
           // HBM for the GroupNorm that consumes this output (models/layerspp.py:244,277).  All 32 rows of a warp belong to
           // one image (checked on the host); Cout % 32 == 0, so whole slabs only.
@@ -490,13 +516,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BLOCK_N, bool TF32>
+template <int BLOCK_N, bool TF32, int KIND>
 int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2, IgemmParams p,
                  int m_tiles, int n_tiles, cudaStream_t stream) {
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
   const int stage_bytes = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
-  const int overhead = 1024 + 4 * 4096 + (3 * kMaxStages + 6) * 8;
+  const int overhead = 1024 + epi_warps(TF32) * 4096 + (3 * kMaxStages + 6) * 8;
   // one persistent CTA per SM: the smem ring takes what the SM has
   int stages = (220 * 1024 - overhead) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -505,7 +531,7 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
   p.n_tiles = n_tiles;
   const int smem = stages * stage_bytes + overhead;
   static bool configured = false;
-  auto kern = igemm_kernel<BLOCK_N, TF32>;
+  auto kern = igemm_kernel<BLOCK_N, TF32, KIND>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
@@ -516,7 +542,7 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
   }
   const long long total = (long long)m_tiles * n_tiles;
   const int grid = (int)(total < indm_num_sms() ? total : indm_num_sms());
-  kern<<<grid, TF32 ? 256 : 192, smem, stream>>>(a, b, a2, b2, p);
+  kern<<<grid, igemm_threads(TF32), smem, stream>>>(a, b, a2, b2, p);
   INDM_CHECK_LAUNCH("igemm");
   return INDM_OK;
 }
@@ -565,6 +591,9 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     }
   }
   if (d->batched_b) p.BN = 1;  // every tile row must belong to the image whose B matrix is loaded
+  INDM_CHECK_ARG(is_pow2(p.BW) && is_pow2(p.BH), "igemm: internal: box extents must be powers of two");
+  for (p.bw_shift = 0; (1 << p.bw_shift) < p.BW; ++p.bw_shift) {}
+  for (p.bh_shift = 0; (1 << p.bh_shift) < p.BH; ++p.bh_shift) {}
   p.tiles_x = (d->W + p.BW - 1) / p.BW;
   p.tiles_y = d->H / p.BH;
   p.tiles_n = (d->N + p.BN - 1) / p.BN;
@@ -676,9 +705,16 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     tmB2 = tmB;
   }
 
-#define INDM_LAUNCH(BN_)                                                                                \
-  return tf32 ? launch_igemm<BN_, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)               \
-              : launch_igemm<BN_, false>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+  // compile-time epilogue specialisation (see igemm_kernel)
+  int kind = 0;
+  const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
+  if (plain && d->bias && d->rowbias && !d->residual && d->out_bf16 && !d->out_f32 && d->gn_partial && d->scale == 1.0f) kind = 1;
+  if (plain && d->bias && !d->rowbias && d->out_f32 && !d->out_bf16 && !d->gn_partial) kind = 2;
+#define INDM_LAUNCH(BN_)                                                                                  \
+  if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);          \
+  if (kind == 1) return launch_igemm<BN_, false, 1>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
+  if (kind == 2) return launch_igemm<BN_, false, 2>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
+  return launch_igemm<BN_, false, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
   switch (block_n) {
     case 32: INDM_LAUNCH(32);
     case 64: INDM_LAUNCH(64);

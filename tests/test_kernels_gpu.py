@@ -189,9 +189,14 @@ def test_igemm_fused_groupnorm_statistics(S, N):
     L.igemm(dtype=dt, a=dev_op(nhwc(x), dt), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dt), Cout=Cout, taps=9,
             out_bf16=o16, out_ld=Cout, gn_partial=part, gn_cpg=Cout // G, gn_groups=G)
     torch.cuda.synchronize()
-    y = o16.float().cpu().reshape(N, S * S, G, Cout // G).double()
+    # the statistics are those of the fp32 accumulator values (the stored copy is their BF16 rounding: zero-mean noise)
+    y = nhwc(F.conv2d(x.double(), w.double(), padding=1)).reshape(N, S * S, G, Cout // G)
     want = torch.stack([y.sum(dim=(1, 3)), (y * y).sum(dim=(1, 3))], dim=-1)
-    assert rel_l2(part.cpu(), want) < 1e-4
+    assert rel_l2(part.cpu(), want) < 1e-5
+    # and they describe the stored tensor to BF16-rounding accuracy
+    y16 = o16.float().cpu().reshape(N, S * S, G, Cout // G).double()
+    want16 = torch.stack([y16.sum(dim=(1, 3)), (y16 * y16).sum(dim=(1, 3))], dim=-1)
+    assert rel_l2(part.cpu(), want16) < 1e-3
 
 
 @pytest.mark.parametrize("in_dt,out_dt", [(L.DTYPE_F32, L.DTYPE_BF16), (L.DTYPE_BF16, L.DTYPE_BF16), (L.DTYPE_F32, L.DTYPE_TF32)])

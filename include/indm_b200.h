@@ -104,6 +104,10 @@ typedef struct indm_igemm {
   int64_t mul_ld;
   void* aux_cos;         /* optional second output (out_mode 0, layout of out_*, operand dtype): cos(2 pi v) of the value v that
                             enters `act` — the derivative of Sin, kept for the log-det estimators (iresblock.py:253-273) */
+  void* splitk_ws;       /* optional fp32 workspace (splitk_ws_bytes): lets launches with too few output tiles for the chip (4x4 / 8x8
+                            feature maps) split K across CTAs; a finish kernel reduces the partial sums and applies the epilogue.
+                            Bytes needed: up to (#SMs / #tiles) * N*H*W*Cout*4; smaller workspaces just split less. */
+  int64_t splitk_ws_bytes;
 } indm_igemm_t;
 
 int indm_igemm(const indm_igemm_t* desc, void* stream);

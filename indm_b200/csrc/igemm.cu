@@ -37,6 +37,9 @@ struct IgemmParams {
   int taps;              // 1 or 9
   int chunks1, chunks2;  // K chunks in segment 1 (per tap) and segment 2
   int batched_b;         // B third coordinate = image index instead of tap
+  int ksplit;            // >1: split-K — work item t covers K-iteration slice (t % ksplit) of tile t / ksplit and writes raw fp32
+                         // partial sums to out_f32 + slice * split_stride; indm_splitk_finish reduces them and applies the epilogue
+  long long split_stride;
   int stride;            // 1: 3x3 pad 1 (or 1x1);  2: 3x3 stride 2 pad 0 over an A grid of (2H+1) x (2W+1)
   int stages;
   // epilogue
@@ -142,7 +145,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int iters = iters1 + p.chunks2;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BN) * 128u;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -177,10 +180,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int ks = t % p.ksplit, tt = t / p.ksplit;
+        const int nt = tt % p.n_tiles, mt = tt / p.n_tiles;
         const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
         const int ncol0 = nt * BLOCK_N;
-        for (int it = 0; it < iters; ++it) {
+        const int it_begin = (int)((long long)iters * ks / p.ksplit), it_end = (int)((long long)iters * (ks + 1) / p.ksplit);
+        for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
@@ -223,7 +228,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&tempty_bar[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
-        for (int it = 0; it < iters; ++it) {
+        const int ks = t % p.ksplit;
+        const int it_begin = (int)((long long)iters * ks / p.ksplit), it_end = (int)((long long)iters * (ks + 1) / p.ksplit);
+        for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(TF32 ? &split_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)stage * A_BYTES));
@@ -234,7 +241,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t o = (uint64_t)(2 * k);
-              umma_tf32(d_tmem, alo + o, bdesc + o, IDESC, (it | k) != 0);   // small terms first
+              umma_tf32(d_tmem, alo + o, bdesc + o, IDESC, ((it - it_begin) | k) != 0);   // small terms first
               umma_tf32(d_tmem, adesc + o, blo + o, IDESC, 1u);
               umma_tf32(d_tmem, adesc + o, bdesc + o, IDESC, 1u);
             }
@@ -242,7 +249,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
+              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((it - it_begin) | k) != 0);
             }
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
@@ -263,7 +270,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        for (int it = 0; it < iters; ++it) {
+        const int ks = t % p.ksplit;
+        const int it_begin = (int)((long long)iters * ks / p.ksplit), it_end = (int)((long long)iters * (ks + 1) / p.ksplit);
+        for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(&full_bar[stage], phase);
           float4* a = reinterpret_cast<float4*>(sA + (size_t)stage * A_BYTES);
           float4* al = reinterpret_cast<float4*>(sAlo + (size_t)stage * A_BYTES);
@@ -310,9 +319,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int buf = j & 1;
-      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int ks = t % p.ksplit, tt = t / p.ksplit;
+      const int nt = tt % p.n_tiles, mt = tt / p.n_tiles;
       const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
       const int ncol0 = nt * BLOCK_N;
+      float* const out32 = p.out_f32 + (long long)ks * p.split_stride;     // split-K: this slice's partial-sum plane
       // row bookkeeping, once per tile.  Direct domain (NCHW / transposed outputs, coalesced along pixels): row = lane.
       // Transposed domain (NHWC outputs): rows it*4 + rsub, it = 0..7.  Invalid rows load from pixel 0 / image 0 (always
       // valid addresses) so the loads stay branch-free and can all be in flight together; their stores are predicated off.
@@ -450,7 +461,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (!((okmask >> it) & 1u)) continue;
-            if (st_f32) *reinterpret_cast<float4*>(p.out_f32 + pixs[it] * p.out_ld + c) = f[it];
+            if (st_f32) *reinterpret_cast<float4*>(out32 + pixs[it] * p.out_ld + c) = f[it];
             if (st_bf16)
               *reinterpret_cast<uint2*>(p.out_bf16 + pixs[it] * p.out_ld + c) = make_uint2(pack_bf16x2(f[it].x, f[it].y), pack_bf16x2(f[it].z, f[it].w));
             if (has_gn) {
@@ -483,7 +494,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
               x = act_apply(p.act, x);
               if (p.mul) x *= TF32 ? ((const float*)p.mul)[pixs[it] * p.mul_ld + c + k] : __bfloat162float(((const __nv_bfloat16*)p.mul)[pixs[it] * p.mul_ld + c + k]);
-              if (p.out_f32) p.out_f32[pixs[it] * p.out_ld + c + k] = x;
+              if (p.out_f32) out32[pixs[it] * p.out_ld + c + k] = x;
               if (p.out_bf16) p.out_bf16[pixs[it] * p.out_ld + c + k] = __float2bfloat16_rn(x);
             }
           }
@@ -516,6 +527,61 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------- split-K finish: sum the partial planes, apply the epilogue
+// One thread per (pixel, 4-channel quad).  Same arithmetic and the same order of epilogue operations as the GEMM kernel:
+// v = (sum + bias + rowbias[n]) * scale * rowscale[n] + residual * res_scale -> fp32 / bf16 NHWC (+ GroupNorm partial sums).
+__global__ void splitk_finish_kernel(const float* __restrict__ ws, int S, long long M, int Cout, long long hw, const float* __restrict__ bias,
+                                     const float* __restrict__ rowbias, long long rowbias_ld, const float* __restrict__ rowscale,
+                                     float scale, const float* __restrict__ residual, long long res_ld, float res_scale,
+                                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long long out_ld,
+                                     float* __restrict__ gn_partial, int gn_cpg, int gn_groups) {
+  const int Q = Cout >> 2;
+  const long long total = M * Q;
+  const long long plane = M * (long long)Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / Q;
+    const int c = (int)(i % Q) * 4;
+    const long long n = pix / hw;
+    float4 acc = *reinterpret_cast<const float4*>(ws + pix * Cout + c);
+    for (int s = 1; s < S; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + s * plane + pix * Cout + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    if (rowbias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(rowbias + n * rowbias_ld + c));
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    const float sc = scale * (rowscale ? rowscale[n] : 1.0f);
+    acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + pix * res_ld + c);
+      acc.x += res_scale * r.x; acc.y += res_scale * r.y; acc.z += res_scale * r.z; acc.w += res_scale * r.w;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + pix * out_ld + c) = acc;
+    if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + pix * out_ld + c) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    if (gn_partial) {
+      // lanes of one group are adjacent (cpg / 4 of them, a power of two <= 8, never straddling a pixel since Cout % 32 == 0)
+      float gs = (acc.x + acc.y) + (acc.z + acc.w);
+      float gq = (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+      const int cq = gn_cpg >> 2;
+      for (int o = 1; o < cq; o <<= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+      }
+      if (((c >> 2) & (cq - 1)) == 0) {
+        float* dst = gn_partial + (n * gn_groups + c / gn_cpg) * 2;
+        atomicAdd(dst, gs);
+        atomicAdd(dst + 1, gq);
+      }
+    }
+  }
+}
+
 template <int BLOCK_N, bool TF32, int KIND>
 int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2, IgemmParams p,
                  int m_tiles, int n_tiles, cudaStream_t stream) {
@@ -540,7 +606,7 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
     }
     configured = true;
   }
-  const long long total = (long long)m_tiles * n_tiles;
+  const long long total = (long long)m_tiles * n_tiles * p.ksplit;
   const int grid = (int)(total < indm_num_sms() ? total : indm_num_sms());
   kern<<<grid, igemm_threads(TF32), smem, stream>>>(a, b, a2, b2, p);
   INDM_CHECK_LAUNCH("igemm");
@@ -674,6 +740,33 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
       }
     }
   }
+  // split-K for launches with too few output tiles to fill the chip (4x4 / 8x8 feature maps): K-iteration slices of each tile go
+  // to different CTAs with the widest tile, raw partial sums land in the caller's workspace, a finish kernel reduces them
+  p.ksplit = 1;
+  p.split_stride = 0;
+  const long long Mpix = (long long)d->N * d->H * d->W;
+  if (d->splitk_ws && d->block_n == 0 && d->out_mode == 0 && !d->batched_b && !d->aux_cos && !d->mul && d->act == 0 &&
+      d->Cout % 32 == 0 && d->Cout >= 128) {
+    const int sms = indm_num_sms();
+    const int bn = d->Cout % 256 == 0 ? 256 : 128;
+    const long long tiles = (long long)m_tiles * ((d->Cout + bn - 1) / bn);
+    const int iters = p.taps * p.chunks1 + p.chunks2;
+    int ks = (int)(sms / tiles);
+    if (ks > iters / 4) ks = iters / 4;
+    while (ks > 1 && (long long)ks * Mpix * d->Cout * 4 > d->splitk_ws_bytes) --ks;
+    if (tiles * 2 <= sms && ks >= 2) {
+      p.ksplit = ks;
+      p.split_stride = Mpix * d->Cout;
+      block_n = bn;
+      // the GEMM kernel only stores raw partial sums
+      p.bias = p.rowbias = p.residual = p.rowscale = nullptr;
+      p.scale = 1.0f;
+      p.out_f32 = (float*)d->splitk_ws;
+      p.out_bf16 = nullptr;
+      p.out_ld = d->Cout;
+      p.gn_partial = nullptr;
+    }
+  }
   INDM_CHECK_ARG(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "igemm: block_n %d unsupported", block_n);
   const int n_tiles = (d->Cout + block_n - 1) / block_n;
   {
@@ -706,6 +799,23 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   }
 
   // compile-time epilogue specialisation (see igemm_kernel)
+  if (p.ksplit > 1) {
+    int rc = tf32 ? (block_n == 256 ? launch_igemm<256, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+                                    : launch_igemm<128, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream))
+                  : (block_n == 256 ? launch_igemm<256, false, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+                                    : launch_igemm<128, false, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream));
+    if (rc) return rc;
+    const long long work = Mpix * (d->Cout / 4);
+    long long blocks = (work + 255) / 256;
+    const long long cap = (long long)indm_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const float*)d->splitk_ws, p.ksplit, Mpix, d->Cout, (long long)d->H * d->W,
+                                                              d->bias, d->rowbias, d->rowbias_ld, d->rowscale, d->scale, d->residual,
+                                                              d->res_ld, d->res_scale, d->out_f32, (__nv_bfloat16*)d->out_bf16, d->out_ld,
+                                                              d->gn_partial, d->gn_cpg, d->gn_groups);
+    INDM_CHECK_LAUNCH("splitk_finish");
+    return INDM_OK;
+  }
   int kind = 0;
   const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
   if (plain && d->bias && d->rowbias && !d->residual && d->out_bf16 && !d->out_f32 && d->gn_partial && d->scale == 1.0f) kind = 1;

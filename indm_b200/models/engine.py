@@ -45,6 +45,7 @@ class ScoreEngine:
         self.ch = cfg.data.num_channels
         self.nf = cfg.model.nf
         self.fir = bool(cfg.model.fir)
+        self.splitk_ws = torch.empty((16 << 20,), dtype=torch.float32, device=self.dev)   # 64 MB split-K workspace shared by all launches
         self.keep = []            # every tensor the plan points into
         self.ops = []             # list of zero-arg callables (forward plan)
         self.bops = None          # current backward plan, built on first use by build_backward()
@@ -117,6 +118,7 @@ class ScoreEngine:
         d.scale = 1.0
         d.res_scale = 1.0
         d.dtype = self.dt
+        d.splitk_ws, d.splitk_ws_bytes = self.splitk_ws.data_ptr(), self.splitk_ws.numel() * 4
         for k, v in kw.items():
             if isinstance(v, torch.Tensor):
                 v = v.data_ptr()

@@ -45,7 +45,10 @@ class ScoreEngine:
         self.ch = cfg.data.num_channels
         self.nf = cfg.model.nf
         self.fir = bool(cfg.model.fir)
-        self.splitk_ws = torch.empty((16 << 20,), dtype=torch.float32, device=self.dev)   # 64 MB split-K workspace shared by all launches
+        # split-K (indm_igemm_t.splitk_ws) is available for launches with few tiles but measured SLOWER on the 4x4 / 8x8 layers at
+        # batch 128 (two launch floors + 18 MB of partial sums vs one 36-iteration CTA per tile): left off.  Set a workspace
+        # tensor here (e.g. torch.empty(16 << 20, device=...)) to enable it.
+        self.splitk_ws = None
         self.keep = []            # every tensor the plan points into
         self.ops = []             # list of zero-arg callables (forward plan)
         self.bops = None          # current backward plan, built on first use by build_backward()
@@ -118,7 +121,8 @@ class ScoreEngine:
         d.scale = 1.0
         d.res_scale = 1.0
         d.dtype = self.dt
-        d.splitk_ws, d.splitk_ws_bytes = self.splitk_ws.data_ptr(), self.splitk_ws.numel() * 4
+        if self.splitk_ws is not None:
+            d.splitk_ws, d.splitk_ws_bytes = self.splitk_ws.data_ptr(), self.splitk_ws.numel() * 4
         for k, v in kw.items():
             if isinstance(v, torch.Tensor):
                 v = v.data_ptr()

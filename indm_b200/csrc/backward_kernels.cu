@@ -211,6 +211,8 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dp, const TP* __res
 // ---------------------------------------------------------------- batched 2-D transpose  in [B][R][C] -> out [B][C][R]
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int C, long long in_ld, long long in_bs) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ T tile[32][33];
   const long long b = blockIdx.z;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -338,8 +340,8 @@ extern "C" int indm_transpose_batched(const void* in, void* out, int64_t B, int 
   if (in_batch_stride == 0) in_batch_stride = (int64_t)R * in_ld;
   dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)B), block(32, 8);
   if (dtype == INDM_DTYPE_BF16)
-    transpose_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_ld, in_batch_stride);
-  else transpose_kernel<float><<<grid, block, 0, stream>>>((const float*)in, (float*)out, R, C, in_ld, in_batch_stride);
+    indm_launch_pdl(transpose_kernel<__nv_bfloat16>, grid, block, 0, stream, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_ld, in_batch_stride);
+  else indm_launch_pdl(transpose_kernel<float>, grid, block, 0, stream, (const float*)in, (float*)out, R, C, in_ld, in_batch_stride);
   INDM_CHECK_LAUNCH("transpose_batched");
   return INDM_OK;
 }

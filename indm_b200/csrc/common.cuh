@@ -41,6 +41,31 @@ static inline int indm_num_sms() {
   return n;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The forward pass is a serial chain of ~290 short kernels replayed from a CUDA graph; with the programmatic-stream-serialization
+// attribute the NEXT kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while
+// the current kernel drains.  Every kernel launched this way calls pdl_trigger() first and pdl_wait() before its first access to
+// global memory: the wait returns only when the preceding grid has completed and its writes are visible.
+#include <utility>
+template <typename... KArgs, typename... Args>
+static inline void indm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError() (INDM_CHECK_LAUNCH)
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

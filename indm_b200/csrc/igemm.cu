@@ -140,6 +140,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();   // let the next kernel of the chain get scheduled; it waits in its own pdl_wait()
 
   const int iters1 = p.taps * p.chunks1;
   const int iters = iters1 + p.chunks2;
@@ -173,6 +174,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -608,7 +610,7 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
   }
   const long long total = (long long)m_tiles * n_tiles * p.ksplit;
   const int grid = (int)(total < indm_num_sms() ? total : indm_num_sms());
-  kern<<<grid, igemm_threads(TF32), smem, stream>>>(a, b, a2, b2, p);
+  indm_launch_pdl(kern, dim3(grid), dim3(igemm_threads(TF32)), (size_t)smem, stream, a, b, a2, b2, p);
   INDM_CHECK_LAUNCH("igemm");
   return INDM_OK;
 }

@@ -31,6 +31,8 @@ __global__ void predictor_update_kernel(float* __restrict__ x, const float* __re
                                         float* __restrict__ x_mean, const float* __restrict__ coef, int coef_ld,
                                         const int32_t* __restrict__ step, long long total4, uint64_t seed, const uint64_t* __restrict__ seed_dev,
                                         uint32_t off) {
+  pdl_trigger();
+  pdl_wait();
   const int st = step ? *step : 0;
   if (seed_dev) seed = *seed_dev;
   const float a = coef[(long long)st * coef_ld + 0], c = coef[(long long)st * coef_ld + 1], d = coef[(long long)st * coef_ld + 2];
@@ -103,9 +105,15 @@ __global__ void langevin_update_kernel(float* __restrict__ x, const float* __res
   }
 }
 
-__global__ void advance_step_kernel(int32_t* step) { *step += 1; }
+__global__ void advance_step_kernel(int32_t* step) {
+  pdl_trigger();
+  pdl_wait();
+  *step += 1;
+}
 
 __global__ void randn_kernel(float* __restrict__ out, long long n4, long long n, uint64_t seed, uint32_t a, uint32_t b) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = normal4(seed, a, b, (uint64_t)i);
     if (i * 4 + 3 < n) reinterpret_cast<float4*>(out)[i] = v;
@@ -133,7 +141,7 @@ extern "C" int indm_pc_predictor_update(float* x, const float* s, const float* z
   INDM_CHECK_ARG(x && s && coef && N > 0 && D > 0 && coef_ld >= 3, "pc_predictor_update: bad arguments");
   INDM_CHECK_ARG((N * D) % 4 == 0, "pc_predictor_update: N*D must be a multiple of 4");
   const long long total4 = N * D / 4;
-  predictor_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, coef, coef_ld, step, total4, seed, seed_dev,
+  indm_launch_pdl(predictor_update_kernel, dim3(ew_grid(total4)), dim3(256), 0, stream, x, s, z, x_mean, coef, coef_ld, step, total4, seed, seed_dev,
                                                               (uint32_t)rng_offset);
   INDM_CHECK_LAUNCH("pc_predictor_update");
   return INDM_OK;
@@ -171,7 +179,7 @@ extern "C" int indm_langevin_update(float* x, const float* s, const float* z, fl
 
 extern "C" int indm_advance_step(int32_t* step, void* stream_) {
   INDM_CHECK_ARG(step, "advance_step: null");
-  advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(step);
+  indm_launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream_, step);
   INDM_CHECK_LAUNCH("advance_step");
   return INDM_OK;
 }
@@ -187,6 +195,8 @@ extern "C" int indm_randn_f32(float* out, int64_t n, uint64_t seed, uint64_t rng
 namespace {
 __global__ void sched_broadcast_kernel(float* __restrict__ out, long long n, const float* __restrict__ sched, int ld, int col_num,
                                        int col_den, const int32_t* __restrict__ step) {
+  pdl_trigger();
+  pdl_wait();
   const int st = step ? *step : 0;
   float v = sched[(long long)st * ld + col_num];
   if (col_den >= 0) v /= sched[(long long)st * ld + col_den];
@@ -197,7 +207,7 @@ __global__ void sched_broadcast_kernel(float* __restrict__ out, long long n, con
 extern "C" int indm_sched_broadcast(float* out, int64_t n, const float* sched, int ld, int col_num, int col_den, const int32_t* step,
                                     void* stream_) {
   INDM_CHECK_ARG(out && sched && n > 0 && ld > 0 && col_num >= 0, "sched_broadcast: bad arguments");
-  sched_broadcast_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream_>>>(out, n, sched, ld, col_num, col_den, step);
+  indm_launch_pdl(sched_broadcast_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream_, out, n, sched, ld, col_num, col_den, step);
   INDM_CHECK_LAUNCH("sched_broadcast");
   return INDM_OK;
 }

@@ -16,6 +16,9 @@ namespace {
 template <typename TIn>
 __global__ void gn_stats_kernel(const TIn* __restrict__ xa, int Ca, const TIn* __restrict__ xb, int Cb, long long P, int G,
                                 int R, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
+
   __shared__ float s_sum[32], s_sq[32];
   const int C = Ca + Cb;
   const int Q = C >> 2;
@@ -76,6 +79,9 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
                                 typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ out,
                                 typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ raw,
                                 float drop_p, const unsigned long long* __restrict__ drop_ctl, unsigned drop_stream) {
+  pdl_trigger();
+  pdl_wait();
+
   // training-mode dropout after the activation (models/layerspp.py:278): drop_ctl = {seed, enabled} in device memory, so the
   // same launch plan serves eval (enabled = 0) and train forward passes
   const bool dropping = RES == 0 && drop_ctl != nullptr && drop_p > 0.f && drop_ctl[1] != 0ull;
@@ -185,6 +191,9 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
 // ---------------------------------------------------------------- softmax over rows, one warp per row
 template <typename TOut>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, TOut* __restrict__ out, long long rows, int cols, int tf32) {
+  pdl_trigger();
+  pdl_wait();
+
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -207,6 +216,9 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, TOut* __restric
 template <typename TOut>
 __global__ void prep_input_kernel(const float* __restrict__ x, TOut* __restrict__ out, long long N, int C, int HW, int cpad,
                                   float mul, float add, int act, int tf32) {
+  pdl_trigger();
+  pdl_wait();
+
   const long long total = N * HW * cpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cpad);
@@ -227,6 +239,9 @@ __global__ void prep_input_kernel(const float* __restrict__ x, TOut* __restrict_
 __global__ void time_embedding_kernel(const float* __restrict__ time_cond, const float* __restrict__ sched,
                                       const int32_t* __restrict__ step, int sched_ld, int sched_col,
                                       const float* __restrict__ freqs, int kind, long long N, int dim, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+
   const int half = dim >> 1;
   const long long total = N * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -252,6 +267,9 @@ __global__ void time_embedding_kernel(const float* __restrict__ time_cond, const
 template <int KV>  // float4 per lane = K / 128
 __global__ void linear_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                               void* __restrict__ out, long long N, int K, int O, int act_in, int act_out, int out_dtype) {
+  pdl_trigger();
+  pdl_wait();
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + warp;
   if (o >= O) return;
@@ -280,6 +298,9 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
 // any K: lanes stride over k (used for the K = 64 conditioning projections of the flow)
 __global__ void linear_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                                       void* __restrict__ out, long long N, int K, int O, int act_in, int act_out, int out_dtype) {
+  pdl_trigger();
+  pdl_wait();
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + warp;
   if (o >= O) return;
@@ -307,6 +328,9 @@ __global__ void linear_generic_kernel(const float* __restrict__ in, const float*
 template <typename TIn, typename TOut, int MODE>
 __global__ void fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
                                 long long N, int H, int W, int C, float k0, float k1, float k2, float k3) {
+  pdl_trigger();
+  pdl_wait();
+
   constexpr int UP = MODE == 1 ? 2 : 1;
   constexpr int DOWN = MODE == 2 ? 2 : 1;
   constexpr int PAD0 = MODE == 1 ? 2 : (MODE == 2 ? 1 : 2);
@@ -358,9 +382,9 @@ extern "C" int indm_gn_stats(const void* xa, int Ca, const void* xb, int Cb, int
   const GnGeom g = gn_geom(C, P, N);
   dim3 grid(g.splits, (unsigned)N);
   if (in_dtype == INDM_DTYPE_F32)
-    gn_stats_kernel<float><<<grid, g.threads, 0, stream>>>((const float*)xa, Ca, (const float*)xb, Cb, P, G, g.R, partial);
+    indm_launch_pdl(gn_stats_kernel<float>, grid, dim3(g.threads), 0, stream, (const float*)xa, Ca, (const float*)xb, Cb, P, G, g.R, partial);
   else if (in_dtype == INDM_DTYPE_BF16)
-    gn_stats_kernel<__nv_bfloat16><<<grid, g.threads, 0, stream>>>((const __nv_bfloat16*)xa, Ca, (const __nv_bfloat16*)xb, Cb, P,
+    indm_launch_pdl(gn_stats_kernel<__nv_bfloat16>, grid, dim3(g.threads), 0, stream, (const __nv_bfloat16*)xa, Ca, (const __nv_bfloat16*)xb, Cb, P,
                                                                    G, g.R, partial);
   else
     INDM_CHECK_ARG(false, "gn_stats: in_dtype must be F32 or BF16");
@@ -379,11 +403,11 @@ static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64
   dim3 grid(g.splits, (unsigned)N);
 #define GN_ARGS (const TIn*)xa, Ca, (const TIn*)xb, Cb, H, W, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream
   if (resample == 0)
-    gn_apply_kernel<TIn, TOut, 0><<<grid, g.threads, 0, stream>>>(GN_ARGS);
+    indm_launch_pdl(gn_apply_kernel<TIn, TOut, 0>, grid, dim3(g.threads), 0, stream, GN_ARGS);
   else if (resample == 1)
-    gn_apply_kernel<TIn, TOut, 1><<<grid, g.threads, 0, stream>>>(GN_ARGS);
+    indm_launch_pdl(gn_apply_kernel<TIn, TOut, 1>, grid, dim3(g.threads), 0, stream, GN_ARGS);
   else
-    gn_apply_kernel<TIn, TOut, 2><<<grid, g.threads, 0, stream>>>(GN_ARGS);
+    indm_launch_pdl(gn_apply_kernel<TIn, TOut, 2>, grid, dim3(g.threads), 0, stream, GN_ARGS);
 #undef GN_ARGS
   INDM_CHECK_LAUNCH("gn_apply");
   return INDM_OK;
@@ -443,9 +467,9 @@ extern "C" int indm_softmax_rows(const float* s, void* out, int64_t rows, int co
   const long long blocks = (rows + wpb - 1) / wpb;
   INDM_CHECK_ARG(blocks < (1LL << 31), "softmax_rows: too many rows");
   if (out_dtype == INDM_DTYPE_BF16)
-    softmax_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, wpb * 32, 0, stream>>>(s, (__nv_bfloat16*)out, rows, cols, 0);
+    indm_launch_pdl(softmax_rows_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(wpb * 32), 0, stream, s, (__nv_bfloat16*)out, rows, cols, 0);
   else if (out_dtype == INDM_DTYPE_TF32 || out_dtype == INDM_DTYPE_F32)
-    softmax_rows_kernel<float><<<(unsigned)blocks, wpb * 32, 0, stream>>>(s, (float*)out, rows, cols, out_dtype == INDM_DTYPE_TF32);
+    indm_launch_pdl(softmax_rows_kernel<float>, dim3((unsigned)blocks), dim3(wpb * 32), 0, stream, s, (float*)out, rows, cols, out_dtype == INDM_DTYPE_TF32);
   else
     INDM_CHECK_ARG(false, "softmax_rows: bad out_dtype");
   INDM_CHECK_LAUNCH("softmax_rows");
@@ -459,9 +483,9 @@ extern "C" int indm_prep_input(const float* x, void* out, int64_t N, int C, int 
   const long long total = (long long)N * H * W * cpad;
   const int grid = grid_for(total, 256);
   if (out_dtype == INDM_DTYPE_BF16)
-    prep_input_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)out, N, C, H * W, cpad, mul, add, act, 0);
+    indm_launch_pdl(prep_input_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, x, (__nv_bfloat16*)out, N, C, H * W, cpad, mul, add, act, 0);
   else if (out_dtype == INDM_DTYPE_TF32 || out_dtype == INDM_DTYPE_F32)
-    prep_input_kernel<float><<<grid, 256, 0, stream>>>(x, (float*)out, N, C, H * W, cpad, mul, add, act, out_dtype == INDM_DTYPE_TF32);
+    indm_launch_pdl(prep_input_kernel<float>, dim3(grid), dim3(256), 0, stream, x, (float*)out, N, C, H * W, cpad, mul, add, act, out_dtype == INDM_DTYPE_TF32);
   else
     INDM_CHECK_ARG(false, "prep_input: bad out_dtype");
   INDM_CHECK_LAUNCH("prep_input");
@@ -473,7 +497,7 @@ extern "C" int indm_time_embedding(const float* time_cond, const float* sched, c
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG((time_cond || sched) && out && N > 0 && dim >= 4 && dim % 2 == 0, "time_embedding: bad arguments");
   INDM_CHECK_ARG(kind == 0 || (kind == 1 && freqs), "time_embedding: kind 1 needs freqs");
-  time_embedding_kernel<<<grid_for(N * (dim / 2), 128), 128, 0, stream>>>(time_cond, sched, step, sched_ld, sched_col, freqs, kind,
+  indm_launch_pdl(time_embedding_kernel, dim3(grid_for(N * (dim / 2), 128)), dim3(128), 0, stream, time_cond, sched, step, sched_ld, sched_col, freqs, kind,
                                                                          N, dim, out);
   INDM_CHECK_LAUNCH("time_embedding");
   return INDM_OK;
@@ -491,12 +515,12 @@ extern "C" int indm_linear_f32(const float* in, const float* w, const float* bia
   while ((long long)gx * gy < 2LL * indm_num_sms() && gy < N) gy *= 2;
   dim3 grid(gx, gy);
   if (K % 128 != 0 || K > 1024) {
-    linear_generic_kernel<<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in, act_out, out_dtype);
+    indm_launch_pdl(linear_generic_kernel, grid, dim3(wpb * 32), 0, stream, in, w, bias, out, N, K, O, act_in, act_out, out_dtype);
     INDM_CHECK_LAUNCH("linear");
     return INDM_OK;
   }
   switch (K / 128) {
-#define LIN(KV) case KV: linear_kernel<KV><<<grid, wpb * 32, 0, stream>>>(in, w, bias, out, N, K, O, act_in, act_out, out_dtype); break;
+#define LIN(KV) case KV: indm_launch_pdl(linear_kernel<KV>, grid, dim3(wpb * 32), 0, stream, in, w, bias, out, N, K, O, act_in, act_out, out_dtype); break;
     LIN(1) LIN(2) LIN(3) LIN(4) LIN(5) LIN(6) LIN(7) LIN(8)
 #undef LIN
   }
@@ -512,11 +536,11 @@ static int fir_launch(const void* x, void* y, int64_t N, int H, int W, int C, co
   const long long total = (long long)N * Ho * Wo * (C / 4);
   const int grid = grid_for(total, 256);
   if (mode == 1)
-    fir_nhwc_kernel<TIn, TOut, 1><<<grid, 256, 0, stream>>>((const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 1>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
   else if (mode == 2)
-    fir_nhwc_kernel<TIn, TOut, 2><<<grid, 256, 0, stream>>>((const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 2>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
   else
-    fir_nhwc_kernel<TIn, TOut, 3><<<grid, 256, 0, stream>>>((const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 3>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
   INDM_CHECK_LAUNCH("fir_nhwc");
   return INDM_OK;
 }

@@ -63,7 +63,11 @@ static inline void indm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef INDM_PDL_EARLY_TRIGGER
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
 #endif
 
 // ---------------------------------------------------------------- small device helpers

@@ -323,6 +323,17 @@ int indm_prior_flow(const float* in, float* out, float* logdet, const float* par
  * h = mu + exp(logvar/2) eps and log q(h|x) = -(sum(logvar + eps^2) + 64 log 2pi)/2 (priors/flow.py:236-241). */
 int indm_posterior_sample(const float* c, const float* eps, float* h, float* logq, int64_t N, void* stream);
 
+/* Tap packing for the few-channel 3x3 convolutions of the iResBlock branch (c in {3, 12, 48}; resflow_.py:441-470), so that
+ * they run as ONE 1x1 tensor-core GEMM over 9c packed values instead of nine 64-wide zero-padded taps:
+ *   im2col: out[n,y,x, t*c + ch] = f(x[n, ch, y + s*dy_t, x + s*dx_t]), zero outside the image and for columns >= 9c;
+ *           x NCHW fp32, out NHWC [N,H,W,Kp] in out_dtype, f = Sin if act == 1, s = -1 if flip (transposed convolution).
+ *   col2im: out[n,ch,y,x] = (residual) + scale * (bias[ch] + sum_t in[n, y + s*dy_t, x + s*dx_t, t*c + ch]), then * mul;
+ *           in fp32 NHWC with row stride ld >= 9c; bias / residual / mul (NCHW fp32) optional. */
+int indm_im2col3x3_nchw(const float* x, void* out, int64_t N, int c, int H, int W, int Kp, int flip, int act, int out_dtype,
+                        void* stream);
+int indm_col2im3x3_nchw(const float* in, int64_t ld, const float* bias, const float* residual, const float* mul, float scale, float* out,
+                        int64_t N, int c, int H, int W, int flip, void* stream);
+
 /* y += alpha * x (fp32): the Neumann-series accumulation of iresblock.py:264-270 */
 int indm_axpy_f32(float* y, const float* x, float alpha, int64_t n, void* stream);
 

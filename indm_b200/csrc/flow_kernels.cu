@@ -153,7 +153,92 @@ __global__ void fixed_point_check_kernel(const float* __restrict__ x, const floa
   if ((threadIdx.x & 31) == 0) atomicMax(flag, __float_as_uint(m));
 }
 
+// ---------------------------------------------------------------- tap packing for the few-channel convolutions of the iResBlock
+// The first / last convolution of g touch c in {3, 12, 48} channels (resflow_.py:441-470).  Run as 9-tap implicit GEMMs they
+// would pad c to a 64-wide K chunk per tap (21x wasted MMA work for c = 3).  Instead the 9 taps x c channels are packed into
+// ONE K (or N) dimension of 9c values:
+//   im2col : out[n,y,x, t*c + ch] = f(x[n, ch, y + s*dy_t, x + s*dx_t])   (zero outside the image; f = identity or Sin; s = +-1)
+//            then a 1x1 GEMM with K = 9c is the 3x3 convolution (s = +1) or its transpose (s = -1, weights indexed alike)
+//   col2im : out[n,ch,y,x] = residual + scale * (bias[ch] + sum_t in[n, y + s*dy_t, x + s*dx_t, t*c + ch]) [* mul]
+//            after a 1x1 GEMM with N = 9c: the 3x3 convolution with few OUTPUT channels (s = +1) or its transpose (s = -1)
+template <typename TOut>
+__global__ void im2col3x3_kernel(const float* __restrict__ x, TOut* __restrict__ out, long long N, int c, int H, int W, int Kp, int flip,
+                                 int act) {
+  const long long total = N * H * W * Kp;
+  const int s = flip ? -1 : 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    long long r = i / Kp;
+    const int xx = (int)(r % W);
+    r /= W;
+    const int yy = (int)(r % H);
+    const long long n = r / H;
+    float v = 0.f;
+    if (k < 9 * c) {
+      const int t = k / c, ch = k - t * c;
+      const int sy = yy + s * (t / 3 - 1), sx = xx + s * (t % 3 - 1);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        v = x[((n * c + ch) * H + sy) * W + sx];
+        if (act == 1) v = sinf(6.283185307179586f * v) * 0.15915494309189535f;
+      }
+    }
+    out[i] = (TOut)v;
+  }
+}
+
+__global__ void col2im3x3_kernel(const float* __restrict__ in, long long ld, const float* __restrict__ bias,
+                                 const float* __restrict__ residual, const float* __restrict__ mul, float scale, float* __restrict__ out,
+                                 long long N, int c, int H, int W, int flip) {
+  const long long total = N * c * H * W;
+  const int s = flip ? -1 : 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    long long r = i / W;
+    const int yy = (int)(r % H);
+    r /= H;
+    const int ch = (int)(r % c);
+    const long long n = r / c;
+    float acc = bias ? bias[ch] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int sy = yy + s * (t / 3 - 1), sx = xx + s * (t % 3 - 1);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) acc += in[((n * H + sy) * W + sx) * ld + t * c + ch];
+    }
+    float v = acc * scale;
+    if (residual) v += residual[i];
+    if (mul) v *= mul[i];
+    out[i] = v;
+  }
+}
+
 }  // namespace
+
+extern "C" int indm_im2col3x3_nchw(const float* x, void* out, int64_t N, int c, int H, int W, int Kp, int flip, int act, int out_dtype,
+                                   void* stream_) {
+  INDM_CHECK_ARG(x && out && N > 0 && c > 0 && H > 0 && W > 0 && Kp >= 9 * c, "im2col3x3: bad arguments");
+  const long long total = (long long)N * H * W * Kp;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)indm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (out_dtype == INDM_DTYPE_BF16)
+    im2col3x3_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, (__nv_bfloat16*)out, N, c, H, W, Kp, flip, act);
+  else
+    im2col3x3_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, (float*)out, N, c, H, W, Kp, flip, act);
+  INDM_CHECK_LAUNCH("im2col3x3");
+  return INDM_OK;
+}
+
+extern "C" int indm_col2im3x3_nchw(const float* in, int64_t ld, const float* bias, const float* residual, const float* mul, float scale,
+                                   float* out, int64_t N, int c, int H, int W, int flip, void* stream_) {
+  INDM_CHECK_ARG(in && out && N > 0 && c > 0 && H > 0 && W > 0 && ld >= 9 * c, "col2im3x3: bad arguments");
+  const long long total = (long long)N * c * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)indm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  col2im3x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(in, ld, bias, residual, mul, scale, out, N, c, H, W, flip);
+  INDM_CHECK_LAUNCH("col2im3x3");
+  return INDM_OK;
+}
 
 extern "C" int indm_prior_flow(const float* in, float* out, float* logdet, const float* params, const indm_flow_op_t* ops, int n_ops,
                                float logdet_const, const float* kl_base, int64_t N, void* stream_) {

@@ -322,8 +322,12 @@ class FlowEngine:
         N, idim = self.N, self.idim
         c0, h0, w0 = core.input_shape
         # operand / activation buffers, sized for the largest scale (scale 0) and reused by every block
-        self.cpad = [((c0 * 4 ** s + self.kchunk - 1) // self.kchunk) * self.kchunk for s in range(len(self.nb))]
-        self.a0 = [torch.empty((N, h0 >> s, w0 >> s, self.cpad[s]), device=dev, dtype=self.tdtype) for s in range(len(self.nb))]
+        # tap packing of the few-channel 3x3 convs (csrc/flow_kernels.cu): K (first conv) / N (last conv) = 9 c packed values
+        self.cs = [c0 * 4 ** s for s in range(len(self.nb))]
+        self.kp = [((9 * c + self.kchunk - 1) // self.kchunk) * self.kchunk for c in self.cs]      # im2col row length
+        self.ld9 = [((9 * c + 3) // 4) * 4 for c in self.cs]                                        # col2im row stride
+        self.a0 = [torch.empty((N, h0 >> s, w0 >> s, self.kp[s]), device=dev, dtype=self.tdtype) for s in range(len(self.nb))]
+        self.o9 = [torch.empty((N, h0 >> s, w0 >> s, self.ld9[s]), device=dev) for s in range(len(self.nb))]
         self.u1 = torch.empty((N, h0, w0, idim), device=dev, dtype=self.tdtype)
         self.u2 = torch.empty((N, h0, w0, idim), device=dev, dtype=self.tdtype)
         self.flag = torch.zeros((1,), device=dev)
@@ -338,10 +342,11 @@ class FlowEngine:
         dev, idim = self.dev, self.idim
         for s, b, m in self.blocks:
             c = m.channels
-            cp = self.cpad[s]
-            self.w[(s, b)] = dict(w1=torch.zeros((9, idim, cp), device=dev, dtype=self.tdtype), b1=torch.empty((idim,), device=dev),
-                                  w2=torch.empty((idim, idim), device=dev, dtype=self.tdtype),
-                                  w3=torch.empty((9, c, idim), device=dev, dtype=self.tdtype), b3=torch.empty((c,), device=dev))
+            kp = self.kp[s]
+            z = lambda *shape: torch.zeros(shape, device=dev, dtype=self.tdtype)
+            self.w[(s, b)] = dict(w1=z(idim, kp), b1=torch.empty((idim,), device=dev), w2=z(idim, idim), w3=z(9 * c, idim),
+                                  b3=torch.empty((c,), device=dev),
+                                  w3v=z(idim, kp), w2d=z(idim, idim), w1v=z(9 * c, idim))      # transposed packs for the VJP chain
         nblk = len(self.blocks)
         self.cond_w = torch.empty((nblk * idim, self.core.latent_dim), device=dev)
         self.cond_b = torch.empty((nblk * idim,), device=dev)
@@ -373,13 +378,18 @@ class FlowEngine:
                 w2, sc2 = self._lop(cv2.weight.detach().to(dev, torch.float32))
                 w3, sc3 = self._lop(cv3.weight.detach().to(dev, torch.float32))
                 cv1.scale.copy_(sc1); cv2.scale.copy_(sc2); cv3.scale.copy_(sc3)      # lipschitz.py:353-354
-                co, ci = w1.shape[:2]
-                W['w1'][:, :, :ci].copy_(self._round(w1.permute(2, 3, 0, 1).reshape(9, co, ci)))
+                co, ci = w1.shape[:2]                                         # idim, c
+                # packed index t * c + ch with t = ky * 3 + kx (what im2col / col2im produce)
+                W['w1'][:, :9 * ci].copy_(self._round(w1.permute(0, 2, 3, 1).reshape(co, 9 * ci)))          # [o][t*c+ch]
                 W['b1'].copy_(cv1.bias.detach())
                 w2m = w2.reshape(w2.shape[0], w2.shape[1])
                 W['w2'].copy_(self._round(w2m))
-                W['w3'].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9, w3.shape[0], w3.shape[1])))
+                W['w3'].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9 * ci, co)))                      # [t*c+ch][k]
                 W['b3'].copy_(cv3.bias.detach())
+                # VJP chain: conv3^T = im2col(flip) . w3v^T ; conv2^T ; conv1^T = col2im(flip)(. w1v^T)
+                W['w3v'][:, :9 * ci].copy_(self._round(w3.permute(1, 2, 3, 0).reshape(co, 9 * ci)))         # [k][t*c+ch]
+                W['w2d'].copy_(self._round(w2m.t()))
+                W['w1v'].copy_(self._round(w1.permute(2, 3, 1, 0).reshape(9 * ci, co)))                     # [t*c+ch][k]
                 # conditioning: conv1x1(u + (A h + a)) + b2 = conv1x1(u) + (W2 A) h + (W2 a + b2)   (lipschitz.py:431-435)
                 A = cv2.h_net.net.weight.detach().to(dev, torch.float32)
                 a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
@@ -388,7 +398,6 @@ class FlowEngine:
                 self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
                 self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
             self._pack_prior()
-            self._vjp_weights()
             self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
             if hasattr(self, 'enc'):
                 for job in self.enc['jobs']:
@@ -464,23 +473,28 @@ class FlowEngine:
 
     def _g(self, i, s, m, x_nchw, out, residual, scale):
         """out = scale * g(x; h) + residual, all NCHW fp32 [N, c, H, W] at scale s; block index i selects the cond bias."""
+        self._g_impl(i, s, m, x_nchw, out, residual, scale, None, None)
+
+    def _g_impl(self, i, s, m, x_nchw, out, residual, scale, d1, d2):
         N, idim = self.N, self.idim
         c = m.channels
         _, h0, w0 = self.core.input_shape
         H, Wd = h0 >> s, w0 >> s
         W = self.w[(self.blocks[i][0], self.blocks[i][1])]
-        a0 = self.a0[s]
-        u1 = self.u1.view(-1)[:N * H * Wd * idim].view(N, H, Wd, idim)
-        u2 = self.u2.view(-1)[:N * H * Wd * idim].view(N, H, Wd, idim)
-        L.call('indm_prep_input', L.ptr(x_nchw), L.ptr(a0), N, c, H, Wd, self.cpad[s], ctypes.c_float(1.0), ctypes.c_float(0.0),
-               0 if m.first else 1, self.dt)
-        okw = dict(out_bf16=u1) if self.mode == 'bf16' else dict(out_f32=u1, round_tf32_out=1)
-        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.cpad[s], b=W['w1'], Cout=idim, taps=9, bias=W['b1'], act=1, out_ld=idim, **okw)
-        okw = dict(out_bf16=u2) if self.mode == 'bf16' else dict(out_f32=u2, round_tf32_out=1)
+        a0, o9 = self.a0[s], self.o9[s]
+        n_el = N * H * Wd * idim
+        u1 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim)
+        u2 = self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
+        L.call('indm_im2col3x3_nchw', L.ptr(x_nchw), L.ptr(a0), N, c, H, Wd, self.kp[s], 0, 0 if m.first else 1, self.dt)
+        okw = dict(out_bf16=u1) if self.mode == 'bf16' else dict(out_f32=u1)
+        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.kp[s], b=W['w1'], Cout=idim, taps=1, bias=W['b1'], act=1, out_ld=idim,
+                aux_cos=d1, **okw)
+        okw = dict(out_bf16=u2) if self.mode == 'bf16' else dict(out_f32=u2)
         L.igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
-                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, **okw)
-        L.igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=c, taps=9, bias=W['b3'], scale=scale, residual=residual,
-                res_scale=1.0, out_mode=1, out_f32=out)
+                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, aux_cos=d2, **okw)
+        L.igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s])
+        L.call('indm_col2im3x3_nchw', L.ptr(o9), self.ld9[s], L.ptr(W['b3']), L.ptr(residual), None, ctypes.c_float(scale), L.ptr(out),
+               N, c, H, Wd, 0)
 
     def _ensure(self):
         if self._version != self.version():
@@ -653,48 +667,18 @@ class FlowEngine:
         return h, kl
 
     # ---- power-series log-det (iresblock.py:90-174): VJP chain of g on the tensor cores
-    def _vjp_weights(self):
-        dev, idim = self.dev, self.idim
-        for i, (s, b, m) in enumerate(self.blocks):
-            W = self.w[(s, b)]
-            cp = self.cpad[s]
-            c = m.channels
-            if 'w3d' not in W:
-                W['w3d'] = torch.zeros((9, idim, cp), device=dev, dtype=self.tdtype)
-                W['w2d'] = torch.empty((idim, idim), device=dev, dtype=self.tdtype)
-                W['w1d'] = torch.empty((9, c, idim), device=dev, dtype=self.tdtype)
-            # transposed, tap-flipped packs of the (already Lipschitz-normalised, operand-rounded) forward weights
-            w1 = W['w1'][:, :, :c].float().reshape(3, 3, idim, c)           # [ky][kx][o][ci]
-            W['w1d'].copy_(w1.flip(0, 1).permute(0, 1, 3, 2).reshape(9, c, idim))
-            W['w2d'].copy_(W['w2'].float().t())
-            w3 = W['w3'].float().reshape(3, 3, c, idim)                       # [ky][kx][o=c][ci=idim]
-            W['w3d'][:, :, :c].copy_(w3.flip(0, 1).permute(0, 1, 3, 2).reshape(9, idim, c))
-
     def _g_store(self, i, s, m, x_nchw, out):
         """out = x + g(x; h) (NCHW fp32) keeping cos(2 pi .) of the three Sin pre-activations for the VJP chain"""
         N, idim = self.N, self.idim
-        c = m.channels
         _, h0, w0 = self.core.input_shape
         H, Wd = h0 >> s, w0 >> s
-        W = self.w[(self.blocks[i][0], self.blocks[i][1])]
-        a0 = self.a0[s]
         n_el = N * H * Wd * idim
-        u1, u2 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim), self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
         d1, d2 = self.d1.view(-1)[:n_el].view(N, H, Wd, idim), self.d2.view(-1)[:n_el].view(N, H, Wd, idim)
-        L.call('indm_prep_input', L.ptr(x_nchw), L.ptr(a0), N, c, H, Wd, self.cpad[s], ctypes.c_float(1.0), ctypes.c_float(0.0),
-               0 if m.first else 1, self.dt)
         d0 = None
         if not m.first:
             d0 = self.d0.view(-1)[:x_nchw.numel()].view(x_nchw.shape)
             L.call('indm_cos2pi_f32', L.ptr(x_nchw), L.ptr(d0), x_nchw.numel())
-        okw = dict(out_bf16=u1) if self.mode == 'bf16' else dict(out_f32=u1)
-        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.cpad[s], b=W['w1'], Cout=idim, taps=9, bias=W['b1'], act=1, out_ld=idim,
-                aux_cos=d1, **okw)
-        okw = dict(out_bf16=u2) if self.mode == 'bf16' else dict(out_f32=u2)
-        L.igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
-                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, aux_cos=d2, **okw)
-        L.igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=c, taps=9, bias=W['b3'], scale=1.0, residual=x_nchw,
-                res_scale=1.0, out_mode=1, out_f32=out)
+        self._g_impl(i, s, m, x_nchw, out, x_nchw, 1.0, d1, d2)
         return d0, d1, d2
 
     def _g_vjp(self, i, s, m, v, out, d0, d1, d2):
@@ -704,15 +688,16 @@ class FlowEngine:
         _, h0, w0 = self.core.input_shape
         H, Wd = h0 >> s, w0 >> s
         W = self.w[(self.blocks[i][0], self.blocks[i][1])]
-        a0 = self.a0[s]
+        a0, o9 = self.a0[s], self.o9[s]
         n_el = N * H * Wd * idim
         t1, t2 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim), self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
-        L.call('indm_nchw_to_nhwc', L.ptr(v), None, L.ptr(a0), N, c, H, Wd, self.cpad[s], ctypes.c_float(1.0), self.dt)
+        L.call('indm_im2col3x3_nchw', L.ptr(v), L.ptr(a0), N, c, H, Wd, self.kp[s], 1, 0, self.dt)
         okw = dict(out_bf16=t2) if self.mode == 'bf16' else dict(out_f32=t2)
-        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.cpad[s], b=W['w3d'], Cout=idim, taps=9, out_ld=idim, mul=d2, mul_ld=idim, **okw)
+        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.kp[s], b=W['w3v'], Cout=idim, taps=1, out_ld=idim, mul=d2, mul_ld=idim, **okw)
         okw = dict(out_bf16=t1) if self.mode == 'bf16' else dict(out_f32=t1)
         L.igemm(dtype=self.dt, a=t2, N=N, H=H, W=Wd, Cin=idim, b=W['w2d'], Cout=idim, taps=1, out_ld=idim, mul=d1, mul_ld=idim, **okw)
-        L.igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1d'], Cout=c, taps=9, out_mode=1, out_f32=out, mul=d0)
+        L.igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1v'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s])
+        L.call('indm_col2im3x3_nchw', L.ptr(o9), self.ld9[s], None, None, L.ptr(d0), ctypes.c_float(1.0), L.ptr(out), N, c, H, Wd, 1)
 
     def forward_logdet(self, x, h, vareps=None, n_terms=None, training=False, seed=0, offset=0):
         """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z, logpx [N]) with

@@ -335,6 +335,7 @@ class FlowEngine:
         self.eps = torch.empty((N, core.latent_dim), device=dev)
         self.cond = torch.empty((N, len(self.blocks) * idim), device=dev)
         self.w = {}
+        self._ops, self._bufs = {}, {}
         self._alloc_weights()
 
     # ---- weights
@@ -471,30 +472,79 @@ class FlowEngine:
         L.call('indm_linear_f32', L.ptr(h), L.ptr(self.cond_w), L.ptr(self.cond_b), L.ptr(self.cond), self.N, self.core.latent_dim,
                nblk * self.idim, 0, 0, L.DTYPE_F32)
 
+    # ---- prebuilt launch lists.  The flow passes issue ~1000 small launches per call; building a ctypes descriptor per launch
+    # from Python (~100 us each) cost more than the GPU work, so every (block, buffers) combination is built once and replayed.
+    def _mk_call(self, name, *args):
+        fn = getattr(L.lib(), name)
+        cargs = [ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a for a in args]
+        keep = [a for a in args if isinstance(a, torch.Tensor)]
+
+        def run(fn=fn, cargs=cargs, keep=keep, name=name):
+            L.check(fn(*cargs, L._stream()), name)
+        return run
+
+    def _mk_igemm(self, **kw):
+        d = L.IgemmDesc()
+        d.scale = 1.0
+        d.res_scale = 1.0
+        keep = []
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                keep.append(v)
+                v = v.data_ptr()
+            setattr(d, k, v)
+        lib = L.lib()
+
+        def run(d=d, lib=lib, keep=keep):
+            L.check(lib.indm_igemm(ctypes.byref(d), L._stream()), 'igemm')
+        return run
+
+    def _replay(self, key, builder):
+        ops = self._ops.get(key)
+        if ops is None:
+            ops = builder()
+            self._ops[key] = ops
+        for op in ops:
+            op()
+
+    def _static(self, name, like):
+        """engine-owned buffer with a stable address (launch lists are keyed by data pointers)"""
+        t = self._bufs.get(name)
+        if t is None or t.shape != like.shape:
+            t = torch.empty_like(like)
+            self._bufs[name] = t
+        return t
+
     def _g(self, i, s, m, x_nchw, out, residual, scale):
         """out = scale * g(x; h) + residual, all NCHW fp32 [N, c, H, W] at scale s; block index i selects the cond bias."""
         self._g_impl(i, s, m, x_nchw, out, residual, scale, None, None)
 
     def _g_impl(self, i, s, m, x_nchw, out, residual, scale, d1, d2):
-        N, idim = self.N, self.idim
-        c = m.channels
-        _, h0, w0 = self.core.input_shape
-        H, Wd = h0 >> s, w0 >> s
-        W = self.w[(self.blocks[i][0], self.blocks[i][1])]
-        a0, o9 = self.a0[s], self.o9[s]
-        n_el = N * H * Wd * idim
-        u1 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim)
-        u2 = self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
-        L.call('indm_im2col3x3_nchw', L.ptr(x_nchw), L.ptr(a0), N, c, H, Wd, self.kp[s], 0, 0 if m.first else 1, self.dt)
-        okw = dict(out_bf16=u1) if self.mode == 'bf16' else dict(out_f32=u1)
-        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.kp[s], b=W['w1'], Cout=idim, taps=1, bias=W['b1'], act=1, out_ld=idim,
-                aux_cos=d1, **okw)
-        okw = dict(out_bf16=u2) if self.mode == 'bf16' else dict(out_f32=u2)
-        L.igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
-                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, aux_cos=d2, **okw)
-        L.igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s])
-        L.call('indm_col2im3x3_nchw', L.ptr(o9), self.ld9[s], L.ptr(W['b3']), L.ptr(residual), None, ctypes.c_float(scale), L.ptr(out),
-               N, c, H, Wd, 0)
+        key = ('g', i, x_nchw.data_ptr(), out.data_ptr(), residual.data_ptr() if residual is not None else 0, float(scale),
+               d1.data_ptr() if d1 is not None else 0)
+
+        def build():
+            N, idim = self.N, self.idim
+            c = m.channels
+            _, h0, w0 = self.core.input_shape
+            H, Wd = h0 >> s, w0 >> s
+            W = self.w[(self.blocks[i][0], self.blocks[i][1])]
+            a0, o9 = self.a0[s], self.o9[s]
+            n_el = N * H * Wd * idim
+            u1 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim)
+            u2 = self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
+            ob = (lambda t: dict(out_bf16=t)) if self.mode == 'bf16' else (lambda t: dict(out_f32=t))
+            return [
+                self._mk_call('indm_im2col3x3_nchw', x_nchw, a0, ctypes.c_int64(N), c, H, Wd, self.kp[s], 0, 0 if m.first else 1, self.dt),
+                self._mk_igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.kp[s], b=W['w1'], Cout=idim, taps=1, bias=W['b1'], act=1,
+                               out_ld=idim, aux_cos=d1, **ob(u1)),
+                self._mk_igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
+                               rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, aux_cos=d2, **ob(u2)),
+                self._mk_igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s]),
+                self._mk_call('indm_col2im3x3_nchw', o9, ctypes.c_int64(self.ld9[s]), W['b3'], residual, None, ctypes.c_float(scale), out,
+                              ctypes.c_int64(N), c, H, Wd, 0),
+            ]
+        self._replay(key, build)
 
     def _ensure(self):
         if self._version != self.version():
@@ -532,23 +582,24 @@ class FlowEngine:
             blks = [(b, m) for (ss, b, m) in self.blocks if ss == s]
             for b, m in reversed(blks):
                 i = idx_of[(s, b)]
-                y = x
-                cur = y
-                nxt = torch.empty_like(y)
+                y = self._static(f'inv_y{s}', x)
+                y.copy_(x)
+                ping = [self._static(f'inv_a{s}', x), self._static(f'inv_b{s}', x)]
+                cur, nxt = y, ping[0]
                 it = 0
                 while True:
                     self._g(i, s, m, cur, nxt, y, -1.0)                       # nxt = y - g(cur)
                     L.call('indm_fixed_point_check', L.ptr(nxt), L.ptr(cur), L.ptr(y), y.numel(), ctypes.c_float(atol), ctypes.c_float(rtol),
                            L.ptr(self.flag))
                     conv = float(self.flag.item()) < 1.0
-                    cur, nxt = nxt, (torch.empty_like(y) if cur is y else cur)
+                    cur, nxt = nxt, (ping[1] if cur is y else cur)
                     if conv:
                         break
                     it += 1
                     if it > max_iter:
                         break
                 self.iterations.append(it)
-                x = cur
+                x = cur.clone()
         return x.reshape(shape)
 
     # ---- posterior q(h|x): BN-ResNet encoder -> weight-normed linear -> reparameterisation -> KL against the flow prior
@@ -683,21 +734,29 @@ class FlowEngine:
 
     def _g_vjp(self, i, s, m, v, out, d0, d1, d2):
         """out = J_g(x)^T v for the block whose cos factors are (d0, d1, d2); v, out NCHW fp32"""
-        N, idim = self.N, self.idim
-        c = m.channels
-        _, h0, w0 = self.core.input_shape
-        H, Wd = h0 >> s, w0 >> s
-        W = self.w[(self.blocks[i][0], self.blocks[i][1])]
-        a0, o9 = self.a0[s], self.o9[s]
-        n_el = N * H * Wd * idim
-        t1, t2 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim), self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
-        L.call('indm_im2col3x3_nchw', L.ptr(v), L.ptr(a0), N, c, H, Wd, self.kp[s], 1, 0, self.dt)
-        okw = dict(out_bf16=t2) if self.mode == 'bf16' else dict(out_f32=t2)
-        L.igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.kp[s], b=W['w3v'], Cout=idim, taps=1, out_ld=idim, mul=d2, mul_ld=idim, **okw)
-        okw = dict(out_bf16=t1) if self.mode == 'bf16' else dict(out_f32=t1)
-        L.igemm(dtype=self.dt, a=t2, N=N, H=H, W=Wd, Cin=idim, b=W['w2d'], Cout=idim, taps=1, out_ld=idim, mul=d1, mul_ld=idim, **okw)
-        L.igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1v'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s])
-        L.call('indm_col2im3x3_nchw', L.ptr(o9), self.ld9[s], None, None, L.ptr(d0), ctypes.c_float(1.0), L.ptr(out), N, c, H, Wd, 1)
+        key = ('vjp', i, v.data_ptr(), out.data_ptr(), d0.data_ptr() if d0 is not None else 0, d1.data_ptr(), d2.data_ptr())
+
+        def build():
+            N, idim = self.N, self.idim
+            c = m.channels
+            _, h0, w0 = self.core.input_shape
+            H, Wd = h0 >> s, w0 >> s
+            W = self.w[(self.blocks[i][0], self.blocks[i][1])]
+            a0, o9 = self.a0[s], self.o9[s]
+            n_el = N * H * Wd * idim
+            t1, t2 = self.u1.view(-1)[:n_el].view(N, H, Wd, idim), self.u2.view(-1)[:n_el].view(N, H, Wd, idim)
+            ob = (lambda t: dict(out_bf16=t)) if self.mode == 'bf16' else (lambda t: dict(out_f32=t))
+            return [
+                self._mk_call('indm_im2col3x3_nchw', v, a0, ctypes.c_int64(N), c, H, Wd, self.kp[s], 1, 0, self.dt),
+                self._mk_igemm(dtype=self.dt, a=a0, N=N, H=H, W=Wd, Cin=self.kp[s], b=W['w3v'], Cout=idim, taps=1, out_ld=idim, mul=d2,
+                               mul_ld=idim, **ob(t2)),
+                self._mk_igemm(dtype=self.dt, a=t2, N=N, H=H, W=Wd, Cin=idim, b=W['w2d'], Cout=idim, taps=1, out_ld=idim, mul=d1,
+                               mul_ld=idim, **ob(t1)),
+                self._mk_igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1v'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s]),
+                self._mk_call('indm_col2im3x3_nchw', o9, ctypes.c_int64(self.ld9[s]), None, None, d0, ctypes.c_float(1.0), out,
+                              ctypes.c_int64(N), c, H, Wd, 1),
+            ]
+        self._replay(key, build)
 
     def forward_logdet(self, x, h, vareps=None, n_terms=None, training=False, seed=0, offset=0):
         """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z, logpx [N]) with
@@ -717,20 +776,25 @@ class FlowEngine:
         bi = 0
         self.vjp_count = 0
         for s in range(len(nb)):
+            # engine-owned buffers with stable addresses: the prebuilt launch lists are keyed by data pointers
+            xs = [self._static(f'fx_a{s}', x), self._static(f'fx_b{s}', x)]
+            ve = self._static(f've{s}', x)
+            neumann = self._static(f'neu{s}', x)
+            bufs = [self._static(f'vj_a{s}', x), self._static(f'vj_b{s}', x)]
+            xs[0].copy_(x)
+            cur_x = 0
+            D = x[0].numel()
             for i, (ss, b, m) in enumerate(self.blocks):
                 if ss != s:
                     continue
                 n = int(n_terms[bi]) if n_terms is not None else int(np.random.poisson(self.lamb[i], 1)[0])     # iresblock.py:306
                 K, coef = series_coefficients(n, training, self.lamb[i])
                 if vareps is not None:
-                    ve = vareps[bi].to(self.dev).float().contiguous()
+                    ve.copy_(vareps[bi])
                 else:
-                    ve = torch.empty_like(x)
                     L.call('indm_randn_f32', L.ptr(ve), ve.numel(), seed, 0x7F300000 + (offset << 8) + bi)
-                out = torch.empty_like(x)
-                d0, d1, d2 = self._g_store(i, s, m, x, out)
-                D = x[0].numel()
-                bufs = [torch.empty_like(x), torch.empty_like(x)]
+                xin, xout = xs[cur_x], xs[1 - cur_x]
+                d0, d1, d2 = self._g_store(i, s, m, xin, xout)
                 cur = ve
                 if not training:
                     # basic estimator: sum_k (-1)^(k+1)/k c_k <J^k^T eps, eps>
@@ -742,7 +806,7 @@ class FlowEngine:
                     self.vjp_count += K
                 else:
                     # Neumann estimator (value): w = eps + sum_k (-1)^k c_k J^k^T eps ; logdet = <J^T w, eps>
-                    neumann = ve.clone()
+                    neumann.copy_(ve)
                     for k in range(1, K + 1):
                         nxt = bufs[k & 1]
                         self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
@@ -752,8 +816,9 @@ class FlowEngine:
                     self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
                     L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
                     self.vjp_count += K + 1
-                x = out
+                cur_x = 1 - cur_x
                 bi += 1
+            x = xs[cur_x]
             if s < len(nb) - 1:
                 x = _squeeze2(x).contiguous()
         out = x.reshape(N, -1)
@@ -761,7 +826,7 @@ class FlowEngine:
             out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
         else:
             out = out.view(shape)
-        return out.contiguous(), logpx
+        return out.clone(), logpx                      # the chain lives in engine-owned buffers: hand out a copy
 
     def forward_map(self, x, h):
         """ResidualFlow.fwdpass(x, h, eval_logdet=False) on the flow's own input layout (resflow_.py:310-324)."""
@@ -773,12 +838,15 @@ class FlowEngine:
         self._cond_table(self.h)
         nb = self.nb
         for s in range(len(nb)):
+            xs = [self._static(f'fx_a{s}', x), self._static(f'fx_b{s}', x)]
+            xs[0].copy_(x)
+            cur_x = 0
             for i, (ss, b, m) in enumerate(self.blocks):
                 if ss != s:
                     continue
-                out = torch.empty_like(x)
-                self._g(i, s, m, x, out, x, 1.0)
-                x = out
+                self._g(i, s, m, xs[cur_x], xs[1 - cur_x], xs[cur_x], 1.0)
+                cur_x = 1 - cur_x
+            x = xs[cur_x]
             if s < len(nb) - 1:
                 x = _squeeze2(x).contiguous()
         out = x.reshape(N, -1)
@@ -786,7 +854,7 @@ class FlowEngine:
             out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
         else:
             out = out.view(shape)
-        return out.contiguous()
+        return out.clone()
 
 
 def _squeeze2(x):

@@ -179,7 +179,7 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, TOut* __restrict__
       const int sy = yy + s * (t / 3 - 1), sx = xx + s * (t % 3 - 1);
       if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
         v = x[((n * c + ch) * H + sy) * W + sx];
-        if (act == 1) v = sinf(6.283185307179586f * v) * 0.15915494309189535f;
+        if (act == 1) v = sinpif(2.0f * v) * 0.15915494309189535f;   // sin(2 pi v) / (2 pi), exact range reduction
       }
     }
     out[i] = (TOut)v;

@@ -86,8 +86,22 @@ __device__ __forceinline__ EpiRow epi_row(const IgemmParams& p, int r, int n0, i
   return e;
 }
 
+// sin / cos of 2 pi v.  Production (BF16) path: exact range reduction to [-1/2, 1/2] then the SFU (abs error ~1e-6, far below
+// the BF16 output resolution) — the precise sinf / cosf cost ~20 instructions each and made the flow's 512x512 GEMMs
+// epilogue-bound.  Validation (TF32) path: sinpif / cospif (exact reduction, full precision).
+template <bool PRECISE>
+__device__ __forceinline__ float sin2pi(float v) {
+  if (PRECISE) return sinpif(2.0f * v);
+  return __sinf(6.283185307179586f * (v - rintf(v)));
+}
+template <bool PRECISE>
+__device__ __forceinline__ float cos2pi(float v) {
+  if (PRECISE) return cospif(2.0f * v);
+  return __cosf(6.283185307179586f * (v - rintf(v)));
+}
+template <bool PRECISE>
 __device__ __forceinline__ float act_apply(int act, float v) {
-  if (act == 1) return sinf(6.283185307179586f * v) * 0.15915494309189535f;
+  if (act == 1) return sin2pi<PRECISE>(v) * 0.15915494309189535f;
   if (act == 2) return v > 0.f ? v : expm1f(v);
   return v;
 }
@@ -376,12 +390,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               // NCHW fp32 (network head; flow fixed-point update x <- y - g(x), iresblock.py:78-88)
               const long long o = ((long long)ed.n * p.Cout + c) * hw + li;
               if (p.residual) f += p.res_scale * p.residual[o];
-              f = act_apply(p.act, f);
+              f = act_apply<TF32>(p.act, f);
               if (p.mul) f *= ((const float*)p.mul)[o];
               p.out_f32[o] = f;
             } else {
               // mode 2, columns >= tcol0: transposed per image (bf16)
-              f = act_apply(p.act, f);
+              f = act_apply<TF32>(p.act, f);
               p.out_t[((long long)ed.n * (p.Cout - p.tcol0) + (c - p.tcol0)) * hw + li] = __float2bfloat16_rn(f);
             }
           }
@@ -432,8 +446,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               if (!((okmask >> it) & 1u)) continue;
-              const float4 cc = make_float4(cosf(6.283185307179586f * f[it].x), cosf(6.283185307179586f * f[it].y),
-                                            cosf(6.283185307179586f * f[it].z), cosf(6.283185307179586f * f[it].w));
+              const float4 cc = make_float4(cos2pi<TF32>(f[it].x), cos2pi<TF32>(f[it].y),
+                                            cos2pi<TF32>(f[it].z), cos2pi<TF32>(f[it].w));
               if (TF32) *reinterpret_cast<float4*>((float*)p.aux_cos + pixs[it] * p.out_ld + c) = cc;
               else *reinterpret_cast<uint2*>((__nv_bfloat16*)p.aux_cos + pixs[it] * p.out_ld + c) = make_uint2(pack_bf16x2(cc.x, cc.y), pack_bf16x2(cc.z, cc.w));
             }
@@ -441,8 +455,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (act) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              f[it].x = act_apply(act, f[it].x); f[it].y = act_apply(act, f[it].y);
-              f[it].z = act_apply(act, f[it].z); f[it].w = act_apply(act, f[it].w);
+              f[it].x = act_apply<TF32>(act, f[it].x); f[it].y = act_apply<TF32>(act, f[it].y);
+              f[it].z = act_apply<TF32>(act, f[it].z); f[it].w = act_apply<TF32>(act, f[it].w);
             }
           }
           if (has_mul) {
@@ -491,10 +505,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               x *= sc;
               if (p.residual) x += p.res_scale * p.residual[pixs[it] * p.res_ld + c + k];
               if (p.aux_cos) {
-                if (TF32) ((float*)p.aux_cos)[pixs[it] * p.out_ld + c + k] = cosf(6.283185307179586f * x);
-                else ((__nv_bfloat16*)p.aux_cos)[pixs[it] * p.out_ld + c + k] = __float2bfloat16_rn(cosf(6.283185307179586f * x));
+                if (TF32) ((float*)p.aux_cos)[pixs[it] * p.out_ld + c + k] = cos2pi<TF32>(x);
+                else ((__nv_bfloat16*)p.aux_cos)[pixs[it] * p.out_ld + c + k] = __float2bfloat16_rn(cos2pi<TF32>(x));
               }
-              x = act_apply(p.act, x);
+              x = act_apply<TF32>(p.act, x);
               if (p.mul) x *= TF32 ? ((const float*)p.mul)[pixs[it] * p.mul_ld + c + k] : __bfloat162float(((const __nv_bfloat16*)p.mul)[pixs[it] * p.mul_ld + c + k]);
               if (p.out_f32) out32[pixs[it] * p.out_ld + c + k] = x;
               if (p.out_bf16) p.out_bf16[pixs[it] * p.out_ld + c + k] = __float2bfloat16_rn(x);

@@ -460,17 +460,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           if (has_mul) {
+            // all 8 multiplier loads issued before the first use (each is an L2 / HBM round trip)
+            if (TF32) {
+              float4 m4[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              float4 m4;
-              if (TF32) m4 = *reinterpret_cast<const float4*>((const float*)p.mul + pixs[it] * p.mul_ld + c);
-              else {
-                const uint2 raw = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)p.mul + pixs[it] * p.mul_ld + c);
-                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-                m4 = make_float4(m01.x, m01.y, m23.x, m23.y);
+              for (int it = 0; it < 8; ++it) m4[it] = *reinterpret_cast<const float4*>((const float*)p.mul + pixs[it] * p.mul_ld + c);
+#pragma unroll
+              for (int it = 0; it < 8; ++it) { f[it].x *= m4[it].x; f[it].y *= m4[it].y; f[it].z *= m4[it].z; f[it].w *= m4[it].w; }
+            } else {
+              uint2 raw[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) raw[it] = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)p.mul + pixs[it] * p.mul_ld + c);
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[it].x));
+                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[it].y));
+                f[it].x *= m01.x; f[it].y *= m01.y; f[it].z *= m23.x; f[it].w *= m23.y;
               }
-              f[it].x *= m4.x; f[it].y *= m4.y; f[it].z *= m4.z; f[it].w *= m4.w;
             }
           }
           // Phase 3: stores (predicated on row validity) — 8 lanes cover one 128-byte (fp32) / 64-byte (bf16) run of a row

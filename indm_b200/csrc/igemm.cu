@@ -364,6 +364,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
 #pragma unroll 1
       for (int sl = half; sl < NSLAB; sl += SLAB_STEP) {
+        const int c0 = ncol0 + sl * 32;
+        const bool direct = KIND ? false : ((p.out_mode == 1) || (p.out_mode == 2 && c0 >= p.tcol0));
+        const int c = c0 + chunk * 4;           // first of this thread's 4 columns in the transposed domain
+        const bool fast = !direct && c0 < p.Cout && (KIND != 0 || c + 4 <= p.Cout);
+        // Prefetch: every global operand of this slab's epilogue (row bias, residual, multiplier) is requested BEFORE the
+        // accumulator leaves TMEM, so the L2 / HBM round trip overlaps tcgen05.ld and the smem transpose.
+        float4 rb[8], rsd[8], mulf[8];
+        uint2 mulh[8];
+        if (fast) {
+          if (has_rowbias) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rb[it] = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)nsafe[it] * p.rowbias_ld + c));
+          }
+          if (has_res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rsd[it] = *reinterpret_cast<const float4*>(p.residual + pixs[it] * p.res_ld + c);
+          }
+          if (has_mul) {
+            if (TF32) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) mulf[it] = *reinterpret_cast<const float4*>((const float*)p.mul + pixs[it] * p.mul_ld + c);
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) mulh[it] = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)p.mul + pixs[it] * p.mul_ld + c);
+            }
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_addr + (uint32_t)(sl * 32), v);
         tmem_ld_wait();
@@ -371,9 +398,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_before();
           mbar_arrive(&tempty_bar[buf]);        // this warp's share of the accumulator buffer has left TMEM
         }
-        const int c0 = ncol0 + sl * 32;
         if (c0 >= p.Cout) continue;             // uniform across the CTA
-        const bool direct = KIND ? false : ((p.out_mode == 1) || (p.out_mode == 2 && c0 >= p.tcol0));
         if (direct) {
           if (!ed.ok) continue;
           const float scale = p.scale * (p.rowscale != nullptr ? p.rowscale[ed.n] : 1.0f);
@@ -408,23 +433,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           stg[lane * 8 + (ch ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * ch]), __uint_as_float(v[4 * ch + 1]),
                                                           __uint_as_float(v[4 * ch + 2]), __uint_as_float(v[4 * ch + 3]));
         __syncwarp();
-        const int c = c0 + chunk * 4;           // first of this thread's 4 columns
         float gs = 0.f, gq = 0.f;               // GroupNorm partial sums of this thread's 8 rows x 4 columns
-        if (KIND != 0 || c + 4 <= p.Cout) {
-          // ---- fast path: whole 4-column chunk valid.  Phase 1: every load of the 8 rows issued back to back.
-          float4 f[8], rb[8], rsd[8];
+        if (fast) {
+          // ---- fast path: whole 4-column chunk valid (global operands were prefetched above)
+          float4 f[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
             f[it] = stg[r * 8 + (chunk ^ (r & 7))];
-          }
-          if (has_rowbias) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) rb[it] = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)nsafe[it] * p.rowbias_ld + c));
-          }
-          if (has_res) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) rsd[it] = *reinterpret_cast<const float4*>(p.residual + pixs[it] * p.res_ld + c);
           }
           float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has_bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
@@ -460,21 +476,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           if (has_mul) {
-            // all 8 multiplier loads issued before the first use (each is an L2 / HBM round trip)
             if (TF32) {
-              float4 m4[8];
 #pragma unroll
-              for (int it = 0; it < 8; ++it) m4[it] = *reinterpret_cast<const float4*>((const float*)p.mul + pixs[it] * p.mul_ld + c);
-#pragma unroll
-              for (int it = 0; it < 8; ++it) { f[it].x *= m4[it].x; f[it].y *= m4[it].y; f[it].z *= m4[it].z; f[it].w *= m4[it].w; }
+              for (int it = 0; it < 8; ++it) { f[it].x *= mulf[it].x; f[it].y *= mulf[it].y; f[it].z *= mulf[it].z; f[it].w *= mulf[it].w; }
             } else {
-              uint2 raw[8];
-#pragma unroll
-              for (int it = 0; it < 8; ++it) raw[it] = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)p.mul + pixs[it] * p.mul_ld + c);
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
-                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[it].x));
-                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[it].y));
+                const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mulh[it].x));
+                const float2 m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mulh[it].y));
                 f[it].x *= m01.x; f[it].y *= m01.y; f[it].z *= m23.x; f[it].w *= m23.y;
               }
             }

@@ -120,8 +120,9 @@ constexpr int igemm_threads(bool tf32) { return 64 + 32 * epi_warps(tf32) + (tf3
 
 // KIND specialises the epilogue at compile time for the two shapes that carry >90% of the network's output bytes, so their
 // slab body has no feature tests, no dead paths and ~half the instructions:
-//   KIND 1 "conv0": + bias + per-image row bias -> BF16 NHWC, GroupNorm statistics     (ResnetBlockBigGANpp.Conv_0)
-//   KIND 2 "conv1": (+ bias) * scale [+ residual * res_scale] -> FP32 NHWC            (ResnetBlockBigGANpp.Conv_1 [+ Conv_2])
+//   KIND 1: BF16 NHWC output ([+ bias] [+ per-image row bias]) * scale [+ GroupNorm statistics]   (Conv_0, q|k|v, P.V, dgrads)
+//   KIND 2: FP32 NHWC output ([+ bias]) * scale [+ residual * res_scale]                         (Conv_1 [+ Conv_2], NIN_3, Q.K^T)
+//   (no activation / cos side output / multiplier / per-image scale / NCHW / ragged-column paths in either)
 //   KIND 0: every feature tested at run time.
 template <int BLOCK_N, bool TF32, int KIND>
 __global__ void __launch_bounds__(igemm_threads(TF32), 1)
@@ -317,8 +318,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ================= epilogue warps
-    const bool has_bias = KIND ? true : (p.bias != nullptr);
-    const bool has_rowbias = KIND == 1 ? true : (KIND == 2 ? false : p.rowbias != nullptr);
+    const bool has_bias = p.bias != nullptr;
+    const bool has_rowbias = KIND == 2 ? false : (p.rowbias != nullptr);
     const bool has_res = KIND == 1 ? false : (p.residual != nullptr);
     const bool has_rowscale = KIND ? false : (p.rowscale != nullptr);
     const bool has_aux = KIND ? false : (p.aux_cos != nullptr);
@@ -326,7 +327,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool has_mul = KIND ? false : (p.mul != nullptr);
     const bool st_f32 = KIND == 2 ? true : (KIND == 1 ? false : p.out_f32 != nullptr);
     const bool st_bf16 = KIND == 1 ? true : (KIND == 2 ? false : p.out_bf16 != nullptr);
-    const bool has_gn = KIND == 1 ? true : (KIND == 2 ? false : p.gn_partial != nullptr);
+    const bool has_gn = KIND == 2 ? false : (p.gn_partial != nullptr);
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;             // which of the SLAB_STEP warps sharing the quarter: takes slabs half, half + SLAB_STEP, ...
     float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * 4096);
@@ -849,8 +850,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   }
   int kind = 0;
   const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
-  if (plain && d->bias && d->rowbias && !d->residual && d->out_bf16 && !d->out_f32 && d->gn_partial && d->scale == 1.0f) kind = 1;
-  if (plain && d->bias && !d->rowbias && d->out_f32 && !d->out_bf16 && !d->gn_partial) kind = 2;
+  if (plain && !d->residual && d->out_bf16 && !d->out_f32) kind = 1;
+  if (plain && !d->rowbias && d->out_f32 && !d->out_bf16 && !d->gn_partial) kind = 2;
 #define INDM_LAUNCH(BN_)                                                                                  \
   if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);          \
   if (kind == 1) return launch_igemm<BN_, false, 1>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \

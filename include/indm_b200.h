@@ -163,7 +163,9 @@ int indm_linear_f32(const float* in, const float* w, const float* bias, void* ou
 
 /* FIR resampling of an NHWC tensor with the separable kernel outer(k1,k1)/sum^2*gain (models/up_or_down_sampling.py:195-257):
  * mode 1: upsample_2d (up 2, pad (2,1), gain 4); mode 2: downsample_2d (down 2, pad (1,1));
- * mode 3: the FIR stage of conv_downsample_2d (up = down = 1, pad (2,2)) -> [H+1, W+1].
+ * mode 3: the FIR stage of conv_downsample_2d (up = down = 1, pad (2,2)) -> [H+1, W+1];
+ * mode 4: its transpose (up = down = 1, pad (1,1)) -> [H-1, W-1] (op/upfirdn2d.py:111-114 g_pad); the transposes of modes 1 / 2
+ * are modes 2 / 1 with the same taps.
  * k1: HOST pointer to the 4 separable taps, already normalised (k/sum(k), times 2 per axis for mode 1). */
 int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N, int H, int W, int C, const float* k1, int mode,
                   void* stream);
@@ -216,6 +218,18 @@ int indm_transpose_batched(const void* in, void* out, int64_t B, int R, int C, i
 /* out NHWC [N,H,W,cpad] (channels >= C zero) = x NCHW fp32 [N,C,H,W] * mul * rowscale[n] (rowscale may be NULL) */
 int indm_nchw_to_nhwc(const float* x, const float* rowscale, void* out, int64_t N, int C, int H, int W, int cpad, float mul,
                       int out_dtype, void* stream);
+
+/* out NCHW fp32 [N,C,H,W] = scale * x[n,y,x,c] for x NHWC fp32 with row stride ld >= C */
+int indm_nhwc_to_nchw_f32(const float* x, int64_t ld, float* out, int64_t N, int C, int H, int W, float scale, void* stream);
+
+/* Backward of the stride-2 VALID 3x3 convolution of the VE input pyramid (models/up_or_down_sampling.py:173-178; forward =
+ * indm_igemm with stride 2): dy [N,H,W,Cout] in `dtype` (BF16 / fp32), w = the nn.Conv2d parameter [Cout,Cin,3,3] fp32.
+ * dgrad: dx fp32 [N,2H+1,2W+1,cin_ld] (channels >= Cin zero) is overwritten; wgrad: dw [Cout,Cin,3,3] fp32 is accumulated into,
+ * x = the forward input [N,2H+1,2W+1,x_ld] in `dtype`.  CUDA-core kernels: these three layers are < 0.1 % of the network. */
+int indm_conv_s2_dgrad(const void* dy, const float* w, float* dx, int dtype, int64_t N, int H, int W, int Cout, int Cin, int cin_ld,
+                       void* stream);
+int indm_conv_s2_wgrad(const void* dy, const void* x, float* dw, int dtype, int64_t N, int H, int W, int Cout, int Cin, int x_ld,
+                       void* stream);
 
 /* out[n] (+)= scale * sum_i a[n][i] * b[n][i], fp32 (the eps^T (J eps) contraction of likelihood.py:36-37) */
 int indm_rowdot_f32(const float* a, const float* b, float* out, int64_t N, int64_t D, float scale, int accumulate, void* stream);

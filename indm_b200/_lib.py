@@ -94,6 +94,9 @@ _SIGS = {
     "indm_transpose_batched": [_vp, _vp, _i64, C.c_int, C.c_int, _i64, _i64, C.c_int, _vp],
     "indm_nchw_to_nhwc": [_vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _f32, C.c_int, _vp],
     "indm_rowdot_f32": [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp],
+    "indm_nhwc_to_nchw_f32": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, C.c_int, _f32, _vp],
+    "indm_conv_s2_dgrad": [_vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_conv_s2_wgrad": [_vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
 }
 EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)
 

@@ -245,6 +245,78 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// ---------------------------------------------------------------- NHWC fp32 [N,H,W,ld] (first C channels) -> NCHW fp32 * scale
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, long long ld, float* __restrict__ out, long long N, int C, int HW,
+                                    float scale) {
+  const long long total = N * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long r = i / HW;
+    const int c = (int)(r % C);
+    const long long n = r / C;
+    out[i] = x[(n * HW + p) * ld + c] * scale;
+  }
+}
+
+// ---------------------------------------------------------------- stride-2 VALID 3x3 convolution (input pyramid) backward
+// The three pyramid convolutions (models/layerspp.py:142-176 -> up_or_down_sampling.py:173-178) are < 0.1 % of the network's
+// FLOPs; their gradients run on the CUDA cores.  Forward: Y[n,y,x,co] = sum X[n,2y+ky,2x+kx,ci] W[co][ci][ky][kx].
+// dgrad: one CTA per input pixel (n,u,v), threads over ci:  dX[n,u,v,ci] = sum_{ky,kx: (u-ky),(v-kx) even, in range} sum_co dY W
+template <typename T>
+__global__ void conv_s2_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int H, int W,
+                                     int Cout, int Cin, int cin_ld) {
+  extern __shared__ float sdy[];                       // up to 4 contributing output pixels x Cout
+  const int AW = 2 * W + 1, AH = 2 * H + 1;
+  long long pix = blockIdx.x;
+  const int v = (int)(pix % AW);
+  pix /= AW;
+  const int u = (int)(pix % AH);
+  const long long n = pix / AH;
+  int taps[4], ntap = 0;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = u - ky;
+    if (yy < 0 || (yy & 1) || (yy >> 1) >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = v - kx;
+      if (xx < 0 || (xx & 1) || (xx >> 1) >= W) continue;
+      const long long src = ((n * H + (yy >> 1)) * W + (xx >> 1)) * Cout;
+      for (int c = threadIdx.x; c < Cout; c += blockDim.x) sdy[ntap * Cout + c] = (float)dy[src + c];
+      taps[ntap++] = ky * 3 + kx;
+    }
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < cin_ld; ci += blockDim.x) {
+    float acc = 0.f;
+    if (ci < Cin) {
+      for (int t = 0; t < ntap; ++t) {
+        const float* wr = w + (long long)ci * 9 + taps[t];
+        const float* d = sdy + t * Cout;
+        for (int co = 0; co < Cout; ++co) acc += d[co] * wr[(long long)co * Cin * 9];
+      }
+    }
+    dx[(((n * AH) + u) * AW + v) * cin_ld + ci] = acc;
+  }
+}
+
+// wgrad: grid (Cout, 9), threads over ci:  dW[co][ci][t] += sum_{n,y,x} dY[n,y,x,co] X[n,2y+ky,2x+kx,ci]
+template <typename T>
+__global__ void conv_s2_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw, long long N, int H, int W,
+                                     int Cout, int Cin, int x_ld) {
+  const int co = blockIdx.x, t = blockIdx.y;
+  const int ky = t / 3, kx = t % 3;
+  const int AW = 2 * W + 1, AH = 2 * H + 1;
+  for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+    float acc = 0.f;
+    for (long long n = 0; n < N; ++n)
+      for (int y = 0; y < H; ++y)
+        for (int xx = 0; xx < W; ++xx) {
+          const float g = (float)dy[((n * H + y) * W + xx) * Cout + co];
+          acc += g * (float)x[((n * AH + 2 * y + ky) * AW + 2 * xx + kx) * x_ld + ci];
+        }
+    atomicAdd(dw + ((long long)co * Cin + ci) * 9 + t, acc);
+  }
+}
+
 // ---------------------------------------------------------------- per-sample dot products  out[n] (+)= sum_i a[n][i] * b[n][i]
 __global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long D,
                               float scale, int accumulate) {
@@ -357,6 +429,43 @@ extern "C" int indm_nchw_to_nhwc(const float* x, const float* rowscale, void* ou
   else
     nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>(x, rowscale, (float*)out, N, C, H * W, cpad, mul);
   INDM_CHECK_LAUNCH("nchw_to_nhwc");
+  return INDM_OK;
+}
+
+extern "C" int indm_nhwc_to_nchw_f32(const float* x, int64_t ld, float* out, int64_t N, int C, int H, int W, float scale, void* stream_) {
+  INDM_CHECK_ARG(x && out && N > 0 && C > 0 && ld >= C, "nhwc_to_nchw: bad arguments");
+  const long long total = (long long)N * C * H * W;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(x, ld, out, N, C, H * W, scale);
+  INDM_CHECK_LAUNCH("nhwc_to_nchw");
+  return INDM_OK;
+}
+
+extern "C" int indm_conv_s2_dgrad(const void* dy, const float* w, float* dx, int dtype, int64_t N, int H, int W, int Cout, int Cin,
+                                  int cin_ld, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(dy && w && dx && N > 0 && H > 0 && W > 0 && Cout > 0 && Cin > 0 && cin_ld >= Cin, "conv_s2_dgrad: bad arguments");
+  const long long blocks = (long long)N * (2 * H + 1) * (2 * W + 1);
+  INDM_CHECK_ARG(blocks < (1LL << 31) && 4 * Cout * 4 <= 48 * 1024, "conv_s2_dgrad: problem too large");
+  const int threads = cin_ld >= 256 ? 256 : (cin_ld >= 128 ? 128 : 64);
+  if (dtype == INDM_DTYPE_BF16)
+    conv_s2_dgrad_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 4 * Cout * 4, stream>>>((const __nv_bfloat16*)dy, w, dx, H, W, Cout, Cin, cin_ld);
+  else
+    conv_s2_dgrad_kernel<float><<<(unsigned)blocks, threads, 4 * Cout * 4, stream>>>((const float*)dy, w, dx, H, W, Cout, Cin, cin_ld);
+  INDM_CHECK_LAUNCH("conv_s2_dgrad");
+  return INDM_OK;
+}
+
+extern "C" int indm_conv_s2_wgrad(const void* dy, const void* x, float* dw, int dtype, int64_t N, int H, int W, int Cout, int Cin, int x_ld,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(dy && x && dw && N > 0 && H > 0 && W > 0 && Cout > 0 && Cin > 0 && x_ld >= Cin, "conv_s2_wgrad: bad arguments");
+  dim3 grid((unsigned)Cout, 9);
+  const int threads = Cin >= 256 ? 256 : (Cin >= 128 ? 128 : 64);
+  if (dtype == INDM_DTYPE_BF16)
+    conv_s2_wgrad_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, N, H, W, Cout, Cin, x_ld);
+  else
+    conv_s2_wgrad_kernel<float><<<grid, threads, 0, stream>>>((const float*)dy, (const float*)x, dw, N, H, W, Cout, Cin, x_ld);
+  INDM_CHECK_LAUNCH("conv_s2_wgrad");
   return INDM_OK;
 }
 

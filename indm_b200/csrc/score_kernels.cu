@@ -323,7 +323,7 @@ __global__ void linear_generic_kernel(const float* __restrict__ in, const float*
 }
 
 // ---------------------------------------------------------------- FIR resampling on NHWC (4-tap separable kernel)
-// MODE 1: up x2 pad (2,1); MODE 2: down x2 pad (1,1); MODE 3: up=down=1 pad (2,2).
+// MODE 1: up x2 pad (2,1); MODE 2: down x2 pad (1,1); MODE 3: up=down=1 pad (2,2); MODE 4: up=down=1 pad (1,1) (transpose of 3).
 // out[oy,ox] = sum_{i,j} xp[oy*down + i, ox*down + j] * kf[i][j], kf = flipped k, xp = zero-inserted + padded input.
 template <typename TIn, typename TOut, int MODE>
 __global__ void fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
@@ -333,9 +333,9 @@ __global__ void fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditi
 
   constexpr int UP = MODE == 1 ? 2 : 1;
   constexpr int DOWN = MODE == 2 ? 2 : 1;
-  constexpr int PAD0 = MODE == 1 ? 2 : (MODE == 2 ? 1 : 2);
-  const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : H + 1);
-  const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : W + 1);
+  constexpr int PAD0 = MODE == 1 ? 2 : ((MODE == 2 || MODE == 4) ? 1 : 2);
+  const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : (MODE == 4 ? H - 1 : H + 1));
+  const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : (MODE == 4 ? W - 1 : W + 1));
   const int Q = C >> 2;
   const long long total = N * Ho * Wo * Q;
   const float kf[4] = {k3, k2, k1, k0};  // flipped
@@ -531,16 +531,18 @@ extern "C" int indm_linear_f32(const float* in, const float* w, const float* bia
 template <typename TIn, typename TOut>
 static int fir_launch(const void* x, void* y, int64_t N, int H, int W, int C, const float* k, int mode, cudaStream_t stream) {
   using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
-  const int Ho = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : H + 1);
-  const int Wo = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : W + 1);
+  const int Ho = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : (mode == 4 ? H - 1 : H + 1));
+  const int Wo = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : (mode == 4 ? W - 1 : W + 1));
   const long long total = (long long)N * Ho * Wo * (C / 4);
   const int grid = grid_for(total, 256);
   if (mode == 1)
     indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 1>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
   else if (mode == 2)
     indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 2>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
-  else
+  else if (mode == 3)
     indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 3>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+  else
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 4>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
   INDM_CHECK_LAUNCH("fir_nhwc");
   return INDM_OK;
 }
@@ -549,7 +551,8 @@ extern "C" int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out
                              int mode, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   INDM_CHECK_ARG(x && y && k1 && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "fir_nhwc: bad arguments");
-  INDM_CHECK_ARG(mode >= 1 && mode <= 3, "fir_nhwc: mode must be 1 (up), 2 (down) or 3 (pad-only)");
+  INDM_CHECK_ARG(mode >= 1 && mode <= 4, "fir_nhwc: mode must be 1 (up), 2 (down), 3 (pad (2,2)) or 4 (pad (1,1))");
+  INDM_CHECK_ARG(mode != 4 || (H > 1 && W > 1), "fir_nhwc: mode 4 needs H, W > 1");
   INDM_CHECK_ARG(mode != 2 || (H % 2 == 0 && W % 2 == 0), "fir_nhwc: down needs even H, W");
   // k1 is a HOST pointer to the 4 separable taps, already normalised (and gain-scaled per axis)
   const bool in_f = dtype_in == INDM_DTYPE_F32 || dtype_in == INDM_DTYPE_TF32, in_b = dtype_in == INDM_DTYPE_BF16;

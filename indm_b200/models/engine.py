@@ -316,7 +316,8 @@ class ScoreEngine:
                 kw.update(residual=xa, res_ld=Cout, res_scale=inv_sqrt2 if rb.skip_rescale else 1.0)
             self._igemm(**kw)
             self.tape.append(('res_block', dict(rb=rb, gn0=gn0, gn1=gn1, out=out, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, has_skip=has_skip,
-                                                h1=h1, h3=h3, raw=raw, dense_off=dense_off[id(rb)],
+                                                h1=h1, h3=h3, raw=raw, dense_off=dense_off[id(rb)], H=H, W=W, resample=resample,
+                                                fir_k1=(k1 if use_fir else None),
                                                 use_fir=use_fir, s=inv_sqrt2 if rb.skip_rescale else 1.0)))
             return out, Ho, Wo
 
@@ -388,7 +389,8 @@ class ScoreEngine:
             sc = inv_sqrt2 if m.skip_rescale else 1.0
             self._igemm(a=fir_out, N=N, H=Hi // 2, W=Wi // 2, Cin=pyr_c, b=wp, Cout=Cout, taps=9, stride=2, bias=bp, scale=sc,
                         residual=h, res_ld=Cout, res_scale=sc, out_f32=out, out_ld=Cout)
-            self.tape.append(('pyramid', dict()))
+            self.tape.append(('pyramid', dict(ds=ds, pyr=pyr, pyr_c=pyr_c, pyr_dt=pyr_dt, Hi=Hi, Wi=Wi, h=h, Cout=Cout, out=out, sc=sc,
+                                              fir_out=fir_out, k1=k1, first=(pyr is x_nhwc))))
             return out
 
         # the pyramid starts from the network input (after the 2x-1 affine): the padded NHWC operand copy of it
@@ -574,8 +576,6 @@ class ScoreEngine:
     def _bwd_res_block(self, r):
         N, rb = self.N, r['rb']
         Cin, Cout, Ho, Wo = r['Cin'], r['Cout'], r['Ho'], r['Wo']
-        if r['use_fir']:
-            raise NotImplementedError('backward through FIR-resampling res-blocks (VE configs) is not built yet')
         g = self._cast_grad(r['out'], r['s'])                                   # d(out) * 1/sqrt(2), operand dtype
         w1d = self._pack_dgrad(rb.Conv_1.weight)
         d_h3 = self._op_t((N, Ho, Wo, Cout))
@@ -589,7 +589,23 @@ class ScoreEngine:
         w0d = self._pack_dgrad(rb.Conv_0.weight)
         d_h1 = self._op_t((N, Ho, Wo, Cin))
         self._igemm(a=d_h2, N=N, H=Ho, W=Wo, Cin=Cout, b=w0d, Cout=Cin, taps=9, **self._okw(d_h1, Cin))
-        if r['has_skip']:
+        if r['use_fir']:
+            # FIR-resampled block (model.fir=True, models/layerspp.py:256-271): both branches pass through upfirdn2d, whose
+            # transpose is upfirdn2d with up <-> down and the same (symmetric) taps (op/upfirdn2d.py:111-114)
+            op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+            H, W = r['H'], r['W']
+            tmode = 2 if r['resample'] == 1 else 1
+            kptr = r['fir_k1'].ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            d_h1s = self._op_t((N, H, W, Cin))
+            self._call('indm_fir_nhwc', d_h1, d_h1s, op_dt, op_dt, ctypes.c_int64(N), Ho, Wo, Cin, kptr, tmode)
+            w2d = self._pack_dgrad(rb.Conv_2.weight)
+            d_raw = self._alloc((N, Ho, Wo, Cin))
+            self._igemm(a=g, N=N, H=Ho, W=Wo, Cin=Cout, b=w2d, Cout=Cin, taps=1, out_f32=d_raw, out_ld=Cin)
+            self._wgrad(g, Cout, r['raw'], Cin, Ho, Wo, Cout, Cin, 1, rb.Conv_2.weight, strides=(Cin, 1, 0))
+            d_xs = self._alloc((N, H, W, Cin))
+            self._call('indm_fir_nhwc', d_raw, d_xs, L.DTYPE_F32, L.DTYPE_F32, ctypes.c_int64(N), Ho, Wo, Cin, kptr, tmode)
+            self._gn_bwd(r['gn0'], d_h1s, extra_pre=d_xs, extra_scale=1.0)
+        elif r['has_skip']:
             w2d = self._pack_dgrad(rb.Conv_2.weight)
             d_raw = self._alloc((N, Ho, Wo, Cin))
             self._igemm(a=g, N=N, H=Ho, W=Wo, Cin=Cout, b=w2d, Cout=Cin, taps=1, out_f32=d_raw, out_ld=Cin)
@@ -682,7 +698,13 @@ class ScoreEngine:
         g = self._cast_grad(r['h0'], 1.0)
         wsd = self._pack_dgrad(r['conv'].weight)
         self.gx = self._alloc((N, self.ch, S, S))
-        self._igemm(a=g, N=N, H=S, W=S, Cin=self.nf, b=wsd, Cout=self.ch, taps=9, scale=r['mul'], out_mode=1, out_f32=self.gx)
+        kw = {}
+        if getattr(self, '_pyr_gx', None) is not None:
+            # VE: the input pyramid also reads the (affinely rescaled) network input
+            pg = self._alloc((N, self.ch, S, S))
+            self._call('indm_nhwc_to_nchw_f32', self._pyr_gx, ctypes.c_int64(r['cpad']), pg, ctypes.c_int64(N), self.ch, S, S, ctypes.c_float(r['mul']))
+            kw = dict(residual=pg, res_scale=1.0)
+        self._igemm(a=g, N=N, H=S, W=S, Cin=self.nf, b=wsd, Cout=self.ch, taps=9, scale=r['mul'], out_mode=1, out_f32=self.gx, **kw)
         self._wgrad(g, self.nf, r['x_nhwc'], r['cpad'], S, S, self.nf, self.ch, 9, r['conv'].weight)
         self._bgrad(g, S * S, self.nf, self.nf, biases=[r['conv'].bias])
 
@@ -743,6 +765,7 @@ class ScoreEngine:
             return
         self._train = bool(train)
         self._grads, self._gwritten, self._gnb_slots, self._pgrad_ptrs, self._scratch_zero = {}, set(), 0, [], []
+        self._pyr_gx = None
         self.gnb_part_all = self._alloc((2 * len(self.tape) + 4, self.N, 32, 2), zero=True)
         if train:
             self.d_dense_tab = self._alloc((self.N, self.dense_total), zero=True)
@@ -765,8 +788,40 @@ class ScoreEngine:
         self.bops = bops
         self._weights_version = None      # new weight packs were registered: repack on next use
 
+    def _accumulate_into(self, target, src, scale):
+        """grad(target) (+)= scale * src  (fp32 tensors of target's shape)"""
+        g, acc = self._grad_of(target)
+        if acc:
+            self._call('indm_axpy_f32', g, src, ctypes.c_float(scale), ctypes.c_int64(g.numel()))
+        else:
+            self._call('indm_cast_scale', src, g, ctypes.c_int64(g.numel()), ctypes.c_float(scale), L.DTYPE_F32)
+
     def _bwd_pyramid(self, r):
-        raise NotImplementedError('backward through the FIR input pyramid (VE configs) is not built yet')
+        """backward of the progressive_input='residual' combine (models/ncsnpp.py:319-326): out = (conv_s2(FIR(pyr)) + b + h) * sc"""
+        N, Hi, Wi, Cout, pc = self.N, r['Hi'], r['Wi'], r['Cout'], r['pyr_c']
+        Ho, Wo = Hi // 2, Wi // 2
+        ds, sc = r['ds'], r['sc']
+        op_dt = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
+        gout = self._grads[r['out'].data_ptr()]
+        self._accumulate_into(r['h'], gout, sc)                       # the res-block branch
+        g = self._cast_grad(r['out'], sc)
+        cin = ds.Conv2d_0.weight.shape[1]
+        if self._train and ds.Conv2d_0.weight.requires_grad:
+            self._call('indm_conv_s2_wgrad', g, r['fir_out'], self._pgrad(ds.Conv2d_0.weight), op_dt, ctypes.c_int64(N), Ho, Wo, Cout, cin, pc)
+        self._bgrad(g, Ho * Wo, Cout, Cout, biases=[ds.Conv2d_0.bias])
+        w32 = self._alloc((Cout, cin, 3, 3))
+        self._pack_f32(w32, [ds.Conv2d_0.weight])
+        with torch.no_grad():
+            self.pack_jobs[-1]()
+        d_fir = self._alloc((N, Hi + 1, Wi + 1, pc))
+        self._call('indm_conv_s2_dgrad', g, w32, d_fir, op_dt, ctypes.c_int64(N), Ho, Wo, Cout, cin, pc)
+        d_src = self._alloc((N, Hi, Wi, pc))
+        self._call('indm_fir_nhwc', d_fir, d_src, L.DTYPE_F32, L.DTYPE_F32, ctypes.c_int64(N), Hi + 1, Wi + 1, pc,
+                   r['k1'].ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 4)
+        if r['first']:
+            self._pyr_gx = d_src          # gradient w.r.t. the NHWC-padded network input copy: folded in by _bwd_stem
+        else:
+            self._accumulate_into(r['pyr'], d_src, 1.0)
 
     def vjp(self, v, train=False):
         """v^T d(out)/d(x_in) for the activations of the last forward()/launch(): [N,C,S,S] fp32 in and out.

@@ -316,7 +316,7 @@ def make_train():
     dropout = 0 so that no mask has to be replayed): raw gradients of every parameter (their norms + a few full tensors),
     the per-sample losses, and the parameters / EMA after clip + AdamW."""
     mutils, sde_lib, losses, ema_mod = rl.load('models.utils', 'sde_lib', 'losses', 'models.ema')
-    for tag, path in (('tiny_vp', 'configs/vp/CIFAR10/indm_fid.py'),):
+    for tag, path in (('tiny_vp', 'configs/vp/CIFAR10/indm_fid.py'), ('tiny_ve', 'configs/ve/CIFAR10/indm.py')):
         cfg = rl.get_config(path)
         tiny(cfg)
         cfg.model.dropout = 0.0
@@ -383,7 +383,8 @@ def make_vjp():
     likelihood.py:27-38): J^T eps with Rademacher eps, and the Hutchinson contraction eps^T J eps from the reference's own div_fn."""
     mutils, sde_lib, likelihood = rl.load('models.utils', 'sde_lib', 'likelihood')
     for tag, (path, is_tiny, B) in {'tiny_vp': ('configs/vp/CIFAR10/indm_fid.py', True, 3),
-                                    'vp_cifar': ('configs/vp/CIFAR10/indm_nll.py', False, 2)}.items():
+                                    'vp_cifar': ('configs/vp/CIFAR10/indm_nll.py', False, 2),
+                                    'tiny_ve': ('configs/ve/CIFAR10/indm.py', True, 3)}.items():
         cfg = rl.get_config(path)
         if is_tiny:
             tiny(cfg)
@@ -394,6 +395,8 @@ def make_vjp():
         t = np.array([0.6, 0.6, 0.6][:B], dtype=np.float32)      # the ODE evaluates one t for the whole batch (likelihood.py:96)
         eps = (rng.integers(0, 2, size=(B, 3, S, S)).astype(np.float32) * 2 - 1)
         sde = sde_lib.get_sde(cfg)
+        if cfg.training.sde == 'vesde':
+            x = x * float(sde.marginal_prob(torch.zeros(1), torch.tensor([0.6]))[1])
         score_fn = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
         xt = torch.from_numpy(x).requires_grad_(True)
         sc = score_fn(xt, torch.from_numpy(t))

@@ -113,7 +113,7 @@ def test_pc_sampler_graph_replay_equals_eager_with_same_philox_stream():
 
 
 @pytest.mark.parametrize("mode,tol", [('tf32', 1e-3), ('bf16', 6e-2)])
-@pytest.mark.parametrize("tag", ['tiny_vp', 'vp_cifar'])
+@pytest.mark.parametrize("tag", ['tiny_vp', 'vp_cifar', 'tiny_ve'])
 def test_score_input_vjp_matches_reference_autograd(tag, mode, tol):
     """J^T eps of score_fn w.r.t. its input through the explicit backward plan, driven by the reference's own call pattern
     (likelihood.py:27-38: torch.autograd.grad(sum(fn(x, t) * eps), x)), against the live reference's autograd result."""

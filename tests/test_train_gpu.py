@@ -20,9 +20,9 @@ def _sub(a, limit=4096):
     return f[::max(1, (f.size + limit - 1) // limit)]
 
 
-def _setup(mode):
-    g = load_npz('train_tiny_vp.npz')
-    cfg = configs.get_config('vp/CIFAR10/indm_fid')
+def _setup(mode, tag='tiny_vp'):
+    g = load_npz(f'train_{tag}.npz')
+    cfg = configs.get_config('vp/CIFAR10/indm_fid' if tag == 'tiny_vp' else 've/CIFAR10/indm')
     tiny(cfg)
     cfg.model.dropout = 0.0
     cfg.flow.model = 'identity'
@@ -34,9 +34,10 @@ def _setup(mode):
     return g, cfg, model, sde_lib.get_sde(cfg)
 
 
+@pytest.mark.parametrize("tag", ['tiny_vp', 'tiny_ve'])
 @pytest.mark.parametrize("mode,tol", [('tf32', 2e-3), ('bf16', 5e-2)])
-def test_parameter_gradients_match_reference(mode, tol):
-    g, cfg, model, sde = _setup(mode)
+def test_parameter_gradients_match_reference(mode, tol, tag):
+    g, cfg, model, sde = _setup(mode, tag)
     model.train()
     opt = losses.get_optimizer(cfg, model.parameters())          # re-homes parameters / gradients into flat storage
     opt.zero_grad()

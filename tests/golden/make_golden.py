@@ -444,6 +444,51 @@ def make_pc():
         print('pc', tag, 'rms', float(before.pow(2).mean().sqrt()), 'nfe', nfe)
 
 
+def make_samplers():
+    """The other sampling components of sampling.py through the reference's own get_sampling_fn, noise replayed:
+    euler_maruyama / ancestral_sampling predictors, the annealed-Langevin corrector, pc_sampler_search (sampling.pc_denoise) and
+    the black-box ODE sampler (the default of configs/vp/*/indm_fid.py)."""
+    mutils, sde_lib, sampling = rl.load('models.utils', 'sde_lib', 'sampling')
+    import tempfile
+    out = {}
+    specs = [('em_vp', 'configs/vp/CIFAR10/indm_fid.py', dict(method='pc', predictor='euler_maruyama', corrector='none', num_scales=6)),
+             # ancestral_sampling cannot be pinned: the reference's pc_sampler calls update_fn(x, t, next_t) but
+             # AncestralSamplingPredictor.update_fn takes (x, t) only (sampling.py:245 vs :351) -> TypeError in the reference itself
+             ('ald_ve', 'configs/ve/CIFAR10/indm.py', dict(method='pc', predictor='reverse_diffusion', corrector='ald', num_scales=6)),
+             ('search_ve', 'configs/ve/CIFAR10/indm.py', dict(method='pc', predictor='reverse_diffusion', corrector='langevin', pc_denoise=True)),
+             ('ode_vp', 'configs/vp/CIFAR10/indm_fid.py', dict(method='ode'))]
+    for tag, path, over in specs:
+        cfg = rl.get_config(path)
+        tiny(cfg)
+        cfg.flow.model = 'identity'
+        for k, v in over.items():
+            setattr(cfg.sampling, k, v)
+        if tag == 'search_ve':
+            cfg.model.num_scales = 8                      # sde.N = 8: pc_sampler_search runs N - 1 steps + the denoising step
+        if tag == 'ode_vp':
+            cfg.eval.rtol = cfg.eval.atol = 1e-3
+        model, _ = ref_model(cfg, seed=11)
+        sde = sde_lib.get_sde(cfg)
+        B, S = 3, cfg.data.image_size
+        rng = np.random.default_rng(71)
+        prior = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+        noises = rng.standard_normal((40, B, 3, S, S)).astype(np.float32)
+        q = [torch.from_numpy(n) for n in noises]
+        real_randn, real_randn_like = torch.randn, torch.randn_like
+        torch.randn = lambda *shape, **kw: torch.from_numpy(prior)
+        torch.randn_like = lambda x, **kw: q.pop(0)
+        try:
+            fn = sampling.get_sampling_fn(cfg, sde, (B, 3, S, S), lambda v: v, cfg.sampling.truncation_time)
+            with tempfile.TemporaryDirectory() as d:
+                before, after, nfe = fn(model, None, sample_dir=d, r=0)
+        finally:
+            torch.randn, torch.randn_like = real_randn, real_randn_like
+        used = 40 - len(q)
+        out.update({f'{tag}_prior': prior, f'{tag}_noises': noises[:used], f'{tag}_out': before.numpy(), f'{tag}_nfe': np.asarray(nfe)})
+        print('sampler', tag, 'rms', float(before.pow(2).mean().sqrt()), 'nfe', nfe, 'noise draws', used)
+    np.savez_compressed(os.path.join(HERE, 'samplers_tiny.npz'), **out)
+
+
 def tiny_flow(cfg, squeeze):
     """Small wolf flow with the same code paths: 2+2 iResBlocks, 128 hidden channels, 16x16 images."""
     cfg.flow.nblocks = '2-2'
@@ -501,7 +546,7 @@ def make_flow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood', 'train']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood', 'train', 'samplers']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

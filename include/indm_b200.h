@@ -104,6 +104,11 @@ typedef struct indm_igemm {
   int64_t mul_ld;
   void* aux_cos;         /* optional second output (out_mode 0, layout of out_*, operand dtype): cos(2 pi v) of the value v that
                             enters `act` — the derivative of Sin, kept for the log-det estimators (iresblock.py:253-273) */
+  int32_t gn_goff;       /* group index that output channel 0 maps to in gn_partial (the second tensor of a channel concat starts at
+                            group Ca / cpg of the consumer's GroupNorm, models/ncsnpp.py:350) */
+  float* gn2_partial;    /* optional second statistics target with its own (cpg, groups, goff): a skip-connection tensor feeds the
+                            next block's GroupNorm and, later, the concatenated GroupNorm of the up path */
+  int32_t gn2_cpg, gn2_groups, gn2_goff;
   void* splitk_ws;       /* optional fp32 workspace (splitk_ws_bytes): lets launches with too few output tiles for the chip (4x4 / 8x8
                             feature maps) split K across CTAs; a finish kernel reduces the partial sums and applies the epilogue.
                             Bytes needed: up to (#SMs / #tiles) * N*H*W*Cout*4; smaller workspaces just split less. */

@@ -38,6 +38,7 @@ class IgemmDesc(C.Structure):
         ("block_n", C.c_int32), ("stride", C.c_int32),
         ("a_H", C.c_int32), ("a_W", C.c_int32), ("pad", C.c_int32),
         ("mul", C.c_void_p), ("mul_ld", C.c_int64), ("aux_cos", C.c_void_p),
+        ("gn_goff", C.c_int32), ("gn2_partial", C.c_void_p), ("gn2_cpg", C.c_int32), ("gn2_groups", C.c_int32), ("gn2_goff", C.c_int32),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
     ]
 

@@ -66,6 +66,9 @@ struct IgemmParams {
   float* gn_partial;     // optional [N][gn_groups][2] atomically accumulated (sum, sumsq) of the stored values
   int gn_cpg;            // channels per group
   int gn_groups;
+  int gn_goff;           // group index of output channel 0 inside the consumer's GroupNorm (non-zero for the second half of a concat)
+  float* gn2_partial;    // second consumer of the same tensor (skip connections feed two GroupNorms with different group sizes)
+  int gn2_cpg, gn2_groups, gn2_goff;
 };
 
 // ---------------------------------------------------------------- epilogue helpers
@@ -327,7 +330,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool has_mul = KIND ? false : (p.mul != nullptr);
     const bool st_f32 = KIND == 2 ? true : (KIND == 1 ? false : p.out_f32 != nullptr);
     const bool st_bf16 = KIND == 1 ? true : (KIND == 2 ? false : p.out_bf16 != nullptr);
-    const bool has_gn = KIND == 2 ? false : (p.gn_partial != nullptr);
+    const bool has_gn = p.gn_partial != nullptr;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;             // which of the SLAB_STEP warps sharing the quarter: takes slabs half, half + SLAB_STEP, ...
     float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * 4096);
@@ -537,16 +540,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // one image (checked on the host); Cout % 32 == 0, so whole slabs only.
           gs += __shfl_xor_sync(0xffffffffu, gs, 8);  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
           gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
-          const int cq = p.gn_cpg >> 2;               // chunks per group: 1, 2, 4 or 8
-          for (int o = 1; o < cq; o <<= 1) {
-            gs += __shfl_xor_sync(0xffffffffu, gs, o);
-            gq += __shfl_xor_sync(0xffffffffu, gq, o);
-          }
+          // gs / gq now hold this warp's 32-row sums of one 4-channel chunk; fold chunks into the consumer's groups
           const int nn = n0 + (q * 32) / (p.BW * p.BH);
-          if (rsub == 0 && (chunk & (cq - 1)) == 0 && nn < p.N) {
-            float* dst = p.gn_partial + ((long long)nn * p.gn_groups + c / p.gn_cpg) * 2;
-            atomicAdd(dst, gs);
-            atomicAdd(dst + 1, gq);
+          {
+            float s1 = gs, q1 = gq;
+            const int cq = p.gn_cpg >> 2;             // chunks per group: 1, 2, 4 or 8
+            for (int o = 1; o < cq; o <<= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            if (rsub == 0 && (chunk & (cq - 1)) == 0 && nn < p.N) {
+              float* dst = p.gn_partial + ((long long)nn * p.gn_groups + p.gn_goff + c / p.gn_cpg) * 2;
+              atomicAdd(dst, s1);
+              atomicAdd(dst + 1, q1);
+            }
+          }
+          if (p.gn2_partial) {
+            float s2 = gs, q2 = gq;
+            const int cq = p.gn2_cpg >> 2;
+            for (int o = 1; o < cq; o <<= 1) {
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+            }
+            if (rsub == 0 && (chunk & (cq - 1)) == 0 && nn < p.N) {
+              float* dst = p.gn2_partial + ((long long)nn * p.gn2_groups + p.gn2_goff + c / p.gn2_cpg) * 2;
+              atomicAdd(dst, s2);
+              atomicAdd(dst + 1, q2);
+            }
           }
         }
         __syncwarp();   // staging buffer is rewritten by the next slab
@@ -727,6 +747,11 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   p.gn_partial = d->gn_partial;
   p.gn_cpg = d->gn_cpg;
   p.gn_groups = d->gn_groups;
+  p.gn_goff = d->gn_goff;
+  p.gn2_partial = d->gn2_partial;
+  p.gn2_cpg = d->gn2_cpg; p.gn2_groups = d->gn2_groups; p.gn2_goff = d->gn2_goff;
+  INDM_CHECK_ARG(!d->gn2_partial || (d->gn_partial && (d->gn2_cpg == 4 || d->gn2_cpg == 8 || d->gn2_cpg == 16 || d->gn2_cpg == 32)),
+                 "igemm: the second GroupNorm target needs the first one and cpg in {4, 8, 16, 32}");
   if (d->out_mode == 1) INDM_CHECK_ARG(d->out_f32 != nullptr, "igemm: out_mode 1 needs out_f32");
   if (d->out_mode == 2) INDM_CHECK_ARG(d->out_t != nullptr && d->tcol0 % 32 == 0, "igemm: out_mode 2 needs out_t, tcol0 %% 32 == 0");
   if (d->out_mode != 1 && (d->out_f32 || d->out_bf16))
@@ -797,6 +822,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
       p.out_bf16 = nullptr;
       p.out_ld = d->Cout;
       p.gn_partial = nullptr;
+      p.gn2_partial = nullptr;
     }
   }
   INDM_CHECK_ARG(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "igemm: block_n %d unsupported", block_n);
@@ -851,7 +877,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   int kind = 0;
   const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
   if (plain && !d->residual && d->out_bf16 && !d->out_f32) kind = 1;
-  if (plain && !d->rowbias && d->out_f32 && !d->out_bf16 && !d->gn_partial) kind = 2;
+  if (plain && !d->rowbias && d->out_f32 && !d->out_bf16) kind = 2;
 #define INDM_LAUNCH(BN_)                                                                                  \
   if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);          \
   if (kind == 1) return launch_igemm<BN_, false, 1>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \

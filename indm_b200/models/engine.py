@@ -56,6 +56,7 @@ class ScoreEngine:
         self._train = False
         self.tape = []            # closures recorded by the forward builders; replayed in reverse to emit the backward plan
         self._cur = self.ops      # list the emit helpers append to
+        self._producers = {}      # data_ptr of an fp32 NHWC tensor -> igemm descriptor that writes it
         self.pack_jobs = []       # (fn) re-run by load_weights()
         self.gn_slots = 0
         self._weights_version = None
@@ -132,6 +133,32 @@ class ScoreEngine:
         def run():
             L.check(lib.indm_igemm(ctypes.byref(d), L._stream()), 'igemm')
         self._cur.append(run)
+        # fp32 NHWC outputs of the forward plan can accumulate the GroupNorm statistics of their consumers in the epilogue
+        # (patched into this descriptor later by _gn): needs whole 32-column slabs and one image per epilogue warp
+        out = kw.get('out_f32')
+        if (self._cur is self.ops and isinstance(out, torch.Tensor) and kw.get('out_mode', 0) == 0 and not kw.get('batched_b')
+                and kw.get('out_bf16') is None and kw['Cout'] % 32 == 0 and kw['H'] * kw['W'] >= 32 and self.mode == 'bf16'):
+            self._producers[out.data_ptr()] = d
+        return d
+
+    def _fuse_stats_into_producers(self, xa, Ca, xb, Cb, G, part):
+        """True if the producers of xa (and xb) now accumulate this GroupNorm's statistics in their epilogues"""
+        C = Ca + Cb
+        cpg = C // G
+        if cpg not in (4, 8, 16, 32) or Ca % cpg != 0:
+            return False
+        prods = [(self._producers.get(xa.data_ptr()), 0)]
+        if xb is not None:
+            prods.append((self._producers.get(xb.data_ptr()), Ca // cpg))
+        for d, _ in prods:
+            if d is None or (d.gn_partial and d.gn2_partial):
+                return False
+        for d, goff in prods:
+            if not d.gn_partial:
+                d.gn_partial, d.gn_cpg, d.gn_groups, d.gn_goff = part.data_ptr(), cpg, G, goff
+            else:
+                d.gn2_partial, d.gn2_cpg, d.gn2_groups, d.gn2_goff = part.data_ptr(), cpg, G, goff
+        return True
 
     def _call(self, name, *args):
         fn = getattr(L.lib(), name)
@@ -153,7 +180,7 @@ class ScoreEngine:
         if slot is None:
             slot = self._gn_slot()
         part = self.gn_part[slot]
-        if not stats_done:
+        if not stats_done and not (in_dt == L.DTYPE_F32 and self._fuse_stats_into_producers(xa, Ca, xb, Cb, G, part)):
             self._call('indm_gn_stats', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), ctypes.c_int64(H * W), G, part)
         Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
         out = self._op_t((N, Ho, Wo, C))

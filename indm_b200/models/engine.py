@@ -60,6 +60,7 @@ class ScoreEngine:
         self.pack_jobs = []       # (fn) re-run by load_weights()
         self.gn_slots = 0
         self._weights_version = None
+        self._repack_graph, self._repack_key = None, None
         self.forward_count = 0    # bumped by every forward(): lets a pending backward detect overwritten activations
         self._drop_on = False
         self._build()
@@ -107,10 +108,28 @@ class ScoreEngine:
         self.pack_jobs.append(job)
 
     def load_weights(self):
-        """(Re)pack all parameters into the engine's device buffers; cheap (one pass over ~62 M parameters)."""
-        with torch.no_grad():
-            for job in self.pack_jobs:
-                job()
+        """(Re)pack all parameters into the engine's device buffers: one pass over ~62 M parameters.  The ~700 small packing jobs
+        are captured into a CUDA graph the first time they run against a given set of parameter storages, so the per-step repack
+        of training (parameters change every optimizer step) costs one graph replay instead of ~11 ms of Python."""
+        key = (tuple(p.data_ptr() for p in self.model.parameters()), len(self.pack_jobs))
+        if self._repack_graph is not None and self._repack_key == key:
+            self._repack_graph.replay()
+        else:
+            with torch.no_grad():
+                for job in self.pack_jobs:
+                    job()
+            self._repack_graph = None
+            if not torch.cuda.is_current_stream_capturing():
+                try:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        with torch.no_grad():
+                            for job in self.pack_jobs:
+                                job()
+                    self._repack_graph, self._repack_key = g, key
+                except Exception:          # capture is an optimisation only: fall back to eager packing
+                    self._repack_graph = None
         self._weights_version = self.weights_version()
 
     def weights_version(self):

@@ -364,6 +364,46 @@ int indm_cos2pi_f32(const float* x, float* out, int64_t n, void* stream);
 int indm_fixed_point_check(const float* x, const float* x_prev, const float* y, int64_t n, float atol, float rtol, float* flag,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Wolf-flow TRAINING backward (what torch.autograd derives in losses.py:300-304 from iresblock.py:264-273, lipschitz.py:350-359):
+ * HBM-bound helpers; the contractions themselves run on indm_igemm / indm_conv_wgrad.  `dtype` = operand dtype of the branch's
+ * hidden activations (INDM_DTYPE_BF16, or INDM_DTYPE_TF32 / _F32 = fp32 storage).  n % 8 == 0.
+ * ---------------------------------------------------------------- */
+
+/* out = a * b */
+int indm_mul_op(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+
+/* out = a (+ a2, may be NULL) + coef * b * c * d: the second-order term  r . u . Sin''(pre)  of the Neumann estimator's gradient
+ * (Sin'' = -4 pi^2 Sin, so d is the stored post-activation) added to the first-order gradient a */
+int indm_fma3_op(const void* a, const void* a2, const void* b, const void* c, const void* d, void* out, int64_t n, float coef, int dtype,
+                 void* stream);
+
+/* out = sin(2 pi x) / (2 pi) (fp32): Sin of layers/base/activations.py:7-12 on the block input */
+int indm_sin2pi_f32(const float* x, float* out, int64_t n, void* stream);
+
+/* out[n][i] = x[n][i] * s[n] (fp32, D values per sample): per-sample loss weight folded into the Neumann vector */
+int indm_rowscale_f32(const float* x, const float* s, float* out, int64_t N, int64_t D, void* stream);
+
+/* Backward of LopConv2d.compute_weight, domain = codomain = inf (lipschitz.py:350-359): raw, dwn (gradient w.r.t. the normalised
+ * weight), out [rows][cols] fp32, rows = output channels: out (+)= dwn / f - [l1 > coeff] <dwn, raw>_row / (f^2 coeff) sign(raw),
+ * f = max(1, l1 / coeff), l1 = ||raw_row||_1 */
+int indm_lop_bwd_f32(const float* raw, const float* dwn, float* out, int rows, int cols, float coeff, int accumulate, void* stream);
+
+/* Backward of ck[n] * KL[n], KL = log q(h|x) - log p(h) (priors/flow.py:233-253), through the latent prior flow's 'forward' op
+ * program (the one indm_prior_flow evaluates with kl_base; every op.backward == 0).  gh [N,64] = d / d h of the -log p part.
+ * Per-sample parameter-gradient factors are written to workspaces as [N, dim] fp32 matrices, slot = index of the op among the
+ * ops of its kind, so the caller forms the weight gradients with small GEMMs over the batch:
+ *   ws_c [n_couplings][ zin N x 32 | ha N x 256 | hb N x 256 | d1 N x 256 | d2 N x 256 | d3 N x 64 ]   (N * 1120 floats per coupling)
+ *        fc1: dW = d1^T zin, db = colsum d1;  fc2: dW = d2^T ha;  fc3 (weight-normed, folded): dW = d3^T hb
+ *   ws_a [n_actnorms][ d log_scale N x 64 | d bias N x 64 ]
+ *   ws_l [n_linears ][ x N x 64 | gy N x 64 ]      dW = gy^T x  (+ the log|det W| term, -sum(ck) W^-T, added by the caller) */
+int indm_prior_flow_bwd(const float* h, const float* params, const indm_flow_op_t* ops, int n_ops, const float* ck, float* ws_c,
+                        float* ws_a, float* ws_l, float* gh, int64_t N, void* stream);
+
+/* Backward of indm_posterior_sample + the log q term of the KL: c [N,128] = (mu | logvar), gh = total d / d h,
+ * gc [N,128] = (gh | gh eps exp(logvar/2)/2 - ck/2) */
+int indm_posterior_bwd(const float* c, const float* eps, const float* gh, const float* ck, float* gc, int64_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

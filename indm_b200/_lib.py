@@ -97,6 +97,13 @@ _SIGS = {
     "indm_rowdot_f32": [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp],
     "indm_nhwc_to_nchw_f32": [_vp, _i64, _vp, _i64, C.c_int, C.c_int, C.c_int, _f32, _vp],
     "indm_conv_s2_dgrad": [_vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_mul_op": [_vp, _vp, _vp, _i64, C.c_int, _vp],
+    "indm_fma3_op": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, C.c_int, _vp],
+    "indm_sin2pi_f32": [_vp, _vp, _i64, _vp],
+    "indm_rowscale_f32": [_vp, _vp, _vp, _i64, _i64, _vp],
+    "indm_lop_bwd_f32": [_vp, _vp, _vp, C.c_int, C.c_int, _f32, C.c_int, _vp],
+    "indm_prior_flow_bwd": [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "indm_posterior_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "indm_conv_s2_wgrad": [_vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
 }
 EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)

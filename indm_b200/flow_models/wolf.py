@@ -335,6 +335,8 @@ class FlowEngine:
         self.eps = torch.empty((N, core.latent_dim), device=dev)
         self.cond = torch.empty((N, len(self.blocks) * idim), device=dev)
         self.w = {}
+        self.w2f = {}
+        self._saved = None
         self._ops, self._bufs = {}, {}
         self._alloc_weights()
 
@@ -396,6 +398,7 @@ class FlowEngine:
                 a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
                 # use the operand-rounded W2 so the folded bias matches what the tensor cores apply to u
                 w2r = W['w2'].float()
+                self.w2f[i] = w2r             # fp32 copy of the operand-rounded W2: the conditioning path's backward uses it
                 self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
                 self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
             self._pack_prior()
@@ -433,6 +436,8 @@ class FlowEngine:
                             ld_w=float(torch.slogdet(st.linear.weight.detach().double().cpu())[1]),
                             ld_winv=float(torch.slogdet(st.linear.weight_inv.detach().double().cpu())[1])))
         self.prior_params = torch.cat(chunks).contiguous()
+        # d log|det W| / d W = W^-T of every invertible linear (permutation.py:107-112), for the KL term's backward
+        self.prior_winvT = [torch.linalg.inv(st.linear.weight.detach().double().cpu()).t().contiguous().float().to(dev) for st in steps]
 
         def op(kind, backward, offs, skip=0, up=0):
             o = L.FlowOp()
@@ -758,7 +763,7 @@ class FlowEngine:
             ]
         self._replay(key, build)
 
-    def forward_logdet(self, x, h, vareps=None, n_terms=None, training=False, seed=0, offset=0):
+    def forward_logdet(self, x, h, vareps=None, n_terms=None, training=False, seed=0, offset=0, save=False):
         """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z, logpx [N]) with
         logpx = -sum over blocks of the power-series log-det estimate: basic estimator with 20 exact terms in eval mode
         (iresblock.py:127-132,253-261), Neumann estimator value with 2 exact terms in training mode (:114-121,264-273)."""
@@ -775,6 +780,9 @@ class FlowEngine:
         nb = self.nb
         bi = 0
         self.vjp_count = 0
+        if save and not training:
+            raise RuntimeError('the flow backward belongs to the training-mode (Neumann) estimator')
+        self._saved = [] if save else None
         for s in range(len(nb)):
             # engine-owned buffers with stable addresses: the prebuilt launch lists are keyed by data pointers
             xs = [self._static(f'fx_a{s}', x), self._static(f'fx_b{s}', x)]
@@ -816,6 +824,11 @@ class FlowEngine:
                     self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
                     L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
                     self.vjp_count += K + 1
+                    if save:
+                        # what the block's backward needs: its input, the probe and the (constant) Neumann vector
+                        sx, sv, sw = (self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w'))
+                        sx.copy_(xin); sv.copy_(ve); sw.copy_(neumann)
+                        self._saved.append((i, s, m, sx, sv, sw))
                 cur_x = 1 - cur_x
                 bi += 1
             x = xs[cur_x]

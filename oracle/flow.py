@@ -371,22 +371,33 @@ def series_coefficients(n, training, lamb=2.0, n_exact_terms=2):
     return K, [1.0 / poisson_1mcdf(lamb, k, offset) * (1.0 if n >= k - offset else 0.0) for k in range(1, K + 1)]
 
 
-def block_logdet(gfn, x, n, vareps, training):
+def block_logdet(gfn, x, n, vareps, training, differentiable=False):
     """g(x) and the power-series log-det estimate of one iResBlock (iresblock.py:90-174): `basic_logdet_estimator`
     (:253-261) in eval mode, `neumann_logdet_estimator` (:264-273) in training mode.  Uses autograd for the VJPs, like the
-    reference.  Returns (g, logdet [B])."""
+    reference.  Returns (g, logdet [B]).  differentiable=True keeps the autograd graph exactly like the reference's training step
+    (:264-273: the Neumann vector is a constant, the last VJP is taken with create_graph) so that the gradient of the estimate
+    w.r.t. parameters, x and h — second order in g — can be taken by the caller."""
     K, coef = series_coefficients(n, training)
+    if differentiable and not training:
+        raise ValueError('the differentiable estimator is the training-mode one')
     with torch.enable_grad():
-        x = x.detach().requires_grad_(True)
+        if differentiable:
+            if not x.requires_grad:
+                x = x.requires_grad_(True)
+        else:
+            x = x.detach().requires_grad_(True)
         g = gfn(x)
         B = x.shape[0]
         if training:
             vjp, neumann = vareps, vareps
-            for k in range(1, K + 1):
-                vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
-                neumann = neumann + (-1) ** k * coef[k - 1] * vjp
-            vj = torch.autograd.grad(g, x, neumann, retain_graph=True)[0]
+            with torch.no_grad():
+                for k in range(1, K + 1):
+                    vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
+                    neumann = neumann + (-1) ** k * coef[k - 1] * vjp
+            vj = torch.autograd.grad(g, x, neumann, retain_graph=True, create_graph=differentiable)[0]
             ld = (vj.reshape(B, -1) * vareps.reshape(B, -1)).sum(1)
+            if differentiable:
+                return g, ld
         else:
             vjp, ld = vareps, torch.zeros(B)
             for k in range(1, K + 1):
@@ -395,7 +406,7 @@ def block_logdet(gfn, x, n, vareps, training):
     return g.detach(), ld.detach()
 
 
-def resflow_forward_logdet(config, P, x, h, ns, varepss, training=False):
+def resflow_forward_logdet(config, P, x, h, ns, varepss, training=False, differentiable=False):
     """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z in image layout, logpx [B]) with
     logpx = -sum_blocks logdet (iresblock.py:63-69 with logpx starting at 0).  ns / varepss: per-block Poisson draws and
     Gaussian probe tensors, in forward block order."""
@@ -406,7 +417,7 @@ def resflow_forward_logdet(config, P, x, h, ns, varepss, training=False):
     for s, n_s in enumerate(nb):
         for b in range(n_s):
             first = (s == 0 and b == 0)
-            g, ld = block_logdet(lambda v: g_branch(P, s, b, first, v, h), x, int(ns[i]), varepss[i], training)
+            g, ld = block_logdet(lambda v: g_branch(P, s, b, first, v, h), x, int(ns[i]), varepss[i], training, differentiable)
             x = x + g
             logpx = logpx - ld
             i += 1

@@ -489,6 +489,95 @@ def make_samplers():
     np.savez_compressed(os.path.join(HERE, 'samplers_tiny.npz'), **out)
 
 
+def make_flowtrain():
+    """Wolf flow in TRAINING mode through the reference's flow_forward (posterior encoder with batch-statistics BatchNorm,
+    reparameterisation, prior-flow KL, Neumann-series log-det with n + 2 terms whose gradient is second order in g), then
+    backward of L = <z, Gz> + <logdet - KL, cl> with fixed cotangents: records z, logdet - KL, h, and the gradient of EVERY
+    flow parameter.  Every random draw is replayed (torch.randn, torch.randn_like, poisson_sample)."""
+    fm = rl.load('flow_models.flow_model')
+    import flow_models.wolf.flows.resflow.layers.iresblock as irb
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    path = 'configs/vp/CIFAR10/indm_nll.py'
+    cfg = rl.get_config(path)
+    tiny_flow(cfg, False)
+    S = 32
+    cfg.data.image_size = cfg.flow.image_size = S
+    with rl.reference_cwd():
+        flow = fm.create_flow_model(cfg)
+    pcfg = pconfigs.get_config('vp/CIFAR10/indm_nll')
+    tiny_flow(pcfg, False)
+    pcfg.data.image_size = pcfg.flow.image_size = S
+    sd = oflow.synth_params(pcfg, 23)
+    flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    flow.train()
+    B = 4
+    rng = np.random.default_rng(43)
+    x = rng.uniform(-1, 1, size=(B, 3, S, S)).astype(np.float32)
+    eps_post = rng.standard_normal((B, 64)).astype(np.float32)
+    layout = oflow.block_layout(pcfg)
+    c0, h0, w0 = oflow.flow_input_shape(pcfg)
+    ns = np.array([1, 0, 2, 3][:len(layout)], dtype=np.int64)
+    varepss = [rng.standard_normal((B, c, h0 >> s, w0 >> s)).astype(np.float32) for (s, b, c, first) in layout]
+    Gz = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+    cl = rng.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+    q_eps, q_n = [torch.from_numpy(v) for v in varepss], list(ns)
+    real = (torch.randn, torch.randn_like, irb.poisson_sample)
+    torch.randn = lambda *a, **k: torch.from_numpy(eps_post).reshape(B, 1, 64)
+    torch.randn_like = lambda t, **k: q_eps.pop(0)
+    irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+    cap = {}
+    disc = flow.module.discriminator
+    real_skl = disc.sampling_and_KL
+
+    def skl(xx, y=None, nsamples=1):
+        h, kl = real_skl(xx, y=y, nsamples=nsamples)
+        h.retain_grad()
+        cap['h'], cap['kl'] = h, kl
+        return h, kl
+    disc.sampling_and_KL = skl
+
+    def keep(name):
+        def hook(mod, inp, outp):
+            outp.retain_grad()
+            cap[name] = outp
+        return hook
+    hooks = [disc.fc.register_forward_hook(keep('fc_out')), disc.encoder.register_forward_hook(keep('enc_out'))]
+    # x must NOT require grad up front: the first block would then differentiate g through the encoder path (h = enc(x)) too,
+    # which the real training step (data batch without grad, requires_grad_ set inside _logdetgrad after the encoder ran) never does
+    xt = torch.from_numpy(x)
+    try:
+        z, ldkl = fm.flow_forward(cfg, flow, xt, reverse=False)
+        loss = (z * torch.from_numpy(Gz)).sum() + (ldkl * torch.from_numpy(cl)).sum()
+        loss.backward(retain_graph=True)
+        gh_total = cap['h'].grad.clone()       # read now: the retain_grad hook fires again in the autograd.grad call below
+        gh_kl = torch.autograd.grad(-(cap['kl'].reshape(B) * torch.from_numpy(cl)).sum(), cap['h'])[0]
+    finally:
+        torch.randn, torch.randn_like, irb.poisson_sample = real
+        disc.sampling_and_KL = real_skl
+        for hk in hooks:
+            hk.remove()
+    assert not q_eps and not q_n
+    out = dict(x=x, eps_post=eps_post, ns=ns, Gz=Gz, cl=cl, z=z.detach().numpy(), ldkl=ldkl.detach().numpy(),
+               h=cap['h'].detach().numpy().reshape(B, 64), kl=cap['kl'].detach().numpy().reshape(B),
+               gh=gh_total.numpy().reshape(B, 64), gh_kl=gh_kl.numpy().reshape(B, 64), fc_out=cap['fc_out'].detach().numpy(),
+               g_fc_out=cap['fc_out'].grad.numpy(), enc_out=cap['enc_out'].detach().numpy(), g_enc_out=cap['enc_out'].grad.numpy(),
+               seed=np.asarray(23))
+    for i, v in enumerate(varepss):
+        out[f'vareps_{i}'] = v
+    nograd = []
+    for k, p_ in flow.module.named_parameters():
+        if p_.grad is None:
+            nograd.append(k)
+        else:
+            out['grad.' + k] = p_.grad.numpy()
+    for k, b_ in flow.module.named_buffers():          # BatchNorm running statistics after the step, Lipschitz scales
+        out['buf.' + k] = b_.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, 'flowtrain_tiny.npz'), **out)
+    print('flowtrain ns', ns, 'ldkl', ldkl.detach().numpy(), 'kl', out['kl'], 'params without grad:', nograd)
+    print('gh', np.linalg.norm(out['gh']), 'gh_kl', np.linalg.norm(out['gh_kl']), 'g_fc_out', np.linalg.norm(out['g_fc_out']))
+
+
 def tiny_flow(cfg, squeeze):
     """Small wolf flow with the same code paths: 2+2 iResBlocks, 128 hidden channels, 16x16 images."""
     cfg.flow.nblocks = '2-2'

@@ -404,6 +404,21 @@ int indm_prior_flow_bwd(const float* h, const float* params, const indm_flow_op_
  * gc [N,128] = (gh | gh eps exp(logvar/2)/2 - ck/2) */
 int indm_posterior_bwd(const float* c, const float* eps, const float* gh, const float* ck, float* gc, int64_t N, void* stream);
 
+/* nn.BatchNorm2d in batch-statistics (training) mode for the posterior encoder (nnet/resnets/resnet_batchnorm.py:18-76), NHWC:
+ * y [P, ld] fp32 raw convolution output with C real channels (channels >= C are padding and are written as zero),
+ * sums [2C] = (sum_p y | sum_p y^2), accumulated (caller zeroes), eps = 1e-5, biased variance for the normalisation.
+ *   apply:     out = act(gamma (y - mean) rstd + beta (+ residual)), act 0 none / 2 ELU -> operand dtype and / or fp32
+ *   bwd_stats: bsum [2C] = (sum gs | sum gs xhat), gs = g * ELU'(o) with o the post-activation value in `dtype` (NULL: no act)
+ *   bwd_apply: dy = gamma rstd (gs - bsum0 / P - xhat bsum1 / P) in `dtype`; gs_out (fp32, optional) = gs
+ * d gamma = bsum1, d beta = bsum0. */
+int indm_bn_stats(const float* y, int64_t P, int C, int ld, float* sums, void* stream);
+int indm_bn_apply(const float* y, const float* sums, const float* gamma, const float* beta, int64_t P, int C, int ld,
+                  const float* residual, int act, void* out_op, float* out_f32, int dtype, void* stream);
+int indm_bn_bwd_stats(const float* g, const void* o, const float* y, const float* sums, int64_t P, int C, int ld, float* bsum,
+                      int dtype, void* stream);
+int indm_bn_bwd_apply(const float* g, const void* o, const float* y, const float* sums, const float* bsum, const float* gamma,
+                      int64_t P, int C, int ld, void* dy, float* gs_out, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

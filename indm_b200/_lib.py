@@ -104,6 +104,10 @@ _SIGS = {
     "indm_lop_bwd_f32": [_vp, _vp, _vp, C.c_int, C.c_int, _f32, C.c_int, _vp],
     "indm_prior_flow_bwd": [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "indm_posterior_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "indm_bn_stats": [_vp, _i64, C.c_int, C.c_int, _vp, _vp],
+    "indm_bn_apply": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp],
+    "indm_bn_bwd_stats": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp],
+    "indm_bn_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp],
     "indm_conv_s2_wgrad": [_vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
 }
 EXPORTS = ["indm_version", "indm_last_error"] + list(_SIGS)

@@ -384,3 +384,171 @@ extern "C" int indm_posterior_bwd(const float* c, const float* eps, const float*
   INDM_CHECK_LAUNCH("posterior_bwd");
   return INDM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm2d in batch-statistics (training) mode for the posterior encoder (modules/encoders/global_encoder.py:12-44,
+// nnet/resnets/resnet_batchnorm.py:18-76): NHWC fp32 conv outputs y [P, ld] with C <= 512 real channels (ld >= C, channels
+// >= C are padding and stay zero).  sums = (sum_p y | sum_p y^2) per channel.
+namespace {
+
+constexpr float BN_EPS = 1e-5f;
+
+template <bool BF16>
+__device__ __forceinline__ float ld_op(const void* p, long long i) {
+  return BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+template <bool BF16>
+__device__ __forceinline__ void st_op(void* p, long long i, float v) {
+  if (BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+// blockDim = (32 channels, 8 row lanes); grid = (ceil(C/32), row chunks)
+__global__ void bn_stats_kernel(const float* __restrict__ y, long long P, int C, int ld, float* __restrict__ sums) {
+  __shared__ float sh[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    for (long long p = (long long)blockIdx.y * 8 + threadIdx.y; p < P; p += (long long)gridDim.y * 8) {
+      const float v = y[p * ld + c];
+      s += v;
+      q += v * v;
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = s;
+  sh[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r) { s += sh[0][r][threadIdx.x]; q += sh[1][r][threadIdx.x]; }
+    atomicAdd(sums + c, s);
+    atomicAdd(sums + C + c, q);
+  }
+}
+
+// out = act(gamma * (y - mean) * rstd + beta (+ residual)); one thread per element of [P, ld]
+template <bool BF16>
+__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, long long P, int C, int ld, const float* __restrict__ residual, int act,
+                                void* __restrict__ out_op, float* __restrict__ out_f32) {
+  const long long total = P * ld;
+  const float invP = 1.0f / (float)P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    float v = 0.f;
+    if (c < C) {
+      const float mean = sums[c] * invP;
+      const float var = fmaxf(sums[C + c] * invP - mean * mean, 0.f);
+      v = (y[i] - mean) * rsqrtf(var + BN_EPS) * gamma[c] + beta[c];
+      if (residual) v += residual[i];
+      if (act == 2) v = v > 0.f ? v : expm1f(v);
+    }
+    if (out_op) st_op<BF16>(out_op, i, v);
+    if (out_f32) out_f32[i] = v;
+  }
+}
+
+// bsum = (sum_p gs | sum_p gs * xhat), gs = g * ELU'(o) (o = post-activation value, operand dtype; NULL = no activation)
+template <bool BF16>
+__global__ void bn_bwd_stats_kernel(const float* __restrict__ g, const void* __restrict__ o, const float* __restrict__ y,
+                                    const float* __restrict__ sums, long long P, int C, int ld, float* __restrict__ bsum) {
+  __shared__ float sh[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    const float invP = 1.0f / (float)P;
+    const float mean = sums[c] * invP;
+    const float rstd = rsqrtf(fmaxf(sums[C + c] * invP - mean * mean, 0.f) + BN_EPS);
+    for (long long p = (long long)blockIdx.y * 8 + threadIdx.y; p < P; p += (long long)gridDim.y * 8) {
+      const long long i = p * ld + c;
+      float gs = g[i];
+      if (o) {
+        const float ov = ld_op<BF16>(o, i);
+        gs *= ov > 0.f ? 1.f : ov + 1.f;
+      }
+      s += gs;
+      q += gs * (y[i] - mean) * rstd;
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = s;
+  sh[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r) { s += sh[0][r][threadIdx.x]; q += sh[1][r][threadIdx.x]; }
+    atomicAdd(bsum + c, s);
+    atomicAdd(bsum + C + c, q);
+  }
+}
+
+// dy = gamma rstd (gs - mean(gs) - xhat mean(gs xhat)) -> operand dtype; optional gs_out (fp32) = gradient w.r.t. the pre-activation sum
+template <bool BF16>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ g, const void* __restrict__ o, const float* __restrict__ y,
+                                    const float* __restrict__ sums, const float* __restrict__ bsum, const float* __restrict__ gamma,
+                                    long long P, int C, int ld, void* __restrict__ dy, float* __restrict__ gs_out) {
+  const long long total = P * ld;
+  const float invP = 1.0f / (float)P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    float d = 0.f, gs = 0.f;
+    if (c < C) {
+      const float mean = sums[c] * invP;
+      const float rstd = rsqrtf(fmaxf(sums[C + c] * invP - mean * mean, 0.f) + BN_EPS);
+      gs = g[i];
+      if (o) {
+        const float ov = ld_op<BF16>(o, i);
+        gs *= ov > 0.f ? 1.f : ov + 1.f;
+      }
+      const float xh = (y[i] - mean) * rstd;
+      d = gamma[c] * rstd * (gs - bsum[c] * invP - xh * bsum[C + c] * invP);
+    }
+    st_op<BF16>(dy, i, d);
+    if (gs_out) gs_out[i] = gs;
+  }
+}
+
+}  // namespace
+
+extern "C" int indm_bn_stats(const float* y, int64_t P, int C, int ld, float* sums, void* stream_) {
+  INDM_CHECK_ARG(y && sums && P > 0 && C > 0 && ld >= C, "bn_stats: bad arguments");
+  long long chunks = (P + 63) / 64;
+  if (chunks > 1024) chunks = 1024;
+  dim3 grid((C + 31) / 32, (unsigned)chunks), block(32, 8);
+  bn_stats_kernel<<<grid, block, 0, (cudaStream_t)stream_>>>(y, P, C, ld, sums);
+  INDM_CHECK_LAUNCH("bn_stats");
+  return INDM_OK;
+}
+
+extern "C" int indm_bn_apply(const float* y, const float* sums, const float* gamma, const float* beta, int64_t P, int C, int ld,
+                             const float* residual, int act, void* out_op, float* out_f32, int dtype, void* stream_) {
+  INDM_CHECK_ARG(y && sums && gamma && beta && (out_op || out_f32) && P > 0 && C > 0 && ld >= C, "bn_apply: bad arguments");
+  if (dtype == INDM_DTYPE_BF16)
+    bn_apply_kernel<true><<<grid_for(P * ld), 256, 0, (cudaStream_t)stream_>>>(y, sums, gamma, beta, P, C, ld, residual, act, out_op, out_f32);
+  else
+    bn_apply_kernel<false><<<grid_for(P * ld), 256, 0, (cudaStream_t)stream_>>>(y, sums, gamma, beta, P, C, ld, residual, act, out_op, out_f32);
+  INDM_CHECK_LAUNCH("bn_apply");
+  return INDM_OK;
+}
+
+extern "C" int indm_bn_bwd_stats(const float* g, const void* o, const float* y, const float* sums, int64_t P, int C, int ld, float* bsum,
+                                 int dtype, void* stream_) {
+  INDM_CHECK_ARG(g && y && sums && bsum && P > 0 && C > 0 && ld >= C, "bn_bwd_stats: bad arguments");
+  long long chunks = (P + 63) / 64;
+  if (chunks > 1024) chunks = 1024;
+  dim3 grid((C + 31) / 32, (unsigned)chunks), block(32, 8);
+  if (dtype == INDM_DTYPE_BF16) bn_bwd_stats_kernel<true><<<grid, block, 0, (cudaStream_t)stream_>>>(g, o, y, sums, P, C, ld, bsum);
+  else bn_bwd_stats_kernel<false><<<grid, block, 0, (cudaStream_t)stream_>>>(g, o, y, sums, P, C, ld, bsum);
+  INDM_CHECK_LAUNCH("bn_bwd_stats");
+  return INDM_OK;
+}
+
+extern "C" int indm_bn_bwd_apply(const float* g, const void* o, const float* y, const float* sums, const float* bsum, const float* gamma,
+                                 int64_t P, int C, int ld, void* dy, float* gs_out, int dtype, void* stream_) {
+  INDM_CHECK_ARG(g && y && sums && bsum && gamma && dy && P > 0 && C > 0 && ld >= C, "bn_bwd_apply: bad arguments");
+  if (dtype == INDM_DTYPE_BF16)
+    bn_bwd_apply_kernel<true><<<grid_for(P * ld), 256, 0, (cudaStream_t)stream_>>>(g, o, y, sums, bsum, gamma, P, C, ld, dy, gs_out);
+  else
+    bn_bwd_apply_kernel<false><<<grid_for(P * ld), 256, 0, (cudaStream_t)stream_>>>(g, o, y, sums, bsum, gamma, P, C, ld, dy, gs_out);
+  INDM_CHECK_LAUNCH("bn_bwd_apply");
+  return INDM_OK;
+}

@@ -110,3 +110,35 @@ def test_kl_and_posterior_head_gradients_match_reference(mode, tol):
             worst, worst_k = e, k
     print(f'{mode}: d/d fc_out rel-L2 {e_c:.2e}; d/d enc_out rel-L2 {e_e:.2e}; worst prior / fc parameter gradient {worst:.2e} ({worst_k})')
     assert e_c < tol and e_e < tol and worst < tol
+
+
+@pytest.mark.parametrize("mode,tol_f,tol", [('tf32', 1e-4, 2e-3), ('bf16', 2e-2, 8e-2)])
+def test_training_mode_encoder_forward_backward(mode, tol_f, tol):
+    """Stage C: posterior encoder with batch-statistics BatchNorm — forward output, BatchNorm running buffers after the step,
+    and every encoder parameter gradient given the reference's cotangent at the encoder output."""
+    from indm_b200.flow_models.wolf_encoder_train import EncoderTrain
+    g, cfg, flow = _setup(mode)
+    core = flow.module
+    N = g['x'].shape[0]
+    eng = core.engine(N)
+    eng._ensure()
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    enc = EncoderTrain(eng)
+    for p in core.parameters():
+        p.grad = None
+    out = enc.forward(cu(g['x']))
+    e_f = rel_l2(out.cpu().numpy(), g['enc_out'].reshape(N, -1))
+    enc.backward(cu(g['g_enc_out'].reshape(N, -1)))
+    torch.cuda.synchronize()
+    worst, worst_k = 0.0, ''
+    for k, p in core.named_parameters():
+        if not k.startswith('discriminator.encoder'):
+            continue
+        assert p.grad is not None, k
+        e = rel_l2(p.grad.cpu().numpy(), g['grad.' + k])
+        if e > worst:
+            worst, worst_k = e, k
+    e_b = max(rel_l2(b.cpu().numpy(), g['buf.' + k]) for k, b in core.named_buffers()
+              if k.startswith('discriminator.encoder') and not k.endswith('num_batches_tracked'))
+    print(f'{mode}: encoder output rel-L2 {e_f:.2e}; worst parameter gradient {worst:.2e} ({worst_k}); running buffers {e_b:.2e}')
+    assert e_f < tol_f and worst < tol and e_b < tol_f

@@ -287,9 +287,18 @@ class WolfCore(nn.Module):
         if nsamples != 1:
             raise NotImplementedError('flow.train_k = 1 in every INDM config')
         if self.training:
-            raise NotImplementedError('training-mode flow forward (batch-statistics BatchNorm in the posterior encoder, '
-                                      'differentiable Neumann estimator) is not on the CUDA path yet: call flow_model.eval() '
-                                      "(estimator='train' selects the training-mode series: 2 exact terms, Neumann form)")
+            # joint training (losses.py:258-320): batch-statistics BatchNorm in the posterior encoder, the Neumann-series
+            # log-det (n + 2 terms), and an explicit backward plan reached through torch.autograd
+            if h is not None:
+                raise NotImplementedError('training-mode flow forward samples h from the posterior')
+            self._draws += 1
+            if not eval_logdet:
+                # losses.py:381-383: the latent under the just-updated flow, without log-det (still batch-statistics BatchNorm)
+                with torch.no_grad():
+                    hh, _ = eng.train_posterior(data, eps=eps, seed=seed, offset=self._draws)
+                    return eng.forward_map(data, hh)
+            anchor = next(p for p in self.parameters() if p.requires_grad)
+            return _FlowTrainFunction.apply(data, anchor, self, dict(eps=eps, vareps=vareps, n_terms=n_terms, seed=seed, offset=self._draws))
         kl = None
         if h is None:
             self._draws += 1
@@ -302,6 +311,31 @@ class WolfCore(nn.Module):
         if kl is not None:
             loss = loss - kl
         return z, loss
+
+
+class _FlowTrainFunction(torch.autograd.Function):
+    """Bridges the flow engine's explicit training backward into torch.autograd, so that the reference's call site
+    `torch.mean(losses).backward()` (losses.py:304) reaches it: forward returns (z, logdet - KL); backward accumulates every
+    flow parameter gradient into `param.grad` (the `anchor` parameter only makes autograd call us)."""
+
+    @staticmethod
+    def forward(ctx, data, anchor, core, kw):
+        eng = core.engine(data.shape[0])
+        z, loss = eng.train_forward(data, **kw)
+        ctx.eng, ctx.token = eng, eng.train_token
+        return z, loss
+
+    @staticmethod
+    def backward(ctx, gz, gloss):
+        eng = ctx.eng
+        if eng.train_token != ctx.token:
+            raise RuntimeError('indm_b200: the flow engine ran another training forward before this backward')
+        if gz is None:
+            gz = torch.zeros((eng.N,) + tuple(eng.core.input_shape), device=eng.dev)
+        if gloss is None:
+            gloss = torch.zeros((eng.N,), device=eng.dev)
+        eng.train_backward(gz.contiguous().float(), gloss.contiguous().float())
+        return None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------ engine
@@ -721,6 +755,55 @@ class FlowEngine:
         L.call('indm_posterior_sample', L.ptr(E['c']), L.ptr(eps.float().contiguous()), L.ptr(h), L.ptr(E['logq']), N)
         _, kl = self.prior_flow(h, 'forward', kl_base=E['logq'])
         return h, kl
+
+    # ---- joint training: forward with everything the explicit backward needs, and that backward
+    train_token = 0
+
+    def train_forward(self, x, eps=None, vareps=None, n_terms=None, seed=0, offset=0):
+        """WolfCore.forward(reverse=False) in training mode (wolf.py:90-128): returns (z, logdet - KL)."""
+        x = x.detach().float().contiguous()
+        h, kl = self.train_posterior(x, eps=eps, seed=seed, offset=offset)
+        _, c, eps_s, enc_out = self._train_saved
+        z, logpx = self.forward_logdet(x, h, vareps=vareps, n_terms=n_terms, training=True, seed=seed, offset=offset, save=True)
+        FlowEngine.train_token += 1
+        self.train_token = FlowEngine.train_token
+        return z, -logpx - kl
+
+    def train_posterior(self, x, eps=None, seed=0, offset=0):
+        """GaussianDiscriminator.sampling_and_KL in training mode: batch-statistics encoder -> fc -> h ~ q(h|x), KL"""
+        from .wolf_encoder_train import EncoderTrain
+        self._ensure()
+        if not hasattr(self, 'enc'):
+            self._build_encoder()
+            with torch.no_grad():
+                for job in self.enc['jobs']:
+                    job()
+        if not hasattr(self, 'enc_train'):
+            self.enc_train = EncoderTrain(self)
+        N, E = self.N, self.enc
+        enc_out = self.enc_train.forward(x)
+        c = self._static('tr_c', E['c'])
+        L.call('indm_linear_f32', L.ptr(enc_out), L.ptr(E['fc_w']), L.ptr(E['fc_b']), L.ptr(c), N, enc_out.shape[1], c.shape[1], 0, 0, L.DTYPE_F32)
+        if eps is None:
+            L.call('indm_randn_f32', L.ptr(self.eps), self.eps.numel(), seed, 0x7F200000 + offset)
+            eps = self.eps
+        eps_s = self._static('tr_eps', self.eps)
+        eps_s.copy_(eps)
+        h = self._static('tr_h', self.h)
+        L.call('indm_posterior_sample', L.ptr(c), L.ptr(eps_s), L.ptr(h), L.ptr(E['logq']), N)
+        _, kl = self.prior_flow(h, 'forward', kl_base=E['logq'])
+        self._train_saved = (h, c, eps_s, enc_out)
+        return h, kl
+
+    def train_backward(self, gz, gloss):
+        """gz = d L / d z, gloss [N] = d L / d (logdet - KL): runs the residual-flow, KL / posterior-head and encoder backward plans"""
+        from .wolf_backward import FlowBackward, PosteriorBackward
+        if not hasattr(self, '_fbw'):
+            self._fbw, self._pbw = FlowBackward(self), PosteriorBackward(self)
+        h, c, eps, enc_out = self._train_saved
+        _, gh_blocks = self._fbw.run(gz, gloss)
+        g_enc = self._pbw.run(h, gh_blocks, -gloss, c, eps, enc_out)
+        self.enc_train.backward(g_enc)
 
     # ---- power-series log-det (iresblock.py:90-174): VJP chain of g on the tensor cores
     def _g_store(self, i, s, m, x_nchw, out):

@@ -258,20 +258,109 @@ def get_step_fn(config, sde, train, optimize_fn=None, scaler=None):
             flow_state['step'] += 1
         return losses_, losses_score_, losses_flow_, losses_logp_
 
-    def _need_ack():
-        if not getattr(config.training, 'freeze_flow', False):
-            raise NotImplementedError(
-                'joint flow + score training needs gradients through the wolf flow (incl. the second-order Neumann log-det term); '
-                'that backward is not on the CUDA path yet.  Set config.training.freeze_flow = True to train the score network on '
-                'the frozen flow latent (flow losses are still evaluated and returned).')
+    def _flow_losses(model, flow_model, mb, flow_kw, logp_noise, D, **lkw):
+        """flow forward (training mode, differentiable) + score loss on the latent + prior log-p of the diffused latent"""
+        latent, losses_flow = flow_forward(config, flow_model, mb, reverse=False, **flow_kw)
+        losses_score = loss_fn(model, latent, **lkw)
+        Ts = torch.ones(latent.shape[0], device=latent.device) * sde.T
+        meanT, stdT = sde.marginal_prob(latent, Ts)
+        noise = logp_noise if logp_noise is not None else torch.randn_like(latent)
+        losses_logp = sde.prior_logp(meanT + stdT[:, None, None, None] * noise)          # calculate_logp, losses.py:219-225
+        if config.training.reduce_mean:
+            losses_flow, losses_logp = -losses_flow / D, -losses_logp / D
+        else:
+            losses_flow, losses_logp = -losses_flow, -losses_logp
+        return latent, losses_score, losses_flow, losses_logp
+
+    def _joint_step(state, flow_state, batch, fid_variant, **kw):
+        """flow_step_fn_nll (losses.py:258-320) / flow_step_fn_fid (:322-406): joint optimisation of the flow and the score
+        network.  The flow forward runs in training mode (batch-statistics BatchNorm, Neumann log-det series) and its explicit
+        backward plan is reached through autograd from `torch.mean(losses).backward()`, like the score network's.
+        Keyword-only test hooks: flow_kw= (draws of the flow forward), logp_noise=, draws= / draws2= (loss_fn draws of the two phases)."""
+        model, flow_model = state['model'], flow_state['model']
+        optimizer, flow_optimizer = state['optimizer'], flow_state['optimizer']
+        batch_size = batch.shape[0]
+        nmb = config.optim.num_micro_batch
+        losses_, losses_score_, losses_flow_, losses_logp_ = (torch.zeros(batch_size) for _ in range(4))
+        optimizer.zero_grad()
+        flow_optimizer.zero_grad()
+        D = float(np.prod(batch.shape[1:]))
+        flow_kw = kw.pop('flow_kw', None) or {}
+        logp_noise = kw.pop('logp_noise', None)
+        draws2 = kw.pop('draws2', None)
+        mbs = [slice(batch_size // nmb * k, batch_size // nmb * (k + 1)) for k in range(nmb)]
+        if not fid_variant:
+            if train:
+                flow_model.train()
+                for sl in mbs:
+                    _, losses_score, losses_flow, losses_logp = _flow_losses(model, flow_model, batch[sl], flow_kw, logp_noise, D,
+                                                                             st=config.training.st, **kw)
+                    losses = losses_score + losses_flow + losses_logp
+                    torch.mean(losses).backward()
+                    losses_[sl] = losses.detach().cpu()
+                    losses_score_[sl], losses_flow_[sl], losses_logp_[sl] = (losses_score.detach().cpu(), losses_flow.detach().cpu(),
+                                                                             losses_logp.detach().cpu())
+                optimize_fn(optimizer, model.parameters(), step=state['step'])
+                optimize_fn(flow_optimizer, flow_model.parameters(), step=flow_state['step'])
+            # update_lipschitz(flow_model) (losses.py:313) only touches spectral / induced-norm layers: a no-op for LopConv2d
+            state['step'] += 1
+            state['ema'].update(model.parameters())
+            flow_state['step'] += 1
+            flow_state['ema'].update(flow_model.parameters())
+            return losses_, losses_score_, losses_flow_, losses_logp_
+        if train:
+            flow_model.train()
+            latents = []
+            # phase 1 (:354-374): the flow is trained on all three losses (score loss importance-sampled)
+            for sl in mbs:
+                latent, losses_score, losses_flow, losses_logp = _flow_losses(model, flow_model, batch[sl], flow_kw, logp_noise, D,
+                                                                              importance_sampling=True, **kw)
+                losses = losses_score + losses_flow + losses_logp
+                torch.mean(losses).backward()
+                latents.append(latent.detach())
+                losses_[sl] = losses.detach().cpu()
+                losses_flow_[sl], losses_logp_[sl] = losses_flow.detach().cpu(), losses_logp.detach().cpu()
+            optimize_fn(flow_optimizer, flow_model.parameters(), step=flow_state['step'])
+            flow_state['ema'].update(flow_model.parameters())
+            # phase 2 (:376-400): the score network on the (re-evaluated unless st) latent
+            if not config.training.st:
+                optimizer.zero_grad()
+            kw2 = dict(kw)
+            if draws2 is not None:
+                kw2['draws'] = draws2
+            for k, sl in enumerate(mbs):
+                if not config.training.st:
+                    with torch.no_grad():
+                        latent, _ = flow_forward(config, flow_model, batch[sl], log_det=None, reverse=False,
+                                                 **{a: b for a, b in flow_kw.items() if a in ('eps', 'seed')})
+                else:
+                    latent = latents[k]
+                losses_add = loss_fn(model, latent.detach(), st=config.training.st, recon_loss=False, **kw2)
+                if config.training.st:
+                    const_adj = (losses_add.mean() / losses_score.mean()).detach()
+                    for p in model.parameters():
+                        if p.grad is not None:
+                            p.grad.mul_(const_adj)
+                torch.mean(losses_add).backward()
+                losses_score_[sl] = losses_add.detach().cpu()
+            optimize_fn(optimizer, model.parameters(), step=state['step'])
+            state['ema'].update(model.parameters())
+            state['step'] += 1
+            flow_state['step'] += 1
+        return losses_, losses_score_, losses_flow_, losses_logp_
+
+    def _frozen(config):
+        return bool(getattr(config.training, 'freeze_flow', False))
 
     def flow_step_fn_nll(state, flow_state, batch, **kw):
-        _need_ack()
-        return _frozen_flow_step(state, flow_state, batch, False, **kw)
+        if _frozen(config):
+            return _frozen_flow_step(state, flow_state, batch, False, **kw)
+        return _joint_step(state, flow_state, batch, False, **kw)
 
     def flow_step_fn_fid(state, flow_state, batch, **kw):
-        _need_ack()
-        return _frozen_flow_step(state, flow_state, batch, True, **kw)
+        if _frozen(config):
+            return _frozen_flow_step(state, flow_state, batch, True, **kw)
+        return _joint_step(state, flow_state, batch, True, **kw)
 
     if config.flow.model == 'identity':
         logging.info('Train only the score network.')

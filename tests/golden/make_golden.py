@@ -578,6 +578,80 @@ def make_flowtrain():
     print('gh', np.linalg.norm(out['gh']), 'gh_kl', np.linalg.norm(out['gh_kl']), 'g_fc_out', np.linalg.norm(out['g_fc_out']))
 
 
+def make_jointtrain():
+    """One JOINT optimisation step of the flow and the score network through the reference's own losses.get_step_fn ->
+    flow_step_fn_nll (losses.py:258-320) on the small INDM-VP model (dropout 0, so no mask to replay), every random draw replayed:
+    the four loss vectors, and parameters / EMA of both networks after clip + AdamW (a sample of tensors, sub-sampled)."""
+    mutils, sde_lib, losses, ema_mod, fm = rl.load('models.utils', 'sde_lib', 'losses', 'models.ema', 'flow_models.flow_model')
+    import flow_models.wolf.flows.resflow.layers.iresblock as irb
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    path = 'configs/vp/CIFAR10/indm_nll.py'
+    cfg = small_joint(rl.get_config(path))
+    cfg.model.dropout = 0.0
+    model, _ = ref_model(cfg, seed=11)
+    model.train()
+    with rl.reference_cwd():
+        flow = fm.create_flow_model(cfg)
+    pcfg = small_joint(pconfigs.get_config('vp/CIFAR10/indm_nll'))
+    flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, 21).items()})
+    sde = sde_lib.get_sde(cfg)
+    B, S = 4, 32
+    rng = np.random.default_rng(71)
+    batch = rng.uniform(-1, 1, size=(B, 3, S, S)).astype(np.float32)
+    layout = oflow.block_layout(pcfg)
+    c0, h0, w0 = oflow.flow_input_shape(pcfg)
+    eps_post = rng.standard_normal((B, 64)).astype(np.float32)
+    ns = np.array([2, 0, 1, 3][:len(layout)], dtype=np.int64)
+    varepss = [rng.standard_normal((B, c, h0 >> s, w0 >> s)).astype(np.float32) for (s, b, c, first) in layout]
+    z = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+    logp_noise = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+    u = rng.uniform(size=(B,)).astype(np.float32)
+    q_like = [torch.from_numpy(v) for v in varepss] + [torch.from_numpy(z), torch.from_numpy(logp_noise)]
+    q_n = list(ns)
+    opt = losses.get_optimizer(cfg, model.parameters())
+    ema = ema_mod.ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    state = dict(optimizer=opt, model=model, ema=ema, step=0)
+    fopt = losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr)
+    fema = ema_mod.ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate)
+    flow_state = dict(optimizer=fopt, model=flow, ema=fema, step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    before = {'s::' + n: p.detach().clone() for n, p in model.named_parameters()}
+    before.update({'f::' + n: p.detach().clone() for n, p in flow.named_parameters()})
+    real = (torch.randn, torch.randn_like, torch.rand, irb.poisson_sample)
+    torch.randn = lambda *a, **k: torch.from_numpy(eps_post).reshape(B, 1, 64)
+    torch.randn_like = lambda t, **k: q_like.pop(0)
+    torch.rand = lambda *a, **k: torch.from_numpy(u)
+    irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+    try:
+        res = step_fn(state, flow_state, torch.from_numpy(batch))
+    finally:
+        torch.randn, torch.randn_like, torch.rand, irb.poisson_sample = real
+    assert not q_like and not q_n, (len(q_like), q_n)
+    out = dict(batch=batch, eps_post=eps_post, ns=ns, z=z, logp_noise=logp_noise, u=u, seed_score=np.asarray(11), seed_flow=np.asarray(21),
+               losses=res[0].numpy(), losses_score=res[1].numpy(), losses_flow=res[2].numpy(), losses_logp=res[3].numpy())
+    for i, v in enumerate(varepss):
+        out[f'vareps_{i}'] = v
+    keep_s = ('all_modules.0.weight', 'all_modules.2.weight', 'all_modules.3.Conv_0.weight', 'all_modules.3.GroupNorm_1.bias')
+    keep_f = ('transforms.0.chain.0.nnet.0.weight', 'transforms.0.chain.1.nnet.3.weight', 'transforms.1.chain.1.nnet.5.weight',
+              'chain.1.nnet.3.h_net.net.weight', 'resnet0.main.0.conv1.weight', 'resnet1.main.1.bn2.weight', 'resnet2.main.1.conv2.weight',
+              'encoder.net.top.weight', 'fc.linear.weight_v', 'fc.linear.weight_g', 'steps.0.linear.weight', 'steps.1.actnorm.log_scale',
+              'steps.1.unit.coupling2_dn.net.fc2.weight', 'steps.0.unit.coupling1_up.net.fc3.linear.weight_v')
+    names, shadow = [], {}
+    for tag, net, em, keep in (('s', model, ema, keep_s), ('f', flow, fema, keep_f)):
+        plist = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+        for i, (n, p) in enumerate(plist):
+            if any(k in n for k in keep):
+                key = f'{tag}::{n}'
+                names.append(key)
+                out['param::' + key] = _sub(p.detach().numpy())
+                out['step::' + key] = _sub((p.detach() - before[key]).numpy())
+                out['ema::' + key] = _sub(em.shadow_params[i].numpy())
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, 'jointtrain_small_vp.npz'), **out)
+    print('jointtrain losses', res[0].numpy(), 'score', res[1].numpy(), 'flow', res[2].numpy(), 'logp', res[3].numpy(), 'kept', len(names))
+
+
 def tiny_flow(cfg, squeeze):
     """Small wolf flow with the same code paths: 2+2 iResBlocks, 128 hidden channels, 16x16 images."""
     cfg.flow.nblocks = '2-2'
@@ -635,7 +709,7 @@ def make_flow():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood', 'train', 'samplers']
+    which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood', 'train', 'samplers', 'flowtrain', 'jointtrain']
     for w in which:
         globals()['make_' + w]()
         print('made', w)

@@ -142,3 +142,67 @@ def test_training_mode_encoder_forward_backward(mode, tol_f, tol):
               if k.startswith('discriminator.encoder') and not k.endswith('num_batches_tracked'))
     print(f'{mode}: encoder output rel-L2 {e_f:.2e}; worst parameter gradient {worst:.2e} ({worst_k}); running buffers {e_b:.2e}')
     assert e_f < tol_f and worst < tol and e_b < tol_f
+
+
+def _sub(a, limit=4096):
+    f = np.ascontiguousarray(a).reshape(-1)
+    return f[::max(1, (f.size + limit - 1) // limit)].copy()
+
+
+@pytest.mark.parametrize("mode,tol,step_tol,ema_tol", [('tf32', 2e-3, 3e-2, 1e-4), ('bf16', 5e-2, 0.4, 5e-4)])
+def test_joint_flow_score_step_matches_reference(mode, tol, step_tol, ema_tol):
+    """The reference's flow_step_fn_nll (losses.py:258-320) end to end: flow forward in training mode -> latent -> score loss +
+    flow loss + prior log-p -> one backward through both networks -> clip + AdamW + EMA on both.  Loss vectors and the applied
+    parameter updates of both networks against the live reference (first AdamW step ~ lr * sign(grad): the update is compared)."""
+    from indm_b200 import losses, sde_lib
+    from indm_b200.models import utils as mutils
+    from indm_b200.models.ema import ExponentialMovingAverage
+    from oracle import ncsnpp as oncsnpp
+    g = load_npz('jointtrain_small_vp.npz')
+    cfg = configs.get_config('vp/CIFAR10/indm_nll')
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks, cfg.model.attn_resolutions = 128, (1, 2), 1, (16,)
+    cfg.flow.nblocks, cfg.flow.intermediate_dim = '2-2', 128
+    cfg.model.dropout = 0.0
+    cfg.device = torch.device('cuda:0')
+    model = mutils.create_model(cfg)
+    model.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(cfg, int(g['seed_score'])).items()})
+    flow = fm.create_flow_model(cfg)
+    flow.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oflow.synth_params(cfg, int(g['seed_flow'])).items()})
+    model.module.compute_mode = flow.module.compute_mode = mode
+    model.train()
+    sde = sde_lib.get_sde(cfg)
+    opt = losses.get_optimizer(cfg, model.parameters())
+    ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    state = dict(optimizer=opt, model=model, ema=ema, step=0)
+    fopt = losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr)
+    fema = ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate)
+    flow_state = dict(optimizer=fopt, model=flow, ema=fema, step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    nets = {'s': (model, ema), 'f': (flow, fema)}
+    before = {f'{t}::{n}': p.detach().clone() for t, (net, _) in nets.items() for n, p in net.named_parameters()}
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    nblk = len(oflow.block_layout(cfg))
+    flow_kw = dict(eps=cu(g['eps_post']), vareps=[cu(g[f'vareps_{i}']) for i in range(nblk)], n_terms=g['ns'])
+    res = step_fn(state, flow_state, cu(g['batch']), draws=dict(u=cu(g['u']), z=cu(g['z'])), flow_kw=flow_kw, logp_noise=cu(g['logp_noise']))
+    torch.cuda.synchronize()
+    assert state['step'] == 1 and flow_state['step'] == 1
+    for i, key in enumerate(('losses', 'losses_score', 'losses_flow', 'losses_logp')):
+        e = float(np.abs(res[i].numpy() - g[key]).max() / np.abs(g[key]).max())
+        print(f'{mode}: {key} rel err {e:.2e}  ({res[i].numpy()} vs {g[key]})')
+        assert e < tol, key
+    for key in [str(k) for k in g['names']]:
+        t, n = key.split('::')
+        net, em = nets[t]
+        plist = [(nn_, p) for nn_, p in net.named_parameters() if p.requires_grad]
+        idx = [nn_ for nn_, _ in plist].index(n)
+        p = plist[idx][1]
+        got = _sub(p.detach().cpu().numpy()) - _sub(before[key].cpu().numpy())
+        ref = g['step::' + key]
+        e = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+        e_ema = float(np.abs(_sub(em.shadow_params[idx].cpu().numpy()) - g['ema::' + key]).max())
+        print(f'   update {key}: rel-L2 of the step {e:.2e}; ema max-abs err {e_ema:.2e}')
+        assert e < step_tol, key
+        # one sign flip of a ~zero-gradient element moves the parameter by 2 lr, and the EMA by 0.82 of that on the first update
+        # (models/ema.py:40: decay = min(decay, (1 + n) / (10 + n)) = 2 / 11); the rel-L2 of the step above bounds how many flip
+        lr_ = cfg.optim.lr if t == 's' else cfg.flow.lr
+        assert e_ema < max(ema_tol, 2.0 * lr_), key

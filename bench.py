@@ -160,20 +160,21 @@ def conv_roofline(net, eng, reps=3):
 
 
 def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup=3):
-    """Second BASELINE metric (configs[2]): training samples/s of the likelihood-weighted INDM-VP step, 128 images per GPU,
-    data parallel (one NCCL all-reduce of the flat gradient buffer per step).  What one step does: wolf flow forward with the
-    training-mode log-det series and KL (values), score-network train-mode forward (dropout 0.1) + DSM loss + full backward
-    (input and parameter gradients) + global-norm clip + AdamW + EMA.  The flow's parameters are frozen: the flow backward
-    (incl. the second-order Neumann term) is not on the CUDA path yet — stated in the result."""
+    """Second BASELINE metric (configs[2]): training samples/s of the INDM-VP joint step `flow_step_fn_nll` (losses.py:258-320),
+    128 images per GPU, data parallel (one NCCL all-reduce per flat gradient buffer: score network and flow).  One step = wolf flow
+    forward in training mode (batch-statistics BatchNorm encoder, posterior sample, prior-flow KL, Neumann log-det series of all
+    32 iResBlocks), score-network train-mode forward (dropout 0.1) + DSM loss + prior log-p, ONE backward through both networks
+    (score dgrad + wgrad, flow first-order + second-order Neumann gradient, encoder / prior backward), then global-norm clip +
+    AdamW + EMA on both."""
     import torch
     from indm_b200 import configs, losses
     from indm_b200.models.ema import ExponentialMovingAverage
     cfg = configs.get_config("vp/CIFAR10/indm_nll")
     cfg.device = dev
-    cfg.training.freeze_flow = True
     opt = losses.get_optimizer(cfg, model.parameters())
     state = dict(optimizer=opt, model=model, ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
-    flow_state = dict(model=flow, step=0)
+    fopt = losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr)
+    flow_state = dict(optimizer=fopt, model=flow, ema=ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate), step=0)
     step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
     batch_host = (torch.rand(PER_GPU_BATCH, 3, 32, 32) * 2 - 1).pin_memory()
 
@@ -184,8 +185,8 @@ def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup
     ms, launches = timed(one, steps, warmup)
     return {"metric": "train_samples_per_sec", "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
             "steps": steps, "warmup": warmup, "per_gpu_batch": PER_GPU_BATCH, "gpu_launches": launches,
-            "config": "vp/CIFAR10/indm_nll flow_step_fn_nll, score network trained (fwd + bwd + clip + AdamW + EMA, dropout 0.1), "
-                      "wolf flow forward + training log-det series evaluated, flow parameters FROZEN (flow backward not built)",
+            "config": "vp/CIFAR10/indm_nll flow_step_fn_nll: JOINT step, wolf flow (16+16 iResBlocks, idim 512, training-mode encoder) and "
+                      "score network (DDPM++ nres=4, dropout 0.1) both trained: fwd + bwd + clip + AdamW + EMA on both",
             "dtype": "bf16"}
 
 

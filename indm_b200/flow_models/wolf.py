@@ -16,6 +16,7 @@ The Lipschitz-normalised weights W / max(1, |row|_1 / 0.98) are computed once pe
 inside every call as the reference does (lipschitz.py:350-363).
 """
 import ctypes
+import threading
 import math
 
 import numpy as np
@@ -371,6 +372,9 @@ class FlowEngine:
         self.w = {}
         self.w2f = {}
         self._saved = None
+        self._graphs, self._pool, self.use_graphs = {}, None, True
+        self._lamb_vers = None
+        self.prior_winvT = []
         self._ops, self._bufs = {}, {}
         self._alloc_weights()
 
@@ -405,73 +409,134 @@ class FlowEngine:
     def version(self):
         return sum(p._version for p in self.core.parameters()) + sum(b._version for b in self.core.buffers()) + L.param_epoch
 
-    def load_weights(self):
+    def _graphed(self, key, fn):
+        """run `fn` (a fixed sequence of launches over engine-owned buffers) through a CUDA graph: eager on first use (lazy
+        launch lists / buffers get built), captured on the second, replayed afterwards.  The flow passes issue thousands of
+        small launches per step; replaying them removes the per-launch host cost that bounded the training step."""
+        st = self._graphs.get(key)
+        if st is None or torch.cuda.is_current_stream_capturing():
+            fn()
+            if st is None:
+                self._graphs[key] = 1
+            return
+        if st == 1:
+            # stream capture from inside an autograd worker thread gets invalidated (observed: cudaErrorStreamCaptureInvalidated
+            # at capture_end when the flow backward is reached through loss.backward()); those calls stay eager — the flow
+            # backward is GPU-bound (76 ms eager == 76 ms replayed at batch 128), so nothing is lost
+            if not self.use_graphs or threading.current_thread() is not threading.main_thread():
+                fn()
+                return
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):   # may run inside an autograd worker thread
+                fn()
+            self._graphs[key] = st = g
+        st.replay()
+
+    def _repack_device(self):
+        """device part of the weight (re)pack: every result is written in place, so launch lists and graphs stay valid"""
         dev = self.dev
+        for i, (s, b, m) in enumerate(self.blocks):
+            cv1, cv2, cv3 = m.convs()
+            W = self.w[(s, b)]
+            w1, sc1 = self._lop(cv1.weight.detach().to(dev, torch.float32))
+            w2, sc2 = self._lop(cv2.weight.detach().to(dev, torch.float32))
+            w3, sc3 = self._lop(cv3.weight.detach().to(dev, torch.float32))
+            cv1.scale.copy_(sc1); cv2.scale.copy_(sc2); cv3.scale.copy_(sc3)      # lipschitz.py:353-354
+            co, ci = w1.shape[:2]                                         # idim, c
+            # packed index t * c + ch with t = ky * 3 + kx (what im2col / col2im produce)
+            W['w1'][:, :9 * ci].copy_(self._round(w1.permute(0, 2, 3, 1).reshape(co, 9 * ci)))          # [o][t*c+ch]
+            W['b1'].copy_(cv1.bias.detach())
+            w2m = w2.reshape(w2.shape[0], w2.shape[1])
+            W['w2'].copy_(self._round(w2m))
+            W['w3'].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9 * ci, co)))                      # [t*c+ch][k]
+            W['b3'].copy_(cv3.bias.detach())
+            # VJP chain: conv3^T = im2col(flip) . w3v^T ; conv2^T ; conv1^T = col2im(flip)(. w1v^T)
+            W['w3v'][:, :9 * ci].copy_(self._round(w3.permute(1, 2, 3, 0).reshape(co, 9 * ci)))         # [k][t*c+ch]
+            W['w2d'].copy_(self._round(w2m.t()))
+            W['w1v'].copy_(self._round(w1.permute(2, 3, 1, 0).reshape(9 * ci, co)))                     # [t*c+ch][k]
+            # conditioning: conv1x1(u + (A h + a)) + b2 = conv1x1(u) + (W2 A) h + (W2 a + b2)   (lipschitz.py:431-435)
+            A = cv2.h_net.net.weight.detach().to(dev, torch.float32)
+            a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
+            # use the operand-rounded W2 so the folded bias matches what the tensor cores apply to u
+            if i not in self.w2f:
+                self.w2f[i] = torch.empty((self.idim, self.idim), device=dev)
+            self.w2f[i].copy_(W['w2'])      # fp32 copy of the operand-rounded W2: the conditioning path's backward uses it
+            w2r = self.w2f[i]
+            self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
+            self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
+        self._pack_prior_device()
+        if hasattr(self, 'enc'):
+            for job in self.enc['jobs']:
+                job()
+
+    def load_weights(self):
         with torch.no_grad():
-            for i, (s, b, m) in enumerate(self.blocks):
-                cv1, cv2, cv3 = m.convs()
-                W = self.w[(s, b)]
-                w1, sc1 = self._lop(cv1.weight.detach().to(dev, torch.float32))
-                w2, sc2 = self._lop(cv2.weight.detach().to(dev, torch.float32))
-                w3, sc3 = self._lop(cv3.weight.detach().to(dev, torch.float32))
-                cv1.scale.copy_(sc1); cv2.scale.copy_(sc2); cv3.scale.copy_(sc3)      # lipschitz.py:353-354
-                co, ci = w1.shape[:2]                                         # idim, c
-                # packed index t * c + ch with t = ky * 3 + kx (what im2col / col2im produce)
-                W['w1'][:, :9 * ci].copy_(self._round(w1.permute(0, 2, 3, 1).reshape(co, 9 * ci)))          # [o][t*c+ch]
-                W['b1'].copy_(cv1.bias.detach())
-                w2m = w2.reshape(w2.shape[0], w2.shape[1])
-                W['w2'].copy_(self._round(w2m))
-                W['w3'].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9 * ci, co)))                      # [t*c+ch][k]
-                W['b3'].copy_(cv3.bias.detach())
-                # VJP chain: conv3^T = im2col(flip) . w3v^T ; conv2^T ; conv1^T = col2im(flip)(. w1v^T)
-                W['w3v'][:, :9 * ci].copy_(self._round(w3.permute(1, 2, 3, 0).reshape(co, 9 * ci)))         # [k][t*c+ch]
-                W['w2d'].copy_(self._round(w2m.t()))
-                W['w1v'].copy_(self._round(w1.permute(2, 3, 1, 0).reshape(9 * ci, co)))                     # [t*c+ch][k]
-                # conditioning: conv1x1(u + (A h + a)) + b2 = conv1x1(u) + (W2 A) h + (W2 a + b2)   (lipschitz.py:431-435)
-                A = cv2.h_net.net.weight.detach().to(dev, torch.float32)
-                a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
-                # use the operand-rounded W2 so the folded bias matches what the tensor cores apply to u
-                w2r = W['w2'].float()
-                self.w2f[i] = w2r             # fp32 copy of the operand-rounded W2: the conditioning path's backward uses it
-                self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
-                self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
-            self._pack_prior()
-            self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
-            if hasattr(self, 'enc'):
-                for job in self.enc['jobs']:
-                    job()
+            self._graphed(('repack', hasattr(self, 'enc')), self._repack_device)
+            self._pack_prior_host()
+            vers = tuple(m.lamb._version for (_, _, m) in self.blocks)
+            if vers != self._lamb_vers:          # lamb is not trained (iresblock.py:40): one read-back, not one per step
+                self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
+                self._lamb_vers = vers
         self._version = self.version()
 
-    def _pack_prior(self):
-        dev = self.dev
+    def _prior_layout(self):
+        """(getter list, per-step record of offsets) of the flat prior-parameter buffer; the offsets never change"""
         steps = self.core.discriminator.prior.flow.steps
-        chunks, off = [], 0
+        getters, off = [], 0
 
-        def put(t):
+        def put(fn, n):
             nonlocal off
-            t = t.detach().to(dev, torch.float32).reshape(-1)
             o = off
-            chunks.append(t)
-            off += t.numel()
+            getters.append((o, n, fn))
+            off += n
             return o
+
+        def plain(t):
+            return put(lambda t=t: t.detach().reshape(-1), t.numel())
 
         def coupling(cp):
             n = cp.net
-            v, g = n.fc3.linear.weight_v.detach().to(dev, torch.float32), n.fc3.linear.weight_g.detach().to(dev, torch.float32)
-            w3 = g * v / v.norm(dim=1, keepdim=True)
-            return [put(n.fc1.weight), put(n.fc1.bias), put(n.fc2.weight), put(n.fc2.bias), put(w3), put(n.fc3.linear.bias)]
+            lin = n.fc3.linear
+
+            def w3(lin=lin):
+                v, g = lin.weight_v.detach(), lin.weight_g.detach()
+                return (g * v / v.norm(dim=1, keepdim=True)).reshape(-1)
+            return [plain(n.fc1.weight), plain(n.fc1.bias), plain(n.fc2.weight), plain(n.fc2.bias), put(w3, lin.weight_v.numel()),
+                    plain(lin.bias)]
 
         rec = []
         for st in steps:
-            rec.append(dict(an=[put(st.actnorm.log_scale), put(st.actnorm.bias)], W=put(st.linear.weight), Winv=put(st.linear.weight_inv),
+            rec.append(dict(an=[plain(st.actnorm.log_scale), plain(st.actnorm.bias)], W=plain(st.linear.weight), Winv=plain(st.linear.weight_inv),
                             c1u=coupling(st.unit.coupling1_up), c1d=coupling(st.unit.coupling1_dn),
-                            uan=[put(st.unit.actnorm.log_scale), put(st.unit.actnorm.bias)],
-                            c2u=coupling(st.unit.coupling2_up), c2d=coupling(st.unit.coupling2_dn),
-                            ld_w=float(torch.slogdet(st.linear.weight.detach().double().cpu())[1]),
-                            ld_winv=float(torch.slogdet(st.linear.weight_inv.detach().double().cpu())[1])))
-        self.prior_params = torch.cat(chunks).contiguous()
-        # d log|det W| / d W = W^-T of every invertible linear (permutation.py:107-112), for the KL term's backward
-        self.prior_winvT = [torch.linalg.inv(st.linear.weight.detach().double().cpu()).t().contiguous().float().to(dev) for st in steps]
+                            uan=[plain(st.unit.actnorm.log_scale), plain(st.unit.actnorm.bias)],
+                            c2u=coupling(st.unit.coupling2_up), c2d=coupling(st.unit.coupling2_dn)))
+        return getters, rec, off
+
+    def _pack_prior_device(self):
+        dev = self.dev
+        if self.prior_params is None:
+            self._prior_getters, self._prior_rec, total = self._prior_layout()
+            self.prior_params = torch.empty((total,), device=dev)
+        for o, n, fn in self._prior_getters:
+            self.prior_params[o:o + n].copy_(fn().to(dev, torch.float32))
+
+    def _pack_prior_host(self):
+        """log|det| of the invertible linears (a per-call constant of the prior-flow kernel) and W^-T (the gradient of that
+        log-det, permutation.py:107-112): 64x64 factorizations in fp64 on the host, one read-back for all of them"""
+        dev = self.dev
+        steps = self.core.discriminator.prior.flow.steps
+        rec = self._prior_rec
+        mats = torch.stack([torch.stack([st.linear.weight.detach(), st.linear.weight_inv.detach()]) for st in steps]).double().cpu()
+        ld = torch.linalg.slogdet(mats)[1]
+        winvT = torch.linalg.inv(mats[:, 0]).transpose(1, 2).contiguous().float()
+        if not self.prior_winvT:
+            self.prior_winvT = [torch.empty((mats.shape[-1], mats.shape[-1]), device=dev) for _ in steps]
+        for j in range(len(steps)):
+            self.prior_winvT[j].copy_(winvT[j])
+            rec[j]['ld_w'], rec[j]['ld_winv'] = float(ld[j, 0]), float(ld[j, 1])
 
         def op(kind, backward, offs, skip=0, up=0):
             o = L.FlowOp()
@@ -491,10 +556,13 @@ class FlowEngine:
             fw += [op(0, 0, r['an']), op(1, 0, [r['W']]), op(2, 0, r['c1u'], 0, 1), op(2, 0, r['c1d'], 0, 0), op(0, 0, r['uan']),
                    op(2, 0, r['c2u'], 1, 1), op(2, 0, r['c2d'], 1, 0)]
             ld_f += r['ld_w']
-        for name, prog, ld in (('backward', bw, ld_b), ('forward', fw, ld_f)):
-            arr = (L.FlowOp * len(prog))(*prog)
-            buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-            self.prior_ops[name] = (buf, len(prog), ld)
+        for name, prog, ldc in (('backward', bw, ld_b), ('forward', fw, ld_f)):
+            if name in self.prior_ops:                       # the op program (offsets) is fixed; only the constant moves
+                self.prior_ops[name] = (self.prior_ops[name][0], len(prog), ldc)
+            else:
+                arr = (L.FlowOp * len(prog))(*prog)
+                buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+                self.prior_ops[name] = (buf, len(prog), ldc)
 
     # ---- building blocks
     def prior_flow(self, z, direction, want_logdet=False, kl_base=None):
@@ -781,17 +849,26 @@ class FlowEngine:
         if not hasattr(self, 'enc_train'):
             self.enc_train = EncoderTrain(self)
         N, E = self.N, self.enc
-        enc_out = self.enc_train.forward(x)
-        c = self._static('tr_c', E['c'])
-        L.call('indm_linear_f32', L.ptr(enc_out), L.ptr(E['fc_w']), L.ptr(E['fc_b']), L.ptr(c), N, enc_out.shape[1], c.shape[1], 0, 0, L.DTYPE_F32)
+        xs = self._static('tr_x', x)
+        xs.copy_(x)
         if eps is None:
             L.call('indm_randn_f32', L.ptr(self.eps), self.eps.numel(), seed, 0x7F200000 + offset)
             eps = self.eps
         eps_s = self._static('tr_eps', self.eps)
         eps_s.copy_(eps)
+        c = self._static('tr_c', E['c'])
         h = self._static('tr_h', self.h)
-        L.call('indm_posterior_sample', L.ptr(c), L.ptr(eps_s), L.ptr(h), L.ptr(E['logq']), N)
-        _, kl = self.prior_flow(h, 'forward', kl_base=E['logq'])
+        self.enc_train._ensure()
+        out = {}
+
+        def body():
+            enc_out = self.enc_train.forward(xs)
+            out['enc_out'] = enc_out
+            L.call('indm_linear_f32', L.ptr(enc_out), L.ptr(E['fc_w']), L.ptr(E['fc_b']), L.ptr(c), N, enc_out.shape[1], c.shape[1], 0, 0, L.DTYPE_F32)
+            L.call('indm_posterior_sample', L.ptr(c), L.ptr(eps_s), L.ptr(h), L.ptr(E['logq']), N)
+        self._graphed(('posterior',), body)
+        enc_out = out.get('enc_out', self.enc_train.top.view(N, -1))
+        _, kl = self.prior_flow(h, 'forward', kl_base=E['logq'])      # carries log|det W| as a host constant: stays out of the graph
         self._train_saved = (h, c, eps_s, enc_out)
         return h, kl
 
@@ -801,9 +878,17 @@ class FlowEngine:
         if not hasattr(self, '_fbw'):
             self._fbw, self._pbw = FlowBackward(self), PosteriorBackward(self)
         h, c, eps, enc_out = self._train_saved
-        _, gh_blocks = self._fbw.run(gz, gloss)
-        g_enc = self._pbw.run(h, gh_blocks, -gloss, c, eps, enc_out)
-        self.enc_train.backward(g_enc)
+        gz_s, gl_s = self._static('bw_gz', gz), self._static('bw_gl', gloss)
+        gz_s.copy_(gz)
+        gl_s.copy_(gloss)
+
+        def body():
+            _, gh_blocks = self._fbw.run(gz_s, gl_s)
+            g_enc = self._pbw.run(h, gh_blocks, -gl_s, c, eps, enc_out)
+            self.enc_train.backward(g_enc)
+        # the whole flow backward is a fixed launch sequence (~1600 launches): one graph, keyed by where the gradients live
+        anchor = next(p for p in self.core.parameters() if p.requires_grad)
+        self._graphed(('bwd', anchor.grad.data_ptr() if anchor.grad is not None else 0, tuple(x[0] for x in self._saved)), body)
 
     # ---- power-series log-det (iresblock.py:90-174): VJP chain of g on the tensor cores
     def _g_store(self, i, s, m, x_nchw, out):
@@ -859,7 +944,8 @@ class FlowEngine:
         if not hasattr(self, 'd1'):
             self.d0 = torch.empty((x.numel(),), device=self.dev)
             self.d1, self.d2 = torch.empty_like(self.u1), torch.empty_like(self.u2)
-        logpx = torch.zeros((N,), device=self.dev)
+        logpx = self._static('logpx', torch.empty((N,), device=self.dev))
+        logpx.zero_()
         nb = self.nb
         bi = 0
         self.vjp_count = 0
@@ -885,33 +971,37 @@ class FlowEngine:
                 else:
                     L.call('indm_randn_f32', L.ptr(ve), ve.numel(), seed, 0x7F300000 + (offset << 8) + bi)
                 xin, xout = xs[cur_x], xs[1 - cur_x]
-                d0, d1, d2 = self._g_store(i, s, m, xin, xout)
-                cur = ve
-                if not training:
-                    # basic estimator: sum_k (-1)^(k+1)/k c_k <J^k^T eps, eps>
-                    for k in range(1, K + 1):
-                        nxt = bufs[k & 1]
-                        self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
-                        L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-((-1) ** (k + 1)) / k * coef[k - 1]), 1)
-                        cur = nxt
-                    self.vjp_count += K
-                else:
-                    # Neumann estimator (value): w = eps + sum_k (-1)^k c_k J^k^T eps ; logdet = <J^T w, eps>
-                    neumann.copy_(ve)
-                    for k in range(1, K + 1):
-                        nxt = bufs[k & 1]
-                        self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
-                        L.call('indm_axpy_f32', L.ptr(neumann), L.ptr(nxt), ctypes.c_float(((-1) ** k) * coef[k - 1]), neumann.numel())
-                        cur = nxt
-                    nxt = bufs[(K + 1) & 1]
-                    self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
-                    L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
-                    self.vjp_count += K + 1
-                    if save:
-                        # what the block's backward needs: its input, the probe and the (constant) Neumann vector
-                        sx, sv, sw = (self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w'))
-                        sx.copy_(xin); sv.copy_(ve); sw.copy_(neumann)
-                        self._saved.append((i, s, m, sx, sv, sw))
+
+                def body(i=i, s=s, m=m, xin=xin, xout=xout, K=K, coef=coef):
+                    d0, d1, d2 = self._g_store(i, s, m, xin, xout)
+                    cur = ve
+                    if not training:
+                        # basic estimator: sum_k (-1)^(k+1)/k c_k <J^k^T eps, eps>
+                        for k in range(1, K + 1):
+                            nxt = bufs[k & 1]
+                            self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
+                            L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-((-1) ** (k + 1)) / k * coef[k - 1]), 1)
+                            cur = nxt
+                    else:
+                        # Neumann estimator (value): w = eps + sum_k (-1)^k c_k J^k^T eps ; logdet = <J^T w, eps>
+                        neumann.copy_(ve)
+                        for k in range(1, K + 1):
+                            nxt = bufs[k & 1]
+                            self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
+                            L.call('indm_axpy_f32', L.ptr(neumann), L.ptr(nxt), ctypes.c_float(((-1) ** k) * coef[k - 1]), neumann.numel())
+                            cur = nxt
+                        nxt = bufs[(K + 1) & 1]
+                        self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
+                        L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
+                        if save:
+                            # what the block's backward needs: its input, the probe and the (constant) Neumann vector
+                            sx, sv, sw = (self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w'))
+                            sx.copy_(xin); sv.copy_(ve); sw.copy_(neumann)
+                # one CUDA graph per (block, series length): the chain is ~5 (K + 2) small launches
+                self._graphed(('blk', i, K, bool(training), bool(save), float(self.lamb[i])), body)
+                self.vjp_count += K if not training else K + 1
+                if training and save:
+                    self._saved.append((i, s, m) + tuple(self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w')))
                 cur_x = 1 - cur_x
                 bi += 1
             x = xs[cur_x]
@@ -922,7 +1012,7 @@ class FlowEngine:
             out = out.view(shape[0], shape[1], 2, 2, shape[2] // 2, shape[3] // 2).permute(0, 1, 4, 2, 5, 3).reshape(shape)
         else:
             out = out.view(shape)
-        return out.clone(), logpx                      # the chain lives in engine-owned buffers: hand out a copy
+        return out.clone(), logpx.clone()              # the chain lives in engine-owned buffers: hand out copies
 
     def forward_map(self, x, h):
         """ResidualFlow.fwdpass(x, h, eval_logdet=False) on the flow's own input layout (resflow_.py:310-324)."""

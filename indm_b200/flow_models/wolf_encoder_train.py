@@ -107,9 +107,11 @@ class EncoderTrain:
     def _ensure(self):
         v = self.eng.version()
         if self._version != v:
-            with torch.no_grad():
+            def body():
                 for job in self.pack_jobs:
                     job()
+            with torch.no_grad():
+                self.eng._graphed(('enc_train_pack',), body)
             self._version = v
 
     # ---- launches

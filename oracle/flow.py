@@ -319,27 +319,36 @@ def _bn_eval(P, p, x, eps=1e-5):
     return x * sc[None, :, None, None] + (P[p + 'bias'] - P[p + 'running_mean'] * sc)[None, :, None, None]
 
 
-def encoder_forward(config, P, x):
+def _bn_train(P, p, x, eps=1e-5):
+    """nn.BatchNorm2d in training mode: batch statistics over (N, H, W), biased variance (running buffers not touched here)."""
+    mean = x.mean(dim=(0, 2, 3), keepdim=True)
+    var = ((x - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps) * P[p + 'weight'][None, :, None, None] + P[p + 'bias'][None, :, None, None]
+
+
+def encoder_forward(config, P, x, training=False):
     """GlobalResNetEncoderBatchNorm.forward (modules/encoders/global_encoder.py:12-36) over ResNetBlockBatchNorm
-    (nnet/resnets/resnet_batchnorm.py:18-76), ELU activation, eval-mode batch norm.  Returns [B, out_planes*h*w]."""
+    (nnet/resnets/resnet_batchnorm.py:18-76), ELU activation; batch norm with running statistics (eval) or batch
+    statistics (training=True, what the joint training step runs).  Returns [B, out_planes*h*w]."""
     enc = config.flow.wolf_params['discriminator']['encoder']
+    _bn = _bn_train if training else _bn_eval
     for lv, hid in enumerate(enc['hidden_planes']):
         for m, stride in enumerate((1, 2)):
             p = f'discriminator.encoder.net.resnet{lv}.main.{m}.'
             out = F.conv2d(x, P[p + 'conv1.weight'], stride=stride, padding=1)
-            out = F.elu(_bn_eval(P, p + 'bn1.', out))
-            out = _bn_eval(P, p + 'bn2.', F.conv2d(out, P[p + 'conv2.weight'], padding=1))
+            out = F.elu(_bn(P, p + 'bn1.', out))
+            out = _bn(P, p + 'bn2.', F.conv2d(out, P[p + 'conv2.weight'], padding=1))
             if (p + 'downsample.0.weight') in P:
-                x = _bn_eval(P, p + 'downsample.1.', F.conv2d(x, P[p + 'downsample.0.weight'], stride=stride))
+                x = _bn(P, p + 'downsample.1.', F.conv2d(x, P[p + 'downsample.0.weight'], stride=stride))
             x = F.elu(out + x)
     x = F.elu(F.conv2d(x, P['discriminator.encoder.net.top.weight'], P['discriminator.encoder.net.top.bias']))
     return x.reshape(x.shape[0], -1)
 
 
-def posterior_sample_and_kl(config, P, x, eps):
+def posterior_sample_and_kl(config, P, x, eps, training=False):
     """GaussianDiscriminator.sampling_and_KL (modules/discriminators/gaussian.py:67-76) with nsamples = 1 and the
     reparameterisation noise `eps` [B, 64] supplied; FlowPrior.calcKL (priors/flow.py:233-253).  Returns (h, KL, mu, logvar)."""
-    c = encoder_forward(config, P, x)
+    c = encoder_forward(config, P, x, training)
     c = F.linear(c, _wn(P, 'discriminator.fc.linear.'), P['discriminator.fc.linear.bias'])
     mu, logvar = c.chunk(2, dim=1)
     h = eps * torch.exp(0.5 * logvar) + mu
@@ -438,6 +447,20 @@ def wolf_forward(config, P, x, eps_post, ns, varepss, training=False):
         x = squeeze2(x)
     h, kl, _, _ = posterior_sample_and_kl(config, P, x, eps_post)
     z, logpx = resflow_forward_logdet(config, P, x, h, ns, varepss, training)
+    if config.flow.squeeze:
+        z = unsqueeze2(z)
+    return z, -logpx - kl, h, kl
+
+
+def wolf_train_forward(config, P, x, eps_post, ns, varepss):
+    """WolfCore.forward(reverse=False) in TRAINING mode (wolf.py:90-128), differentiable exactly like the reference's graph:
+    batch-statistics encoder -> h ~ q(h|x), KL -> residual flow with the Neumann log-det series (n + 2 terms, constant Neumann
+    vector, last VJP with create_graph).  Returns (z, logdet - KL, h, KL); torch.autograd of any scalar of (z, logdet - KL) w.r.t.
+    the entries of P is the gradient the joint training step applies (losses.py:300-304)."""
+    if config.flow.squeeze:
+        x = squeeze2(x)
+    h, kl, _, _ = posterior_sample_and_kl(config, P, x, eps_post, training=True)
+    z, logpx = resflow_forward_logdet(config, P, x, h, ns, varepss, training=True, differentiable=True)
     if config.flow.squeeze:
         z = unsqueeze2(z)
     return z, -logpx - kl, h, kl

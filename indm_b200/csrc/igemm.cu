@@ -16,6 +16,7 @@
 // drain TMEM (warp w owns TMEM lanes 32w..32w+31 = tile rows).  Several CTAs are co-resident per SM so one CTA's
 // epilogue overlaps another's main loop.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "../../include/indm_b200.h"
 #include "common.cuh"
@@ -127,14 +128,20 @@ constexpr int igemm_threads(bool tf32) { return 64 + 32 * epi_warps(tf32) + (tf3
 //   KIND 2: FP32 NHWC output ([+ bias]) * scale [+ residual * res_scale]                         (Conv_1 [+ Conv_2], NIN_3, Q.K^T)
 //   (no activation / cos side output / multiplier / per-image scale / NCHW / ragged-column paths in either)
 //   KIND 0: every feature tested at run time.
-template <int BLOCK_N, bool TF32, int KIND>
+//   CTA2: the CTAs of a 2-cluster (a CTA pair on one TPC) own two consecutive M tiles of the same N tile and issue ONE
+//   tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own A tile and half of the B tile (TMA credits the LEADER's full
+//   barrier), the leader's MMA warp issues for both, tcgen05.commit multicasts stage-free / accumulator-ready to both CTAs, and
+//   both CTAs' epilogue warps release the accumulator buffer on the leader's barrier.  Per-CTA operand bytes per MAC drop from
+//   (128 + N) to (128 + N/2) per 128 x N x 64 chunk: the L2 -> SM operand stream was the measured bound of the one-CTA kernel.
+template <int BLOCK_N, bool TF32, int KIND, bool CTA2>
 __global__ void __launch_bounds__(igemm_threads(TF32), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
   constexpr int KCHUNK = TF32 ? 32 : 64;           // elements per 128-byte swizzle row
   constexpr int A_BYTES = kTileM * 128;            // 16 KB
-  constexpr int B_BYTES = BLOCK_N * 128;
-  constexpr uint32_t IDESC = umma_idesc(TF32 ? 2u : 1u, 128u, (uint32_t)BLOCK_N);
+  constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128;   // rows of B staged by THIS CTA
+  constexpr uint32_t IDESC = umma_idesc(TF32 ? 2u : 1u, CTA2 ? 256u : 128u, (uint32_t)BLOCK_N);
+  static_assert(!(CTA2 && TF32), "the CTA-pair path is BF16 only");
   constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   constexpr int NSLAB = BLOCK_N / 32 + (BLOCK_N < 32 ? 1 : 0);
@@ -164,7 +171,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int iters = iters1 + p.chunks2;
   const uint32_t a_box_bytes = (uint32_t)(p.BW * p.BH * p.BN) * 128u;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
+  // CTA2: work items are PAIRS of M tiles (2 mp, 2 mp + 1) x one N tile; CTA rank r of the cluster takes M tile 2 mp + r (an M tile
+  // past the end is all out-of-bounds: TMA zero-fills it, the epilogue masks every row)
+  const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const int total_tiles = CTA2 ? ((m_tiles + 1) / 2) * p.n_tiles : m_tiles * p.n_tiles * p.ksplit;
+  const int t_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -180,16 +192,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 32 * EPI);
+      mbar_init(&tempty_bar[b], (CTA2 ? 64 : 32) * EPI);     // CTA2: the leader's barrier collects both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();      // the peer's barriers must be initialised before TMA / arrives target them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
@@ -199,16 +217,43 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ================= TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int ks = t % p.ksplit, tt = t / p.ksplit;
-        const int nt = tt % p.n_tiles, mt = tt / p.n_tiles;
+      for (int t = t_first; t < total_tiles; t += t_step) {
+        const int ks = CTA2 ? 0 : t % p.ksplit, tt = CTA2 ? t : t / p.ksplit;
+        const int nt = tt % p.n_tiles, mt = CTA2 ? 2 * (tt / p.n_tiles) + cta_rank : tt / p.n_tiles;
         const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
-        const int ncol0 = nt * BLOCK_N;
-        const int it_begin = (int)((long long)iters * ks / p.ksplit), it_end = (int)((long long)iters * (ks + 1) / p.ksplit);
+        const int ncol0 = nt * BLOCK_N + (CTA2 ? cta_rank * (BLOCK_N / 2) : 0);   // CTA2: this CTA's half of the B tile
+        const int it_begin = CTA2 ? 0 : (int)((long long)iters * ks / p.ksplit), it_end = CTA2 ? iters : (int)((long long)iters * (ks + 1) / p.ksplit);
         for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
+          if (CTA2) {
+            // one arrival (the leader's) per phase; both CTAs' four loads complete_tx on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (a_box_bytes + (uint32_t)B_BYTES));
+            if (it < iters1) {
+              const int tap = it / p.chunks1;
+              const int ch = it - tap * p.chunks1;
+              int ay = y0, ax = x0;
+              if (p.stride == 2) {
+                ay = 2 * y0 - p.pad + (p.taps == 9 ? tap / 3 : 0);
+                ax = 2 * x0 - p.pad + (p.taps == 9 ? tap % 3 : 0);
+              } else if (p.taps == 9) {
+                ay += tap / 3 - 1;
+                ax += tap % 3 - 1;
+              }
+              tma_load_4d_2sm(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
+              tma_load_3d_2sm(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, tap);
+            } else {
+              const int ch = it - iters1;
+              tma_load_4d_2sm(a_dst, &tmA2, &full_bar[stage], ch * KCHUNK, x0, y0, n0);
+              tma_load_3d_2sm(b_dst, &tmB2, &full_bar[stage], ch * KCHUNK, ncol0, 0);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], a_box_bytes + (uint32_t)B_BYTES);
           if (it < iters1) {
             const int tap = it / p.chunks1;
@@ -238,18 +283,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer
+    if (lane == 0 && cta_rank == 0) {
+      // ================= MMA issuer (CTA2: the pair's leader issues for both CTAs)
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      for (int t = t_first; t < total_tiles; t += t_step, ++j) {
         const int buf = j & 1;
         mbar_wait(&tempty_bar[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * ACC_COLS;
-        const int ks = t % p.ksplit;
-        const int it_begin = (int)((long long)iters * ks / p.ksplit), it_end = (int)((long long)iters * (ks + 1) / p.ksplit);
+        const int ks = CTA2 ? 0 : t % p.ksplit;
+        const int it_begin = CTA2 ? 0 : (int)((long long)iters * ks / p.ksplit), it_end = CTA2 ? iters : (int)((long long)iters * (ks + 1) / p.ksplit);
         for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(TF32 ? &split_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
@@ -265,6 +310,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               umma_tf32(d_tmem, adesc + o, blo + o, IDESC, 1u);
               umma_tf32(d_tmem, adesc + o, bdesc + o, IDESC, 1u);
             }
+          } else if (CTA2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -272,13 +321,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((it - it_begin) | k) != 0);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+          if (CTA2) umma_commit_2sm(&empty_bar[stage]);   // frees this smem stage in both CTAs
+          else umma_commit(&empty_bar[stage]);            // frees this smem stage when the MMAs above have read it
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator complete
+        if (CTA2) umma_commit_2sm(&tfull_bar[buf]);       // accumulator complete, both CTAs' epilogues
+        else umma_commit(&tfull_bar[buf]);
       }
     }
     __syncwarp();
@@ -337,10 +388,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int chunk = lane & 7, rsub = lane >> 3;  // transposed domain: 4 columns (chunk), rows it*4 + rsub
     const long long hw = (long long)p.H * p.W;
     int j = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+    for (int t = t_first; t < total_tiles; t += t_step, ++j) {
       const int buf = j & 1;
-      const int ks = t % p.ksplit, tt = t / p.ksplit;
-      const int nt = tt % p.n_tiles, mt = tt / p.n_tiles;
+      const int ks = CTA2 ? 0 : t % p.ksplit, tt = CTA2 ? t : t / p.ksplit;
+      const int nt = tt % p.n_tiles, mt = CTA2 ? 2 * (tt / p.n_tiles) + cta_rank : tt / p.n_tiles;
       const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
       const int ncol0 = nt * BLOCK_N;
       float* const out32 = p.out_f32 + (long long)ks * p.split_stride;     // split-K: this slice's partial-sum plane
@@ -364,7 +415,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
       if (half >= NSLAB) {                       // narrow tile: this warp has no slab, it only releases the buffer
         tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);
+        if (CTA2) mbar_arrive_leader(&tempty_bar[buf]);
+        else mbar_arrive(&tempty_bar[buf]);
       }
 #pragma unroll 1
       for (int sl = half; sl < NSLAB; sl += SLAB_STEP) {
@@ -400,7 +452,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_wait();
         if (sl + SLAB_STEP >= NSLAB) {
           tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);        // this warp's share of the accumulator buffer has left TMEM
+          if (CTA2) mbar_arrive_leader(&tempty_bar[buf]);
+          else mbar_arrive(&tempty_bar[buf]);   // this warp's share of the accumulator buffer has left TMEM
         }
         if (c0 >= p.Cout) continue;             // uniform across the CTA
         if (direct) {
@@ -575,8 +628,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CTA2) {
+    cluster_sync_all();          // neither CTA may retire (or free TMEM) while the peer still reads its smem / signals its barriers
+    if (warp == 0) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 
@@ -634,11 +692,11 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, int S, long l
   }
 }
 
-template <int BLOCK_N, bool TF32, int KIND>
+template <int BLOCK_N, bool TF32, int KIND, bool CTA2 = false>
 int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2, IgemmParams p,
                  int m_tiles, int n_tiles, cudaStream_t stream) {
   constexpr int A_BYTES = kTileM * 128;
-  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128;
   const int stage_bytes = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
   const int overhead = 1024 + epi_warps(TF32) * 4096 + (3 * kMaxStages + 6) * 8;
   // one persistent CTA per SM: the smem ring takes what the SM has
@@ -649,7 +707,7 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
   p.n_tiles = n_tiles;
   const int smem = stages * stage_bytes + overhead;
   static bool configured = false;
-  auto kern = igemm_kernel<BLOCK_N, TF32, KIND>;
+  auto kern = igemm_kernel<BLOCK_N, TF32, KIND, CTA2>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
@@ -657,6 +715,14 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
       return INDM_ERR_CUDA;
     }
     configured = true;
+  }
+  if (CTA2) {
+    const long long pairs = (long long)((m_tiles + 1) / 2) * n_tiles;
+    const int half_sms = indm_num_sms() / 2;
+    const int grid = 2 * (int)(pairs < half_sms ? pairs : half_sms);
+    indm_launch_pdl_cluster2(kern, dim3(grid), dim3(igemm_threads(TF32)), (size_t)smem, stream, a, b, a2, b2, p);
+    INDM_CHECK_LAUNCH("igemm (CTA pair)");
+    return INDM_OK;
   }
   const long long total = (long long)m_tiles * n_tiles * p.ksplit;
   const int grid = (int)(total < indm_num_sms() ? total : indm_num_sms());
@@ -827,13 +893,23 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   }
   INDM_CHECK_ARG(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "igemm: block_n %d unsupported", block_n);
   const int n_tiles = (d->Cout + block_n - 1) / block_n;
+  // compile-time epilogue specialisation (see igemm_kernel)
+  int kind = 0;
+  const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
+  if (plain && !d->residual && d->out_bf16 && !d->out_f32) kind = 1;
+  if (plain && !d->rowbias && d->out_f32 && !d->out_bf16) kind = 2;
+  // CTA pairs (cta_group::2) for the launches that fill the chip: wide tiles of the plain BF16 convolutions
+  static const bool cta2_enabled = []() { const char* e = getenv("INDM_IGEMM_CTA2"); return !(e && e[0] == '0'); }();
+  const bool cta2 = cta2_enabled && kind != 0 && p.ksplit == 1 && !d->batched_b && (block_n == 128 || block_n == 256) &&
+                    (long long)m_tiles * n_tiles >= indm_num_sms();
+  const int b_rows = cta2 ? block_n / 2 : block_n;
   {
     const long long ld = d->b_ld ? d->b_ld : d->Cin;
     const long long ts = d->b_tap_stride ? d->b_tap_stride : (long long)d->Cout * ld;
     const int third = d->batched_b ? d->N : d->taps;
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)third};
     uint64_t str[2] = {(uint64_t)ld * esz, (uint64_t)ts * esz};
-    uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)block_n, 1u};
+    uint32_t box[3] = {(uint32_t)kchunk, (uint32_t)b_rows, 1u};
     int rc = indm_make_tmap(&tmB, dt, 3, d->b, dims, str, box, "igemm B");
     if (rc) return rc;
   }
@@ -848,7 +924,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     const long long ldb = d->b2_ld ? d->b2_ld : d->Cin2;
     uint64_t bdims[3] = {(uint64_t)d->Cin2, (uint64_t)d->Cout, 1};
     uint64_t bstr[2] = {(uint64_t)ldb * esz, (uint64_t)d->Cout * ldb * esz};
-    uint32_t bbox[3] = {(uint32_t)kchunk, (uint32_t)block_n, 1u};
+    uint32_t bbox[3] = {(uint32_t)kchunk, (uint32_t)b_rows, 1u};
     rc = indm_make_tmap(&tmB2, dt, 3, d->b2, bdims, bstr, bbox, "igemm B2");
     if (rc) return rc;
   } else {
@@ -856,7 +932,6 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     tmB2 = tmB;
   }
 
-  // compile-time epilogue specialisation (see igemm_kernel)
   if (p.ksplit > 1) {
     int rc = tf32 ? (block_n == 256 ? launch_igemm<256, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
                                     : launch_igemm<128, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream))
@@ -874,10 +949,12 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     INDM_CHECK_LAUNCH("splitk_finish");
     return INDM_OK;
   }
-  int kind = 0;
-  const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
-  if (plain && !d->residual && d->out_bf16 && !d->out_f32) kind = 1;
-  if (plain && !d->rowbias && d->out_f32 && !d->out_bf16) kind = 2;
+  if (cta2) {
+    if (block_n == 256) return kind == 1 ? launch_igemm<256, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+                                         : launch_igemm<256, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+    return kind == 1 ? launch_igemm<128, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+                     : launch_igemm<128, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+  }
 #define INDM_LAUNCH(BN_)                                                                                  \
   if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);          \
   if (kind == 1) return launch_igemm<BN_, false, 1>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \

@@ -110,6 +110,48 @@ def test_igemm_conv3x3(dtype, N, S, Cin, Cout, bn):
     assert rel_l2(o16.float().cpu(), want) < 4e-3
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("N,S,Cin,Cin2,Cout", [(20, 32, 128, 0, 128), (38, 16, 256, 0, 256), (302, 8, 128, 0, 128), (80, 16, 128, 256, 256),
+                                               (75, 16, 64, 0, 512)])
+def test_igemm_cta_pair_path(kind, N, S, Cin, Cin2, Cout):
+    """Launches that fill the chip (>= 148 output tiles) with the plain BF16 epilogues take the cta_group::2 path: pairs of M tiles
+    issued as one M = 256 MMA, B split across the pair.  Covers 128- and 256-wide tiles, two N tiles, an odd number of M tiles
+    (302 images at 8x8: 151 tiles, the last pair has one all-out-of-bounds tile), the fused second K segment, fused GroupNorm
+    statistics, against fp64 convolution."""
+    dtype = L.DTYPE_BF16
+    x = round_in(rnd(N, Cin, S, S, seed=40), dtype)
+    w = round_in(rnd(Cout, Cin, 3, 3, seed=41) / math.sqrt(9 * Cin), dtype)
+    bias = rnd(Cout, seed=42)
+    kw = dict(dtype=dtype, a=dev_op(nhwc(x), dtype), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dtype), Cout=Cout, taps=9, bias=bias.to(DEV),
+              scale=0.7071, out_ld=Cout)
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    if Cin2:
+        xs = round_in(rnd(N, Cin2, S, S, seed=43), dtype)
+        w2 = round_in(rnd(Cout, Cin2, 1, 1, seed=44) / math.sqrt(Cin2), dtype)
+        kw.update(a2=dev_op(nhwc(xs), dtype), Cin2=Cin2, b2=dev_op(w2.reshape(Cout, Cin2), dtype))
+        want = want + F.conv2d(xs.double(), w2.double())
+    want = nhwc(want)
+    part = torch.zeros((N, 32, 2), device=DEV)
+    if kind == 1:
+        rowb = rnd(N, Cout, seed=45)
+        out = torch.zeros((N, S, S, Cout), device=DEV, dtype=torch.bfloat16)
+        kw.update(rowbias=rowb.to(DEV), rowbias_ld=Cout, out_bf16=out, gn_partial=part, gn_cpg=Cout // 32, gn_groups=32)
+        want = (want + rowb[:, None, None, :].double()) * 0.7071
+        tol = 4e-3
+    else:
+        res = rnd(N, S, S, Cout, seed=46)
+        out = torch.full((N, S, S, Cout), float('nan'), device=DEV)
+        kw.update(residual=res.to(DEV), res_ld=Cout, res_scale=0.7071, out_f32=out, gn_partial=part, gn_cpg=Cout // 32, gn_groups=32)
+        want = want * 0.7071 + res.double() * 0.7071
+        tol = 2e-5
+    L.igemm(**kw)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().cpu(), want) < tol
+    g = want.reshape(N, S * S, 32, Cout // 32)
+    ws, wq = g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))
+    assert rel_l2(part[..., 0].cpu(), ws) < 2e-3 and rel_l2(part[..., 1].cpu(), wq) < 2e-3
+
+
 @pytest.mark.parametrize("dtype", [L.DTYPE_BF16, L.DTYPE_TF32])
 def test_igemm_fused_skip_segment(dtype):
     N, S, C1, C2, Cout = 2, 16, 128, 384, 256

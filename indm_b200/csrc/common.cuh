@@ -116,6 +116,18 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// one lane of a converged warp (elect.sync): lets single-thread instructions (TMA, tcgen05.mma, commit) sit inside warp-uniform
+// control flow, so their operands stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -249,7 +261,10 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* tmap
 }
 // arrive on the leader CTA's copy of `bar` (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
+  // relaxed: the only thing the leader's MMA warp needs ordered before this arrive is the tcgen05.ld of the accumulator, which
+  // tcgen05.wait::ld + tcgen05.fence::before_thread_sync already give; a release at cluster scope compiled to MEMBAR.ALL.GPU and
+  // waited for every outstanding global load / store of the epilogue thread (13 % of the kernel's stall samples)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");

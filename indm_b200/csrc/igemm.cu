@@ -70,6 +70,7 @@ struct IgemmParams {
   int gn_goff;           // group index of output channel 0 inside the consumer's GroupNorm (non-zero for the second half of a concat)
   float* gn2_partial;    // second consumer of the same tensor (skip connections feed two GroupNorms with different group sizes)
   int gn2_cpg, gn2_groups, gn2_goff;
+  int dbg;                // development probes (INDM_IGEMM_DBG): 1 = epilogue without global loads / stores
 };
 
 // ---------------------------------------------------------------- epilogue helpers
@@ -213,78 +214,81 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = t_first; t < total_tiles; t += t_step) {
-        const int ks = CTA2 ? 0 : t % p.ksplit, tt = CTA2 ? t : t / p.ksplit;
-        const int nt = tt % p.n_tiles, mt = CTA2 ? 2 * (tt / p.n_tiles) + cta_rank : tt / p.n_tiles;
-        const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
-        const int ncol0 = nt * BLOCK_N + (CTA2 ? cta_rank * (BLOCK_N / 2) : 0);   // CTA2: this CTA's half of the B tile
-        const int it_begin = CTA2 ? 0 : (int)((long long)iters * ks / p.ksplit), it_end = CTA2 ? iters : (int)((long long)iters * (ks + 1) / p.ksplit);
-        for (int it = it_begin; it < it_end; ++it) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // ================= TMA producer.  The WHOLE warp runs the loop (warp-uniform control flow: coordinates, stage and phase live
+    // in uniform registers) and one elected lane issues; inside a lane-0 branch every operand of UTMALDG / UTCHMMA went through
+    // an ELECT + R2UR.BROADCAST waterfall (~90 dependent instructions per K iteration on the issuing thread, the measured
+    // ~0.45 us fixed cost per iteration that bounded the main loop).
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = t_first; t < total_tiles; t += t_step) {
+      const int ks = CTA2 ? 0 : t % p.ksplit, tt = CTA2 ? t : t / p.ksplit;
+      const int nt = tt % p.n_tiles, mt = CTA2 ? 2 * (tt / p.n_tiles) + cta_rank : tt / p.n_tiles;
+      const int x0 = (mt % p.tiles_x) * p.BW, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (mt / (p.tiles_x * p.tiles_y)) * p.BN;
+      const int ncol0 = nt * BLOCK_N + (CTA2 ? cta_rank * (BLOCK_N / 2) : 0);   // CTA2: this CTA's half of the B tile
+      const int it_begin = CTA2 ? 0 : (int)((long long)iters * ks / p.ksplit), it_end = CTA2 ? iters : (int)((long long)iters * (ks + 1) / p.ksplit);
+      // (tap, chunk) of the first iteration, then advanced incrementally: no division in the loop
+      int tap = it_begin < iters1 ? it_begin / p.chunks1 : 0;
+      int ch = it_begin < iters1 ? it_begin - tap * p.chunks1 : it_begin - iters1;
+      int ty = p.taps == 9 ? tap / 3 : 0, tx = p.taps == 9 ? tap - 3 * ty : 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* a_dst = sA + (size_t)stage * A_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * B_BYTES;
+          const bool seg1 = it < iters1;
+          int ay = y0, ax = x0;
+          if (seg1) {
+            if (p.stride == 2) {
+              // strided window: input pixel (2y + ky - pad, 2x + kx - pad); the tensor map traverses with element stride 2
+              ay = 2 * y0 - p.pad + ty;
+              ax = 2 * x0 - p.pad + tx;
+            } else if (p.taps == 9) {
+              ay += ty - 1;
+              ax += tx - 1;
+            }
+          }
           if (CTA2) {
             // one arrival (the leader's) per phase; both CTAs' four loads complete_tx on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (a_box_bytes + (uint32_t)B_BYTES));
-            if (it < iters1) {
-              const int tap = it / p.chunks1;
-              const int ch = it - tap * p.chunks1;
-              int ay = y0, ax = x0;
-              if (p.stride == 2) {
-                ay = 2 * y0 - p.pad + (p.taps == 9 ? tap / 3 : 0);
-                ax = 2 * x0 - p.pad + (p.taps == 9 ? tap % 3 : 0);
-              } else if (p.taps == 9) {
-                ay += tap / 3 - 1;
-                ax += tap % 3 - 1;
-              }
+            if (seg1) {
               tma_load_4d_2sm(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
               tma_load_3d_2sm(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, tap);
             } else {
-              const int ch = it - iters1;
               tma_load_4d_2sm(a_dst, &tmA2, &full_bar[stage], ch * KCHUNK, x0, y0, n0);
               tma_load_3d_2sm(b_dst, &tmB2, &full_bar[stage], ch * KCHUNK, ncol0, 0);
             }
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-            continue;
-          }
-          mbar_arrive_expect_tx(&full_bar[stage], a_box_bytes + (uint32_t)B_BYTES);
-          if (it < iters1) {
-            const int tap = it / p.chunks1;
-            const int ch = it - tap * p.chunks1;
-            int ay = y0, ax = x0;
-            if (p.stride == 2) {
-              // strided window: input pixel (2y + ky - pad, 2x + kx - pad); the tensor map traverses with element stride 2
-              ay = 2 * y0 - p.pad + (p.taps == 9 ? tap / 3 : 0);
-              ax = 2 * x0 - p.pad + (p.taps == 9 ? tap % 3 : 0);
-            } else if (p.taps == 9) {
-              ay += tap / 3 - 1;
-              ax += tap % 3 - 1;
-            }
-            tma_load_4d(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
-            tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, p.batched_b ? n0 : tap);
           } else {
-            const int ch = it - iters1;
-            tma_load_4d(a_dst, &tmA2, &full_bar[stage], ch * KCHUNK, x0, y0, n0);
-            tma_load_3d(b_dst, &tmB2, &full_bar[stage], ch * KCHUNK, ncol0, 0);
+            mbar_arrive_expect_tx(&full_bar[stage], a_box_bytes + (uint32_t)B_BYTES);
+            if (seg1) {
+              tma_load_4d(a_dst, &tmA, &full_bar[stage], ch * KCHUNK, ax, ay, n0);
+              tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * KCHUNK, ncol0, p.batched_b ? n0 : tap);
+            } else {
+              tma_load_4d(a_dst, &tmA2, &full_bar[stage], ch * KCHUNK, x0, y0, n0);
+              tma_load_3d(b_dst, &tmB2, &full_bar[stage], ch * KCHUNK, ncol0, 0);
+            }
           }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+        }
+        __syncwarp();
+        // advance (tap, chunk): segment 1 walks taps x chunks1, then segment 2 walks chunks2
+        if (++ch == (it < iters1 ? p.chunks1 : p.chunks2)) {
+          ch = 0;
+          if (it < iters1) {
+            ++tap;
+            if (++tx == 3) {
+              tx = 0;
+              ++ty;
+            }
           }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && cta_rank == 0) {
-      // ================= MMA issuer (CTA2: the pair's leader issues for both CTAs)
+    if (cta_rank == 0) {
+      // ================= MMA issuer (CTA2: the pair's leader issues for both CTAs); warp-uniform loop, elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;
@@ -298,41 +302,45 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int it = it_begin; it < it_end; ++it) {
           mbar_wait(TF32 ? &split_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)stage * A_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
-          if (TF32) {
-            const uint64_t alo = umma_desc_sw128(smem_u32(sAlo + (size_t)stage * A_BYTES));
-            const uint64_t blo = umma_desc_sw128(smem_u32(sBlo + (size_t)stage * B_BYTES));
+          if (elect_one()) {
+            const uint64_t adesc = umma_desc_sw128(smem_u32(sA + (size_t)stage * A_BYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)stage * B_BYTES));
+            if (TF32) {
+              const uint64_t alo = umma_desc_sw128(smem_u32(sAlo + (size_t)stage * A_BYTES));
+              const uint64_t blo = umma_desc_sw128(smem_u32(sBlo + (size_t)stage * B_BYTES));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t o = (uint64_t)(2 * k);
-              umma_tf32(d_tmem, alo + o, bdesc + o, IDESC, ((it - it_begin) | k) != 0);   // small terms first
-              umma_tf32(d_tmem, adesc + o, blo + o, IDESC, 1u);
-              umma_tf32(d_tmem, adesc + o, bdesc + o, IDESC, 1u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t o = (uint64_t)(2 * k);
+                umma_tf32(d_tmem, alo + o, bdesc + o, IDESC, ((it - it_begin) | k) != 0);   // small terms first
+                umma_tf32(d_tmem, adesc + o, blo + o, IDESC, 1u);
+                umma_tf32(d_tmem, adesc + o, bdesc + o, IDESC, 1u);
+              }
+            } else if (CTA2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((it - it_begin) | k) != 0);
+              }
             }
-          } else if (CTA2) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (it | k) != 0);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((it - it_begin) | k) != 0);
+            if (CTA2) umma_commit_2sm(&empty_bar[stage]);   // frees this smem stage in both CTAs
+            else umma_commit(&empty_bar[stage]);            // frees this smem stage when the MMAs above have read it
+            if (it + 1 == it_end) {
+              if (CTA2) umma_commit_2sm(&tfull_bar[buf]);   // accumulator complete, both CTAs' epilogues
+              else umma_commit(&tfull_bar[buf]);
             }
           }
-          if (CTA2) umma_commit_2sm(&empty_bar[stage]);   // frees this smem stage in both CTAs
-          else umma_commit(&empty_bar[stage]);            // frees this smem stage when the MMAs above have read it
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (CTA2) umma_commit_2sm(&tfull_bar[buf]);       // accumulator complete, both CTAs' epilogues
-        else umma_commit(&tfull_bar[buf]);
       }
     }
-    __syncwarp();
   } else if (warp >= 2 + EPI) {
     if (TF32) {
       // ================= operand splitter: hi/lo decomposition of each landed stage, elementwise, so the swizzled
@@ -428,7 +436,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // accumulator leaves TMEM, so the L2 / HBM round trip overlaps tcgen05.ld and the smem transpose.
         float4 rb[8], rsd[8], mulf[8];
         uint2 mulh[8];
-        if (fast) {
+        if (fast && !(p.dbg & 1)) {
           if (has_rowbias) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) rb[it] = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)nsafe[it] * p.rowbias_ld + c));
@@ -456,6 +464,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           else mbar_arrive(&tempty_bar[buf]);   // this warp's share of the accumulator buffer has left TMEM
         }
         if (c0 >= p.Cout) continue;             // uniform across the CTA
+        if (p.dbg & 1) continue;
         if (direct) {
           if (!ed.ok) continue;
           const float scale = p.scale * (p.rowscale != nullptr ? p.rowscale[ed.n] : 1.0f);
@@ -816,6 +825,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   p.gn_goff = d->gn_goff;
   p.gn2_partial = d->gn2_partial;
   p.gn2_cpg = d->gn2_cpg; p.gn2_groups = d->gn2_groups; p.gn2_goff = d->gn2_goff;
+  static const int dbg_flags = []() { const char* e = getenv("INDM_IGEMM_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg_flags;
   INDM_CHECK_ARG(!d->gn2_partial || (d->gn_partial && (d->gn2_cpg == 4 || d->gn2_cpg == 8 || d->gn2_cpg == 16 || d->gn2_cpg == 32)),
                  "igemm: the second GroupNorm target needs the first one and cpg in {4, 8, 16, 32}");
   if (d->out_mode == 1) INDM_CHECK_ARG(d->out_f32 != nullptr, "igemm: out_mode 1 needs out_f32");

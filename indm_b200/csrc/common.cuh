@@ -93,6 +93,15 @@ __device__ __forceinline__ void pdl_trigger() {}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU with ONE SFU op per element: x sigmoid(x) = 0.5 x (1 + tanh(x / 2)); tanh.approx.f32 has ~2^-11 relative error, below the
+// BF16 resolution of the operand copies it feeds (x / (1 + __expf(-x)) costs an ex2 and a rcp: the GroupNorm apply kernels were
+// SFU-issue bound, not HBM bound)
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

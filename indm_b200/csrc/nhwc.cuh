@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Shared pieces of the NHWC streaming kernels (score_kernels.cu, backward_kernels.cu): typed 4-channel vector access and
 // launch geometry.  Everything here has internal linkage.
 #pragma once
@@ -60,8 +61,9 @@ inline GnGeom gn_geom(int C, long long P_iter, long long N) {
   if (g.R < 1) g.R = 1;
   if (g.R > P_iter) g.R = (int)P_iter;
   g.threads = g.Q * g.R;
-  // ~4 waves of CTAs over the chip, but at least ~8 pixel-rows of work per thread row
-  long long want = (4LL * indm_num_sms() + N - 1) / N;
+  // ~8 CTAs per SM over the chip (measured best of 4 / 8 / 12 / 16 / 24), but at least ~8 pixel-rows of work per thread row
+  static const int waves = []() { const char* e = getenv("INDM_GN_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+  long long want = ((long long)waves * indm_num_sms() + N - 1) / N;
   long long maxs = P_iter / (g.R * 4LL);
   if (maxs < 1) maxs = 1;
   if (want > maxs) want = maxs;

@@ -117,7 +117,10 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
   }
   auto norm = [&](float4 v) {
     float4 y = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
-    if (act) y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+    if (act) {
+      if (std::is_same<TOut, __nv_bfloat16>::value) y = make_float4(silu_fast(y.x), silu_fast(y.y), silu_fast(y.z), silu_fast(y.w));
+      else y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+    }
     return y;
   };
   if (RES == 2) {

@@ -94,14 +94,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Warp-uniform loops with elect.sync-predicated issue: the TMA / tcgen05.mma operands stay in uniform registers (inside a
+  // lane-0 branch every issue went through an ELECT + R2UR waterfall, which bounded the K loop of igemm.cu the same way).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int pt = blockIdx.y + i * gridDim.y;
-        const int x0 = (pt % p.tiles_x) * p.BW, y0 = ((pt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (pt / (p.tiles_x * p.tiles_y)) * p.BN;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int pt = blockIdx.y + i * gridDim.y;
+      const int x0 = (pt % p.tiles_x) * p.BW, y0 = ((pt / p.tiles_x) % p.tiles_y) * p.BH, n0 = (pt / (p.tiles_x * p.tiles_y)) * p.BN;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (elect_one()) {
         uint8_t* base = smem + (size_t)stage * STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)((A_BOXES + B_BOXES) * p.BW * p.BH * p.BN * 128));
 #pragma unroll
@@ -109,21 +111,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 #pragma unroll
         for (int b = 0; b < B_BOXES; ++b)
           tma_load_4d(base + (A_BOXES + b) * BOX_BYTES, &tmX, &full_bar[stage], c0 + b * KC, x0 + dx, y0 + dy, n0);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int ksteps = (p.BW * p.BH * p.BN) / UK;   // pixels actually present in a box (rows beyond are stale smem: skip them)
-      for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    const int ksteps = (p.BW * p.BH * p.BN) / UK;   // pixels actually present in a box (rows beyond are stale smem: skip them)
+    for (int i = 0; i < my_tiles; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
         const uint32_t b_addr = a_addr + A_BOXES * BOX_BYTES;
         for (int k = 0; k < ksteps; ++k) {
@@ -133,14 +135,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
           else umma_f16(tmem_base, adesc, bdesc, IDESC, (i | k) != 0);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        if (i + 1 == my_tiles) umma_commit(acc_bar);
       }
-      umma_commit(acc_bar);
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
-    __syncwarp();
   }
 
   if (my_tiles > 0) {

@@ -51,8 +51,18 @@ __device__ __forceinline__ float4 load_dy(const T* __restrict__ dy, long long n,
   return f4_scale(Vec4<T>::load(dy + ((n * Ho + (y >> 1)) * Wo + (x >> 1)) * C + c), 0.25f);
 }
 
+// SiLU'(u) = sg (1 + u (1 - sg)).  FAST (BF16 production path): sigmoid through ONE SFU op, sg = (1 + tanh(u / 2)) / 2
+// (tanh.approx, ~2^-11 relative: below the BF16 gradients it multiplies); the validation path keeps ex2 + rcp.
+template <bool FAST>
 __device__ __forceinline__ float dsilu(float u) {
-  const float sg = 1.0f / (1.0f + __expf(-u));
+  float sg;
+  if (FAST) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+    sg = fmaf(0.5f, t, 0.5f);
+  } else {
+    sg = 1.0f / (1.0f + __expf(-u));
+  }
   return sg * (1.0f + u * (1.0f - sg));
 }
 
@@ -121,10 +131,10 @@ __global__ void gn_bwd_kernel(const GnBwdP p) {
         du = make_float4(du.x * k.x, du.y * k.y, du.z * k.z, du.w * k.w);
       }
       if (p.act) {
-        du.x *= dsilu(xh.x * ga.x + be.x);
-        du.y *= dsilu(xh.y * ga.y + be.y);
-        du.z *= dsilu(xh.z * ga.z + be.z);
-        du.w *= dsilu(xh.w * ga.w + be.w);
+        du.x *= dsilu<std::is_same<TDy, __nv_bfloat16>::value>(xh.x * ga.x + be.x);
+        du.y *= dsilu<std::is_same<TDy, __nv_bfloat16>::value>(xh.y * ga.y + be.y);
+        du.z *= dsilu<std::is_same<TDy, __nv_bfloat16>::value>(xh.z * ga.z + be.z);
+        du.w *= dsilu<std::is_same<TDy, __nv_bfloat16>::value>(xh.w * ga.w + be.w);
       }
       const float4 dxh = make_float4(du.x * ga.x, du.y * ga.y, du.z * ga.z, du.w * ga.w);
       if (MODE == 0) {

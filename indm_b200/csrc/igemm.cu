@@ -911,7 +911,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   if (plain && !d->rowbias && d->out_f32 && !d->out_bf16) kind = 2;
   // CTA pairs (cta_group::2) for the launches that fill the chip: wide tiles of the plain BF16 convolutions
   static const bool cta2_enabled = []() { const char* e = getenv("INDM_IGEMM_CTA2"); return !(e && e[0] == '0'); }();
-  const bool cta2 = cta2_enabled && kind != 0 && p.ksplit == 1 && !d->batched_b && (block_n == 128 || block_n == 256) &&
+  const bool cta2 = cta2_enabled && !tf32 && p.ksplit == 1 && !d->batched_b && (block_n == 128 || block_n == 256) &&
                     (long long)m_tiles * n_tiles >= indm_num_sms();
   const int b_rows = cta2 ? block_n / 2 : block_n;
   {
@@ -961,10 +961,13 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     return INDM_OK;
   }
   if (cta2) {
-    if (block_n == 256) return kind == 1 ? launch_igemm<256, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
-                                         : launch_igemm<256, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
-    return kind == 1 ? launch_igemm<128, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
-                     : launch_igemm<128, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+#define INDM_LAUNCH2(BN_)                                                                                       \
+  if (kind == 1) return launch_igemm<BN_, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
+  if (kind == 2) return launch_igemm<BN_, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
+  return launch_igemm<BN_, false, 0, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+    if (block_n == 256) { INDM_LAUNCH2(256); }
+    INDM_LAUNCH2(128);
+#undef INDM_LAUNCH2
   }
 #define INDM_LAUNCH(BN_)                                                                                  \
   if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);          \

@@ -149,7 +149,8 @@ class FlowBackward:
             wg(G2, idim, idim, S1, idim, idim, G['w2'], idim), wg(Q2, idim, idim, T1F, idim, idim, G['w2'], idim),
             wg(G1, idim, idim, Ax, kp, kp, G['w1'], kp), wg(Q1, idim, idim, Ae, kp, kp, G['w1'], kp),
             call('indm_colsum', G1, wdt, _i64(N), _i64(H * Wd), idim, _i64(idim), None, _i64(0), G['b1'], _f(1.0)),
-            call('indm_colsum', G2, wdt, _i64(N), _i64(H * Wd), idim, _i64(idim), self.gb2_img, _i64(idim), G['b2'], _f(1.0)),
+            call('indm_colsum', G2, wdt, _i64(N), _i64(H * Wd), idim, _i64(idim), self.gb2_img, _i64(idim), None, _f(1.0)),
+            call('indm_colsum', self.gb2_img, L.DTYPE_F32, _i64(1), _i64(N), idim, _i64(idim), None, _i64(0), G['b2'], _f(1.0)),
         ]
         return ops, gx_src
 

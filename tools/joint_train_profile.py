@@ -63,6 +63,17 @@ def main():
             print(f'step {tot * 1e3:.1f} ms | ' + ' | '.join(f'{k} {v * 1e3:.1f} ms ({T[k + " #"]} launches)' for k, v in T.items() if not k.endswith('#')),
                   '| flow VJPs', flow.module.engine(B).vjp_count, flush=True)
     print('max memory GiB', torch.cuda.max_memory_allocated() / 2**30)
+    if '--kineto' in sys.argv:
+        # per-kernel device time of one step (CUPTI through torch.profiler; a development view, not a bench number)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn(state, flow_state, batch)
+            torch.cuda.synchronize()
+        rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0]
+        tot = sum(r[2] for r in rows)
+        print(f'device time of one step: {tot:.1f} ms over {sum(r[1] for r in rows)} kernels')
+        for k, c, t in sorted(rows, key=lambda r: -r[2])[:28]:
+            print(f'  {t:8.2f} ms {100 * t / tot:5.1f}%  x{c:5d}  {k[:110]}')
 
 
 if __name__ == '__main__':

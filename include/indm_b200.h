@@ -254,6 +254,12 @@ int indm_colsum(const void* x, int dtype, int64_t N, int64_t P, int C, int64_t x
 int indm_sgemm_f32(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
                    float beta, float* C, int64_t ldc, void* stream);
 
+/* The same GEMM over a batch: operand z of A / B / C at base + z * stride (elements; stride 0 = shared by the whole batch).
+ * Used to run the per-iResBlock conditioning-path products of the flow backward (32 blocks) as one launch each. */
+int indm_sgemm_batched_f32(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int64_t lda, int64_t stride_a,
+                           const float* B, int64_t ldb, int64_t stride_b, float beta, float* C, int64_t ldc, int64_t stride_c, int batch,
+                           void* stream);
+
 /* dx = dy * SiLU'(pre) */
 int indm_silu_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, void* stream);
 

@@ -50,10 +50,15 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long P, int C, long 
 
 // ---------------------------------------------------------------- small FP32 GEMM  C = alpha * op(A) op(B) + beta * C
 // 64 x 64 tiles, 256 threads, 4 x 4 per thread.  op(A) is M x K, op(B) is K x N; row-major storage with leading dimensions.
+// blockIdx.z = batch index (operand z lives at base + z * stride; stride 0 shares an operand across the batch).
 __global__ void __launch_bounds__(256) sgemm_kernel(int ta, int tb, int M, int N, int K, float alpha, const float* __restrict__ A,
                                                     long long lda, const float* __restrict__ B, long long ldb, float beta,
-                                                    float* __restrict__ C, long long ldc) {
+                                                    float* __restrict__ C, long long ldc, long long sA = 0, long long sB = 0,
+                                                    long long sC = 0) {
   __shared__ float sa[16][64 + 4], sb[16][64 + 4];
+  A += (long long)blockIdx.z * sA;
+  B += (long long)blockIdx.z * sB;
+  C += (long long)blockIdx.z * sC;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   float acc[4][4] = {};
@@ -224,6 +229,17 @@ extern "C" int indm_sgemm_f32(int trans_a, int trans_b, int M, int N, int K, flo
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   INDM_CHECK_LAUNCH("sgemm");
+  return INDM_OK;
+}
+
+extern "C" int indm_sgemm_batched_f32(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                                      int64_t stride_a, const float* B, int64_t ldb, int64_t stride_b, float beta, float* C, int64_t ldc,
+                                      int64_t stride_c, int batch, void* stream_) {
+  INDM_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "sgemm_batched: bad arguments");
+  dim3 grid((N + 63) / 64, (M + 63) / 64, (unsigned)batch);
+  sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, stride_a, stride_b,
+                                                        stride_c);
+  INDM_CHECK_LAUNCH("sgemm_batched");
   return INDM_OK;
 }
 

@@ -462,7 +462,9 @@ class FlowEngine:
             a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
             # use the operand-rounded W2 so the folded bias matches what the tensor cores apply to u
             if i not in self.w2f:
-                self.w2f[i] = torch.empty((self.idim, self.idim), device=dev)
+                if not hasattr(self, 'w2f_all'):
+                    self.w2f_all = torch.empty((len(self.blocks), self.idim, self.idim), device=dev)
+                self.w2f[i] = self.w2f_all[i]
             self.w2f[i].copy_(W['w2'])      # fp32 copy of the operand-rounded W2: the conditioning path's backward uses it
             w2r = self.w2f[i]
             self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)

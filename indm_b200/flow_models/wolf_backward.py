@@ -50,15 +50,19 @@ class FlowBackward:
         self.o9 = [torch.empty_like(e.o9[s]) for s in range(len(e.nb))]
         self.grads = {}
         hd = e.core.latent_dim
+        nblk = len(e.blocks)
+        z = lambda *shape: torch.zeros(shape, device=dev)
+        # conditioning-path gradients of all blocks stacked, so their small products run as ONE batched launch each
+        self.gw2_all, self.gA_all, self.ga_all, self.gb2_all = z(nblk, idim, idim), z(nblk, idim, hd), z(nblk, idim), z(nblk, idim)
+        self.gb2_img_all = z(nblk, N, idim)
+        self.gc_all = torch.empty((nblk, N, idim), device=dev)
+        self.cvec_all = torch.empty((nblk, N, idim), device=dev)
+        self.ghb_all = torch.empty((nblk, N, hd), device=dev)
         for i, (s, b, m) in enumerate(e.blocks):
             c, kp = m.channels, e.kp[s]
-            z = lambda *shape: torch.zeros(shape, device=dev)
             # packed like the forward operands: w1 [idim][kp], w3 [kp][idim] (columns / rows >= 9c stay zero)
-            self.grads[i] = dict(w1=z(idim, kp), w2=z(idim, idim), w3=z(kp, idim), b1=z(idim), b2=z(idim), b3=z(c),
-                                 A=z(idim, hd), a=z(idim))
-        self.gb2_img = torch.zeros((N, idim), device=dev)
-        self.gc = torch.empty((N, idim), device=dev)
-        self.cvec = torch.empty((N, idim), device=dev)
+            self.grads[i] = dict(w1=z(idim, kp), w2=self.gw2_all[i], w3=z(kp, idim), b1=z(idim), b2=self.gb2_all[i], b3=z(c),
+                                 A=self.gA_all[i], a=self.ga_all[i])
         self.gh = torch.zeros((N, hd), device=dev)
         self.ones = {}
         self._ops = {}
@@ -149,8 +153,7 @@ class FlowBackward:
             wg(G2, idim, idim, S1, idim, idim, G['w2'], idim), wg(Q2, idim, idim, T1F, idim, idim, G['w2'], idim),
             wg(G1, idim, idim, Ax, kp, kp, G['w1'], kp), wg(Q1, idim, idim, Ae, kp, kp, G['w1'], kp),
             call('indm_colsum', G1, wdt, _i64(N), _i64(H * Wd), idim, _i64(idim), None, _i64(0), G['b1'], _f(1.0)),
-            call('indm_colsum', G2, wdt, _i64(N), _i64(H * Wd), idim, _i64(idim), self.gb2_img, _i64(idim), None, _f(1.0)),
-            call('indm_colsum', self.gb2_img, L.DTYPE_F32, _i64(1), _i64(N), idim, _i64(idim), None, _i64(0), G['b2'], _f(1.0)),
+            call('indm_colsum', G2, wdt, _i64(N), _i64(H * Wd), idim, _i64(idim), self.gb2_img_all[i], _i64(idim), None, _f(1.0)),
         ]
         return ops, gx_src
 
@@ -163,7 +166,6 @@ class FlowBackward:
             ent = self._block_ops(i, s, m, xin, ve, wS, gy, gx, tmp)
             self._ops[key] = ent
         ops, gx_src = ent
-        self.gb2_img.zero_()
         for op in ops:
             op()
         # db3 = sum over images and pixels of gy (NCHW): row sums against ones, then over images
@@ -175,21 +177,31 @@ class FlowBackward:
             ones = self.ones[s] = torch.ones_like(gy)
         L.call('indm_rowdot_f32', L.ptr(gy), L.ptr(ones), L.ptr(rows), e.N * c, HW, _f(1.0), 0)
         self.grads[i]['b3'].add_(rows.view(e.N, c).sum(0))
-        # conditioning path: a2 = W2 (s1 + A h + a) + b2 (lipschitz.py:431-435)
-        idim, hd, N = e.idim, e.core.latent_dim, e.N
-        cv2 = m.convs()[1]
-        Aw_, ab_ = cv2.h_net.net.weight, cv2.h_net.net.bias
-        G = self.grads[i]
-        w2f = e.w2f[i]
-        sg = lambda ta, tb, M, Nn, K, A, lda, B, ldb, beta, C, ldc: L.call(
-            'indm_sgemm_f32', ta, tb, M, Nn, K, _f(1.0), L.ptr(A), _i64(lda), L.ptr(B), _i64(ldb), _f(beta), L.ptr(C), _i64(ldc))
-        sg(0, 0, N, idim, idim, self.gb2_img, idim, w2f, idim, 0.0, self.gc, idim)                 # gc = gb2 W2
-        sg(1, 0, idim, hd, N, self.gc, idim, e.h, hd, 1.0, G['A'], hd)                              # dA += gc^T h
-        L.call('indm_colsum', L.ptr(self.gc), L.DTYPE_F32, _i64(1), _i64(N), idim, _i64(idim), None, _i64(0), L.ptr(G['a']), _f(1.0))
-        sg(0, 0, N, hd, idim, self.gc, idim, Aw_.detach(), hd, 1.0, self.gh, hd)                    # dh += gc A
-        L.call('indm_linear_f32', L.ptr(e.h), L.ptr(Aw_.detach()), L.ptr(ab_.detach()), L.ptr(self.cvec), N, hd, idim, 0, 0, L.DTYPE_F32)
-        sg(1, 0, idim, idim, N, self.gb2_img, idim, self.cvec, idim, 1.0, G['w2'], idim)            # dW2 += gb2^T c
         return gx_src
+
+    def _conditioning_path(self):
+        """a2 = W2 (s1 + A h + a) + b2 (lipschitz.py:431-435) for all blocks at once: with gb2 = per-image pixel sums of G2,
+        gc = gb2 W2;  dA = gc^T h;  da = sum_n gc;  dh += gc A;  dW2 += gb2^T (A h + a);  db2 = sum_n gb2.
+        Per block these are [N x 512] x [512 x 512]-sized products on a handful of CTAs (5 launches x 32 blocks took 10 ms);
+        batched over the blocks they are 4 launches."""
+        e = self.eng
+        idim, hd, N, nblk = e.idim, e.core.latent_dim, e.N, len(e.blocks)
+        A_all = torch.stack([m.convs()[1].h_net.net.weight.detach() for (_, _, m) in e.blocks]).contiguous()      # [nblk, idim, hd]
+        a_all = torch.stack([m.convs()[1].h_net.net.bias.detach() for (_, _, m) in e.blocks])                      # [nblk, idim]
+
+        def bg(ta, tb, M, Nn, K, A, lda, sA, B, ldb, sB, beta, C, ldc, sC):
+            L.call('indm_sgemm_batched_f32', ta, tb, M, Nn, K, _f(1.0), L.ptr(A), _i64(lda), _i64(sA), L.ptr(B), _i64(ldb), _i64(sB), _f(beta),
+                   L.ptr(C), _i64(ldc), _i64(sC), nblk)
+        gb = self.gb2_img_all
+        bg(0, 0, N, idim, idim, gb, idim, N * idim, e.w2f_all, idim, idim * idim, 0.0, self.gc_all, idim, N * idim)        # gc = gb2 W2
+        bg(1, 0, idim, hd, N, self.gc_all, idim, N * idim, e.h, hd, 0, 0.0, self.gA_all, hd, idim * hd)                    # dA = gc^T h
+        self.ga_all.copy_(self.gc_all.sum(dim=1))
+        bg(0, 0, N, hd, idim, self.gc_all, idim, N * idim, A_all, hd, idim * hd, 0.0, self.ghb_all, hd, N * hd)           # gc A per block
+        self.gh.add_(self.ghb_all.sum(dim=0))
+        bg(0, 1, N, idim, hd, e.h, hd, 0, A_all, hd, idim * hd, 0.0, self.cvec_all, idim, N * idim)                        # h A^T
+        self.cvec_all.add_(a_all[:, None, :])
+        bg(1, 0, idim, idim, N, gb, idim, N * idim, self.cvec_all, idim, N * idim, 1.0, self.gw2_all, idim, idim * idim)  # dW2 += gb2^T c
+        self.gb2_all.copy_(gb.sum(dim=1))
 
     def run(self, gz, cS):
         """gz: gradient w.r.t. the flow output (the flow's own input layout [N, c0, H, W]); cS [N]: d loss / d (sum of block
@@ -204,6 +216,7 @@ class FlowBackward:
             for t in G.values():
                 t.zero_()
         self.gh.zero_()
+        self.gb2_img_all.zero_()
         cS = cS.float().contiguous()
         g = gz.float().contiguous()
         nscales = len(e.nb)
@@ -227,6 +240,7 @@ class FlowBackward:
             n_, c_, h_, w_ = g.shape
             g = g.view(n_, c_ // 4, 2, 2, h_, w_).permute(0, 1, 4, 2, 5, 3).reshape(n_, c_ // 4, 2 * h_, 2 * w_).contiguous()
             cur_scale -= 1
+        self._conditioning_path()
         self._to_param_grads()
         return g.clone(), self.gh.clone()
 

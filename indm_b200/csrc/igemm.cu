@@ -128,6 +128,10 @@ constexpr int igemm_threads(bool tf32) { return 64 + 32 * epi_warps(tf32) + (tf3
 //   KIND 1: BF16 NHWC output ([+ bias] [+ per-image row bias]) * scale [+ GroupNorm statistics]   (Conv_0, q|k|v, P.V, dgrads)
 //   KIND 2: FP32 NHWC output ([+ bias]) * scale [+ residual * res_scale]                         (Conv_1 [+ Conv_2], NIN_3, Q.K^T)
 //   (no activation / cos side output / multiplier / per-image scale / NCHW / ragged-column paths in either)
+//   KIND 3: BF16 NHWC output, ([+ bias] [+ row bias]) * scale -> [cos side output] -> [Sin / ELU]   (iResBlock branch GEMMs)
+//   KIND 4: BF16 NHWC output, * scale * multiplier                                                 (iResBlock VJP chain)
+//   (the generic epilogue keeps row bias + residual + multiplier registers live at once and spills: its reloads were 28 % of
+//    the stall samples of the flow's 512 x 512 GEMMs, which ran 2.4 - 2.9x slower than the same GEMM with a plain epilogue)
 //   KIND 0: every feature tested at run time.
 //   CTA2: the CTAs of a 2-cluster (a CTA pair on one TPC) own two consecutive M tiles of the same N tile and issue ONE
 //   tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own A tile and half of the B tile (TMA credits the LEADER's full
@@ -381,14 +385,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else {
     // ================= epilogue warps
     const bool has_bias = p.bias != nullptr;
-    const bool has_rowbias = KIND == 2 ? false : (p.rowbias != nullptr);
-    const bool has_res = KIND == 1 ? false : (p.residual != nullptr);
+    const bool has_rowbias = (KIND == 2 || KIND == 4) ? false : (p.rowbias != nullptr);
+    const bool has_res = (KIND == 1 || KIND == 3 || KIND == 4) ? false : (p.residual != nullptr);
     const bool has_rowscale = KIND ? false : (p.rowscale != nullptr);
-    const bool has_aux = KIND ? false : (p.aux_cos != nullptr);
-    const int act = KIND ? 0 : p.act;
-    const bool has_mul = KIND ? false : (p.mul != nullptr);
-    const bool st_f32 = KIND == 2 ? true : (KIND == 1 ? false : p.out_f32 != nullptr);
-    const bool st_bf16 = KIND == 1 ? true : (KIND == 2 ? false : p.out_bf16 != nullptr);
+    const bool has_aux = (KIND == 0 || KIND == 3) ? (p.aux_cos != nullptr) : false;
+    const int act = (KIND == 0 || KIND == 3) ? p.act : 0;
+    const bool has_mul = KIND == 4 ? true : (KIND == 0 ? (p.mul != nullptr) : false);
+    const bool st_f32 = KIND == 2 ? true : (KIND == 0 ? p.out_f32 != nullptr : false);
+    const bool st_bf16 = KIND == 2 ? false : (KIND == 0 ? p.out_bf16 != nullptr : true);
     const bool has_gn = p.gn_partial != nullptr;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;             // which of the SLAB_STEP warps sharing the quarter: takes slabs half, half + SLAB_STEP, ...
@@ -909,6 +913,11 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   const bool plain = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->aux_cos && d->act == 0 && !d->mul;
   if (plain && !d->residual && d->out_bf16 && !d->out_f32) kind = 1;
   if (plain && !d->rowbias && d->out_f32 && !d->out_bf16) kind = 2;
+  // the two epilogues of the iResBlock branch / VJP chain (wide tiles only: idim 128 / 512)
+  const bool flowish = !tf32 && d->out_mode == 0 && d->Cout % 32 == 0 && !d->rowscale && !d->residual && d->out_bf16 && !d->out_f32 &&
+                       (block_n == 128 || block_n == 256);
+  if (flowish && !d->mul && (d->act != 0 || d->aux_cos)) kind = 3;
+  if (flowish && d->mul && !d->bias && !d->rowbias && d->act == 0 && !d->aux_cos) kind = 4;
   // CTA pairs (cta_group::2) for the launches that fill the chip: wide tiles of the plain BF16 convolutions
   static const bool cta2_enabled = []() { const char* e = getenv("INDM_IGEMM_CTA2"); return !(e && e[0] == '0'); }();
   const bool cta2 = cta2_enabled && !tf32 && p.ksplit == 1 && !d->batched_b && (block_n == 128 || block_n == 256) &&
@@ -964,6 +973,8 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
 #define INDM_LAUNCH2(BN_)                                                                                       \
   if (kind == 1) return launch_igemm<BN_, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
   if (kind == 2) return launch_igemm<BN_, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
+  if (kind == 3) return launch_igemm<BN_, false, 3, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
+  if (kind == 4) return launch_igemm<BN_, false, 4, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
   return launch_igemm<BN_, false, 0, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
     if (block_n == 256) { INDM_LAUNCH2(256); }
     INDM_LAUNCH2(128);
@@ -977,8 +988,14 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   switch (block_n) {
     case 32: INDM_LAUNCH(32);
     case 64: INDM_LAUNCH(64);
-    case 128: INDM_LAUNCH(128);
-    default: INDM_LAUNCH(256);
+    case 128:
+      if (kind == 3) return launch_igemm<128, false, 3>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+      if (kind == 4) return launch_igemm<128, false, 4>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+      INDM_LAUNCH(128);
+    default:
+      if (kind == 3) return launch_igemm<256, false, 3>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+      if (kind == 4) return launch_igemm<256, false, 4>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+      INDM_LAUNCH(256);
   }
 #undef INDM_LAUNCH
 }

@@ -159,13 +159,14 @@ def conv_roofline(net, eng, reps=3):
     return tot_fl / (tot_ms * 1e-3) / 1e12, tot_ms / n_launch, n_launch // reps
 
 
-def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup=3):
+def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup=16):
     """Second BASELINE metric (configs[2]): training samples/s of the INDM-VP joint step `flow_step_fn_nll` (losses.py:258-320),
     128 images per GPU, data parallel (one NCCL all-reduce per flat gradient buffer: score network and flow).  One step = wolf flow
     forward in training mode (batch-statistics BatchNorm encoder, posterior sample, prior-flow KL, Neumann log-det series of all
     32 iResBlocks), score-network train-mode forward (dropout 0.1) + DSM loss + prior log-p, ONE backward through both networks
     (score dgrad + wgrad, flow first-order + second-order Neumann gradient, encoder / prior backward), then global-norm clip +
-    AdamW + EMA on both."""
+    AdamW + EMA on both.  Warm-up is 16 steps: the flow's per-(block, series length) log-det chains are captured as CUDA graphs on
+    their second use, and the Poisson series lengths need a few steps to have all been seen (steady state of a training run)."""
     import torch
     from indm_b200 import configs, losses
     from indm_b200.models.ema import ExponentialMovingAverage

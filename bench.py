@@ -13,6 +13,8 @@ copied in, and the samples copied back, every step.
 
     python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                   CPU arm: the oracle port of the reference's PyTorch CPU path
+    python bench.py --num-scales 4 --skip-train --skip-cpu   profiling slice of the same command for `ncu` (a line printed by such
+                                                           a run says so in config.workload and is never a bench value)
 """
 import argparse
 import json
@@ -33,13 +35,23 @@ NUM_SCALES = 1000
 GFLOP_PER_IMAGE_FWD = 21.69      # score-net forward, CIFAR nres=4 (2*MAC, forward hooks on the reference)
 
 
-def workload_config(device):
+def igemm_traffic():
+    """DRAM bytes per igemm launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the launches of one forward) from the
+    committed `ncu --set full` capture, if one was summarised into profiles/igemm_traffic.json; else None."""
+    p = os.path.join(ROOT, "profiles", "igemm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f)
+
+
+def workload_config(device, num_scales=NUM_SCALES):
     from indm_b200 import configs
     cfg = configs.get_config("vp/CIFAR10/indm_fid")
     cfg.sampling.method = "pc"
     cfg.sampling.predictor = "reverse_diffusion"
     cfg.sampling.corrector = "none"
-    cfg.sampling.num_scales = NUM_SCALES
+    cfg.sampling.num_scales = num_scales                  # loop length only; the SDE keeps N = model.num_scales = 1000
     cfg.device = device
     return cfg
 
@@ -208,7 +220,7 @@ def run_ours(args):
     from indm_b200.models import utils as mutils
     from indm_b200.flow_models import flow_model as fm
 
-    cfg = workload_config(dev)
+    cfg = workload_config(dev, args.num_scales)
     flow_note = "wolf"
     torch.manual_seed(0)
     model = mutils.create_model(cfg)
@@ -267,7 +279,7 @@ def run_ours(args):
     ms_step, launches = timed(step_resident, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
-    train = train_throughput(cfg, model, flow, sde, dev, world, timed)
+    train = None if args.skip_train else train_throughput(cfg, model, flow, sde, dev, world, timed)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -275,6 +287,7 @@ def run_ours(args):
     value = world * PER_GPU_BATCH / (ms_step * 1e-3)
     e2e = world * PER_GPU_BATCH / (ms_e2e * 1e-3)
     pk, pk_kind = peaks()
+    traffic = igemm_traffic()
     eng = net.engine(PER_GPU_BATCH)
     tf, ms_launch, n_ig = conv_roofline(net, eng)
     peak_tf = pk["bf16_tflops_sustained"]
@@ -283,20 +296,23 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "vp/CIFAR10/indm_fid (DDPM++ nres=4 nf=128) + sampling.method=pc predictor=reverse_diffusion "
-                               "corrector=none, 1000 steps, 128 images per GPU (1024 / 8 GPUs); step = one full pc_sampler call",
-                   "flow": flow_note, "per_gpu_batch": PER_GPU_BATCH, "num_scales": NUM_SCALES,
+                               "corrector=none, 1000 steps, 128 images per GPU (1024 / 8 GPUs); step = one full pc_sampler call"
+                               + ("" if args.num_scales == NUM_SCALES else f" -- PROFILING SLICE with {args.num_scales} PC steps, not a bench value"),
+                   "flow": flow_note, "per_gpu_batch": PER_GPU_BATCH, "num_scales": args.num_scales,
                    "l2_policy": "inputs larger than L2 (activations ~5 GB per forward), no flush",
                    "noise": "in-kernel Philox4x32-10 (no noise tensor in HBM)"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": prior_host.numel() * 4, "d2h_bytes_per_step": prior_host.numel() * 4},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                      "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/GEMM)", "peak_source": pk_kind + " bf16_tflops_sustained",
                      "launches_per_forward": n_ig, "avg_launch_ms": ms_launch,
                      "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD},
     }
-    out["train"] = train
-    if world == 1:
+    if train is not None:
+        out["train"] = train
+    if world == 1 and not args.skip_cpu:
         v, sample = cpu_sample(os.cpu_count() or 1, n_pc=2, batch=16)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
     print(json.dumps(out), flush=True)
@@ -310,6 +326,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-scales", type=int, default=NUM_SCALES, help="PC steps per sampler call (profiling slices only; the bench is 1000)")
+    ap.add_argument("--skip-train", action="store_true", help="profiling: leave out the training leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling: leave out the CPU baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

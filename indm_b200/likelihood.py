@@ -7,8 +7,10 @@ Execution differences, arithmetic unchanged:
   * one ODE right-hand side costs 1 network forward + 1 input-VJP: drift and divergence share the forward
     (the reference evaluates the drift twice, likelihood.py:97-98 — 2 forwards + 1 backward);
   * the flow's log-determinant uses the tensor-core VJP chain (flow_models/wolf.py).
-The black-box integrator stays `scipy.integrate.solve_ivp` (RK45) on the host like the reference, stepping the whole batch
-vector with one adaptive step size (likelihood.py:111-116).
+The black-box integrator is `scipy.integrate.solve_ivp` (RK45) on the host like the reference, stepping the whole batch
+vector with one adaptive step size (likelihood.py:111-116).  `method='RK45-device'` selects the same Dormand-Prince 5(4)
+algorithm with the float64 state and stage derivatives resident on the GPU (`indm_b200/ode.py`, pinned step for step
+against SciPy): one scalar crosses to the host per step instead of 12 full-state copies.
 """
 import numpy as np
 import torch
@@ -16,6 +18,9 @@ from scipy import integrate
 
 from .flow_models.flow_model import flow_forward
 from .models import utils as mutils
+from .ode import solve_ivp_rk45
+
+DEVICE_METHOD = 'RK45-device'
 
 
 def get_div_fn(fn):
@@ -82,16 +87,30 @@ def get_likelihood_fn(config, sde, inverse_scaler, hutchinson_type='Rademacher',
             if residual:
                 z = torch.randn_like(data) if noise is None else noise
                 mean, std = sde.marginal_prob(data, torch.ones(data.shape[0], device=data.device) * eps_bpd)
-                perturbed_data = mean + std[:, None, None, None] * z
-                init = np.concatenate([mutils.to_flattened_numpy(perturbed_data), np.zeros((shape[0],))], axis=0)
+                start = mean + std[:, None, None, None] * z
             else:
-                init = np.concatenate([mutils.to_flattened_numpy(data), np.zeros((shape[0],))], axis=0)
+                start = data
 
-            solution = integrate.solve_ivp(ode_func, (eps_bpd, sde.T), init, rtol=rtol, atol=atol, method=method)
-            nfe = solution.nfev
-            zp = solution.y[:, -1]
-            z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
-            delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
+            if method == DEVICE_METHOD:
+                def ode_func_device(t, y):
+                    sample = y[:-shape[0]].reshape(shape).to(torch.float32)
+                    vec_t = torch.ones(shape[0], device=sample.device) * t
+                    drift, logp_grad = drift_and_div(model, sample, vec_t, epsilon)
+                    return torch.cat([drift.reshape(-1), logp_grad.reshape(-1)])
+
+                init_dev = torch.cat([start.reshape(-1).to(torch.float64),
+                                      torch.zeros(shape[0], dtype=torch.float64, device=data.device)])
+                solution = solve_ivp_rk45(ode_func_device, (eps_bpd, sde.T), init_dev, rtol=rtol, atol=atol)
+                nfe = solution.nfev
+                z = solution.y_final[:-shape[0]].reshape(shape).to(torch.float32)
+                delta_logp = solution.y_final[-shape[0]:].to(torch.float32)
+            else:
+                init = np.concatenate([mutils.to_flattened_numpy(start), np.zeros((shape[0],))], axis=0)
+                solution = integrate.solve_ivp(ode_func, (eps_bpd, sde.T), init, rtol=rtol, atol=atol, method=method)
+                nfe = solution.nfev
+                zp = solution.y[:, -1]
+                z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
+                delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
             prior_logp = sde.prior_logp(z)
             if residual:
                 residual_fn = get_likelihood_residual_fn(config, sde, score_fn, eps_bpd=eps_bpd)

@@ -517,7 +517,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
 def get_ode_sampler(config, sde, shape, inverse_scaler, denoise=False, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3, device='cuda'):
     """Probability-flow ODE sampler with the black-box solver (sampling.py:547-621; the default of configs/vp/*/indm_fid.py).
     The right-hand side f - g^2 score / 2 is one score-network forward on the engine; SciPy RK45 steps the whole batch on the host
-    like the reference.  Returns `ode_sampler(model, flow_model, temperature, ...) -> (before_flow, after_flow, nfe)`."""
+    like the reference, or `method='RK45-device'` keeps the float64 state on the GPU (indm_b200/ode.py).  Returns `ode_sampler(model, flow_model, temperature, ...) -> (before_flow, after_flow, nfe)`."""
     from scipy import integrate
 
     def denoise_update_fn(model, x):
@@ -543,9 +543,22 @@ def get_ode_sampler(config, sde, shape, inverse_scaler, denoise=False, rtol=1e-5
                 vec_t = torch.ones(shape[0], device=x.device) * t
                 return mutils.to_flattened_numpy(drift_fn(model, x, vec_t))
 
-            solution = integrate.solve_ivp(ode_func, (sde.T, eps), mutils.to_flattened_numpy(x), rtol=rtol, atol=atol, method=method)
-            nfe = solution.nfev
-            x = torch.tensor(solution.y[:, -1]).reshape(shape).to(device).type(torch.float32)
+            if method == 'RK45-device':
+                # same Dormand-Prince 5(4) algorithm, float64 state resident on the GPU (indm_b200/ode.py)
+                from .ode import solve_ivp_rk45
+
+                def ode_func_device(t, y):
+                    xs = y.reshape(shape).to(torch.float32)
+                    vec_t = torch.ones(shape[0], device=xs.device) * t
+                    return drift_fn(model, xs, vec_t).reshape(-1)
+
+                solution = solve_ivp_rk45(ode_func_device, (sde.T, eps), x.reshape(-1).to(torch.float64), rtol=rtol, atol=atol)
+                nfe = solution.nfev
+                x = solution.y_final.reshape(shape).to(torch.float32)
+            else:
+                solution = integrate.solve_ivp(ode_func, (sde.T, eps), mutils.to_flattened_numpy(x), rtol=rtol, atol=atol, method=method)
+                nfe = solution.nfev
+                x = torch.tensor(solution.y[:, -1]).reshape(shape).to(device).type(torch.float32)
             sample_before_flow = denoise_update_fn(model, x) if denoise else x
             if config.flow.model != 'identity':
                 sample_after_flow, _ = flow_forward(config, flow_model, sample_before_flow * temperature, log_det=None, reverse=True)

@@ -80,15 +80,66 @@ class FusedAdamW(torch.optim.Optimizer):
         L.param_epoch += 1            # engines repack their operand copies of the weights on next use
 
     def state_dict(self):
-        return dict(steps=self.steps, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
-                    param_groups=[{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups])
+        """`torch.optim.AdamW.state_dict()` layout — the wire format of the reference's `checkpoint_N.pth['optimizer']`
+        (utils.py:37-43 saves `state['optimizer'].state_dict()`): per-parameter `step` / `exp_avg` / `exp_avg_sq` keyed by the
+        parameter's index, views into the flat moment buffers."""
+        return pack_adamw_state(self._params, self.steps, self.exp_avg, self.exp_avg_sq, self.param_groups)
 
     def load_state_dict(self, sd):
-        self.steps = sd['steps']
-        self.exp_avg.copy_(sd['exp_avg'])
-        self.exp_avg_sq.copy_(sd['exp_avg_sq'])
-        for g, s in zip(self.param_groups, sd['param_groups']):
-            g.update(s)
+        """Accepts a `torch.optim.AdamW` state dict (reference checkpoints, utils.py:24) and this class's own."""
+        self.steps = unpack_adamw_state(sd, self._params, self.exp_avg, self.exp_avg_sq, self.param_groups)
+
+
+def pack_adamw_state(params, steps, exp_avg_flat, exp_avg_sq_flat, param_groups):
+    """Flat moment buffers -> the dict `torch.optim.AdamW.state_dict()` returns (state empty before the first step, like torch)."""
+    state, off = {}, 0
+    for i, p in enumerate(params):
+        n = p.numel()
+        if steps > 0:
+            state[i] = dict(step=torch.tensor(float(steps)), exp_avg=exp_avg_flat[off:off + n].view_as(p),
+                            exp_avg_sq=exp_avg_sq_flat[off:off + n].view_as(p))
+        off += n
+    groups, base = [], 0
+    for g in param_groups:
+        d = {k: v for k, v in g.items() if k != 'params'}
+        d['params'] = list(range(base, base + len(g['params'])))
+        base += len(g['params'])
+        groups.append(d)
+    return dict(state=state, param_groups=groups)
+
+
+def unpack_adamw_state(sd, params, exp_avg_flat, exp_avg_sq_flat, param_groups):
+    """Inverse of `pack_adamw_state`; `step` may be an int (torch 1.7.1, the reference's pin) or a tensor.  Returns the step count.
+    Parameters without saved state (a checkpoint written before the first step) get zero moments."""
+    if 'state' not in sd:                      # round-1 layout of this class (flat tensors)
+        exp_avg_flat.copy_(sd['exp_avg'])
+        exp_avg_sq_flat.copy_(sd['exp_avg_sq'])
+        for g, s in zip(param_groups, sd['param_groups']):
+            g.update({k: v for k, v in s.items() if k != 'params'})
+        return int(sd['steps'])
+    n_saved = sum(len(g['params']) for g in sd['param_groups'])
+    if n_saved != len(params):
+        raise ValueError(f"loaded state dict contains a parameter group that doesn't match the size of optimizer's group "
+                         f"({n_saved} vs {len(params)} parameters)")
+    ids = [i for g in sd['param_groups'] for i in g['params']]
+    steps, off = 0, 0
+    with torch.no_grad():
+        for i, p in zip(ids, params):
+            n = p.numel()
+            st = sd['state'].get(i)
+            if st is None:
+                exp_avg_flat[off:off + n].zero_()
+                exp_avg_sq_flat[off:off + n].zero_()
+            else:
+                if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state of parameter {i} has shape {tuple(st['exp_avg'].shape)}, expected {tuple(p.shape)}")
+                exp_avg_flat[off:off + n].copy_(st['exp_avg'].reshape(-1))
+                exp_avg_sq_flat[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+                steps = max(steps, int(float(st['step'])))
+            off += n
+    for g, s in zip(param_groups, sd['param_groups']):
+        g.update({k: v for k, v in s.items() if k != 'params'})
+    return steps
 
 
 def get_optimizer(config, params, lr=None, beta1=None, eps=None, weight_decay=None):

@@ -1,0 +1,52 @@
+"""Checkpoint wire format of the reference (utils.py:14-48): `checkpoint_N.pth` / `flow_checkpoint_N.pth` are `torch.save`d dicts
+`{'optimizer': AdamW.state_dict(), 'model': DataParallel state dict ('module.'-prefixed keys), 'ema': {'decay', 'num_updates',
+'shadow_params'}, 'step': int}`.  Same function names, arguments and behaviour; the VDM-only entries are out of scope.
+`FusedAdamW` reads and writes torch.optim.AdamW's per-parameter layout (losses.pack_adamw_state), the model containers keep the
+reference's state-dict keys (tests/test_model_structure.py), so files move between the two code bases in both directions."""
+import logging
+import os
+
+import torch
+
+
+def restore_checkpoint(config, ckpt_dir, state, device):
+    """utils.py:14-34.  Missing file: warn, create the parent directory, return `state` unchanged.  VE-SDE runs do not restore the
+    optimizer (utils.py:23-24); the model is loaded with strict=False like the reference."""
+    if not os.path.exists(ckpt_dir):
+        os.makedirs(os.path.dirname(ckpt_dir) or '.', exist_ok=True)
+        logging.warning(f"No checkpoint found at {ckpt_dir}. Returned the same state as input")
+        return state
+    logging.info(ckpt_dir + ' loaded ...')
+    loaded_state = torch.load(ckpt_dir, map_location=device, weights_only=False)
+    if config.training.sde != 'vesde':
+        state['optimizer'].load_state_dict(loaded_state['optimizer'])
+    state['model'].load_state_dict(loaded_state['model'], strict=False)
+    state['ema'].load_state_dict(loaded_state['ema'])
+    state['step'] = loaded_state['step']
+    from . import _lib as L
+    L.param_epoch += 1                 # engines repack their operand copies of the weights on next use
+    return state
+
+
+def save_checkpoint(config, ckpt_dir, state):
+    """utils.py:37-48"""
+    saved_state = {
+        'optimizer': state['optimizer'].state_dict(),
+        'model': state['model'].state_dict(),
+        'ema': state['ema'].state_dict(),
+        'step': state['step'],
+    }
+    torch.save(saved_state, ckpt_dir)
+
+
+def create_name(prefix, name, ext):
+    """utils.py:50-59: `checkpoint_12.pth` from 12 / '12', `<prefix>_<stem>.<ext>` from a path-like name."""
+    try:
+        name = f'{prefix}_{int(name)}.{ext}'
+    except (TypeError, ValueError):
+        if len(name.split('.')) == 1:
+            name = f'{prefix}_{name}.{ext}'
+        else:
+            name = name.split('/')[-1]
+            name = f'{prefix}_{name.split(".")[0]}.{ext}'
+    return name

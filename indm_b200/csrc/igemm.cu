@@ -12,9 +12,10 @@
 // same accumulator (the res-block skip path Conv_2, models/layerspp.py:281-282), and the epilogue fuses bias,
 // per-image (time-embedding) bias, FP32 residual add, the 1/sqrt(2) skip rescale and the output cast.
 //
-// One CTA per output tile, 128 threads: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, then all four warps
-// drain TMEM (warp w owns TMEM lanes 32w..32w+31 = tile rows).  Several CTAs are co-resident per SM so one CTA's
-// epilogue overlaps another's main loop.
+// Execution: a PERSISTENT, warp-specialised kernel — one CTA per SM loops over output tiles; warp 0 = TMA producer, warp 1 =
+// MMA issuer (elect.sync-predicated, warp-uniform loops), 8 epilogue warps drain a DOUBLE-BUFFERED TMEM accumulator so the
+// epilogue of tile i overlaps the main loop of tile i+1; the launches that fill the chip run as CTA pairs (cta_group::2,
+// M = 256, B split across the pair).  The role table and the compile-time epilogue kinds are documented at igemm_kernel.
 #include <cuda.h>
 #include <cstdlib>
 

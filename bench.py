@@ -144,31 +144,75 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU arm
-def conv_roofline(net, eng, reps=3):
-    """Average achieved TFLOP/s of the dominant kernel (igemm) over one eager forward, CUDA events around every launch."""
+def _closure(op, cls_name=None, key=None):
+    for c in (op.__closure__ or ()):
+        v = c.cell_contents
+        if cls_name is not None and v.__class__.__name__ == cls_name:
+            return v
+    if key is not None:
+        names = op.__code__.co_freevars
+        if key in names:
+            return op.__closure__[names.index(key)].cell_contents
+    return None
+
+
+def _gn_apply_bytes(op):
+    """Algorithmic HBM bytes of one `indm_gn_apply` launch: input read once (fp32 residual stream or bf16) + operand-dtype output
+    (+ the raw operand copy when a skip conv follows) written once.  None for any other launch."""
+    if _closure(op, key="name") not in ("indm_gn_apply", "indm_gn_apply_dropout"):
+        return None
+    a = _closure(op, key="cargs")
+    val = lambda v: getattr(v, "value", v)
+    Ca, Cb, in_dt, N, H, W = val(a[1]), (val(a[3]) if val(a[2]) else 0), val(a[4]), val(a[5]), val(a[6]), val(a[7])
+    dropout = _closure(op, key="name") == "indm_gn_apply_dropout"
+    resample = 0 if dropout else val(a[14])
+    raw = None if dropout else val(a[16])
+    from indm_b200 import _lib as L
+    C = Ca + Cb
+    Po = H * W * (4 if resample == 1 else 1) // (4 if resample == 2 else 1)
+    return N * H * W * C * (4 if in_dt == L.DTYPE_F32 else 2) + N * Po * C * 2 * (2 if raw else 1)
+
+
+def kernel_rooflines(net, eng, reps=3):
+    """Per-launch device time of one eager forward, CUDA events around every launch on the launching stream.  The GPU is first parked
+    in a ~30 ms spin (`torch.cuda._sleep`) while the host enqueues the whole forward, so the intervals are kernel durations and not
+    host launch gaps (an eager launch costs the host ~10 us, more than the small kernels run).  Returns
+    (igemm TFLOP/s, igemm ms per launch, igemm launches per forward, igemm share of the forward's device time,
+     GroupNorm-apply GB/s, ms per launch, launches per forward, share)."""
     import torch
     for _ in range(2):
         eng.launch()
     torch.cuda.synchronize()
-    tot_ms, tot_fl, n_launch = 0.0, 0.0, 0
+    ig_ms = ig_fl = gn_ms = gn_by = all_ms = 0.0
+    n_ig = n_gn = 0
     for _ in range(reps):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(eng.ops) + 1)]
+        torch.cuda._sleep(60_000_000)
         evs[0].record()
         for i, op in enumerate(eng.ops):
             op()
             evs[i + 1].record()
         torch.cuda.synchronize()
         for i, op in enumerate(eng.ops):
-            d = None
-            for c in (op.__closure__ or ()):
-                if c.cell_contents.__class__.__name__ == "IgemmDesc":
-                    d = c.cell_contents
-            if d is None:
+            dt = evs[i].elapsed_time(evs[i + 1])
+            all_ms += dt
+            d = _closure(op, cls_name="IgemmDesc")
+            if d is not None:
+                ig_ms += dt
+                ig_fl += 2.0 * d.N * d.H * d.W * d.Cout * (d.Cin * d.taps + (d.Cin2 if d.a2 else 0))
+                n_ig += 1
                 continue
-            tot_ms += evs[i].elapsed_time(evs[i + 1])
-            tot_fl += 2.0 * d.N * d.H * d.W * d.Cout * (d.Cin * d.taps + (d.Cin2 if d.a2 else 0))
-            n_launch += 1
-    return tot_fl / (tot_ms * 1e-3) / 1e12, tot_ms / n_launch, n_launch // reps
+            try:
+                b = _gn_apply_bytes(op)
+            except Exception:
+                b = None
+            if b is not None:
+                gn_ms += dt
+                gn_by += b
+                n_gn += 1
+    return (ig_fl / (ig_ms * 1e-3) / 1e12, ig_ms / n_ig, n_ig // reps, ig_ms / all_ms,
+            (gn_by / (gn_ms * 1e-3) / 1e9 if n_gn else None), (gn_ms / n_gn if n_gn else None), n_gn // reps, gn_ms / all_ms,
+            all_ms / reps)
 
 
 def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup=16):
@@ -289,7 +333,7 @@ def run_ours(args):
     pk, pk_kind = peaks()
     traffic = igemm_traffic()
     eng = net.engine(PER_GPU_BATCH)
-    tf, ms_launch, n_ig = conv_roofline(net, eng)
+    tf, ms_launch, n_ig, ig_share, gn_gbs, gn_ms_launch, n_gn, gn_share, fwd_ms = kernel_rooflines(net, eng)
     peak_tf = pk["bf16_tflops_sustained"]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -307,9 +351,18 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                      "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/GEMM)", "peak_source": pk_kind + " bf16_tflops_sustained",
-                     "launches_per_forward": n_ig, "avg_launch_ms": ms_launch,
-                     "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD},
+                     "launches_per_forward": n_ig, "avg_launch_ms": ms_launch, "share_of_forward_device_time": ig_share,
+                     "forward_device_ms": fwd_ms, "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD,
+                     "timing": "CUDA events around every launch of an eager forward, GPU parked in a spin while the host enqueues"},
     }
+    if gn_gbs is not None:
+        # second kernel class of the step (norm / elementwise kernels are HBM bound)
+        out["roofline_hbm"] = {"bound": "hbm", "achieved": gn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn_gbs / pk["hbm_gbs"],
+                               "traffic": (traffic or {}).get("gn_apply_dram_bytes_per_launch"),
+                               "kernel": "gn_apply_kernel (GroupNorm + SiLU [+ resample] [+ raw operand copy])",
+                               "peak_source": pk_kind + " hbm_gbs", "launches_per_forward": n_gn, "avg_launch_ms": gn_ms_launch,
+                               "share_of_forward_device_time": gn_share,
+                               "algorithmic_bytes": "input read once (4 B fp32 residual stream / 2 B bf16) + 2 B output per element (+ 2 B raw copy)"}
     if train is not None:
         out["train"] = train
     if world == 1 and not args.skip_cpu:

@@ -56,6 +56,27 @@ def test_pf_ode_nll_matches_reference(mode, tol):
     assert e_z < (2e-2 if mode == 'tf32' else 0.6)
 
 
+def test_pf_ode_nll_device_integrator_matches_reference():
+    """method='RK45-device' (indm_b200/ode.py: SciPy's Dormand-Prince controller with the float64 state resident on the GPU) against
+    the live reference's SciPy run: same golden NLL within 0.01 bpd, same number of function evaluations as the SciPy path."""
+    g, cfg, model, flow, sde = _setup('tf32')
+    flow_kw, rad, gauss, _ = _draws(g, 'nll', len(oflow.block_layout(cfg)))
+    data = torch.from_numpy(g['data']).cuda()
+    out = {}
+    for method in ('RK45', 'RK45-device'):
+        fn = likelihood.get_likelihood_fn(cfg, sde, lambda v: (v + 1.) / 2., rtol=1e-3, atol=1e-3, method=method)
+        out[method] = fn(model, flow, data, eps_bpd=1e-5, epsilon=rad, noise=gauss[0], residual_noise=(gauss[1], gauss[2]),
+                         flow_kw=flow_kw)
+    torch.cuda.synchronize()
+    bpd, z, nfe = out['RK45-device']
+    err = float(np.abs(bpd.cpu().numpy() - g['nll_bpd']).max())
+    d = float((bpd - out['RK45'][0]).abs().max())
+    print(f'NLL device integrator: |err| vs reference {err:.2e}, vs SciPy path {d:.2e}; nfe {nfe} / SciPy path {out["RK45"][2]} / ref {int(g["nll_nfe"])}')
+    assert err < 0.01 and d < 0.01
+    assert abs(nfe - out['RK45'][2]) <= 12          # same controller; fp32-atomics noise in the RHS may move one step decision
+    assert rel_l2(z.cpu().numpy(), g['nll_z']) < 2e-2
+
+
 # 0.01 bpd (north_star) is held in the validation precision (observed 1e-4).  The BF16 Hutchinson term carries the BF16 rounding
 # of one forward + one VJP (score / VJP rel-L2 1e-2): observed 0.039 - 0.052 bpd from run to run (fp32 atomics in the fused
 # GroupNorm statistics reorder the roundings), so the production precision is bounded at 0.08.

@@ -174,17 +174,51 @@ def _gn_apply_bytes(op):
 
 
 def kernel_rooflines(net, eng, reps=3):
-    """Per-launch device time of one eager forward, CUDA events around every launch on the launching stream.  The GPU is first parked
-    in a ~30 ms spin (`torch.cuda._sleep`) while the host enqueues the whole forward, so the intervals are kernel durations and not
-    host launch gaps (an eager launch costs the host ~10 us, more than the small kernels run).  Returns
-    (igemm TFLOP/s, igemm ms per launch, igemm launches per forward, igemm share of the forward's device time,
-     GroupNorm-apply GB/s, ms per launch, launches per forward, share)."""
+    """Device time of the two kernel classes of one score-network forward, CUDA events on the launching stream, GPU first parked in
+    a ~30 ms spin (`torch.cuda._sleep`) while the host enqueues, so host launch gaps are not measured.  Two views:
+      * class stream: ONLY the launches of one class (all 115 igemm launches of the forward, in order, on their real buffers), back
+        to back between two events -> average launch duration = elapsed / launches.  Launches pipeline as they do inside the
+        sampler's CUDA graph; operands are NOT freshly written by a producer (5 GB of activations cycle through the 126 MB L2), so
+        this is cold-operand, i.e. conservative.  This is the figure `achieved` uses.
+      * evented: an event after every launch of the whole forward; each interval also contains the event-record / launch
+        serialisation (~4-5 us per launch, visible against ncu's per-kernel durations) -> reported as `*_evented` only."""
     import torch
     for _ in range(2):
         eng.launch()
     torch.cuda.synchronize()
-    ig_ms = ig_fl = gn_ms = gn_by = all_ms = 0.0
-    n_ig = n_gn = 0
+    ig_ops, gn_ops, ig_fl, gn_by = [], [], 0.0, 0.0
+    for op in eng.ops:
+        d = _closure(op, cls_name="IgemmDesc")
+        if d is not None:
+            ig_ops.append(op)
+            ig_fl += 2.0 * d.N * d.H * d.W * d.Cout * (d.Cin * d.taps + (d.Cin2 if d.a2 else 0))
+            continue
+        try:
+            b = _gn_apply_bytes(op)
+        except Exception:
+            b = None
+        if b is not None:
+            gn_ops.append(op)
+            gn_by += b
+
+    def stream_ms(ops):
+        tot = 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(60_000_000)
+            e0.record()
+            for op in ops:
+                op()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
+    fwd_ms = stream_ms(eng.ops)
+    ig_ms = stream_ms(ig_ops)
+    gn_ms = stream_ms(gn_ops) if gn_ops else None
+    # evented view
+    ev_ig = ev_gn = ev_all = 0.0
     for _ in range(reps):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(eng.ops) + 1)]
         torch.cuda._sleep(60_000_000)
@@ -195,24 +229,18 @@ def kernel_rooflines(net, eng, reps=3):
         torch.cuda.synchronize()
         for i, op in enumerate(eng.ops):
             dt = evs[i].elapsed_time(evs[i + 1])
-            all_ms += dt
-            d = _closure(op, cls_name="IgemmDesc")
-            if d is not None:
-                ig_ms += dt
-                ig_fl += 2.0 * d.N * d.H * d.W * d.Cout * (d.Cin * d.taps + (d.Cin2 if d.a2 else 0))
-                n_ig += 1
-                continue
-            try:
-                b = _gn_apply_bytes(op)
-            except Exception:
-                b = None
-            if b is not None:
-                gn_ms += dt
-                gn_by += b
-                n_gn += 1
-    return (ig_fl / (ig_ms * 1e-3) / 1e12, ig_ms / n_ig, n_ig // reps, ig_ms / all_ms,
-            (gn_by / (gn_ms * 1e-3) / 1e9 if n_gn else None), (gn_ms / n_gn if n_gn else None), n_gn // reps, gn_ms / all_ms,
-            all_ms / reps)
+            ev_all += dt
+            if op in ig_ops:
+                ev_ig += dt
+            elif op in gn_ops:
+                ev_gn += dt
+    eng.launch()                       # leave the buffers in a consistent state
+    torch.cuda.synchronize()
+    return dict(fwd_ms=fwd_ms, n_ig=len(ig_ops), ig_ms=ig_ms, ig_tflops=ig_fl / (ig_ms * 1e-3) / 1e12,
+                ig_tflops_evented=ig_fl / (ev_ig / reps * 1e-3) / 1e12, ig_share_evented=ev_ig / ev_all,
+                n_gn=len(gn_ops), gn_ms=gn_ms, gn_gbs=(gn_by / (gn_ms * 1e-3) / 1e9 if gn_ops else None),
+                gn_gbs_evented=(gn_by / (ev_gn / reps * 1e-3) / 1e9 if gn_ops else None), gn_share_evented=ev_gn / ev_all,
+                fwd_ms_evented=ev_all / reps)
 
 
 def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup=16):
@@ -333,7 +361,8 @@ def run_ours(args):
     pk, pk_kind = peaks()
     traffic = igemm_traffic()
     eng = net.engine(PER_GPU_BATCH)
-    tf, ms_launch, n_ig, ig_share, gn_gbs, gn_ms_launch, n_gn, gn_share, fwd_ms = kernel_rooflines(net, eng)
+    kr = kernel_rooflines(net, eng)
+    tf = kr["ig_tflops"]
     peak_tf = pk["bf16_tflops_sustained"]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -351,17 +380,22 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                      "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/GEMM)", "peak_source": pk_kind + " bf16_tflops_sustained",
-                     "launches_per_forward": n_ig, "avg_launch_ms": ms_launch, "share_of_forward_device_time": ig_share,
-                     "forward_device_ms": fwd_ms, "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD,
-                     "timing": "CUDA events around every launch of an eager forward, GPU parked in a spin while the host enqueues"},
+                     "launches_per_forward": kr["n_ig"], "avg_launch_ms": kr["ig_ms"] / kr["n_ig"],
+                     "share_of_forward_device_time": kr["ig_ms"] / kr["fwd_ms"], "forward_device_ms": kr["fwd_ms"],
+                     "algorithmic_gflop_per_image_forward": GFLOP_PER_IMAGE_FWD,
+                     "timing": "two CUDA events around the forward's 115 igemm launches issued back to back on their real buffers "
+                               "(cold operands), GPU parked in a spin while the host enqueues; forward_device_ms = the same for all launches",
+                     "achieved_evented": kr["ig_tflops_evented"], "share_evented": kr["ig_share_evented"],
+                     "evented_note": "event after every launch of the whole forward: intervals include ~4-5 us of event/launch serialisation"},
     }
-    if gn_gbs is not None:
+    if kr["gn_gbs"] is not None:
         # second kernel class of the step (norm / elementwise kernels are HBM bound)
-        out["roofline_hbm"] = {"bound": "hbm", "achieved": gn_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gn_gbs / pk["hbm_gbs"],
+        out["roofline_hbm"] = {"bound": "hbm", "achieved": kr["gn_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kr["gn_gbs"] / pk["hbm_gbs"],
                                "traffic": (traffic or {}).get("gn_apply_dram_bytes_per_launch"),
                                "kernel": "gn_apply_kernel (GroupNorm + SiLU [+ resample] [+ raw operand copy])",
-                               "peak_source": pk_kind + " hbm_gbs", "launches_per_forward": n_gn, "avg_launch_ms": gn_ms_launch,
-                               "share_of_forward_device_time": gn_share,
+                               "peak_source": pk_kind + " hbm_gbs", "launches_per_forward": kr["n_gn"], "avg_launch_ms": kr["gn_ms"] / kr["n_gn"],
+                               "share_of_forward_device_time": kr["gn_ms"] / kr["fwd_ms"],
+                               "achieved_evented": kr["gn_gbs_evented"], "share_evented": kr["gn_share_evented"],
                                "algorithmic_bytes": "input read once (4 B fp32 residual stream / 2 B bf16) + 2 B output per element (+ 2 B raw copy)"}
     if train is not None:
         out["train"] = train

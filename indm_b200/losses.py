@@ -102,6 +102,7 @@ def pack_adamw_state(params, steps, exp_avg_flat, exp_avg_sq_flat, param_groups)
     groups, base = [], 0
     for g in param_groups:
         d = {k: v for k, v in g.items() if k != 'params'}
+        d.setdefault('amsgrad', False)          # torch 1.7.1's AdamW (the reference's pin) reads it from the loaded group
         d['params'] = list(range(base, base + len(g['params'])))
         base += len(g['params'])
         groups.append(d)

@@ -89,3 +89,52 @@ def test_step_fn_updates_match_reference(mode, tol, step_tol, ema_tol):
         print(f'   update {n}: rel-L2 of the step {e:.2e}; ema max-abs err {e_ema:.2e}')
         assert e < step_tol, n
         assert e_ema < ema_tol
+
+
+def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
+    """Checkpoint wire format (reference utils.py:37-43 saves `optimizer.state_dict()` of torch.optim.AdamW): FusedAdamW emits and
+    accepts that layout, so optimisation continues identically after moving the state in either direction."""
+    from indm_b200.losses import FusedAdamW
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(0)
+    shapes = [(8, 4, 3, 3), (8,), (16, 8), (16,)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(3)]
+    kw = dict(lr=2e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
+
+    def params():
+        return [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+
+    def step(opt, ps, gs):
+        for p, gr in zip(ps, gs):
+            if p.grad is None:
+                p.grad = gr.to(dev).clone()
+            else:
+                p.grad.copy_(gr.to(dev))
+        opt.step()
+
+    pf, pt = params(), params()
+    fo, to = FusedAdamW(pf, **kw), torch.optim.AdamW(pt, **kw)
+    for k in range(2):
+        step(fo, pf, grads[k])
+        step(to, pt, grads[k])
+    sd_f, sd_t = fo.state_dict(), to.state_dict()
+    assert sorted(sd_f.keys()) == ['param_groups', 'state'] and sorted(sd_f['state'].keys()) == [0, 1, 2, 3]
+    assert sd_f['param_groups'][0]['params'] == [0, 1, 2, 3] and float(sd_f['state'][0]['step']) == 2.0
+    for i in range(4):
+        assert torch.allclose(sd_f['state'][i]['exp_avg'], sd_t['state'][i]['exp_avg'], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(sd_f['state'][i]['exp_avg_sq'], sd_t['state'][i]['exp_avg_sq'], rtol=1e-5, atol=1e-9)
+    # fused -> torch and torch -> fused, then one more step everywhere
+    pt2 = [torch.nn.Parameter(p.detach().clone()) for p in pf]
+    to2 = torch.optim.AdamW(pt2, lr=1.0)
+    to2.load_state_dict(sd_f)
+    pf2 = [torch.nn.Parameter(p.detach().clone()) for p in pt]
+    fo2 = FusedAdamW(pf2, lr=1.0)
+    fo2.load_state_dict(sd_t)
+    assert fo2.steps == 2 and fo2.param_groups[0]['lr'] == kw['lr']
+    for opt, ps in ((fo, pf), (to, pt), (to2, pt2), (fo2, pf2)):
+        step(opt, ps, grads[2])
+    torch.cuda.synchronize()
+    for i in range(4):
+        for other in (pt, pt2, pf2):
+            assert torch.allclose(pf[i], other[i], rtol=1e-5, atol=1e-6), (i, float((pf[i] - other[i]).abs().max()))

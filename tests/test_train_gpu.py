@@ -93,7 +93,9 @@ def test_step_fn_updates_match_reference(mode, tol, step_tol, ema_tol):
 
 def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
     """Checkpoint wire format (reference utils.py:37-43 saves `optimizer.state_dict()` of torch.optim.AdamW): FusedAdamW emits and
-    accepts that layout, so optimisation continues identically after moving the state in either direction."""
+    accepts that layout, so optimisation continues identically after moving the state in either direction.  The torch.optim.AdamW
+    side runs on the CPU (state dicts are deep-copied across, as `torch.save` / `torch.load` would)."""
+    import copy
     from indm_b200.losses import FusedAdamW
     dev = torch.device('cuda:0')
     g = torch.Generator().manual_seed(0)
@@ -102,39 +104,48 @@ def test_fused_adamw_state_dict_interoperates_with_torch_adamw():
     grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(3)]
     kw = dict(lr=2e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
 
-    def params():
-        return [torch.nn.Parameter(t.clone().to(dev)) for t in init]
-
     def step(opt, ps, gs):
         for p, gr in zip(ps, gs):
             if p.grad is None:
-                p.grad = gr.to(dev).clone()
+                p.grad = gr.to(p.device).clone()
             else:
-                p.grad.copy_(gr.to(dev))
+                p.grad.copy_(gr.to(p.device))
         opt.step()
 
-    pf, pt = params(), params()
+    def to_cpu(sd):
+        sd = copy.deepcopy(sd)
+        for st in sd['state'].values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    st[k] = v.detach().cpu().clone()
+        return sd
+
+    pf = [torch.nn.Parameter(t.clone().to(dev)) for t in init]
+    pt = [torch.nn.Parameter(t.clone()) for t in init]
     fo, to = FusedAdamW(pf, **kw), torch.optim.AdamW(pt, **kw)
     for k in range(2):
         step(fo, pf, grads[k])
         step(to, pt, grads[k])
-    sd_f, sd_t = fo.state_dict(), to.state_dict()
+    torch.cuda.synchronize()
+    sd_f, sd_t = to_cpu(fo.state_dict()), to_cpu(to.state_dict())
     assert sorted(sd_f.keys()) == ['param_groups', 'state'] and sorted(sd_f['state'].keys()) == [0, 1, 2, 3]
     assert sd_f['param_groups'][0]['params'] == [0, 1, 2, 3] and float(sd_f['state'][0]['step']) == 2.0
     for i in range(4):
+        assert torch.allclose(pf[i].detach().cpu(), pt[i].detach(), rtol=1e-5, atol=1e-6)
         assert torch.allclose(sd_f['state'][i]['exp_avg'], sd_t['state'][i]['exp_avg'], rtol=1e-5, atol=1e-7)
         assert torch.allclose(sd_f['state'][i]['exp_avg_sq'], sd_t['state'][i]['exp_avg_sq'], rtol=1e-5, atol=1e-9)
     # fused -> torch and torch -> fused, then one more step everywhere
-    pt2 = [torch.nn.Parameter(p.detach().clone()) for p in pf]
+    pt2 = [torch.nn.Parameter(p.detach().cpu().clone()) for p in pf]
     to2 = torch.optim.AdamW(pt2, lr=1.0)
     to2.load_state_dict(sd_f)
-    pf2 = [torch.nn.Parameter(p.detach().clone()) for p in pt]
+    pf2 = [torch.nn.Parameter(p.detach().clone().to(dev)) for p in pt]
     fo2 = FusedAdamW(pf2, lr=1.0)
     fo2.load_state_dict(sd_t)
-    assert fo2.steps == 2 and fo2.param_groups[0]['lr'] == kw['lr']
+    assert fo2.steps == 2 and fo2.param_groups[0]['lr'] == kw['lr'] and tuple(fo2.param_groups[0]['betas']) == (0.9, 0.99)
     for opt, ps in ((fo, pf), (to, pt), (to2, pt2), (fo2, pf2)):
         step(opt, ps, grads[2])
     torch.cuda.synchronize()
     for i in range(4):
-        for other in (pt, pt2, pf2):
-            assert torch.allclose(pf[i], other[i], rtol=1e-5, atol=1e-6), (i, float((pf[i] - other[i]).abs().max()))
+        for name, other in (('fused', pf), ('torch<-fused', pt2), ('fused<-torch', pf2)):
+            d = float((other[i].detach().cpu() - pt[i].detach()).abs().max())
+            assert d < 2e-6, (name, i, d)

@@ -32,6 +32,8 @@ METRIC = "pc_sampling_images_per_sec"
 UNIT = "images/s"
 PER_GPU_BATCH = 128
 NUM_SCALES = 1000
+WORKLOAD = ("vp/CIFAR10/indm_fid (DDPM++ nres=4 nf=128) + sampling.method=pc predictor=reverse_diffusion corrector=none, 1000 steps, "
+            "128 images per GPU (1024 / 8 GPUs); step = one full pc_sampler call")
 GFLOP_PER_IMAGE_FWD = 21.69      # score-net forward, CIFAR nres=4 (2*MAC, forward hooks on the reference)
 
 
@@ -137,7 +139,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": PER_GPU_BATCH / value * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "vp/CIFAR10/indm_fid + pc/reverse_diffusion/none, 1000 steps (CPU arm: bounded sample)"},
+           "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "num_scales": NUM_SCALES,
+                      "cpu_arm": "bounded sample of that workload on the host cores, extrapolated to the 1000-step figure; the flow inverse "
+                                 "(one pass per 1000 PC steps, < 1 % of the work) is not part of the sample"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -368,8 +372,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "vp/CIFAR10/indm_fid (DDPM++ nres=4 nf=128) + sampling.method=pc predictor=reverse_diffusion "
-                               "corrector=none, 1000 steps, 128 images per GPU (1024 / 8 GPUs); step = one full pc_sampler call"
+        "config": {"workload": WORKLOAD
                                + ("" if args.num_scales == NUM_SCALES else f" -- PROFILING SLICE with {args.num_scales} PC steps, not a bench value"),
                    "flow": flow_note, "per_gpu_batch": PER_GPU_BATCH, "num_scales": args.num_scales,
                    "l2_policy": "inputs larger than L2 (activations ~5 GB per forward), no flush",

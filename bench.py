@@ -101,7 +101,10 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(threads, n_pc=2, batch=16, repeats=1):
+CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH = 24, 32      # ~10 s of work on the GPU box's 16 host cores (0.45 s per PC step at batch 32)
+
+
+def cpu_sample(threads, n_pc=CPU_SAMPLE_STEPS, batch=CPU_SAMPLE_BATCH, repeats=1):
     """Bounded sample of the same workload on the host: `n_pc` reverse-diffusion PC steps of the oracle port (PyTorch CPU
     FP32 restatement of the reference, oracle/) at batch `batch`; extrapolated to the 1000-step figure."""
     import numpy as np
@@ -122,7 +125,7 @@ def cpu_sample(threads, n_pc=2, batch=16, repeats=1):
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     per_step = best / n_pc
-    return batch / (per_step * NUM_SCALES), f"{n_pc} PC steps (1 NFE each) of the oracle port at batch {batch}, FP32, extrapolated x{NUM_SCALES // n_pc}"
+    return batch / (per_step * NUM_SCALES), f"{n_pc} PC steps (1 NFE each) of the oracle port at batch {batch}, FP32, {best:.1f} s of CPU work, extrapolated x{NUM_SCALES / n_pc:.1f}"
 
 
 def run_reference(args):
@@ -132,7 +135,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     vals = []
     for i in range(args.warmup + args.steps):
-        v, sample = cpu_sample(threads, n_pc=2, batch=16)
+        v, sample = cpu_sample(threads)
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
@@ -403,7 +406,7 @@ def run_ours(args):
     if train is not None:
         out["train"] = train
     if world == 1 and not args.skip_cpu:
-        v, sample = cpu_sample(os.cpu_count() or 1, n_pc=2, batch=16)
+        v, sample = cpu_sample(os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -50,3 +50,16 @@ def create_name(prefix, name, ext):
             name = name.split('/')[-1]
             name = f'{prefix}_{name.split(".")[0]}.{ext}'
     return name
+
+
+def get_loss_fns(config, sde, inverse_scaler, train=True, scaler=None):
+    """utils.py:132-140: the four per-step callables the reference's train / eval loops use —
+    `(train_step_fn, nll_fn, nelbo_fn, sampling_fn)` — built from this package's hot-path factories."""
+    from . import likelihood, losses, sampling
+    optimize_fn = losses.optimization_manager(config)
+    train_step_fn = losses.get_step_fn(config, sde, train=train, optimize_fn=optimize_fn, scaler=scaler)
+    nll_fn = likelihood.get_likelihood_fn(config, sde, inverse_scaler, rtol=config.eval.rtol, atol=config.eval.atol)
+    nelbo_fn = likelihood.get_elbo_fn(config, sde, inverse_scaler=inverse_scaler)
+    sampling_shape = (config.sampling.batch_size, config.data.num_channels, config.data.image_size, config.data.image_size)
+    sampling_fn = sampling.get_sampling_fn(config, sde, sampling_shape, inverse_scaler, config.sampling.truncation_time)
+    return train_step_fn, nll_fn, nelbo_fn, sampling_fn

@@ -190,3 +190,14 @@ def test_get_bpd_loop_counts_and_means():
     assert (res['nll_train_eps'] is None) == (tt == 1e-5)
     if tt != 1e-5:
         assert seen['nll'][-1] == (True, tt, 500)
+
+
+@pytest.mark.parametrize("name", ["vp/CIFAR10/indm_nll", "vp/CIFAR10/indm_fid", "ve/CIFAR10/indm"])
+def test_get_loss_fns_builds_the_four_step_callables(name):
+    """reference utils.py:132-140"""
+    from indm_b200 import sde_lib
+    cfg = configs.get_config(name)
+    cfg.device = torch.device("cpu")
+    sde = sde_lib.get_sde(cfg)
+    fns = utils.get_loss_fns(cfg, sde, datasets.get_data_inverse_scaler(cfg), scaler=datasets.get_data_scaler(cfg))
+    assert len(fns) == 4 and all(callable(f) for f in fns)

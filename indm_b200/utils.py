@@ -9,6 +9,9 @@ import os
 import torch
 
 
+_STATEFUL = ('optimizer', 'model', 'ema')          # entries restored through load_state_dict / saved through state_dict
+
+
 def restore_checkpoint(config, ckpt_dir, state, device):
     """utils.py:14-34.  Missing file: warn, create the parent directory, return `state` unchanged.  VE-SDE runs do not restore the
     optimizer (utils.py:23-24); the model is loaded with strict=False like the reference."""
@@ -17,12 +20,15 @@ def restore_checkpoint(config, ckpt_dir, state, device):
         logging.warning(f"No checkpoint found at {ckpt_dir}. Returned the same state as input")
         return state
     logging.info(ckpt_dir + ' loaded ...')
-    loaded_state = torch.load(ckpt_dir, map_location=device, weights_only=False)
-    if config.training.sde != 'vesde':
-        state['optimizer'].load_state_dict(loaded_state['optimizer'])
-    state['model'].load_state_dict(loaded_state['model'], strict=False)
-    state['ema'].load_state_dict(loaded_state['ema'])
-    state['step'] = loaded_state['step']
+    loaded = torch.load(ckpt_dir, map_location=device, weights_only=False)
+    for key in _STATEFUL:
+        if key == 'optimizer' and config.training.sde == 'vesde':
+            continue
+        if key == 'model':
+            state[key].load_state_dict(loaded[key], strict=False)
+        else:
+            state[key].load_state_dict(loaded[key])
+    state['step'] = loaded['step']
     from . import _lib as L
     L.param_epoch += 1                 # engines repack their operand copies of the weights on next use
     return state
@@ -30,13 +36,9 @@ def restore_checkpoint(config, ckpt_dir, state, device):
 
 def save_checkpoint(config, ckpt_dir, state):
     """utils.py:37-48"""
-    saved_state = {
-        'optimizer': state['optimizer'].state_dict(),
-        'model': state['model'].state_dict(),
-        'ema': state['ema'].state_dict(),
-        'step': state['step'],
-    }
-    torch.save(saved_state, ckpt_dir)
+    payload = {key: state[key].state_dict() for key in _STATEFUL}
+    payload['step'] = state['step']
+    torch.save(payload, ckpt_dir)
 
 
 def create_name(prefix, name, ext):

@@ -128,6 +128,55 @@ def cpu_sample(threads, n_pc=CPU_SAMPLE_STEPS, batch=CPU_SAMPLE_BATCH, repeats=1
     return batch / (per_step * NUM_SCALES), f"{n_pc} PC steps (1 NFE each) of the oracle port at batch {batch}, FP32, {best:.1f} s of CPU work, extrapolated x{NUM_SCALES / n_pc:.1f}"
 
 
+def cpu_train_sample(threads, batch=8):
+    """Bounded sample of the second metric on the host: ONE joint training step (flow_step_fn_nll, reference losses.py:258-320) of the
+    oracle port at batch `batch`: wolf flow forward in training mode with the Neumann log-det series (autograd VJPs, last one with
+    create_graph), score-network forward on the latent, DSM loss with importance-sampled t, prior log-p, and ONE backward through
+    both networks.  The optimiser update (AdamW + EMA: ~0.1 % of the step on CPU) is left out; dropout is not part of the oracle."""
+    import numpy as np
+    import torch
+    from indm_b200 import configs
+    from oracle import ncsnpp as oncsnpp, sde as osde, flow as oflow
+    torch.set_num_threads(threads)
+    cfg = configs.get_config("vp/CIFAR10/indm_nll")
+    cfg.device = torch.device("cpu")
+    Ps = {k: v.requires_grad_(True) for k, v in oncsnpp.to_torch(oncsnpp.synth_params(cfg, 0)).items()}
+    Pf = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in oflow.to_torch(oflow.synth_params(cfg, 1)).items()}
+    sde = osde.get_sde(cfg)
+    g = torch.Generator().manual_seed(0)
+    rng = np.random.RandomState(0)
+    x = torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1
+    layout = oflow.block_layout(cfg)
+    shp = oflow.flow_input_shape(cfg)
+    ns = rng.poisson(2.0, size=len(layout))
+    varepss = []
+    for (s_, b_, c_, first_) in layout:
+        f = 2 ** s_
+        varepss.append(torch.randn(batch, c_, shp[1] // f, shp[2] // f, generator=g))
+    eps_post = torch.randn(batch, 64, generator=g)
+    u = torch.rand(batch, generator=g)
+    noise = torch.randn(batch, 3, 32, 32, generator=g)
+    noise_T = torch.randn(batch, 3, 32, 32, generator=g)
+    t0 = time.perf_counter()
+    z, logdet_minus_kl, _, _ = oflow.wolf_train_forward(cfg, Pf, x, eps_post, ns, varepss)
+    t, Z = sde.importance_time(u, cfg.training.truncation_time)
+    mean, std = sde.marginal_prob(z, t)
+    perturbed = mean + std[:, None, None, None] * noise
+    score = oncsnpp.score_fn(cfg, sde, Ps, perturbed, t)
+    losses_score = 0.5 * Z * ((score * std[:, None, None, None] + noise) ** 2).reshape(batch, -1).sum(1)
+    meanT, stdT = sde.marginal_prob(z, torch.ones(batch))
+    logp = sde.prior_logp(meanT + stdT[:, None, None, None] * noise_T)
+    loss = torch.mean(losses_score - logdet_minus_kl - logp)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    assert sum(1 for v in Ps.values() if v.grad is None) <= 1, "score-network parameters without gradient"     # `sigmas` is a buffer
+    n_flow = sum(1 for v in Pf.values() if v.requires_grad and v.grad is not None)
+    assert n_flow > 0.9 * sum(1 for v in Pf.values() if v.requires_grad), "flow parameters without gradient"
+    n_vjp = int(sum(int(n) + 3 for n in ns))
+    return batch / dt, (f"1 joint step (flow fwd with {n_vjp} autograd VJPs + score fwd + one backward through both) of the oracle port at "
+                        f"batch {batch}, FP32, {dt:.1f} s of CPU work")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -408,6 +457,12 @@ def run_ours(args):
     if world == 1 and not args.skip_cpu:
         v, sample = cpu_sample(os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+        if train is not None:
+            try:
+                tv, tsample = cpu_train_sample(os.cpu_count() or 1)
+                out["train"]["cpu_baseline"] = {"value": tv, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": tsample}
+            except Exception as e:             # a reported baseline only: never let it take the bench line down
+                out["train"]["cpu_baseline"] = {"value": None, "error": repr(e)[:200]}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -14,5 +14,7 @@ Modules
   sde.py      VP / VE SDE math                     (sde_lib.py)
   ncsnpp.py   NCSN++ / DDPM++ forward, score_fn    (models/ncsnpp.py, layerspp.py, layers.py, utils.py)
   sampler.py  predictor / corrector / pc_sampler   (sampling.py)
+  flow.py     wolf flow: posterior encoder, prior flow, iResBlocks (forward / inverse / log-det series / differentiable
+              training forward)                    (flow_models/wolf/**: wolf.py, resflow_.py, iresblock.py, priors/flow.py ...)
   ref_loader.py + ref_stubs/   import shim for the unmodified reference (build container only)
 """

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Index-math model (numpy, CPU) of the padded-pixel implicit GEMM planned for round 2: a 3x3 stride-1 pad-1
+convolution over NHWC activations where ONE halo tile per K chunk serves all nine taps.
+
+Geometry.  Wp = W + 2.  The padded image P[y', x'] (y' in [0, H + 2), x' in [0, Wp)) is X shifted by (1, 1) with a zero border;
+its pixels are numbered q = y' * Wp + x'.  A tile owns R output rows y0 .. y0 + R - 1 of one image and issues MMAs of `tile_m` rows:
+GEMM row m <-> output position (y0 + m // Wp, m % Wp); rows with m % Wp >= W or m >= R * Wp are junk (computed, never stored).
+The shared-memory halo tile holds padded rows y0 .. y0 + R + 1 (what one TMA box [1][R + 2][Wp][64ch] at coordinates
+(y0 - 1, -1) delivers, out-of-bounds zero-filled), i.e. local pixel index l = q - y0 * Wp, and tap (dy, dx) in {-1, 0, 1}^2 reads
+the rows  l = (1 + dy) * Wp + (1 + dx) + m : the same tile at a constant row offset — a descriptor start-address offset of
+((1 + dy) * Wp + 1 + dx) * 128 bytes on the device.  The largest row touched is 2 * Wp + 2 + tile_m - 1, so the buffer is
+`halo_rows(tile_m, W)` rows long; rows past the loaded box are only ever read by junk GEMM rows.
+
+`conv3x3_padded_pixel` executes exactly that schedule with numpy (fp64) and is checked against a direct convolution in
+tests/test_halo_model_cpu.py; `plan` is the host-side tile list a launcher would build."""
+import numpy as np
+
+
+def rows_per_tile(tile_m, W):
+    return max(tile_m // (W + 2), 0)
+
+
+def halo_rows(tile_m, W):
+    return 2 * (W + 2) + 2 + tile_m
+
+
+def plan(N, H, W, tile_m=128):
+    """[(image, y0, R)]: tiles never span images (TMA zero-fills only at tensor edges); the last tile of an image may be short"""
+    R = rows_per_tile(tile_m, W)
+    if R < 1:
+        raise ValueError(f"image rows of {W} + 2 pixels do not fit a {tile_m}-row tile")
+    return [(n, y0, min(R, H - y0)) for n in range(N) for y0 in range(0, H, R)]
+
+
+def mma_row_efficiency(H, W, tile_m=128):
+    """useful GEMM rows / issued GEMM rows over one image"""
+    tiles = plan(1, H, W, tile_m)
+    return H * W / (len(tiles) * tile_m)
+
+
+def operand_bytes_per_tile(W, cin, cout_per_cta, tile_m=128, elem=2):
+    """(padded-pixel, per-tap) shared-memory fill per tile: A halo once per 64-channel chunk + nine B taps, against nine A boxes +
+    nine B taps"""
+    chunks = (cin + 63) // 64
+    R = rows_per_tile(tile_m, W)
+    halo = (R + 2) * (W + 2) * 64 * elem
+    b = cout_per_cta * 64 * elem
+    return chunks * (halo + 9 * b), chunks * 9 * (tile_m * 64 * elem + b)
+
+
+def conv3x3_padded_pixel(x, w, tile_m=128):
+    """x [N, H, W, Cin], w [3, 3, Cout, Cin] (tap-major like the engine's weight pack) -> y [N, H, W, Cout], following the tile
+    schedule above: per tile, per 64-channel chunk, one halo tile; per tap one GEMM of `tile_m` rows at a row offset."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[2]
+    Wp = W + 2
+    y = np.zeros((N, H, W, Cout), dtype=np.float64)
+    for (n, y0, R) in plan(N, H, W, tile_m):
+        acc = np.zeros((tile_m, Cout), dtype=np.float64)                 # the TMEM accumulator
+        for c0 in range(0, Cin, 64):
+            c1 = min(c0 + 64, Cin)
+            halo = np.full((halo_rows(tile_m, W), c1 - c0), np.nan)      # NaN = never loaded: only junk rows may read it
+            box = np.zeros((R + 2, Wp, c1 - c0))                          # TMA box, out-of-bounds zero-filled
+            ylo, yhi = max(y0 - 1, 0), min(y0 + R + 1, H)
+            box[ylo - (y0 - 1):yhi - (y0 - 1), 1:W + 1] = x[n, ylo:yhi, :, c0:c1]
+            halo[:(R + 2) * Wp] = box.reshape(-1, c1 - c0)
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    off = (1 + dy) * Wp + (1 + dx)
+                    a = halo[off:off + tile_m]                             # the shifted view: a start-address offset on the device
+                    acc += np.nan_to_num(a, nan=1e30) @ w[dy + 1, dx + 1, :, c0:c1].T.astype(np.float64)
+        for m in range(R * Wp):                                           # epilogue: drop junk rows
+            if m % Wp < W:
+                y[n, y0 + m // Wp, m % Wp] = acc[m]
+    return y
+
+
+if __name__ == "__main__":
+    for (H, W, cin, cout) in [(32, 32, 128, 128), (32, 32, 256, 128), (16, 16, 256, 256), (64, 64, 128, 128)]:
+        for tile_m, half in ((128, cout), (256, cout // 2)):
+            new, old = operand_bytes_per_tile(W, cin, half if tile_m == 256 else cout, 128 if tile_m == 128 else 128)
+            print(f"{H}x{W} {cin}->{cout} tile_m={tile_m}: row efficiency {mma_row_efficiency(H, W, tile_m):.2f}, "
+                  f"operand bytes per CTA tile {new / 1024:.0f} KB vs {old / 1024:.0f} KB per-tap")

@@ -7,15 +7,34 @@ import logging
 import numpy as np
 import torch
 
-from . import datasets
+from . import datasets, parallel
+
+
+def _stats(values):
+    """(mean, std, count) of a list of per-sample figures over ALL ranks: under torch.distributed every rank holds the figures of its
+    own slice of each batch (evaluation shards by image, no data-path collective); three float64 scalars are summed."""
+    v = np.asarray(values, dtype=np.float64)
+    acc = torch.tensor([v.sum(), (v * v).sum(), float(v.size)], dtype=torch.float64)
+    rank, ws = parallel.world()
+    if ws > 1:
+        import torch.distributed as dist
+        dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+        acc = acc.to(dev)
+        dist.all_reduce(acc)
+        acc = acc.cpu()
+    n = max(float(acc[2]), 1.0)
+    mean = float(acc[0]) / n
+    return mean, float(max(float(acc[1]) / n - mean * mean, 0.0) ** 0.5), int(acc[2])
 
 
 def _passes(config, eval_ds, scaler, num_data, fn):
-    """One pass over ceil(num_data / eval.batch_size) batches; `fn(batch) -> tuple of [B] tensors`; returns lists of floats."""
+    """One pass over ceil(num_data / eval.batch_size) batches; `fn(batch) -> tuple of [B] tensors`; returns lists of floats (this
+    rank's slice of every batch when torch.distributed is initialised: every rank iterates the same `eval_ds`)."""
     outs = None
     it = iter(eval_ds)
     for _ in range((num_data - 1) // config.eval.batch_size + 1):
         batch, it = datasets.get_batch(config, it, eval_ds)
+        batch = parallel.shard_batch(batch)
         batch = scaler(datasets.dequantize(batch))
         vals = fn(batch)
         if outs is None:
@@ -36,11 +55,11 @@ def get_bpd(config, eval_ds, scaler, nelbo_fn, nll_fn, score_model, flow_model=N
         full, full_res = [], []
         for _ in range(config.eval.num_nelbo):
             a, b = _passes(config, eval_ds, scaler, num_data, lambda x: nelbo_fn(score_model, flow_model, x, None))
-            full.append(np.mean(a))
-            full_res.append(np.mean(b))
-            logging.info("step: %d, num samples: %d, mean nelbo bpd: %.5e, std nelbo bpd: %.5e" % (step, len(a), np.mean(a), np.std(a)))
-            logging.info("step: %d, num samples: %d, mean nelbo_residual bpd: %.5e, std nelbo_residual bpd: %.5e"
-                         % (step, len(b), np.mean(b), np.std(b)))
+            (ma, sa, na), (mb, sb, nb) = _stats(a), _stats(b)
+            full.append(ma)
+            full_res.append(mb)
+            logging.info("step: %d, num samples: %d, mean nelbo bpd: %.5e, std nelbo bpd: %.5e" % (step, na, ma, sa))
+            logging.info("step: %d, num samples: %d, mean nelbo_residual bpd: %.5e, std nelbo_residual bpd: %.5e" % (step, nb, mb, sb))
         if full:
             res['nelbo'], res['nelbo_residual'] = float(np.mean(full)), float(np.mean(full_res))
             logging.info("step: %d, average nelbo bpd out of %d evaluations: %.5e" % (step, len(full), np.mean(full)))
@@ -52,8 +71,9 @@ def get_bpd(config, eval_ds, scaler, nelbo_fn, nll_fn, score_model, flow_model=N
         def nll(residual, eps, tag):
             (v,) = _passes(config, eval_ds, scaler, num_data,
                            lambda x: (nll_fn(score_model, flow_model, x, None, residual=residual, eps_bpd=eps)[0],))
-            logging.info("step: %d, [%s] num samples: %d, mean nll bpd: %.5e, std nll bpd: %.5e" % (step, tag, len(v), np.mean(v), np.std(v)))
-            return float(np.mean(v))
+            m, sd, cnt = _stats(v)
+            logging.info("step: %d, [%s] num samples: %d, mean nll bpd: %.5e, std nll bpd: %.5e" % (step, tag, cnt, m, sd))
+            return m
 
         if not config.eval.skip_nll_wrong:
             res['nll_wrong'] = nll(False, eps_bpd, "NLL WRONG w/ eps=%.1e" % eps_bpd)

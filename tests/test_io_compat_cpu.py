@@ -201,3 +201,48 @@ def test_get_loss_fns_builds_the_four_step_callables(name):
     sde = sde_lib.get_sde(cfg)
     fns = utils.get_loss_fns(cfg, sde, datasets.get_data_inverse_scaler(cfg), scaler=datasets.get_data_scaler(cfg))
     assert len(fns) == 4 and all(callable(f) for f in fns)
+
+
+def test_sample_cache_pc_denoise_branch(tmp_path):
+    """sampling_lib.py:60-105: with sampling.pc_denoise the cached latent-side samples are denoised by a second sampler call
+    (`final_time=`, `before_data=scaler(cached)`), cached under `*_denoise_{time}.npz`; a cached denoised latent is only pushed
+    through the flow inverse again."""
+    cfg = configs.get_config("vp/CIFAR10/indm_fid")
+    cfg.data.image_size = 8
+    cfg.flow.model = "identity"
+    cfg.device = torch.device("cpu")
+    cfg.sampling.pc_denoise = True
+    cfg.sampling.pc_denoise_time = 0.001
+    scaler, inv = datasets.get_data_scaler(cfg), datasets.get_data_inverse_scaler(cfg)
+    g = torch.Generator().manual_seed(0)
+    before = torch.rand(4, 3, 8, 8, generator=g)
+    after = torch.rand(4, 3, 8, 8, generator=g)
+    calls = []
+
+    def sampling_fn(score_model, flow_model, temperature, data_mean, sample_dir=None, r=None, final_time=0., before_data=None):
+        calls.append((final_time, None if before_data is None else before_data.clone()))
+        if before_data is None:
+            return before, after, 1000
+        return inv(before_data) * 0.5, inv(before_data) * 0.25, 10      # a recognisable "denoised" result
+
+    sd, td = str(tmp_path / "s"), str(tmp_path / "s" / "ckpt")
+    out = sampling_lib.get_samples(cfg, None, None, sampling_fn, 1, 3, sd, inverse_scaler=inv, this_sample_dir=td, scaler=scaler)
+    assert [c[0] for c in calls] == [0., 0.001]
+    cached = np.load(os.path.join(sd, "samples_3_before_flow.npz"))["samples"]
+    want_in = scaler(torch.tensor(cached).permute(0, 3, 1, 2) / 255.)
+    assert torch.allclose(calls[1][1].double(), want_in.double(), atol=1e-6)
+    den = np.load(os.path.join(td, "samples_3_denoise_0.001.npz"))["samples"]
+    np.testing.assert_array_equal(out, den)
+    assert np.abs(den.astype(np.int64) - np.clip(cached * 0.25, 0., 255.).astype(np.uint8).astype(np.int64)).max() <= 1
+    assert den.dtype == np.uint8 and den.shape == (4, 8, 8, 3)
+    assert os.path.exists(os.path.join(sd, "samples_3_before_flow_denoise_0.001.npz"))
+    # second call: everything cached, the sampler is not invoked
+    out2 = sampling_lib.get_samples(cfg, None, None, sampling_fn, 1, 3, sd, inverse_scaler=inv, this_sample_dir=td, scaler=scaler)
+    assert len(calls) == 2
+    np.testing.assert_array_equal(out2, den)
+    # denoised latent cached but final file missing: only the (identity) flow inverse runs
+    os.remove(os.path.join(td, "samples_3_denoise_0.001.npz"))
+    out3 = sampling_lib.get_samples(cfg, None, None, sampling_fn, 1, 3, sd, inverse_scaler=inv, this_sample_dir=td, scaler=scaler)
+    assert len(calls) == 2
+    lat = np.load(os.path.join(sd, "samples_3_before_flow_denoise_0.001.npz"))["samples"]
+    np.testing.assert_array_equal(out3, np.clip(lat, 0., 255.).astype(np.uint8))

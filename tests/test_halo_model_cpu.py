@@ -36,3 +36,22 @@ def test_plan_and_buffer_sizes():
     assert new < 0.6 * old
     with pytest.raises(ValueError):
         hm.plan(1, 4, 200, 128)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 32, 32, 64, 8), (1, 16, 16, 128, 4), (1, 64, 64, 64, 4), (2, 9, 30, 16, 4), (1, 3, 126, 8, 2)])
+def test_cta_pair_schedule_with_tma_store_clipping(N, H, W, Cin, Cout):
+    """each CTA of a pair loads its own halo box (row-granular extra offset for CTA 1), the output box clips junk columns / rows"""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((N, H, W, Cin))
+    w = rng.standard_normal((3, 3, Cout, Cin))
+    got = hm.conv3x3_padded_pixel_pair(x, w)
+    want = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2),
+                                      torch.from_numpy(w).permute(2, 3, 0, 1).contiguous(), padding=1).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10)
+
+
+def test_pair_halo_box_sizes():
+    assert hm.pair_halo_box(0, 32) == (0, 6, 0)                 # CTA 0: 6 padded rows (26 KB per 64-channel chunk)
+    skip, rows, shift = hm.pair_halo_box(1, 32)
+    assert (skip, shift) == (3, 26) and rows == 7              # CTA 1 starts 26 pixels into padded row 3
+    assert rows * 34 * 128 <= 32 * 1024

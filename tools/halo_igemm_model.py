@@ -75,6 +75,53 @@ def conv3x3_padded_pixel(x, w, tile_m=128):
     return y
 
 
+def pair_halo_box(r, W, tile_m_cta=128):
+    """CTA pair (cta_group::2, M = 256): CTA r owns GEMM rows [128 r, 128 r + 128) of the 256-row tile.  Its own halo box starts
+    `skip` padded rows below the tile's first halo row and its taps carry an extra row offset `shift` (the position of row 128 r
+    inside its first padded row); `rows` padded rows cover everything its 128 GEMM rows can touch.
+    Returns (skip, rows, shift)."""
+    Wp = W + 2
+    first = r * tile_m_cta
+    skip, shift = first // Wp, first % Wp
+    last_touched = shift + 2 * Wp + 2 + tile_m_cta - 1            # largest local row index read by any tap
+    rows = last_touched // Wp + 1
+    return skip, rows, shift
+
+
+def conv3x3_padded_pixel_pair(x, w):
+    """Same schedule for CTA pairs: a 256-row tile owns R = 256 // Wp image rows; each CTA of the pair loads its OWN halo box
+    (`pair_halo_box`) and contributes GEMM rows [128 r, 128 r + 128); the epilogue is the TMA-store view: the tile's rows are the
+    box [Cout][Wp][R] at x = 0, whose columns x >= W and rows y >= H the hardware clips."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[2]
+    Wp = W + 2
+    y = np.zeros((N, H, W, Cout), dtype=np.float64)
+    for (n, y0, R) in plan(N, H, W, 256):
+        Rfull = rows_per_tile(256, W)
+        acc = np.zeros((256, Cout), dtype=np.float64)
+        for r in (0, 1):
+            skip, rows, shift = pair_halo_box(r, W)
+            for c0 in range(0, Cin, 64):
+                c1 = min(c0 + 64, Cin)
+                box = np.zeros((rows, Wp, c1 - c0))                                 # TMA box at (y0 - 1 + skip, -1), zero-filled
+                for i in range(rows):
+                    yy = y0 - 1 + skip + i
+                    if 0 <= yy < H:
+                        box[i, 1:W + 1] = x[n, yy, :, c0:c1]
+                halo = box.reshape(-1, c1 - c0)
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        off = shift + (1 + dy) * Wp + (1 + dx)
+                        assert off + 128 <= halo.shape[0]                            # never reads past the loaded box
+                        acc[128 * r:128 * r + 128] += halo[off:off + 128] @ w[dy + 1, dx + 1, :, c0:c1].T.astype(np.float64)
+        # TMA store of the box [Cout][Wp][Rfull] at (x = 0, y = y0): out-of-bounds columns / rows are clipped by the hardware
+        tile = acc[:Rfull * Wp].reshape(Rfull, Wp, Cout)
+        for i in range(Rfull):
+            if y0 + i < H:
+                y[n, y0 + i] = tile[i, :W]
+    return y
+
+
 if __name__ == "__main__":
     for (H, W, cin, cout) in [(32, 32, 128, 128), (32, 32, 256, 128), (16, 16, 256, 256), (64, 64, 128, 128)]:
         for tile_m, half in ((128, cout), (256, cout // 2)):

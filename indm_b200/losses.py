@@ -6,10 +6,11 @@ run on the engine's explicit plans (models/engine.py); the DSM loss and its grad
 AdamW run as one pass over flat parameter storage; under torch.distributed the flat gradient buffer is all-reduced with NCCL
 before the clip (data-parallel training, one process per GPU, where the reference uses nn.DataParallel).
 
-Scope of this module: `step_fn` (score network only) is complete.  The joint flow + score step functions need gradients
-through the flow (first-order through g and its posterior encoder, second-order through the Neumann log-det estimator,
-iresblock.py:264-273); those are not on the CUDA path yet, so `flow_step_fn_*` train the score network on the flow's latent
-with the flow parameters frozen and say so loudly unless `config.training.freeze_flow` acknowledges it.
+Scope of this module: `step_fn` (score network only), `flow_step_fn_nll` and `flow_step_fn_fid` (JOINT flow + score steps,
+both phases of the FID variant) are complete: the flow's gradients — first order through g and the posterior encoder, second
+order through the Neumann log-det estimator (iresblock.py:264-273) — come from the explicit backward plans of
+flow_models/wolf_backward.py, reached through torch.autograd.  Joint training is the default, like the reference;
+`config.training.freeze_flow=True` opts into a variant that keeps the flow parameters fixed.
 """
 import logging
 
@@ -17,11 +18,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from . import sde_lib
 from .flow_models.flow_model import flow_forward
 from .models import utils as mutils
-from .models.ema import flat_view
-from .sde_lib import VESDE, VPSDE
 
 
 # ------------------------------------------------------------------------------------------------ optimizer
@@ -34,6 +32,8 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True):
         params = [p for p in params]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise NotImplementedError('FusedAdamW steps one parameter group (the reference builds one, losses.py:33-41)')
         ps = [p for g in self.param_groups for p in g['params'] if p.requires_grad]
         if not ps or not ps[0].is_cuda:
             raise RuntimeError('indm_b200 FusedAdamW needs CUDA parameters: there is no CPU path')
@@ -93,7 +93,10 @@ class FusedAdamW(torch.optim.Optimizer):
 def pack_adamw_state(params, steps, exp_avg_flat, exp_avg_sq_flat, param_groups):
     """Flat moment buffers -> the dict `torch.optim.AdamW.state_dict()` returns (state empty before the first step, like torch)."""
     state, off = {}, 0
-    for i, p in enumerate(params):
+    every = [p for g in param_groups for p in g['params']]      # torch indexes state by position in the FULL group list:
+    for i, p in enumerate(every):                               # a frozen parameter keeps its index and simply has no state
+        if not p.requires_grad:
+            continue
         n = p.numel()
         if steps > 0:
             state[i] = dict(step=torch.tensor(float(steps)), exp_avg=exp_avg_flat[off:off + n].view_as(p),
@@ -119,13 +122,16 @@ def unpack_adamw_state(sd, params, exp_avg_flat, exp_avg_sq_flat, param_groups):
             g.update({k: v for k, v in s.items() if k != 'params'})
         return int(sd['steps'])
     n_saved = sum(len(g['params']) for g in sd['param_groups'])
-    if n_saved != len(params):
+    every = [p for g in param_groups for p in g['params']]
+    if n_saved != len(every):
         raise ValueError(f"loaded state dict contains a parameter group that doesn't match the size of optimizer's group "
-                         f"({n_saved} vs {len(params)} parameters)")
+                         f"({n_saved} vs {len(every)} parameters)")
     ids = [i for g in sd['param_groups'] for i in g['params']]
     steps, off = 0, 0
     with torch.no_grad():
-        for i, p in zip(ids, params):
+        for i, p in zip(ids, every):
+            if not p.requires_grad:       # frozen: holds an index, no state (torch.optim.AdamW never steps it)
+                continue
             n = p.numel()
             st = sd['state'].get(i)
             if st is None:

@@ -501,7 +501,10 @@ class ScoreEngine:
         self._bind_time_source(None, None, 0, 0)
 
     def _bind_time_source(self, sched, step, sched_ld, sched_col):
-        """time embedding reads `self.time_cond[n]`, or a device schedule table row `*step` (sampler graphs)."""
+        """Build the time-embedding launch that reads `self.time_cond[n]` (sched is None: installed as the plan's default) or a
+        device schedule table row `*step`.  The schedule-reading launch is only RETURNED: the sampler passes it to
+        `launch(temb_op=...)` for the launches it captures, so an ordinary `forward(x, t)` on the same (cached) engine is always
+        conditioned on `t` (it used to stay bound to the sampler's table after any PC sampling call)."""
         a = self._temb_args
         fn = L.lib().indm_time_embedding
         args = [ctypes.c_void_p(self.time_cond.data_ptr()),
@@ -512,8 +515,10 @@ class ScoreEngine:
 
         def run():
             L.check(fn(*args, L._stream()), 'indm_time_embedding')
-        self.ops[self._temb_op_index] = run
         self.keep.append((sched, step))
+        if sched is None:
+            self.ops[self._temb_op_index] = run
+        return run
 
 
     # ------------------------------------------------------------------ backward (input-VJP) plan
@@ -887,10 +892,14 @@ class ScoreEngine:
         return self.gx
 
     # ------------------------------------------------------------------ execution
-    def launch(self):
-        """enqueue the whole forward on the current stream (inputs: self.x_in, self.time_cond / schedule, self.out_scale)"""
-        for op in self.ops:
-            op()
+    def launch(self, temb_op=None):
+        """enqueue the whole forward on the current stream (inputs: self.x_in, self.time_cond, self.out_scale); `temb_op` (from
+        `_bind_time_source(sched, ...)`) replaces the time-embedding launch for this call only (sampler graphs)"""
+        for i, op in enumerate(self.ops):
+            if temb_op is not None and i == self._temb_op_index:
+                temb_op()
+            else:
+                op()
 
     def forward(self, x, time_cond, out_scale=None, train=False, seed=None):
         """train=True enables the dropout masks (a fresh Philox seed per call unless `seed` is given)"""

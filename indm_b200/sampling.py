@@ -339,7 +339,7 @@ class _GraphedPC:
             self.sched.copy_(rows)          # same buffer: the captured graph stays valid
         else:
             self.sched = rows.to(self.dev)
-            self.eng._bind_time_source(self.sched, self.step, self.LD, 0)
+            self._temb_op = self.eng._bind_time_source(self.sched, self.step, self.LD, 0)
             self.graph = None
         self.n_rows = rows.shape[0]
 
@@ -348,19 +348,19 @@ class _GraphedPC:
         if self.langevin:
             for i in range(self.n_steps):
                 self._fill_scale()
-                eng.launch()
+                eng.launch(self._temb_op)
                 L.call('indm_langevin_norms', L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.norms), L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
                 L.call('indm_langevin_update', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.x_mean), L.ptr(self.norms),
                        L.ptr(self.sched[:, 5:]), self.LD, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
         elif self.ald:
             for i in range(self.n_steps):
                 self._fill_scale()
-                eng.launch()
+                eng.launch(self._temb_op)
                 L.call('indm_pc_predictor_update', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.x_mean),
                        L.ptr(self.sched[:, 8:]), self.LD, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
         if self.predictor_name != 'none':
             self._fill_scale()
-            eng.launch()
+            eng.launch(self._temb_op)
             L.call('indm_pc_predictor_update', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_p), L.ptr(self.x_mean), L.ptr(self.sched[:, 2:]),
                    self.LD, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 0)
         L.call('indm_advance_step', L.ptr(self.step))
@@ -426,14 +426,32 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
     if pred_name is None or corr_name is None:
         raise NotImplementedError(f'predictor {predictor} / corrector {corrector} are not INDM sampling components')
 
+    def _sde_key():
+        """everything of the SDE the schedule table depends on: a sampler built later for the same net with another SDE (other N,
+        beta / sigma range, VE vs VP) must not reuse a cached graph's stale `sde`"""
+        vals = tuple(float(getattr(sde, a)) for a in ('beta_0', 'beta_1', 'sigma_min', 'sigma_max') if hasattr(sde, a))
+        return (type(sde).__name__, int(sde.N), float(sde.T)) + vals
+
+    def _fresh_seed(seed):
+        """seed=None (the reference-signature callers: sampling_lib.get_samples, utils.get_loss_fns): a fresh Philox key per call
+        drawn from torch's global generator (so torch.manual_seed still controls it) with the rank mixed in — every sampling
+        round and every rank gets its own noise path, like the reference's torch.randn_like draws (sampling.py:207,290)."""
+        if seed is not None:
+            return int(seed)
+        s = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            s = (s + 0x9E3779B97F4A7C15 * (torch.distributed.get_rank() + 1)) % (2 ** 62)
+        return s
+
     def _graph(net, seed):
-        key = (shape[0], pred_name, corr_name, n_steps, probability_flow)
+        key = (shape[0], pred_name, corr_name, n_steps, probability_flow, _sde_key())
         cache = net.__dict__.setdefault('_pc_graphs', {})
         g = cache.get(key)
         if g is None:
             g = _GraphedPC(config, sde, net, shape[0], corr_name, n_steps, probability_flow, seed, predictor_name=pred_name)
             cache[key] = g
-        g.seed_dev.fill_(int(seed))
+        g.sde = sde
+        g.seed_dev.fill_(_fresh_seed(seed))
         return g
 
     def _finish(sample_before_flow, flow_model, temperature):
@@ -453,7 +471,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
         return x
 
     def pc_sampler_search(model, flow_model, temperature=1., data_mean=None, final_time=0., before_data=None, sample_dir=None, r=None,
-                          *, noise=None, seed=0, prior=None):
+                          *, noise=None, seed=None, prior=None):
         """sampling.py:458-493 (selected by sampling.pc_denoise): sde.N - 1 steps on the continuous-gap discretisation
         (explicit next_t, sde_lib.py:180-183,318-322), then one denoising step unless sampling.need_sample."""
         net = model.module if hasattr(model, 'module') else model
@@ -462,7 +480,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
             if before_data is None:
                 x0 = (sde.prior_sampling(shape, data_mean) if prior is None else prior).to(device)
                 timesteps = torch.linspace(sde.T, eps, sde.N)
-                g = _graph(net, seed)
+                g = _graph(net, seed if noise is None else (seed or 0))     # replayed noise: no generator draw
                 g.set_schedule(timesteps[:-1], [config.sampling.snr] * (sde.N - 1), next_timesteps=timesteps[1:])
                 x, x_mean = g.run(x0, sde.N - 1, noises=noise)
                 x, x_mean = x.clone(), x_mean.clone()
@@ -477,7 +495,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
                                   '(sampling.py:509-513) and cannot run; not reproduced')
 
     def pc_sampler(model, flow_model, temperature=1., data_mean=None, final_time=0., before_data=None, sample_dir=None, r=None,
-                   *, noise=None, seed=0, prior=None):
+                   *, noise=None, seed=None, prior=None):
         net = model.module if hasattr(model, 'module') else model
         net.eval()
         with torch.no_grad():
@@ -491,7 +509,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
             else:
                 snrs = [config.sampling.begin_snr + (config.sampling.end_snr - config.sampling.begin_snr) * i / num_scales
                         for i in range(num_scales)]
-            g = _graph(net, seed)
+            g = _graph(net, seed if noise is None else (seed or 0))     # replayed noise: no generator draw
             g.set_schedule(timesteps, snrs)
             if sample_dir is not None and num_scales >= 2:
                 # side effect of the reference loop at i == num_scales-2 (sampling.py:436-445): x_mean of that step

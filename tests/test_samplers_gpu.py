@@ -98,3 +98,42 @@ def test_ancestral_predictor_follows_the_reference_formulas(base):
             want = want_mean + torch.sqrt(adj ** 2 * (sigma ** 2 - adj ** 2) / sigma ** 2) * z
     assert rel_l2(got_mean.cpu().numpy(), want_mean.cpu().numpy()) < 1e-5
     assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ['em_vp', 'search_ve'])
+def test_plain_forward_after_sampling_is_conditioned_on_t(tag):
+    """The sampler's schedule-reading time embedding must not leak into ordinary `model(x, t)` calls on the same cached engine
+    (same batch size): a forward after `pc_sampler` equals the forward of a model that never sampled."""
+    cfg, model, sde = _setup(tag, 'tf32')
+    cfg2, fresh, _ = _setup(tag, 'tf32')
+    g = load_npz('samplers_tiny.npz')
+    prior = torch.from_numpy(g[f'{tag}_prior']) * (cfg.model.sigma_max if tag.endswith('ve') else 1.0)
+    fn = sampling.get_sampling_fn(cfg, sde, tuple(prior.shape), lambda v: v, cfg.sampling.truncation_time)
+    fn(model, None, prior=prior)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(tuple(prior.shape), generator=gen).cuda()
+    t = (torch.rand(prior.shape[0], generator=gen) * 0.8 + 0.1).cuda()
+    with torch.no_grad():
+        a = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)(x, t).cpu().numpy()
+        b = mutils.get_score_fn(cfg2, sde, fresh, train=False, continuous=True)(x, t).cpu().numpy()
+    assert np.isfinite(a).all()
+    assert rel_l2(a, b) < 1e-6
+
+
+def test_unseeded_sampler_calls_use_fresh_noise_and_manual_seed_controls_it():
+    """Reference-signature callers pass no seed (sampling_lib.get_samples): every call must draw its own noise path, yet
+    torch.manual_seed must make a run reproducible; an explicit seed= pins the path."""
+    cfg, model, sde = _setup('em_vp', 'bf16')
+    shape = (2, 3, 16, 16)
+    fn = sampling.get_sampling_fn(cfg, sde, shape, lambda v: v, cfg.sampling.truncation_time)
+    prior = torch.randn(shape, generator=torch.Generator().manual_seed(1))
+    torch.manual_seed(7)
+    a1 = fn(model, None, prior=prior)[0].cpu().numpy()
+    a2 = fn(model, None, prior=prior)[0].cpu().numpy()
+    torch.manual_seed(7)
+    b1 = fn(model, None, prior=prior)[0].cpu().numpy()
+    assert rel_l2(a2, a1) > 1e-3                  # two rounds: different Brownian paths
+    assert np.array_equal(a1, b1)                 # same global seed: same path
+    s1 = fn(model, None, prior=prior, seed=5)[0].cpu().numpy()
+    s2 = fn(model, None, prior=prior, seed=5)[0].cpu().numpy()
+    assert np.array_equal(s1, s2)

@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from .. import precision
 
 COEFF = 0.98
 
@@ -76,6 +77,10 @@ class _IResBlock(nn.Module):
         super().__init__()
         self.geom_p = nn.Parameter(torch.tensor(np.log(0.5) - np.log(1. - 0.5), dtype=torch.float32))
         self.lamb = nn.Parameter(torch.tensor(2.))
+        # no loss term reaches these two (iresblock.py:36-42: learn_p is off, lamb only parameterises the Poisson draw): the
+        # reference's AdamW finds .grad None and skips them — no weight decay either (indm_b200/losses.py:_stepped)
+        self.geom_p._indm_no_grad = True
+        self.lamb._indm_no_grad = True
         self.register_buffer('last_n_samples', torch.zeros(1))
         self.register_buffer('last_firmom', torch.zeros(1))
         self.register_buffer('last_secmom', torch.zeros(1))
@@ -240,7 +245,7 @@ class WolfCore(nn.Module):
                                                              for _ in range(pr['num_steps'])])
         self.latent_dim = d['dim']
         self._engines = {}
-        self.compute_mode = 'bf16'
+        self.compute_mode = 'auto'    # indm_b200/precision.py policy; 'bf16' / 'tf32' force one arithmetic
         self._draws = 0               # number of prior draws made with the in-kernel generator (advances the Philox stream)
 
     @classmethod
@@ -260,8 +265,10 @@ class WolfCore(nn.Module):
                     out.append((s, b, m))
         return out
 
-    def engine(self, batch, mode=None):
-        mode = mode or self.compute_mode
+    def engine(self, batch, mode=None, leg=None):
+        if leg is None:
+            leg = 'training' if self.training else 'eval'
+        mode = precision.resolve('flow', mode or self.compute_mode, leg)
         dev = next(self.parameters()).device
         key = (int(batch), mode, str(dev))
         e = self._engines.get(key)
@@ -280,7 +287,7 @@ class WolfCore(nn.Module):
         reference uses, iresblock.py:306)."""
         if not data.is_cuda:
             raise RuntimeError('indm_b200 WolfCore needs CUDA tensors: there is no CPU / PyTorch fallback path')
-        eng = self.engine(data.shape[0])
+        eng = self.engine(data.shape[0], leg='reverse' if reverse else None)
         if reverse:
             if eps is None and h is None:
                 self._draws += 1      # a fresh h ~ prior per call, like discriminator.sample_from_prior (wolf.py:83)

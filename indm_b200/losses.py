@@ -23,6 +23,15 @@ from .models import utils as mutils
 
 
 # ------------------------------------------------------------------------------------------------ optimizer
+def _stepped(p):
+    """True for the parameters torch.optim.AdamW would update: trainable AND reached by the loss.  torch skips a parameter whose
+    `.grad` is None entirely — no moment update and NO WEIGHT DECAY (torch/optim/adamw.py) — which is what happens to the
+    iResBlocks' `lamb` / `geom_p` in the reference (nn.Parameters no loss term touches, iresblock.py:36-42).  With flat storage
+    every slot has a gradient, so those parameters are marked `_indm_no_grad` by their module: they stay inside the flat buffers
+    (the parameters must tile one contiguous buffer for the fused EMA pass) and `FusedAdamW.step` restores their values."""
+    return p.requires_grad and not getattr(p, '_indm_no_grad', False)
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (decoupled weight decay, bias correction, amsgrad off) as ONE kernel over flat storage,
     with `clip_grad_norm_` folded in (the clip coefficient is computed on the device from the global gradient norm: no host
@@ -46,14 +55,18 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self._sumsq = torch.zeros((1,), dtype=torch.float32, device=dev)
-        off = 0
+        off, skip = 0, []
         with torch.no_grad():
             for p in ps:
                 n = p.numel()
                 self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + n].view_as(p)
                 p.grad = self.flat_g[off:off + n].view_as(p)
+                if not _stepped(p):
+                    skip += list(range(off, off + n))
                 off += n
+        # flat offsets of the parameters torch.optim.AdamW would skip (see _stepped): their values are carried across the kernel
+        self._skip_idx = torch.tensor(skip, dtype=torch.int64, device=dev) if skip else None
         self.steps = 0
         self.max_norm = -1.0          # set by optimize_fn (losses.py:58-59); < 0 disables clipping
         L.param_epoch += 1
@@ -74,9 +87,12 @@ class FusedAdamW(torch.optim.Optimizer):
             L.call('indm_sumsq_f32', L.ptr(self.flat_g), self.flat_g.numel(), L.ptr(self._sumsq))
             sumsq = self._sumsq
         b1, b2 = g['betas']
+        keep = self.flat_p.index_select(0, self._skip_idx) if self._skip_idx is not None else None
         L.call('indm_adamw_ema_f32', L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), None,
                self.flat_p.numel(), float(g['lr']), float(b1), float(b2), float(g['eps']), float(g['weight_decay']), self.steps,
                L.ptr(sumsq), float(self.max_norm), 0.0)
+        if keep is not None:          # zero gradient, zero moments: the kernel only applied the weight decay; undo it
+            self.flat_p.index_copy_(0, self._skip_idx, keep)
         L.param_epoch += 1            # engines repack their operand copies of the weights on next use
 
     def state_dict(self):
@@ -98,7 +114,7 @@ def pack_adamw_state(params, steps, exp_avg_flat, exp_avg_sq_flat, param_groups)
         if not p.requires_grad:
             continue
         n = p.numel()
-        if steps > 0:
+        if steps > 0 and _stepped(p):
             state[i] = dict(step=torch.tensor(float(steps)), exp_avg=exp_avg_flat[off:off + n].view_as(p),
                             exp_avg_sq=exp_avg_sq_flat[off:off + n].view_as(p))
         off += n
@@ -133,7 +149,7 @@ def unpack_adamw_state(sd, params, exp_avg_flat, exp_avg_sq_flat, param_groups):
             if not p.requires_grad:       # frozen: holds an index, no state (torch.optim.AdamW never steps it)
                 continue
             n = p.numel()
-            st = sd['state'].get(i)
+            st = sd['state'].get(i) if _stepped(p) else None
             if st is None:
                 exp_avg_flat[off:off + n].zero_()
                 exp_avg_sq_flat[off:off + n].zero_()

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import layers, layerspp, utils
+from .. import precision
 from .engine import ScoreEngine
 
 
@@ -123,11 +124,11 @@ class NCSNpp(nn.Module):
         modules.append(layers.conv3x3(in_ch, channels, init_scale=init_scale))
         self.all_modules = nn.ModuleList(modules)
         self._engines = {}
-        self.compute_mode = 'bf16'   # 'bf16' (production) or 'tf32' (validation mode)
+        self.compute_mode = 'auto'   # 'auto' (indm_b200/precision.py policy), or 'bf16' / 'tf32' to force one arithmetic
 
     # ---------------------------------------------------------------------------------------------------------------
     def engine(self, batch, mode=None):
-        mode = mode or self.compute_mode
+        mode = precision.resolve('score', mode or self.compute_mode, 'training' if self.training else 'sampling')
         dev = next(self.parameters()).device
         key = (int(batch), mode, str(dev))
         eng = self._engines.get(key)

@@ -464,3 +464,36 @@ def wolf_train_forward(config, P, x, eps_post, ns, varepss):
     if config.flow.squeeze:
         z = unsqueeze2(z)
     return z, -logpx - kl, h, kl
+
+
+# ------------------------------------------------------------------------------------------------ replayed draws (fixtures)
+def replay_draws(config, seed, B, training=False):
+    """Every random draw one wolf forward consumes (flow_model.py:53-67 -> wolf.py:90-130), regenerated from one numpy PCG64
+    seed in a fixed order, so the full-size fixtures (tests/golden/make_golden.py:make_fullflow / make_fulljoint /
+    make_fulllikelihood) only need to store the seed: x ~ U(-1, 1) image batch, eps_post (reparameterisation noise,
+    gaussian.py:67-76), ns (Poisson(2) series lengths, iresblock.py:306), varepss (one Gaussian probe per iResBlock,
+    iresblock.py:107), z_rev / eps_rev (latent and prior noise of a reverse pass), Gz / cl (cotangents of a training backward)."""
+    rng = np.random.default_rng(seed)
+    S, C = config.data.image_size, config.data.num_channels
+    layout = block_layout(config)
+    c0, h0, w0 = flow_input_shape(config)
+    d = dict(x=rng.uniform(-1, 1, size=(B, C, S, S)).astype(np.float32),
+             eps_post=rng.standard_normal((B, 64)).astype(np.float32),
+             ns=rng.poisson(2.0, size=len(layout)).astype(np.int64))
+    d['varepss'] = [rng.standard_normal((B, c, h0 >> s, w0 >> s)).astype(np.float32) for (s, b, c, first) in layout]
+    d['z_rev'] = rng.standard_normal((B, C, S, S)).astype(np.float32)
+    d['eps_rev'] = rng.standard_normal((B, 64)).astype(np.float32)
+    d['Gz'] = rng.standard_normal((B, C, S, S)).astype(np.float32)
+    d['cl'] = rng.uniform(0.5, 1.5, size=(B,)).astype(np.float32)
+    return d
+
+
+def grad_digest(name, g, seed=97, n_sub=256):
+    """What a full-size fixture keeps of one parameter gradient (13 M flow + 63 M score parameters do not fit a committed file):
+    its L2 norm, its projection on a seeded Gaussian direction (every element takes part) and a strided sub-sample."""
+    import zlib
+    g = np.ascontiguousarray(g, dtype=np.float32).reshape(-1)
+    r = np.random.default_rng([seed, zlib.crc32(name.encode())]).standard_normal(g.size).astype(np.float32)
+    step = max(1, g.size // n_sub)
+    return np.float64(np.linalg.norm(g.astype(np.float64))), np.float64(np.dot(g.astype(np.float64), r.astype(np.float64)) / np.sqrt(g.size)), \
+        g[::step][:n_sub].copy()

@@ -708,7 +708,236 @@ def make_flow():
               'zf rms', float(zf.pow(2).mean().sqrt()))
 
 
+# ------------------------------------------------------------------------------------------------ full-size fixtures (round 2)
+FULL = {'cifar': ('configs/vp/CIFAR10/indm_nll.py', 'vp/CIFAR10/indm_nll'), 'celeba': ('configs/vp/CELEBA/indm_nll.py', 'vp/CELEBA/indm_nll')}
+
+
+def _full_flow(tag, seed=21):
+    fm = rl.load('flow_models.flow_model')
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    path, pname = FULL[tag]
+    cfg = rl.get_config(path)
+    with rl.reference_cwd():
+        flow = fm.create_flow_model(cfg)
+    pcfg = pconfigs.get_config(pname)
+    flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, seed).items()})
+    return fm, cfg, pcfg, flow
+
+
+def make_fullflow():
+    """The wolf flow AT THE BENCHED SIZE — flow.nblocks = '16-16', flow.intermediate_dim = 512 (configs/ve/CIFAR10/indm.py:68-69;
+    CIFAR 3x32x32 and CelebA 3x64x64 squeezed to 12x32x32) — through the live reference's flow_forward, batch 2, every random draw
+    replayed from ONE seed (oracle.flow.replay_draws): (1) the reverse pass (prior sample of h + fixed-point inverse of all 32
+    blocks), (2) the eval-mode forward with the (20 + n)-term power-series log-det and the KL, (3) the training-mode forward
+    (batch-statistics encoder, Neumann series) and the gradient of EVERY flow parameter for fixed cotangents — kept as
+    norm / seeded projection / sub-sample per tensor (oracle.flow.grad_digest)."""
+    import time
+    from oracle import flow as oflow
+    for tag in ('cifar', 'celeba'):
+        fm, cfg, pcfg, flow = _full_flow(tag)
+        import flow_models.wolf.flows.resflow.layers.iresblock as irb
+        B, draw_seed = 2, 141
+        d = oflow.replay_draws(pcfg, draw_seed, B)
+        out = dict(seed=np.asarray(21), draw_seed=np.asarray(draw_seed), B=np.asarray(B))
+        real = (torch.randn, torch.randn_like, irb.poisson_sample)
+        # (1) reverse
+        flow.eval()
+        torch.randn = lambda *a, **k: torch.from_numpy(d['eps_rev'])
+        t0 = time.time()
+        try:
+            with torch.no_grad():
+                x_rev, _ = fm.flow_forward(cfg, flow, torch.from_numpy(d['z_rev']), log_det=None, reverse=True)
+        finally:
+            torch.randn = real[0]
+        out['x_rev'] = x_rev.numpy()
+        print('fullflow', tag, 'reverse', round(time.time() - t0, 1), 's  max|x - z|', float((x_rev - torch.from_numpy(d['z_rev'])).abs().max()))
+        # the posterior sample and its KL are captured too, so a log-det error and a KL error can be told apart
+        cap = {}
+        disc = flow.module.discriminator
+        real_skl = disc.sampling_and_KL
+
+        def skl(xx, y=None, nsamples=1):
+            h_, kl_ = real_skl(xx, y=y, nsamples=nsamples)
+            cap['h'], cap['kl'] = h_.detach().clone(), kl_.detach().clone()
+            return h_, kl_
+        disc.sampling_and_KL = skl
+        # (2) eval-mode forward with log-det and KL
+        q_eps, q_n = [torch.from_numpy(v) for v in d['varepss']], list(d['ns'])
+        torch.randn = lambda *a, **k: torch.from_numpy(d['eps_post']).reshape(B, 1, 64)
+        torch.randn_like = lambda t, **k: q_eps.pop(0)
+        irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+        t0 = time.time()
+        try:
+            z, ldkl = fm.flow_forward(cfg, flow, torch.from_numpy(d['x']), reverse=False)
+        finally:
+            torch.randn, torch.randn_like, irb.poisson_sample = real
+        assert not q_eps and not q_n
+        out.update(z_eval=z.detach().numpy(), ldkl_eval=ldkl.detach().numpy(), h_eval=cap['h'].numpy().reshape(B, 64),
+                   kl_eval=cap['kl'].numpy().reshape(B))
+        print('fullflow', tag, 'eval forward', round(time.time() - t0, 1), 's  ldkl', ldkl.detach().numpy())
+        # (3) training-mode forward + backward
+        flow.train()
+        q_eps, q_n = [torch.from_numpy(v) for v in d['varepss']], list(d['ns'])
+        torch.randn = lambda *a, **k: torch.from_numpy(d['eps_post']).reshape(B, 1, 64)
+        torch.randn_like = lambda t, **k: q_eps.pop(0)
+        irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+        t0 = time.time()
+        try:
+            z, ldkl = fm.flow_forward(cfg, flow, torch.from_numpy(d['x']), reverse=False)
+            loss = (z * torch.from_numpy(d['Gz'])).sum() + (ldkl * torch.from_numpy(d['cl'])).sum()
+            loss.backward()
+        finally:
+            torch.randn, torch.randn_like, irb.poisson_sample = real
+        assert not q_eps and not q_n
+        out.update(z_train=z.detach().numpy(), ldkl_train=ldkl.detach().numpy(), h_train=cap['h'].numpy().reshape(B, 64),
+                   kl_train=cap['kl'].numpy().reshape(B))
+        disc.sampling_and_KL = real_skl
+        names, norms, projs = [], [], []
+        for k, p_ in flow.module.named_parameters():
+            if p_.grad is None:
+                continue
+            n_, pr_, sub_ = oflow.grad_digest(k, p_.grad.numpy())
+            names.append(k); norms.append(n_); projs.append(pr_)
+            out['gsub.' + k] = sub_
+        out.update(grad_names=np.array(names), grad_norms=np.array(norms), grad_projs=np.array(projs))
+        print('fullflow', tag, 'train fwd+bwd', round(time.time() - t0, 1), 's  ldkl', ldkl.detach().numpy(), 'grads', len(names),
+              'total norm', float(np.sqrt((np.array(norms) ** 2).sum())))
+        np.savez_compressed(os.path.join(HERE, f'flowfull_{tag}.npz'), **out)
+
+
+def make_fulljoint():
+    """One JOINT optimisation step (losses.get_step_fn -> flow_step_fn_nll, losses.py:258-320) of the live reference at the
+    BENCHED sizes: configs/vp/CIFAR10/indm_nll.py with the full DDPM++ (nres = 4, nf = 128) and the full wolf flow (16-16 / 512),
+    batch 2, dropout 0 (no mask to replay), every random draw replayed: the four loss vectors, and for EVERY parameter of both
+    networks the applied update (p_after - p_before) as norm / projection / sub-sample."""
+    import time
+    mutils, sde_lib, losses, ema_mod, fm = rl.load('models.utils', 'sde_lib', 'losses', 'models.ema', 'flow_models.flow_model')
+    import flow_models.wolf.flows.resflow.layers.iresblock as irb
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    path, pname = FULL['cifar']
+    cfg = rl.get_config(path)
+    cfg.model.dropout = 0.0
+    model, _ = ref_model(cfg, seed=11)
+    model.train()
+    with rl.reference_cwd():
+        flow = fm.create_flow_model(cfg)
+    pcfg = pconfigs.get_config(pname)
+    flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, 21).items()})
+    sde = sde_lib.get_sde(cfg)
+    B, draw_seed = 2, 171
+    d = oflow.replay_draws(pcfg, draw_seed, B)
+    rng = np.random.default_rng(draw_seed + 1)
+    S = cfg.data.image_size
+    z = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+    logp_noise = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+    u = rng.uniform(size=(B,)).astype(np.float32)
+    q_like = [torch.from_numpy(v) for v in d['varepss']] + [torch.from_numpy(z), torch.from_numpy(logp_noise)]
+    q_n = list(d['ns'])
+    opt = losses.get_optimizer(cfg, model.parameters())
+    ema = ema_mod.ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    state = dict(optimizer=opt, model=model, ema=ema, step=0)
+    fopt = losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr)
+    fema = ema_mod.ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate)
+    flow_state = dict(optimizer=fopt, model=flow, ema=fema, step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    before = {'s::' + n: p.detach().clone() for n, p in model.named_parameters()}
+    before.update({'f::' + n: p.detach().clone() for n, p in flow.named_parameters()})
+    real = (torch.randn, torch.randn_like, torch.rand, irb.poisson_sample)
+    torch.randn = lambda *a, **k: torch.from_numpy(d['eps_post']).reshape(B, 1, 64)
+    torch.randn_like = lambda t, **k: q_like.pop(0)
+    torch.rand = lambda *a, **k: torch.from_numpy(u)
+    irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+    t0 = time.time()
+    try:
+        res = step_fn(state, flow_state, torch.from_numpy(d['x']))
+    finally:
+        torch.randn, torch.randn_like, torch.rand, irb.poisson_sample = real
+    assert not q_like and not q_n, (len(q_like), q_n)
+    out = dict(draw_seed=np.asarray(draw_seed), B=np.asarray(B), z=z, logp_noise=logp_noise, u=u, seed_score=np.asarray(11), seed_flow=np.asarray(21),
+               losses=res[0].numpy(), losses_score=res[1].numpy(), losses_flow=res[2].numpy(), losses_logp=res[3].numpy())
+    names, norms, projs = [], [], []
+    for tag, net in (('s', model), ('f', flow)):
+        for n, p in net.named_parameters():
+            if not p.requires_grad:
+                continue
+            key = f'{tag}::{n}'
+            n_, pr_, sub_ = oflow.grad_digest(key, (p.detach() - before[key]).numpy())
+            names.append(key); norms.append(n_); projs.append(pr_)
+            out['usub.' + key] = sub_
+    out.update(names=np.array(names), upd_norms=np.array(norms), upd_projs=np.array(projs))
+    np.savez_compressed(os.path.join(HERE, 'jointfull_vp.npz'), **out)
+    print('fulljoint', round(time.time() - t0, 1), 's losses', res[0].numpy(), 'score', res[1].numpy(), 'flow', res[2].numpy(), 'logp', res[3].numpy(),
+          'tensors', len(names))
+
+
+def make_fulllikelihood():
+    """likelihood.get_likelihood_fn (PF-ODE NLL, RK45 at the reference's default rtol = atol = 1e-5) and likelihood.get_elbo_fn of
+    the live reference AT THE BENCHED SIZES (configs/vp/CIFAR10/indm_nll.py: full DDPM++ + full wolf flow), batch 2, every random
+    draw replayed."""
+    import time
+    mutils, sde_lib, likelihood, fm = rl.load('models.utils', 'sde_lib', 'likelihood', 'flow_models.flow_model')
+    import flow_models.wolf.flows.resflow.layers.iresblock as irb
+    from oracle import flow as oflow
+    from indm_b200 import configs as pconfigs
+    path, pname = FULL['cifar']
+    cfg = rl.get_config(path)
+    model, _ = ref_model(cfg, seed=11)
+    with rl.reference_cwd():
+        flow = fm.create_flow_model(cfg)
+    pcfg = pconfigs.get_config(pname)
+    flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, 21).items()})
+    flow.eval()
+    sde = sde_lib.get_sde(cfg)
+    B, S = 2, 32
+    inverse_scaler = lambda v: (v + 1.) / 2.
+    out = dict(seed_score=np.asarray(11), seed_flow=np.asarray(21), B=np.asarray(B))
+    for which, draw_seed in (('nll', 151), ('elbo', 152)):
+        d = oflow.replay_draws(pcfg, draw_seed, B)
+        rng = np.random.default_rng(draw_seed + 1000)
+        rad = (rng.integers(0, 2, size=(B, 3, S, S)).astype(np.float32))         # randint_like result in {0, 1}
+        gauss = [rng.standard_normal((B, 3, S, S)).astype(np.float32) for _ in range(4)]
+        u = rng.uniform(size=(B,)).astype(np.float32)
+        q_like = [torch.from_numpy(v) for v in d['varepss']] + [torch.from_numpy(v) for v in gauss]
+        q_n = list(d['ns'])
+        real = (torch.randn, torch.randn_like, torch.randint_like, torch.rand, irb.poisson_sample)
+        torch.randn = lambda *a, **k: torch.from_numpy(d['eps_post']).reshape(B, 1, 64)
+        torch.randn_like = lambda t, **k: q_like.pop(0)
+        torch.randint_like = lambda t, **k: torch.from_numpy(rad)
+        torch.rand = lambda *a, **k: torch.from_numpy(u)
+        irb.poisson_sample = lambda lamb, m: np.array([q_n.pop(0)])
+        t0 = time.time()
+        try:
+            if which == 'nll':
+                fn = likelihood.get_likelihood_fn(cfg, sde, inverse_scaler)
+                bpd, z, nfe = fn(model, flow, torch.from_numpy(d['x']), eps_bpd=1e-5)
+                out.update(nll_bpd=bpd.detach().numpy(), nll_z=z.detach().numpy(), nll_nfe=np.asarray(nfe))
+                used = 3             # perturbation z, residual x2
+            else:
+                fn = likelihood.get_elbo_fn(cfg, sde, inverse_scaler)
+                a, b = fn(model, flow, torch.from_numpy(d['x']))
+                out.update(elbo_bpd=a.detach().numpy(), elbo_bpd_residual=b.detach().numpy())
+                used = 4             # z, lp_z, residual x2
+        finally:
+            torch.randn, torch.randn_like, torch.randint_like, torch.rand, irb.poisson_sample = real
+        assert len(q_like) == 4 - used and not q_n, (len(q_like), q_n)
+        out.update({f'{which}_draw_seed': np.asarray(draw_seed), f'{which}_rad': rad.astype(np.int8), f'{which}_u': u})
+        print('fulllikelihood', which, round(time.time() - t0, 1), 's', {k: v for k, v in out.items() if k.endswith('bpd') or k.endswith('nfe') or k.endswith('residual')})
+    if os.environ.get('INDM_GOLDEN_SENSITIVITY'):
+        # noise floor of the fixture: the same reference run with another intra-op thread count (fp32 summation order in the
+        # convolutions changes at the 1e-7 level) — how far the reference's OWN NLL moves says how tight a parity bound can be
+        old = dict(np.load(os.path.join(HERE, 'likelihood_full_vp.npz')))
+        print('sensitivity: threads', torch.get_num_threads(), {k: (out[k] - old[k]).tolist() for k in ('nll_bpd', 'elbo_bpd', 'elbo_bpd_residual')},
+              'nfe', int(out['nll_nfe']), 'vs', int(old['nll_nfe']),
+              'latent rel-L2', float(np.linalg.norm(out['nll_z'] - old['nll_z']) / np.linalg.norm(old['nll_z'])))
+        return
+    np.savez_compressed(os.path.join(HERE, 'likelihood_full_vp.npz'), **out)
+
+
 if __name__ == '__main__':
+    if os.environ.get('INDM_GOLDEN_THREADS'):
+        torch.set_num_threads(int(os.environ['INDM_GOLDEN_THREADS']))
     which = sys.argv[1:] or ['configs', 'ops', 'sde', 'ncsnpp', 'pc', 'flow', 'vjp', 'flowfwd', 'likelihood', 'train', 'samplers', 'flowtrain', 'jointtrain']
     for w in which:
         globals()['make_' + w]()

@@ -1,0 +1,348 @@
+"""GPU: parity AT THE BENCHED SIZES AND IN THE BENCHED PRECISION.  The wolf flow with flow.nblocks = '16-16' and
+flow.intermediate_dim = 512 (CIFAR 3x32x32, CelebA 3x64x64 squeezed), the full DDPM++ (nres = 4, nf = 128), against fixtures the
+live reference produced at exactly those sizes (tests/golden/make_golden.py: make_fullflow / make_fulljoint / make_fulllikelihood;
+batch 2, every random draw regenerated from one seed by oracle.flow.replay_draws).
+
+mode 'auto' = the default precision policy (indm_b200/precision.py) = what bench.py times; it is held to BASELINE.json's
+north_star numbers: flow log-det 1e-3 relative, inverse round trip 1e-4 max-abs, NLL / NELBO 0.01 bpd.  mode 'bf16' forces BF16
+everywhere and is reported beside it with the bounds BF16 operands allow.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import load_npz, rel_l2  # noqa: E402
+from indm_b200 import configs, precision  # noqa: E402
+from indm_b200.flow_models import flow_model as fm  # noqa: E402
+from oracle import flow as oflow, ncsnpp as oncsnpp  # noqa: E402
+
+FULL = {'cifar': 'vp/CIFAR10/indm_nll', 'celeba': 'vp/CELEBA/indm_nll'}
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _flow(tag, mode, seed=21):
+    cfg = configs.get_config(FULL[tag])
+    cfg.device = torch.device('cuda:0')
+    flow = fm.create_flow_model(cfg)
+    flow.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oflow.synth_params(cfg, seed).items()})
+    flow.module.compute_mode = mode
+    return cfg, flow
+
+
+@pytest.mark.parametrize("mode,tol", [('auto', 2e-4), ('bf16', 2e-2)])
+@pytest.mark.parametrize("tag", ['cifar', 'celeba'])
+def test_fullsize_flow_reverse_matches_reference(tag, mode, tol):
+    """flow_forward(reverse=True) at 16-16 / 512: prior sample of h, fixed-point inverse of all 32 iResBlocks (the flow leg of every
+    sampler call)."""
+    g = load_npz(f'flowfull_{tag}.npz')
+    cfg, flow = _flow(tag, mode, int(g['seed']))
+    flow.eval()
+    d = oflow.replay_draws(cfg, int(g['draw_seed']), int(g['B']))
+    x, _ = fm.flow_forward(cfg, flow, cu(d['z_rev']), log_det=None, reverse=True, eps=cu(d['eps_rev']))
+    torch.cuda.synchronize()
+    err = float(np.abs(x.cpu().numpy() - g['x_rev']).max())
+    eng = flow.module.engine(int(g['B']), leg='reverse')
+    print(f'{tag} {mode} ({eng.mode}): reverse max-abs err {err:.3e}; iterations {sum(eng.iterations)} over {len(eng.iterations)} blocks')
+    assert err < tol
+
+
+@pytest.mark.parametrize("mode,rt_tol", [('auto', 1e-4), ('bf16', 2e-2)])
+@pytest.mark.parametrize("tag", ['cifar', 'celeba'])
+def test_fullsize_flow_round_trip(tag, mode, rt_tol):
+    """x -> fwdpass(x, h) -> bwdpass(., h) with the same h and a tight stop rule (SURVEY §8c caveats i / ii):
+    north_star's inverse round trip within 1e-4 max-abs, on all 32 blocks at idim 512."""
+    g = load_npz(f'flowfull_{tag}.npz')
+    cfg, flow = _flow(tag, mode, int(g['seed']))
+    flow.eval()
+    core = flow.module
+    d = oflow.replay_draws(cfg, int(g['draw_seed']), int(g['B']))
+    x = cu(d['x'])
+    xf = fm.squeeze2(x).contiguous() if cfg.flow.squeeze else x
+    eng = core.engine(x.shape[0], leg='reverse')
+    eng._ensure()
+    h = eng.prior_flow(cu(d['eps_rev']), 'backward')
+    zf = core(xf, reverse=False, eval_logdet=False, h=h)
+    back = core(zf, reverse=True, h=h, atol=1e-12, rtol=1e-12)
+    torch.cuda.synchronize()
+    rt = float((back - xf).abs().max())
+    print(f'{tag} {mode}: round trip max-abs {rt:.3e}; |z - x| max {float((zf - xf).abs().max()):.3f}')
+    assert rt < rt_tol
+
+
+@pytest.mark.parametrize("mode,tol_z,tol_ld", [('auto', 1e-4, 1e-3), ('bf16', 2e-2, 5e-2)])
+@pytest.mark.parametrize("tag", ['cifar', 'celeba'])
+def test_fullsize_flow_eval_logdet_matches_reference(tag, mode, tol_z, tol_ld):
+    """flow_forward(reverse=False) in eval mode at 16-16 / 512: posterior encoder, KL, and the (20 + n)-term log-det series of
+    32 blocks (~ 700 VJP chains).  north_star: log-det within 1e-3 relative."""
+    g = load_npz(f'flowfull_{tag}.npz')
+    cfg, flow = _flow(tag, mode, int(g['seed']))
+    flow.eval()
+    d = oflow.replay_draws(cfg, int(g['draw_seed']), int(g['B']))
+    z, ldkl = fm.flow_forward(cfg, flow, cu(d['x']), reverse=False, eps=cu(d['eps_post']), vareps=[cu(v) for v in d['varepss']],
+                              n_terms=d['ns'])
+    torch.cuda.synchronize()
+    e_z = float(np.abs(z.cpu().numpy() - g['z_eval']).max())
+    e_ld = float(np.abs(ldkl.cpu().numpy() - g['ldkl_eval']).max() / np.abs(g['ldkl_eval']).max())
+    print(f'{tag} {mode}: z max-abs err {e_z:.3e}; (logdet - KL) rel err {e_ld:.3e}; ref {g["ldkl_eval"]} got {ldkl.cpu().numpy()}')
+    assert e_z < tol_z and e_ld < tol_ld
+
+
+def _check_digest(names, norms, projs, subs, get, tol_norm, tol_sub, label, floor_fn=None):
+    worst_n = worst_p = worst_s = 0.0
+    total_ref = float(np.sqrt((norms ** 2).sum()))
+    for k, n_ref, p_ref in zip(names, norms, projs):
+        k = str(k)
+        n_, p_, s_ = oflow.grad_digest(k, get(k))
+        # a tensor whose gradient is far below the whole gradient's scale is compared on that scale
+        floor = 1e-4 * total_ref / np.sqrt(len(names)) if floor_fn is None else floor_fn(k, get(k).size)
+        e_n = abs(n_ - n_ref) / max(n_ref, floor)
+        e_p = abs(p_ - p_ref) / max(n_ref, floor)          # |<g, r>| / sqrt(n) has the scale of ||g||
+        e_s = float(np.linalg.norm(s_ - subs[k]) / max(np.linalg.norm(subs[k]), floor * np.sqrt(s_.size / max(get(k).size, 1))))
+        if max(e_n, e_p) > tol_norm or e_s > tol_sub:
+            print(f'   {label} {k}: norm err {e_n:.2e}, projection err {e_p:.2e}, sub-sample rel-L2 {e_s:.2e} (norm {n_ref:.3e})')
+        worst_n, worst_p, worst_s = max(worst_n, e_n), max(worst_p, e_p), max(worst_s, e_s)
+    return worst_n, worst_p, worst_s
+
+
+@pytest.mark.parametrize("mode,tol_z,tol_ld,tol_g", [('auto', 5e-3, 5e-2, 8e-2), ('tf32', 1e-4, 1e-3, 5e-3), ('bf16', 5e-3, 5e-2, 8e-2)])
+@pytest.mark.parametrize("tag", ['cifar', 'celeba'])
+def test_fullsize_flow_training_forward_and_gradients(tag, mode, tol_z, tol_ld, tol_g):
+    """Training-mode forward (batch-statistics encoder, Neumann series) and the gradient of EVERY flow parameter at 16-16 / 512
+    against the live reference's autograd: L = <z, Gz> + <logdet - KL, cl>."""
+    g = load_npz(f'flowfull_{tag}.npz')
+    cfg, flow = _flow(tag, mode, int(g['seed']))
+    flow.train()
+    core = flow.module
+    d = oflow.replay_draws(cfg, int(g['draw_seed']), int(g['B']))
+    for p in core.parameters():
+        p.grad = None
+    z, ldkl = fm.flow_forward(cfg, flow, cu(d['x']), reverse=False, eps=cu(d['eps_post']), vareps=[cu(v) for v in d['varepss']],
+                              n_terms=d['ns'])
+    ((z * cu(d['Gz'])).sum() + (ldkl * cu(d['cl'])).sum()).backward()
+    torch.cuda.synchronize()
+    e_z = float(np.abs(z.detach().cpu().numpy() - g['z_train']).max())
+    e_ld = float(np.abs(ldkl.detach().cpu().numpy() - g['ldkl_train']).max() / np.abs(g['ldkl_train']).max())
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in core.named_parameters() if p.grad is not None}
+    names = [str(k) for k in g['grad_names']]
+    missing = [k for k in names if k not in grads]
+    assert not missing, missing[:4]
+    subs = {k: g['gsub.' + k] for k in names}
+    wn, wp, ws = _check_digest(names, g['grad_norms'], g['grad_projs'], subs, lambda k: grads[k], tol_g, 4 * tol_g, 'grad')
+    eng = core.engine(int(g['B']), leg='training')
+    # which term carries the error: the posterior sample h (encoder), the KL, or the blocks' log-det series
+    h_got, ld_got = eng._train_saved[0].cpu().numpy(), -eng._bufs['logpx'].cpu().numpy()
+    ld_ref = g['ldkl_train'] + g['kl_train']
+    kl_got = ld_got - ldkl.detach().cpu().numpy()
+    print(f'   h rel-L2 {rel_l2(h_got, g["h_train"]):.2e}; KL abs err {np.abs(kl_got - g["kl_train"]).max():.2e} (KL {g["kl_train"]}); '
+          f'log-det abs err {np.abs(ld_got - ld_ref).max():.2e} (log-det {ld_ref})')
+    print(f'{tag} {mode} ({eng.mode}): z max-abs err {e_z:.3e}; training (logdet - KL) rel err {e_ld:.3e}; {len(names)} gradients: worst norm err '
+          f'{wn:.2e}, worst projection err {wp:.2e}, worst sub-sample rel-L2 {ws:.2e}')
+    assert e_z < tol_z and e_ld < tol_ld
+    assert wn < tol_g and wp < tol_g and ws < 4 * tol_g
+
+
+def _joint_models(mode, dropout=None):
+    from indm_b200 import sde_lib
+    from indm_b200.models import utils as mutils
+    cfg = configs.get_config('vp/CIFAR10/indm_nll')
+    if dropout is not None:
+        cfg.model.dropout = dropout
+    cfg.device = torch.device('cuda:0')
+    model = mutils.create_model(cfg)
+    model.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(cfg, 11).items()})
+    flow = fm.create_flow_model(cfg)
+    flow.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oflow.synth_params(cfg, 21).items()})
+    model.module.compute_mode = flow.module.compute_mode = mode
+    return cfg, model, flow, sde_lib.get_sde(cfg)
+
+
+@pytest.mark.parametrize("mode,tol,upd_tol", [('auto', 5e-2, 0.5), ('tf32', 2e-3, 6e-2)])
+def test_fullsize_joint_step_matches_reference(mode, tol, upd_tol):
+    """flow_step_fn_nll (losses.py:258-320) with the full DDPM++ and the full wolf flow, batch 2: the four loss vectors and the
+    applied update of EVERY parameter of both networks (1006 tensors; the first AdamW step is ~ lr * sign(grad), so the update is
+    compared as a vector: norm, seeded projection, sub-sample)."""
+    from indm_b200 import losses
+    from indm_b200.models.ema import ExponentialMovingAverage
+    g = load_npz('jointfull_vp.npz')
+    cfg, model, flow, sde = _joint_models(mode, dropout=0.0)
+    model.train()
+    d = oflow.replay_draws(cfg, int(g['draw_seed']), int(g['B']))
+    opt = losses.get_optimizer(cfg, model.parameters())
+    state = dict(optimizer=opt, model=model, ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+    fopt = losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr)
+    flow_state = dict(optimizer=fopt, model=flow, ema=ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate), step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    nets = {'s': model, 'f': flow}
+    before = {f'{t}::{n}': p.detach().clone() for t, net in nets.items() for n, p in net.named_parameters()}
+    flow_kw = dict(eps=cu(d['eps_post']), vareps=[cu(v) for v in d['varepss']], n_terms=d['ns'])
+    res = step_fn(state, flow_state, cu(d['x']), draws=dict(u=cu(g['u']), z=cu(g['z'])), flow_kw=flow_kw, logp_noise=cu(g['logp_noise']))
+    torch.cuda.synchronize()
+    for i, key in enumerate(('losses', 'losses_score', 'losses_flow', 'losses_logp')):
+        e = float(np.abs(res[i].numpy() - g[key]).max() / np.abs(g[key]).max())
+        print(f'{mode}: {key} rel err {e:.2e}  ({res[i].numpy()} vs {g[key]})')
+        assert e < tol, key
+    after = {f'{t}::{n}': p for t, net in nets.items() for n, p in net.named_parameters()}
+    names = [str(k) for k in g['names']]
+    subs = {k: g['usub.' + k] for k in names}
+    upd = lambda k: (after[k].detach() - before[k]).cpu().numpy()
+    # the first AdamW step moves every element with a real gradient by ~ lr: a tensor whose update is far below lr * sqrt(n) has an
+    # analytically ZERO gradient (e.g. the attention key bias NIN_1.b: softmax is invariant to it) and only carries rounding noise
+    lr_of = lambda k: cfg.optim.lr if k.startswith('s::') else cfg.flow.lr
+    # NIN_1.b (attention key bias) is left out: softmax is invariant to it, its gradient is analytically zero; the reference's fp32
+    # noise there (~1e-10) is below Adam's eps (update ~ 0) while BF16 noise is above it (update ~ lr * sign(noise)) — with no effect
+    # on the network function either way
+    names = [k for k in names if not k.endswith('NIN_1.b')]
+    keep = np.array([not str(k).endswith('NIN_1.b') for k in g['names']])
+    wn, wp, ws = _check_digest(names, g['upd_norms'][keep], g['upd_projs'][keep], subs, upd, upd_tol, 2 * upd_tol, 'update',
+                               floor_fn=lambda k, n: 0.05 * lr_of(k) * np.sqrt(n))
+    print(f'{mode}: {len(names)} parameter updates: worst norm err {wn:.2e}, worst projection err {wp:.2e}, worst sub-sample rel-L2 {ws:.2e}')
+    assert wn < upd_tol and wp < upd_tol and ws < 2 * upd_tol
+
+
+@pytest.mark.parametrize("mode,tol", [('auto', 0.01), ('bf16', 0.15)])
+def test_fullsize_nll_and_nelbo_match_reference(mode, tol):
+    """likelihood.get_likelihood_fn (PF-ODE NLL, RK45 at the reference's default rtol = atol = 1e-5) and get_elbo_fn with the full
+    DDPM++ and the full wolf flow, batch 2.  north_star: within 0.01 bpd — in the default (benched) precision."""
+    from indm_b200 import likelihood
+    g = load_npz('likelihood_full_vp.npz')
+    cfg, model, flow, sde = _joint_models(mode)
+    model.eval()
+    flow.eval()
+    B, S = int(g['B']), 32
+    for which in ('nll', 'elbo'):
+        seed = int(g[f'{which}_draw_seed'])
+        d = oflow.replay_draws(cfg, seed, B)
+        rng = np.random.default_rng(seed + 1000)
+        rad = rng.integers(0, 2, size=(B, 3, S, S)).astype(np.float32)
+        gauss = [rng.standard_normal((B, 3, S, S)).astype(np.float32) for _ in range(4)]
+        u = rng.uniform(size=(B,)).astype(np.float32)
+        assert np.array_equal(rad.astype(np.int8), g[f'{which}_rad']) and np.array_equal(u, g[f'{which}_u'])
+        flow_kw = dict(eps=cu(d['eps_post']), vareps=[cu(v) for v in d['varepss']], n_terms=d['ns'])
+        eps = cu(rad) * 2 - 1.
+        if which == 'nll':
+            fn = likelihood.get_likelihood_fn(cfg, sde, lambda v: (v + 1.) / 2., method='RK45-device')
+            bpd, z, nfe = fn(model, flow, cu(d['x']), eps_bpd=1e-5, epsilon=eps, noise=cu(gauss[0]), residual_noise=(cu(gauss[1]), cu(gauss[2])),
+                             flow_kw=flow_kw)
+            err = float(np.abs(bpd.cpu().numpy() - g['nll_bpd']).max())
+            print(f'NLL {mode}: bpd {bpd.cpu().numpy()} ref {g["nll_bpd"]} |err| {err:.2e}; nfe {nfe} ref {int(g["nll_nfe"])}; '
+                  f'latent rel-L2 {rel_l2(z.cpu().numpy(), g["nll_z"]):.2e}')
+            assert err < tol
+        else:
+            fn = likelihood.get_elbo_fn(cfg, sde, lambda v: (v + 1.) / 2.)
+            a, b = fn(model, flow, cu(d['x']), draws=dict(u=cu(u), z=cu(gauss[0]), epsilon=eps, lp_z=cu(gauss[1]),
+                                                         residual_noise=(cu(gauss[2]), cu(gauss[3]))), flow_kw=flow_kw)
+            e_a = float(np.abs(a.cpu().numpy() - g['elbo_bpd']).max())
+            e_b = float(np.abs(b.cpu().numpy() - g['elbo_bpd_residual']).max())
+            print(f'NELBO {mode}: {a.cpu().numpy()} ref {g["elbo_bpd"]} |err| {e_a:.2e}; with residual |err| {e_b:.2e}')
+            assert e_a < tol and e_b < tol
+
+
+def test_default_policy_is_what_the_docs_say():
+    assert precision.POLICY['score'] == {'sampling': 'bf16', 'training': 'bf16', 'likelihood': 'tf32'}
+    assert precision.POLICY['flow']['reverse'] == 'tf32' and precision.POLICY['flow']['eval'] == 'tf32'
+
+
+# ------------------------------------------------------------------------------------------------ at the benched BATCH
+# The fixtures above are batch 2; bench.py runs 128 images per GPU, where the GEMM launches take other code paths (CTA pairs,
+# 256-wide tiles, the persistent tile loop wrapping many times).  Nothing on the eval paths couples samples (GroupNorm is per
+# sample, BatchNorm is folded, the log-det is per sample), so the reference's rows are embedded in a batch of 128 and compared.
+BENCH_BATCH = 128
+
+
+def _embed(rows, n, seed, scale=1.0, rademacher=False):
+    rng = np.random.default_rng(seed)
+    shape = (n - rows.shape[0],) + tuple(rows.shape[1:])
+    fill = (rng.integers(0, 2, size=shape).astype(np.float32) * 2 - 1) if rademacher else (rng.standard_normal(shape).astype(np.float32) * scale)
+    return np.concatenate([rows, fill], axis=0)
+
+
+@pytest.mark.parametrize("mode,tol_z,tol_ld", [('auto', 1e-4, 1e-3), ('bf16', 2e-2, 5e-2)])
+def test_fullsize_flow_eval_logdet_at_bench_batch(mode, tol_z, tol_ld):
+    g = load_npz('flowfull_cifar.npz')
+    cfg, flow = _flow('cifar', mode, int(g['seed']))
+    flow.eval()
+    B = int(g['B'])
+    d = oflow.replay_draws(cfg, int(g['draw_seed']), B)
+    x = np.clip(_embed(d['x'], BENCH_BATCH, 1, scale=0.5), -1, 1)
+    z, ldkl = fm.flow_forward(cfg, flow, cu(x), reverse=False, eps=cu(_embed(d['eps_post'], BENCH_BATCH, 2)),
+                              vareps=[cu(_embed(v, BENCH_BATCH, 10 + i)) for i, v in enumerate(d['varepss'])], n_terms=d['ns'])
+    torch.cuda.synchronize()
+    e_z = float(np.abs(z[:B].cpu().numpy() - g['z_eval']).max())
+    e_ld = float(np.abs(ldkl[:B].cpu().numpy() - g['ldkl_eval']).max() / np.abs(g['ldkl_eval']).max())
+    print(f'batch {BENCH_BATCH} {mode}: z max-abs err {e_z:.3e}; (logdet - KL) rel err {e_ld:.3e}; ref {g["ldkl_eval"]} got {ldkl[:B].cpu().numpy()}')
+    assert torch.isfinite(ldkl).all() and e_z < tol_z and e_ld < tol_ld
+
+
+@pytest.mark.parametrize("mode,rt_tol", [('auto', 1e-4), ('bf16', 2e-2)])
+def test_fullsize_flow_round_trip_at_bench_batch(mode, rt_tol):
+    cfg, flow = _flow('cifar', mode)
+    flow.eval()
+    core = flow.module
+    rng = np.random.default_rng(5)
+    x = cu(rng.uniform(-1, 1, size=(BENCH_BATCH, 3, 32, 32)).astype(np.float32))
+    eng = core.engine(BENCH_BATCH, leg='reverse')
+    eng._ensure()
+    h = eng.prior_flow(cu(rng.standard_normal((BENCH_BATCH, 64)).astype(np.float32)), 'backward')
+    zf = core(x, reverse=False, eval_logdet=False, h=h)
+    back = core(zf, reverse=True, h=h, atol=1e-12, rtol=1e-12)
+    torch.cuda.synchronize()
+    rt = float((back - x).abs().max())
+    print(f'batch {BENCH_BATCH} {mode}: round trip max-abs {rt:.3e}')
+    assert rt < rt_tol
+
+
+@pytest.mark.parametrize("mode,tol", [('tf32', 1e-3), ('bf16', 2e-2)])
+@pytest.mark.parametrize("tag", ['vp_cifar', 've_cifar'])
+def test_score_network_at_bench_batch(tag, mode, tol):
+    """The full-size score-network goldens (rows of the live reference) inside a batch of 128: the launch shapes bench.py times."""
+    from indm_b200 import sde_lib
+    from indm_b200.models import utils as mutils
+    g = load_npz(f'ncsnpp_{tag}.npz')
+    cfg = configs.get_config('vp/CIFAR10/indm_fid' if tag == 'vp_cifar' else 've/CIFAR10/indm')
+    cfg.device = torch.device('cuda:0')
+    model = mutils.create_model(cfg)
+    model.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(cfg, int(g['seed'])).items()})
+    model.eval()
+    model.module.compute_mode = mode
+    sde = sde_lib.get_sde(cfg)
+    B = g['x'].shape[0]
+    rng = np.random.default_rng(8)
+    x = cu(_embed(g['x'], BENCH_BATCH, 3, scale=float(np.std(g['x']))))
+    t = cu(np.concatenate([g['t'], rng.uniform(0.05, 0.95, size=BENCH_BATCH - B).astype(np.float32)]))
+    with torch.no_grad():
+        score = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)(x, t)
+    torch.cuda.synchronize()
+    e = rel_l2(score[:B].cpu().numpy(), g['score'])
+    print(f'batch {BENCH_BATCH} {tag} {mode}: score rel-L2 {e:.3e}')
+    assert torch.isfinite(score).all() and e < tol
+
+
+@pytest.mark.parametrize("mode,tol", [('tf32', 1e-3), ('bf16', 5e-2)])
+def test_score_vjp_at_bench_batch(mode, tol):
+    """Input-VJP of the full DDPM++ (the Hutchinson term of the PF-ODE, likelihood.py:27-38) with the reference's rows inside a batch
+    of 128."""
+    from indm_b200 import sde_lib
+    from indm_b200.models import utils as mutils
+    g = load_npz('vjp_vp_cifar.npz')
+    cfg = configs.get_config('vp/CIFAR10/indm_nll')
+    cfg.device = torch.device('cuda:0')
+    model = mutils.create_model(cfg)
+    model.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(cfg, int(g['seed'])).items()})
+    model.eval()
+    model.module.compute_mode = mode
+    sde = sde_lib.get_sde(cfg)
+    B = g['x'].shape[0]
+    x = cu(_embed(g['x'], BENCH_BATCH, 4)).requires_grad_(True)
+    t = cu(np.concatenate([g['t'], np.full(BENCH_BATCH - B, 0.6, np.float32)]))
+    eps = cu(_embed(g['eps'], BENCH_BATCH, 5, rademacher=True))
+    sc = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)(x, t)
+    vjp, = torch.autograd.grad((sc * eps).sum(), x)
+    torch.cuda.synchronize()
+    e_s, e_v = rel_l2(sc[:B].detach().cpu().numpy(), g['score']), rel_l2(vjp[:B].cpu().numpy(), g['vjp'])
+    print(f'batch {BENCH_BATCH} {mode}: score rel-L2 {e_s:.3e}, input-VJP rel-L2 {e_v:.3e}')
+    assert e_s < tol and e_v < tol

@@ -117,7 +117,7 @@ def test_plain_forward_after_sampling_is_conditioned_on_t(tag):
         a = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)(x, t).cpu().numpy()
         b = mutils.get_score_fn(cfg2, sde, fresh, train=False, continuous=True)(x, t).cpu().numpy()
     assert np.isfinite(a).all()
-    assert rel_l2(a, b) < 1e-6
+    assert rel_l2(a, b) < 1e-5          # fp32 atomics in the fused GroupNorm statistics reorder roundings from run to run
 
 
 def test_unseeded_sampler_calls_use_fresh_noise_and_manual_seed_controls_it():
@@ -132,8 +132,8 @@ def test_unseeded_sampler_calls_use_fresh_noise_and_manual_seed_controls_it():
     a2 = fn(model, None, prior=prior)[0].cpu().numpy()
     torch.manual_seed(7)
     b1 = fn(model, None, prior=prior)[0].cpu().numpy()
-    assert rel_l2(a2, a1) > 1e-3                  # two rounds: different Brownian paths
-    assert np.array_equal(a1, b1)                 # same global seed: same path
+    assert rel_l2(a2, a1) > 1e-2                  # two rounds: different Brownian paths
+    assert rel_l2(a1, b1) < 1e-3                  # same global seed: same path (not bitwise: fp32 atomics in the GroupNorm statistics)
     s1 = fn(model, None, prior=prior, seed=5)[0].cpu().numpy()
     s2 = fn(model, None, prior=prior, seed=5)[0].cpu().numpy()
-    assert np.array_equal(s1, s2)
+    assert rel_l2(s1, s2) < 1e-3 and rel_l2(s1, a1) > 1e-2

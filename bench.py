@@ -11,6 +11,11 @@ followed by the flow inverse.  `value` = images/s with the prior sample already 
 through the public API `sampling.get_pc_sampler(...)(model, flow_model)` with the prior drawn on the host (pinned) and
 copied in, and the samples copied back, every step.
 
+Extra legs on the same JSON line (each says its own config; `--skip-extras` leaves them out): `ve_pc` = the north-star target
+workload (ve/CIFAR10/indm: reverse diffusion + Langevin corrector, 2 NFE per step, FIR resampling, 1000 steps, 128 images per
+GPU), `train` = the INDM-VP joint training step, `nll` = PF-ODE likelihood (sharded by image under torchrun), `celeba` = the
+64x64 nres=8 configs (bounded slices), `ref_ops` = the reference's two native ops through the C-ABI.
+
     python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                   CPU arm: the oracle port of the reference's PyTorch CPU path
     python bench.py --num-scales 4 --skip-train --skip-cpu   profiling slice of the same command for `ncu` (a line printed by such
@@ -101,31 +106,20 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------- CPU arm
-CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH = 24, 32      # ~10 s of work on the GPU box's 16 host cores (0.45 s per PC step at batch 32)
-
-
-def cpu_sample(threads, n_pc=CPU_SAMPLE_STEPS, batch=CPU_SAMPLE_BATCH, repeats=1):
-    """Bounded sample of the same workload on the host: `n_pc` reverse-diffusion PC steps of the oracle port (PyTorch CPU
-    FP32 restatement of the reference, oracle/) at batch `batch`; extrapolated to the 1000-step figure."""
-    import numpy as np
-    import torch
-    from oracle import ncsnpp as oncsnpp, sde as osde, sampler as osampler
-    torch.set_num_threads(threads)
-    cfg = workload_config(torch.device("cpu"))
-    params = oncsnpp.to_torch(oncsnpp.synth_params(cfg, 0))
-    sde = osde.get_sde(cfg)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 3, 32, 32, generator=g)
-    noises = [torch.randn(batch, 3, 32, 32, generator=g) for _ in range(n_pc)]
-    best = None
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            osampler.pc_sampler(sde, lambda a, b: oncsnpp.score_fn(cfg, sde, params, a, b), x, noises, n_pc, 1e-5, cfg.sampling.snr)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    per_step = best / n_pc
-    return batch / (per_step * NUM_SCALES), f"{n_pc} PC steps (1 NFE each) of the oracle port at batch {batch}, FP32, {best:.1f} s of CPU work, extrapolated x{NUM_SCALES / n_pc:.1f}"
+def cpu_sample(threads, samples=3):
+    """cpu_baseline of the GPU arm's line: the `--impl reference` arm itself (same bounded samples), run as a child process with the
+    GPU hidden (the reference wraps its model in nn.DataParallel, which grabs every visible GPU): `samples` timed samples after one
+    warm-up sample + one flow inverse, ~15-30 s of host work."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(samples), "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not line:
+        raise RuntimeError("cpu arm failed: " + (r.stderr or r.stdout)[-400:])
+    d = json.loads(line[-1])
+    return d["value"], d["cpu_baseline"]["kind"], d["cpu_baseline"]["sample"]
 
 
 def cpu_train_sample(threads, batch=8):
@@ -178,24 +172,108 @@ def cpu_train_sample(threads, batch=8):
                         f"batch {batch}, FP32, {dt:.1f} s of CPU work")
 
 
+REF_VENDORED = os.path.join(ROOT, "oracle", "_ref")
+REF_SAMPLE_STEPS = 1           # PC steps per bounded sample at the full per-GPU batch (128): a few seconds of host work
+
+
+def _reference_sampler(threads):
+    """The reference's OWN pc_sampler on the host (oracle/_ref: the unmodified reference modules placed by oracle/make_ref.py),
+    on this arm's config: returns (sample_fn() -> seconds for REF_SAMPLE_STEPS PC steps at batch 128, flow_fn() -> seconds for one
+    flow inverse at batch 128, kind).  Falls back to the oracle port when oracle/_ref is absent."""
+    import tempfile
+    import torch
+    torch.set_num_threads(threads)
+    from oracle import ncsnpp as oncsnpp, flow as oflow
+    from indm_b200 import configs as pconfigs
+    if os.path.isdir(os.path.join(REF_VENDORED, "models")):
+        os.environ["INDM_REFERENCE_ROOT"] = REF_VENDORED
+        from oracle import ref_loader as rl
+        mutils, sde_lib, sampling, fm, _ = rl.load("models.utils", "sde_lib", "sampling", "flow_models.flow_model", "models.ncsnpp")
+        cfg = rl.get_config("configs/vp/CIFAR10/indm_fid.py")
+        cfg.sampling.method, cfg.sampling.predictor, cfg.sampling.corrector = "pc", "reverse_diffusion", "none"
+        cfg.sampling.num_scales = REF_SAMPLE_STEPS
+        pcfg = workload_config(torch.device("cpu"))
+        model = mutils.create_model(cfg)
+        model.module.load_state_dict({k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(pcfg, 0).items()})
+        model.eval()
+        with rl.reference_cwd():
+            flow = fm.create_flow_model(cfg)
+        flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, 1).items()})
+        flow.eval()
+        sde = sde_lib.get_sde(cfg)
+        shape = (PER_GPU_BATCH, 3, 32, 32)
+        cfg_id = rl.get_config("configs/vp/CIFAR10/indm_fid.py")
+        cfg_id.sampling.method, cfg_id.sampling.predictor, cfg_id.sampling.corrector = "pc", "reverse_diffusion", "none"
+        cfg_id.sampling.num_scales = REF_SAMPLE_STEPS
+        cfg_id.flow.model = "identity"
+        fn = sampling.get_sampling_fn(cfg_id, sde, shape, lambda v: (v + 1.) / 2., cfg.sampling.truncation_time)
+        tmp = tempfile.mkdtemp()
+
+        def sample_fn():
+            t0 = time.perf_counter()
+            fn(model, None, sample_dir=tmp, r=0)            # sampling.get_pc_sampler(...).pc_sampler: the reference's own loop
+            return time.perf_counter() - t0
+
+        def flow_fn():
+            z = torch.randn(shape)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                fm.flow_forward(cfg, flow, z, log_det=None, reverse=True)
+            return time.perf_counter() - t0
+        return sample_fn, flow_fn, "reference"
+    # oracle port (the restatement pinned against the reference's outputs, tests/test_oracle_*.py)
+    from oracle import sde as osde, sampler as osampler
+    cfg = workload_config(torch.device("cpu"))
+    params = oncsnpp.to_torch(oncsnpp.synth_params(cfg, 0))
+    fparams = oflow.to_torch(oflow.synth_params(cfg, 1))
+    sde = osde.get_sde(cfg)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(PER_GPU_BATCH, 3, 32, 32, generator=g)
+    noises = [torch.randn(PER_GPU_BATCH, 3, 32, 32, generator=g) for _ in range(REF_SAMPLE_STEPS)]
+
+    def sample_fn():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            osampler.pc_sampler(sde, lambda a_, b_: oncsnpp.score_fn(cfg, sde, params, a_, b_), x, noises, REF_SAMPLE_STEPS, 1e-5, cfg.sampling.snr)
+        return time.perf_counter() - t0
+
+    def flow_fn():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            oflow.wolf_reverse(cfg, fparams, x, torch.randn(PER_GPU_BATCH, 64, generator=g))
+        return time.perf_counter() - t0
+    return sample_fn, flow_fn, "port"
+
+
 def run_reference(args):
+    """CPU arm: the reference's own implementation of the path on the box's host cores, on this arm's config.  One step = one
+    bounded sample: REF_SAMPLE_STEPS PC steps of `pc_sampler` at the full per-GPU batch (128 images); the flow inverse (one pass per
+    1000 PC steps) is timed once during warm-up; images/s = 128 / (1000 * seconds per PC step + seconds per flow inverse)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""      # before torch initialises CUDA: the reference's nn.DataParallel would grab the GPUs
     threads = os.cpu_count() or 1
-    vals = []
+    sample_fn, flow_fn, kind = _reference_sampler(threads)
+    t_flow = flow_fn()
+    per_step = []
     for i in range(args.warmup + args.steps):
-        v, sample = cpu_sample(threads)
+        dt = sample_fn() / REF_SAMPLE_STEPS
         if i >= args.warmup:
-            vals.append(v)
-    value = sum(vals) / len(vals)
+            per_step.append(dt)
+    t_step = sum(per_step) / len(per_step)
+    t_call = NUM_SCALES * t_step + t_flow
+    value = PER_GPU_BATCH / t_call
+    sample = (f"{REF_SAMPLE_STEPS} PC steps (1 NFE each) of the {'reference' if kind == 'reference' else 'oracle port of the reference'}'s pc_sampler at "
+              f"batch {PER_GPU_BATCH}, FP32, {t_step * REF_SAMPLE_STEPS:.1f} s of CPU work per sample ({t_step:.2f} s per PC step) x {args.steps} timed samples; "
+              f"flow inverse at batch {PER_GPU_BATCH} timed once: {t_flow:.1f} s; figure = 128 / (1000 x step + flow)")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": PER_GPU_BATCH / value * 1e3, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": t_call * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "num_scales": NUM_SCALES,
-                      "cpu_arm": "bounded sample of that workload on the host cores, extrapolated to the 1000-step figure; the flow inverse "
-                                 "(one pass per 1000 PC steps, < 1 % of the work) is not part of the sample"},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "cpu_arm": "each step is a bounded sample of that workload on the host cores (see cpu_baseline.sample); ms_per_step is the "
+                                 "extrapolated time of one full 1000-step pc_sampler call at batch 128, not the duration of a sample"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -228,6 +306,64 @@ def _gn_apply_bytes(op):
     C = Ca + Cb
     Po = H * W * (4 if resample == 1 else 1) // (4 if resample == 2 else 1)
     return N * H * W * C * (4 if in_dt == L.DTYPE_F32 else 2) + N * Po * C * 2 * (2 if raw else 1)
+
+
+def _fir_bytes(op):
+    """Algorithmic HBM bytes of one `indm_fir_nhwc` launch (input read once + output written once); None for other launches."""
+    if _closure(op, key="name") != "indm_fir_nhwc":
+        return None
+    from indm_b200 import _lib as L
+    a = _closure(op, key="cargs")
+    val = lambda v: getattr(v, "value", v)
+    din, dout, N, H, W, C, mode = val(a[2]), val(a[3]), val(a[4]), val(a[5]), val(a[6]), val(a[7]), val(a[9])
+    Ho, Wo = {1: (2 * H, 2 * W), 2: (H // 2, W // 2), 3: (H + 1, W + 1), 4: (H - 1, W - 1)}[mode]
+    esz = lambda d: 2 if d == L.DTYPE_BF16 else 4
+    return N * H * W * C * esz(din) + N * Ho * Wo * C * esz(dout)
+
+
+def class_stream_ms(ops, reps=3):
+    """average device time of the launches in `ops` issued back to back between two CUDA events (GPU parked in a spin while the host
+    enqueues)"""
+    import torch
+    tot = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(60_000_000)
+        e0.record()
+        for op in ops:
+            op()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def fir_roofline(eng, pk, pk_kind):
+    """roofline_hbm of the FIR resampling class (`fir_nhwc_kernel`) of one VE score-network forward"""
+    import torch
+    for _ in range(2):
+        eng.launch()
+    torch.cuda.synchronize()
+    ops, by = [], 0.0
+    for op in eng.ops:
+        try:
+            b = _fir_bytes(op)
+        except Exception:
+            b = None
+        if b is not None:
+            ops.append(op)
+            by += b
+    if not ops:
+        return None
+    ms, fwd = class_stream_ms(ops), class_stream_ms(eng.ops)
+    eng.launch()
+    torch.cuda.synchronize()
+    gbs = by / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+            "kernel": "fir_nhwc_kernel (upfirdn2d call sites of models/up_or_down_sampling.py: up x2, down x2, pad (2,2))",
+            "peak_source": pk_kind + " hbm_gbs", "launches_per_forward": len(ops), "avg_launch_ms": ms / len(ops),
+            "share_of_forward_device_time": ms / fwd, "forward_device_ms": fwd,
+            "algorithmic_bytes": "input read once + output written once, operand dtypes as launched (SURVEY 8d: 2 x (in + out) bytes counts r+w)"}
 
 
 def kernel_rooflines(net, eng, reps=3):
@@ -332,6 +468,221 @@ def train_throughput(cfg_s, model, flow, sde, dev, world, timed, steps=6, warmup
             "dtype": "bf16"}
 
 
+def _randomise_zero_init(net):
+    """random-init weights of that architecture; the ~0-initialised tensors (init_scale=0) get ordinary magnitudes so the network
+    output is not identically ~0"""
+    import torch
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            if p_.dim() > 1 and float(p_.abs().max()) < 1e-6:
+                fan = p_[0].numel() + p_.shape[0] * (p_[0, 0].numel() if p_.dim() > 2 else 1)
+                p_.uniform_(-1, 1).mul_((6.0 / fan) ** 0.5)
+
+
+def ve_pc_leg(dev, world, timed, steps=2, warmup=1, num_scales=NUM_SCALES, global_norms=False):
+    """The north-star TARGET workload: configs/ve/CIFAR10/indm.py — NCSN++ (nres=4, FIR resampling, input pyramid, Fourier
+    embedding) + wolf flow, PC sampling with the reverse-diffusion predictor AND the Langevin corrector (2 NFE per step, per-sample
+    norms, sampling.py:263-292,410-456), 1000 steps, 128 images per GPU.  One step = one complete pc_sampler call."""
+    import torch
+    from indm_b200 import configs, sde_lib, sampling
+    from indm_b200.models import utils as mutils
+    from indm_b200.flow_models import flow_model as fm
+    cfg = configs.get_config("ve/CIFAR10/indm")
+    cfg.sampling.method, cfg.sampling.predictor, cfg.sampling.corrector = "pc", "reverse_diffusion", "langevin"
+    cfg.sampling.num_scales = num_scales
+    cfg.sampling.global_langevin_norms = bool(global_norms)
+    cfg.device = dev
+    torch.manual_seed(0)
+    model = mutils.create_model(cfg)
+    _randomise_zero_init(model.module)
+    flow = fm.create_flow_model(cfg)
+    flow.eval()
+    sde = sde_lib.get_sde(cfg)
+    shape = (PER_GPU_BATCH, 3, 32, 32)
+    fn = sampling.get_sampling_fn(cfg, sde, shape, lambda v: v, cfg.sampling.truncation_time)
+    prior_host = (torch.randn(shape) * cfg.model.sigma_max).pin_memory()
+    out = {}
+
+    def call():
+        out["r"] = fn(model, flow, prior=prior_host.to(dev, non_blocking=True), seed=1)
+        out["host"] = out["r"][1].cpu()
+
+    ms, launches = timed(call, steps, warmup)
+    pk, pk_kind = peaks()
+    eng = model.module.engine(PER_GPU_BATCH)
+    res = {"metric": METRIC, "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_pc_step": ms / num_scales,
+           "steps": steps, "warmup": warmup, "per_gpu_batch": PER_GPU_BATCH, "num_scales": num_scales, "nfe_per_call": 2 * num_scales,
+           "gpu_launches": launches, "finite": bool(torch.isfinite(out["host"]).all()), "dtype": "bf16 (score net) / 3xTF32 (flow inverse)",
+           "config": "ve/CIFAR10/indm (NCSN++ nres=4 nf=128, fir=True, progressive_input=residual, fourier embedding) + wolf flow; "
+                     "sampling.method=pc predictor=reverse_diffusion corrector=langevin snr=0.16, 1000 steps x 2 NFE, 128 images per GPU; "
+                     "end to end through sampling.get_sampling_fn (host prior in, samples out)",
+           "langevin_statistics": ("global batch means: 3 floats all-reduced (NCCL, inside the CUDA graph) per corrector step"
+                                   if (global_norms and world > 1) else "per-rank batch means (no communication)" if world > 1 else "single batch"),
+           "score_forward_tflops_algorithmic": 21.75 * PER_GPU_BATCH * 2 * num_scales / (ms * 1e-3) / 1e3}
+    try:
+        fr = fir_roofline(eng, pk, pk_kind)
+        if fr is not None:
+            res["roofline_hbm"] = fr
+    except Exception as e:
+        res["roofline_hbm"] = {"error": repr(e)[:200]}
+    return res
+
+
+def nll_leg(dev, world, timed):
+    """PF-ODE likelihood (likelihood.get_likelihood_fn, BASELINE configs[2] second half) on vp/CIFAR10/indm_nll, 128 images per GPU,
+    sharded by image (per-rank solvers on their sub-batches; no data-path collective), device-resident RK45, in the
+    DEFAULT precision policy (score forward + Hutchinson VJP and flow log-det in compensated TF32: the mode that meets 0.01 bpd)."""
+    import numpy as np
+    import torch
+    from indm_b200 import configs, sde_lib, likelihood
+    cfg = configs.get_config("vp/CIFAR10/indm_nll")
+    cfg.device = dev
+    sde = sde_lib.get_sde(cfg)
+    from indm_b200.models import utils as mutils
+    from indm_b200.flow_models import flow_model as fm
+    torch.manual_seed(0)
+    model = mutils.create_model(cfg)
+    flow = fm.create_flow_model(cfg)
+    model.eval()
+    flow.eval()
+    g = torch.Generator().manual_seed(1 + int(os.environ.get("RANK", "0")))
+    data = (torch.rand(PER_GPU_BATCH, 3, 32, 32, generator=g) * 2 - 1).pin_memory()
+    fn = likelihood.get_likelihood_fn(cfg, sde, lambda v: (v + 1.) / 2., method="RK45-device")
+    out = {}
+
+    def call():
+        np.random.seed(7)
+        out["r"] = fn(model, flow, data.to(dev, non_blocking=True))
+        out["bpd"] = out["r"][0].cpu()
+
+    ms, launches = timed(call, 1, 1)
+    nfe = int(out["r"][2])
+    return {"metric": "nll_images_per_sec", "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": "images/s", "ms_per_call": ms, "nfe": nfe,
+            "ms_per_nfe": ms / max(nfe, 1), "per_gpu_batch": PER_GPU_BATCH, "gpu_launches": launches, "bpd_mean": float(out["bpd"].mean()),
+            "finite": bool(torch.isfinite(out["bpd"]).all()), "dtype": "3xTF32 (score forward + input-VJP, flow log-det): the precision pinned at 0.01 bpd",
+            "config": "vp/CIFAR10/indm_nll likelihood_fn(method='RK45-device', rtol=atol=1e-5), wolf flow forward + (20+n)-term log-det inside the "
+                      "call, 128 images per GPU, sharded by image; weights = the modules' initialisers (head conv ~0: smooth ODE, few NFE) — "
+                      "ms_per_nfe (1 forward + 1 input-VJP) is the transferable figure"}
+
+
+def celeba_leg(dev, timed, batch=64, pc_steps=40):
+    """BASELINE configs[3] / [4] (3x64x64, nres = 8, wolf flow with flow.squeeze) on ONE GPU as bounded slices: `pc_steps` steps of
+    the 1000-step VE PC + Langevin schedule (every step replays the same CUDA graph, so ms per PC step is the 1000-step figure
+    / 1000; the flow inverse is timed inside the slice and reported amortised over 1000), and the VP joint training step."""
+    import torch
+    from indm_b200 import configs, sde_lib, sampling, losses
+    from indm_b200.models import utils as mutils
+    from indm_b200.models.ema import ExponentialMovingAverage
+    from indm_b200.flow_models import flow_model as fm
+    res = {}
+    torch.manual_seed(0)
+    cfg = configs.get_config("ve/CELEBA/indm")
+    cfg.model.num_res_blocks = 8
+    cfg.device = dev
+    model = mutils.create_model(cfg)
+    _randomise_zero_init(model.module)
+    flow = fm.create_flow_model(cfg)
+    flow.eval()
+    sde = sde_lib.get_sde(cfg)
+    ms = {}
+    for n in (pc_steps // 2, pc_steps):          # two slice lengths: the difference isolates the per-step cost from the flow inverse
+        cfg.sampling.num_scales = n
+        fn = sampling.get_sampling_fn(cfg, sde, (batch, 3, 64, 64), lambda v: v, cfg.sampling.truncation_time)
+        ms[n], _ = timed(lambda: fn(model, flow, seed=1), 2, 1)
+    per_step = (ms[pc_steps] - ms[pc_steps // 2]) / (pc_steps - pc_steps // 2)
+    flow_ms = max(ms[pc_steps] - per_step * pc_steps, 0.0)
+    res["ve_pc"] = {"config": "ve/CELEBA/indm num_res_blocks=8, 64x64, PC reverse_diffusion + langevin (2 NFE per step), wolf flow (squeeze) inverse",
+                    "batch": batch, "slice_pc_steps": [pc_steps // 2, pc_steps], "ms_per_pc_step": per_step, "flow_inverse_ms": flow_ms,
+                    "images_per_sec_at_1000_steps": batch / ((per_step * 1000 + flow_ms) * 1e-3),
+                    "score_forward_tflops_algorithmic": 142.9 * batch * 2 / (per_step * 1e-3) / 1e3,
+                    "note": "bounded slice of the 1000-step schedule on one GPU, not a full run; extrapolated figure labelled as such"}
+    del model, flow, fn
+    torch.cuda.empty_cache()
+    cfg = configs.get_config("vp/CELEBA/indm_nll")
+    cfg.model.num_res_blocks = 8
+    cfg.device = dev
+    model = mutils.create_model(cfg)
+    flow = fm.create_flow_model(cfg)
+    sde = sde_lib.get_sde(cfg)
+    state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model,
+                 ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+    flow_state = dict(optimizer=losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr), model=flow,
+                      ema=ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate), step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    bh = (torch.rand(batch, 3, 64, 64) * 2 - 1).pin_memory()
+    ms_t, _ = timed(lambda: step_fn(state, flow_state, bh.to(dev, non_blocking=True)), 4, 10)
+    res["train"] = {"config": "vp/CELEBA/indm_nll num_res_blocks=8, 64x64, flow_step_fn_nll JOINT step (flow + score)", "batch": batch,
+                    "ms_per_step": ms_t, "samples_per_sec": batch / (ms_t * 1e-3),
+                    "score_fwd_bwd_tflops_algorithmic": 3 * 142.9 * batch / (ms_t * 1e-3) / 1e3}
+    del model, flow, state, flow_state, step_fn
+    torch.cuda.empty_cache()
+    return res
+
+
+def ref_ops_leg(dev):
+    """The reference's two native ops through the C-ABI (`indm_upfirdn2d_f32`, `indm_bias_act_f32`: what op/upfirdn2d.cpp:12-19 and
+    op/fused_bias_act.cpp:11-17 bind) on SURVEY section 7's gate shape 16 x 256 x 32 x 32 FP32: GB/s of algorithmic bytes (input read
+    once + output written once) against the measured HBM copy bandwidth.  Inputs are cycled through 12 distinct buffers (> L2)."""
+    import torch
+    from indm_b200 import _lib as L
+    pk, pk_kind = peaks()
+    N, C, S = 16, 256, 32
+    k = torch.tensor([1., 3., 3., 1.])
+    k2 = (k[:, None] * k[None, :])
+    k2 = (k2 / k2.sum()).to(dev)
+    res = {}
+    cases = {"up2 (pad 2,1)": (2, 1, 2, 1, 4.0), "down2 (pad 1,1)": (1, 2, 1, 1, 1.0), "pad (2,2)": (1, 1, 2, 2, 1.0)}
+    nbuf = 12
+    xs = [torch.randn(N * C, S, S, 1, device=dev) for _ in range(nbuf)]
+    for name, (up, down, p0, p1, gain) in cases.items():
+        Ho = (S * up + p0 + p1 - 4) // down + 1
+        ys = [torch.empty(N * C, Ho, Ho, 1, device=dev) for _ in range(nbuf)]
+        kk = (k2 * gain).contiguous()
+
+        def run(i):
+            L.call("indm_upfirdn2d_f32", L.ptr(xs[i % nbuf]), L.ptr(kk), L.ptr(ys[i % nbuf]), N * C, S, S, 4, 4, up, up, down, down, p0, p1, p0, p1)
+        for i in range(nbuf):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 4 * nbuf
+        e0.record()
+        for i in range(reps):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        by = 4 * N * C * (S * S + Ho * Ho)
+        res["upfirdn2d " + name] = {"us": us, "GB/s": by / (us * 1e-6) / 1e9, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / pk["hbm_gbs"], "bytes": by}
+    xb = [torch.randn(N, C, S, S, device=dev) for _ in range(nbuf)]
+    yb = [torch.empty(N, C, S, S, device=dev) for _ in range(nbuf)]
+    bias = torch.randn(C, device=dev)
+
+    def runb(i):
+        L.call("indm_bias_act_f32", L.ptr(xb[i % nbuf]), L.ptr(bias), None, L.ptr(yb[i % nbuf]), xb[0].numel(), C, S * S, 3, 0,
+               0.2, 2.0 ** 0.5)
+    try:
+        for i in range(nbuf):
+            runb(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 4 * nbuf
+        e0.record()
+        for i in range(reps):
+            runb(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        by = 8 * xb[0].numel()
+        res["fused_leaky_relu (bias_act)"] = {"us": us, "GB/s": by / (us * 1e-6) / 1e9, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / pk["hbm_gbs"], "bytes": by}
+    except Exception as e:
+        res["fused_leaky_relu (bias_act)"] = {"error": repr(e)[:200]}
+    res["shape"] = f"{N} x {C} x {S} x {S} fp32, 12 rotating buffers (> L2), CUDA events over 48 launches"
+    res["peak_source"] = pk_kind + " hbm_gbs"
+    return res
+
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -354,13 +705,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = mutils.create_model(cfg)
     net = model.module
-    # random-init weights of that architecture; the ~0-initialised tensors (init_scale=0) get ordinary magnitudes so the
-    # network output is not identically ~0
-    with torch.no_grad():
-        for n_, p_ in net.named_parameters():
-            if p_.dim() > 1 and float(p_.abs().max()) < 1e-6:
-                fan = p_[0].numel() + p_.shape[0] * (p_[0, 0].numel() if p_.dim() > 2 else 1)
-                p_.uniform_(-1, 1).mul_((6.0 / fan) ** 0.5)
+    _randomise_zero_init(net)
     flow = fm.create_flow_model(cfg)
     flow.eval()
     flow_note = "wolf (prior-flow sample of h + fixed-point inverse of 16+16 iResBlocks, idim 512), inside every timed step"
@@ -407,8 +752,24 @@ def run_ours(args):
         clocks.start()
     ms_step, launches = timed(step_resident, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    e2e_steps = max(2, min(args.steps, 4))
+    ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
     train = None if args.skip_train else train_throughput(cfg, model, flow, sde, dev, world, timed)
+    extras = {}
+    if not args.skip_extras:
+        import traceback
+
+        def leg(name, fn):
+            try:
+                extras[name] = fn()
+            except Exception as e:          # an extra leg never takes the bench line down; the failure is on the line
+                extras[name] = {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
+            torch.cuda.empty_cache()
+        leg("ve_pc", lambda: ve_pc_leg(dev, world, timed, num_scales=args.num_scales, global_norms=args.global_langevin_norms))
+        leg("nll", lambda: nll_leg(dev, world, timed))
+        if world == 1:
+            leg("celeba", lambda: celeba_leg(dev, timed))
+            leg("ref_ops", lambda: ref_ops_leg(dev))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -455,9 +816,16 @@ def run_ours(args):
                                "algorithmic_bytes": "input read once (4 B fp32 residual stream / 2 B bf16) + 2 B output per element (+ 2 B raw copy)"}
     if train is not None:
         out["train"] = train
+    out["e2e"]["steps"] = e2e_steps
+    out.update(extras)
+    from indm_b200 import precision
+    out["config"]["precision_policy"] = precision.POLICY
     if world == 1 and not args.skip_cpu:
-        v, sample = cpu_sample(os.cpu_count() or 1)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+        try:
+            v, kind, sample = cpu_sample(os.cpu_count() or 1)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": sample}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "error": repr(e)[:300]}
         if train is not None:
             try:
                 tv, tsample = cpu_train_sample(os.cpu_count() or 1)
@@ -478,6 +846,9 @@ def main():
     ap.add_argument("--num-scales", type=int, default=NUM_SCALES, help="PC steps per sampler call (profiling slices only; the bench is 1000)")
     ap.add_argument("--skip-train", action="store_true", help="profiling: leave out the training leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling: leave out the CPU baseline sample")
+    ap.add_argument("--skip-extras", action="store_true", help="leave out the extra legs (ve_pc, nll, celeba, ref_ops)")
+    ap.add_argument("--global-langevin-norms", action="store_true",
+                    help="ve_pc leg under torchrun: all-reduce the Langevin norm statistics (global batch means) instead of per-rank means")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -306,6 +306,15 @@ int indm_langevin_update(float* x, const float* s, const float* z, float* x_mean
                          int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
                          uint64_t rng_offset, void* stream);
 
+/* Batch-sharded sampling with GLOBAL Langevin statistics (the reference takes .mean() over the whole batch, sampling.py:286-287):
+ * sums[0] = sum_n |s_n|, sums[1] = sum_n |z_n|, sums[2] = N from the per-sample sums of squares of indm_langevin_norms; the caller
+ * all-reduces the three floats over ranks (NCCL, on the same stream) and hands them to indm_langevin_update_global, which is
+ * indm_langevin_update with the two means taken as gsums[0] / gsums[2], gsums[1] / gsums[2]. */
+int indm_langevin_norm_sums(const float* norms, float* sums, int64_t N, void* stream);
+int indm_langevin_update_global(float* x, const float* s, const float* z, float* x_mean, const float* gsums, const float* coef,
+                                int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
+                                uint64_t rng_offset, void* stream);
+
 /* *step += 1 (device-side step counter advanced inside the captured graph) */
 int indm_advance_step(int32_t* step, void* stream);
 

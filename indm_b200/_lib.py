@@ -64,6 +64,8 @@ _SIGS = {
     "indm_pc_predictor_update": [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
     "indm_langevin_norms": [_vp, _vp, _vp, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
     "indm_langevin_update": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
+    "indm_langevin_norm_sums": [_vp, _vp, _i64, _vp],
+    "indm_langevin_update_global": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _i64, _u64, _vp, _u64, _vp],
     "indm_advance_step": [_vp, _vp],
     "indm_randn_f32": [_vp, _i64, _u64, _u64, _vp],
     "indm_prior_flow": [_vp, _vp, _vp, _vp, _vp, C.c_int, _f32, _vp, _i64, _vp],

@@ -69,15 +69,39 @@ __global__ void langevin_norms_kernel(const float* __restrict__ s, const float* 
   }
 }
 
+// local sums of the per-sample L2 norms and the local batch size: sums[0] = sum_n |s_n|, sums[1] = sum_n |z_n|, sums[2] = N.
+// Summed over ranks (one 12-byte all-reduce) they give the GLOBAL batch means of sampling.py:286-287 for a batch-sharded sampler.
+__global__ void langevin_norm_sums_kernel(const float* __restrict__ norms, float* __restrict__ sums, int N) {
+  float gs = 0.f, gz = 0.f;
+  for (int n = threadIdx.x; n < N; n += 32) {
+    gs += sqrtf(norms[n * 2 + 0]);
+    gz += sqrtf(norms[n * 2 + 1]);
+  }
+  gs = warp_sum(gs);
+  gz = warp_sum(gz);
+  if (threadIdx.x == 0) {
+    sums[0] = gs;
+    sums[1] = gz;
+    sums[2] = (float)N;
+  }
+}
+
 __global__ void langevin_update_kernel(float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ z,
-                                       float* __restrict__ x_mean, const float* __restrict__ norms, const float* __restrict__ coef,
+                                       float* __restrict__ x_mean, const float* __restrict__ norms, const float* __restrict__ gsums,
+                                       const float* __restrict__ coef,
                                        int coef_ld, const int32_t* __restrict__ step, int N, long long total4, uint64_t seed,
                                        const uint64_t* __restrict__ seed_dev, uint32_t off) {
   __shared__ float sh[2];
   const int st = step ? *step : 0;
   if (seed_dev) seed = *seed_dev;
-  // batch means of the per-sample L2 norms (sampling.py:286-287): N is small, every CTA recomputes them
-  if (threadIdx.x < 32) {
+  if (gsums) {
+    // global statistics: sums over all ranks' samples (already all-reduced), divided by the global batch size
+    if (threadIdx.x == 0) {
+      sh[0] = gsums[0] / gsums[2];
+      sh[1] = gsums[1] / gsums[2];
+    }
+  } else if (threadIdx.x < 32) {
+    // batch means of the per-sample L2 norms (sampling.py:286-287): N is small, every CTA recomputes them
     float gs = 0.f, gz = 0.f;
     for (int n = threadIdx.x; n < N; n += 32) {
       gs += sqrtf(norms[n * 2 + 0]);
@@ -171,9 +195,29 @@ extern "C" int indm_langevin_update(float* x, const float* s, const float* z, fl
   INDM_CHECK_ARG(x && s && norms && coef && N > 0 && D > 0 && coef_ld >= 2, "langevin_update: bad arguments");
   INDM_CHECK_ARG((N * D) % 4 == 0, "langevin_update: N*D must be a multiple of 4");
   const long long total4 = N * D / 4;
-  langevin_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, norms, coef, coef_ld, step, (int)N, total4, seed,
+  langevin_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, norms, nullptr, coef, coef_ld, step, (int)N, total4, seed,
                                                              seed_dev, (uint32_t)rng_offset);
   INDM_CHECK_LAUNCH("langevin_update");
+  return INDM_OK;
+}
+
+extern "C" int indm_langevin_norm_sums(const float* norms, float* sums, int64_t N, void* stream_) {
+  INDM_CHECK_ARG(norms && sums && N > 0, "langevin_norm_sums: bad arguments");
+  langevin_norm_sums_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(norms, sums, (int)N);
+  INDM_CHECK_LAUNCH("langevin_norm_sums");
+  return INDM_OK;
+}
+
+extern "C" int indm_langevin_update_global(float* x, const float* s, const float* z, float* x_mean, const float* gsums, const float* coef,
+                                           int coef_ld, const int32_t* step, int64_t N, int64_t D, uint64_t seed, const uint64_t* seed_dev,
+                                           uint64_t rng_offset, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(x && s && gsums && coef && N > 0 && D > 0 && coef_ld >= 2, "langevin_update_global: bad arguments");
+  INDM_CHECK_ARG((N * D) % 4 == 0, "langevin_update_global: N*D must be a multiple of 4");
+  const long long total4 = N * D / 4;
+  langevin_update_kernel<<<ew_grid(total4), 256, 0, stream>>>(x, s, z, x_mean, nullptr, gsums, coef, coef_ld, step, (int)N, total4, seed,
+                                                             seed_dev, (uint32_t)rng_offset);
+  INDM_CHECK_LAUNCH("langevin_update_global");
   return INDM_OK;
 }
 

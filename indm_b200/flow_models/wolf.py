@@ -330,6 +330,7 @@ class _FlowTrainFunction(torch.autograd.Function):
     def forward(ctx, data, anchor, core, kw):
         eng = core.engine(data.shape[0])
         z, loss = eng.train_forward(data, **kw)
+        eng.precapture_backward()
         ctx.eng, ctx.token = eng, eng.train_token
         return z, loss
 
@@ -338,6 +339,9 @@ class _FlowTrainFunction(torch.autograd.Function):
         eng = ctx.eng
         if eng.train_token != ctx.token:
             raise RuntimeError('indm_b200: the flow engine ran another training forward before this backward')
+        hook = getattr(eng.core, '_before_backward', None)
+        if hook is not None:
+            hook()
         if gz is None:
             gz = torch.zeros((eng.N,) + tuple(eng.core.input_shape), device=eng.dev)
         if gloss is None:
@@ -719,6 +723,14 @@ class FlowEngine:
         return x.reshape(shape)
 
     # ---- posterior q(h|x): BN-ResNet encoder -> weight-normed linear -> reparameterisation -> KL against the flow prior
+    def _enc_engine(self):
+        """The engine that runs the posterior encoder / fc / KL legs.  The encoder is < 2 % of the flow's work but its output decides
+        h and the KL term (20-35 nats against a log-det of ~0.03 here): BF16 operands there put 4e-3 into h and 0.03-0.1 nats into
+        the KL — the whole error of the training-mode (log-det - KL).  POLICY['flow']['encoder'] (default 'tf32') therefore runs
+        these legs on the compensated-TF32 engine of the same batch even when the iResBlocks run in BF16."""
+        want = precision.POLICY['flow'].get('encoder', self.mode) if self.core.compute_mode in (None, 'auto') else self.mode
+        return self if want == self.mode else self.core.engine(self.N, mode=want)
+
     def _build_encoder(self):
         core, N, dev = self.core, self.N, self.dev
         enc = core.config.flow.wolf_params['discriminator']['encoder']
@@ -811,6 +823,9 @@ class FlowEngine:
 
     def posterior(self, x, eps=None, seed=0, offset=0):
         """GaussianDiscriminator.sampling_and_KL (gaussian.py:67-76) with nsamples = 1: returns (h [N,64], KL [N])."""
+        enc = self._enc_engine()
+        if enc is not self:
+            return enc.posterior(x, eps=eps, seed=seed, offset=offset)
         self._ensure()
         if not hasattr(self, 'enc'):          # built on first use: sampling-only callers never need the posterior encoder
             self._build_encoder()
@@ -849,6 +864,11 @@ class FlowEngine:
     def train_posterior(self, x, eps=None, seed=0, offset=0):
         """GaussianDiscriminator.sampling_and_KL in training mode: batch-statistics encoder -> fc -> h ~ q(h|x), KL"""
         from .wolf_encoder_train import EncoderTrain
+        enc = self._enc_engine()
+        if enc is not self:
+            h, kl = enc.train_posterior(x, eps=eps, seed=seed, offset=offset)
+            self._train_saved = enc._train_saved
+            return h, kl
         self._ensure()
         if not hasattr(self, 'enc'):
             self._build_encoder()
@@ -881,23 +901,49 @@ class FlowEngine:
         self._train_saved = (h, c, eps_s, enc_out)
         return h, kl
 
-    def train_backward(self, gz, gloss):
-        """gz = d L / d z, gloss [N] = d L / d (logdet - KL): runs the residual-flow, KL / posterior-head and encoder backward plans"""
+    def _bwd_key(self):
+        anchor = next(p for p in self.core.parameters() if p.requires_grad)
+        return ('bwd', anchor.grad.data_ptr() if anchor.grad is not None else 0, tuple(x[0] for x in self._saved))
+
+    def _bwd_body(self):
         from .wolf_backward import FlowBackward, PosteriorBackward
+        enc = self._enc_engine()
         if not hasattr(self, '_fbw'):
-            self._fbw, self._pbw = FlowBackward(self), PosteriorBackward(self)
+            self._fbw, self._pbw = FlowBackward(self), PosteriorBackward(enc)
         h, c, eps, enc_out = self._train_saved
+        gz_s, gl_s = self._bufs['bw_gz'], self._bufs['bw_gl']
+        _, gh_blocks = self._fbw.run(gz_s, gl_s)
+        g_enc = self._pbw.run(h, gh_blocks, -gl_s, c, eps, enc_out)
+        enc.enc_train.backward(g_enc)
+
+    def train_backward(self, gz, gloss):
+        """gz = d L / d z, gloss [N] = d L / d (logdet - KL): runs the residual-flow, KL / posterior-head and encoder backward plans.
+        The whole flow backward is a fixed launch sequence (~1600 launches) over engine-owned buffers: one CUDA graph, keyed by
+        where the gradients live.  autograd calls this from its worker thread, where stream capture gets invalidated — the graph
+        is therefore captured ahead of time on the main thread (`precapture_backward`, called at the end of the training forward once
+        the eager first run has built the launch lists) and only REPLAYED here."""
         gz_s, gl_s = self._static('bw_gz', gz), self._static('bw_gl', gloss)
         gz_s.copy_(gz)
         gl_s.copy_(gloss)
+        self._graphed(self._bwd_key(), self._bwd_body)
 
-        def body():
-            _, gh_blocks = self._fbw.run(gz_s, gl_s)
-            g_enc = self._pbw.run(h, gh_blocks, -gl_s, c, eps, enc_out)
-            self.enc_train.backward(g_enc)
-        # the whole flow backward is a fixed launch sequence (~1600 launches): one graph, keyed by where the gradients live
-        anchor = next(p for p in self.core.parameters() if p.requires_grad)
-        self._graphed(('bwd', anchor.grad.data_ptr() if anchor.grad is not None else 0, tuple(x[0] for x in self._saved)), body)
+    def precapture_backward(self):
+        """main thread, after train_forward: capture (without running) the backward graph for the buffers of this forward, if the
+        plan has run eagerly once and no graph exists yet"""
+        if not self.use_graphs or threading.current_thread() is not threading.main_thread() or torch.cuda.is_current_stream_capturing():
+            return
+        if 'bw_gz' not in self._bufs or not self._saved:
+            return
+        key = self._bwd_key()
+        if self._graphs.get(key) != 1:
+            return
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(g, pool=self._pool):
+            self._bwd_body()
+        self._graphs[key] = g
 
     # ---- power-series log-det (iresblock.py:90-174): VJP chain of g on the tensor cores
     def _g_store(self, i, s, m, x_nchw, out):

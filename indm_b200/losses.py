@@ -69,15 +69,41 @@ class FusedAdamW(torch.optim.Optimizer):
         self._skip_idx = torch.tensor(skip, dtype=torch.int64, device=dev) if skip else None
         self.steps = 0
         self.max_norm = -1.0          # set by optimize_fn (losses.py:58-59); < 0 disables clipping
+        self.fused_ema = None         # an ExponentialMovingAverage over the same parameters: its update rides in the AdamW kernel
         L.param_epoch += 1
+
+    def attach_ema(self, ema):
+        """The step functions call `optimize_fn(...)` and then `ema.update(params)` (losses.py:311-316): with the EMA attached, the
+        AdamW kernel applies shadow -= (1 - decay) (shadow - p) to the freshly updated parameter in the same pass (one read of p less,
+        one launch less) and the following `ema.update` only advances its counter."""
+        ok = ema is not None and getattr(ema, '_flat', None) is not None and ema._flat.numel() == self.flat_p.numel() and ema._flat.is_cuda
+        self.fused_ema = ema if ok else None
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
+        self._reduced = False
+
+    def start_allreduce(self):
+        """Data-parallel exchange of this optimiser's flat gradient buffer, started EARLY on a side stream: the joint step calls it
+        when the score network's backward is complete and the flow's backward is about to be queued, so the NCCL all-reduce of the
+        62.8 M score gradients runs under the flow backward instead of after it.  `step` then only waits for the side stream."""
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+            return
+        if getattr(self, '_comm', None) is None:
+            self._comm = torch.cuda.Stream()
+        self._comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm):
+            torch.distributed.all_reduce(self.flat_g)
+            self.flat_g.div_(torch.distributed.get_world_size())
+        self._reduced = True
 
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        if getattr(self, '_reduced', False):
+            torch.cuda.current_stream().wait_stream(self._comm)       # the exchange was started early (start_allreduce)
+            self._reduced = False
+        elif torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(self.flat_g)                 # NCCL over NVLink: SUM, then the mean
             self.flat_g.div_(torch.distributed.get_world_size())
         self.steps += 1
@@ -88,11 +114,20 @@ class FusedAdamW(torch.optim.Optimizer):
             sumsq = self._sumsq
         b1, b2 = g['betas']
         keep = self.flat_p.index_select(0, self._skip_idx) if self._skip_idx is not None else None
-        L.call('indm_adamw_ema_f32', L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), None,
+        ema, ema_ptr, decay = self.fused_ema, None, 0.0
+        if ema is not None:
+            decay = ema.next_decay()
+            ema_ptr = L.ptr(ema._flat)
+            keep_ema = ema._flat.index_select(0, self._skip_idx) if self._skip_idx is not None else None
+        L.call('indm_adamw_ema_f32', L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), ema_ptr,
                self.flat_p.numel(), float(g['lr']), float(b1), float(b2), float(g['eps']), float(g['weight_decay']), self.steps,
-               L.ptr(sumsq), float(self.max_norm), 0.0)
+               L.ptr(sumsq), float(self.max_norm), float(decay))
         if keep is not None:          # zero gradient, zero moments: the kernel only applied the weight decay; undo it
             self.flat_p.index_copy_(0, self._skip_idx, keep)
+            if ema is not None:       # their shadow is their (constant) value: restore what the pass blended with the decayed value
+                ema._flat.index_copy_(0, self._skip_idx, keep_ema)
+        if ema is not None:
+            ema.fused_update_done()
         L.param_epoch += 1            # engines repack their operand copies of the weights on next use
 
     def state_dict(self):
@@ -276,6 +311,10 @@ def get_step_fn(config, sde, train, optimize_fn=None, scaler=None):
         yT = meanT + stdT[:, None, None, None] * torch.randn_like(batch)
         return sde.prior_logp(yT)
 
+    def _attach(optimizer, st):
+        if isinstance(optimizer, FusedAdamW):
+            optimizer.attach_ema(st.get('ema'))
+
     def step_fn(state, flow_state, batch, **kw):
         """losses.py:227-256: one optimisation step of the score network (flow.model == 'identity')."""
         model, optimizer = state['model'], state['optimizer']
@@ -290,6 +329,7 @@ def get_step_fn(config, sde, train, optimize_fn=None, scaler=None):
                 (torch.mean(losses) / 1.0).backward()
             losses_[sl] = losses.detach().cpu()
         if train:
+            _attach(optimizer, state)
             optimize_fn(optimizer, model.parameters(), step=state['step'])
             state['step'] += 1
             state['ema'].update(model.parameters())
@@ -366,16 +406,25 @@ def get_step_fn(config, sde, train, optimize_fn=None, scaler=None):
         if not fid_variant:
             if train:
                 flow_model.train()
-                for sl in mbs:
+                dev_rows = []         # per-micro-batch loss vectors stay on the device: ONE read-back per step, after the optimiser
+                core = flow_model.module if hasattr(flow_model, 'module') else flow_model
+                for k_mb, sl in enumerate(mbs):   # launches are queued (the reference syncs four times per micro-batch, losses.py:306-309)
                     _, losses_score, losses_flow, losses_logp = _flow_losses(model, flow_model, batch[sl], flow_kw, logp_noise, D,
                                                                              st=config.training.st, **kw)
                     losses = losses_score + losses_flow + losses_logp
+                    # last micro-batch: when autograd reaches the flow, the score network's gradients are final -> start their
+                    # all-reduce on a side stream so that it overlaps the flow backward
+                    last = k_mb == len(mbs) - 1 and isinstance(optimizer, FusedAdamW)
+                    core._before_backward = optimizer.start_allreduce if last else None
                     torch.mean(losses).backward()
-                    losses_[sl] = losses.detach().cpu()
-                    losses_score_[sl], losses_flow_[sl], losses_logp_[sl] = (losses_score.detach().cpu(), losses_flow.detach().cpu(),
-                                                                             losses_logp.detach().cpu())
+                    core._before_backward = None
+                    dev_rows.append(torch.stack([losses.detach(), losses_score.detach(), losses_flow.detach(), losses_logp.detach()]))
+                _attach(optimizer, state)
+                _attach(flow_optimizer, flow_state)
                 optimize_fn(optimizer, model.parameters(), step=state['step'])
                 optimize_fn(flow_optimizer, flow_model.parameters(), step=flow_state['step'])
+                host = torch.cat(dev_rows, dim=1).cpu()
+                losses_, losses_score_, losses_flow_, losses_logp_ = host[0].clone(), host[1].clone(), host[2].clone(), host[3].clone()
             # update_lipschitz(flow_model) (losses.py:313) only touches spectral / induced-norm layers: a no-op for LopConv2d
             state['step'] += 1
             state['ema'].update(model.parameters())

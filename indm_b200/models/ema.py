@@ -42,6 +42,18 @@ class ExponentialMovingAverage:
             self.shadow_params.append(s)
             off += p.numel()
         self.collected_params = []
+        self._fused_done = False
+
+    def next_decay(self):
+        """the decay the next `update` call will use (models/ema.py:38-41)"""
+        if self.num_updates is None:
+            return self.decay
+        n = self.num_updates + 1
+        return min(self.decay, (1 + n) / (10 + n))
+
+    def fused_update_done(self):
+        """the optimiser kernel already applied the next update (losses.FusedAdamW.attach_ema): the next `update` only counts it"""
+        self._fused_done = True
 
     def update(self, parameters):
         """models/ema.py:32-51: shadow -= (1 - decay) * (shadow - param), decay = min(decay, (1 + n) / (10 + n))"""
@@ -49,6 +61,9 @@ class ExponentialMovingAverage:
         if self.num_updates is not None:
             self.num_updates += 1
             decay = min(decay, (1 + self.num_updates) / (10 + self.num_updates))
+        if self._fused_done:
+            self._fused_done = False
+            return
         params = [p for p in parameters if p.requires_grad]
         if not params:
             return

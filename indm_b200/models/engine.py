@@ -63,6 +63,7 @@ class ScoreEngine:
         self._repack_graph, self._repack_key = None, None
         self.forward_count = 0    # bumped by every forward(): lets a pending backward detect overwritten activations
         self._drop_on = False
+        self._bwd_graphs, self._bwd_ran = {}, set()   # {train flag: (CUDA graph of the backward plan, key)}; plans that ran eagerly once
         self._build()
         self.load_weights()
 
@@ -887,9 +888,39 @@ class ScoreEngine:
         if self._weights_version != self.weights_version():
             self.load_weights()
         self.gout.copy_(v)
-        for op in self.bops:
-            op()
+        g = self._bwd_graphs.get(train)
+        if g is not None and g[1] == self._bwd_graph_key(train):
+            g[0].replay()             # captured ahead of time on the main thread (precapture_backward); autograd only replays
+        else:
+            for op in self.bops:
+                op()
+            self._bwd_ran.add(train)
         return self.gx
+
+    def _bwd_graph_key(self, train):
+        return tuple(ptr for _, ptr in self._plans[train]['pgrads']) if train else ()
+
+    def precapture_backward(self, train=False):
+        """Called on the main thread right after a forward whose backward will be asked for (models/ncsnpp.py:_EngineFunction): the
+        backward plan (~800 launches) becomes one CUDA graph once it has run eagerly (that first run builds weight packs and lazily
+        sized buffers).  torch.autograd invokes `vjp` from its worker thread, where a capture would be invalidated and ~800 eager
+        launches per call bound the step on the host; a replay has neither problem."""
+        import threading
+        if train not in self._bwd_ran or threading.current_thread() is not threading.main_thread() or torch.cuda.is_current_stream_capturing():
+            return
+        key = self._bwd_graph_key(train)
+        g = self._bwd_graphs.get(train)
+        if g is not None and g[1] == key:
+            return
+        if self._weights_version != self.weights_version():
+            self.load_weights()
+        self.build_backward(train)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for op in self.bops:
+                op()
+        self._bwd_graphs[train] = (graph, key)
 
     # ------------------------------------------------------------------ execution
     def launch(self, temb_op=None):

@@ -24,6 +24,7 @@ class _EngineFunction(torch.autograd.Function):
     def forward(ctx, x, time_cond, scale, net, train, anchor):
         eng = net.engine(x.shape[0])
         out = eng.forward(x.float(), time_cond.float(), scale, train=train).clone()
+        eng.precapture_backward(train)
         ctx.eng, ctx.token, ctx.train, ctx.need_x = eng, eng.forward_count, train, x.requires_grad
         return out
 

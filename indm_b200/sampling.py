@@ -312,6 +312,12 @@ class _GraphedPC:
         self.x = eng.x_in                                # the sampler state IS the network input buffer (no copies)
         self.x_mean = torch.zeros_like(self.x)
         self.norms = torch.zeros((batch, 2), device=self.dev)
+        # sampling.global_langevin_norms: batch-sharded sampling with the Langevin step size taken from the GLOBAL batch means of
+        # the gradient / noise norms (sampling.py:286-288 takes .mean() over the whole batch): three floats all-reduced per
+        # corrector step on the sampling stream (NCCL; inside the captured graph).  Off = per-rank statistics, no communication.
+        self.global_norms = bool(getattr(config.sampling, 'global_langevin_norms', False)) and \
+            torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        self.gsums = torch.zeros((3,), device=self.dev)
         self.step = torch.zeros((1,), dtype=torch.int32, device=self.dev)
         self.seed_dev = torch.zeros((1,), dtype=torch.int64, device=self.dev)   # read by the kernels: graph-replay safe
         self.sched = None
@@ -350,6 +356,12 @@ class _GraphedPC:
                 self._fill_scale()
                 eng.launch(self._temb_op)
                 L.call('indm_langevin_norms', L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.norms), L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
+                if self.global_norms:
+                    L.call('indm_langevin_norm_sums', L.ptr(self.norms), L.ptr(self.gsums), N)
+                    torch.distributed.all_reduce(self.gsums)
+                    L.call('indm_langevin_update_global', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.x_mean), L.ptr(self.gsums),
+                           L.ptr(self.sched[:, 5:]), self.LD, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
+                    continue
                 L.call('indm_langevin_update', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.x_mean), L.ptr(self.norms),
                        L.ptr(self.sched[:, 5:]), self.LD, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
         elif self.ald:
@@ -444,7 +456,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
         return s
 
     def _graph(net, seed):
-        key = (shape[0], pred_name, corr_name, n_steps, probability_flow, _sde_key())
+        key = (shape[0], pred_name, corr_name, n_steps, probability_flow, _sde_key(), bool(getattr(config.sampling, 'global_langevin_norms', False)))
         cache = net.__dict__.setdefault('_pc_graphs', {})
         g = cache.get(key)
         if g is None:

@@ -15,6 +15,7 @@
 // Deliberately simple otherwise: one CTA per tile, one accumulator, 4 epilogue warps storing bf16 rows straight from registers.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "../common.cuh"
 #include "../tmap.cuh"
@@ -32,6 +33,7 @@ struct HaloParams {
   uint32_t box_bytes;    // bytes one TMA box delivers: (R + 2) Wp rows of 128 B
   const float* bias;
   __nv_bfloat16* out;
+  int variant;   // 0: descriptor base-offset field = (start >> 7) & 7;  1: base-offset 0 (swizzle taken from the absolute address)
 };
 
 __device__ __forceinline__ uint64_t desc_sw128_rowoff(uint32_t smem_addr) {
@@ -117,7 +119,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         if (elect_one()) {
           const int ty = tap / 3, tx = tap - 3 * ty;
-          const uint64_t adesc = desc_sw128_rowoff(a_base + (uint32_t)(ty * p.Wp + tx) * 128u);
+          const uint32_t a_addr = a_base + (uint32_t)(ty * p.Wp + tx) * 128u;
+          const uint64_t adesc = p.variant == 0 ? desc_sw128_rowoff(a_addr) : umma_desc_sw128(a_addr);
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (size_t)s * kBBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
@@ -185,6 +188,7 @@ extern "C" int indm_exp_conv3x3_halo_bf16(const void* x, const void* wpack, cons
   p.halo_bytes = (((uint32_t)(2 * p.Wp + 2 + kTileM) * 128u) + 1023u) & ~1023u;
   p.bias = bias;
   p.out = (__nv_bfloat16*)out;
+  { const char* e = getenv("INDM_HALO_VARIANT"); p.variant = e ? atoi(e) : 1; }
   INDM_CHECK_ARG(p.R + 2 <= 256 && p.box_bytes <= p.halo_bytes, "exp_conv3x3_halo: box does not fit the halo buffer");
   CUtensorMap tmA, tmB;
   {

@@ -142,7 +142,8 @@ constexpr int igemm_threads(bool tf32) { return 64 + 32 * epi_warps(tf32) + (tf3
 template <int BLOCK_N, bool TF32, int KIND, bool CTA2>
 __global__ void __launch_bounds__(igemm_threads(TF32), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+             const __grid_constant__ CUtensorMap tmOut, const IgemmParams p) {
   constexpr int KCHUNK = TF32 ? 32 : 64;           // elements per 128-byte swizzle row
   constexpr int A_BYTES = kTileM * 128;            // 16 KB
   constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128;   // rows of B staged by THIS CTA
@@ -153,6 +154,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int NSLAB = BLOCK_N / 32 + (BLOCK_N < 32 ? 1 : 0);
   constexpr int EPI = epi_warps(TF32);
   constexpr int SLAB_STEP = EPI / 4;               // warps per TMEM lane quarter
+  // KIND 5 / 6 = KIND 1 / 2 with the slab leaving through a TMA store: the warp keeps the accumulator's own layout (row = lane),
+  // writes its 32 x 32 slab into a swizzled staging tile and one elected lane issues cp.async.bulk.tensor — no transpose, no
+  // per-thread global addressing, no store instructions (the transposed epilogue spent ~1000 instructions per slab there)
+  constexpr bool TSTORE = KIND == 5 || KIND == 6;
+  constexpr int EK = KIND == 5 ? 1 : (KIND == 6 ? 2 : KIND);      // the epilogue feature set
+  constexpr int STG_BYTES = TSTORE ? 8192 : 4096;                 // per epilogue warp (TSTORE: two buffers)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -161,7 +168,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* sAlo = sB + (size_t)p.stages * B_BYTES;
   uint8_t* sBlo = sAlo + (TF32 ? (size_t)p.stages * A_BYTES : 0);
   uint8_t* sStage = sBlo + (TF32 ? (size_t)p.stages * B_BYTES : 0);   // one 4 KB transpose buffer per epilogue warp
-  uint64_t* bars = (uint64_t*)(sStage + EPI * 4096);
+  uint64_t* bars = (uint64_t*)(sStage + EPI * STG_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* split_bar = bars + 2 * kMaxStages;
@@ -187,6 +194,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TSTORE) tma_prefetch_desc(&tmOut);
     if (p.chunks2 > 0) {
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
@@ -386,18 +394,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else {
     // ================= epilogue warps
     const bool has_bias = p.bias != nullptr;
-    const bool has_rowbias = (KIND == 2 || KIND == 4) ? false : (p.rowbias != nullptr);
-    const bool has_res = (KIND == 1 || KIND == 3 || KIND == 4) ? false : (p.residual != nullptr);
-    const bool has_rowscale = KIND ? false : (p.rowscale != nullptr);
-    const bool has_aux = (KIND == 0 || KIND == 3) ? (p.aux_cos != nullptr) : false;
-    const int act = (KIND == 0 || KIND == 3) ? p.act : 0;
-    const bool has_mul = KIND == 4 ? true : (KIND == 0 ? (p.mul != nullptr) : false);
-    const bool st_f32 = KIND == 2 ? true : (KIND == 0 ? p.out_f32 != nullptr : false);
-    const bool st_bf16 = KIND == 2 ? false : (KIND == 0 ? p.out_bf16 != nullptr : true);
+    const bool has_rowbias = (EK == 2 || EK == 4) ? false : (p.rowbias != nullptr);
+    const bool has_res = (EK == 1 || EK == 3 || EK == 4) ? false : (p.residual != nullptr);
+    const bool has_rowscale = EK ? false : (p.rowscale != nullptr);
+    const bool has_aux = (EK == 0 || EK == 3) ? (p.aux_cos != nullptr) : false;
+    const int act = (EK == 0 || EK == 3) ? p.act : 0;
+    const bool has_mul = EK == 4 ? true : (EK == 0 ? (p.mul != nullptr) : false);
+    const bool st_f32 = EK == 2 ? true : (EK == 0 ? p.out_f32 != nullptr : false);
+    const bool st_bf16 = EK == 2 ? false : (EK == 0 ? p.out_bf16 != nullptr : true);
     const bool has_gn = p.gn_partial != nullptr;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;             // which of the SLAB_STEP warps sharing the quarter: takes slabs half, half + SLAB_STEP, ...
-    float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * 4096);
+    float4* stg = reinterpret_cast<float4*>(sStage + (size_t)(warp - 2) * STG_BYTES);
+    int tbuf = 0;                                 // TSTORE: staging buffer of the next slab
     const int chunk = lane & 7, rsub = lane >> 3;  // transposed domain: 4 columns (chunk), rows it*4 + rsub
     const long long hw = (long long)p.H * p.W;
     int j = 0;
@@ -434,6 +443,149 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
       for (int sl = half; sl < NSLAB; sl += SLAB_STEP) {
         const int c0 = ncol0 + sl * 32;
+        if (TSTORE) {
+          // ======== row = lane epilogue with a TMA store (KIND 5: bf16 NHWC; KIND 6: fp32 NHWC + residual)
+          if (c0 >= p.Cout) {                    // uniform: a slab past the last channel only releases the buffer
+            if (sl + SLAB_STEP >= NSLAB) {
+              tc_fence_before();
+              if (CTA2) mbar_arrive_leader(&tempty_bar[buf]);
+              else mbar_arrive(&tempty_bar[buf]);
+            }
+            continue;
+          }
+          // the residual row of this thread (32 consecutive floats) is requested before the accumulator leaves TMEM
+          float4 rsd[8];
+          if (EK == 2 && has_res && !(p.dbg & 1)) {
+            const float* rp = p.residual + (ed.ok ? ed.pix : 0) * p.res_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rsd[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
+          }
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)(sl * 32), v);
+          tmem_ld_wait();
+          if (sl + SLAB_STEP >= NSLAB) {
+            tc_fence_before();
+            if (CTA2) mbar_arrive_leader(&tempty_bar[buf]);
+            else mbar_arrive(&tempty_bar[buf]);
+          }
+          if (p.dbg & 1) continue;               // development probe: accumulator drained, nothing computed or stored
+          // the staging buffer about to be written was handed to a TMA store two slabs ago: wait until that store has read it
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg) + tbuf * 4096;
+          const float* rbp = (EK == 1 && has_rowbias) ? p.rowbias + (long long)(ed.ok ? ed.n : 0) * p.rowbias_ld + c0 : nullptr;
+          const float okf = ed.ok ? 1.0f : 0.0f;
+          float s4[8], q4[8];                    // per 4-channel chunk: sum / sum of squares of this row's stored values
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (has_bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (EK == 1 && has_rowbias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rbp + 4 * j));
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            x.x *= p.scale; x.y *= p.scale; x.z *= p.scale; x.w *= p.scale;
+            if (EK == 2 && has_res) {
+              x.x += p.res_scale * rsd[j].x; x.y += p.res_scale * rsd[j].y; x.z += p.res_scale * rsd[j].z; x.w += p.res_scale * rsd[j].w;
+            }
+            if (has_gn) {
+              s4[j] = okf * ((x.x + x.y) + (x.z + x.w));
+              q4[j] = okf * ((x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w));
+            }
+            if (EK == 2) {
+              // fp32 rows of 128 B, SWIZZLE_128B: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
+              *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = x;
+            } else if (j & 1) {
+              // bf16 rows of 64 B, SWIZZLE_64B: chunk (j >> 1) of row `lane` lives at chunk (j >> 1) ^ ((lane >> 1) & 3)
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[4 * j - 4]), __uint_as_float(v[4 * j - 3]));
+              o.y = pack_bf16x2(__uint_as_float(v[4 * j - 2]), __uint_as_float(v[4 * j - 1]));
+              o.z = pack_bf16x2(x.x, x.y);
+              o.w = pack_bf16x2(x.z, x.w);
+              *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((((j >> 1) ^ (lane >> 1)) & 3) << 4)) = o;
+            } else {
+              // even chunk: park the finished values in v[] for the pack of the following odd chunk
+              v[4 * j] = __float_as_uint(x.x); v[4 * j + 1] = __float_as_uint(x.y);
+              v[4 * j + 2] = __float_as_uint(x.z); v[4 * j + 3] = __float_as_uint(x.w);
+            }
+          }
+          fence_proxy_async_smem();              // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            const int r0 = q * 32;
+            tma_store_4d(&tmOut, sbuf, c0, x0 + (r0 & (p.BW - 1)), y0 + ((r0 >> p.bw_shift) & (p.BH - 1)),
+                         n0 + (r0 >> (p.bw_shift + p.bh_shift)));
+            tma_store_commit();
+          }
+          tbuf ^= 1;
+          if (has_gn) {
+            // 16 per-row partial sums -> sums over the warp's 32 rows by recursive halving: after the step with lane mask m a lane
+            // keeps the half of the values selected by its bit m, so 8 + 4 + 2 + 1 shuffles leave ONE value per lane (lane bits
+            // 4..1 = its index: bit 4 = sum / sum of squares, bits 3..1 = chunk), and a last exchange with lane ^ 1 completes it
+            float a8[8];
+            {
+              const bool hi = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = hi ? s4[i] : q4[i];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                a8[i] = (hi ? q4[i] : s4[i]) + recv;
+              }
+            }
+            float a4[4];
+            {
+              const bool hi = (lane & 8) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = hi ? a8[i] : a8[i + 4];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                a4[i] = (hi ? a8[i + 4] : a8[i]) + recv;
+              }
+            }
+            float a2[2];
+            {
+              const bool hi = (lane & 4) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = hi ? a4[i] : a4[i + 2];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                a2[i] = (hi ? a4[i + 2] : a4[i]) + recv;
+              }
+            }
+            float a1;
+            {
+              const bool hi = (lane & 2) != 0;
+              const float send = hi ? a2[0] : a2[1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+              a1 = (hi ? a2[1] : a2[0]) + recv;
+            }
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            // this lane now holds: (lane bit 4 ? sum of squares : sum) of chunk ((lane >> 1) & 7) over the warp's 32 rows
+            const int chunk_id = (lane >> 1) & 7;
+            const int isq = (lane >> 4) & 1;
+            const int nn = n0 + (q * 32) / (p.BW * p.BH);
+            const int cc = c0 + chunk_id * 4;
+            {
+              float t1 = a1;
+              const int cq = p.gn_cpg >> 2;             // chunks per group: 1, 2, 4 or 8 (adjacent chunks = lane bits 1..3)
+              for (int o = 1; o < cq; o <<= 1) t1 += __shfl_xor_sync(0xffffffffu, t1, o << 1);
+              if ((lane & 1) == 0 && (chunk_id & (cq - 1)) == 0 && nn < p.N)
+                atomicAdd(p.gn_partial + ((long long)nn * p.gn_groups + p.gn_goff + cc / p.gn_cpg) * 2 + isq, t1);
+            }
+            if (p.gn2_partial) {
+              float t2 = a1;
+              const int cq = p.gn2_cpg >> 2;
+              for (int o = 1; o < cq; o <<= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o << 1);
+              if ((lane & 1) == 0 && (chunk_id & (cq - 1)) == 0 && nn < p.N)
+                atomicAdd(p.gn2_partial + ((long long)nn * p.gn2_groups + p.gn2_goff + cc / p.gn2_cpg) * 2 + isq, t2);
+            }
+          }
+          continue;
+        }
         const bool direct = KIND ? false : ((p.out_mode == 1) || (p.out_mode == 2 && c0 >= p.tcol0));
         const int c = c0 + chunk * 4;           // first of this thread's 4 columns in the transposed domain
         const bool fast = !direct && c0 < p.Cout && (KIND != 0 || c + 4 <= p.Cout);
@@ -641,6 +793,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
+  if (TSTORE && warp >= 2 && warp < 2 + EPI && lane == 0) tma_store_wait_all<0>();   // this lane's bulk stores are complete
   tc_fence_before();
   if (CTA2) {
     cluster_sync_all();          // neither CTA may retire (or free TMEM) while the peer still reads its smem / signals its barriers
@@ -707,12 +860,12 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, int S, long l
 }
 
 template <int BLOCK_N, bool TF32, int KIND, bool CTA2 = false>
-int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2, IgemmParams p,
-                 int m_tiles, int n_tiles, cudaStream_t stream) {
+int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2, const CUtensorMap& tout,
+                 IgemmParams p, int m_tiles, int n_tiles, cudaStream_t stream) {
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128;
   const int stage_bytes = (A_BYTES + B_BYTES) * (TF32 ? 2 : 1);
-  const int overhead = 1024 + epi_warps(TF32) * 4096 + (3 * kMaxStages + 6) * 8;
+  const int overhead = 1024 + epi_warps(TF32) * ((KIND == 5 || KIND == 6) ? 8192 : 4096) + (3 * kMaxStages + 6) * 8;
   // one persistent CTA per SM: the smem ring takes what the SM has
   int stages = (220 * 1024 - overhead) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -734,13 +887,13 @@ int launch_igemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& 
     const long long pairs = (long long)((m_tiles + 1) / 2) * n_tiles;
     const int half_sms = indm_num_sms() / 2;
     const int grid = 2 * (int)(pairs < half_sms ? pairs : half_sms);
-    indm_launch_pdl_cluster2(kern, dim3(grid), dim3(igemm_threads(TF32)), (size_t)smem, stream, a, b, a2, b2, p);
+    indm_launch_pdl_cluster2(kern, dim3(grid), dim3(igemm_threads(TF32)), (size_t)smem, stream, a, b, a2, b2, tout, p);
     INDM_CHECK_LAUNCH("igemm (CTA pair)");
     return INDM_OK;
   }
   const long long total = (long long)m_tiles * n_tiles * p.ksplit;
   const int grid = (int)(total < indm_num_sms() ? total : indm_num_sms());
-  indm_launch_pdl(kern, dim3(grid), dim3(igemm_threads(TF32)), (size_t)smem, stream, a, b, a2, b2, p);
+  indm_launch_pdl(kern, dim3(grid), dim3(igemm_threads(TF32)), (size_t)smem, stream, a, b, a2, b2, tout, p);
   INDM_CHECK_LAUNCH("igemm");
   return INDM_OK;
 }
@@ -846,7 +999,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
 
   // ---- tensor maps
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap tmA, tmB, tmA2, tmB2;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmOut;
   {
     const long long ld = d->a_ld ? d->a_ld : d->Cin;
     // stride 2: the A grid is the (2H+1) x (2W+1) FIR-padded image (models/up_or_down_sampling.py:173-178), H x W the output grid
@@ -919,10 +1072,36 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
                        (block_n == 128 || block_n == 256);
   if (flowish && !d->mul && (d->act != 0 || d->aux_cos)) kind = 3;
   if (flowish && d->mul && !d->bias && !d->rowbias && d->act == 0 && !d->aux_cos) kind = 4;
+  // TMA-store epilogue (KIND 5 / 6) for the plain kinds when every 32-row slab of the tile is a rectangular box of the output
+  // grid: the tile decomposes exactly (BW BH BN = 128, all powers of two) and the output rows are 16-byte aligned
+  static const bool tstore_enabled = []() { const char* e = getenv("INDM_IGEMM_TSTORE"); return !(e && e[0] == '0'); }();
+  bool tstore = false;
+  if (tstore_enabled && (kind == 1 || kind == 2) && p.ksplit == 1 && p.BW * p.BH * p.BN == 128) {
+    const bool f32o = kind == 2;
+    const void* obase = f32o ? (const void*)d->out_f32 : (const void*)d->out_bf16;
+    const long long old_ = d->out_ld ? d->out_ld : d->Cout;
+    const int oes = f32o ? 4 : 2;
+    if (((uintptr_t)obase & 15) == 0 && (old_ * oes) % 16 == 0 &&
+        (!d->residual || ((((uintptr_t)d->residual) & 15) == 0 && ((d->res_ld ? d->res_ld : d->Cout) % 4) == 0)) &&
+        (!d->rowbias || ((((uintptr_t)d->rowbias) & 15) == 0 && (d->rowbias_ld % 4) == 0)) && (!d->bias || (((uintptr_t)d->bias) & 15) == 0)) {
+      const int sbw = p.BW < 32 ? p.BW : 32;
+      const int sbh = p.BH < 32 / sbw ? p.BH : 32 / sbw;
+      const int sbn = 32 / (sbw * sbh);
+      const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+      const uint64_t str[3] = {(uint64_t)old_ * oes, (uint64_t)d->W * old_ * oes, (uint64_t)d->H * d->W * old_ * oes};
+      const uint32_t box[4] = {32u, (uint32_t)sbw, (uint32_t)sbh, (uint32_t)sbn};
+      int rc = indm_make_tmap(&tmOut, f32o ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, obase, dims, str, box,
+                              "igemm out", nullptr, f32o ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      tstore = true;
+      kind = kind == 1 ? 5 : 6;
+    }
+  }
   // CTA pairs (cta_group::2) for the launches that fill the chip: wide tiles of the plain BF16 convolutions
   static const bool cta2_enabled = []() { const char* e = getenv("INDM_IGEMM_CTA2"); return !(e && e[0] == '0'); }();
+  static const int cta2_min_tiles = []() { const char* e = getenv("INDM_IGEMM_CTA2_MIN_TILES"); return e ? atoi(e) : 0; }();
   const bool cta2 = cta2_enabled && !tf32 && p.ksplit == 1 && !d->batched_b && (block_n == 128 || block_n == 256) &&
-                    (long long)m_tiles * n_tiles >= indm_num_sms();
+                    (long long)m_tiles * n_tiles >= (cta2_min_tiles > 0 ? cta2_min_tiles : indm_num_sms());
   const int b_rows = cta2 ? block_n / 2 : block_n;
   {
     const long long ld = d->b_ld ? d->b_ld : d->Cin;
@@ -952,12 +1131,13 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
     tmA2 = tmA;
     tmB2 = tmB;
   }
+  if (!tstore) tmOut = tmA;     // unused by the other kinds: any valid map
 
   if (p.ksplit > 1) {
-    int rc = tf32 ? (block_n == 256 ? launch_igemm<256, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
-                                    : launch_igemm<128, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream))
-                  : (block_n == 256 ? launch_igemm<256, false, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
-                                    : launch_igemm<128, false, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream));
+    int rc = tf32 ? (block_n == 256 ? launch_igemm<256, true, 0>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream)
+                                    : launch_igemm<128, true, 0>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream))
+                  : (block_n == 256 ? launch_igemm<256, false, 0>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream)
+                                    : launch_igemm<128, false, 0>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream));
     if (rc) return rc;
     const long long work = Mpix * (d->Cout / 4);
     long long blocks = (work + 255) / 256;
@@ -972,30 +1152,34 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   }
   if (cta2) {
 #define INDM_LAUNCH2(BN_)                                                                                       \
-  if (kind == 1) return launch_igemm<BN_, false, 1, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
-  if (kind == 2) return launch_igemm<BN_, false, 2, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
-  if (kind == 3) return launch_igemm<BN_, false, 3, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
-  if (kind == 4) return launch_igemm<BN_, false, 4, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
-  return launch_igemm<BN_, false, 0, true>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+  if (kind == 5) return launch_igemm<BN_, false, 5, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 6) return launch_igemm<BN_, false, 6, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 1) return launch_igemm<BN_, false, 1, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 2) return launch_igemm<BN_, false, 2, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 3) return launch_igemm<BN_, false, 3, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 4) return launch_igemm<BN_, false, 4, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  return launch_igemm<BN_, false, 0, true>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream)
     if (block_n == 256) { INDM_LAUNCH2(256); }
     INDM_LAUNCH2(128);
 #undef INDM_LAUNCH2
   }
 #define INDM_LAUNCH(BN_)                                                                                  \
-  if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);          \
-  if (kind == 1) return launch_igemm<BN_, false, 1>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
-  if (kind == 2) return launch_igemm<BN_, false, 2>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);    \
-  return launch_igemm<BN_, false, 0>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream)
+  if (tf32) return launch_igemm<BN_, true, 0>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);          \
+  if (kind == 5) return launch_igemm<BN_, false, 5>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 6) return launch_igemm<BN_, false, 6>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 1) return launch_igemm<BN_, false, 1>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  if (kind == 2) return launch_igemm<BN_, false, 2>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);    \
+  return launch_igemm<BN_, false, 0>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream)
   switch (block_n) {
     case 32: INDM_LAUNCH(32);
     case 64: INDM_LAUNCH(64);
     case 128:
-      if (kind == 3) return launch_igemm<128, false, 3>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
-      if (kind == 4) return launch_igemm<128, false, 4>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+      if (kind == 3) return launch_igemm<128, false, 3>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);
+      if (kind == 4) return launch_igemm<128, false, 4>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);
       INDM_LAUNCH(128);
     default:
-      if (kind == 3) return launch_igemm<256, false, 3>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
-      if (kind == 4) return launch_igemm<256, false, 4>(tmA, tmB, tmA2, tmB2, p, m_tiles, n_tiles, stream);
+      if (kind == 3) return launch_igemm<256, false, 3>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);
+      if (kind == 4) return launch_igemm<256, false, 4>(tmA, tmB, tmA2, tmB2, tmOut, p, m_tiles, n_tiles, stream);
       INDM_LAUNCH(256);
   }
 #undef INDM_LAUNCH

@@ -332,9 +332,14 @@ __global__ void linear_generic_kernel(const float* __restrict__ in, const float*
 // ---------------------------------------------------------------- FIR resampling on NHWC (4-tap separable kernel)
 // MODE 1: up x2 pad (2,1); MODE 2: down x2 pad (1,1); MODE 3: up=down=1 pad (2,2); MODE 4: up=down=1 pad (1,1) (transpose of 3).
 // out[oy,ox] = sum_{i,j} xp[oy*down + i, ox*down + j] * kf[i][j], kf = flipped k, xp = zero-inserted + padded input.
+// Separable evaluation along a strip of output rows: thread = (output column ox, channel quad q); it walks RS consecutive output rows
+// keeping the four horizontally filtered rows h(uy) = sum_j kf[j] x[iy(uy)][ix(ox, j)] the vertical taps need in registers, so an
+// input pixel is loaded once per output COLUMN tap, not once per 2-D tap: 4 (plain), 8 (down x2) or ~1 (up x2) 16-byte loads per
+// output quad instead of 16 / 16 / 4, no runtime division, channel-contiguous (fully coalesced) accesses.  grid = (column tiles x
+// channel tiles, row strips, N).
 template <typename TIn, typename TOut, int MODE>
-__global__ void fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
-                                long long N, int H, int W, int C, float k0, float k1, float k2, float k3) {
+__global__ void __launch_bounds__(256) fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
+                                long long N, int H, int W, int C, float k0, float k1, float k2, float k3, int qb_log2, int RS, int ctiles) {
   pdl_trigger();
   pdl_wait();
 
@@ -344,34 +349,60 @@ __global__ void fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditi
   const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : (MODE == 4 ? H - 1 : H + 1));
   const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : (MODE == 4 ? W - 1 : W + 1));
   const int Q = C >> 2;
-  const long long total = N * Ho * Wo * Q;
   const float kf[4] = {k3, k2, k1, k0};  // flipped
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(idx % Q);
-    long long t = idx / Q;
-    const int ox = (int)(t % Wo);
-    t /= Wo;
-    const int oy = (int)(t % Ho);
-    const long long n = t / Ho;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int qb = 1 << qb_log2;                                   // channel quads per CTA (power of two)
+  const int ct = blockIdx.x % ctiles, xt = blockIdx.x / ctiles;
+  const int q = ct * qb + (threadIdx.x & (qb - 1));
+  const int ox = xt * (256 >> qb_log2) + (threadIdx.x >> qb_log2);
+  if (q >= Q || ox >= Wo) return;
+  const long long n = blockIdx.z;
+  const int oy_begin = blockIdx.y * RS;
+  const int oy_end = oy_begin + RS < Ho ? oy_begin + RS : Ho;
+  const TIn* xin = x + n * (long long)H * W * C + q * 4;
+  // column taps of this thread: input column and weight per j (invalid taps get weight 0 and a safe column)
+  int ixs[4];
+  float wj[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int uy = oy * DOWN + i - PAD0;
-      if (uy < 0 || (uy % UP) != 0) continue;
-      const int iy = uy / UP;
-      if (iy >= H) continue;
+  for (int j = 0; j < 4; ++j) {
+    const int ux = ox * DOWN + j - PAD0;
+    const bool ok = ux >= 0 && (ux % UP) == 0 && (ux / UP) < W;
+    ixs[j] = ok ? ux / UP : 0;
+    wj[j] = ok ? kf[j] : 0.f;
+  }
+  auto hrow = [&](int uy) -> float4 {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (uy < 0 || (uy % UP) != 0) return a;
+    const int iy = uy / UP;
+    if (iy >= H) return a;
+    const TIn* row = xin + (long long)iy * W * C;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ux = ox * DOWN + j - PAD0;
-        if (ux < 0 || (ux % UP) != 0) continue;
-        const int ix = ux / UP;
-        if (ix >= W) continue;
-        const float wgt = kf[i] * kf[j];
-        const float4 v = Vec4<TIn>::load(x + ((n * H + iy) * W + ix) * C + q * 4);
-        acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+    for (int j = 0; j < 4; ++j) {
+      if (wj[j] != 0.f) {
+        const float4 v = Vec4<TIn>::load(row + (long long)ixs[j] * C);
+        a.x += v.x * wj[j]; a.y += v.y * wj[j]; a.z += v.z * wj[j]; a.w += v.w * wj[j];
       }
     }
-    Vec4<TOut>::store(y + ((n * Ho + oy) * Wo + ox) * C + q * 4, acc);
+    return a;
+  };
+  int u0 = oy_begin * DOWN - PAD0;
+  float4 h0 = hrow(u0), h1 = hrow(u0 + 1), h2 = hrow(u0 + 2), h3 = hrow(u0 + 3);
+  auto* yout = y + n * (long long)Ho * Wo * C + (long long)ox * C + q * 4;
+  for (int oy = oy_begin; oy < oy_end; ++oy) {
+    float4 acc;
+    acc.x = h0.x * kf[0] + h1.x * kf[1] + h2.x * kf[2] + h3.x * kf[3];
+    acc.y = h0.y * kf[0] + h1.y * kf[1] + h2.y * kf[2] + h3.y * kf[3];
+    acc.z = h0.z * kf[0] + h1.z * kf[1] + h2.z * kf[2] + h3.z * kf[3];
+    acc.w = h0.w * kf[0] + h1.w * kf[1] + h2.w * kf[2] + h3.w * kf[3];
+    Vec4<TOut>::store(yout + (long long)oy * Wo * C, acc);
+    if (oy + 1 < oy_end) {
+      if (DOWN == 1) {
+        h0 = h1; h1 = h2; h2 = h3; h3 = hrow(u0 + 4);
+        u0 += 1;
+      } else {
+        h0 = h2; h1 = h3; h2 = hrow(u0 + 4); h3 = hrow(u0 + 5);
+        u0 += 2;
+      }
+    }
   }
 }
 
@@ -542,16 +573,25 @@ static int fir_launch(const void* x, void* y, int64_t N, int H, int W, int C, co
   using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
   const int Ho = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : (mode == 4 ? H - 1 : H + 1));
   const int Wo = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : (mode == 4 ? W - 1 : W + 1));
-  const long long total = (long long)N * Ho * Wo * (C / 4);
-  const int grid = grid_for(total, 256);
+  // CTA = 256 threads = (qb channel quads) x (256 / qb output columns); qb = largest power of two <= min(Q, 64)
+  const int Q = C / 4;
+  int qb_log2 = 0;
+  while ((2 << qb_log2) <= Q && qb_log2 < 6) ++qb_log2;
+  const int qb = 1 << qb_log2, cols = 256 >> qb_log2;
+  const int ctiles = (Q + qb - 1) / qb, xtiles = (Wo + cols - 1) / cols;
+  // strip length: long strips amortise the 3 warm-up rows; keep >= ~4 CTAs per SM
+  int RS = Ho;
+  while (RS > 8 && (long long)N * ((Ho + RS - 1) / RS) * ctiles * xtiles < 4LL * indm_num_sms()) RS = (RS + 1) / 2;
+  const dim3 grid((unsigned)(ctiles * xtiles), (unsigned)((Ho + RS - 1) / RS), (unsigned)N);
+  INDM_CHECK_ARG(N <= 65535, "fir_nhwc: N > 65535");
   if (mode == 1)
-    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 1>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 1>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   else if (mode == 2)
-    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 2>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 2>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   else if (mode == 3)
-    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 3>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 3>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   else
-    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 4>, dim3(grid), dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3]);
+    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 4>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   INDM_CHECK_LAUNCH("fir_nhwc");
   return INDM_OK;
 }

@@ -32,7 +32,8 @@ static inline indm_encode_tiled_fn indm_get_encode_tiled() {
 // (how the stride-2 convolution of the input pyramid samples every other pixel without a gather kernel).
 static inline int indm_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
                                  const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                                 const char* what, const uint32_t* elem_strides = nullptr) {
+                                 const char* what, const uint32_t* elem_strides = nullptr,
+                                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   indm_encode_tiled_fn fn = indm_get_encode_tiled();
   if (!fn) {
     indm_set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver?)", what);
@@ -59,7 +60,7 @@ static inline int indm_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int r
     }
   }
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     indm_set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", what,
                    (int)r, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),

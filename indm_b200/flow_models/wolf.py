@@ -364,6 +364,7 @@ class FlowEngine:
         self.blocks = core.blocks()
         self.nb = core.generator.flow.n_blocks
         self._version = None
+        self._version_blk = None
         self.iterations = []          # fixed-point iterations of the last reverse() call, per block
         N, idim = self.N, self.idim
         c0, h0, w0 = core.input_shape
@@ -446,8 +447,8 @@ class FlowEngine:
             self._graphs[key] = st = g
         st.replay()
 
-    def _repack_device(self):
-        """device part of the weight (re)pack: every result is written in place, so launch lists and graphs stay valid"""
+    def _repack_blocks(self):
+        """device part of the iResBlock weight (re)pack: every result is written in place, so launch lists and graphs stay valid"""
         dev = self.dev
         for i, (s, b, m) in enumerate(self.blocks):
             cv1, cv2, cv3 = m.convs()
@@ -480,20 +481,31 @@ class FlowEngine:
             w2r = self.w2f[i]
             self.cond_w[i * self.idim:(i + 1) * self.idim].copy_(w2r @ A)
             self.cond_b[i * self.idim:(i + 1) * self.idim].copy_(w2r @ a + cv2.bias.detach().to(dev, torch.float32))
+
+    def _repack_head(self):
+        """prior flow + posterior encoder / fc packs (what the encoder legs need)"""
         self._pack_prior_device()
         if hasattr(self, 'enc'):
             for job in self.enc['jobs']:
                 job()
 
-    def load_weights(self):
+    def load_weights(self, blocks=True):
+        """(re)pack after a parameter update.  The iResBlock packs (Lipschitz normalisation of 96 convolutions: ~1300 small launches
+        inside one graph, ~5 ms) are only refreshed for an engine whose block passes are about to run: the engine that only serves
+        the posterior-encoder legs of a mixed-precision training step (`_enc_engine`) skips them."""
         with torch.no_grad():
-            self._graphed(('repack', hasattr(self, 'enc')), self._repack_device)
-            self._pack_prior_host()
-            vers = tuple(m.lamb._version for (_, _, m) in self.blocks)
-            if vers != self._lamb_vers:          # lamb is not trained (iresblock.py:40): one read-back, not one per step
-                self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
-                self._lamb_vers = vers
-        self._version = self.version()
+            ver = self.version()
+            if self._version != ver:
+                self._graphed(('repack_head', hasattr(self, 'enc')), self._repack_head)
+                self._pack_prior_host()
+                vers = tuple(m.lamb._version for (_, _, m) in self.blocks)
+                if vers != self._lamb_vers:          # lamb is not trained (iresblock.py:40): one read-back, not one per step
+                    self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
+                    self._lamb_vers = vers
+                self._version = ver
+            if blocks and self._version_blk != ver:
+                self._graphed(('repack_blocks',), self._repack_blocks)
+                self._version_blk = ver
 
     def _prior_layout(self):
         """(getter list, per-step record of offsets) of the flat prior-parameter buffer; the offsets never change"""
@@ -666,9 +678,10 @@ class FlowEngine:
             ]
         self._replay(key, build)
 
-    def _ensure(self):
-        if self._version != self.version():
-            self.load_weights()
+    def _ensure(self, blocks=True):
+        ver = self.version()
+        if self._version != ver or (blocks and self._version_blk != ver):
+            self.load_weights(blocks=blocks)
 
     # ---- public passes
     def reverse(self, z, eps=None, h=None, seed=0, offset=0, atol=1e-5, rtol=1e-5, max_iter=1000):
@@ -826,7 +839,7 @@ class FlowEngine:
         enc = self._enc_engine()
         if enc is not self:
             return enc.posterior(x, eps=eps, seed=seed, offset=offset)
-        self._ensure()
+        self._ensure(blocks=False)
         if not hasattr(self, 'enc'):          # built on first use: sampling-only callers never need the posterior encoder
             self._build_encoder()
             with torch.no_grad():
@@ -869,7 +882,7 @@ class FlowEngine:
             h, kl = enc.train_posterior(x, eps=eps, seed=seed, offset=offset)
             self._train_saved = enc._train_saved
             return h, kl
-        self._ensure()
+        self._ensure(blocks=False)
         if not hasattr(self, 'enc'):
             self._build_encoder()
             with torch.no_grad():
@@ -1004,6 +1017,7 @@ class FlowEngine:
         nb = self.nb
         bi = 0
         self.vjp_count = 0
+        self.vjp_per_block = []       # VJP chains evaluated per block in this pass (bench.py counts algorithmic FLOPs from it)
         if save and not training:
             raise RuntimeError('the flow backward belongs to the training-mode (Neumann) estimator')
         self._saved = [] if save else None
@@ -1055,6 +1069,7 @@ class FlowEngine:
                 # one CUDA graph per (block, series length): the chain is ~5 (K + 2) small launches
                 self._graphed(('blk', i, K, bool(training), bool(save), float(self.lamb[i])), body)
                 self.vjp_count += K if not training else K + 1
+                self.vjp_per_block.append(K if not training else K + 1)
                 if training and save:
                     self._saved.append((i, s, m) + tuple(self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w')))
                 cur_x = 1 - cur_x

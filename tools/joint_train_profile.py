@@ -44,6 +44,7 @@ def main():
     step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
     B = 128
     batch = torch.rand(B, 3, 32, 32, device=dev) * 2 - 1
+    FlowEngine.precapture_backward = lambda self: None      # the phase timers below synchronise inside the backward: no capture here
     FlowEngine.load_weights = timed('flow repack', FlowEngine.load_weights)
     FlowEngine.train_posterior = timed('flow encoder+posterior+KL', FlowEngine.train_posterior)
     FlowEngine.forward_logdet = timed('flow blocks fwd+logdet', FlowEngine.forward_logdet)

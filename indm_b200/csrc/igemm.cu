@@ -22,6 +22,7 @@
 #include "../../include/indm_b200.h"
 #include "common.cuh"
 #include "tmap.cuh"
+#include "igemm_halo.cuh"
 
 namespace {
 
@@ -1072,6 +1073,9 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
                        (block_n == 128 || block_n == 256);
   if (flowish && !d->mul && (d->act != 0 || d->aux_cos)) kind = 3;
   if (flowish && d->mul && !d->bias && !d->rowbias && d->act == 0 && !d->aux_cos) kind = 4;
+  // 3x3 convolutions of wide feature maps: the padded-pixel kernel loads every activation box once per K chunk instead of once
+  // per tap (igemm_halo.cu)
+  if (p.ksplit == 1 && d->out_mode == 0 && indm_halo_eligible(d, kind)) return indm_igemm_halo(d, kind, stream_);
   // TMA-store epilogue (KIND 5 / 6) for the plain kinds when every 32-row slab of the tile is a rectangular box of the output
   // grid: the tile decomposes exactly (BW BH BN = 128, all powers of two) and the output rows are 16-byte aligned
   static const bool tstore_enabled = []() { const char* e = getenv("INDM_IGEMM_TSTORE"); return !(e && e[0] == '0'); }();

@@ -473,3 +473,53 @@ def test_conv_wgrad_matches_autograd(shape, mode):
     e = rel_l2(got, want.float())
     print(f'wgrad {shape} {mode}: rel-L2 {e:.3e}')
     assert e < (2e-3 if mode == 'tf32' else 1e-4)
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("N,S,Cin,Cin2,Cout", [(20, 32, 128, 0, 128), (19, 32, 64, 0, 128), (18, 32, 128, 256, 128), (18, 32, 256, 0, 256),
+                                               (4, 64, 128, 0, 128)])
+def test_igemm_halo_padded_pixel_path(kind, N, S, Cin, Cin2, Cout):
+    """3x3 convolutions of 32- and 64-wide maps take the padded-pixel kernel (csrc/igemm_halo.cu): one activation box per K chunk,
+    nine descriptor offsets, tiles of 128 padded pixels that start anywhere inside an image row, CTA pairs over two images.  Covers an
+    odd image count (the last pair's second image is out of bounds), the fused 1x1 skip segment, 256-wide tiles, GroupNorm statistics
+    of two consumers, against fp64 convolution; and bit-for-bit insensitivity to what the previous launch left in shared memory."""
+    dtype = L.DTYPE_BF16
+    x = round_in(rnd(N, Cin, S, S, seed=50), dtype)
+    w = round_in(rnd(Cout, Cin, 3, 3, seed=51) / math.sqrt(9 * Cin), dtype)
+    bias = rnd(Cout, seed=52)
+    kw = dict(dtype=dtype, a=dev_op(nhwc(x), dtype), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dtype), Cout=Cout, taps=9, bias=bias.to(DEV),
+              scale=0.7071, out_ld=Cout)
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    if Cin2:
+        xs = round_in(rnd(N, Cin2, S, S, seed=53), dtype)
+        w2 = round_in(rnd(Cout, Cin2, 1, 1, seed=54) / math.sqrt(Cin2), dtype)
+        kw.update(a2=dev_op(nhwc(xs), dtype), Cin2=Cin2, b2=dev_op(w2.reshape(Cout, Cin2), dtype))
+        want = want + F.conv2d(xs.double(), w2.double())
+    want = nhwc(want)
+    part = torch.zeros((N, 32, 2), device=DEV)
+    part2 = torch.zeros((N, 16, 2), device=DEV)
+    gn = dict(gn_partial=part, gn_cpg=Cout // 32, gn_groups=32, gn2_partial=part2, gn2_cpg=Cout // 16, gn2_groups=16)
+    if kind == 1:
+        rowb = rnd(N, Cout, seed=55)
+        out = torch.full((N, S, S, Cout), float('nan'), device=DEV, dtype=torch.bfloat16)
+        kw.update(rowbias=rowb.to(DEV), rowbias_ld=Cout, out_bf16=out, **gn)
+        want = (want + rowb[:, None, None, :].double()) * 0.7071
+        tol = 4e-3
+    else:
+        res = rnd(N, S, S, Cout, seed=56)
+        out = torch.full((N, S, S, Cout), float('nan'), device=DEV)
+        kw.update(residual=res.to(DEV), res_ld=Cout, res_scale=0.7071, out_f32=out, **gn)
+        want = want * 0.7071 + res.double() * 0.7071
+        tol = 2e-5
+    L.igemm(**kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float().cpu(), want) < tol
+    for pt, G in ((part, 32), (part2, 16)):
+        g = want.reshape(N, S * S, G, Cout // G)
+        ws, wq = g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))
+        assert rel_l2(pt[..., 0].cpu(), ws) < 2e-3 and rel_l2(pt[..., 1].cpu(), wq) < 2e-3
+    first = out.clone()
+    L.igemm(**kw)
+    torch.cuda.synchronize()
+    assert torch.equal(first, out)

@@ -791,6 +791,13 @@ def run_ours(args):
         b, a, _ = sampler(model, flow, prior=x0, seed=1)
         return a.cpu()
 
+    if args.train_only:
+        tr = train_throughput(cfg, model, flow, sde, dev, world, timed, both_modes=False)
+        if rank == 0:
+            print(json.dumps(tr), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -891,6 +898,7 @@ def main():
     ap.add_argument("--skip-train", action="store_true", help="profiling: leave out the training leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling: leave out the CPU baseline sample")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the extra legs (ve_pc, nll, celeba, ref_ops)")
+    ap.add_argument("--train-only", action="store_true", help="development: only the training leg (prints its JSON object)")
     ap.add_argument("--global-langevin-norms", action="store_true",
                     help="ve_pc leg under torchrun: all-reduce the Langevin norm statistics (global batch means) instead of per-rank means")
     args = ap.parse_args()

@@ -371,6 +371,11 @@ int indm_col2im3x3_nchw(const float* in, int64_t ld, const float* bias, const fl
 /* y += alpha * x (fp32): the Neumann-series accumulation of iresblock.py:264-270 */
 int indm_axpy_f32(float* y, const float* x, float alpha, int64_t n, void* stream);
 
+/* One term of the Neumann log-det series (iresblock.py:264-273) with its coefficient read from device memory:
+ * acc += coef[*k] * v ; cur = v.  `k` is a device counter the caller advances with indm_advance_step after the launch, so one
+ * captured launch sequence serves every term of every series length. */
+int indm_series_step_f32(float* acc, float* cur, const float* v, const float* coef, int32_t* k, int64_t n, void* stream);
+
 /* out = cos(2 pi x) (fp32): derivative of the leading Sin of an iResBlock branch w.r.t. the block input */
 int indm_cos2pi_f32(const float* x, float* out, int64_t n, void* stream);
 

@@ -73,6 +73,7 @@ _SIGS = {
     "indm_axpy_f32": [_vp, _vp, _f32, _i64, _vp],
     "indm_im2col3x3_nchw": [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "indm_col2im3x3_nchw": [_vp, _i64, _vp, _vp, _vp, _f32, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "indm_series_step_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "indm_cos2pi_f32": [_vp, _vp, _i64, _vp],
     "indm_fixed_point_check": [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp],
     "indm_sched_broadcast": [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp],

@@ -136,6 +136,18 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += alpha * x[i];
 }
 
+// One term of the Neumann series with everything that varies from term to term read from device memory, so that ONE captured
+// graph serves every term of every series length: acc += coef[*k] * v ; cur = v ; (last thread block) *k += 1.
+__global__ void series_step_kernel(float* __restrict__ acc, float* __restrict__ cur, const float* __restrict__ v,
+                                   const float* __restrict__ coef, int* __restrict__ k, long long n) {
+  const float a = coef[*k];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float t = v[i];
+    acc[i] += a * t;
+    cur[i] = t;
+  }
+}
+
 __global__ void cos2pi_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = cosf(6.283185307179586f * x[i]);
@@ -289,6 +301,16 @@ extern "C" int indm_axpy_f32(float* y, const float* x, float alpha, int64_t n, v
   if (blocks > cap) blocks = cap;
   axpy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(y, x, alpha, n);
   INDM_CHECK_LAUNCH("axpy");
+  return INDM_OK;
+}
+
+extern "C" int indm_series_step_f32(float* acc, float* cur, const float* v, const float* coef, int32_t* k, int64_t n, void* stream_) {
+  INDM_CHECK_ARG(acc && cur && v && coef && k && n > 0, "series_step: bad arguments");
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)indm_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  series_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(acc, cur, v, coef, k, n);
+  INDM_CHECK_LAUNCH("series_step");
   return INDM_OK;
 }
 

@@ -38,6 +38,18 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long P, int C, long 
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   const int c = q * 4;
+  // the R row groups of the CTA hold partial sums of the same columns: fold them through shared memory so that one thread per
+  // column quad issues the atomics (the totals of a 512-channel tensor are 512 heavily contended addresses)
+  __shared__ float4 fold[256];
+  if (R > 1) {
+    fold[threadIdx.x] = acc;
+    __syncthreads();
+    if (rr != 0) return;
+    for (int r2 = 1; r2 < R; ++r2) {
+      const float4 o = fold[r2 * Q + q];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+  }
   if (out_img) {
     float* d = out_img + n * out_ld + c;
     atomicAdd(d, acc.x * scale); atomicAdd(d + 1, acc.y * scale); atomicAdd(d + 2, acc.z * scale); atomicAdd(d + 3, acc.w * scale);
@@ -209,8 +221,8 @@ extern "C" int indm_colsum(const void* x, int dtype, int64_t N, int64_t P, int C
   if (R < 1) R = 1;
   if (R > P) R = (int)P;
   const int threads = Q * R;
-  INDM_CHECK_ARG(threads <= 1024, "colsum: C too large");
-  long long splits = ((out_img ? 8LL : 2LL) * indm_num_sms() + N - 1) / N;
+  INDM_CHECK_ARG(threads <= 256 || R == 1, "colsum: C too large");
+  long long splits = ((out_img ? 8LL : 4LL) * indm_num_sms() + N - 1) / N;
   const long long maxs = (P + R * 8LL - 1) / (R * 8LL);
   if (splits > maxs) splits = maxs;
   if (splits < 1) splits = 1;

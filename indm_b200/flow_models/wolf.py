@@ -256,6 +256,10 @@ class WolfCore(nn.Module):
     def add_config(self, config):
         self.config = config
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._lamb_epoch = getattr(self, '_lamb_epoch', 0) + 1      # engines re-read the iResBlocks' lamb on next use
+
     def blocks(self):
         """[(scale, block index, module)] in forward order"""
         out = []
@@ -372,7 +376,9 @@ class FlowEngine:
         # tap packing of the few-channel 3x3 convs (csrc/flow_kernels.cu): K (first conv) / N (last conv) = 9 c packed values
         self.cs = [c0 * 4 ** s for s in range(len(self.nb))]
         self.kp = [((9 * c + self.kchunk - 1) // self.kchunk) * self.kchunk for c in self.cs]      # im2col row length
-        self.ld9 = [((9 * c + 3) // 4) * 4 for c in self.cs]                                        # col2im row stride
+        # col2im row stride = the N extent of the idim -> 9c GEMMs, padded to whole 32-column slabs (27 -> 32, 108 -> 128) with zero
+        # weight rows: a ragged N (27) took the generic scalar epilogue and ran the 134 MB-input GEMM at a fifth of the HBM roofline
+        self.ld9 = [((9 * c + 31) // 32) * 32 for c in self.cs]
         self.a0 = [torch.empty((N, h0 >> s, w0 >> s, self.kp[s]), device=dev, dtype=self.tdtype) for s in range(len(self.nb))]
         self.o9 = [torch.empty((N, h0 >> s, w0 >> s, self.ld9[s]), device=dev) for s in range(len(self.nb))]
         self.u1 = torch.empty((N, h0, w0, idim), device=dev, dtype=self.tdtype)
@@ -385,7 +391,7 @@ class FlowEngine:
         self.w2f = {}
         self._saved = None
         self._graphs, self._pool, self.use_graphs = {}, None, True
-        self._lamb_vers = None
+        self._lamb_vers = -1
         self.prior_winvT = []
         self._ops, self._bufs = {}, {}
         self._alloc_weights()
@@ -397,9 +403,9 @@ class FlowEngine:
             c = m.channels
             kp = self.kp[s]
             z = lambda *shape: torch.zeros(shape, device=dev, dtype=self.tdtype)
-            self.w[(s, b)] = dict(w1=z(idim, kp), b1=torch.empty((idim,), device=dev), w2=z(idim, idim), w3=z(9 * c, idim),
+            self.w[(s, b)] = dict(w1=z(idim, kp), b1=torch.empty((idim,), device=dev), w2=z(idim, idim), w3=z(self.ld9[s], idim),
                                   b3=torch.empty((c,), device=dev),
-                                  w3v=z(idim, kp), w2d=z(idim, idim), w1v=z(9 * c, idim))      # transposed packs for the VJP chain
+                                  w3v=z(idim, kp), w2d=z(idim, idim), w1v=z(self.ld9[s], idim))      # transposed packs for the VJP chain
         nblk = len(self.blocks)
         self.cond_w = torch.empty((nblk * idim, self.core.latent_dim), device=dev)
         self.cond_b = torch.empty((nblk * idim,), device=dev)
@@ -463,12 +469,12 @@ class FlowEngine:
             W['b1'].copy_(cv1.bias.detach())
             w2m = w2.reshape(w2.shape[0], w2.shape[1])
             W['w2'].copy_(self._round(w2m))
-            W['w3'].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9 * ci, co)))                      # [t*c+ch][k]
+            W['w3'][:9 * ci].copy_(self._round(w3.permute(2, 3, 0, 1).reshape(9 * ci, co)))             # [t*c+ch][k]
             W['b3'].copy_(cv3.bias.detach())
             # VJP chain: conv3^T = im2col(flip) . w3v^T ; conv2^T ; conv1^T = col2im(flip)(. w1v^T)
             W['w3v'][:, :9 * ci].copy_(self._round(w3.permute(1, 2, 3, 0).reshape(co, 9 * ci)))         # [k][t*c+ch]
             W['w2d'].copy_(self._round(w2m.t()))
-            W['w1v'].copy_(self._round(w1.permute(2, 3, 1, 0).reshape(9 * ci, co)))                     # [t*c+ch][k]
+            W['w1v'][:9 * ci].copy_(self._round(w1.permute(2, 3, 1, 0).reshape(9 * ci, co)))            # [t*c+ch][k]
             # conditioning: conv1x1(u + (A h + a)) + b2 = conv1x1(u) + (W2 A) h + (W2 a + b2)   (lipschitz.py:431-435)
             A = cv2.h_net.net.weight.detach().to(dev, torch.float32)
             a = cv2.h_net.net.bias.detach().to(dev, torch.float32)
@@ -489,19 +495,22 @@ class FlowEngine:
             for job in self.enc['jobs']:
                 job()
 
-    def load_weights(self, blocks=True):
+    def load_weights(self, blocks=True, head=True):
         """(re)pack after a parameter update.  The iResBlock packs (Lipschitz normalisation of 96 convolutions: ~1300 small launches
         inside one graph, ~5 ms) are only refreshed for an engine whose block passes are about to run: the engine that only serves
         the posterior-encoder legs of a mixed-precision training step (`_enc_engine`) skips them."""
         with torch.no_grad():
             ver = self.version()
-            if self._version != ver:
+            # lamb (the Poisson rate of the series length) is never trained (iresblock.py:40; no loss reaches it, the optimiser skips
+            # it): ONE batched read-back per state-dict load, not a host sync per optimiser step
+            vers = getattr(self.core, '_lamb_epoch', 0)
+            if vers != self._lamb_vers:
+                vals = torch.stack([m.lamb.detach().reshape(()) for (_, _, m) in self.blocks]).cpu().tolist()
+                self.lamb = [float(v) for v in vals]
+                self._lamb_vers = vers
+            if head and self._version != ver:
                 self._graphed(('repack_head', hasattr(self, 'enc')), self._repack_head)
                 self._pack_prior_host()
-                vers = tuple(m.lamb._version for (_, _, m) in self.blocks)
-                if vers != self._lamb_vers:          # lamb is not trained (iresblock.py:40): one read-back, not one per step
-                    self.lamb = [float(m.lamb.detach()) for (_, _, m) in self.blocks]
-                    self._lamb_vers = vers
                 self._version = ver
             if blocks and self._version_blk != ver:
                 self._graphed(('repack_blocks',), self._repack_blocks)
@@ -672,16 +681,18 @@ class FlowEngine:
                                out_ld=idim, aux_cos=d1, **ob(u1)),
                 self._mk_igemm(dtype=self.dt, a=u1, N=N, H=H, W=Wd, Cin=idim, b=W['w2'], Cout=idim, taps=1, rowbias=self.cond[:, i * idim:],
                                rowbias_ld=self.cond.shape[1], act=1, out_ld=idim, aux_cos=d2, **ob(u2)),
-                self._mk_igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s]),
+                self._mk_igemm(dtype=self.dt, a=u2, N=N, H=H, W=Wd, Cin=idim, b=W['w3'], Cout=self.ld9[s], taps=1, out_f32=o9, out_ld=self.ld9[s]),
                 self._mk_call('indm_col2im3x3_nchw', o9, ctypes.c_int64(self.ld9[s]), W['b3'], residual, None, ctypes.c_float(scale), out,
                               ctypes.c_int64(N), c, H, Wd, 0),
             ]
         self._replay(key, build)
 
-    def _ensure(self, blocks=True):
+    def _ensure(self, blocks=True, head=True):
+        """head = prior flow + posterior encoder packs (one host read-back per refresh for the 64 x 64 log-dets): the block passes of
+        a training step (forward_logdet / forward_map / the backward) never touch them"""
         ver = self.version()
-        if self._version != ver or (blocks and self._version_blk != ver):
-            self.load_weights(blocks=blocks)
+        if (head and self._version != ver) or (blocks and self._version_blk != ver):
+            self.load_weights(blocks=blocks, head=head)
 
     # ---- public passes
     def reverse(self, z, eps=None, h=None, seed=0, offset=0, atol=1e-5, rtol=1e-5, max_iter=1000):
@@ -959,16 +970,21 @@ class FlowEngine:
         self._graphs[key] = g
 
     # ---- power-series log-det (iresblock.py:90-174): VJP chain of g on the tensor cores
-    def _g_store(self, i, s, m, x_nchw, out):
-        """out = x + g(x; h) (NCHW fp32) keeping cos(2 pi .) of the three Sin pre-activations for the VJP chain"""
+    def _dviews(self, s, m, x_nchw):
+        """views of the cos-factor buffers (d0: input Sin', None for the flow's first block; d1, d2: the two hidden Sin') for a block
+        at scale s"""
         N, idim = self.N, self.idim
         _, h0, w0 = self.core.input_shape
         H, Wd = h0 >> s, w0 >> s
         n_el = N * H * Wd * idim
         d1, d2 = self.d1.view(-1)[:n_el].view(N, H, Wd, idim), self.d2.view(-1)[:n_el].view(N, H, Wd, idim)
-        d0 = None
+        d0 = None if m.first else self.d0.view(-1)[:x_nchw.numel()].view(x_nchw.shape)
+        return d0, d1, d2
+
+    def _g_store(self, i, s, m, x_nchw, out):
+        """out = x + g(x; h) (NCHW fp32) keeping cos(2 pi .) of the three Sin pre-activations for the VJP chain"""
+        d0, d1, d2 = self._dviews(s, m, x_nchw)
         if not m.first:
-            d0 = self.d0.view(-1)[:x_nchw.numel()].view(x_nchw.shape)
             L.call('indm_cos2pi_f32', L.ptr(x_nchw), L.ptr(d0), x_nchw.numel())
         self._g_impl(i, s, m, x_nchw, out, x_nchw, 1.0, d1, d2)
         return d0, d1, d2
@@ -993,17 +1009,34 @@ class FlowEngine:
                                mul_ld=idim, **ob(t2)),
                 self._mk_igemm(dtype=self.dt, a=t2, N=N, H=H, W=Wd, Cin=idim, b=W['w2d'], Cout=idim, taps=1, out_ld=idim, mul=d1,
                                mul_ld=idim, **ob(t1)),
-                self._mk_igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1v'], Cout=9 * c, taps=1, out_f32=o9, out_ld=self.ld9[s]),
+                self._mk_igemm(dtype=self.dt, a=t1, N=N, H=H, W=Wd, Cin=idim, b=W['w1v'], Cout=self.ld9[s], taps=1, out_f32=o9, out_ld=self.ld9[s]),
                 self._mk_call('indm_col2im3x3_nchw', o9, ctypes.c_int64(self.ld9[s]), None, None, d0, ctypes.c_float(1.0), out,
                               ctypes.c_int64(N), c, H, Wd, 1),
             ]
         self._replay(key, build)
 
+    def _series_rng(self):
+        """Generator of the Poisson series lengths (iresblock.py:306 draws them from numpy's global generator).  The reference is ONE
+        process (nn.DataParallel): every replica evaluates the same n for a block.  With one process per GPU the ranks must agree
+        too — otherwise each step costs the slowest rank's draw (the series length decides 5 - 15 % of a block's work) and the ranks
+        estimate different truncations of one mini-batch's log-det: rank 0 draws a seed from numpy's global generator once and
+        broadcasts it; all ranks then draw from a private RandomState(seed), in lock step.  Single process: numpy's global generator,
+        exactly like the reference."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return np.random
+        rng = getattr(self.core, '_shared_series_rng', None)
+        if rng is None:
+            seed = torch.tensor([int(np.random.randint(0, 2 ** 31 - 1))], dtype=torch.int64, device=self.dev)
+            dist.broadcast(seed, src=0)
+            rng = self.core._shared_series_rng = np.random.RandomState(int(seed.item()))
+        return rng
+
     def forward_logdet(self, x, h, vareps=None, n_terms=None, training=False, seed=0, offset=0, save=False):
         """ResidualFlow.fwdpass(x, h, eval_logdet=True) (resflow_.py:310-324): returns (z, logpx [N]) with
         logpx = -sum over blocks of the power-series log-det estimate: basic estimator with 20 exact terms in eval mode
         (iresblock.py:127-132,253-261), Neumann estimator value with 2 exact terms in training mode (:114-121,264-273)."""
-        self._ensure()
+        self._ensure(head=False)
         N = self.N
         x = x.float().contiguous()
         shape = x.shape
@@ -1033,7 +1066,7 @@ class FlowEngine:
             for i, (ss, b, m) in enumerate(self.blocks):
                 if ss != s:
                     continue
-                n = int(n_terms[bi]) if n_terms is not None else int(np.random.poisson(self.lamb[i], 1)[0])     # iresblock.py:306
+                n = int(n_terms[bi]) if n_terms is not None else int(self._series_rng().poisson(self.lamb[i], 1)[0])     # iresblock.py:306
                 K, coef = series_coefficients(n, training, self.lamb[i])
                 if vareps is not None:
                     ve.copy_(vareps[bi])
@@ -1041,33 +1074,60 @@ class FlowEngine:
                     L.call('indm_randn_f32', L.ptr(ve), ve.numel(), seed, 0x7F300000 + (offset << 8) + bi)
                 xin, xout = xs[cur_x], xs[1 - cur_x]
 
-                def body(i=i, s=s, m=m, xin=xin, xout=xout, K=K, coef=coef):
-                    d0, d1, d2 = self._g_store(i, s, m, xin, xout)
-                    cur = ve
-                    if not training:
+                if training:
+                    # Neumann estimator (value): w = eps + sum_k (-1)^k c_k J^k^T eps ; logdet = <J^T w, eps>.  THREE graphs per block
+                    # — start (branch + cos factors, w = cur = eps), one series term (cur <- J^T cur ; w += coef[k] cur ; k += 1; the
+                    # coefficient comes from a device table indexed by a device counter) and finish — replayed 1 + K + 1 times, so no
+                    # series length ever triggers a new capture (one graph per (block, K) meant ~100 ms capture stalls in random
+                    # steps for the first few hundred steps of a run).
+                    curb = self._static(f'ser_cur{s}', x)
+                    tab = self._static('ser_coef', torch.empty((64,), device=self.dev))
+                    kctr = self._static('ser_k', torch.zeros((1,), dtype=torch.int32, device=self.dev))
+                    if K > tab.numel():
+                        raise RuntimeError(f'series of {K} terms exceeds the coefficient table')
+                    # pageable source: the runtime stages it before returning, so the host list can be rebuilt for the next block
+                    tab[:K].copy_(torch.tensor([((-1) ** k) * coef[k - 1] for k in range(1, K + 1)], dtype=torch.float32))
+                    kctr.zero_()
+                    sx, sv, sw = (self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w')) if save else (None, None, None)
+
+                    dv = self._dviews(s, m, xin)
+
+                    def start(i=i, s=s, m=m, xin=xin, xout=xout):
+                        self._g_store(i, s, m, xin, xout)
+                        neumann.copy_(ve)
+                        curb.copy_(ve)
+
+                    def term(i=i, s=s, m=m, dv=dv):
+                        d0, d1, d2 = dv
+                        nxt = bufs[0]
+                        self._g_vjp(i, s, m, curb, nxt, d0, d1, d2)
+                        L.call('indm_series_step_f32', L.ptr(neumann), L.ptr(curb), L.ptr(nxt), L.ptr(tab), L.ptr(kctr), neumann.numel())
+                        L.call('indm_advance_step', L.ptr(kctr))
+
+                    def finish(i=i, s=s, m=m, xin=xin, dv=dv):
+                        d0, d1, d2 = dv
+                        nxt = bufs[1]
+                        self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
+                        L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
+                        if save:
+                            # what the block's backward needs: its input, the probe and the (constant) Neumann vector
+                            sx.copy_(xin); sv.copy_(ve); sw.copy_(neumann)
+                    self._graphed(('blk_start', i, xin.data_ptr(), xout.data_ptr()), start)
+                    for _k in range(K):
+                        self._graphed(('blk_term', i, xin.data_ptr()), term)
+                    self._graphed(('blk_finish', i, xin.data_ptr(), bool(save)), finish)
+                else:
+                    def body(i=i, s=s, m=m, xin=xin, xout=xout, K=K, coef=coef):
+                        d0, d1, d2 = self._g_store(i, s, m, xin, xout)
+                        cur = ve
                         # basic estimator: sum_k (-1)^(k+1)/k c_k <J^k^T eps, eps>
                         for k in range(1, K + 1):
                             nxt = bufs[k & 1]
                             self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
                             L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-((-1) ** (k + 1)) / k * coef[k - 1]), 1)
                             cur = nxt
-                    else:
-                        # Neumann estimator (value): w = eps + sum_k (-1)^k c_k J^k^T eps ; logdet = <J^T w, eps>
-                        neumann.copy_(ve)
-                        for k in range(1, K + 1):
-                            nxt = bufs[k & 1]
-                            self._g_vjp(i, s, m, cur, nxt, d0, d1, d2)
-                            L.call('indm_axpy_f32', L.ptr(neumann), L.ptr(nxt), ctypes.c_float(((-1) ** k) * coef[k - 1]), neumann.numel())
-                            cur = nxt
-                        nxt = bufs[(K + 1) & 1]
-                        self._g_vjp(i, s, m, neumann, nxt, d0, d1, d2)
-                        L.call('indm_rowdot_f32', L.ptr(nxt), L.ptr(ve), L.ptr(logpx), N, D, ctypes.c_float(-1.0), 1)
-                        if save:
-                            # what the block's backward needs: its input, the probe and the (constant) Neumann vector
-                            sx, sv, sw = (self._static(f'sv_{nm}{i}', xin) for nm in ('x', 'e', 'w'))
-                            sx.copy_(xin); sv.copy_(ve); sw.copy_(neumann)
-                # one CUDA graph per (block, series length): the chain is ~5 (K + 2) small launches
-                self._graphed(('blk', i, K, bool(training), bool(save), float(self.lamb[i])), body)
+                    # one CUDA graph per (block, series length): the chain is ~5 K small launches
+                    self._graphed(('blk', i, K, False, False, float(self.lamb[i])), body)
                 self.vjp_count += K if not training else K + 1
                 self.vjp_per_block.append(K if not training else K + 1)
                 if training and save:
@@ -1086,7 +1146,7 @@ class FlowEngine:
 
     def forward_map(self, x, h):
         """ResidualFlow.fwdpass(x, h, eval_logdet=False) on the flow's own input layout (resflow_.py:310-324)."""
-        self._ensure()
+        self._ensure(head=False)
         N = self.N
         x = x.float().contiguous()
         shape = x.shape

@@ -118,7 +118,7 @@ class FlowBackward:
             call('indm_mul_op', R3, D2, Q2, _i64(n_big), dt),
             ig(a=Q2, Cin=idim, b=Wt['w2d'], Cout=idim, out_ld=idim, **geo, **ob(R2)),
             call('indm_mul_op', R2, D1, Q1, _i64(n_big), dt),
-            ig(a=Q1, Cin=idim, b=Wt['w1v'], Cout=9 * c, out_f32=o9, out_ld=ld9, **geo),
+            ig(a=Q1, Cin=idim, b=Wt['w1v'], Cout=ld9, out_f32=o9, out_ld=ld9, **geo),
             call('indm_col2im3x3_nchw', o9, _i64(ld9), None, None, None, _f(1.0), r1, _i64(N), c, H, Wd, 1),
         ]
         # 3. forward mode of the probe
@@ -136,7 +136,7 @@ class FlowBackward:
             call('indm_fma3_op', GA, None, R3, U2F, S2, G2, _i64(n_big), _f(K2), dt),
             ig(a=G2, Cin=idim, b=Wt['w2d'], Cout=idim, out_ld=idim, mul=D1, mul_ld=idim, **geo, **ob(GA)),
             call('indm_fma3_op', GA, None, R2, U1F, S1, G1, _i64(n_big), _f(K2), dt),
-            ig(a=G1, Cin=idim, b=Wt['w1v'], Cout=9 * c, out_f32=o9, out_ld=ld9, **geo),
+            ig(a=G1, Cin=idim, b=Wt['w1v'], Cout=ld9, out_f32=o9, out_ld=ld9, **geo),
             call('indm_col2im3x3_nchw', o9, _i64(ld9), None, None, d0, _f(1.0), tmp, _i64(N), c, H, Wd, 1),
         ]
         if first:

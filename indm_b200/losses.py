@@ -13,6 +13,7 @@ flow_models/wolf_backward.py, reached through torch.autograd.  Joint training is
 `config.training.freeze_flow=True` opts into a variant that keeps the flow parameters fixed.
 """
 import logging
+import os
 
 import numpy as np
 import torch
@@ -88,6 +89,8 @@ class FusedAdamW(torch.optim.Optimizer):
         when the score network's backward is complete and the flow's backward is about to be queued, so the NCCL all-reduce of the
         62.8 M score gradients runs under the flow backward instead of after it.  `step` then only waits for the side stream."""
         if not (torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+            return
+        if os.environ.get('INDM_EARLY_ALLREDUCE', '1') == '0':
             return
         if getattr(self, '_comm', None) is None:
             self._comm = torch.cuda.Stream()

@@ -792,7 +792,7 @@ def run_ours(args):
         return a.cpu()
 
     if args.train_only:
-        tr = train_throughput(cfg, model, flow, sde, dev, world, timed, both_modes=False)
+        tr = train_throughput(cfg, model, flow, sde, dev, world, timed, both_modes=(args.train_both == 1))
         if rank == 0:
             print(json.dumps(tr), flush=True)
         if world > 1:
@@ -805,7 +805,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     e2e_steps = max(2, min(args.steps, 4))
     ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
-    train = None if args.skip_train else train_throughput(cfg, model, flow, sde, dev, world, timed, both_modes=(world == 1))
+    train = None if args.skip_train else train_throughput(cfg, model, flow, sde, dev, world, timed, both_modes=(world == 1 if args.train_both < 0 else args.train_both == 1))
     extras = {}
     if not args.skip_extras:
         import traceback
@@ -899,6 +899,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling: leave out the CPU baseline sample")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the extra legs (ve_pc, nll, celeba, ref_ops)")
     ap.add_argument("--train-only", action="store_true", help="development: only the training leg (prints its JSON object)")
+    ap.add_argument("--train-both", type=int, default=-1, help="development: 1 / 0 forces the TF32-blocks side measurement of the training leg on / off")
     ap.add_argument("--global-langevin-norms", action="store_true",
                     help="ve_pc leg under torchrun: all-reduce the Langevin norm statistics (global batch means) instead of per-rank means")
     args = ap.parse_args()

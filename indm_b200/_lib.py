@@ -149,11 +149,28 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_SYNC_DEBUG = bool(os.environ.get("INDM_SYNC_DEBUG"))     # development: synchronise after every C-ABI launch and name the one that faults
+
+
 def check(rc, what):
     global launches
     if rc != 0:
         raise RuntimeError(f"indm_b200.{what} failed (status {rc}): {lib().indm_last_error().decode()}")
     launches += 1
+    if _SYNC_DEBUG and not torch.cuda.is_current_stream_capturing():
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise RuntimeError(f"indm_b200.{what}: device fault surfaced after this launch: {e}") from e
+
+
+def debug_sync(what):
+    """development (INDM_SYNC_DEBUG): synchronise and name `what` if a device fault surfaces here (graph replays, captures)"""
+    if _SYNC_DEBUG and not torch.cuda.is_current_stream_capturing():
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise RuntimeError(f"indm_b200: device fault surfaced after {what}: {e}") from e
 
 
 def call(name, *args):

@@ -16,6 +16,7 @@ The Lipschitz-normalised weights W / max(1, |row|_1 / 0.98) are computed once pe
 inside every call as the reference does (lipschitz.py:350-363).
 """
 import ctypes
+import os
 import threading
 import math
 
@@ -390,7 +391,7 @@ class FlowEngine:
         self.w = {}
         self.w2f = {}
         self._saved = None
-        self._graphs, self._pool, self.use_graphs = {}, None, True
+        self._graphs, self._pool, self.use_graphs = {}, None, not os.environ.get('INDM_NO_GRAPHS')
         self._lamb_vers = -1
         self.prior_winvT = []
         self._ops, self._bufs = {}, {}
@@ -446,12 +447,15 @@ class FlowEngine:
                 return
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            if self._pool is None:
-                self._pool = torch.cuda.graph_pool_handle()
-            with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):   # may run inside an autograd worker thread
+            L.debug_sync(f'pre-capture {key[:2]}')
+            # every graph owns its private memory pool: a pool handle shared by the engine's graphs tripped the caching allocator
+            # (use_count assert at capture_begin / freed-pool memory replayed) once graphs of the same engine had been dropped
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # may run inside an autograd worker thread
                 fn()
             self._graphs[key] = st = g
+            L.debug_sync(f'capture of flow graph {key[:2]}')
         st.replay()
+        L.debug_sync(f'replay of flow graph {key[:2]}')
 
     def _repack_blocks(self):
         """device part of the iResBlock weight (re)pack: every result is written in place, so launch lists and graphs stay valid"""
@@ -501,6 +505,13 @@ class FlowEngine:
         the posterior-encoder legs of a mixed-precision training step (`_enc_engine`) skips them."""
         with torch.no_grad():
             ver = self.version()
+            # parameters re-homed (losses.FusedAdamW moves them into flat storage) or replaced since the packs last ran: the repack
+            # graphs start over — one eager pass over the new storages, captured on the following use
+            sig = hash(tuple(p.data_ptr() for p in self.core.parameters()))
+            if sig != getattr(self, '_param_sig', None):
+                self._param_sig = sig
+                for key in [k for k in self._graphs if k[0] in ('repack_head', 'repack_blocks')]:
+                    del self._graphs[key]
             # lamb (the Poisson rate of the series length) is never trained (iresblock.py:40; no loss reaches it, the optimiser skips
             # it): ONE batched read-back per state-dict load, not a host sync per optimiser step
             vers = getattr(self.core, '_lamb_epoch', 0)
@@ -963,9 +974,7 @@ class FlowEngine:
             return
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        if self._pool is None:
-            self._pool = torch.cuda.graph_pool_handle()
-        with torch.cuda.graph(g, pool=self._pool):
+        with torch.cuda.graph(g):
             self._bwd_body()
         self._graphs[key] = g
 

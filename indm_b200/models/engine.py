@@ -115,6 +115,7 @@ class ScoreEngine:
         key = (tuple(p.data_ptr() for p in self.model.parameters()), len(self.pack_jobs))
         if self._repack_graph is not None and self._repack_key == key:
             self._repack_graph.replay()
+            L.debug_sync('replay of the score repack graph')
         else:
             with torch.no_grad():
                 for job in self.pack_jobs:
@@ -129,6 +130,7 @@ class ScoreEngine:
                             for job in self.pack_jobs:
                                 job()
                     self._repack_graph, self._repack_key = g, key
+                    L.debug_sync('capture of the score repack graph')
                 except Exception:          # capture is an optimisation only: fall back to eager packing
                     self._repack_graph = None
         self._weights_version = self.weights_version()

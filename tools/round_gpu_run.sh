@@ -4,31 +4,31 @@
 #   2. ncu --set full capture of the first igemm / GroupNorm launches of one score-network forward
 #   3. pytest -m gpu in ONE process (as the driver runs it)
 #   4. bench.py (N = 1, defaults)
-#     gpurun --timeout 960 -- 'bash tools/round_gpu_run.sh'
+#     gpurun --timeout 1500 -- 'bash tools/round_gpu_run.sh'
 set -u
 O=gpurun_out
 mkdir -p $O
-TAG=${TAG:-r1_final}
+TAG=${TAG:-r2_final}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/${TAG}_gpu.txt 2>&1
 
 echo "== leg 1: ncu launch list of the bench slice"; date +%T
 timeout 260 ncu --metrics gpu__time_duration.sum --clock-control none -c 16000 --csv \
     --log-file $O/${TAG}_ncu_launches_bench_slice.csv \
-    python bench.py --steps 1 --warmup 1 --num-scales 4 --skip-train --skip-cpu > $O/${TAG}_ncu_launches_bench_slice.log 2>&1
+    python bench.py --steps 1 --warmup 1 --num-scales 4 --skip-train --skip-cpu --skip-extras > $O/${TAG}_ncu_launches_bench_slice.log 2>&1
 echo "rc=$?"
 
 echo "== leg 2: ncu --set full, igemm + GroupNorm kernels of the first forward"; date +%T
-timeout 240 ncu --set full --clock-control none --import-source on -k 'regex:igemm_kernel|gn_apply|gn_stats' -c 60 \
+timeout 240 ncu --set full --clock-control none --import-source on -k 'regex:igemm_kernel|igemm_halo_kernel|gn_apply|gn_stats' -c 70 \
     -o $O/${TAG}_ncu_full_forward -f python tools/quick_bench.py > $O/${TAG}_ncu_full_forward.log 2>&1
 echo "rc=$?"
 
 echo "== leg 3: pytest -m gpu (one process)"; date +%T
-timeout 480 python -m pytest tests/ -q -m gpu --durations=12 -p no:cacheprovider > $O/${TAG}_pytest_gpu.log 2>&1
+timeout 600 python -m pytest tests/ -q -s -m gpu --durations=12 -p no:cacheprovider > $O/${TAG}_pytest_gpu.log 2>&1
 echo "rc=$?"
 tail -25 $O/${TAG}_pytest_gpu.log
 
 echo "== leg 4: bench.py"; date +%T
-timeout 300 python bench.py > $O/${TAG}_bench_n1.log 2> $O/${TAG}_bench_n1.err
+timeout 600 python bench.py > $O/${TAG}_bench_n1.log 2> $O/${TAG}_bench_n1.err
 echo "rc=$?"
 tail -c 3000 $O/${TAG}_bench_n1.log
 date +%T

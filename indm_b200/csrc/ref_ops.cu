@@ -105,50 +105,62 @@ __global__ void __launch_bounds__(256) upfirdn2d_spec_kernel(const float* __rest
   float kf[K * K];                                 // flipped kernel: kf[i][j] = k[K-1-i][K-1-j]
 #pragma unroll
   for (int i = 0; i < K * K; ++i) kf[i] = __ldg(k + (K * K - 1 - i));
+  constexpr int RG = 4;                            // output rows per thread: 4 independent row computations in flight
   const int qw = (p.out_w + 3) >> 2;               // output quads per row
-  const long long total = planes * (long long)p.out_h * qw;
+  const int rgs = (p.out_h + RG - 1) / RG;
+  const long long total = planes * (long long)rgs * qw;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int qx = (int)(idx % qw);
     const long long t = idx / qw;
-    const int oy = (int)(t % p.out_h);
-    const long long plane = t / p.out_h;
+    const int rg = (int)(t % rgs);
+    const long long plane = t / rgs;
     const int ox0 = qx * 4;
     const float* src = x + plane * (long long)p.in_h * p.in_w;
     const int ux0 = ox0 * DOWN - p.pad_x0;         // first upsampled-grid column of the span
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[RG][4];
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      const int uy = oy * DOWN + i - p.pad_y0;
-      const int iy = uy >> UPS;
-      if (uy < 0 || (uy & UPM) || iy >= p.in_h) continue;
-      const float* row = src + (long long)iy * p.in_w;
-      float v[SPAN];                               // the span of this input row on the upsampled grid (0 where no sample sits)
+    for (int r = 0; r < RG; ++r) {
+      acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+      const int oy = rg * RG + r;
 #pragma unroll
-      for (int s_ = 0; s_ < SPAN; ++s_) {
-        const int ux = ux0 + s_;
-        const int ix = ux >> UPS;
-        v[s_] = (ux >= 0 && !(ux & UPM) && ix < p.in_w) ? __ldg(row + ix) : 0.f;
-      }
+      for (int i = 0; i < K; ++i) {
+        const int uy = oy * DOWN + i - p.pad_y0;
+        const int iy = uy >> UPS;
+        if (oy >= p.out_h || uy < 0 || (uy & UPM) || iy >= p.in_h) continue;
+        const float* row = src + (long long)iy * p.in_w;
+        float v[SPAN];                             // the span of this input row on the upsampled grid (0 where no sample sits)
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
+        for (int s_ = 0; s_ < SPAN; ++s_) {
+          const int ux = ux0 + s_;
+          const int ix = ux >> UPS;
+          v[s_] = (ux >= 0 && !(ux & UPM) && ix < p.in_w) ? __ldg(row + ix) : 0.f;
+        }
 #pragma unroll
-        for (int j = 0; j < K; ++j) acc[o] += v[o * DOWN + j] * kf[i * K + j];
+        for (int o = 0; o < 4; ++o) {
+#pragma unroll
+          for (int j = 0; j < K; ++j) acc[r][o] += v[o * DOWN + j] * kf[i * K + j];
+        }
       }
     }
-    float* dst = y + plane * (long long)p.out_h * p.out_w + (long long)oy * p.out_w + ox0;
-    if (ox0 + 3 < p.out_w && (p.out_w & 3) == 0) {
-      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    } else {
 #pragma unroll
-      for (int o = 0; o < 4; ++o)
-        if (ox0 + o < p.out_w) dst[o] = acc[o];
+    for (int r = 0; r < RG; ++r) {
+      const int oy = rg * RG + r;
+      if (oy >= p.out_h) break;
+      float* dst = y + plane * (long long)p.out_h * p.out_w + (long long)oy * p.out_w + ox0;
+      if (ox0 + 3 < p.out_w && (p.out_w & 3) == 0) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (ox0 + o < p.out_w) dst[o] = acc[r][o];
+      }
     }
   }
 }
 
 template <int UP, int DOWN, int K>
 int launch_upfirdn_spec(const float* x, const float* k, float* y, long long major, const UpfirdnParams& p, cudaStream_t stream) {
-  const long long total = major * (long long)p.out_h * ((p.out_w + 3) / 4);
+  const long long total = major * (long long)((p.out_h + 3) / 4) * ((p.out_w + 3) / 4);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)indm_num_sms() * 32;
   if (blocks > cap) blocks = cap;

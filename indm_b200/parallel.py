@@ -3,7 +3,8 @@
 
   * sampling / likelihood evaluation shard by image: every rank owns a contiguous slice of the global batch and runs its own
     CUDA graph; there is no data-path collective.  The Langevin corrector's batch-mean norms
-    (sampling.py:286-288) can optionally be made global with a 2-float all-reduce (`allreduce_langevin_norms`).
+    (sampling.py:286-288) can optionally be made global (`sampling.global_langevin_norms`): `allreduce_langevin_sums_` sums the
+    three floats (sum |s_n|, sum |z_n|, N) over ranks, on the sampling stream, inside the sampler's CUDA graph.
   * training is data parallel: gradients accumulated by the engine into one flat buffer are summed with ONE all-reduce (NCCL over
     NVLink on GPUs, gloo on CPU in the tests) and divided by the world size before the global-norm clip (losses.FusedAdamW.step).
 """
@@ -40,14 +41,15 @@ def allreduce_mean_(flat, group=None):
     return flat
 
 
-def allreduce_langevin_norms(norm_sums, counts, group=None):
-    """global batch means of the per-sample gradient / noise norms: `norm_sums` [2] = local sums of |s_n| and |z_n|, `counts` =
-    local batch size; returns the two global means (makes a sharded Langevin trajectory identical to the single-batch one)"""
-    buf = torch.cat([norm_sums.reshape(2).double(), torch.tensor([float(counts)], dtype=torch.float64, device=norm_sums.device)])
+def allreduce_langevin_sums_(sums3, group=None):
+    """in place: `sums3` = [sum_n |s_n|, sum_n |z_n|, N] of this rank's shard (written by `indm_langevin_norm_sums`) -> the same
+    three sums over all ranks; `indm_langevin_update_global` divides the first two by the third, which makes a sharded Langevin
+    trajectory identical to the single-batch one.  Called by the sampler (indm_b200/sampling.py) on the sampling stream — NCCL
+    collectives are capturable, so the exchange lives inside the per-step CUDA graph."""
     _, ws = world()
     if ws > 1:
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return (buf[:2] / buf[2]).float()
+        dist.all_reduce(sums3, op=dist.ReduceOp.SUM, group=group)
+    return sums3
 
 
 def gather_cat(x, group=None):

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import parallel
 from . import sde_lib
 from .models import utils as mutils
 
@@ -358,7 +359,7 @@ class _GraphedPC:
                 L.call('indm_langevin_norms', L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.norms), L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
                 if self.global_norms:
                     L.call('indm_langevin_norm_sums', L.ptr(self.norms), L.ptr(self.gsums), N)
-                    torch.distributed.all_reduce(self.gsums)
+                    parallel.allreduce_langevin_sums_(self.gsums)
                     L.call('indm_langevin_update_global', L.ptr(self.x), L.ptr(eng.out), L.ptr(noise_c), L.ptr(self.x_mean), L.ptr(self.gsums),
                            L.ptr(self.sched[:, 5:]), self.LD, L.ptr(self.step), N, D, 0, L.ptr(self.seed_dev), 1 + i)
                     continue

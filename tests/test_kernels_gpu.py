@@ -523,3 +523,26 @@ def test_igemm_halo_padded_pixel_path(kind, N, S, Cin, Cin2, Cout):
     L.igemm(**kw)
     torch.cuda.synchronize()
     assert torch.equal(first, out)
+
+
+@pytest.mark.parametrize("N,S,Cin,Cout", [(16, 8, 256, 256), (32, 4, 256, 256)])
+def test_igemm_split_k_path(N, S, Cin, Cout):
+    """Launches with too few output tiles to fill the chip can split K across CTAs (indm_igemm_t.splitk_ws: raw partial sums in a
+    caller workspace + a finish kernel that applies the epilogue).  The engine leaves it off (measured slower than one CTA per tile
+    on the 4x4 / 8x8 layers at batch 128), but the path stays tested: bias + row bias + scale + fused statistics against fp64."""
+    dtype = L.DTYPE_BF16
+    x = round_in(rnd(N, Cin, S, S, seed=60), dtype)
+    w = round_in(rnd(Cout, Cin, 3, 3, seed=61) / math.sqrt(9 * Cin), dtype)
+    bias, rowb = rnd(Cout, seed=62), rnd(N, Cout, seed=63)
+    ws = torch.empty(8 << 20, device=DEV)
+    out = torch.zeros((N, S, S, Cout), device=DEV, dtype=torch.bfloat16)
+    part = torch.zeros((N, 32, 2), device=DEV)
+    L.igemm(dtype=dtype, a=dev_op(nhwc(x), dtype), N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dtype), Cout=Cout, taps=9, bias=bias.to(DEV),
+            rowbias=rowb.to(DEV), rowbias_ld=Cout, scale=0.7071, out_bf16=out, out_ld=Cout, splitk_ws=ws, splitk_ws_bytes=ws.numel() * 4,
+            **(dict(gn_partial=part, gn_cpg=Cout // 32, gn_groups=32) if S * S >= 32 else {}))
+    torch.cuda.synchronize()
+    want = (nhwc(F.conv2d(x.double(), w.double(), bias.double(), padding=1)) + rowb[:, None, None, :].double()) * 0.7071
+    assert rel_l2(out.float().cpu(), want) < 4e-3
+    if S * S >= 32:
+        g = want.reshape(N, S * S, 32, Cout // 32)
+        assert rel_l2(part[..., 0].cpu(), g.sum(dim=(1, 3))) < 2e-3 and rel_l2(part[..., 1].cpu(), (g * g).sum(dim=(1, 3))) < 2e-3

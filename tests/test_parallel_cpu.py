@@ -31,8 +31,9 @@ def _worker(rank, ws, port, q):
         parallel.allreduce_mean_(g)
         # global Langevin norms from local sums
         local = x[a:b]
-        sums = torch.stack([local.norm(dim=1).sum(), (2 * local).norm(dim=1).sum()])
-        means = parallel.allreduce_langevin_norms(sums, local.shape[0])
+        sums = torch.stack([local.norm(dim=1).sum(), (2 * local).norm(dim=1).sum(), torch.tensor(float(local.shape[0]))])
+        parallel.allreduce_langevin_sums_(sums)
+        means = sums[:2] / sums[2]
         allx = parallel.gather_cat(mine)
         q.put((rank, a, b, mine.clone(), g.clone(), means.clone(), allx.clone()))
     finally:

@@ -12,16 +12,20 @@ TAG=${TAG:-r2_final}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/${TAG}_gpu.txt 2>&1
 
 echo "== leg 1: ncu launch list of the bench slice"; date +%T
-timeout 260 ncu --metrics gpu__time_duration.sum --clock-control none -c 16000 --csv \
+timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
     --log-file $O/${TAG}_ncu_launches_bench_slice.csv \
-    python bench.py --steps 1 --warmup 1 --num-scales 4 --skip-train --skip-cpu --skip-extras > $O/${TAG}_ncu_launches_bench_slice.log 2>&1
+    python bench.py --steps 1 --warmup 1 --num-scales 2 --skip-train --skip-cpu --skip-extras > $O/${TAG}_ncu_launches_bench_slice.log 2>&1
 echo "rc=$?"
 
 echo "== leg 2: ncu --set full, igemm + GroupNorm kernels of the first forward"; date +%T
-timeout 240 ncu --set full --clock-control none --import-source on -k 'regex:igemm_kernel|igemm_halo_kernel|gn_apply|gn_stats' -c 70 \
-    -o $O/${TAG}_ncu_full_forward -f python tools/quick_bench.py > $O/${TAG}_ncu_full_forward.log 2>&1
+timeout 420 ncu --set full --clock-control none --import-source on -k 'regex:igemm_kernel|igemm_halo_kernel|gn_apply|gn_stats' -c 30 \
+    -o /tmp/${TAG}_ncu_full_forward -f python tools/quick_bench.py > $O/${TAG}_ncu_full_forward.log 2>&1
 echo "rc=$?"
+# the .ncu-rep (70+ MB) exceeds what gpurun copies back: keep its raw page as CSV
+ncu -i /tmp/${TAG}_ncu_full_forward.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_forward_raw.csv 2>/dev/null
+ls -la $O/${TAG}_ncu_full_forward_raw.csv
 
+if [ "${LEGS:-all}" = "ncu" ]; then exit 0; fi
 echo "== leg 3: pytest -m gpu (one process)"; date +%T
 timeout 600 python -m pytest tests/ -q -s -m gpu --durations=12 -p no:cacheprovider > $O/${TAG}_pytest_gpu.log 2>&1
 echo "rc=$?"

@@ -25,7 +25,10 @@ def short(k):
 
 
 def full(rep, tag):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):          # raw page already exported on the GPU box (tools/round_gpu_run.sh)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
     hdr, units, body = rows[0], rows[1], rows[2:]
     ix = [hdr.index(k) for k in KEEP if k in hdr]
@@ -40,7 +43,7 @@ def full(rep, tag):
     assert units[rd] == "Mbyte" and units[wr] == "Mbyte", (units[rd], units[wr])
     agg = collections.defaultdict(list)
     for r in body:
-        agg["igemm" if "igemm_kernel" in r[kn] else ("gn_apply" if "gn_apply" in r[kn] else "other")].append(
+        agg["igemm" if "igemm" in r[kn] else ("gn_apply" if "gn_apply" in r[kn] else "other")].append(
             (float(r[rd]) + float(r[wr])) * 1e6)
     js = {"source": f"profiles/{tag}_summary.csv: ncu --set full --clock-control none, mean of (dram__bytes_read.sum + dram__bytes_write.sum) over "
                     f"the {len(agg['igemm'])} igemm launches captured at the start of one score-network forward (stem, level-0 and first "
@@ -63,7 +66,7 @@ def launch_list(path, tag):
     lines = [f"# {tag}: per-kernel device time of ONE PC sampling step (score-network forward + fused predictor update)",
              "",
              f"Source: `profiles/{os.path.basename(path)}` = `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-             "`python bench.py --steps 1 --warmup 1 --num-scales 4 --skip-train --skip-cpu` (the bench command with a 4-step schedule). "
+             "`python bench.py --steps 1 --warmup 1 --num-scales 2 --skip-train --skip-cpu --skip-extras` (the bench command with a 2-step schedule). "
              f"{len(rows)} launches captured before the time limit; steps are delimited by `predictor_update_kernel`. ncu serialises "
              "launches and runs them cold-cache: compare SHARES with bench.py's live `share_of_forward_device_time`, not absolutes.",
              ""]
@@ -76,7 +79,7 @@ def launch_list(path, tag):
             cnt[short(names[i])] += 1
         classes = collections.Counter()
         for k, v in agg.items():
-            classes["igemm_kernel (all instantiations)" if k.startswith("igemm_kernel") else
+            classes["igemm_kernel + igemm_halo_kernel (all instantiations)" if k.startswith("igemm") else
                     ("gn_apply_kernel (all)" if k.startswith("gn_apply") else "everything else")] += v
         lines += [f"One step = {len(list(seg))} launches, {tot / 1e3:.1f} us summed kernel time.", "", "| class | us | share |", "|---|---|---|"]
         lines += [f"| {k} | {v / 1e3:.1f} | {100 * v / tot:.1f} % |" for k, v in classes.most_common()]

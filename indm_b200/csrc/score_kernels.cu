@@ -195,6 +195,76 @@ __global__ void gn_apply_kernel(const TIn* __restrict__ xa, int Ca, const TIn* _
   }
 }
 
+// Equal-work variant of gn_apply for RES == 0 (round 2): the (image, pixel) space is cut into gridDim.x contiguous ranges of the
+// same length — a grid of exactly (resident CTAs per SM x SMs) CTAs with no tail wave — instead of (splits, N) blocks whose count
+// (1280 for 128 images) ran 2.16 waves on 592 resident slots, the last one at 16 % occupancy.  A range may cross image boundaries:
+// the per-(image, group) scale / shift are rebuilt when it does.
+template <typename TIn, typename TOut, bool DROP, int UNR = 4>
+__global__ void __launch_bounds__(256) gn_apply_flat_kernel(const TIn* __restrict__ xa, int Ca, const TIn* __restrict__ xb, int Cb, long long N, long long P,
+                                     int G, int R, const float* __restrict__ partial, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, int act,
+                                     typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ out,
+                                     typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ raw,
+                                     float drop_p, const unsigned long long* __restrict__ drop_ctl, unsigned drop_stream) {
+  pdl_trigger();
+  pdl_wait();
+  const bool dropping = DROP && drop_ctl != nullptr && drop_p > 0.f && drop_ctl[1] != 0ull;
+  const unsigned long long drop_seed = dropping ? drop_ctl[0] : 0ull;
+  const int C = Ca + Cb;
+  const int Q = C >> 2;
+  const int q = threadIdx.x % Q;
+  const int rr = threadIdx.x / Q;
+  if (rr >= R) return;
+  const int c = q * 4;
+  const int cpg = C / G;
+  const int g = c / cpg;
+  const float cnt = (float)((double)P * cpg);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 be = *reinterpret_cast<const float4*>(beta + c);
+  const long long total = N * P;
+  long long per = (total + gridDim.x - 1) / gridDim.x;
+  per = (per + R - 1) / R * R;
+  const long long g0 = (long long)blockIdx.x * per, g1 = min(total, g0 + per);
+  const bool in_a = c < Ca;
+  const int ld = in_a ? Ca : Cb;
+  const TIn* base = in_a ? xa + c : xb + (c - Ca);
+  for (long long n = g0 / P; n * P < g1; ++n) {
+    const float su = partial[(n * G + g) * 2 + 0];
+    const float sq = partial[(n * G + g) * 2 + 1];
+    const float mean = su / cnt;
+    const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float4 sc = make_float4(ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd);
+    const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+    const long long p0 = max(g0, n * P) - n * P, p1 = min(g1, (n + 1) * P) - n * P;      // this image's pixels inside the range
+    const TIn* src = base + n * P * ld;
+    for (long long p = p0 + rr; p < p1; p += (long long)UNR * R) {
+      float4 v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const long long pp = p + (long long)u * R;
+        v[u] = pp < p1 ? Vec4<TIn>::load(src + pp * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const long long pp = p + (long long)u * R;
+        if (pp >= p1) break;
+        float4 y = make_float4(v[u].x * sc.x + sh.x, v[u].y * sc.y + sh.y, v[u].z * sc.z + sh.z, v[u].w * sc.w + sh.w);
+        if (act) {
+          if (std::is_same<TOut, __nv_bfloat16>::value) y = make_float4(silu_fast(y.x), silu_fast(y.y), silu_fast(y.z), silu_fast(y.w));
+          else y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+        }
+        if (DROP && dropping) {
+          const float4 k = dropout_scale4(drop_seed, drop_stream, (unsigned long long)((n * P + pp) * Q + q), drop_p);
+          y = make_float4(y.x * k.x, y.y * k.y, y.z * k.z, y.w * k.w);
+        }
+        Vec4<TOut>::store(out + (n * P + pp) * C + c, y);
+        if (raw) Vec4<TOut>::store(raw + (n * P + pp) * C + c, v[u]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- softmax over rows, one warp per row
 template <typename TOut>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, TOut* __restrict__ out, long long rows, int cols, int tf32) {
@@ -439,6 +509,25 @@ static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64
   const long long Piter = resample == 2 ? (long long)(H / 2) * (W / 2) : (long long)H * W;
   const GnGeom g = gn_geom(C, Piter, N);
   dim3 grid(g.splits, (unsigned)N);
+  static const bool flat = []() { const char* e = getenv("INDM_GN_FLAT"); return !(e && e[0] == '0'); }();
+  if (flat && resample == 0 && g.threads <= 256) {
+    // equal-work ranges over the (image, pixel) space: grid = resident slots of the chip, or fewer when there is less than one
+    // UNR-trip of work per CTA
+    const long long total = (long long)N * H * W;
+    long long ctas = (long long)indm_num_sms() * (g.threads > 128 ? 4 : 8);
+    const long long max_ctas = (total + (long long)g.R * 4 - 1) / ((long long)g.R * 4);
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    const long long P = (long long)H * W;
+    if (drop_ctl != nullptr && drop_p > 0.f)
+      indm_launch_pdl(gn_apply_flat_kernel<TIn, TOut, true>, dim3((unsigned)ctas), dim3(g.threads), 0, stream, (const TIn*)xa, Ca, (const TIn*)xb, Cb,
+                      (long long)N, P, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream);
+    else
+      indm_launch_pdl(gn_apply_flat_kernel<TIn, TOut, false>, dim3((unsigned)ctas), dim3(g.threads), 0, stream, (const TIn*)xa, Ca, (const TIn*)xb, Cb,
+                      (long long)N, P, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream);
+    INDM_CHECK_LAUNCH("gn_apply (flat)");
+    return INDM_OK;
+  }
 #define GN_ARGS (const TIn*)xa, Ca, (const TIn*)xb, Cb, H, W, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream
   if (resample == 0 && drop_ctl != nullptr && drop_p > 0.f)
     indm_launch_pdl(gn_apply_kernel<TIn, TOut, 0, true>, grid, dim3(g.threads), 0, stream, GN_ARGS);

@@ -407,8 +407,10 @@ __global__ void linear_generic_kernel(const float* __restrict__ in, const float*
 // input pixel is loaded once per output COLUMN tap, not once per 2-D tap: 4 (plain), 8 (down x2) or ~1 (up x2) 16-byte loads per
 // output quad instead of 16 / 16 / 4, no runtime division, channel-contiguous (fully coalesced) accesses.  grid = (column tiles x
 // channel tiles, row strips, N).
+// four channels per thread: kept for the down x2 mode (few output pixels: the eight-channel variant halves the thread count
+// and ran 24 -> 33 us there)
 template <typename TIn, typename TOut, int MODE>
-__global__ void __launch_bounds__(256) fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
+__global__ void __launch_bounds__(256) fir_nhwc4_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
                                 long long N, int H, int W, int C, float k0, float k1, float k2, float k3, int qb_log2, int RS, int ctiles) {
   pdl_trigger();
   pdl_wait();
@@ -464,6 +466,87 @@ __global__ void __launch_bounds__(256) fir_nhwc_kernel(const TIn* __restrict__ x
     acc.z = h0.z * kf[0] + h1.z * kf[1] + h2.z * kf[2] + h3.z * kf[3];
     acc.w = h0.w * kf[0] + h1.w * kf[1] + h2.w * kf[2] + h3.w * kf[3];
     Vec4<TOut>::store(yout + (long long)oy * Wo * C, acc);
+    if (oy + 1 < oy_end) {
+      if (DOWN == 1) {
+        h0 = h1; h1 = h2; h2 = h3; h3 = hrow(u0 + 4);
+        u0 += 1;
+      } else {
+        h0 = h2; h1 = h3; h2 = hrow(u0 + 4); h3 = hrow(u0 + 5);
+        u0 += 2;
+      }
+    }
+  }
+}
+
+template <typename TIn, typename TOut, int MODE>
+__global__ void __launch_bounds__(256) fir_nhwc_kernel(const TIn* __restrict__ x, typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ y,
+                                long long N, int H, int W, int C, float k0, float k1, float k2, float k3, int qb_log2, int RS, int ctiles) {
+  pdl_trigger();
+  pdl_wait();
+
+  // a thread owns EIGHT channels (one 16-byte load of a bf16 input, two of an fp32 input; one 16-byte store of a bf16 output): with
+  // four, the bf16 variants moved 8 bytes per load / store instruction and ran slower than the fp32 ones on half the bytes
+  constexpr int UP = MODE == 1 ? 2 : 1;
+  constexpr int DOWN = MODE == 2 ? 2 : 1;
+  constexpr int PAD0 = MODE == 1 ? 2 : ((MODE == 2 || MODE == 4) ? 1 : 2);
+  const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : (MODE == 4 ? H - 1 : H + 1));
+  const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : (MODE == 4 ? W - 1 : W + 1));
+  const int Q = C >> 3;                                          // channel octets
+  const float kf[4] = {k3, k2, k1, k0};  // flipped
+  const int qb = 1 << qb_log2;                                   // channel octets per CTA (power of two)
+  const int ct = blockIdx.x % ctiles, xt = blockIdx.x / ctiles;
+  const int q = ct * qb + (threadIdx.x & (qb - 1));
+  const int ox = xt * (256 >> qb_log2) + (threadIdx.x >> qb_log2);
+  if (q >= Q || ox >= Wo) return;
+  const long long n = blockIdx.z;
+  const int oy_begin = blockIdx.y * RS;
+  const int oy_end = oy_begin + RS < Ho ? oy_begin + RS : Ho;
+  const TIn* xin = x + n * (long long)H * W * C + q * 8;
+  int ixs[4];
+  float wj[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ux = ox * DOWN + j - PAD0;
+    const bool ok = ux >= 0 && (ux % UP) == 0 && (ux / UP) < W;
+    ixs[j] = ok ? ux / UP : 0;
+    wj[j] = ok ? kf[j] : 0.f;
+  }
+  struct F8 { float4 a, b; };
+  auto hrow = [&](int uy) -> F8 {
+    F8 r;
+    r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.b = r.a;
+    if (uy < 0 || (uy % UP) != 0) return r;
+    const int iy = uy / UP;
+    if (iy >= H) return r;
+    const TIn* row = xin + (long long)iy * W * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (wj[j] != 0.f) {
+        const TIn* p = row + (long long)ixs[j] * C;
+        const float4 va = Vec4<TIn>::load(p), vb = Vec4<TIn>::load(p + 4);
+        r.a.x += va.x * wj[j]; r.a.y += va.y * wj[j]; r.a.z += va.z * wj[j]; r.a.w += va.w * wj[j];
+        r.b.x += vb.x * wj[j]; r.b.y += vb.y * wj[j]; r.b.z += vb.z * wj[j]; r.b.w += vb.w * wj[j];
+      }
+    }
+    return r;
+  };
+  int u0 = oy_begin * DOWN - PAD0;
+  F8 h0 = hrow(u0), h1 = hrow(u0 + 1), h2 = hrow(u0 + 2), h3 = hrow(u0 + 3);
+  auto* yout = y + n * (long long)Ho * Wo * C + (long long)ox * C + q * 8;
+  for (int oy = oy_begin; oy < oy_end; ++oy) {
+    float4 ya, yb;
+    ya.x = h0.a.x * kf[0] + h1.a.x * kf[1] + h2.a.x * kf[2] + h3.a.x * kf[3];
+    ya.y = h0.a.y * kf[0] + h1.a.y * kf[1] + h2.a.y * kf[2] + h3.a.y * kf[3];
+    ya.z = h0.a.z * kf[0] + h1.a.z * kf[1] + h2.a.z * kf[2] + h3.a.z * kf[3];
+    ya.w = h0.a.w * kf[0] + h1.a.w * kf[1] + h2.a.w * kf[2] + h3.a.w * kf[3];
+    yb.x = h0.b.x * kf[0] + h1.b.x * kf[1] + h2.b.x * kf[2] + h3.b.x * kf[3];
+    yb.y = h0.b.y * kf[0] + h1.b.y * kf[1] + h2.b.y * kf[2] + h3.b.y * kf[3];
+    yb.z = h0.b.z * kf[0] + h1.b.z * kf[1] + h2.b.z * kf[2] + h3.b.z * kf[3];
+    yb.w = h0.b.w * kf[0] + h1.b.w * kf[1] + h2.b.w * kf[2] + h3.b.w * kf[3];
+    auto* dst = yout + (long long)oy * Wo * C;
+    Vec4<TOut>::store(dst, ya);
+    Vec4<TOut>::store(dst + 4, yb);
     if (oy + 1 < oy_end) {
       if (DOWN == 1) {
         h0 = h1; h1 = h2; h2 = h3; h3 = hrow(u0 + 4);
@@ -662,21 +745,23 @@ static int fir_launch(const void* x, void* y, int64_t N, int H, int W, int C, co
   using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
   const int Ho = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : (mode == 4 ? H - 1 : H + 1));
   const int Wo = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : (mode == 4 ? W - 1 : W + 1));
-  // CTA = 256 threads = (qb channel quads) x (256 / qb output columns); qb = largest power of two <= min(Q, 64)
-  const int Q = C / 4;
+  // CTA = 256 threads = (qb channel groups) x (256 / qb output columns); a thread owns 8 channels (4 in the down x2 mode)
+  const int Q = mode == 2 ? C / 4 : C / 8;
   int qb_log2 = 0;
   while ((2 << qb_log2) <= Q && qb_log2 < 6) ++qb_log2;
   const int qb = 1 << qb_log2, cols = 256 >> qb_log2;
   const int ctiles = (Q + qb - 1) / qb, xtiles = (Wo + cols - 1) / cols;
-  // strip length: long strips amortise the 3 warm-up rows; keep >= ~4 CTAs per SM
+  // strip length: long strips amortise the 3 warm-up rows; keep enough CTAs in flight
   int RS = Ho;
-  while (RS > 8 && (long long)N * ((Ho + RS - 1) / RS) * ctiles * xtiles < 4LL * indm_num_sms()) RS = (RS + 1) / 2;
+  static const int fir_waves = []() { const char* e = getenv("INDM_FIR_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+  const int waves = mode == 1 ? (fir_waves < 4 ? fir_waves : 4) : fir_waves;
+  while (RS > 4 && (long long)N * ((Ho + RS - 1) / RS) * ctiles * xtiles < (long long)waves * indm_num_sms()) RS = (RS + 1) / 2;
   const dim3 grid((unsigned)(ctiles * xtiles), (unsigned)((Ho + RS - 1) / RS), (unsigned)N);
   INDM_CHECK_ARG(N <= 65535, "fir_nhwc: N > 65535");
   if (mode == 1)
     indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 1>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   else if (mode == 2)
-    indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 2>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
+    indm_launch_pdl(fir_nhwc4_kernel<TIn, TOut, 2>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   else if (mode == 3)
     indm_launch_pdl(fir_nhwc_kernel<TIn, TOut, 3>, grid, dim3(256), 0, stream, (const TIn*)x, (TO*)y, N, H, W, C, k[0], k[1], k[2], k[3], qb_log2, RS, ctiles);
   else
@@ -688,7 +773,7 @@ static int fir_launch(const void* x, void* y, int64_t N, int H, int W, int C, co
 extern "C" int indm_fir_nhwc(const void* x, void* y, int dtype_in, int dtype_out, int64_t N, int H, int W, int C, const float* k1,
                              int mode, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  INDM_CHECK_ARG(x && y && k1 && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "fir_nhwc: bad arguments");
+  INDM_CHECK_ARG(x && y && k1 && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "fir_nhwc: bad arguments (C must be a multiple of 8)");
   INDM_CHECK_ARG(mode >= 1 && mode <= 4, "fir_nhwc: mode must be 1 (up), 2 (down), 3 (pad (2,2)) or 4 (pad (1,1))");
   INDM_CHECK_ARG(mode != 4 || (H > 1 && W > 1), "fir_nhwc: mode 4 needs H, W > 1");
   INDM_CHECK_ARG(mode != 2 || (H % 2 == 0 && W % 2 == 0), "fir_nhwc: down needs even H, W");

@@ -151,16 +151,23 @@ def ref_model(cfg, seed):
     return model, shapes
 
 
-def make_ncsnpp():
+def make_ncsnpp(only=None):
     mutils, sde_lib = rl.load('models.utils', 'sde_lib')
     specs = {
         'tiny_vp': ('configs/vp/CIFAR10/indm_fid.py', True, 3),
         'tiny_ve': ('configs/ve/CIFAR10/indm.py', True, 3),
         'vp_cifar': ('configs/vp/CIFAR10/indm_fid.py', False, 2),
         've_cifar': ('configs/ve/CIFAR10/indm.py', False, 2),
+        # BASELINE configs 4 / 5: 3x64x64, the deep variant (model.num_res_blocks = 8), one image
+        've_celeba': ('configs/ve/CELEBA/indm.py', False, 1),
+        'vp_celeba': ('configs/vp/CELEBA/indm_nll.py', False, 1),
     }
     for tag, (path, is_tiny, B) in specs.items():
+        if only is not None and tag not in only:
+            continue
         cfg = rl.get_config(path)
+        if tag.endswith('celeba'):
+            cfg.model.num_res_blocks = 8
         if is_tiny:
             tiny(cfg)
         model, shapes = ref_model(cfg, seed=11)
@@ -723,6 +730,10 @@ def _full_flow(tag, seed=21):
     pcfg = pconfigs.get_config(pname)
     flow.module.load_state_dict({k: torch.from_numpy(v) for k, v in oflow.synth_params(pcfg, seed).items()})
     return fm, cfg, pcfg, flow
+
+
+def make_ncsnpp_celeba():
+    make_ncsnpp(only=('ve_celeba', 'vp_celeba'))
 
 
 def make_fullflow():

@@ -364,3 +364,33 @@ def test_score_vjp_at_bench_batch(mode, tol):
     e_s, e_v = rel_l2(sc[:B].detach().cpu().numpy(), g['score']), rel_l2(vjp[:B].cpu().numpy(), g['vjp'])
     print(f'batch {BENCH_BATCH} {mode}: score rel-L2 {e_s:.3e}, input-VJP rel-L2 {e_v:.3e}')
     assert e_s < tol and e_v < tol
+
+
+@pytest.mark.parametrize("mode,tol", [('tf32', 1e-3), ('bf16', 2e-2)])
+@pytest.mark.parametrize("tag", ['ve_celeba', 'vp_celeba'])
+def test_celeba_deep_score_network_matches_reference(tag, mode, tol):
+    """BASELINE configs 4 / 5: 3x64x64 with model.num_res_blocks = 8 (142.9 GFLOP per image) against the live reference's output
+    for one image (tests/golden/ncsnpp_*_celeba.npz), evaluated inside a batch of 16 so that the 64-wide feature maps take the
+    padded-pixel kernel and CTA pairs, as they do at the benched batch."""
+    from indm_b200 import sde_lib
+    from indm_b200.models import utils as mutils
+    g = load_npz(f'ncsnpp_{tag}.npz')
+    cfg = configs.get_config('ve/CELEBA/indm' if tag == 've_celeba' else 'vp/CELEBA/indm_nll')
+    cfg.model.num_res_blocks = 8
+    cfg.device = torch.device('cuda:0')
+    model = mutils.create_model(cfg)
+    model.load_state_dict({'module.' + k: torch.from_numpy(v) for k, v in oncsnpp.synth_params(cfg, int(g['seed'])).items()})
+    model.eval()
+    model.module.compute_mode = mode
+    sde = sde_lib.get_sde(cfg)
+    NB = 16
+    B = g['x'].shape[0]
+    rng = np.random.default_rng(9)
+    x = cu(_embed(g['x'], NB, 6, scale=float(np.std(g['x']))))
+    t = cu(np.concatenate([g['t'], rng.uniform(0.05, 0.95, size=NB - B).astype(np.float32)]))
+    with torch.no_grad():
+        score = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)(x, t)
+    torch.cuda.synchronize()
+    e = rel_l2(score[:B].cpu().numpy(), g['score'])
+    print(f'{tag} {mode} (batch {NB}): score rel-L2 {e:.3e}')
+    assert torch.isfinite(score).all() and e < tol

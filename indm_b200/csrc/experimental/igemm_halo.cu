@@ -1,18 +1,19 @@
-// EXPERIMENTAL — not part of libindm_b200.so, not on any product path, never run on hardware yet (written in round 1 after the
-// GPU budget was spent; it compiles for sm_100a, nothing more is claimed).  Build: `make -C indm_b200/csrc experimental`.
+// EXPERIMENT OF RECORD — not part of libindm_b200.so, not on any product path.  Build: `make -C indm_b200/csrc experimental`,
+// run: `python tools/experimental/halo_conv_check.py` (INDM_HALO_VARIANT = 0 / 1).  The production kernel that grew out of it is
+// csrc/igemm_halo.cu.
 //
-// Padded-pixel implicit GEMM for 3x3 stride-1 pad-1 convolutions (index math validated on the CPU by
-// tools/halo_igemm_model.py + tests/test_halo_model_cpu.py).  Per 64-channel K chunk ONE TMA box
-// [1][R + 2][W + 2][64] at (y0 - 1, -1) lands in shared memory as (R + 2)(W + 2) consecutive 128-byte rows; tap (ty, tx) of the
-// 3x3 window is then the same tile read from a start address advanced by (ty (W + 2) + tx) rows, so the A operand is loaded once
-// per chunk instead of once per tap.  GEMM row m <-> output position (y0 + m / (W + 2), m % (W + 2)); rows with m % (W + 2) >= W or
-// m >= R (W + 2) are junk (computed, never stored).
+// Padded-pixel implicit GEMM for 3x3 stride-1 pad-1 convolutions in its simplest form (one CTA per tile, one accumulator, 4
+// epilogue warps storing bf16 rows straight from registers).  Per 64-channel K chunk ONE TMA box [1][R + 2][W + 2][64] at
+// (y0 - 1, -1) lands in shared memory as (R + 2)(W + 2) consecutive 128-byte rows; tap (ty, tx) of the 3x3 window is the same tile
+// read from a start address advanced by (ty (W + 2) + tx) rows.  GEMM row m <-> output position (y0 + m / (W + 2), m % (W + 2)).
 //
-// What round 2 has to establish on the device before anything is built on this:
-//   1. tcgen05 reads a 128B-swizzled K-major tile correctly from a start address that is a multiple of 128 B but not of 1024 B
-//      when the descriptor's base-offset field (bits 49-51) carries (start >> 7) & 7  (PTX ISA, matrix descriptor);
-//   2. rows past the loaded box (never written, possibly NaN bit patterns) only ever contaminate junk rows.
-// Deliberately simple otherwise: one CTA per tile, one accumulator, 4 epilogue warps storing bf16 rows straight from registers.
+// What it established on a B200 (round 2):
+//   * variant 1 (descriptor base-offset field left 0): rel-L2 1.7e-3 against torch's convolution on every shape = BF16 output
+//     rounding.  tcgen05 reads a 128B-swizzled K-major tile correctly from a start address that is a multiple of 128 B but not of
+//     1024 B with NO base offset: the swizzle is a function of the absolute shared-memory address, like TMA's.
+//   * variant 0 (base-offset = (start >> 7) & 7, the reading of the PTX ISA text round 1 had assumed): rel-L2 0.9 — wrong.
+//   * rows past the loaded box only ever contaminate junk rows (every MMA row is independent).
+//   * even this form ran the 128 -> 128 32x32 layer at 439 TFLOP/s (production tap-shifted kernel: 623).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>

@@ -206,3 +206,46 @@ def test_joint_flow_score_step_matches_reference(mode, tol, step_tol, ema_tol):
         # (models/ema.py:40: decay = min(decay, (1 + n) / (10 + n)) = 2 / 11); the rel-L2 of the step above bounds how many flip
         lr_ = cfg.optim.lr if t == 's' else cfg.flow.lr
         assert e_ema < max(ema_tol, 2.0 * lr_), key
+
+
+def test_training_after_sampling_on_the_same_flow_engines_at_batch_128():
+    """Regression (round 2): sampling (flow reverse on the TF32 engine) followed, in the same process, by joint training steps — first
+    with the default policy (BF16 blocks, TF32 encoder legs on that same engine), then with the TF32-blocks policy.  With one
+    memory-pool handle shared by an engine's CUDA graphs this sequence faulted (illegal address / caching-allocator assert) at batch
+    128 once graphs had been dropped; every graph owns its pool now.  Small score network: the flow is what is exercised."""
+    from indm_b200 import losses, sde_lib, precision
+    from indm_b200.models import utils as mutils
+    from indm_b200.models.ema import ExponentialMovingAverage
+    B = 128
+    cfg = configs.get_config('vp/CIFAR10/indm_nll')
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks, cfg.model.attn_resolutions = 128, (1, 2), 1, (16,)
+    cfg.device = torch.device('cuda:0')
+    torch.manual_seed(0)
+    model = mutils.create_model(cfg)
+    flow = fm.create_flow_model(cfg)
+    flow.eval()
+    sde = sde_lib.get_sde(cfg)
+    z = torch.randn(B, 3, 32, 32, device='cuda')
+    for _ in range(2):
+        x, _ = fm.flow_forward(cfg, flow, z, log_det=None, reverse=True)
+    assert torch.isfinite(x).all()
+    state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model,
+                 ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+    flow_state = dict(optimizer=losses.get_optimizer(cfg, flow.parameters(), lr=cfg.flow.lr), model=flow,
+                      ema=ExponentialMovingAverage(flow.parameters(), decay=cfg.flow.ema_rate), step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    batch = torch.rand(B, 3, 32, 32, device='cuda') * 2 - 1
+    try:
+        for _ in range(3):
+            res = step_fn(state, flow_state, batch)
+            assert torch.isfinite(res[0]).all()
+        precision.set_policy('flow', 'training', 'tf32')
+        for _ in range(3):
+            res = step_fn(state, flow_state, batch)
+            assert torch.isfinite(res[0]).all()
+        flow.eval()
+        x, _ = fm.flow_forward(cfg, flow, z, log_det=None, reverse=True)      # and back to sampling on the updated weights
+        torch.cuda.synchronize()
+        assert torch.isfinite(x).all()
+    finally:
+        precision.set_policy('flow', 'training', 'bf16')

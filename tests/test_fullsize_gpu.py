@@ -117,7 +117,9 @@ def _check_digest(names, norms, projs, subs, get, tol_norm, tol_sub, label, floo
     return worst_n, worst_p, worst_s
 
 
-@pytest.mark.parametrize("mode,tol_z,tol_ld,tol_g", [('auto', 5e-3, 5e-2, 8e-2), ('tf32', 1e-4, 1e-3, 5e-3), ('bf16', 5e-3, 5e-2, 8e-2)])
+# 'auto' = the default policy the training leg of bench.py runs: BF16 iResBlocks, 3xTF32 posterior encoder / KL -> the loss term
+# (logdet - KL) is held to north_star's 1e-3 relative (observed 4e-6 - 1e-5), the latent to 2e-4 max-abs (observed 4e-5 - 6e-5)
+@pytest.mark.parametrize("mode,tol_z,tol_ld,tol_g", [('auto', 2e-4, 1e-3, 2e-2), ('tf32', 1e-4, 1e-3, 5e-3), ('bf16', 5e-3, 5e-2, 8e-2)])
 @pytest.mark.parametrize("tag", ['cifar', 'celeba'])
 def test_fullsize_flow_training_forward_and_gradients(tag, mode, tol_z, tol_ld, tol_g):
     """Training-mode forward (batch-statistics encoder, Neumann series) and the gradient of EVERY flow parameter at 16-16 / 512

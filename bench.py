@@ -601,7 +601,20 @@ def nll_leg(dev, world, timed):
 
     ms, launches = timed(call, 1, 1)
     nfe = int(out["r"][2])
-    return {"metric": "nll_images_per_sec", "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": "images/s", "ms_per_call": ms, "nfe": nfe,
+    bpd_policy = out["bpd"].clone()
+    # the same call with BF16 forced everywhere (round 1's timed mode: 0.03 - 0.05 bpd from the reference), side by side
+    bf16 = None
+    try:
+        model.module.compute_mode = flow.module.compute_mode = "bf16"
+        ms_b, _ = timed(call, 1, 1)
+        bf16 = {"value": world * PER_GPU_BATCH / (ms_b * 1e-3), "unit": "images/s", "ms_per_call": ms_b, "nfe": int(out["r"][2]),
+                "ms_per_nfe": ms_b / max(int(out["r"][2]), 1), "max_abs_bpd_diff_vs_policy": float((out["bpd"] - bpd_policy).abs().max())}
+    except Exception as e:
+        bf16 = {"error": repr(e)[:200]}
+    finally:
+        model.module.compute_mode = flow.module.compute_mode = "auto"
+        out["bpd"] = bpd_policy
+    return {"metric": "nll_images_per_sec", "bf16_everywhere": bf16, "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": "images/s", "ms_per_call": ms, "nfe": nfe,
             "ms_per_nfe": ms / max(nfe, 1), "per_gpu_batch": PER_GPU_BATCH, "gpu_launches": launches, "bpd_mean": float(out["bpd"].mean()),
             "finite": bool(torch.isfinite(out["bpd"]).all()), "dtype": "3xTF32 (score forward + input-VJP, flow log-det): the precision pinned at 0.01 bpd",
             "config": "vp/CIFAR10/indm_nll likelihood_fn(method='RK45-device', rtol=atol=1e-5), wolf flow forward + (20+n)-term log-det inside the "

@@ -66,7 +66,9 @@ def test_prior_flow_sample_matches_reference(tag):
     assert float((ld_f.cpu() - ldf_ref).abs().max()) < 1e-3 * max(1.0, float(ldf_ref.abs().max()))
 
 
-@pytest.mark.parametrize("mode,tol", [('tf32', 2e-4), ('bf16', 5e-3)])
+# 'auto' = the default precision policy (indm_b200/precision.py: flow reverse / eval legs in compensated TF32) = what users and bench.py
+# run: held to north_star's numbers.  'bf16' forces BF16 everywhere and is bounded at BF16 operand resolution.
+@pytest.mark.parametrize("mode,tol", [('auto', 2e-4), ('tf32', 2e-4), ('bf16', 5e-3)])
 @pytest.mark.parametrize("tag", ['tiny', 'tiny_sq'])
 def test_wolf_reverse_matches_reference(tag, mode, tol):
     """flow_forward(config, flow, z, reverse=True): prior sample of h + fixed-point inverse of every iResBlock."""
@@ -82,7 +84,7 @@ def test_wolf_reverse_matches_reference(tag, mode, tol):
     assert err < tol
 
 
-@pytest.mark.parametrize("mode,tol,rt_tol", [('tf32', 2e-4, 1e-4), ('bf16', 5e-3, 5e-3)])
+@pytest.mark.parametrize("mode,tol,rt_tol", [('auto', 2e-4, 1e-4), ('tf32', 2e-4, 1e-4), ('bf16', 5e-3, 5e-3)])
 @pytest.mark.parametrize("tag", ['tiny', 'tiny_sq'])
 def test_resflow_forward_and_round_trip(tag, mode, tol, rt_tol):
     """ResidualFlow.fwdpass(x, h, eval_logdet=False) against the reference, then bwdpass with the same h."""
@@ -109,7 +111,7 @@ def _cfg_fwd(tag):
     return cfg
 
 
-@pytest.mark.parametrize("mode,tol_z,tol_ld", [('tf32', 1e-4, 1e-3), ('bf16', 5e-3, 5e-2)])
+@pytest.mark.parametrize("mode,tol_z,tol_ld", [('auto', 1e-4, 1e-3), ('tf32', 1e-4, 1e-3), ('bf16', 5e-3, 5e-2)])
 @pytest.mark.parametrize("tag", ['tiny', 'tiny_sq'])
 def test_wolf_forward_logdet_kl_matches_reference(tag, mode, tol_z, tol_ld):
     """flow_forward(config, flow, x, reverse=False) in eval mode — posterior encoder (BN folded, ELU), reparameterisation,

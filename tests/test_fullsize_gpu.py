@@ -174,7 +174,10 @@ def _joint_models(mode, dropout=None, damp=1.0):
     return cfg, model, flow, sde_lib.get_sde(cfg)
 
 
-@pytest.mark.parametrize("mode,tol,upd_tol", [('auto', 5e-2, 0.5), ('tf32', 2e-3, 6e-2)])
+# 'auto': the default training policy (BF16 score net + iResBlocks, TF32 encoder legs): losses within 2e-3 (the score loss carries the
+# BF16 score network, 3e-4; the flow loss 1e-5), updates as vectors within 0.5 (first Adam step = lr * sign(grad): BF16 flips signs of
+# near-zero gradients)
+@pytest.mark.parametrize("mode,tol,upd_tol", [('auto', 2e-3, 0.5), ('tf32', 2e-3, 6e-2)])
 def test_fullsize_joint_step_matches_reference(mode, tol, upd_tol):
     """flow_step_fn_nll (losses.py:258-320) with the full DDPM++ and the full wolf flow, batch 2: the four loss vectors and the
     applied update of EVERY parameter of both networks (1006 tensors; the first AdamW step is ~ lr * sign(grad), so the update is

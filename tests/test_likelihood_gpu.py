@@ -37,7 +37,8 @@ def _draws(g, which, nblk):
     return flow_kw, cu(g[f'{which}_rad']) * 2 - 1., [cu(g[f'{which}_gauss_{i}']) for i in range(4)], cu(g[f'{which}_u'])
 
 
-@pytest.mark.parametrize("mode,tol", [('tf32', 0.01), ('bf16', 0.1)])
+# 'auto' = the default precision policy (likelihood leg: score forward + Hutchinson VJP and flow log-det in compensated TF32): 0.01 bpd
+@pytest.mark.parametrize("mode,tol", [('auto', 0.01), ('tf32', 0.01), ('bf16', 0.1)])
 def test_pf_ode_nll_matches_reference(mode, tol):
     g, cfg, model, flow, sde = _setup(mode)
     flow_kw, rad, gauss, _ = _draws(g, 'nll', len(oflow.block_layout(cfg)))
@@ -53,7 +54,7 @@ def test_pf_ode_nll_matches_reference(mode, tol):
     # The PF-ODE of this random-weight network amplifies perturbations ~100x (measured on the live reference: 1e-5 relative
     # weight noise moves z by 1e-3), so the BF16 latent (score error ~1e-2 per evaluation) is only sanity-bounded; the
     # validation precision is held to 2e-2 (observed 6e-4).
-    assert e_z < (2e-2 if mode == 'tf32' else 0.6)
+    assert e_z < (0.6 if mode == 'bf16' else 2e-2)
 
 
 def test_pf_ode_nll_device_integrator_matches_reference():
@@ -80,7 +81,7 @@ def test_pf_ode_nll_device_integrator_matches_reference():
 # 0.01 bpd (north_star) is held in the validation precision (observed 1e-4).  The BF16 Hutchinson term carries the BF16 rounding
 # of one forward + one VJP (score / VJP rel-L2 1e-2): observed 0.039 - 0.052 bpd from run to run (fp32 atomics in the fused
 # GroupNorm statistics reorder the roundings), so the production precision is bounded at 0.08.
-@pytest.mark.parametrize("mode,tol", [('tf32', 0.01), ('bf16', 0.08)])
+@pytest.mark.parametrize("mode,tol", [('auto', 0.01), ('tf32', 0.01), ('bf16', 0.08)])
 def test_nelbo_matches_reference(mode, tol):
     g, cfg, model, flow, sde = _setup(mode)
     flow_kw, rad, gauss, u = _draws(g, 'elbo', len(oflow.block_layout(cfg)))

@@ -113,6 +113,10 @@ typedef struct indm_igemm {
                             feature maps) split K across CTAs; a finish kernel reduces the partial sums and applies the epilogue.
                             Bytes needed: up to (#SMs / #tiles) * N*H*W*Cout*4; smaller workspaces just split less. */
   int64_t splitk_ws_bytes;
+  /* padded-pixel ("PP") operand layout (round 2, small feature maps): a (and a2) point to a buffer of
+   * ((N (H + 1) + 1) (W + 2)) rows of Cin channels in which pixel (n, y, x) lives at row (n (H + 1) + y + 1)(W + 2) + x + 1 and
+   * every other row is zero (written by indm_gn_apply_pp).  Only for taps == 9, stride 1, BF16, plain epilogues; outputs are dense. */
+  int32_t a_pp;
 } indm_igemm_t;
 
 int indm_igemm(const indm_igemm_t* desc, void* stream);
@@ -143,6 +147,14 @@ int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, 
 int indm_gn_apply_dropout(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
                           const float* partial, const float* gamma, const float* beta, float eps, int act_silu, void* out,
                           int out_dtype, float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream, void* stream);
+
+/* indm_gn_apply (no resampling; optional dropout as in indm_gn_apply_dropout, drop_ctl may be NULL) writing `out` (and the optional
+ * un-normalised copy `raw`) in the padded-pixel layout of indm_igemm_t.a_pp: pixel (n, y, x) -> row (n (H + 1) + y + 1)(W + 2) + x + 1
+ * of a buffer of (N (H + 1) + 1)(W + 2) rows of C channels.  Only the interior rows are written: the caller zeroes the buffer
+ * once and the border rows stay zero (the 'same' padding of the 3x3 convolutions of ResnetBlockBigGANpp, models/layerspp.py:262-281). */
+int indm_gn_apply_pp(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                     const float* partial, const float* gamma, const float* beta, float eps, int act_silu, void* out, void* raw,
+                     int out_dtype, float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream, void* stream);
 
 /* Row softmax of fp32 scores s[rows][cols] -> probabilities in out_dtype (models/layerspp.py:96-97). */
 int indm_softmax_rows(const float* s, void* out, int64_t rows, int cols, int out_dtype, void* stream);

@@ -40,6 +40,7 @@ class IgemmDesc(C.Structure):
         ("mul", C.c_void_p), ("mul_ld", C.c_int64), ("aux_cos", C.c_void_p),
         ("gn_goff", C.c_int32), ("gn2_partial", C.c_void_p), ("gn2_cpg", C.c_int32), ("gn2_groups", C.c_int32), ("gn2_goff", C.c_int32),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
+        ("a_pp", C.c_int32),
     ]
 
 
@@ -83,6 +84,8 @@ _SIGS = {
                           C.c_int, C.c_int, _vp, _vp, _vp, _f32, _vp, C.c_int, _vp, C.c_int, C.c_int, _f32, _vp, C.c_uint32, _vp],
     "indm_gn_apply_dropout": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32, C.c_int,
                               _vp, C.c_int, _f32, _vp, C.c_uint32, _vp],
+    "indm_gn_apply_pp": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32, C.c_int,
+                         _vp, _vp, C.c_int, _f32, _vp, C.c_uint32, _vp],
     "indm_cast_scale": [_vp, _vp, _i64, _f32, C.c_int, _vp],
     "indm_colsum": [_vp, C.c_int, _i64, _i64, C.c_int, _i64, _vp, _i64, _vp, _f32, _vp],
     "indm_sgemm_batched_f32": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _vp, _i64, _i64, _vp, _i64, _i64, _f32, _vp, _i64, _i64,

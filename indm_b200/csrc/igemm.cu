@@ -1075,6 +1075,10 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   if (flowish && d->mul && !d->bias && !d->rowbias && d->act == 0 && !d->aux_cos) kind = 4;
   // 3x3 convolutions of wide feature maps: the padded-pixel kernel loads every activation box once per K chunk instead of once
   // per tap (igemm_halo.cu)
+  if (d->a_pp) {
+    INDM_CHECK_ARG(d->out_mode == 0 && !d->splitk_ws, "igemm: a_pp operands need out_mode 0 and no split-K");
+    return indm_igemm_halo_flat(d, kind, stream_);
+  }
   if (p.ksplit == 1 && d->out_mode == 0 && indm_halo_eligible(d, kind)) return indm_igemm_halo(d, kind, stream_);
   // TMA-store epilogue (KIND 5 / 6) for the plain kinds when every 32-row slab of the tile is a rectangular box of the output
   // grid: the tile decomposes exactly (BW BH BN = 128, all powers of two) and the output rows are 16-byte aligned

@@ -30,7 +30,13 @@ namespace {
 
 constexpr int kMaxA = 4, kMaxB = 12;
 
-template <int BLOCK_N, int EK>     // EK 1: bf16 NHWC out (+ bias + per-image bias); EK 2: fp32 NHWC out (+ bias + residual)
+// FLAT (round 2, small feature maps): the A operand lives in the padded-pixel ("PP") layout — pixel (n, y, x) at row
+// (n (H + 1) + y + 1) Wp + x + 1 of a zero-bordered buffer, written by indm_gn_apply_pp — so the WHOLE BATCH is one sequence of padded
+// pixels: tile k = padded pixels 128 k .. + 127 regardless of image boundaries, one 2-D TMA box of 128 + 2 Wp + 2 rows per chunk,
+// tap offset ty Wp + tx, both CTAs of a pair take consecutive tiles.  4x4 / 8x8 maps, whose tap-shifted tiles re-read a 16 KB A tile
+// for every tap and sat on the per-SM L2 -> SM ingest limit (~0.5 us per K iteration, 0.07 - 0.35 of the tensor peak), load A once
+// per chunk.  Border rows are computed and dropped (8x8: 64 of 90 padded pixels are real).
+template <int BLOCK_N, int EK, bool FLAT>     // EK 1: bf16 NHWC out (+ bias + per-image bias); EK 2: fp32 NHWC out (+ bias + residual)
 __global__ void __launch_bounds__(320, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const HaloParams p) {
@@ -57,7 +63,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_trigger();
   const int rank = (int)cluster_ctarank();
   const int img_pairs = (p.N + 1) / 2;
-  const int total = img_pairs * p.tiles_per_img * p.n_tiles;
+  // FLAT: tiles_per_img holds the number of 128-row tiles of the whole padded batch; work items are pairs of consecutive tiles
+  const int total = FLAT ? ((p.tiles_per_img + 1) / 2) * p.n_tiles : img_pairs * p.tiles_per_img * p.n_tiles;
   const int t_first = (int)(blockIdx.x >> 1), t_step = (int)(gridDim.x >> 1);
 
   if (threadIdx.x == 0) {
@@ -95,8 +102,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto decode = [&](int t, int& nt, int& k, int& n) {
     nt = t % p.n_tiles;
     const int r = t / p.n_tiles;
-    k = r % p.tiles_per_img;
-    n = 2 * (r / p.tiles_per_img) + rank;
+    if (FLAT) {
+      k = 2 * r + rank;      // a tile past the end loads only out-of-bounds rows (zero fill) and stores nothing
+      n = 0;
+    } else {
+      k = r % p.tiles_per_img;
+      n = 2 * (r / p.tiles_per_img) + rank;
+    }
   };
 
   if (warp == 0) {
@@ -117,7 +129,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&a_empty[sa], pa ^ 1u);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2u * p.box_bytes);
-            tma_load_4d_2sm(sA + (size_t)sa * p.a_buf_bytes, ta, &a_full[sa], c * 64, -1, y_first - 1, n);
+            if (FLAT) tma_load_2d_2sm(sA + (size_t)sa * p.a_buf_bytes, ta, &a_full[sa], c * 64, k * 128 - p.Wp - 1);
+            else tma_load_4d_2sm(sA + (size_t)sa * p.a_buf_bytes, ta, &a_full[sa], c * 64, -1, y_first - 1, n);
           }
           __syncwarp();
           if (++sa == p.sa_stages) {
@@ -152,7 +165,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * BLOCK_N;
-        const int s0 = k * 128 - ((k * 128) / p.Wp) * p.Wp;     // first padded pixel of the tile inside its first image row
+        const int s0 = FLAT ? 0 : k * 128 - ((k * 128) / p.Wp) * p.Wp;     // first padded pixel of the tile inside its first image row
         int it = 0;
         for (int seg = 0; seg < 2; ++seg) {
           const int chunks = seg == 0 ? p.chunks1 : p.chunks2;
@@ -212,17 +225,32 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // this lane's own row -> pixel index inside the image (or -1: junk column / past the image / image past the batch); the rows
       // a thread handles in the transposed domain (it * 4 + rsub) get theirs by shuffle: one division per thread per tile
       const int pp = k * 128 + q * 32 + lane;
-      const int y = pp / p.Wp, x = pp - y * p.Wp;
-      const int mine = (x < p.W && y < p.H && n < p.N) ? y * p.W + x : -1;
-      int poff[8];
+      int mine, my_n;
+      if (FLAT) {
+        // padded pixel of the whole batch -> (image, row, column); row 0 of an image's block and columns 0 / W + 1 are borders
+        const int R = pp / p.Wp, col = pp - R * p.Wp;
+        my_n = R / (p.H + 1);
+        const int yr = R - my_n * (p.H + 1);
+        mine = (yr >= 1 && col >= 1 && col <= p.W && my_n < p.N) ? (my_n * p.H + (yr - 1)) * p.W + (col - 1) : -1;
+      } else {
+        const int y = pp / p.Wp, x = pp - y * p.Wp;
+        my_n = n;
+        mine = (x < p.W && y < p.H && n < p.N) ? y * p.W + x : -1;
+      }
+      int poff[8], nrow[8];
       unsigned okmask = 0;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         poff[it] = __shfl_sync(0xffffffffu, mine, it * 4 + rsub);
+        nrow[it] = FLAT ? __shfl_sync(0xffffffffu, my_n, it * 4 + rsub) : n;
         okmask |= (poff[it] >= 0 ? 1u : 0u) << it;
-        if (poff[it] < 0) poff[it] = 0;
+        if (poff[it] < 0) {
+          poff[it] = 0;
+          nrow[it] = 0;
+        }
       }
-      const long long img = (long long)(n < p.N ? n : 0) * p.H * p.W;
+      const int nA = FLAT ? __shfl_sync(0xffffffffu, my_n, 0) : n;        // image of the warp's first row (statistics: nA and nA + 1)
+      const long long img = FLAT ? 0ll : (long long)(n < p.N ? n : 0) * p.H * p.W;
       mbar_wait(&tfull[buf], ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BLOCK_N;
@@ -250,16 +278,21 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bia = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-        if (EK == 1 && p.rowbias) {
+        if (EK == 1 && p.rowbias && !FLAT) {
           const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)(n < p.N ? n : 0) * p.rowbias_ld + c));
           bia.x += rb.x; bia.y += rb.y; bia.z += rb.z; bia.w += rb.w;
         }
-        float gs = 0.f, gq = 0.f;
+        float gs = 0.f, gq = 0.f, gsB = 0.f, gqB = 0.f;     // FLAT: (gs, gq) = rows of image nA, (gsB, gqB) = rows of image nA + 1
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + rsub;
           float4 xv = stg[r * 8 + (chunk ^ (r & 7))];
-          xv.x = (xv.x + bia.x) * p.scale; xv.y = (xv.y + bia.y) * p.scale; xv.z = (xv.z + bia.z) * p.scale; xv.w = (xv.w + bia.w) * p.scale;
+          float4 bi = bia;
+          if (FLAT && EK == 1 && p.rowbias) {             // a warp's rows may belong to two images: the per-image bias goes per row
+            const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)nrow[it] * p.rowbias_ld + c));
+            bi.x += rb.x; bi.y += rb.y; bi.z += rb.z; bi.w += rb.w;
+          }
+          xv.x = (xv.x + bi.x) * p.scale; xv.y = (xv.y + bi.y) * p.scale; xv.z = (xv.z + bi.z) * p.scale; xv.w = (xv.w + bi.w) * p.scale;
           if (EK == 2 && p.residual) {
             xv.x += p.res_scale * rsd[it].x; xv.y += p.res_scale * rsd[it].y; xv.z += p.res_scale * rsd[it].z; xv.w += p.res_scale * rsd[it].w;
           }
@@ -269,40 +302,51 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (EK == 2) *reinterpret_cast<float4*>(p.out_f32 + (img + poff[it]) * p.out_ld + c) = xv;
               else *reinterpret_cast<uint2*>(p.out_bf16 + (img + poff[it]) * p.out_ld + c) = make_uint2(pack_bf16x2(xv.x, xv.y), pack_bf16x2(xv.z, xv.w));
             }
-            gs += (xv.x + xv.y) + (xv.z + xv.w);
-            gq += (xv.x * xv.x + xv.y * xv.y) + (xv.z * xv.z + xv.w * xv.w);
+            const float s_ = (xv.x + xv.y) + (xv.z + xv.w);
+            const float q_ = (xv.x * xv.x + xv.y * xv.y) + (xv.z * xv.z + xv.w * xv.w);
+            if (!FLAT || nrow[it] == nA) {
+              gs += s_;
+              gq += q_;
+            } else {
+              gsB += s_;
+              gqB += q_;
+            }
           }
         }
         if (has_gn && !(p.dbg & 4)) {
           // this thread holds 8 rows x 4 channels; lanes with the same chunk (lane ^ 8, ^ 16) hold the other rows
-          gs += __shfl_xor_sync(0xffffffffu, gs, 8);  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
-          gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
-          {
-            float s1 = gs, q1 = gq;
-            const int cq = p.gn_cpg >> 2;             // chunks per group: 1, 2, 4 or 8
-            for (int o = 1; o < cq; o <<= 1) {
-              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-              q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          auto flush = [&](float a, float b, int nn) {
+            a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+            {
+              float s1 = a, q1 = b;
+              const int cq = p.gn_cpg >> 2;             // chunks per group: 1, 2, 4 or 8
+              for (int o = 1; o < cq; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+              }
+              if (rsub == 0 && (chunk & (cq - 1)) == 0 && nn < p.N) {
+                float* dst = p.gn_partial + ((long long)nn * p.gn_groups + p.gn_goff + c / p.gn_cpg) * 2;
+                atomicAdd(dst, s1);
+                atomicAdd(dst + 1, q1);
+              }
             }
-            if (rsub == 0 && (chunk & (cq - 1)) == 0 && n < p.N) {
-              float* dst = p.gn_partial + ((long long)n * p.gn_groups + p.gn_goff + c / p.gn_cpg) * 2;
-              atomicAdd(dst, s1);
-              atomicAdd(dst + 1, q1);
+            if (p.gn2_partial) {
+              float s2 = a, q2 = b;
+              const int cq = p.gn2_cpg >> 2;
+              for (int o = 1; o < cq; o <<= 1) {
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+              }
+              if (rsub == 0 && (chunk & (cq - 1)) == 0 && nn < p.N) {
+                float* dst = p.gn2_partial + ((long long)nn * p.gn2_groups + p.gn2_goff + c / p.gn2_cpg) * 2;
+                atomicAdd(dst, s2);
+                atomicAdd(dst + 1, q2);
+              }
             }
-          }
-          if (p.gn2_partial) {
-            float s2 = gs, q2 = gq;
-            const int cq = p.gn2_cpg >> 2;
-            for (int o = 1; o < cq; o <<= 1) {
-              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-              q2 += __shfl_xor_sync(0xffffffffu, q2, o);
-            }
-            if (rsub == 0 && (chunk & (cq - 1)) == 0 && n < p.N) {
-              float* dst = p.gn2_partial + ((long long)n * p.gn2_groups + p.gn2_goff + c / p.gn2_cpg) * 2;
-              atomicAdd(dst, s2);
-              atomicAdd(dst + 1, q2);
-            }
-          }
+          };
+          flush(gs, gq, FLAT ? nA : n);
+          if (FLAT) flush(gsB, gqB, nA + 1);      // zero when the warp's rows all belong to one image (adds nothing)
         }
         __syncwarp();   // the staging buffer is rewritten by the next slab
       }
@@ -313,7 +357,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
-template <int BLOCK_N, int EK>
+template <int BLOCK_N, int EK, bool FLAT = false>
 int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2, HaloParams p, cudaStream_t stream) {
   constexpr int B_BYTES = (BLOCK_N / 2) * 128;
   const int overhead = 1024 + 8 * 4096 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
@@ -330,7 +374,7 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a
   }
   p.sb_stages = sb;
   const size_t smem = (size_t)overhead + (size_t)p.sa_stages * p.a_buf_bytes + (size_t)sb * B_BYTES;
-  auto kern = igemm_halo_kernel<BLOCK_N, EK>;
+  auto kern = igemm_halo_kernel<BLOCK_N, EK, FLAT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -340,7 +384,7 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a
     }
     configured = true;
   }
-  const long long items = (long long)((p.N + 1) / 2) * p.tiles_per_img * p.n_tiles;
+  const long long items = FLAT ? (long long)((p.tiles_per_img + 1) / 2) * p.n_tiles : (long long)((p.N + 1) / 2) * p.tiles_per_img * p.n_tiles;
   const int half_sms = indm_num_sms() / 2;
   const int grid = 2 * (int)(items < half_sms ? items : half_sms);
   indm_launch_pdl_cluster2(kern, dim3(grid), dim3(320), smem, stream, a, b, a2, b2, p);
@@ -432,4 +476,85 @@ int indm_igemm_halo(const indm_igemm_t* d, int kind, void* stream_) {
   }
   if (block_n == 256) return kind == 1 ? launch_halo<256, 1>(tmA, tmB, tmA2, tmB2, p, stream) : launch_halo<256, 2>(tmA, tmB, tmA2, tmB2, p, stream);
   return kind == 1 ? launch_halo<128, 1>(tmA, tmB, tmA2, tmB2, p, stream) : launch_halo<128, 2>(tmA, tmB, tmA2, tmB2, p, stream);
+}
+
+// ---------------------------------------------------------------- padded-pixel ("PP") operand layout, whole batch as one pixel sequence
+int indm_igemm_halo_flat(const indm_igemm_t* d, int kind, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  INDM_CHECK_ARG(d->dtype == INDM_DTYPE_BF16 && d->taps == 9 && (d->stride == 0 || d->stride == 1) && !d->batched_b,
+                 "igemm (a_pp): the padded-pixel operand layout is for BF16 3x3 stride-1 convolutions");
+  INDM_CHECK_ARG(kind == 1 || kind == 2, "igemm (a_pp): only the plain epilogues (bf16 out [+ bias + row bias] / fp32 out [+ bias + residual])");
+  INDM_CHECK_ARG(d->Cin % 64 == 0 && (!d->a2 || d->Cin2 % 64 == 0) && d->Cout % 64 == 0, "igemm (a_pp): Cin %% 64, Cout %% 64");
+  INDM_CHECK_ARG(d->a_ld == 0 && d->a_img_stride == 0 && d->a2_ld == 0 && d->b_ld == 0 && d->b_tap_stride == 0 && d->b2_ld == 0,
+                 "igemm (a_pp): dense operands only");
+  HaloParams p{};
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2;
+  INDM_CHECK_ARG(128 + 2 * p.Wp + 2 <= 256, "igemm (a_pp): W too large for one box (W <= 61)");
+  const long long T = ((long long)d->N * (d->H + 1) + 1) * p.Wp;          // rows of the padded buffer
+  p.tiles_per_img = (int)((T + 127) / 128);
+  // tile width: the widest whose pair count still fills most of the chip (A costs one box per pixel tile here, so narrow N tiles
+  // re-read little; B is what a CTA mostly ingests, in proportion to the tile width)
+  static const int forced_bn = []() { const char* e = getenv("INDM_PP_BLOCKN"); return e ? atoi(e) : 0; }();
+  const long long pairs = (p.tiles_per_img + 1) / 2;
+  int block_n = 64;
+  if (d->Cout % 256 == 0 && pairs * (d->Cout / 256) >= indm_num_sms() / 4) block_n = 256;
+  else if (pairs * (d->Cout / 128) >= indm_num_sms() / 4) block_n = 128;
+  if (forced_bn && d->Cout % forced_bn == 0) block_n = forced_bn;
+  p.n_tiles = d->Cout / block_n;
+  p.Cout = d->Cout;
+  p.chunks1 = d->Cin / 64;
+  p.chunks2 = d->a2 ? d->Cin2 / 64 : 0;
+  const int box_rows = 128 + 2 * p.Wp + 2;
+  p.box_bytes = (uint32_t)box_rows * 128u;
+  p.a_buf_bytes = (p.box_bytes + 1023u) & ~1023u;
+  p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
+  p.residual = d->residual; p.res_ld = d->res_ld ? d->res_ld : d->Cout;
+  p.scale = d->scale; p.res_scale = d->res_scale;
+  p.out_f32 = d->out_f32; p.out_bf16 = (__nv_bfloat16*)d->out_bf16; p.out_ld = d->out_ld ? d->out_ld : d->Cout;
+  p.gn_partial = d->gn_partial; p.gn_cpg = d->gn_cpg; p.gn_groups = d->gn_groups; p.gn_goff = d->gn_goff;
+  p.gn2_partial = d->gn2_partial; p.gn2_cpg = d->gn2_cpg; p.gn2_groups = d->gn2_groups; p.gn2_goff = d->gn2_goff;
+  { static const int dbg_flags = []() { const char* e = getenv("INDM_IGEMM_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg_flags; }
+  if (p.gn_partial) {
+    INDM_CHECK_ARG(p.gn_cpg >= 4 && 32 % p.gn_cpg == 0 && (!p.gn2_partial || (p.gn2_cpg >= 4 && 32 % p.gn2_cpg == 0)),
+                   "igemm (a_pp): fused GroupNorm statistics need cpg | 32");
+    INDM_CHECK_ARG((d->H + 1) * p.Wp >= 32, "igemm (a_pp): fused GroupNorm statistics need >= 32 padded pixels per image (a warp's rows may span two images, not three)");
+  }
+  INDM_CHECK_ARG((((uintptr_t)d->out_bf16 | (uintptr_t)d->out_f32 | (uintptr_t)d->residual | (uintptr_t)d->rowbias | (uintptr_t)d->bias) & 15) == 0 &&
+                 p.out_ld % 4 == 0 && p.res_ld % 4 == 0 && p.rowbias_ld % 4 == 0, "igemm (a_pp): 16-byte aligned epilogue operands");
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  {
+    const uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)T};
+    const uint64_t str[1] = {(uint64_t)d->Cin * 2};
+    const uint32_t box[2] = {64u, (uint32_t)box_rows};
+    int rc = indm_make_tmap(&tmA, dt, 2, d->a, dims, str, box, "igemm (a_pp) A");
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, 9ull};
+    const uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout * d->Cin * 2};
+    const uint32_t box[3] = {64u, (uint32_t)(block_n / 2), 1u};
+    int rc = indm_make_tmap(&tmB, dt, 3, d->b, dims, str, box, "igemm (a_pp) B");
+    if (rc) return rc;
+  }
+  if (d->a2) {
+    const uint64_t dims[2] = {(uint64_t)d->Cin2, (uint64_t)T};
+    const uint64_t str[1] = {(uint64_t)d->Cin2 * 2};
+    const uint32_t box[2] = {64u, (uint32_t)box_rows};
+    int rc = indm_make_tmap(&tmA2, dt, 2, d->a2, dims, str, box, "igemm (a_pp) A2");
+    if (rc) return rc;
+    const uint64_t bdims[3] = {(uint64_t)d->Cin2, (uint64_t)d->Cout, 1ull};
+    const uint64_t bstr[2] = {(uint64_t)d->Cin2 * 2, (uint64_t)d->Cout * d->Cin2 * 2};
+    const uint32_t bbox[3] = {64u, (uint32_t)(block_n / 2), 1u};
+    rc = indm_make_tmap(&tmB2, dt, 3, d->b2, bdims, bstr, bbox, "igemm (a_pp) B2");
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
+  if (block_n == 256)
+    return kind == 1 ? launch_halo<256, 1, true>(tmA, tmB, tmA2, tmB2, p, stream) : launch_halo<256, 2, true>(tmA, tmB, tmA2, tmB2, p, stream);
+  if (block_n == 64)
+    return kind == 1 ? launch_halo<64, 1, true>(tmA, tmB, tmA2, tmB2, p, stream) : launch_halo<64, 2, true>(tmA, tmB, tmA2, tmB2, p, stream);
+  return kind == 1 ? launch_halo<128, 1, true>(tmA, tmB, tmA2, tmB2, p, stream) : launch_halo<128, 2, true>(tmA, tmB, tmA2, tmB2, p, stream);
 }

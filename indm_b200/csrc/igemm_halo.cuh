@@ -31,3 +31,5 @@ struct HaloParams {
 // kind: the plain epilogue kind igemm.cu derived (1 = bf16 out [+ bias + per-image bias], 2 = fp32 out [+ bias + residual])
 bool indm_halo_eligible(const indm_igemm_t* d, int kind);
 int indm_igemm_halo(const indm_igemm_t* d, int kind, void* stream);
+// a / a2 in the padded-pixel layout (indm_igemm_t.a_pp): the whole batch as one padded-pixel sequence
+int indm_igemm_halo_flat(const indm_igemm_t* d, int kind, void* stream);

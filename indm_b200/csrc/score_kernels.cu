@@ -2,6 +2,7 @@
 // +nearest-up / mean-down resampling, +raw copy for the fused skip conv), row softmax, input layout conversion,
 // time embedding, small dense layers.  All are HBM/L2-streaming kernels: 128-bit accesses, one fixed channel quad
 // per thread so per-channel parameters live in registers, grids sized from the SM count.
+#include <cstring>
 #include <type_traits>
 
 #include "../../include/indm_b200.h"
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(256) gn_apply_flat_kernel(const TIn* __restric
                                      const float* __restrict__ beta, float eps, int act,
                                      typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ out,
                                      typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type* __restrict__ raw,
-                                     float drop_p, const unsigned long long* __restrict__ drop_ctl, unsigned drop_stream) {
+                                     float drop_p, const unsigned long long* __restrict__ drop_ctl, unsigned drop_stream, int ppH, int ppW) {
+  // ppW > 0: out / raw are padded-pixel buffers (indm_igemm_t.a_pp): pixel (n, y, x) -> row (n (H + 1) + y + 1)(W + 2) + x + 1
   pdl_trigger();
   pdl_wait();
   const bool dropping = DROP && drop_ctl != nullptr && drop_p > 0.f && drop_ctl[1] != 0ull;
@@ -258,10 +260,177 @@ __global__ void __launch_bounds__(256) gn_apply_flat_kernel(const TIn* __restric
           const float4 k = dropout_scale4(drop_seed, drop_stream, (unsigned long long)((n * P + pp) * Q + q), drop_p);
           y = make_float4(y.x * k.x, y.y * k.y, y.z * k.z, y.w * k.w);
         }
-        Vec4<TOut>::store(out + (n * P + pp) * C + c, y);
-        if (raw) Vec4<TOut>::store(raw + (n * P + pp) * C + c, v[u]);
+        const long long orow = ppW ? (n * (ppH + 1) + pp / ppW + 1) * (ppW + 2) + pp % ppW + 1 : n * P + pp;
+        Vec4<TOut>::store(out + orow * C + c, y);
+        if (raw) Vec4<TOut>::store(raw + orow * C + c, v[u]);
       }
     }
+  }
+}
+
+// Streaming variant of gn_apply for a single dense source with BF16 output (round 2).  The register kernels above were bound by
+// instruction issue (~90 instructions per 4 channels: 64-bit index arithmetic, range checks, 8-byte stores), not by HBM: their
+// fp32-input and bf16-input forms took the same time.  Here (1) one producer lane per CTA keeps a ring of STAGES bulk copies
+// (cp.async.bulk, ~16 KB each) in flight into shared memory, so no thread waits on a global load; (2) eight consumer warps handle
+// 8 channels per thread (one 16-byte store), with all 64-bit arithmetic hoisted to once per chunk; an image boundary inside a chunk
+// splits it into segments with constant scale / shift.  Same equal-work pixel ranges as the flat kernel.
+constexpr int kGnStreamMaxStages = 8;
+template <typename TIn>
+__device__ __forceinline__ void gn_load8(const unsigned char* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void gn_load8<float>(const unsigned char* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 16);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void gn_load8<__nv_bfloat16>(const unsigned char* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+template <typename TIn, bool DROP, bool PP, bool RAW>
+__global__ void __launch_bounds__(288) gn_apply_stream_kernel(const TIn* __restrict__ x, int C, long long N, int P, int G, int R, int chunk_px,
+                                       int stages, const float* __restrict__ partial, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int act, __nv_bfloat16* __restrict__ out,
+                                       __nv_bfloat16* __restrict__ raw, float drop_p, const unsigned long long* __restrict__ drop_ctl,
+                                       unsigned drop_stream, int ppH, int ppW, int interleave) {
+  // interleave: chunk j goes to CTA j % gridDim.x, so at any moment the grid reads (and writes) one contiguous window of
+  // gridDim.x chunks instead of gridDim.x far-apart streams; N * P < 2^31 (host check)
+  extern __shared__ __align__(128) unsigned char gn_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(gn_smem);
+  uint64_t* empty = full + kGnStreamMaxStages;
+  unsigned char* ring = gn_smem + 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t px_bytes = (uint32_t)C * (uint32_t)sizeof(TIn);
+  const uint32_t chunk_bytes = (uint32_t)chunk_px * px_bytes;
+  const long long total = N * P;
+  long long per = (total + gridDim.x - 1) / gridDim.x;
+  per = (per + chunk_px - 1) / chunk_px * chunk_px;
+  const long long g0 = interleave ? (long long)blockIdx.x * chunk_px : (long long)blockIdx.x * per;
+  const long long g1 = interleave ? total : min(total, g0 + per);
+  const long long gstep = interleave ? (long long)gridDim.x * chunk_px : (long long)chunk_px;
+  const int nchunks = g1 > g0 ? (int)((g1 - g0 + gstep - 1) / gstep) : 0;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  if (warp == 8) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0; k < nchunks; ++k) {
+        mbar_wait(&empty[s], ph ^ 1u);
+        const long long gp0 = g0 + (long long)k * gstep;
+        const uint32_t bytes = (uint32_t)min((long long)chunk_px, g1 - gp0) * px_bytes;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_load_1d(ring + (size_t)s * chunk_bytes, reinterpret_cast<const unsigned char*>(x) + gp0 * px_bytes, bytes, &full[s]);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+  const bool dropping = DROP && drop_ctl != nullptr && drop_p > 0.f && drop_ctl[1] != 0ull;
+  const unsigned long long drop_seed = dropping ? drop_ctl[0] : 0ull;
+  const int Q8 = C >> 3;
+  const int q = tid % Q8;
+  const int rr = tid / Q8;            // < R = 256 / Q8 by construction
+  const int c = q * 8;
+  const int cpg = C / G;
+  const int ga_ = c / cpg, gb_ = (c + 4) / cpg;
+  const float cnt = (float)((double)P * cpg);
+  float gam[8], bet[8], sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gam[i] = gamma[c + i];
+    bet[i] = beta[c + i];
+    sc[i] = sh[i] = 0.f;
+  }
+  long long n = nchunks ? g0 / P : 0;            // image of the next pixel; n_end: first pixel of image n + 1
+  long long n_end = (n + 1) * (long long)P;
+  long long n_have = -1;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int k = 0; k < nchunks; ++k) {
+    mbar_wait(&full[s], ph);
+    const long long gp0 = g0 + (long long)k * gstep;
+    const int npx = (int)min((long long)chunk_px, g1 - gp0);
+    if (interleave && gp0 >= n_end) {
+      n = (long long)((int)gp0 / P);
+      n_end = (n + 1) * (long long)P;
+    }
+    const unsigned char* src = ring + (size_t)s * chunk_bytes + (uint32_t)c * (uint32_t)sizeof(TIn);
+    __nv_bfloat16* outc = out + gp0 * C + c;
+    __nv_bfloat16* rawc = RAW ? raw + gp0 * C + c : nullptr;
+    int r0 = 0;
+    while (r0 < npx) {
+      const int r1 = (int)min((long long)npx, n_end - gp0);       // pixels [r0, r1) of this chunk belong to image n
+      if (n_have != n) {
+        n_have = n;
+        const float2 pa = *reinterpret_cast<const float2*>(partial + (n * G + ga_) * 2);
+        const float2 pb = *reinterpret_cast<const float2*>(partial + (n * G + gb_) * 2);
+        const float mean_a = pa.x / cnt, mean_b = pb.x / cnt;
+        const float rstd_a = rsqrtf(fmaxf(pa.y / cnt - mean_a * mean_a, 0.f) + eps);
+        const float rstd_b = rsqrtf(fmaxf(pb.y / cnt - mean_b * mean_b, 0.f) + eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float mean = i < 4 ? mean_a : mean_b, rstd = i < 4 ? rstd_a : rstd_b;
+          sc[i] = gam[i] * rstd;
+          sh[i] = bet[i] - mean * sc[i];
+        }
+      }
+      const int pp0 = PP ? (int)(gp0 - n * (long long)P) : 0;      // pixel index inside image n of chunk row 0 (may be negative)
+      const long long pprow0 = PP ? n * (ppH + 1) + 1 : 0;
+      int r = r0 + (rr - r0 % R + R) % R;
+#pragma unroll 2
+      for (; r < r1; r += R) {
+        float v[8], y[8];
+        gn_load8<TIn>(src + (uint32_t)r * px_bytes, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          y[i] = fmaf(v[i], sc[i], sh[i]);
+          if (act) y[i] = silu_fast(y[i]);
+        }
+        if (DROP && dropping) {
+          const unsigned long long qi = (unsigned long long)(gp0 + r) * (unsigned long long)(2 * Q8) + (unsigned long long)(2 * q);
+          const float4 k0 = dropout_scale4(drop_seed, drop_stream, qi, drop_p), k1 = dropout_scale4(drop_seed, drop_stream, qi + 1, drop_p);
+          y[0] *= k0.x; y[1] *= k0.y; y[2] *= k0.z; y[3] *= k0.w; y[4] *= k1.x; y[5] *= k1.y; y[6] *= k1.z; y[7] *= k1.w;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]); o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+        size_t off;
+        if (PP) {
+          const int pp = pp0 + r, yy = pp / ppW, xx = pp - yy * ppW;
+          off = (size_t)((pprow0 + yy) * (ppW + 2) + xx + 1) * C - (size_t)gp0 * C;
+        } else {
+          off = (size_t)((uint32_t)r * (uint32_t)C);
+        }
+        *reinterpret_cast<uint4*>(outc + off) = o;
+        if (RAW) {
+          uint4 w;
+          w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]); w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(rawc + off) = w;
+        }
+      }
+      r0 = r1;
+      if (gp0 + r0 >= n_end) {
+        ++n;
+        n_end += P;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == stages) { s = 0; ph ^= 1u; }
   }
 }
 
@@ -583,17 +752,219 @@ extern "C" int indm_gn_stats(const void* xa, int Ca, const void* xb, int Cb, int
   return INDM_OK;
 }
 
+// Register-path sibling of the stream kernel: same 8-channels-per-thread inner loop with the index arithmetic hoisted, loads
+// straight from global (two rows = 2 x 32 B per thread in flight), no shared memory — so its CTAs can start under the tail of the
+// preceding convolution (programmatic dependent launch), which the 64 KB ring of the stream kernel cannot.
+template <typename TIn, bool DROP, bool PP, bool RAW>
+__global__ void __launch_bounds__(256) gn_apply_flat8_kernel(const TIn* __restrict__ xa, int Ca, const TIn* __restrict__ xb, int Cb, long long N, int P, int G, int R,
+                                      const float* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float eps, int act, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw, float drop_p,
+                                      const unsigned long long* __restrict__ drop_ctl, unsigned drop_stream, int ppH, int ppW) {
+  pdl_trigger();
+  pdl_wait();
+  const bool dropping = DROP && drop_ctl != nullptr && drop_p > 0.f && drop_ctl[1] != 0ull;
+  const unsigned long long drop_seed = dropping ? drop_ctl[0] : 0ull;
+  const int C = Ca + Cb;
+  const int Q8 = C >> 3;
+  const int q = threadIdx.x % Q8;
+  const int rr = threadIdx.x / Q8;
+  if (rr >= R) return;
+  const int c = q * 8;
+  const int cpg = C / G;
+  const int ga_ = c / cpg, gb_ = (c + 4) / cpg;
+  const float cnt = (float)((double)P * cpg);
+  const bool in_a = c < Ca;                       // channel concat of two sources: this thread's 8 channels live in one of them
+  const uint32_t px_bytes = (uint32_t)(in_a ? Ca : Cb) * (uint32_t)sizeof(TIn);
+  const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(in_a ? xa + c : xb + (c - Ca));
+  const long long total = N * P;
+  long long per = (total + gridDim.x - 1) / gridDim.x;
+  per = (per + R - 1) / R * R;
+  const long long g0 = (long long)blockIdx.x * per, g1 = min(total, g0 + per);
+  for (long long n = g0 / P; n * P < g1; ++n) {
+    float sc[8], sh[8];
+    {
+      const float2 pa = *reinterpret_cast<const float2*>(partial + (n * G + ga_) * 2);
+      const float2 pb = *reinterpret_cast<const float2*>(partial + (n * G + gb_) * 2);
+      const float mean_a = pa.x / cnt, mean_b = pb.x / cnt;
+      const float rstd_a = rsqrtf(fmaxf(pa.y / cnt - mean_a * mean_a, 0.f) + eps);
+      const float rstd_b = rsqrtf(fmaxf(pb.y / cnt - mean_b * mean_b, 0.f) + eps);
+      const float4 g0v = *reinterpret_cast<const float4*>(gamma + c), g1v = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float4 b0v = *reinterpret_cast<const float4*>(beta + c), b1v = *reinterpret_cast<const float4*>(beta + c + 4);
+      const float gam[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
+      const float bet[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mean = i < 4 ? mean_a : mean_b, rstd = i < 4 ? rstd_a : rstd_b;
+        sc[i] = gam[i] * rstd;
+        sh[i] = bet[i] - mean * sc[i];
+      }
+    }
+    const long long p0 = max(g0, n * P), p1 = min(g1, (n + 1) * P);       // this image's pixels inside the range (global indices)
+    const int npx = (int)(p1 - p0);
+    const unsigned char* src = xsrc + p0 * px_bytes;
+    __nv_bfloat16* outc = out + p0 * C + c;
+    __nv_bfloat16* rawc = RAW ? raw + p0 * C + c : nullptr;
+    const int pp0 = PP ? (int)(p0 - n * P) : 0;
+    const long long pprow0 = PP ? n * (ppH + 1) + 1 : 0;
+    for (int r = rr; r < npx; r += 2 * R) {
+      float v[2][8];
+      const bool two = r + R < npx;
+      gn_load8<TIn>(src + (size_t)r * px_bytes, v[0]);
+      if (two) gn_load8<TIn>(src + (size_t)(r + R) * px_bytes, v[1]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const int ru = r + u * R;
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          y[i] = fmaf(v[u][i], sc[i], sh[i]);
+          if (act) y[i] = silu_fast(y[i]);
+        }
+        if (DROP && dropping) {
+          const unsigned long long qi = (unsigned long long)(p0 + ru) * (unsigned long long)(2 * Q8) + (unsigned long long)(2 * q);
+          const float4 k0 = dropout_scale4(drop_seed, drop_stream, qi, drop_p), k1 = dropout_scale4(drop_seed, drop_stream, qi + 1, drop_p);
+          y[0] *= k0.x; y[1] *= k0.y; y[2] *= k0.z; y[3] *= k0.w; y[4] *= k1.x; y[5] *= k1.y; y[6] *= k1.z; y[7] *= k1.w;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]); o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+        size_t off;
+        if (PP) {
+          const int pp = pp0 + ru, yy = pp / ppW, xx = pp - yy * ppW;
+          off = (size_t)((pprow0 + yy) * (ppW + 2) + xx + 1) * C - (size_t)p0 * C;
+        } else {
+          off = (size_t)((uint32_t)ru * (uint32_t)C);
+        }
+        *reinterpret_cast<uint4*>(outc + off) = o;
+        if (RAW) {
+          uint4 w;
+          w.x = pack_bf16x2(v[u][0], v[u][1]); w.y = pack_bf16x2(v[u][2], v[u][3]); w.z = pack_bf16x2(v[u][4], v[u][5]);
+          w.w = pack_bf16x2(v[u][6], v[u][7]);
+          *reinterpret_cast<uint4*>(rawc + off) = w;
+        }
+      }
+    }
+  }
+}
+
+template <typename TIn, bool DROP, bool PP, bool RAW>
+static int gn_apply_flat8_go(dim3 grid, int threads, cudaStream_t stream, const void* xa, int Ca, const void* xb, int Cb, int64_t N, int P, int G, int R,
+                             const float* partial, const float* gamma, const float* beta, float eps, int act, void* out, void* raw,
+                             float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream, int ppH, int ppW) {
+  indm_launch_pdl(gn_apply_flat8_kernel<TIn, DROP, PP, RAW>, grid, dim3(threads), 0, stream, (const TIn*)xa, Ca, (const TIn*)xb, Cb, (long long)N, P, G, R, partial,
+                  gamma, beta, eps, act, (__nv_bfloat16*)out, (__nv_bfloat16*)raw, drop_p, drop_ctl, drop_stream, ppH, ppW);
+  INDM_CHECK_LAUNCH("gn_apply (flat8)");
+  return INDM_OK;
+}
+
+template <typename TIn>
+static int gn_apply_flat8_launch(const void* xa, int Ca, const void* xb, int Cb, int64_t N, int H, int W, int G, const float* partial, const float* gamma,
+                                 const float* beta, float eps, int act, void* out, void* raw, float drop_p,
+                                 const unsigned long long* drop_ctl, unsigned drop_stream, cudaStream_t stream, bool pp) {
+  static const int per_sm = []() { const char* e = getenv("INDM_GN_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 3; }();   // 72 - 120 registers: 3 resident CTAs; best of 2 / 3 / 4 in the forward
+  const int C = Ca + Cb;
+  const int Q8 = C / 8;
+  int R = 256 / Q8;
+  const long long total = (long long)N * H * W;
+  if (R > total) R = (int)total;
+  const int threads = Q8 * R;
+  long long ctas = (long long)indm_num_sms() * per_sm;
+  const long long max_ctas = (total + (long long)R * 2 - 1) / ((long long)R * 2);
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  const bool drop = drop_ctl != nullptr && drop_p > 0.f;
+  const dim3 grid((unsigned)ctas);
+#define GN_F(D, P_, R_) return gn_apply_flat8_go<TIn, D, P_, R_>(grid, threads, stream, xa, Ca, xb, Cb, N, H * W, G, R, partial, gamma, beta, eps, act, out, raw, drop_p, drop_ctl, drop_stream, pp ? H : 0, pp ? W : 0)
+  if (drop) {
+    if (pp) { if (raw) GN_F(true, true, true); GN_F(true, true, false); }
+    if (raw) GN_F(true, false, true);
+    GN_F(true, false, false);
+  }
+  if (pp) { if (raw) GN_F(false, true, true); GN_F(false, true, false); }
+  if (raw) GN_F(false, false, true);
+  GN_F(false, false, false);
+#undef GN_F
+}
+
+static int gn_stream_interleave() {
+  static const int v = []() { const char* e = getenv("INDM_GN_INTERLEAVE"); return (e && e[0] == '1') ? 1 : 0; }();      // measured slower than contiguous ranges (26.9 vs 19.5 us on 32x32x128): off
+  return v;
+}
+
+template <typename TIn, bool DROP, bool PP, bool RAW>
+static int gn_apply_stream_go(dim3 grid, size_t smem, cudaStream_t stream, const void* xa, int C, int64_t N, int P, int G, int R, int chunk_px,
+                              int stages, const float* partial, const float* gamma, const float* beta, float eps, int act, void* out, void* raw,
+                              float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream, int ppH, int ppW) {
+  auto kern = gn_apply_stream_kernel<TIn, DROP, PP, RAW>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      indm_set_error("gn_apply (stream): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return INDM_ERR_CUDA;
+    }
+    configured = true;
+  }
+  indm_launch_pdl(kern, grid, dim3(288), smem, stream, (const TIn*)xa, C, (long long)N, P, G, R, chunk_px, stages, partial, gamma, beta, eps, act,
+                  (__nv_bfloat16*)out, (__nv_bfloat16*)raw, drop_p, drop_ctl, drop_stream, ppH, ppW, gn_stream_interleave());
+  INDM_CHECK_LAUNCH("gn_apply (stream)");
+  return INDM_OK;
+}
+
+template <typename TIn>
+static int gn_apply_stream_launch(const void* xa, int C, int64_t N, int H, int W, int G, const float* partial, const float* gamma,
+                                  const float* beta, float eps, int act, void* out, void* raw, float drop_p,
+                                  const unsigned long long* drop_ctl, unsigned drop_stream, cudaStream_t stream, bool pp) {
+  static const int chunk_kb = []() { const char* e = getenv("INDM_GN_CHUNK_KB"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+  static const int stages = []() { const char* e = getenv("INDM_GN_STAGES"); const int v = e ? atoi(e) : 0; return v > 0 && v <= kGnStreamMaxStages ? v : 4; }();
+  static const int per_sm = []() { const char* e = getenv("INDM_GN_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+  const int R = 256 / (C / 8);
+  int chunk_px = chunk_kb * 1024 / (C * (int)sizeof(TIn));
+  chunk_px = chunk_px / R * R;
+  if (chunk_px < R) chunk_px = R;
+  const long long total = (long long)N * H * W;
+  const long long nchunks = (total + chunk_px - 1) / chunk_px;
+  long long ctas = (long long)indm_num_sms() * per_sm;
+  if (ctas > (nchunks + 1) / 2) ctas = (nchunks + 1) / 2;
+  if (ctas < 1) ctas = 1;
+  const size_t smem = 128 + (size_t)stages * chunk_px * C * sizeof(TIn);
+  const bool drop = drop_ctl != nullptr && drop_p > 0.f;
+  const dim3 grid((unsigned)ctas);
+#define GN_S(D, P_, R_) return gn_apply_stream_go<TIn, D, P_, R_>(grid, smem, stream, xa, C, N, H * W, G, R, chunk_px, stages, partial, gamma, beta, eps, act, out, raw, drop_p, drop_ctl, drop_stream, pp ? H : 0, pp ? W : 0)
+  if (drop) {
+    if (pp) { if (raw) GN_S(true, true, true); GN_S(true, true, false); }
+    if (raw) GN_S(true, false, true);
+    GN_S(true, false, false);
+  }
+  if (pp) { if (raw) GN_S(false, true, true); GN_S(false, true, false); }
+  if (raw) GN_S(false, false, true);
+  GN_S(false, false, false);
+#undef GN_S
+}
+
 template <typename TIn, typename TOut>
 static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64_t N, int H, int W, int G, const float* partial,
                            const float* gamma, const float* beta, float eps, int act, int resample, void* out, void* raw,
-                           float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream, cudaStream_t stream) {
+                           float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream, cudaStream_t stream, bool pp = false) {
   using TO = typename std::conditional<std::is_same<TOut, Tf32Out>::value, float, TOut>::type;
   const int C = Ca + Cb;
   const long long Piter = resample == 2 ? (long long)(H / 2) * (W / 2) : (long long)H * W;
   const GnGeom g = gn_geom(C, Piter, N);
   dim3 grid(g.splits, (unsigned)N);
   static const bool flat = []() { const char* e = getenv("INDM_GN_FLAT"); return !(e && e[0] == '0'); }();
-  if (flat && resample == 0 && g.threads <= 256) {
+  INDM_CHECK_ARG(!pp || (resample == 0 && g.threads <= 256), "gn_apply_pp: no resampling, C <= 1024");
+  // single dense source, BF16 out: 8 channels per thread.  INDM_GN_KERNEL = flat8 (default) | stream | flat
+  static const int which = []() { const char* e = getenv("INDM_GN_KERNEL"); return !e ? 2 : (!strcmp(e, "stream") ? 1 : (!strcmp(e, "flat") ? 0 : 2)); }();
+  const bool stream_on = which == 1;
+  if (which == 2 && std::is_same<TOut, __nv_bfloat16>::value && resample == 0 && Ca % 8 == 0 && Cb % 8 == 0 && C / 8 <= 256 &&
+      (((uintptr_t)xa | (uintptr_t)xb | (uintptr_t)out | (uintptr_t)raw) & 15) == 0 && (long long)N * H * W < (1ll << 31)) {
+    return gn_apply_flat8_launch<TIn>(xa, Ca, xb, Cb, N, H, W, G, partial, gamma, beta, eps, act, out, raw, drop_p, drop_ctl, drop_stream, stream, pp);
+  }
+  if (stream_on && std::is_same<TOut, __nv_bfloat16>::value && resample == 0 && Cb == 0 && C % 8 == 0 && C / 8 <= 256 &&
+      (256 % (C / 8) == 0) && (((uintptr_t)xa | (uintptr_t)out | (uintptr_t)raw) & 15) == 0 && (long long)N * H * W < (1ll << 31)) {
+    return gn_apply_stream_launch<TIn>(xa, C, N, H, W, G, partial, gamma, beta, eps, act, out, raw, drop_p, drop_ctl, drop_stream, stream, pp);
+  }
+  if ((flat || pp) && resample == 0 && g.threads <= 256) {
     // equal-work ranges over the (image, pixel) space: grid = resident slots of the chip, or fewer when there is less than one
     // UNR-trip of work per CTA
     const long long total = (long long)N * H * W;
@@ -604,10 +975,10 @@ static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64
     const long long P = (long long)H * W;
     if (drop_ctl != nullptr && drop_p > 0.f)
       indm_launch_pdl(gn_apply_flat_kernel<TIn, TOut, true>, dim3((unsigned)ctas), dim3(g.threads), 0, stream, (const TIn*)xa, Ca, (const TIn*)xb, Cb,
-                      (long long)N, P, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream);
+                      (long long)N, P, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream, pp ? H : 0, pp ? W : 0);
     else
       indm_launch_pdl(gn_apply_flat_kernel<TIn, TOut, false>, dim3((unsigned)ctas), dim3(g.threads), 0, stream, (const TIn*)xa, Ca, (const TIn*)xb, Cb,
-                      (long long)N, P, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream);
+                      (long long)N, P, G, g.R, partial, gamma, beta, eps, act, (TO*)out, (TO*)raw, drop_p, drop_ctl, drop_stream, pp ? H : 0, pp ? W : 0);
     INDM_CHECK_LAUNCH("gn_apply (flat)");
     return INDM_OK;
   }
@@ -628,7 +999,7 @@ static int gn_apply_launch(const void* xa, int Ca, const void* xb, int Cb, int64
 static int gn_apply_impl(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
                          const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
                          void* out, void* raw, int out_dtype, float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream,
-                         void* stream_);
+                         void* stream_, bool pp = false);
 
 extern "C" int indm_gn_apply(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
                              const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
@@ -646,10 +1017,18 @@ extern "C" int indm_gn_apply_dropout(const void* xa, int Ca, const void* xb, int
                        (const unsigned long long*)drop_ctl, drop_stream, stream_);
 }
 
+extern "C" int indm_gn_apply_pp(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
+                                const float* partial, const float* gamma, const float* beta, float eps, int act_silu, void* out,
+                                void* raw, int out_dtype, float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream, void* stream_) {
+  INDM_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "gn_apply_pp: need 0 <= p < 1");
+  return gn_apply_impl(xa, Ca, xb, Cb, in_dtype, N, H, W, G, partial, gamma, beta, eps, act_silu, 0, out, raw, out_dtype, drop_p,
+                       (const unsigned long long*)drop_ctl, drop_stream, stream_, true);
+}
+
 static int gn_apply_impl(const void* xa, int Ca, const void* xb, int Cb, int in_dtype, int64_t N, int H, int W, int G,
                          const float* partial, const float* gamma, const float* beta, float eps, int act_silu, int resample,
                          void* out, void* raw, int out_dtype, float drop_p, const unsigned long long* drop_ctl, unsigned drop_stream,
-                         void* stream_) {
+                         void* stream_, bool pp) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!xb) Cb = 0;
   const int C = Ca + Cb;
@@ -662,7 +1041,7 @@ static int gn_apply_impl(const void* xa, int Ca, const void* xb, int Cb, int in_
   const bool in_f32 = in_dtype == INDM_DTYPE_F32, in_bf = in_dtype == INDM_DTYPE_BF16;
   const bool out_bf = out_dtype == INDM_DTYPE_BF16, out_tf = out_dtype == INDM_DTYPE_TF32, out_f = out_dtype == INDM_DTYPE_F32;
   INDM_CHECK_ARG((in_f32 || in_bf) && (out_bf || out_tf || out_f), "gn_apply: unsupported dtypes %d -> %d", in_dtype, out_dtype);
-#define GN_GO(TI, TO_) return gn_apply_launch<TI, TO_>(xa, Ca, xb, Cb, N, H, W, G, partial, gamma, beta, eps, act_silu, resample, out, raw, drop_p, drop_ctl, drop_stream, stream)
+#define GN_GO(TI, TO_) return gn_apply_launch<TI, TO_>(xa, Ca, xb, Cb, N, H, W, G, partial, gamma, beta, eps, act_silu, resample, out, raw, drop_p, drop_ctl, drop_stream, stream, pp)
   if (in_f32 && out_bf) GN_GO(float, __nv_bfloat16);
   if (in_f32 && out_tf) GN_GO(float, Tf32Out);
   if (in_f32 && out_f) GN_GO(float, float);

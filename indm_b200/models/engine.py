@@ -14,6 +14,7 @@ All 44 Dense_0 layers are evaluated at once (one [N,4nf] x [sum Cout, 4nf] produ
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -27,8 +28,12 @@ class _Buf:
 
 
 class ScoreEngine:
-    def __init__(self, model, batch, mode='bf16', device=None):
+    def __init__(self, model, batch, mode='bf16', device=None, pp=False):
         cfg = model.config
+        # pp: inference-only plan whose small-feature-map residual blocks keep their convolution operands in the padded-pixel
+        # layout (indm_igemm_t.a_pp): the 3x3 convolutions then read every activation once instead of once per tap
+        self.pp = bool(pp) and mode == 'bf16' and not os.environ.get('INDM_NO_PP')
+        self.pp_max_w = int(os.environ.get('INDM_PP_MAX_W', '4'))
         self.model = model
         self.cfg = cfg
         self.N = int(batch)
@@ -190,7 +195,7 @@ class ScoreEngine:
             L.check(fn(*cargs, L._stream()), name)
         self._cur.append(run)
 
-    def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False, dropout=0.0):
+    def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False, dropout=0.0, pp=False):
         """GroupNorm(+SiLU)(+resample) of concat(xa, xb) -> operand tensor (and optional raw copy of the input).
         Emits the statistics launch unless a producer already accumulated them into `slot`."""
         N = self.N
@@ -205,9 +210,19 @@ class ScoreEngine:
         if not stats_done and not (in_dt == L.DTYPE_F32 and self._fuse_stats_into_producers(xa, Ca, xb, Cb, G, part)):
             self._call('indm_gn_stats', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), ctypes.c_int64(H * W), G, part)
         Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
+        odt_ = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32
+        if pp:
+            # zero-bordered padded-pixel buffers: only interior rows are ever written, so the borders stay zero across forwards
+            assert resample == 0
+            rows = (N * (H + 1) + 1) * (W + 2)
+            out = self._alloc((rows, C), self.tdtype, zero=True)
+            raw = self._alloc((rows, C), self.tdtype, zero=True) if want_raw else None
+            self._call('indm_gn_apply_pp', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
+                       act, out, raw, odt_, ctypes.c_float(dropout), self.drop_ctl if dropout > 0.0 else None, ctypes.c_uint32(slot))
+            self._last_gn = None
+            return out, raw
         out = self._op_t((N, Ho, Wo, C))
         raw = self._op_t((N, Ho, Wo, C)) if want_raw else None
-        odt_ = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_TF32
         if dropout > 0.0:
             assert resample == 0 and not want_raw
             self._call('indm_gn_apply_dropout', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
@@ -307,8 +322,9 @@ class ScoreEngine:
             has_skip = hasattr(rb, 'Conv_2')
             resample = 1 if rb.up else (2 if rb.down else 0)
             use_fir = self.fir and resample != 0
+            use_pp = (self.pp and resample == 0 and W <= self.pp_max_w and Cin % 64 == 0 and Cout % 128 == 0)
             h1, raw = self._gn(xa, Ca, xb, Cb, L.DTYPE_F32, H, W, rb.GroupNorm_0, 1, 0 if use_fir else resample,
-                               has_skip and not use_fir)
+                               has_skip and not use_fir, pp=use_pp)
             gn0 = self._last_gn
             Ho, Wo = (2 * H, 2 * W) if resample == 1 else ((H // 2, W // 2) if resample == 2 else (H, W))
             if use_fir:
@@ -341,10 +357,12 @@ class ScoreEngine:
                 kw['out_f32'] = h2
             if fuse_stats:
                 kw.update(gn_partial=self.gn_part[slot1], gn_cpg=cpg1, gn_groups=G1)
+            if use_pp:
+                kw['a_pp'] = 1
             self._igemm(**kw)
             in_dt1 = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
             h3, _ = self._gn(h2, Cout, None, 0, in_dt1, Ho, Wo, rb.GroupNorm_1, 1, 0, False, slot=slot1, stats_done=fuse_stats,
-                             dropout=float(rb.dropout))
+                             dropout=float(rb.dropout), pp=use_pp)
             gn1 = self._last_gn
             # conv1 (+ fused skip 1x1 | + residual), * 1/sqrt(2)
             w1 = self._op_t((9, Cout, Cout)); self._pack_conv(w1, rb.Conv_1.weight)
@@ -363,6 +381,8 @@ class ScoreEngine:
                 self._pack_f32(b1, [rb.Conv_1.bias])
                 assert xb is None and Ca == Cout and resample == 0
                 kw.update(residual=xa, res_ld=Cout, res_scale=inv_sqrt2 if rb.skip_rescale else 1.0)
+            if use_pp:
+                kw['a_pp'] = 1
             self._igemm(**kw)
             self.tape.append(('res_block', dict(rb=rb, gn0=gn0, gn1=gn1, out=out, Cin=Cin, Cout=Cout, Ho=Ho, Wo=Wo, has_skip=has_skip,
                                                 h1=h1, h3=h3, raw=raw, dense_off=dense_off[id(rb)], H=H, W=W, resample=resample,
@@ -813,6 +833,9 @@ class ScoreEngine:
     def build_backward(self, train=False):
         """emit the backward plan: input-VJP only (train=False: likelihood / Hutchinson) or input-VJP + every parameter
         gradient (train=True: losses.get_step_fn)"""
+        if self.pp:
+            raise RuntimeError('ScoreEngine(pp=True) is an inference-only plan (padded-pixel operands are not kept for the backward): '
+                               'use NCSNpp.engine(batch) for vector-Jacobian products')
         if self._plans.get(train) is not None:
             self.bops = self._plans[train]['ops']
             self.gout, self.gx = self._plans[train]['gout'], self._plans[train]['gx']

@@ -128,13 +128,15 @@ class NCSNpp(nn.Module):
         self.compute_mode = 'auto'   # 'auto' (indm_b200/precision.py policy), or 'bf16' / 'tf32' to force one arithmetic
 
     # ---------------------------------------------------------------------------------------------------------------
-    def engine(self, batch, mode=None):
+    def engine(self, batch, mode=None, infer=False):
+        """infer=True: the forward-only plan (ScoreEngine(pp=True)) the samplers run; the default plan also serves the backward"""
         mode = precision.resolve('score', mode or self.compute_mode, 'training' if self.training else 'sampling')
         dev = next(self.parameters()).device
-        key = (int(batch), mode, str(dev))
+        infer = bool(infer) and mode == 'bf16'
+        key = (int(batch), mode, str(dev), infer)
         eng = self._engines.get(key)
         if eng is None:
-            eng = ScoreEngine(self, batch, mode=mode, device=dev)
+            eng = ScoreEngine(self, batch, mode=mode, device=dev, pp=infer)
             self._engines[key] = eng
         return eng
 

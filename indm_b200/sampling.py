@@ -299,7 +299,7 @@ class _GraphedPC:
 
     def __init__(self, config, sde, net, batch, corrector_name, n_steps, probability_flow, seed, predictor_name='reverse_diffusion'):
         self.sde, self.net, self.N = sde, net, batch
-        self.eng = net.engine(batch)
+        self.eng = net.engine(batch, infer=True)      # forward-only plan: padded-pixel operands on the small feature maps
         self.dev = self.eng.dev
         self.langevin = corrector_name == 'langevin'
         self.ald = corrector_name == 'ald'

@@ -525,6 +525,103 @@ def test_igemm_halo_padded_pixel_path(kind, N, S, Cin, Cin2, Cout):
     assert torch.equal(first, out)
 
 
+def to_pp(x_nhwc):
+    """[N,H,W,C] -> the padded-pixel buffer of indm_igemm_t.a_pp: [(N (H + 1) + 1)(W + 2), C], zero borders"""
+    N, H, W, C = x_nhwc.shape
+    buf = torch.zeros((N * (H + 1) + 1, W + 2, C), dtype=x_nhwc.dtype)
+    v = buf[:N * (H + 1)].view(N, H + 1, W + 2, C)
+    v[:, 1:, 1:W + 1] = x_nhwc
+    return buf.reshape(-1, C)
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("N,S,Cin,Cin2,Cout", [(37, 8, 256, 0, 256), (128, 8, 256, 0, 256), (21, 4, 256, 0, 256), (128, 4, 256, 0, 256),
+                                               (9, 8, 128, 256, 128), (7, 16, 128, 0, 256), (3, 8, 64, 0, 128), (1, 4, 64, 0, 128)])
+def test_igemm_whole_batch_padded_pixel_operands(kind, N, S, Cin, Cin2, Cout):
+    """indm_igemm_t.a_pp: 3x3 convolutions of small maps whose operands live in the zero-bordered padded-pixel buffer
+    (indm_gn_apply_pp): the whole batch is one sequence of padded pixels cut into 128-pixel tiles that cross image boundaries,
+    every tap a row offset into one shared-memory box.  Odd batch sizes (ragged last tile / idle second CTA of the last pair),
+    the fused 1x1 skip segment, fused GroupNorm statistics of two consumers where a warp's rows span two images; against fp64."""
+    dtype = L.DTYPE_BF16
+    x = round_in(rnd(N, Cin, S, S, seed=70), dtype)
+    w = round_in(rnd(Cout, Cin, 3, 3, seed=71) / math.sqrt(9 * Cin), dtype)
+    bias = rnd(Cout, seed=72)
+    kw = dict(dtype=dtype, a=to_pp(nhwc(x)).to(torch.bfloat16).to(DEV), a_pp=1, N=N, H=S, W=S, Cin=Cin, b=pack_w(w, dtype), Cout=Cout,
+              taps=9, bias=bias.to(DEV), scale=0.7071, out_ld=Cout)
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    if Cin2:
+        xs = round_in(rnd(N, Cin2, S, S, seed=73), dtype)
+        w2 = round_in(rnd(Cout, Cin2, 1, 1, seed=74) / math.sqrt(Cin2), dtype)
+        kw.update(a2=to_pp(nhwc(xs)).to(torch.bfloat16).to(DEV), Cin2=Cin2, b2=dev_op(w2.reshape(Cout, Cin2), dtype))
+        want = want + F.conv2d(xs.double(), w2.double())
+    want = nhwc(want)
+    stats = (S + 1) * (S + 2) >= 32
+    part = torch.zeros((N, 32, 2), device=DEV)
+    part2 = torch.zeros((N, 16, 2), device=DEV)
+    gn = dict(gn_partial=part, gn_cpg=Cout // 32, gn_groups=32, gn2_partial=part2, gn2_cpg=Cout // 16, gn2_groups=16) if stats else {}
+    if kind == 1:
+        rowb = rnd(N, Cout, seed=75)
+        out = torch.full((N, S, S, Cout), float('nan'), device=DEV, dtype=torch.bfloat16)
+        kw.update(rowbias=rowb.to(DEV), rowbias_ld=Cout, out_bf16=out, **gn)
+        want = (want + rowb[:, None, None, :].double()) * 0.7071
+        tol = 4e-3
+    else:
+        res = rnd(N, S, S, Cout, seed=76)
+        out = torch.full((N, S, S, Cout), float('nan'), device=DEV)
+        kw.update(residual=res.to(DEV), res_ld=Cout, res_scale=0.7071, out_f32=out, **gn)
+        want = want * 0.7071 + res.double() * 0.7071
+        tol = 2e-5
+    L.igemm(**kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    e = rel_l2(out.float().cpu(), want)
+    print(f'a_pp kind {kind} N={N} S={S} Cin={Cin}+{Cin2} Cout={Cout}: rel-L2 {e:.2e}')
+    assert e < tol
+    if stats:
+        for pt, G in ((part, 32), (part2, 16)):
+            g = want.reshape(N, S * S, G, Cout // G)
+            ws, wq = g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))
+            assert rel_l2(pt[..., 0].cpu(), ws) < 2e-3 and rel_l2(pt[..., 1].cpu(), wq) < 2e-3
+    first = out.clone()
+    L.igemm(**kw)
+    torch.cuda.synchronize()
+    assert torch.equal(first, out)
+
+
+def test_igemm_padded_pixel_rejects_what_it_cannot_run():
+    x = torch.zeros(((2 * 5 + 1) * 6, 64), device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros((9, 128, 64), device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros((2, 4, 4, 128), device=DEV)
+    part = torch.zeros((2, 32, 2), device=DEV)
+    with pytest.raises(RuntimeError):       # 4x4 maps: a warp's 32 rows can span three images, no fused statistics
+        L.igemm(dtype=L.DTYPE_BF16, a=x, a_pp=1, N=2, H=4, W=4, Cin=64, b=w, Cout=128, taps=9, out_f32=out, out_ld=128,
+                gn_partial=part, gn_cpg=4, gn_groups=32)
+    with pytest.raises(RuntimeError):       # 1x1 products have no padded-pixel form
+        L.igemm(dtype=L.DTYPE_BF16, a=x, a_pp=1, N=2, H=4, W=4, Cin=64, b=w, Cout=128, taps=1, out_f32=out, out_ld=128)
+
+
+@pytest.mark.parametrize("N,S,C,Cb", [(5, 8, 256, 0), (3, 4, 256, 256), (2, 16, 128, 0)])
+def test_gn_apply_pp_is_gn_apply_scattered_into_the_padded_buffer(N, S, C, Cb):
+    """indm_gn_apply_pp writes exactly what indm_gn_apply writes, at the padded-pixel rows, and never touches the border rows."""
+    xa = rnd(N, S, S, C, seed=80).to(DEV)
+    xb = rnd(N, S, S, Cb, seed=81).to(DEV) if Cb else None
+    Ct = C + Cb
+    gamma, beta = (1 + 0.1 * rnd(Ct, seed=82)).to(DEV), rnd(Ct, seed=83).to(DEV)
+    part = torch.zeros((N, 32, 2), device=DEV)
+    L.call('indm_gn_stats', L.ptr(xa), C, L.ptr(xb) if Cb else None, Cb, L.DTYPE_F32, N, S * S, 32, L.ptr(part))
+    dense = torch.empty((N, S, S, Ct), device=DEV, dtype=torch.bfloat16)
+    raw = torch.empty_like(dense)
+    L.call('indm_gn_apply', L.ptr(xa), C, L.ptr(xb) if Cb else None, Cb, L.DTYPE_F32, N, S, S, 32, L.ptr(part), L.ptr(gamma), L.ptr(beta),
+           1e-6, 1, 0, L.ptr(dense), L.ptr(raw), L.DTYPE_BF16)
+    rows = (N * (S + 1) + 1) * (S + 2)
+    pp = torch.zeros((rows, Ct), device=DEV, dtype=torch.bfloat16)
+    pr = torch.zeros_like(pp)
+    L.call('indm_gn_apply_pp', L.ptr(xa), C, L.ptr(xb) if Cb else None, Cb, L.DTYPE_F32, N, S, S, 32, L.ptr(part), L.ptr(gamma), L.ptr(beta),
+           1e-6, 1, L.ptr(pp), L.ptr(pr), L.DTYPE_BF16, 0.0, None, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(pp.cpu(), to_pp(dense.cpu())) and torch.equal(pr.cpu(), to_pp(raw.cpu()))
+
+
 @pytest.mark.parametrize("N,S,Cin,Cout", [(16, 8, 256, 256), (32, 4, 256, 256)])
 def test_igemm_split_k_path(N, S, Cin, Cout):
     """Launches with too few output tiles to fill the chip can split K across CTAs (indm_igemm_t.splitk_ws: raw partial sums in a

@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--config', default='vp/CIFAR10/indm_fid')
     ap.add_argument('--mode', default='bf16')
     ap.add_argument('--per-op', action='store_true')
+    ap.add_argument('--infer', action='store_true', help='the forward-only plan of the samplers (padded-pixel operands on small maps)')
     a = ap.parse_args()
     cfg = configs.get_config(a.config)
     cfg.device = torch.device('cuda:0')
@@ -29,7 +30,7 @@ def main():
     net.compute_mode = a.mode
     net.eval()
     t0 = time.time()
-    eng = net.engine(a.batch)
+    eng = net.engine(a.batch, infer=a.infer)
     torch.cuda.synchronize()
     print(f'engine build {time.time() - t0:.2f}s, {eng.num_launches} launches/forward, '
           f'{torch.cuda.memory_allocated() / 2**30:.2f} GiB allocated')
@@ -38,6 +39,13 @@ def main():
     for _ in range(3):
         eng.launch()
     torch.cuda.synchronize()
+    if a.infer:
+        base = net.engine(a.batch)
+        base.x_in.copy_(eng.x_in); base.time_cond.copy_(eng.time_cond)
+        base.launch()
+        torch.cuda.synchronize()
+        d = (eng.out.float() - base.out.float()).norm() / base.out.float().norm()
+        print(f'infer plan vs default plan: output rel-L2 {float(d):.3e}')
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     for _ in range(5):

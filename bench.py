@@ -294,14 +294,15 @@ def _closure(op, cls_name=None, key=None):
 def _gn_apply_bytes(op):
     """Algorithmic HBM bytes of one `indm_gn_apply` launch: input read once (fp32 residual stream or bf16) + operand-dtype output
     (+ the raw operand copy when a skip conv follows) written once.  None for any other launch."""
-    if _closure(op, key="name") not in ("indm_gn_apply", "indm_gn_apply_dropout"):
+    name = _closure(op, key="name")
+    if name not in ("indm_gn_apply", "indm_gn_apply_dropout", "indm_gn_apply_pp"):
         return None
     a = _closure(op, key="cargs")
     val = lambda v: getattr(v, "value", v)
     Ca, Cb, in_dt, N, H, W = val(a[1]), (val(a[3]) if val(a[2]) else 0), val(a[4]), val(a[5]), val(a[6]), val(a[7])
-    dropout = _closure(op, key="name") == "indm_gn_apply_dropout"
-    resample = 0 if dropout else val(a[14])
-    raw = None if dropout else val(a[16])
+    dropout = name == "indm_gn_apply_dropout"
+    resample = 0 if name != "indm_gn_apply" else val(a[14])
+    raw = None if dropout else val(a[15] if name == "indm_gn_apply_pp" else a[16])      # padded-pixel borders are never written
     from indm_b200 import _lib as L
     C = Ca + Cb
     Po = H * W * (4 if resample == 1 else 1) // (4 if resample == 2 else 1)
@@ -553,7 +554,7 @@ def ve_pc_leg(dev, world, timed, steps=2, warmup=1, num_scales=NUM_SCALES, globa
 
     ms, launches = timed(call, steps, warmup)
     pk, pk_kind = peaks()
-    eng = model.module.engine(PER_GPU_BATCH)
+    eng = model.module.engine(PER_GPU_BATCH, infer=True)      # the plan the sampler runs
     res = {"metric": METRIC, "value": world * PER_GPU_BATCH / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_pc_step": ms / num_scales,
            "steps": steps, "warmup": warmup, "per_gpu_batch": PER_GPU_BATCH, "num_scales": num_scales, "nfe_per_call": 2 * num_scales,
            "gpu_launches": launches, "finite": bool(torch.isfinite(out["host"]).all()), "dtype": "bf16 (score net) / 3xTF32 (flow inverse)",
@@ -851,7 +852,7 @@ def run_ours(args):
     e2e = world * PER_GPU_BATCH / (ms_e2e * 1e-3)
     pk, pk_kind = peaks()
     traffic = igemm_traffic()
-    eng = net.engine(PER_GPU_BATCH)
+    eng = net.engine(PER_GPU_BATCH, infer=True)               # the plan the sampler runs
     kr = kernel_rooflines(net, eng)
     tf = kr["ig_tflops"]
     peak_tf = pk["bf16_tflops_sustained"]

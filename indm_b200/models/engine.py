@@ -33,7 +33,8 @@ class ScoreEngine:
         # pp: inference-only plan whose small-feature-map residual blocks keep their convolution operands in the padded-pixel
         # layout (indm_igemm_t.a_pp): the 3x3 convolutions then read every activation once instead of once per tap
         self.pp = bool(pp) and mode == 'bf16' and not os.environ.get('INDM_NO_PP')
-        self.pp_max_w = int(os.environ.get('INDM_PP_MAX_W', '4'))
+        self.pp_max_w = int(os.environ.get('INDM_PP_MAX_W', '4'))   # measured: faster on 4x4 maps, slower on 8x8 / 16x16 (border rows)
+        self.pp_convs = 0         # convolutions of this plan that read padded-pixel operands
         self.model = model
         self.cfg = cfg
         self.N = int(batch)
@@ -359,6 +360,7 @@ class ScoreEngine:
                 kw.update(gn_partial=self.gn_part[slot1], gn_cpg=cpg1, gn_groups=G1)
             if use_pp:
                 kw['a_pp'] = 1
+                self.pp_convs += 2
             self._igemm(**kw)
             in_dt1 = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
             h3, _ = self._gn(h2, Cout, None, 0, in_dt1, Ho, Wo, rb.GroupNorm_1, 1, 0, False, slot=slot1, stats_done=fuse_stats,

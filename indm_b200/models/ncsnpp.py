@@ -143,7 +143,12 @@ class NCSNpp(nn.Module):
     def forward(self, x, time_cond):
         if not x.is_cuda:
             raise RuntimeError('indm_b200.NCSNpp.forward needs CUDA tensors: there is no CPU / PyTorch fallback path')
-        eng = self.engine(x.shape[0])
+        anchor = None
+        need_grad = False
+        if torch.is_grad_enabled():
+            anchor = next((p for p in self.parameters() if p.requires_grad), None) if self.training else None
+            need_grad = x.requires_grad or anchor is not None
+        eng = self.engine(x.shape[0], infer=not need_grad)     # nothing to differentiate: the forward-only plan
         scale = None
         if self.config.model.scale_by_sigma:
             if self.embedding_type == 'fourier':
@@ -151,9 +156,7 @@ class NCSNpp(nn.Module):
             else:
                 used_sigmas = self.sigmas[time_cond.long()].float()
             scale = 1.0 / used_sigmas.float()
-        if torch.is_grad_enabled():
-            anchor = next((p for p in self.parameters() if p.requires_grad), None) if self.training else None
-            if x.requires_grad or anchor is not None:
-                return _EngineFunction.apply(x, time_cond, scale, self, anchor is not None, anchor)
+        if need_grad:
+            return _EngineFunction.apply(x, time_cond, scale, self, anchor is not None, anchor)
         out = eng.forward(x.float(), time_cond.float(), scale, train=self.training)
         return out.clone()

@@ -55,6 +55,35 @@ def test_score_network_matches_reference(tag, mode):
     assert e_raw < TOL[mode] and e_score < TOL[mode]
 
 
+@pytest.mark.parametrize("tag", ['vp_cifar', 've_cifar'])
+def test_forward_only_plan_uses_padded_pixel_operands_and_agrees_with_the_default_plan(tag):
+    """NCSNpp.engine(infer=True) — what the samplers and every no-grad forward run — keeps the 4x4 residual blocks' convolution
+    operands in the padded-pixel layout (indm_igemm_t.a_pp).  Same input through both plans: equal within the BF16 tolerance
+    (the golden comparison of the no-grad forward above already runs this plan); and it refuses to build a backward."""
+    g = load_npz(f'ncsnpp_{tag}.npz')
+    cfg = _cfg(tag)
+    model = _model(cfg, int(g['seed']))
+    net = model.module
+    net.compute_mode = 'bf16'
+    B = g['x'].shape[0]
+    fast, base = net.engine(B, infer=True), net.engine(B)
+    assert fast is not base and fast.pp and fast.pp_convs > 0 and base.pp_convs == 0
+    x = torch.from_numpy(g['x']).cuda()
+    tc = torch.full((B,), 0.5 if tag == 've_cifar' else 500.0, device='cuda')
+    a = fast.forward(x, tc, None, train=False).clone()
+    b = base.forward(x, tc, None, train=False).clone()
+    torch.cuda.synchronize()
+    e = rel_l2(a.cpu().numpy(), b.cpu().numpy())
+    print(f'{tag}: forward-only plan vs default plan rel-L2 {e:.2e} ({fast.pp_convs} padded-pixel convolutions)')
+    assert e < TOL['bf16']      # two BF16 evaluations with different summation orders (observed 6e-3 - 9e-3; each is ~1e-2 from the reference)
+    with pytest.raises(RuntimeError):
+        fast.build_backward(False)
+    with torch.no_grad():
+        assert net.engine(B, infer=True) is fast
+        net(x, tc)
+        assert fast.forward_count == 2          # the no-grad model call went through the forward-only plan
+
+
 @pytest.mark.parametrize("mode", ['tf32', 'bf16'])
 @pytest.mark.parametrize("tag", ['tiny_vp', 'tiny_ve'])
 def test_pc_sampler_trajectory_matches_reference(tag, mode):

@@ -4,13 +4,14 @@
 #   2. ncu --set full capture of the first igemm / GroupNorm launches of one score-network forward
 #   3. pytest -m gpu in ONE process (as the driver runs it)
 #   4. bench.py (N = 1, defaults)
-#     gpurun --timeout 1500 -- 'bash tools/round_gpu_run.sh'
+#     gpurun --timeout 1500 -- 'bash tools/round_gpu_run.sh'        (LEGS=ncu: legs 1-2 only; LEGS=tests: legs 3-4 only)
 set -u
 O=gpurun_out
 mkdir -p $O
 TAG=${TAG:-r2_final}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/${TAG}_gpu.txt 2>&1
 
+if [ "${LEGS:-all}" != "tests" ]; then
 echo "== leg 1: ncu launch list of the bench slice"; date +%T
 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv \
     --log-file $O/${TAG}_ncu_launches_bench_slice.csv \
@@ -19,11 +20,12 @@ echo "rc=$?"
 
 echo "== leg 2: ncu --set full, igemm + GroupNorm kernels of the first forward"; date +%T
 timeout 420 ncu --set full --clock-control none --import-source on -k 'regex:igemm_kernel|igemm_halo_kernel|gn_apply|gn_stats' -c 30 \
-    -o /tmp/${TAG}_ncu_full_forward -f python tools/quick_bench.py > $O/${TAG}_ncu_full_forward.log 2>&1
+    -o /tmp/${TAG}_ncu_full_forward -f python tools/quick_bench.py --infer > $O/${TAG}_ncu_full_forward.log 2>&1
 echo "rc=$?"
 # the .ncu-rep (70+ MB) exceeds what gpurun copies back: keep its raw page as CSV
 ncu -i /tmp/${TAG}_ncu_full_forward.ncu-rep --page raw --csv > $O/${TAG}_ncu_full_forward_raw.csv 2>/dev/null
 ls -la $O/${TAG}_ncu_full_forward_raw.csv
+fi
 
 if [ "${LEGS:-all}" = "ncu" ]; then exit 0; fi
 echo "== leg 3: pytest -m gpu (one process)"; date +%T

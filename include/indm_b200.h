@@ -156,6 +156,12 @@ int indm_gn_apply_pp(const void* xa, int Ca, const void* xb, int Cb, int in_dtyp
                      const float* partial, const float* gamma, const float* beta, float eps, int act_silu, void* out, void* raw,
                      int out_dtype, float drop_p, const uint64_t* drop_ctl, uint32_t drop_stream, void* stream);
 
+/* Fused single-head self-attention forward of AttnBlockpp (models/layerspp.py:94-99): out[n] = softmax(q k^T * scale) v for
+ * qkv = [N, L, 3C] (q | k | v along the channel axis, as the fused q|k|v projection writes it) -> out [N, L, C].  Scores live in
+ * TMEM and probabilities in shared memory: neither reaches HBM.  Covers dtype BF16, L = 256, C = 256 (the 16x16 attention of the
+ * CIFAR-10 / CelebA networks); anything else returns INDM_ERR_UNSUPPORTED and callers use the GEMM + indm_softmax_rows path. */
+int indm_attention_fwd(const void* qkv, void* out, int64_t N, int L, int C, float scale, int dtype, void* stream);
+
 /* Row softmax of fp32 scores s[rows][cols] -> probabilities in out_dtype (models/layerspp.py:96-97). */
 int indm_softmax_rows(const float* s, void* out, int64_t rows, int cols, int out_dtype, void* stream);
 

@@ -86,6 +86,7 @@ _SIGS = {
                               _vp, C.c_int, _f32, _vp, C.c_uint32, _vp],
     "indm_gn_apply_pp": [_vp, C.c_int, _vp, C.c_int, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _f32, C.c_int,
                          _vp, _vp, C.c_int, _f32, _vp, C.c_uint32, _vp],
+    "indm_attention_fwd": [_vp, _vp, _i64, C.c_int, C.c_int, _f32, C.c_int, _vp],
     "indm_cast_scale": [_vp, _vp, _i64, _f32, C.c_int, _vp],
     "indm_colsum": [_vp, C.c_int, _i64, _i64, C.c_int, _i64, _vp, _i64, _vp, _f32, _vp],
     "indm_sgemm_batched_f32": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32, _vp, _i64, _i64, _vp, _i64, _i64, _f32, _vp, _i64, _i64,

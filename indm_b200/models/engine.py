@@ -32,7 +32,10 @@ class ScoreEngine:
         cfg = model.config
         # pp: inference-only plan whose small-feature-map residual blocks keep their convolution operands in the padded-pixel
         # layout (indm_igemm_t.a_pp): the 3x3 convolutions then read every activation once instead of once per tap
-        self.pp = bool(pp) and mode == 'bf16' and not os.environ.get('INDM_NO_PP')
+        self.infer = bool(pp) and mode == 'bf16'
+        self.pp = self.infer and not os.environ.get('INDM_NO_PP')
+        self.fused_attn = self.infer and not os.environ.get('INDM_NO_FUSED_ATTN')   # indm_attention_fwd (keeps no probabilities for a backward)
+        self.fused_attn_blocks = 0
         self.pp_max_w = int(os.environ.get('INDM_PP_MAX_W', '4'))   # measured: faster on 4x4 maps, slower on 8x8 / 16x16 (border rows)
         self.pp_convs = 0         # convolutions of this plan that read padded-pixel operands
         self.model = model
@@ -407,6 +410,12 @@ class ScoreEngine:
             # q | k | v rows in one GEMM (N = 3C); V^T (the K-major B operand of P.V) by a batched transpose of the v columns
             qkv = self._op_t((N, Lq, 3 * C))
             self._igemm(a=h, N=N, H=H, W=W, Cin=C, b=wqkv, Cout=3 * C, taps=1, bias=bqkv, **self._okw(qkv, 3 * C))
+            if self.fused_attn and Lq == 256 and C == 256:
+                # forward-only plan: scores in TMEM, probabilities in shared memory, V read in place — one launch
+                o = self._op_t((N, Lq, C))
+                self._call('indm_attention_fwd', qkv, o, ctypes.c_int64(N), Lq, C, ctypes.c_float(float(int(C) ** (-0.5))), L.DTYPE_BF16)
+                self.fused_attn_blocks += 1
+                return attn_out(ab, gna, x, C, H, W, qkv, None, h, o)
             qk = qkv                                    # q at columns [0, C), k at [C, 2C): row stride 3C
             vt = self._op_t((N, C, Lq))
             op_dt_ = L.DTYPE_BF16 if self.mode == 'bf16' else L.DTYPE_F32
@@ -424,6 +433,9 @@ class ScoreEngine:
             else:
                 kw.update(out_f32=o, round_tf32_out=1)
             self._igemm(**kw)
+            return attn_out(ab, gna, x, C, H, W, qkv, p, h, o)
+
+        def attn_out(ab, gna, x, C, H, W, qkv, p, h, o):
             w3 = self._op_t((C, C))
             b3 = self._alloc((C,))
 
@@ -835,8 +847,8 @@ class ScoreEngine:
     def build_backward(self, train=False):
         """emit the backward plan: input-VJP only (train=False: likelihood / Hutchinson) or input-VJP + every parameter
         gradient (train=True: losses.get_step_fn)"""
-        if self.pp:
-            raise RuntimeError('ScoreEngine(pp=True) is an inference-only plan (padded-pixel operands are not kept for the backward): '
+        if self.infer:
+            raise RuntimeError('ScoreEngine(pp=True) is an inference-only plan (padded-pixel operands / attention probabilities are not kept for the backward): '
                                'use NCSNpp.engine(batch) for vector-Jacobian products')
         if self._plans.get(train) is not None:
             self.bops = self._plans[train]['ops']

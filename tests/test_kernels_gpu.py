@@ -525,6 +525,36 @@ def test_igemm_halo_padded_pixel_path(kind, N, S, Cin, Cin2, Cout):
     assert torch.equal(first, out)
 
 
+@pytest.mark.parametrize("N", [1, 5, 128])
+def test_fused_attention_forward_matches_softmax_attention(N):
+    """indm_attention_fwd (scores in TMEM, probabilities in shared memory, V read in place as an MN-major operand) against
+    softmax(q k^T C^-1/2) v in fp64 on the BF16-rounded q | k | v (models/layerspp.py:94-99), L = 256, C = 256; peaked and flat
+    rows both occur (q, k scaled so the logits span ~[-8, 8])."""
+    Lq, Cc = 256, 256
+    qkv = (rnd(N, Lq, 3 * Cc, seed=90) * torch.tensor([1.5] * Cc + [1.5] * Cc + [1.0] * Cc)).to(torch.bfloat16)
+    out = torch.full((N, Lq, Cc), float('nan'), device=DEV, dtype=torch.bfloat16)
+    dq = qkv.to(DEV)
+    L.call('indm_attention_fwd', L.ptr(dq), L.ptr(out), N, Lq, Cc, Cc ** -0.5, L.DTYPE_BF16)
+    torch.cuda.synchronize()
+    q, k, v = (t.double() for t in qkv.split(Cc, dim=2))
+    want = torch.softmax(q @ k.transpose(1, 2) * Cc ** -0.5, dim=-1) @ v
+    assert torch.isfinite(out.float()).all()
+    e = rel_l2(out.float().cpu(), want)
+    print(f'fused attention N={N}: rel-L2 {e:.2e}')
+    assert e < 4e-3                                   # BF16 probabilities and output
+    first = out.clone()
+    L.call('indm_attention_fwd', L.ptr(dq), L.ptr(out), N, Lq, Cc, Cc ** -0.5, L.DTYPE_BF16)
+    torch.cuda.synchronize()
+    assert torch.equal(first, out)
+
+
+def test_fused_attention_rejects_other_shapes():
+    x = torch.zeros((2, 64, 3 * 128), device=DEV, dtype=torch.bfloat16)
+    o = torch.zeros((2, 64, 128), device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        L.call('indm_attention_fwd', L.ptr(x), L.ptr(o), 2, 64, 128, 128 ** -0.5, L.DTYPE_BF16)
+
+
 def to_pp(x_nhwc):
     """[N,H,W,C] -> the padded-pixel buffer of indm_igemm_t.a_pp: [(N (H + 1) + 1)(W + 2), C], zero borders"""
     N, H, W, C = x_nhwc.shape

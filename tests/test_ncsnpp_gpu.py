@@ -68,6 +68,7 @@ def test_forward_only_plan_uses_padded_pixel_operands_and_agrees_with_the_defaul
     B = g['x'].shape[0]
     fast, base = net.engine(B, infer=True), net.engine(B)
     assert fast is not base and fast.pp and fast.pp_convs > 0 and base.pp_convs == 0
+    assert fast.fused_attn_blocks > 0 and base.fused_attn_blocks == 0       # 16x16 attention in one launch (indm_attention_fwd)
     x = torch.from_numpy(g['x']).cuda()
     tc = torch.full((B,), 0.5 if tag == 've_cifar' else 500.0, device='cuda')
     a = fast.forward(x, tc, None, train=False).clone()

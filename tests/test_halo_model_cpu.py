@@ -55,3 +55,25 @@ def test_pair_halo_box_sizes():
     skip, rows, shift = hm.pair_halo_box(1, 32)
     assert (skip, shift) == (3, 26) and rows == 7              # CTA 1 starts 26 pixels into padded row 3
     assert rows * 34 * 128 <= 32 * 1024
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(7, 4, 4, 16, 4), (128, 4, 4, 8, 2), (5, 8, 8, 16, 4), (3, 16, 16, 8, 2), (2, 5, 7, 8, 2), (1, 4, 4, 8, 2)])
+def test_whole_batch_padded_pixel_schedule_equals_direct_convolution(N, H, W, Cin, Cout):
+    """index math of indm_igemm_t.a_pp (igemm_halo_kernel<..., FLAT>): one box per tile of 128 padded pixels of the whole batch,
+    nine row offsets, the shared zero row between images is the bottom padding of one image and the top padding of the next"""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((N, H, W, Cin))
+    w = rng.standard_normal((3, 3, Cout, Cin))
+    got = hm.conv3x3_whole_batch_padded(x, w)
+    want = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2),
+                                      torch.from_numpy(w).permute(2, 3, 0, 1).contiguous(), padding=1).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10)
+
+
+def test_whole_batch_padded_pixel_sizes():
+    assert hm.to_padded_pixels(np.ones((128, 4, 4, 1))).shape[0] == (128 * 5 + 1) * 6
+    assert hm.pp_box_rows(4) == 142 and hm.pp_box_rows(8) == 150 and hm.pp_box_rows(61) == 256      # the kernel's limit: 256 box rows
+    pp = hm.to_padded_pixels(np.ones((3, 4, 4, 2)))
+    assert pp.sum() == 3 * 16 * 2 and pp[:6].sum() == 0 and pp[5 * 6:5 * 6 + 6].sum() == 0
+    # useful rows per tile: 16 / 30 at 4x4, 64 / 90 at 8x8, 256 / 306 at 16x16 (DESIGN.md: why only the 4x4 blocks use it)
+    assert abs(16 / (5 * 6) - 0.533) < 1e-3

@@ -128,3 +128,54 @@ if __name__ == "__main__":
             new, old = operand_bytes_per_tile(W, cin, half if tile_m == 256 else cout, 128 if tile_m == 128 else 128)
             print(f"{H}x{W} {cin}->{cout} tile_m={tile_m}: row efficiency {mma_row_efficiency(H, W, tile_m):.2f}, "
                   f"operand bytes per CTA tile {new / 1024:.0f} KB vs {old / 1024:.0f} KB per-tap")
+
+
+# ---------------------------------------------------------------- whole-batch padded-pixel layout (indm_igemm_t.a_pp, FLAT kernel)
+def to_padded_pixels(x):
+    """[N,H,W,C] -> [(N (H + 1) + 1)(W + 2), C]: pixel (n, y, x) at row (n (H + 1) + y + 1)(W + 2) + x + 1, every other row zero
+    (what indm_gn_apply_pp writes; consecutive images share one zero row)"""
+    N, H, W, C = x.shape
+    buf = np.zeros((N * (H + 1) + 1, W + 2, C), dtype=x.dtype)
+    buf[:N * (H + 1)].reshape(N, H + 1, W + 2, C)[:, 1:, 1:W + 1] = x
+    return buf.reshape(-1, C)
+
+
+def pp_box_rows(W, tile_m=128):
+    """rows of the one shared-memory box that serves the nine taps of a tile of `tile_m` padded pixels"""
+    return tile_m + 2 * (W + 2) + 2
+
+
+def conv3x3_whole_batch_padded(x, w, tile_m=128):
+    """3x3 'same' convolution of x [N,H,W,Cin] with w [3,3,Cout,Cin] the way igemm_halo_kernel<..., FLAT> schedules it: tile k =
+    padded pixels [k tile_m, (k + 1) tile_m) of the WHOLE BATCH; its box starts at row k tile_m - (W + 2) - 1 (rows outside the
+    buffer are TMA zero fill); tap (ty, tx) reads box rows m + ty (W + 2) + tx; the epilogue maps padded pixel -> (n, y, x) and
+    skips border rows / columns and the tail past the last image."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[2]
+    Wp = W + 2
+    pp = to_padded_pixels(x)
+    T = pp.shape[0]
+    out = np.full((N, H, W, Cout), 1e30)
+    box_rows = pp_box_rows(W, tile_m)
+    written = 0
+    for k in range((T + tile_m - 1) // tile_m):
+        first = k * tile_m - Wp - 1
+        box = np.zeros((box_rows, Cin), dtype=x.dtype)
+        lo, hi = max(first, 0), min(first + box_rows, T)
+        if hi > lo:
+            box[lo - first:hi - first] = pp[lo:hi]
+        acc = np.zeros((tile_m, Cout))
+        for ty in range(3):
+            for tx in range(3):
+                off = ty * Wp + tx
+                assert off + tile_m <= box_rows
+                acc += box[off:off + tile_m] @ w[ty, tx].T
+        for m in range(tile_m):
+            q = k * tile_m + m
+            R, col = divmod(q, Wp)
+            n, yr = divmod(R, H + 1)
+            if yr >= 1 and 1 <= col <= W and n < N:
+                out[n, yr - 1, col - 1] = acc[m]
+                written += 1
+    assert written == N * H * W
+    return out

@@ -199,6 +199,20 @@ class ScoreEngine:
             L.check(fn(*cargs, L._stream()), name)
         self._cur.append(run)
 
+    def _call_unless_dropping(self, name, args, drop_name, drop_args):
+        """`name(*args)` when dropout is off for this forward (eval / sampling: the kernels instantiated without the Philox path
+        keep 79 instead of 120 registers), `drop_name(*drop_args)` when forward(train=True) switched the masks on"""
+        fn, fn_drop = getattr(L.lib(), name), getattr(L.lib(), drop_name)
+        conv = lambda seq: [ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else a for a in seq]
+        cargs, dargs = conv(args), conv(drop_args)
+
+        def run():
+            if self._drop_on:
+                L.check(fn_drop(*dargs, L._stream()), drop_name)
+            else:
+                L.check(fn(*cargs, L._stream()), name)
+        self._cur.append(run)
+
     def _gn(self, xa, Ca, xb, Cb, in_dt, H, W, gparams, act, resample, want_raw, slot=None, stats_done=False, dropout=0.0, pp=False):
         """GroupNorm(+SiLU)(+resample) of concat(xa, xb) -> operand tensor (and optional raw copy of the input).
         Emits the statistics launch unless a producer already accumulated them into `slot`."""
@@ -221,16 +235,21 @@ class ScoreEngine:
             rows = (N * (H + 1) + 1) * (W + 2)
             out = self._alloc((rows, C), self.tdtype, zero=True)
             raw = self._alloc((rows, C), self.tdtype, zero=True) if want_raw else None
-            self._call('indm_gn_apply_pp', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
-                       act, out, raw, odt_, ctypes.c_float(dropout), self.drop_ctl if dropout > 0.0 else None, ctypes.c_uint32(slot))
+            head = (xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6), act, out, raw, odt_)
+            if dropout > 0.0:
+                self._call_unless_dropping('indm_gn_apply_pp', head + (ctypes.c_float(0.0), None, ctypes.c_uint32(slot)),
+                                           'indm_gn_apply_pp', head + (ctypes.c_float(dropout), self.drop_ctl, ctypes.c_uint32(slot)))
+            else:
+                self._call('indm_gn_apply_pp', *head, ctypes.c_float(0.0), None, ctypes.c_uint32(slot))
             self._last_gn = None
             return out, raw
         out = self._op_t((N, Ho, Wo, C))
         raw = self._op_t((N, Ho, Wo, C)) if want_raw else None
         if dropout > 0.0:
             assert resample == 0 and not want_raw
-            self._call('indm_gn_apply_dropout', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
-                       act, out, odt_, ctypes.c_float(dropout), self.drop_ctl, ctypes.c_uint32(slot))
+            head = (xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6), act)
+            self._call_unless_dropping('indm_gn_apply', head + (0, out, None, odt_),
+                                       'indm_gn_apply_dropout', head + (out, odt_, ctypes.c_float(dropout), self.drop_ctl, ctypes.c_uint32(slot)))
         else:
             self._call('indm_gn_apply', xa, Ca, xb, Cb, in_dt, ctypes.c_int64(N), H, W, G, part, gamma, beta, ctypes.c_float(1e-6),
                        act, resample, out, raw, odt_)

@@ -995,7 +995,7 @@ extern "C" int indm_igemm(const indm_igemm_t* d, void* stream_) {
   if (d->gn_partial) {
     INDM_CHECK_ARG((d->gn_cpg == 4 || d->gn_cpg == 8 || d->gn_cpg == 16 || d->gn_cpg == 32) && d->Cout % 32 == 0,
                    "igemm: fused GroupNorm statistics need cpg | 32 and Cout %% 32 == 0 (cpg=%d Cout=%d)", d->gn_cpg, d->Cout);
-    INDM_CHECK_ARG(p.BN == 1 || p.BW * p.BH >= 32, "igemm: fused GroupNorm statistics need >= 32 pixels per image per tile");
+    INDM_CHECK_ARG(d->a_pp || p.BN == 1 || p.BW * p.BH >= 32, "igemm: fused GroupNorm statistics need >= 32 pixels per image per tile");
   }
 
   // ---- tensor maps

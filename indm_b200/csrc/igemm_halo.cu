@@ -282,7 +282,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float4 rb = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)(n < p.N ? n : 0) * p.rowbias_ld + c));
           bia.x += rb.x; bia.y += rb.y; bia.z += rb.z; bia.w += rb.w;
         }
-        float gs = 0.f, gq = 0.f, gsB = 0.f, gqB = 0.f;     // FLAT: (gs, gq) = rows of image nA, (gsB, gqB) = rows of image nA + 1
+        float gs = 0.f, gq = 0.f, gsB = 0.f, gqB = 0.f, gsC = 0.f, gqC = 0.f;     // FLAT: rows of image nA / nA + 1 / nA + 2
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + rsub;
@@ -307,9 +307,12 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (!FLAT || nrow[it] == nA) {
               gs += s_;
               gq += q_;
-            } else {
+            } else if (nrow[it] == nA + 1) {
               gsB += s_;
               gqB += q_;
+            } else {
+              gsC += s_;
+              gqC += q_;
             }
           }
         }
@@ -347,6 +350,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           };
           flush(gs, gq, FLAT ? nA : n);
           if (FLAT) flush(gsB, gqB, nA + 1);      // zero when the warp's rows all belong to one image (adds nothing)
+          if (FLAT && (p.H + 1) * p.Wp < 32) flush(gsC, gqC, nA + 2);      // 4x4 maps: 30 padded pixels per image, 32 rows can touch three
         }
         __syncwarp();   // the staging buffer is rewritten by the next slab
       }
@@ -517,7 +521,7 @@ int indm_igemm_halo_flat(const indm_igemm_t* d, int kind, void* stream_) {
   if (p.gn_partial) {
     INDM_CHECK_ARG(p.gn_cpg >= 4 && 32 % p.gn_cpg == 0 && (!p.gn2_partial || (p.gn2_cpg >= 4 && 32 % p.gn2_cpg == 0)),
                    "igemm (a_pp): fused GroupNorm statistics need cpg | 32");
-    INDM_CHECK_ARG((d->H + 1) * p.Wp >= 32, "igemm (a_pp): fused GroupNorm statistics need >= 32 padded pixels per image (a warp's rows may span two images, not three)");
+    INDM_CHECK_ARG((d->H + 1) * p.Wp >= 16, "igemm (a_pp): fused GroupNorm statistics need >= 16 padded pixels per image (a warp's 32 rows may span three images, not more)");
   }
   INDM_CHECK_ARG((((uintptr_t)d->out_bf16 | (uintptr_t)d->out_f32 | (uintptr_t)d->residual | (uintptr_t)d->rowbias | (uintptr_t)d->bias) & 15) == 0 &&
                  p.out_ld % 4 == 0 && p.res_ld % 4 == 0 && p.rowbias_ld % 4 == 0, "igemm (a_pp): 16-byte aligned epilogue operands");

@@ -168,7 +168,8 @@ class ScoreEngine:
         # (patched into this descriptor later by _gn): needs whole 32-column slabs and one image per epilogue warp
         out = kw.get('out_f32')
         if (self._cur is self.ops and isinstance(out, torch.Tensor) and kw.get('out_mode', 0) == 0 and not kw.get('batched_b')
-                and kw.get('out_bf16') is None and kw['Cout'] % 32 == 0 and kw['H'] * kw['W'] >= 32 and self.mode == 'bf16'):
+                and kw.get('out_bf16') is None and kw['Cout'] % 32 == 0 and self.mode == 'bf16'
+                and (kw['H'] * kw['W'] >= 32 or (kw.get('a_pp') and (kw['H'] + 1) * (kw['W'] + 2) >= 16))):
             self._producers[out.data_ptr()] = d
         return d
 
@@ -370,7 +371,8 @@ class ScoreEngine:
             G1 = rb.GroupNorm_1.num_groups
             cpg1 = Cout // G1
             px = Ho * Wo
-            fuse_stats = (32 % cpg1 == 0) and (Cout % 32 == 0) and (px >= 32) and self.mode == 'bf16'
+            fuse_stats = ((32 % cpg1 == 0) and (Cout % 32 == 0) and self.mode == 'bf16'
+                          and (px >= 32 or (use_pp and (Ho + 1) * (Wo + 2) >= 16)))      # the padded-pixel kernel also covers 4x4 maps
             slot1 = self._gn_slot()
             kw = dict(a=h1, N=N, H=Ho, W=Wo, Cin=Cin, b=w0, Cout=Cout, taps=9, bias=b0,
                       rowbias=self.dense_tab[:, dense_off[id(rb)]:], rowbias_ld=self.dense_total, out_ld=Cout)

@@ -585,7 +585,7 @@ def test_igemm_whole_batch_padded_pixel_operands(kind, N, S, Cin, Cin2, Cout):
         kw.update(a2=to_pp(nhwc(xs)).to(torch.bfloat16).to(DEV), Cin2=Cin2, b2=dev_op(w2.reshape(Cout, Cin2), dtype))
         want = want + F.conv2d(xs.double(), w2.double())
     want = nhwc(want)
-    stats = (S + 1) * (S + 2) >= 32
+    stats = (S + 1) * (S + 2) >= 16           # 4x4 maps: a warp's 32 rows touch up to three images
     part = torch.zeros((N, 32, 2), device=DEV)
     part2 = torch.zeros((N, 16, 2), device=DEV)
     gn = dict(gn_partial=part, gn_cpg=Cout // 32, gn_groups=32, gn2_partial=part2, gn2_cpg=Cout // 16, gn2_groups=16) if stats else {}
@@ -623,8 +623,9 @@ def test_igemm_padded_pixel_rejects_what_it_cannot_run():
     w = torch.zeros((9, 128, 64), device=DEV, dtype=torch.bfloat16)
     out = torch.zeros((2, 4, 4, 128), device=DEV)
     part = torch.zeros((2, 32, 2), device=DEV)
-    with pytest.raises(RuntimeError):       # 4x4 maps: a warp's 32 rows can span three images, no fused statistics
-        L.igemm(dtype=L.DTYPE_BF16, a=x, a_pp=1, N=2, H=4, W=4, Cin=64, b=w, Cout=128, taps=9, out_f32=out, out_ld=128,
+    x2 = torch.zeros(((2 * 3 + 1) * 4, 64), device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):       # 2x2 maps: a warp's 32 rows can span four images, no fused statistics
+        L.igemm(dtype=L.DTYPE_BF16, a=x2, a_pp=1, N=2, H=2, W=2, Cin=64, b=w, Cout=128, taps=9, out_f32=out, out_ld=128,
                 gn_partial=part, gn_cpg=4, gn_groups=32)
     with pytest.raises(RuntimeError):       # 1x1 products have no padded-pixel form
         L.igemm(dtype=L.DTYPE_BF16, a=x, a_pp=1, N=2, H=4, W=4, Cin=64, b=w, Cout=128, taps=1, out_f32=out, out_ld=128)

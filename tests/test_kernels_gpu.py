@@ -555,6 +555,43 @@ def test_fused_attention_rejects_other_shapes():
         L.call('indm_attention_fwd', L.ptr(x), L.ptr(o), 2, 64, 128, 128 ** -0.5, L.DTYPE_BF16)
 
 
+@pytest.mark.parametrize("N,S,C,Cb", [(3, 8, 128, 0), (2, 16, 256, 0), (5, 4, 128, 128)])
+def test_gn_apply_dropout_mask_is_the_same_in_every_kernel_variant(N, S, C, Cb):
+    """nn.Dropout inside ResnetBlockBigGANpp (models/layerspp.py:278): the mask is a pure function of (seed, stream, element quad), so
+    the 8-channel BF16 kernel, the TF32-output kernel (whose indexing the backward kernels share) and the padded-pixel variant must
+    drop exactly the same elements and scale the kept ones by 1 / (1 - p); enabled = 0 in the control buffer switches it off."""
+    p_drop, seed, stream_id = 0.1, 0x1234, 7
+    xa = rnd(N, S, S, C, seed=95).to(DEV)
+    xb = rnd(N, S, S, Cb, seed=96).to(DEV) if Cb else None
+    Ct = C + Cb
+    gamma, beta = (1 + 0.1 * rnd(Ct, seed=97)).to(DEV), (0.5 + rnd(Ct, seed=98)).to(DEV)
+    part = torch.zeros((N, 32, 2), device=DEV)
+    L.call('indm_gn_stats', L.ptr(xa), C, L.ptr(xb) if Cb else None, Cb, L.DTYPE_F32, N, S * S, 32, L.ptr(part))
+    ctl = torch.tensor([seed, 1], dtype=torch.int64, device=DEV)
+    head = (L.ptr(xa), C, L.ptr(xb) if Cb else None, Cb, L.DTYPE_F32, N, S, S, 32, L.ptr(part), L.ptr(gamma), L.ptr(beta), 1e-6, 1)
+    ob = torch.empty((N, S, S, Ct), device=DEV, dtype=torch.bfloat16)
+    of = torch.empty((N, S, S, Ct), device=DEV)
+    plain = torch.empty((N, S, S, Ct), device=DEV)
+    L.call('indm_gn_apply_dropout', *head, L.ptr(ob), L.DTYPE_BF16, p_drop, L.ptr(ctl), stream_id)
+    L.call('indm_gn_apply_dropout', *head, L.ptr(of), L.DTYPE_TF32, p_drop, L.ptr(ctl), stream_id)
+    L.call('indm_gn_apply', *head, 0, L.ptr(plain), None, L.DTYPE_TF32)
+    pp = torch.zeros(((N * (S + 1) + 1) * (S + 2), Ct), device=DEV, dtype=torch.bfloat16)
+    L.call('indm_gn_apply_pp', *head, L.ptr(pp), None, L.DTYPE_BF16, p_drop, L.ptr(ctl), stream_id)
+    torch.cuda.synchronize()
+    zb, zf = (ob == 0).cpu(), (of == 0).cpu()
+    assert torch.equal(zb, zf)                                           # same elements dropped
+    frac = float(zf.float().mean())
+    assert abs(frac - p_drop) < 0.02, frac
+    kept = ~zf
+    assert rel_l2(of.cpu()[kept], plain.cpu()[kept] / (1 - p_drop)) < 1e-6     # kept elements scaled by 1 / (1 - p)
+    assert rel_l2(ob.float().cpu(), of.cpu()) < 4e-3
+    assert torch.equal(pp.cpu(), to_pp(ob.cpu()))
+    ctl.zero_()                                                          # enabled = 0: the same launch is a plain GroupNorm apply
+    L.call('indm_gn_apply_dropout', *head, L.ptr(ob), L.DTYPE_BF16, p_drop, L.ptr(ctl), stream_id)
+    torch.cuda.synchronize()
+    assert rel_l2(ob.float().cpu(), plain.cpu()) < 4e-3 and float((ob == 0).float().mean()) < 1e-3
+
+
 def to_pp(x_nhwc):
     """[N,H,W,C] -> the padded-pixel buffer of indm_igemm_t.a_pp: [(N (H + 1) + 1)(W + 2), C], zero borders"""
     N, H, W, C = x_nhwc.shape

@@ -111,6 +111,34 @@ def test_dropout_switches_with_the_train_flag_on_one_engine(mode):
     assert d_te > 0.05 and d_ss > 0.05
 
 
+def test_backward_recomputes_the_dropout_mask_of_its_forward():
+    """With dropout on, the input-VJP of the explicit backward plan must differentiate the network WITH the masks of the forward it
+    follows (the backward kernels recompute them from the Philox key): central finite difference of <w, net(x)> along a random
+    direction at a fixed seed, compensated-TF32 arithmetic."""
+    cfg = _cfg('tiny_vp')
+    model = _model(cfg)
+    model.module.compute_mode = 'tf32'
+    eng = model.module.engine(2)
+    gen = torch.Generator('cuda').manual_seed(9)
+    x = torch.randn(2, 3, 16, 16, device='cuda', generator=gen)
+    d = torch.randn(2, 3, 16, 16, device='cuda', generator=gen)
+    w = torch.randn(2, 3, 16, 16, device='cuda', generator=gen)
+    t = torch.full((2,), 300.0, device='cuda')
+    f = lambda xx: float((eng.forward(xx, t, None, train=True, seed=11).double() * w.double()).sum())
+    h = 1e-2
+    fd = (f(x + h * d) - f(x - h * d)) / (2 * h)
+    eng.forward(x, t, None, train=True, seed=11)
+    g = eng.vjp(w, train=False)
+    an = float((g.double() * d.double()).sum())
+    eng.forward(x, t, None, train=False)
+    g0 = eng.vjp(w, train=False)
+    an_eval = float((g0.double() * d.double()).sum())
+    torch.cuda.synchronize()
+    print(f'dropout VJP: finite difference {fd:.5f}, analytic {an:.5f} (eval-mode derivative {an_eval:.5f})')
+    assert abs(fd - an) < 2e-2 * max(abs(fd), 1e-3)
+    assert abs(an - an_eval) > 10 * abs(fd - an)          # the masked and unmasked derivatives are far apart: the check can tell them apart
+
+
 @pytest.mark.parametrize("mode", ['tf32', 'bf16'])
 @pytest.mark.parametrize("tag", ['tiny_vp', 'tiny_ve'])
 def test_pc_sampler_trajectory_matches_reference(tag, mode):

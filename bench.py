@@ -184,7 +184,6 @@ def _reference_sampler(threads):
     import torch
     torch.set_num_threads(threads)
     from oracle import ncsnpp as oncsnpp, flow as oflow
-    from indm_b200 import configs as pconfigs
     if os.path.isdir(os.path.join(REF_VENDORED, "models")):
         os.environ["INDM_REFERENCE_ROOT"] = REF_VENDORED
         from oracle import ref_loader as rl

@@ -9,7 +9,6 @@ work or host<->device traffic in the loop.  Noise can alternatively be supplied 
 trajectories against a recorded reference run (SURVEY.md §7 hard part 3).
 """
 import abc
-import functools
 import io
 import os
 

@@ -20,10 +20,13 @@ def main():
     ap.add_argument('--config', default='vp/CIFAR10/indm_fid')
     ap.add_argument('--mode', default='bf16')
     ap.add_argument('--per-op', action='store_true')
+    ap.add_argument('--nres', type=int, default=0, help='override model.num_res_blocks (CelebA bench legs use 8)')
     ap.add_argument('--infer', action='store_true', help='the forward-only plan of the samplers (padded-pixel operands on small maps)')
     a = ap.parse_args()
     cfg = configs.get_config(a.config)
     cfg.device = torch.device('cuda:0')
+    if a.nres:
+        cfg.model.num_res_blocks = a.nres
     torch.manual_seed(0)
     model = mutils.create_model(cfg)
     net = model.module

@@ -38,8 +38,44 @@ def test_gn_apply_bytes_from_launch_closure():
     assert bench._gn_apply_bytes(op) == N * H * W * C * 2 * 2
     op = _engine_style_call('indm_gn_apply_dropout', *bf, vp, L.DTYPE_BF16, ctypes.c_float(0.1), vp, ctypes.c_uint32(3))
     assert bench._gn_apply_bytes(op) == N * H * W * C * 2 * 2
+    # padded-pixel variant of the forward-only plan: the zero borders are never written, so the bytes are the dense ones
+    op = _engine_style_call('indm_gn_apply_pp', *common, vp, vp, L.DTYPE_BF16, ctypes.c_float(0.0), None, ctypes.c_uint32(3))
+    assert bench._gn_apply_bytes(op) == N * H * W * C * 4 + 2 * N * H * W * C * 2
+    op = _engine_style_call('indm_gn_apply_pp', *common, vp, None, L.DTYPE_BF16, ctypes.c_float(0.0), None, ctypes.c_uint32(3))
+    assert bench._gn_apply_bytes(op) == N * H * W * C * 4 + N * H * W * C * 2
     assert bench._gn_apply_bytes(_engine_style_call('indm_gn_stats', vp)) is None
     assert bench._gn_apply_bytes(lambda: None) is None
+
+
+def test_gn_apply_bytes_sees_the_dropout_switch_closure():
+    """ScoreEngine._call_unless_dropping: one closure holding both the plain and the dropout launch; the accounting reads the
+    plain one (`name` / `cargs`), which is what runs whenever the masks are off (sampling, bench)"""
+    import torch  # noqa: F401  (engine import below needs it)
+    from indm_b200 import _lib as L
+    from indm_b200.models import engine as E
+
+    class _FakeLib:
+        def __getattr__(self, k):
+            return lambda *a: 0
+
+    class _Eng:
+        _drop_on = False
+        _cur = []
+        _call_unless_dropping = E.ScoreEngine._call_unless_dropping
+
+    real = L.lib
+    L.lib = lambda: _FakeLib()
+    try:
+        N, H, W, C = 128, 16, 16, 256
+        vp = ctypes.c_void_p(0x1000)
+        head = (vp, C, None, 0, L.DTYPE_BF16, ctypes.c_int64(N), H, W, 32, vp, vp, vp, ctypes.c_float(1e-6), 1)
+        e = _Eng()
+        e._call_unless_dropping('indm_gn_apply', head + (0, vp, None, L.DTYPE_BF16),
+                                'indm_gn_apply_dropout', head + (vp, L.DTYPE_BF16, ctypes.c_float(0.1), vp, ctypes.c_uint32(3)))
+        op = e._cur[-1]
+        assert bench._gn_apply_bytes(op) == N * H * W * C * 2 * 2
+    finally:
+        L.lib = real
 
 
 def test_workload_config_slice_keeps_the_sde():
